@@ -1,0 +1,196 @@
+// ff63.cuh -- arithmetic in Z_p for 63-bit primes, host + device (sm_100a).
+//
+// Replaces the reference's FFInt operators (reference: source/FFInt.cpp:130-192
+// add/sub/mul/div/pow/neg, :356-405 mod_mul/mod_pow/mod_inv; FFInt.hpp:149-174
+// integer-exponent pow).  Results are the canonical residues the reference
+// produces; HOW they are computed is different:
+//
+//  * FireFly's primes (reference: source/ReconstHelper.cpp:24-125) are all of the
+//    form p = 2^63 - c with 25 <= c <= 13797.  2^63 = c (mod p), so a 128-bit
+//    product folds with two 32x32->64 multiplies by a 16-bit constant instead of
+//    a long-double quotient estimate (reference DEFAULT) or a Barrett preinverse
+//    (reference FLINT).  This is the "pm" (pseudo-Mersenne) path, c < 2^15.
+//  * Any other odd modulus 2^62 < p < 2^63 uses the Barrett path ("generic").
+//  * Inside multiplication chains values are kept LAZY: any representative in
+//    [0, 2^64) of the residue class.  mul/sqr accept and return lazy values;
+//    canon() brings one back to [0, p).  add/sub/neg are canonical-in /
+//    canonical-out exactly like FFInt.
+//
+// The B200 integer path: IMAD.WIDE.U32 (32x32+64 -> 64) on the fma pipe, IADD3 /
+// LOP3 / SHF on the alu pipe.  One lazy multiplication is 7 multiply
+// instructions (4 product + 2 fold + 1 fold) and ~10 adds.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define FF63_HD __host__ __device__ __forceinline__
+#define FF63_D __device__ __forceinline__
+#else
+#define FF63_HD inline
+#endif
+
+namespace ff63 {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+// ----- small helpers ---------------------------------------------------------
+FF63_HD u32 lo32(u64 x) { return (u32)x; }
+FF63_HD u32 hi32(u64 x) { return (u32)(x >> 32); }
+
+FF63_HD u64 umulhi(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+  return __umul64hi(a, b);
+#else
+  return (u64)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
+// ----- canonical add / sub / neg (reference: FFInt.cpp:131-139, 190-192) ------
+// a, b in [0,p).  p < 2^63 so a+b never wraps.
+FF63_HD u64 add(u64 a, u64 b, u64 p) {
+  u64 s = a + b;
+  return s >= p ? s - p : s;
+}
+FF63_HD u64 sub(u64 a, u64 b, u64 p) {
+  u64 s = a - b;
+  return a < b ? s + p : s;
+}
+// -0 == 0: FFInt::operator-() builds FFInt(p - n) whose ctor reduces p to 0.
+FF63_HD u64 neg(u64 a, u64 p) { return a ? p - a : 0; }
+
+// ----- pseudo-Mersenne path: p = 2^63 - c, c < 2^15, d = 2c ---------------------
+// lazy value: any u64 congruent to the residue.  2^64 = d (mod p).
+
+// lazy -> canonical.  v = b*2^63 + l  ->  l + b*c < 2^63 + c < 2p.
+FF63_HD u64 canon_pm(u64 v, u32 c, u64 p) {
+  u64 l = (v & 0x7fffffffffffffffULL) + ((v >> 63) ? (u64)c : 0ULL);
+  return l >= p ? l - p : l;
+}
+
+// fold a 128-bit value (hi:lo) to a lazy 64-bit one.
+//   R  = lo + d*hi            < 2^64 + 2^80      (one 64x16 multiply = 2 IMAD.WIDE)
+//   r  = R_lo + d*R_hi        R_hi <= d, d*R_hi <= d^2 < 2^32   (1 IMAD)
+//   a carry out of that last add is worth another d; it cannot carry twice
+//   because after a wrap r < d^2.
+FF63_HD u64 fold_pm(u64 hi, u64 lo, u32 d) {
+  u64 u = (u64)lo32(hi) * d;            // < 2^48
+  u64 v = (u64)hi32(hi) * d;            // < 2^48
+  u64 a = lo + u;
+  u32 cy = a < u;
+  u64 vs = v << 32;
+  u64 b = a + vs;
+  cy += b < vs;
+  u32 rh = hi32(v) + cy;                // <= d
+  u64 t = (u64)(rh * d);                // 32-bit product, fits
+  u64 r = b + t;
+  if (r < t) r += d;
+  return r;
+}
+
+// lazy x lazy -> lazy
+FF63_HD u64 mul_pm(u64 x, u64 y, u32 d) {
+  return fold_pm(umulhi(x, y), x * y, d);
+}
+FF63_HD u64 sqr_pm(u64 x, u32 d) {
+  return fold_pm(umulhi(x, x), x * x, d);
+}
+
+// canonical x canonical -> canonical (straightforward; used off the hot loop)
+FF63_HD u64 mul_canon_pm(u64 a, u64 b, u32 c, u64 p) {
+  return canon_pm(mul_pm(a, b, 2 * c), c, p);
+}
+
+// ----- generic path: any modulus 2 <= p < 2^63 ----------------------------------
+// Barrett reduction with a normalised divisor.  Off the benchmarked path
+// (FireFly's own prime table never needs it) but required so that a user prime
+// set through FFInt::set_new_prime (reference: FFInt.cpp:350-352) still works.
+//   k    = number of leading zero bits of p minus one, pn = p << k in [2^62, 2^63)
+//   pinv = floor((2^126 - 1) / pn)  in [2^63, 2^64)
+//   x = a*b < p^2;  xn = x << k < pn * p < 2^126;  q = hi64((xn >> 62) * pinv)
+//   Q - 3 <= q <= Q = floor(xn / pn), so xn - q*pn in [0, 4 pn): at most three
+//   corrections; the remainder is (xn mod pn) >> k.
+struct Barrett {
+  u64 p;      // modulus
+  u64 pn;     // p << k
+  u64 pinv;   // floor((2^126 - 1) / pn)
+  u32 k;
+};
+
+inline Barrett make_barrett(u64 p) {
+  Barrett f;
+  f.p = p;
+  u32 k = 0;
+  while (((p << k) >> 62) == 0) ++k;
+  f.k = k;
+  f.pn = p << k;
+  unsigned __int128 num = (((unsigned __int128)1) << 126) - 1;
+  f.pinv = (u64)(num / f.pn);
+  return f;
+}
+
+FF63_HD u64 mul_barrett(u64 a, u64 b, const Barrett& f) {
+  u64 lo = a * b, hi = umulhi(a, b);
+  if (f.k) { hi = (hi << f.k) | (lo >> (64 - f.k)); lo <<= f.k; }
+  u64 xs = (hi << 2) | (lo >> 62);
+  u64 q = umulhi(xs, f.pinv);
+  u64 ql = q * f.pn, qh = umulhi(q, f.pn);
+  u64 r = lo - ql;
+  u64 rh = hi - qh - (lo < ql);
+  for (int i = 0; i < 3; i++) {
+    if (rh || r >= f.pn) { rh -= (r < f.pn); r -= f.pn; }
+  }
+  return r >> f.k;
+}
+
+#if defined(__CUDACC__)
+// ----- device-only tuned variants -------------------------------------------------
+// Same values as mul_pm / sqr_pm; written in PTX so that NVVM cannot "improve"
+// the limb arithmetic (it inserts known-bit masks on squares) and so that the
+// multiply/add mix that reaches ptxas is the one counted in DESIGN.md.
+FF63_D u64 mul_pm_dev(u64 x, u64 y, u32 d) {
+  u64 r;
+  asm("{\n\t"
+      ".reg .u32 x0,x1,y0,y1,w0,w1,w2,w3,u0,u1,v0,v1,r0,r1,r2,t;\n\t"
+      ".reg .u64 t0,ma,mb,t3,u,v;\n\t"
+      ".reg .pred p;\n\t"
+      "mov.b64 {x0,x1}, %1;\n\t"
+      "mov.b64 {y0,y1}, %2;\n\t"
+      "mul.wide.u32 t0, x0, y0;\n\t"
+      "mul.wide.u32 ma, x0, y1;\n\t"
+      "mul.wide.u32 mb, x1, y0;\n\t"
+      "mul.wide.u32 t3, x1, y1;\n\t"
+      "mov.b64 {w0,w1}, t0;\n\t"
+      "mov.b64 {w2,w3}, t3;\n\t"
+      "mov.b64 {u0,u1}, ma;\n\t"
+      "mov.b64 {v0,v1}, mb;\n\t"
+      "add.cc.u32 w1, w1, u0;\n\t"
+      "addc.cc.u32 w2, w2, u1;\n\t"
+      "addc.u32 w3, w3, 0;\n\t"
+      "add.cc.u32 w1, w1, v0;\n\t"
+      "addc.cc.u32 w2, w2, v1;\n\t"
+      "addc.u32 w3, w3, 0;\n\t"
+      // fold 1: (w1:w0) + d*w2 + (d*w3 << 32)
+      "mul.wide.u32 u, w2, %3;\n\t"
+      "mul.wide.u32 v, w3, %3;\n\t"
+      "mov.b64 {u0,u1}, u;\n\t"
+      "mov.b64 {v0,v1}, v;\n\t"
+      "add.cc.u32 r0, w0, u0;\n\t"
+      "addc.cc.u32 r1, w1, u1;\n\t"
+      "addc.u32 r2, v1, 0;\n\t"
+      "add.cc.u32 r1, r1, v0;\n\t"
+      "addc.u32 r2, r2, 0;\n\t"
+      // fold 2: + d*r2 (< 2^32), one conditional +d on wrap
+      "mul.lo.u32 t, r2, %3;\n\t"
+      "add.cc.u32 r0, r0, t;\n\t"
+      "addc.cc.u32 r1, r1, 0;\n\t"
+      "addc.u32 t, 0, 0;\n\t"
+      "setp.ne.u32 p, t, 0;\n\t"
+      "@p add.u32 r0, r0, %3;\n\t"
+      "mov.b64 %0, {r0,r1};\n\t"
+      "}" : "=l"(r) : "l"(x), "l"(y), "r"(d));
+  return r;
+}
+#endif  // __CUDACC__
+
+}  // namespace ff63
