@@ -1,0 +1,280 @@
+"""firefly_b200 -- thin ctypes binding of libffgpu.so (include/ffgpu.h).
+
+The product is the shared library: a tape compiler for FireFly's expression
+collections and the sm_100a kernels that evaluate them at batches of probe points
+mod a 63-bit prime.  This module only loads it and wraps the C ABI for tests and
+bench.py; the C++ drop-in for FireFly's ``BlackBoxBase`` is
+``include/firefly_gpu/GpuBlackBox.hpp``.
+
+Mirrors, by name and meaning, the part of the reference API that sits on the hot path
+(reference: source/include/firefly/ShuntingYardParser.hpp:44-135):
+
+    ShuntingYardParser(file | functions, vars, check_is_equal)  -> GpuParser(...)
+    parser.precompute_tokens() after FFInt::set_new_prime(p)    -> parser.set_prime(p)
+    parser.evaluate_pre(values)                                 -> parser.evaluate_pre(values)
+    parser.get_rp_function(i)                                   -> parser.get_rp_function(i)
+
+There is no CPU fallback: importing works anywhere the library was built, evaluating
+needs a B200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libffgpu.so")
+
+INSTR_DTYPE = np.dtype(
+    [("op", "u1"), ("src", "u1"), ("flags", "u1"), ("rsv", "u1"), ("arg", "<u4"), ("imm", "<u8")]
+)
+# tape.hpp
+OPS = ["HALT", "LOAD", "ADD", "SUB", "MUL", "SQR", "NEG", "INV", "POWU", "NPOWU", "POWL", "NPOWL", "STORE", "MULADD"]
+SRCS = ["NONE", "POP", "VAR", "NEGVAR", "CONST"]
+F_PUSH, F_SWAP, F_NEGR = 1, 2, 4
+CHECK_IS_EQUAL = 1
+
+
+class FFGpuError(RuntimeError):
+    pass
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise FFGpuError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)"
+        )
+    lib = C.CDLL(LIB_PATH)
+    u64p = C.POINTER(C.c_uint64)
+    strs = C.POINTER(C.c_char_p)
+    sig = {
+        "ffgpu_create": (C.c_void_p, [C.POINTER(C.c_int), C.c_int]),
+        "ffgpu_destroy": (None, [C.c_void_p]),
+        "ffgpu_n_devices": (C.c_int, [C.c_void_p]),
+        "ffgpu_last_error": (C.c_char_p, []),
+        "ffgpu_compile": (C.c_void_p, [C.c_void_p, strs, C.c_size_t, strs, C.c_size_t, C.c_uint]),
+        "ffgpu_compile_text": (C.c_void_p, [C.c_void_p, C.c_char_p, strs, C.c_size_t, C.c_uint]),
+        "ffgpu_compile_file": (C.c_void_p, [C.c_void_p, C.c_char_p, strs, C.c_size_t, C.c_uint]),
+        "ffgpu_tape_destroy": (None, [C.c_void_p]),
+        "ffgpu_n_vars": (C.c_size_t, [C.c_void_p]),
+        "ffgpu_n_functions": (C.c_size_t, [C.c_void_p]),
+        "ffgpu_n_out": (C.c_size_t, [C.c_void_p]),
+        "ffgpu_n_instr": (C.c_size_t, [C.c_void_p]),
+        "ffgpu_stack_depth": (C.c_size_t, [C.c_void_p]),
+        "ffgpu_rpn": (C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
+        "ffgpu_get_tape": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t]),
+        "ffgpu_work": (None, [C.c_void_p, u64p]),
+        "ffgpu_set_prime": (C.c_int, [C.c_void_p, C.c_uint64]),
+        "ffgpu_get_prime": (C.c_uint64, [C.c_void_p]),
+        "ffgpu_n_primes": (C.c_uint32, []),
+        "ffgpu_prime": (C.c_uint64, [C.c_uint32]),
+        "ffgpu_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32]),
+        "ffgpu_eval_device": (
+            C.c_int,
+            [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p],
+        ),
+        "ffgpu_host_alloc": (C.c_void_p, [C.c_size_t]),
+        "ffgpu_host_free": (None, [C.c_void_p]),
+        "ffgpu_set_launch": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+        "ffgpu_set_chunk": (C.c_int, [C.c_void_p, C.c_size_t]),
+        "ffgpu_launch_count": (C.c_uint64, []),
+        "ffgpu_fill_points": (
+            C.c_int,
+            [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64,
+             C.c_uint64, C.c_void_p],
+        ),
+        "ffgpu_checksum": (
+            C.c_int,
+            [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint64, C.c_void_p, C.c_void_p],
+        ),
+        "ffgpu_field_ops": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)      # AttributeError here = the library does not match include/ffgpu.h
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+EXPORTS = [
+    "ffgpu_create", "ffgpu_destroy", "ffgpu_n_devices", "ffgpu_last_error", "ffgpu_compile", "ffgpu_compile_text",
+    "ffgpu_compile_file", "ffgpu_tape_destroy", "ffgpu_n_vars", "ffgpu_n_functions", "ffgpu_n_out", "ffgpu_n_instr",
+    "ffgpu_stack_depth", "ffgpu_rpn", "ffgpu_get_tape", "ffgpu_work", "ffgpu_set_prime", "ffgpu_get_prime",
+    "ffgpu_n_primes", "ffgpu_prime", "ffgpu_eval", "ffgpu_eval_device", "ffgpu_host_alloc", "ffgpu_host_free",
+    "ffgpu_set_launch", "ffgpu_set_chunk", "ffgpu_launch_count", "ffgpu_fill_points", "ffgpu_checksum",
+    "ffgpu_field_ops",
+]
+
+
+def last_error() -> str:
+    return (lib.ffgpu_last_error() or b"").decode()
+
+
+def primes(n: int = 300) -> list[int]:
+    """The n largest primes below 2^63, descending (reference: primes(), source/ReconstHelper.cpp:24-125)."""
+    return [lib.ffgpu_prime(i) for i in range(min(n, lib.ffgpu_n_primes()))]
+
+
+def _strs(xs: Sequence[str]):
+    arr = (C.c_char_p * max(len(xs), 1))()
+    for i, x in enumerate(xs):
+        arr[i] = x.encode()
+    return arr
+
+
+class Context:
+    """A set of GPUs (default: the current CUDA device)."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None):
+        if devices:
+            ids = (C.c_int * len(devices))(*devices)
+            self.h = lib.ffgpu_create(ids, len(devices))
+        else:
+            self.h = lib.ffgpu_create(None, 0)
+        if not self.h:
+            raise FFGpuError(last_error())
+
+    @property
+    def n_devices(self) -> int:
+        return lib.ffgpu_n_devices(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.ffgpu_destroy(self.h)
+            self.h = None
+
+    def field_ops(self, op: int, a, b, p: int) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        b = np.ascontiguousarray(b, dtype=np.uint64)
+        r = np.empty_like(a)
+        if lib.ffgpu_field_ops(self.h, op, a.ctypes.data, b.ctypes.data, r.ctypes.data, a.size, p):
+            raise FFGpuError(last_error())
+        return r
+
+
+class GpuParser:
+    """A compiled collection (ShuntingYardParser's role on the hot path).
+
+    ``ctx=None`` gives a host-only handle: RPN, tape and work counts can be inspected,
+    evaluation raises.
+    """
+
+    def __init__(self, ctx: Optional[Context], functions=None, vars: Sequence[str] = (), check_is_equal: bool = False,
+                 *, file: Optional[str] = None, text: Optional[str] = None):
+        self.ctx = ctx
+        ch = ctx.h if ctx is not None else None
+        flags = CHECK_IS_EQUAL if check_is_equal else 0
+        v = _strs(vars)
+        if file is not None:
+            self.h = lib.ffgpu_compile_file(ch, file.encode(), v, len(vars), flags)
+        elif text is not None:
+            self.h = lib.ffgpu_compile_text(ch, text.encode(), v, len(vars), flags)
+        else:
+            f = _strs(functions)
+            self.h = lib.ffgpu_compile(ch, f, len(functions), v, len(vars), flags)
+        if not self.h:
+            raise FFGpuError(last_error())
+        self.n_vars = lib.ffgpu_n_vars(self.h)
+        self.n_out = lib.ffgpu_n_out(self.h)
+        self.n_functions = lib.ffgpu_n_functions(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.ffgpu_tape_destroy(self.h)
+            self.h = None
+
+    # -- inspection ------------------------------------------------------------------
+    def get_rp_function(self, i: int) -> list[str]:
+        n = lib.ffgpu_rpn(self.h, i, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        lib.ffgpu_rpn(self.h, i, buf, n + 1)
+        s = buf.value.decode()
+        return s.split(" ") if s else []
+
+    def tape(self) -> np.ndarray:
+        n = lib.ffgpu_get_tape(self.h, None, 0)
+        arr = np.zeros(n, dtype=INSTR_DTYPE)
+        lib.ffgpu_get_tape(self.h, arr.ctypes.data, n)
+        return arr
+
+    def work(self) -> dict:
+        w = (C.c_uint64 * 5)()
+        lib.ffgpu_work(self.h, w)
+        return {"tokens": w[0], "mm": w[1], "ma": w[2], "inv": w[3], "max_rpn_depth": w[4]}
+
+    @property
+    def n_instr(self) -> int:
+        return lib.ffgpu_n_instr(self.h)
+
+    @property
+    def stack_depth(self) -> int:
+        return lib.ffgpu_stack_depth(self.h)
+
+    # -- prime -----------------------------------------------------------------------
+    def set_prime(self, p: int):
+        """FFInt::set_new_prime(p) followed by prime_changed() -> precompute_tokens()."""
+        if lib.ffgpu_set_prime(self.h, p):
+            raise FFGpuError(last_error())
+
+    @property
+    def prime(self) -> int:
+        return lib.ffgpu_get_prime(self.h)
+
+    # -- evaluation ------------------------------------------------------------------
+    def evaluate_pre(self, values, thread_id: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """values: uint64 [n_vars][n_points] (or [n_vars] for one point) -> uint64 [n_out][n_points]."""
+        a = np.asarray(values, dtype=np.uint64)
+        single = a.ndim == 1
+        if single:
+            a = a.reshape(self.n_vars, 1)
+        if a.shape[0] != self.n_vars:
+            raise ValueError(f"expected {self.n_vars} rows of values, got {a.shape[0]}")
+        a = np.ascontiguousarray(a)
+        n = a.shape[1]
+        if out is None:
+            out = np.empty((self.n_out, n), dtype=np.uint64)
+        if lib.ffgpu_eval(self.h, a.ctypes.data, n, out.ctypes.data, thread_id):
+            raise FFGpuError(last_error())
+        return out[:, 0] if single else out
+
+    def eval_ptr(self, values_ptr: int, n_points: int, out_ptr: int, thread_id: int = 0):
+        """Host pointers (e.g. pinned memory from ``host_alloc``)."""
+        if lib.ffgpu_eval(self.h, values_ptr, n_points, out_ptr, thread_id):
+            raise FFGpuError(last_error())
+
+    def eval_device(self, d_values: int, in_stride: int, n_points: int, d_out: int, out_stride: int,
+                    stream: int = 0, device_index: int = 0):
+        """Device pointers; asynchronous on ``stream`` (a raw cudaStream_t)."""
+        if lib.ffgpu_eval_device(self.h, device_index, d_values, in_stride, n_points, d_out, out_stride, stream):
+            raise FFGpuError(last_error())
+
+    def set_launch(self, probes_per_thread: int = 0, threads_per_block: int = 0):
+        if lib.ffgpu_set_launch(self.h, probes_per_thread, threads_per_block):
+            raise FFGpuError(last_error())
+
+    def set_chunk(self, points: int = 0):
+        lib.ffgpu_set_chunk(self.h, points)
+
+
+def launch_count() -> int:
+    return lib.ffgpu_launch_count()
+
+
+def synthetic_points(n_vars: int, n_points: int, p: int, seed: int = 0x4D595DF4D0F33173, first_point: int = 0,
+                     total_points: Optional[int] = None) -> np.ndarray:
+    """Host twin of ffgpu_fill_points: x[v][j] = 1 + splitmix64(seed + v*total + first + j) mod (p-1)."""
+    total = n_points if total_points is None else total_points
+    with np.errstate(over="ignore"):
+        v = np.arange(n_vars, dtype=np.uint64).reshape(-1, 1)
+        j = np.arange(n_points, dtype=np.uint64).reshape(1, -1)
+        z = np.uint64(seed) + v * np.uint64(total) + np.uint64(first_point) + j
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+        return np.uint64(1) + z % np.uint64(p - 1)

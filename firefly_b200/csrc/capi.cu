@@ -1,0 +1,489 @@
+// capi.cu -- the C ABI of include/ffgpu.h: contexts, compiled tapes, host-buffer evaluation
+// with multi-GPU sharding and copy/compute pipelining, device-buffer evaluation.
+//
+// Host-side counterpart of what Reconstructor::get_job / compute_probe<N> do around bb.eval
+// (reference: source/include/firefly/Reconstructor.hpp:3325-3477): take a batch of probe points,
+// run the black box, hand back [function][point].  Here the batch is sharded over the GPUs of
+// the context by contiguous point ranges (no communication between GPUs -- probes are
+// independent), and every shard is cut into chunks whose H2D copy, kernel and D2H copy run on
+// two alternating streams so that copies overlap compute.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/ffgpu.h"
+#include "compiler.hpp"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(const std::string& msg) {
+  g_err = msg;
+  return -1;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return -1;
+}
+#define FF_CUDA(call)                                   \
+  do {                                                  \
+    cudaError_t e_ = (call);                            \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+  } while (0)
+
+constexpr int N_SLOTS = 8;        // concurrent ffgpu_eval callers served without contention
+constexpr int N_BUF = 2;          // double buffering per slot and device
+
+struct DevBuf {
+  cudaStream_t stream = nullptr;
+  uint64_t* d_in = nullptr;
+  uint64_t* d_out = nullptr;
+  size_t cap_in = 0, cap_out = 0;   // elements
+};
+struct SlotDev {
+  DevBuf buf[N_BUF];
+};
+struct Slot {
+  std::mutex mtx;
+  std::vector<SlotDev> dev;
+};
+struct Device {
+  int id = 0;
+  int sm_count = 148;
+};
+
+// ---- the 300 largest primes below 2^63 (what the reference tabulates in ReconstHelper.cpp:24-125),
+// found by a deterministic Miller-Rabin search instead of a table
+typedef unsigned __int128 u128;
+uint64_t mulmod64(uint64_t a, uint64_t b, uint64_t m) { return (uint64_t)((u128)a * b % m); }
+uint64_t powmod64(uint64_t b, uint64_t e, uint64_t m) {
+  uint64_t r = 1;
+  for (; e; e >>= 1, b = mulmod64(b, b, m))
+    if (e & 1) r = mulmod64(r, b, m);
+  return r;
+}
+bool is_prime64(uint64_t n) {
+  if (n < 2) return false;
+  for (uint64_t q : {2ULL, 3ULL, 5ULL, 7ULL, 11ULL, 13ULL, 17ULL, 19ULL, 23ULL, 29ULL, 31ULL, 37ULL}) {
+    if (n % q == 0) return n == q;
+  }
+  uint64_t d = n - 1;
+  int s = 0;
+  while (!(d & 1)) { d >>= 1; ++s; }
+  for (uint64_t a : {2ULL, 3ULL, 5ULL, 7ULL, 11ULL, 13ULL, 17ULL, 19ULL, 23ULL, 29ULL, 31ULL, 37ULL}) {
+    uint64_t x = powmod64(a, d, n);
+    if (x == 1 || x == n - 1) continue;
+    bool comp = true;
+    for (int i = 1; i < s && comp; ++i) {
+      x = mulmod64(x, x, n);
+      if (x == n - 1) comp = false;
+    }
+    if (comp) return false;
+  }
+  return true;
+}
+const std::vector<uint64_t>& prime_table() {
+  static const std::vector<uint64_t> tab = [] {
+    std::vector<uint64_t> t;
+    for (uint64_t n = (1ULL << 63) - 1; t.size() < 300; n -= 2)
+      if (is_prime64(n)) t.push_back(n);
+    return t;
+  }();
+  return tab;
+}
+
+}  // namespace
+
+struct ffgpu_ctx {
+  std::vector<Device> devs;
+  Slot slots[N_SLOTS];
+};
+
+struct ffgpu_tape {
+  ffgpu_ctx* ctx = nullptr;
+  ffgpu::Collection col;
+  std::vector<ffgpu::Instr*> d_tape;   // per device
+  int force_k = 0, force_threads = 0;
+  size_t chunk = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = 0;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    ok = cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+ffgpu_tape* finish_compile(ffgpu_ctx* ctx, std::unique_ptr<ffgpu_tape> t, bool ok, const std::string& err) {
+  if (!ok) {
+    g_err = err;
+    return nullptr;
+  }
+  t->ctx = ctx;       // NULL: host-only handle (RPN / tape inspection; evaluation refuses)
+  if (ctx) t->d_tape.assign(ctx->devs.size(), nullptr);
+  return t.release();
+}
+
+std::vector<std::string> to_vec(const char* const* s, size_t n) {
+  std::vector<std::string> v;
+  v.reserve(n);
+  for (size_t i = 0; i < n; ++i) v.emplace_back(s[i] ? s[i] : "");
+  return v;
+}
+
+int launch(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, size_t n_points, uint64_t* d_out,
+           size_t out_stride, cudaStream_t stream) {
+  const ffgpu::Collection& c = t->col;
+  ffgpu::EvalParams prm;
+  prm.tape = t->d_tape[g];
+  prm.values = d_values;
+  prm.out = d_out;
+  prm.n_points = n_points;
+  prm.in_stride = in_stride;
+  prm.out_stride = out_stride;
+  prm.p = c.prime;
+  prm.c = (uint32_t)((1ULL << 63) - c.prime);
+  prm.d = 2 * prm.c;
+  prm.stack_depth = c.stack_depth;
+  const ffgpu::LaunchShape sh =
+      ffgpu::choose_shape(n_points, c.stack_depth, t->ctx->devs[g].sm_count, t->force_k, t->force_threads);
+  cudaError_t e = ffgpu::launch_eval(prm, sh, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "launch_eval");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int ensure(DevBuf& b, size_t need_in, size_t need_out) {
+  if (!b.stream) FF_CUDA(cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
+  if (b.cap_in < need_in) {
+    FF_CUDA(cudaStreamSynchronize(b.stream));
+    if (b.d_in) FF_CUDA(cudaFree(b.d_in));
+    b.d_in = nullptr;
+    b.cap_in = 0;
+    FF_CUDA(cudaMalloc(&b.d_in, need_in * sizeof(uint64_t)));
+    b.cap_in = need_in;
+  }
+  if (b.cap_out < need_out) {
+    FF_CUDA(cudaStreamSynchronize(b.stream));
+    if (b.d_out) FF_CUDA(cudaFree(b.d_out));
+    b.d_out = nullptr;
+    b.cap_out = 0;
+    FF_CUDA(cudaMalloc(&b.d_out, need_out * sizeof(uint64_t)));
+    b.cap_out = need_out;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ffgpu_last_error(void) { return g_err.c_str(); }
+
+ffgpu_ctx* ffgpu_create(const int* device_ids, int n_devices) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_err = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+            " (libffgpu has no CPU evaluation path; a B200 is required)";
+    return nullptr;
+  }
+  std::unique_ptr<ffgpu_ctx> ctx(new ffgpu_ctx);
+  std::vector<int> ids;
+  if (!device_ids || n_devices <= 0) {
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) cur = 0;
+    ids.push_back(cur);
+  } else {
+    ids.assign(device_ids, device_ids + n_devices);
+  }
+  for (int id : ids) {
+    if (id < 0 || id >= count) {
+      g_err = "device id " + std::to_string(id) + " out of range";
+      return nullptr;
+    }
+    Device d;
+    d.id = id;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, id) == cudaSuccess) d.sm_count = prop.multiProcessorCount;
+    ctx->devs.push_back(d);
+  }
+  for (auto& s : ctx->slots) s.dev.resize(ctx->devs.size());
+  return ctx.release();
+}
+
+void ffgpu_destroy(ffgpu_ctx* ctx) {
+  if (!ctx) return;
+  for (auto& s : ctx->slots) {
+    for (size_t g = 0; g < s.dev.size(); ++g) {
+      DeviceGuard guard(ctx->devs[g].id);
+      for (auto& b : s.dev[g].buf) {
+        if (b.stream) cudaStreamSynchronize(b.stream);
+        if (b.d_in) cudaFree(b.d_in);
+        if (b.d_out) cudaFree(b.d_out);
+        if (b.stream) cudaStreamDestroy(b.stream);
+      }
+    }
+  }
+  delete ctx;
+}
+
+int ffgpu_n_devices(const ffgpu_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+
+ffgpu_tape* ffgpu_compile(ffgpu_ctx* ctx, const char* const* functions, size_t n_functions, const char* const* vars,
+                          size_t n_vars, unsigned flags) {
+  std::unique_ptr<ffgpu_tape> t(new ffgpu_tape);
+  std::string err;
+  const bool ok = t->col.compile_strings(to_vec(functions, n_functions), to_vec(vars, n_vars),
+                                         (flags & FFGPU_CHECK_IS_EQUAL) != 0, err);
+  return finish_compile(ctx, std::move(t), ok, err);
+}
+
+ffgpu_tape* ffgpu_compile_text(ffgpu_ctx* ctx, const char* text, const char* const* vars, size_t n_vars,
+                               unsigned flags) {
+  std::unique_ptr<ffgpu_tape> t(new ffgpu_tape);
+  std::string err;
+  const bool ok = t->col.compile_text(text ? text : "", to_vec(vars, n_vars), (flags & FFGPU_CHECK_IS_EQUAL) != 0, err);
+  return finish_compile(ctx, std::move(t), ok, err);
+}
+
+ffgpu_tape* ffgpu_compile_file(ffgpu_ctx* ctx, const char* path, const char* const* vars, size_t n_vars,
+                               unsigned flags) {
+  std::ifstream in(path ? path : "");
+  if (!in.good()) {
+    g_err = std::string("File '") + (path ? path : "") + "' does not exist!";
+    return nullptr;
+  }
+  std::stringstream ss;
+  ss << in.rdbuf();
+  return ffgpu_compile_text(ctx, ss.str().c_str(), vars, n_vars, flags);
+}
+
+void ffgpu_tape_destroy(ffgpu_tape* t) {
+  if (!t) return;
+  for (size_t g = 0; g < t->d_tape.size(); ++g) {
+    if (!t->d_tape[g]) continue;
+    DeviceGuard guard(t->ctx->devs[g].id);
+    cudaDeviceSynchronize();
+    cudaFree(t->d_tape[g]);
+  }
+  delete t;
+}
+
+size_t ffgpu_n_vars(const ffgpu_tape* t) { return t->col.vars.size(); }
+size_t ffgpu_n_functions(const ffgpu_tape* t) { return t->col.functions.size(); }
+size_t ffgpu_n_out(const ffgpu_tape* t) { return t->col.n_out; }
+size_t ffgpu_n_instr(const ffgpu_tape* t) { return t->col.tape.size() - 2; }
+size_t ffgpu_stack_depth(const ffgpu_tape* t) { return t->col.stack_depth; }
+
+size_t ffgpu_rpn(const ffgpu_tape* t, size_t i, char* buf, size_t cap) {
+  if (i >= t->col.functions.size()) return 0;
+  std::string s;
+  for (const std::string& tok : t->col.functions[i].rpn) {
+    if (!s.empty()) s += ' ';
+    s += tok;
+  }
+  if (buf && cap) {
+    const size_t n = std::min(s.size(), cap - 1);
+    std::memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return s.size();
+}
+
+size_t ffgpu_get_tape(const ffgpu_tape* t, void* buf, size_t cap) {
+  const size_t n = std::min(cap, t->col.tape.size());
+  if (buf && n) std::memcpy(buf, t->col.tape.data(), n * sizeof(ffgpu::Instr));
+  return t->col.tape.size();
+}
+
+void ffgpu_work(const ffgpu_tape* t, uint64_t w[5]) {
+  w[0] = t->col.work.tokens;
+  w[1] = t->col.work.mm;
+  w[2] = t->col.work.ma;
+  w[3] = t->col.work.inv;
+  w[4] = t->col.work.max_rpn_depth;
+}
+
+uint32_t ffgpu_n_primes(void) { return (uint32_t)prime_table().size(); }
+uint64_t ffgpu_prime(uint32_t i) { return i < prime_table().size() ? prime_table()[i] : 0; }
+uint64_t ffgpu_get_prime(const ffgpu_tape* t) { return t->col.prime; }
+
+int ffgpu_set_prime(ffgpu_tape* t, uint64_t p) {
+  if (!t) return fail("null tape");
+  const uint64_t two63 = 1ULL << 63;
+  if (p >= two63 || two63 - p >= (1u << 15) || p < 3)
+    return fail("unsupported prime " + std::to_string(p) + ": need p = 2^63 - c with 0 < c < 2^15");
+  std::string err;
+  if (!t->col.resolve(p, err)) return fail(err);
+  const size_t bytes = t->col.tape.size() * sizeof(ffgpu::Instr);
+  for (size_t g = 0; t->ctx && g < t->ctx->devs.size(); ++g) {
+    DeviceGuard guard(t->ctx->devs[g].id);
+    // quiescence is the caller's contract; make it true for our own streams anyway
+    FF_CUDA(cudaDeviceSynchronize());
+    if (!t->d_tape[g]) FF_CUDA(cudaMalloc(&t->d_tape[g], bytes));
+    FF_CUDA(cudaMemcpy(t->d_tape[g], t->col.tape.data(), bytes, cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+int ffgpu_set_launch(ffgpu_tape* t, int k, int threads) {
+  if (!(k == 0 || k == 1 || k == 2 || k == 4)) return fail("probes_per_thread must be 0, 1, 2 or 4");
+  if (!(threads == 0 || threads == 128 || threads == 256 || threads == 512))
+    return fail("threads_per_block must be 0, 128, 256 or 512");
+  t->force_k = k;
+  t->force_threads = threads;
+  return 0;
+}
+
+int ffgpu_set_chunk(ffgpu_tape* t, size_t points) {
+  t->chunk = points;
+  return 0;
+}
+
+uint64_t ffgpu_launch_count(void) { return g_launches.load(); }
+
+int ffgpu_eval_device(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, size_t n_points,
+                      uint64_t* d_out, size_t out_stride, void* stream) {
+  if (!t) return fail("null tape");
+  if (!t->ctx) return fail("tape was compiled without a context: no GPU to evaluate on (there is no CPU path)");
+  if (g < 0 || g >= (int)t->ctx->devs.size()) return fail("device index out of range");
+  if (!t->col.prime || !t->d_tape[g]) return fail("ffgpu_set_prime has not been called");
+  if (in_stride < n_points || out_stride < n_points) return fail("row stride smaller than n_points");
+  if (n_points == 0) return 0;
+  DeviceGuard guard(t->ctx->devs[g].id);
+  return launch(t, g, d_values, in_stride, n_points, d_out, out_stride, (cudaStream_t)stream);
+}
+
+int ffgpu_eval(ffgpu_tape* t, const uint64_t* values, size_t n_points, uint64_t* out, uint32_t thread_id) {
+  if (!t) return fail("null tape");
+  if (!t->ctx) return fail("tape was compiled without a context: no GPU to evaluate on (there is no CPU path)");
+  if (!t->col.prime) return fail("ffgpu_set_prime has not been called");
+  if (n_points == 0) return 0;
+  ffgpu_ctx* ctx = t->ctx;
+  const size_t G = ctx->devs.size();
+  const size_t n_vars = t->col.vars.size(), n_out = t->col.n_out;
+  Slot& slot = ctx->slots[thread_id % N_SLOTS];
+  std::lock_guard<std::mutex> lock(slot.mtx);
+
+  // contiguous shard per device; chunk size: large enough to amortise launches, small enough to pipeline
+  const size_t per_dev = (n_points + G - 1) / G;
+  size_t chunk = t->chunk;
+  if (!chunk) {
+    const size_t bytes_per_point = 8 * (n_vars + n_out);
+    chunk = std::max<size_t>(1 << 16, (32u << 20) / std::max<size_t>(bytes_per_point, 1));
+  }
+  chunk = std::min(chunk, per_dev);
+  chunk = (chunk + 1) & ~(size_t)1;
+  const size_t n_chunks = (per_dev + chunk - 1) / chunk;
+  int prev_dev = 0;
+  cudaGetDevice(&prev_dev);
+  int rc = 0;
+  for (size_t ci = 0; ci < n_chunks && rc == 0; ++ci) {
+    for (size_t g = 0; g < G && rc == 0; ++g) {
+      const size_t lo_dev = g * per_dev, hi_dev = std::min(n_points, lo_dev + per_dev);
+      const size_t lo = lo_dev + ci * chunk;
+      if (lo >= hi_dev) continue;
+      const size_t cnt = std::min(chunk, hi_dev - lo);
+      const size_t cnt_even = (cnt + 1) & ~(size_t)1;     // the pad lane computes on junk and is never copied back
+      rc = [&]() -> int {
+        FF_CUDA(cudaSetDevice(ctx->devs[g].id));
+        DevBuf& b = slot.dev[g].buf[ci % N_BUF];
+        if (ensure(b, chunk * std::max<size_t>(n_vars, 1), chunk * std::max<size_t>(n_out, 1))) return -1;
+        if (n_vars)
+          FF_CUDA(cudaMemcpy2DAsync(b.d_in, chunk * 8, values + lo, n_points * 8, cnt * 8, n_vars,
+                                    cudaMemcpyHostToDevice, b.stream));
+        if (launch(t, (int)g, b.d_in, chunk, cnt_even, b.d_out, chunk, b.stream)) return -1;
+        if (n_out)
+          FF_CUDA(cudaMemcpy2DAsync(out + lo, n_points * 8, b.d_out, chunk * 8, cnt * 8, n_out,
+                                    cudaMemcpyDeviceToHost, b.stream));
+        return 0;
+      }();
+    }
+  }
+  // drain
+  for (size_t g = 0; g < G; ++g) {
+    cudaSetDevice(ctx->devs[g].id);
+    for (auto& b : slot.dev[g].buf) {
+      if (!b.stream) continue;
+      cudaError_t e = cudaStreamSynchronize(b.stream);
+      if (e != cudaSuccess && rc == 0) rc = cuda_fail(e, "cudaStreamSynchronize");
+    }
+  }
+  cudaSetDevice(prev_dev);
+  return rc;
+}
+
+void* ffgpu_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    cuda_fail(e, "cudaHostAlloc");
+    return nullptr;
+  }
+  return p;
+}
+void ffgpu_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int ffgpu_fill_points(ffgpu_ctx* ctx, int g, uint64_t* d_values, size_t n_vars, size_t n_points, size_t stride,
+                      uint64_t first_point, uint64_t total_points, uint64_t seed, uint64_t p, void* stream) {
+  if (!ctx || g < 0 || g >= (int)ctx->devs.size()) return fail("device index out of range");
+  DeviceGuard guard(ctx->devs[g].id);
+  cudaError_t e = ffgpu::launch_fill_points(d_values, n_vars, n_points, stride, first_point, total_points, seed, p,
+                                            (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "fill_points");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int ffgpu_checksum(ffgpu_ctx* ctx, int g, const uint64_t* d_out, size_t n_out, size_t n_points, size_t stride,
+                   uint64_t p, uint64_t* d_sums, void* stream) {
+  if (!ctx || g < 0 || g >= (int)ctx->devs.size()) return fail("device index out of range");
+  DeviceGuard guard(ctx->devs[g].id);
+  cudaError_t e = ffgpu::launch_checksum(d_out, n_out, n_points, stride, p, d_sums, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "checksum");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int ffgpu_field_ops(ffgpu_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t* r, size_t n, uint64_t p) {
+  if (!ctx) return fail("null context");
+  if (n == 0) return 0;
+  const uint64_t two63 = 1ULL << 63;
+  if (p >= two63 || two63 - p >= (1u << 15)) return fail("unsupported prime");
+  DeviceGuard guard(ctx->devs[0].id);
+  uint64_t *da = nullptr, *db = nullptr, *dr = nullptr;
+  FF_CUDA(cudaMalloc(&da, n * 8));
+  FF_CUDA(cudaMalloc(&db, n * 8));
+  FF_CUDA(cudaMalloc(&dr, n * 8));
+  FF_CUDA(cudaMemcpy(da, a, n * 8, cudaMemcpyHostToDevice));
+  FF_CUDA(cudaMemcpy(db, b, n * 8, cudaMemcpyHostToDevice));
+  cudaError_t e = ffgpu::launch_field_ops(op, da, db, dr, n, p, nullptr);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(r, dr, n * 8, cudaMemcpyDeviceToHost);
+  cudaFree(da);
+  cudaFree(db);
+  cudaFree(dr);
+  if (e != cudaSuccess) return cuda_fail(e, "field_ops");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+}  // extern "C"

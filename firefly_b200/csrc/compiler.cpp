@@ -1,0 +1,673 @@
+// compiler.cpp -- see compiler.hpp.  Host-only C++ (no CUDA).
+#include "compiler.hpp"
+
+#include <algorithm>
+#include <cctype>
+#include <cstring>
+
+#include "ffhost.hpp"
+
+namespace ffgpu {
+
+// ------------------------------------------------------------------------------------------
+// 1. validate  (behaviour of reference ShuntingYardParser::validate, ShuntingYardParser.cpp:778-837)
+// ------------------------------------------------------------------------------------------
+bool validate_expr(std::string& s, uint64_t index, std::string& err) {
+  // Work on the characters plus a terminating NUL; deleted characters are marked and
+  // squeezed out at the end.  The scan is strictly left to right and looks at the live
+  // buffer, so marks made earlier are visible to later tests (as in the reference).
+  const char DEL = '$';
+  std::vector<char> b(s.begin(), s.end());
+  b.push_back('\0');
+  const size_t n = b.size();
+  std::vector<long> open;               // positions of '(' ; negative = directly preceded by '('
+  for (size_t i = 0; i < n; ++i) {
+    const char ch = b[i];
+    if (ch == '+' && b[i + 1] == '-') b[i] = DEL;          // "+-" -> "-"
+    if (b[i] == '-' && b[i + 1] == '+') b[i + 1] = DEL;    // "-+" -> "-"
+    if (b[i] == '(') {
+      open.push_back((i != 0 && b[i - 1] == '(') ? -(long)i : (long)i);
+    } else if (b[i] == ')') {
+      if (open.empty()) {
+        err = "Mismatch of closing parentheses in expression " + std::to_string(index) + ".";
+        return false;
+      }
+      const long top = open.back();
+      if (i + 1 < n && b[i + 1] == ')' && top < 0) {        // "((x))" -> "(x)"
+        b[(size_t)(-top)] = DEL;
+        b[i] = DEL;
+      }
+      open.pop_back();
+    }
+  }
+  if (!open.empty()) {
+    err = "Mismatch of opening parentheses in expression " + std::to_string(index) + ".";
+    return false;
+  }
+  std::string out;
+  out.reserve(s.size());
+  for (size_t i = 0; i + 1 < n; ++i)
+    if (b[i] != DEL) out.push_back(b[i]);
+  s.swap(out);
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// 2. parse: infix -> RPN  (behaviour of reference ShuntingYardParser::parse, :201-313)
+// ------------------------------------------------------------------------------------------
+namespace {
+inline bool is_op_char(char c) { return c == '+' || c == '-' || c == '*' || c == '/' || c == '^'; }
+inline bool is_letter(char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'); }
+inline int weight(char c) {
+  switch (c) {
+    case '^': case '!': case '~': case ';': return 3;
+    case '*': case '/': return 2;
+    case '+': case '-': return 1;
+    default: return 0;
+  }
+}
+}  // namespace
+
+bool parse_expr(std::string& s, std::vector<std::string>& out, std::string& err) {
+  // a global sign in front of a parenthesis: "+(" loses the sign, "-(" becomes "0-("
+  if (s.size() > 2 && (s[0] == '+' || s[0] == '-') && s[1] == '(') {
+    if (s[0] == '+') s.erase(0, 1);
+    else s.insert(s.begin(), '0');
+  }
+  out.clear();
+  std::string cur;                  // operand being collected
+  std::vector<char> ops;            // operator stack
+  bool neg_exp = false;             // inside "^(-": the '-' is still to be swallowed
+  const size_t n = s.size();
+  auto at = [&](size_t i) -> char { return i < n ? s[i] : '\0'; };
+  size_t pos = 0;                   // counts non-NUL characters like the reference's c_counter
+  for (size_t idx = 0; idx < n; ++idx) {
+    const char ch = s[idx];
+    if (ch == '\0') continue;
+    if (ch == '(') {
+      ops.push_back(ch);
+    } else if (ch == ')') {
+      if (!cur.empty()) out.push_back(cur);
+      cur.clear();
+      while (!ops.empty()) {
+        const char t = ops.back();
+        ops.pop_back();
+        if (t == '(') break;
+        out.emplace_back(1, t);
+      }
+    } else if (is_op_char(ch)) {
+      if (!neg_exp && !cur.empty()) {
+        out.push_back(cur);
+        cur.clear();
+      }
+      if (!ops.empty() && pos > 0 && at(pos - 1) == '(') {
+        // a sign directly behind an opening parenthesis
+        if (at(pos + 1) == '(') {           // "(-(" : 0 - (...)
+          out.emplace_back("0");
+          ops.push_back(ch);
+        } else if (!neg_exp) {
+          cur.insert(cur.begin(), ch);      // glue the sign to the operand that follows
+        } else {
+          neg_exp = false;                  // the '-' of "^(-"
+        }
+      } else if (ops.empty() && out.empty()) {
+        cur.insert(cur.begin(), ch);        // sign at the very beginning
+      } else {
+        while (!ops.empty() && ops.back() != '(' && weight(ops.back()) >= weight(ch)) {
+          out.emplace_back(1, ops.back());
+          ops.pop_back();
+        }
+        if (ch == '^') {
+          if (out.empty()) {
+            err = "malformed expression: '^' without a base";
+            return false;
+          }
+          std::string& base = out.back();
+          const bool signed_base = base.size() > 1 && base.front() == '-' && at(pos - 1) != ')';
+          if (at(pos + 1) == '(' && at(pos + 2) == '-') {
+            neg_exp = true;
+            if (signed_base) { base.erase(base.begin()); ops.push_back(';'); }
+            else ops.push_back('~');
+          } else if (signed_base) {
+            base.erase(base.begin());
+            ops.push_back('!');
+          } else {
+            ops.push_back('^');
+          }
+        } else {
+          ops.push_back(ch);
+        }
+      }
+    } else if (ch != ' ') {
+      cur.push_back(ch);                    // digits, letters and anything else
+    }
+    ++pos;
+  }
+  if (!cur.empty()) out.push_back(cur);
+  while (!ops.empty()) {
+    out.emplace_back(1, ops.back());
+    ops.pop_back();
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// 3. literals  (behaviour of precompute's operand branch, :668-711, and FFInt(mpz_class), FFInt.cpp:30-36)
+// ------------------------------------------------------------------------------------------
+namespace {
+// GMP's mpz_set_str(.., base 0) as reached through mpz_class(std::string): optional '-',
+// then 0x/0X hex, 0b/0B binary, leading 0 octal, otherwise decimal.
+bool big_literal(const std::string& t, uint64_t p, uint64_t& out) {
+  size_t i = 0;
+  bool negative = false;
+  while (i < t.size() && std::isspace((unsigned char)t[i])) ++i;
+  if (i < t.size() && t[i] == '-') { negative = true; ++i; }
+  unsigned base = 10;
+  if (i + 1 < t.size() && t[i] == '0' && (t[i + 1] == 'x' || t[i + 1] == 'X')) { base = 16; i += 2; }
+  else if (i + 1 < t.size() && t[i] == '0' && (t[i + 1] == 'b' || t[i + 1] == 'B')) { base = 2; i += 2; }
+  else if (i < t.size() && t[i] == '0') { base = 8; }
+  if (i >= t.size()) return false;
+  uint64_t r = 0;
+  bool any = false;
+  for (; i < t.size(); ++i) {
+    const unsigned char ch = (unsigned char)t[i];
+    if (std::isspace(ch)) continue;
+    unsigned d;
+    if (ch >= '0' && ch <= '9') d = ch - '0';
+    else if (ch >= 'a' && ch <= 'z') d = ch - 'a' + 10;
+    else if (ch >= 'A' && ch <= 'Z') d = ch - 'A' + 10;
+    else return false;
+    if (d >= base) return false;
+    r = (uint64_t)(((ffhost::u128)r * base + d) % p);
+    any = true;
+  }
+  if (!any) return false;
+  out = negative ? ffhost::neg(r, p) : r;
+  return true;
+}
+// std::stoull on a digit-initial string: the leading run of digits (<= 18 characters: no overflow)
+uint64_t leading_digits(const std::string& t, size_t from) {
+  uint64_t v = 0;
+  for (size_t i = from; i < t.size() && t[i] >= '0' && t[i] <= '9'; ++i) v = v * 10 + (uint64_t)(t[i] - '0');
+  return v;
+}
+}  // namespace
+
+bool literal_value(const std::string& token, uint64_t p, uint64_t& out, std::string& err) {
+  if (token.size() > 18) {
+    const std::string t = token[0] == '+' ? token.substr(1) : token;
+    if (!big_literal(t, p, out)) {
+      err = "cannot read integer '" + token + "'";
+      return false;
+    }
+    return true;
+  }
+  size_t from = 0;
+  bool negative = false;
+  if (!token.empty() && (token[0] == '-' || token[0] == '+')) { negative = token[0] == '-'; from = 1; }
+  const uint64_t v = leading_digits(token, from) % p;
+  out = negative ? ffhost::neg(v, p) : v;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// 4. RPN -> expression tree
+// ------------------------------------------------------------------------------------------
+bool Collection::build_tree(Function& f, std::string& err) {
+  f.nodes.clear();
+  f.literals.clear();
+  f.nodes.reserve(f.rpn.size());
+  std::vector<int32_t> st;
+  for (const std::string& tok : f.rpn) {
+    Node nd{};
+    nd.l = nd.r = -1;
+    const bool is_operator = tok.size() == 1 && (is_op_char(tok[0]) || tok[0] == '!' || tok[0] == '~' || tok[0] == ';');
+    if (is_operator) {
+      if (st.size() < 2) {
+        err = "malformed expression: operator '" + tok + "' lacks operands";
+        return false;
+      }
+      nd.r = st.back(); st.pop_back();
+      nd.l = st.back(); st.pop_back();
+      switch (tok[0]) {
+        case '+': nd.kind = N_ADD; break;
+        case '-': nd.kind = N_SUB; break;
+        case '*': nd.kind = N_MUL; break;
+        case '/': nd.kind = N_DIV; break;
+        case '^': nd.kind = N_POW; break;
+        case '~': nd.kind = N_NEGPOW; break;
+        case '!': nd.kind = N_POWNEG; break;
+        default: nd.kind = N_NEGPOWNEG; break;
+      }
+      nd.is_const = f.nodes[nd.l].is_const && f.nodes[nd.r].is_const;
+    } else {
+      // operand: big integer, signed/unsigned variable, or number
+      bool as_number = false;
+      if (tok.size() > 18) {
+        as_number = true;
+      } else {
+        const bool sgn = !tok.empty() && (tok[0] == '-' || tok[0] == '+');
+        const std::string name = sgn ? tok.substr(1) : tok;
+        auto it = var_index.find(name);
+        if (it != var_index.end()) {
+          nd.kind = (sgn && tok[0] == '-') ? N_NEGVAR : N_VAR;
+          nd.var = it->second;
+          nd.is_const = false;
+        } else if (!name.empty() && std::isdigit((unsigned char)name[0])) {
+          as_number = true;
+        } else {
+          err = "Variable '" + name + "' not declared!";
+          return false;
+        }
+      }
+      if (as_number) {
+        uint64_t probe;
+        if (!literal_value(tok, 9223372036854775783ULL, probe, err)) return false;
+        nd.kind = N_NUM;
+        nd.is_const = true;
+        nd.lit = (uint32_t)f.literals.size();
+        f.literals.push_back(Literal{tok});
+      }
+    }
+    st.push_back((int32_t)f.nodes.size());
+    f.nodes.push_back(nd);
+  }
+  if (st.empty()) {
+    err = "Error in functional evaluation! Please check your input.";
+    return false;
+  }
+  f.root = st.back();      // evaluate_pre returns the top of the stack
+
+  // spill-stack need (Sethi-Ullman): operands that can be addressed directly cost nothing
+  auto direct = [&](int32_t i) {
+    const Node& n = f.nodes[i];
+    return n.is_const || n.kind == N_VAR || n.kind == N_NEGVAR;
+  };
+  for (size_t i = 0; i < f.nodes.size(); ++i) {
+    Node& n = f.nodes[i];
+    if (direct((int32_t)i)) { n.need = 0; continue; }
+    const bool dl = direct(n.l), dr = direct(n.r);
+    // a constant exponent / divisor rides in the instruction
+    if (dr) n.need = f.nodes[n.l].need;
+    else if (dl) n.need = f.nodes[n.r].need;
+    else {
+      const unsigned a = f.nodes[n.l].need, b = f.nodes[n.r].need;
+      const unsigned lf = std::max(a, b + 1), rf = std::max(b, a + 1);
+      const unsigned m = std::min(lf, rf);
+      n.need = (uint8_t)std::min(m, 255u);
+    }
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// 5. node evaluation on the host (constants per prime; fingerprints)
+// ------------------------------------------------------------------------------------------
+void eval_nodes(const Function& f, uint64_t p, const uint64_t* point, std::vector<uint64_t>& val) {
+  val.assign(f.nodes.size(), 0);
+  std::string err;
+  for (size_t i = 0; i < f.nodes.size(); ++i) {
+    const Node& n = f.nodes[i];
+    if (!n.is_const && !point) continue;
+    uint64_t v = 0;
+    switch (n.kind) {
+      case N_VAR: v = point[n.var] % p; break;
+      case N_NEGVAR: v = ffhost::neg(point[n.var] % p, p); break;
+      case N_NUM: literal_value(f.literals[n.lit].text, p, v, err); break;
+      case N_ADD: v = ffhost::add(val[n.l], val[n.r], p); break;
+      case N_SUB: v = ffhost::sub(val[n.l], val[n.r], p); break;
+      case N_MUL: v = ffhost::mul(val[n.l], val[n.r], p); break;
+      case N_DIV: v = ffhost::div(val[n.l], val[n.r], p); break;
+      case N_POW: v = ffhost::pow_ff(val[n.l], val[n.r], p); break;
+      case N_POWNEG: v = ffhost::neg(ffhost::pow_ff(val[n.l], val[n.r], p), p); break;
+      case N_NEGPOW: v = ffhost::pow_int(val[n.l], ffhost::to_neg_int(val[n.r]), p); break;
+      case N_NEGPOWNEG: v = ffhost::neg(ffhost::pow_int(val[n.l], ffhost::to_neg_int(val[n.r]), p), p); break;
+    }
+    val[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 6. algorithmic work on the reference's token list
+// ------------------------------------------------------------------------------------------
+void Collection::count_work(const Function& f) {
+  // Replay precompute's folding on the RPN to know which tokens evaluate_pre would walk.
+  enum K : uint8_t { OPR, VARI, NUMB };
+  struct T { K k; char op; uint64_t lit; bool small; };
+  std::vector<T> tk;
+  for (const std::string& s : f.rpn) {
+    const bool is_operator = s.size() == 1 && (is_op_char(s[0]) || s[0] == '!' || s[0] == '~' || s[0] == ';');
+    if (is_operator) {
+      if (s[0] == '/' && tk.size() >= 2 && tk[tk.size() - 1].k == NUMB && tk[tk.size() - 2].k == NUMB) {
+        tk.pop_back();
+        tk.back().small = false;                      // NUM NUM / -> NUM
+      } else if (s[0] == '/' && tk.size() >= 2 && tk[tk.size() - 1].k == NUMB && tk[tk.size() - 2].k == VARI) {
+        tk.back().small = false;
+        tk.push_back(T{OPR, '*', 0, false});          // VAR NUM / -> VAR (1/NUM) *
+      } else {
+        tk.push_back(T{OPR, s[0], 0, false});
+      }
+    } else {
+      const bool sgn = s.size() <= 18 && !s.empty() && (s[0] == '-' || s[0] == '+');
+      const std::string name = sgn ? s.substr(1) : s;
+      if (s.size() <= 18 && var_index.count(name)) tk.push_back(T{VARI, 0, 0, false});
+      else {
+        uint64_t v = 0;
+        bool small = s.size() <= 18 && !(sgn && s[0] == '-');
+        if (small) v = leading_digits(s, sgn ? 1 : 0);
+        tk.push_back(T{NUMB, 0, v, small});
+      }
+    }
+  }
+  uint64_t depth = 0;
+  for (size_t i = 0; i < tk.size(); ++i) {
+    const T& t = tk[i];
+    ++work.tokens;
+    if (t.k != OPR) { ++depth; work.max_rpn_depth = std::max(work.max_rpn_depth, depth); continue; }
+    if (depth) --depth;
+    auto chain = [&](uint64_t e) -> uint64_t {
+      if (e <= 1) return 0;
+      return (uint64_t)(63 - __builtin_clzll(e)) + (uint64_t)__builtin_popcountll(e) - 1;
+    };
+    const bool lit_exp = i > 0 && tk[i - 1].k == NUMB && tk[i - 1].small;
+    switch (t.op) {
+      case '+': case '-': ++work.ma; break;
+      case '*': ++work.mm; break;
+      case '/': ++work.mm; ++work.inv; break;
+      case '^': work.mm += lit_exp ? chain(tk[i - 1].lit) : 94; break;          // generic exponent: ~1.5*63
+      case '!': work.mm += lit_exp ? chain(tk[i - 1].lit) : 94; ++work.ma; break;
+      case '~': work.mm += lit_exp ? chain(tk[i - 1].lit) : 94; ++work.inv; break;
+      case ';': work.mm += lit_exp ? chain(tk[i - 1].lit) : 94; ++work.inv; ++work.ma; break;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 7. code generation
+// ------------------------------------------------------------------------------------------
+namespace {
+struct Emitter {
+  const Function& f;
+  uint32_t fn;
+  std::vector<Instr>& tape;
+  std::vector<ConstPatch>& patches;
+  uint32_t depth = 0, max_depth = 0;
+
+  bool direct(int32_t i) const {
+    const Node& n = f.nodes[i];
+    return n.is_const || n.kind == N_VAR || n.kind == N_NEGVAR;
+  }
+  // fill the operand fields of `ins` from a directly addressable node
+  void operand(Instr& ins, int32_t i, bool inverse = false) {
+    const Node& n = f.nodes[i];
+    if (n.is_const) {
+      ins.src = SRC_CONST;
+      patches.push_back(ConstPatch{(uint32_t)tape.size(), fn, i, inverse});
+    } else {
+      ins.src = n.kind == N_VAR ? SRC_VAR : SRC_NEGVAR;
+      ins.arg = n.var;
+    }
+  }
+  void put(Instr ins) { tape.push_back(ins); }
+  static Instr mk(uint8_t op, uint8_t flags = 0) {
+    Instr i{};
+    i.op = op;
+    i.flags = flags;
+    return i;
+  }
+
+  void apply(const Node& n, bool acc_is_right, uint8_t src_kind_pop, int32_t other) {
+    // ACC holds one operand; the other is `other` (direct) or the spill-stack top.
+    const bool from_stack = src_kind_pop == SRC_POP;
+    auto finish = [&](Instr ins) {
+      if (from_stack) { ins.src = SRC_POP; put(ins); --depth; }
+      else { operand(ins, other); put(ins); }
+    };
+    switch (n.kind) {
+      case N_ADD: finish(mk(OP_ADD)); break;
+      case N_MUL: finish(mk(OP_MUL)); break;
+      case N_SUB: finish(mk(OP_SUB, acc_is_right ? F_SWAP : 0)); break;
+      case N_DIV: finish(mk(OP_MUL)); break;           // the divisor has been inverted already
+      case N_POW: finish(mk(OP_POWL, acc_is_right ? F_SWAP : 0)); break;
+      case N_POWNEG: finish(mk(OP_POWL, (acc_is_right ? F_SWAP : 0) | F_NEGR)); break;
+      case N_NEGPOW: finish(mk(OP_NPOWL, acc_is_right ? F_SWAP : 0)); break;
+      case N_NEGPOWNEG: finish(mk(OP_NPOWL, (acc_is_right ? F_SWAP : 0) | F_NEGR)); break;
+      default: break;
+    }
+  }
+
+};
+}  // namespace
+
+void Collection::emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots) {
+  const Function& f = functions[fn];
+  Emitter em{f, fn, tape, patches};
+  // Explicit work stack (expressions can be nested 10^5 deep: no recursion); items are
+  // pushed in reverse execution order.
+  struct Item { uint8_t what; int32_t node; bool push; bool swap; int32_t other; };
+  enum { GEN, APPLY_POP, APPLY_DIRECT, INVERT, POW_CONST, MUL_INVCONST };
+  std::vector<Item> work;
+  work.push_back(Item{GEN, f.root, false, false, -1});
+  auto direct = [&](int32_t i) { return em.direct(i); };
+  while (!work.empty()) {
+    const Item it = work.back();
+    work.pop_back();
+    switch (it.what) {
+      case INVERT: em.put(Emitter::mk(OP_INV)); continue;
+      case APPLY_POP: em.apply(f.nodes[it.node], it.swap, SRC_POP, -1); continue;
+      case APPLY_DIRECT: em.apply(f.nodes[it.node], it.swap, SRC_NONE, it.other); continue;
+      case POW_CONST: {
+        const Node& n = f.nodes[it.node];
+        Instr ins = Emitter::mk((n.kind == N_POW || n.kind == N_POWNEG) ? OP_POWU : OP_NPOWU,
+                                (n.kind == N_POWNEG || n.kind == N_NEGPOWNEG) ? F_NEGR : 0);
+        ins.src = SRC_CONST;
+        patches.push_back(ConstPatch{(uint32_t)tape.size(), fn, n.r, false});
+        em.put(ins);
+        continue;
+      }
+      case MUL_INVCONST: {
+        const Node& n = f.nodes[it.node];
+        Instr ins = Emitter::mk(OP_MUL);
+        ins.src = SRC_CONST;
+        patches.push_back(ConstPatch{(uint32_t)tape.size(), fn, n.r, true});
+        em.put(ins);
+        continue;
+      }
+      default: break;
+    }
+    const Node& n = f.nodes[it.node];
+    if (direct(it.node)) {
+      Instr ins = Emitter::mk(OP_LOAD, it.push ? F_PUSH : 0);
+      if (it.push) { ++em.depth; em.max_depth = std::max(em.max_depth, em.depth); }
+      em.operand(ins, it.node);
+      em.put(ins);
+      continue;
+    }
+    const bool dl = direct(n.l), dr = direct(n.r);
+    const bool is_pow = n.kind == N_POW || n.kind == N_POWNEG || n.kind == N_NEGPOW || n.kind == N_NEGPOWNEG;
+    const unsigned a = f.nodes[n.l].need, b = f.nodes[n.r].need;
+    const bool left_first = std::max(a, b + 1) <= std::max(b, a + 1);
+    if (is_pow && f.nodes[n.r].is_const) {
+      work.push_back(Item{POW_CONST, it.node, false, false, -1});
+      work.push_back(Item{GEN, n.l, it.push, false, -1});
+    } else if (n.kind == N_DIV && f.nodes[n.r].is_const) {
+      work.push_back(Item{MUL_INVCONST, it.node, false, false, -1});
+      work.push_back(Item{GEN, n.l, it.push, false, -1});
+    } else if (n.kind == N_DIV) {
+      if (dl) {                      // invert the divisor, multiply by the simple numerator
+        work.push_back(Item{APPLY_DIRECT, it.node, false, true, n.l});
+        work.push_back(Item{INVERT, -1, false, false, -1});
+        work.push_back(Item{GEN, n.r, it.push, false, -1});
+      } else if (left_first) {
+        work.push_back(Item{APPLY_POP, it.node, false, true, -1});
+        work.push_back(Item{INVERT, -1, false, false, -1});
+        work.push_back(Item{GEN, n.r, true, false, -1});
+        work.push_back(Item{GEN, n.l, it.push, false, -1});
+      } else {
+        work.push_back(Item{APPLY_POP, it.node, false, false, -1});
+        work.push_back(Item{GEN, n.l, true, false, -1});
+        work.push_back(Item{INVERT, -1, false, false, -1});
+        work.push_back(Item{GEN, n.r, it.push, false, -1});
+      }
+    } else if (dr) {
+      work.push_back(Item{APPLY_DIRECT, it.node, false, false, n.r});
+      work.push_back(Item{GEN, n.l, it.push, false, -1});
+    } else if (dl) {
+      work.push_back(Item{APPLY_DIRECT, it.node, false, true, n.l});
+      work.push_back(Item{GEN, n.r, it.push, false, -1});
+    } else if (left_first) {
+      work.push_back(Item{APPLY_POP, it.node, false, true, -1});
+      work.push_back(Item{GEN, n.r, true, false, -1});
+      work.push_back(Item{GEN, n.l, it.push, false, -1});
+    } else {
+      work.push_back(Item{APPLY_POP, it.node, false, false, -1});
+      work.push_back(Item{GEN, n.l, true, false, -1});
+      work.push_back(Item{GEN, n.r, it.push, false, -1});
+    }
+  }
+  for (uint32_t slot : out_slots) {
+    Instr st = Emitter::mk(OP_STORE);
+    st.arg = slot;
+    em.put(st);
+  }
+  stack_depth = std::max(stack_depth, em.max_depth);
+}
+
+// ------------------------------------------------------------------------------------------
+// 8. collection level
+// ------------------------------------------------------------------------------------------
+namespace {
+const uint64_t P0 = 9223372036854775783ULL;   // 2^63 - 25, the largest 63-bit prime
+const uint64_t P1 = 9223372036854775643ULL;   // 2^63 - 165, the next one
+inline uint64_t splitmix64(uint64_t& s) {
+  uint64_t z = (s += 0x9E3779B97F4A7C15ULL);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+}  // namespace
+
+bool Collection::add_function(std::string text, uint64_t index, bool strip_blanks, std::string& err) {
+  if (strip_blanks) {
+    text.erase(std::remove_if(text.begin(), text.end(), [](char c) { return c == ' ' || c == '\t' || c == '\n'; }),
+               text.end());
+    if (text.empty()) return true;          // blank chunk between ';' adds no function
+  }
+  if (!validate_expr(text, index, err)) return false;
+  Function f;
+  if (!parse_expr(text, f.rpn, err)) return false;
+  if (!build_tree(f, err)) return false;
+  if (check_is_equal) {
+    // fingerprint = values at one random point in each of two primes (reference: :125-140)
+    std::vector<uint64_t> v1, v2;
+    eval_nodes(f, P1, chk_pts1_.data(), v1);
+    eval_nodes(f, P0, chk_pts2_.data(), v2);
+    const std::string key = std::to_string(v1[f.root]) + ":" + std::to_string(v2[f.root]);
+    auto it = chk_map_.find(key);
+    if (it != chk_map_.end()) {
+      evaluation_positions.push_back(it->second);
+      return true;
+    }
+    chk_map_.emplace(key, (uint64_t)functions.size());
+    evaluation_positions.push_back((uint64_t)functions.size());
+  }
+  functions.push_back(std::move(f));
+  return true;
+}
+
+bool Collection::finish(std::string& err) {
+  (void)err;
+  n_out = check_is_equal ? evaluation_positions.size() : functions.size();
+  // output slots per distinct function
+  std::vector<std::vector<uint32_t>> slots(functions.size());
+  if (check_is_equal) {
+    for (size_t k = 0; k < evaluation_positions.size(); ++k) slots[evaluation_positions[k]].push_back((uint32_t)k);
+  } else {
+    for (size_t k = 0; k < functions.size(); ++k) slots[k].push_back((uint32_t)k);
+  }
+  tape.clear();
+  patches.clear();
+  stack_depth = 0;
+  work = WorkCount{};
+  for (size_t i = 0; i < functions.size(); ++i) {
+    emit_function((uint32_t)i, slots[i]);
+    count_work(functions[i]);
+  }
+  Instr halt{};
+  halt.op = OP_HALT;
+  tape.push_back(halt);
+  tape.push_back(halt);            // the interpreter prefetches one instruction ahead
+  prime = 0;
+  chk_map_.clear();
+  return true;
+}
+
+static void init_vars(Collection& c, const std::vector<std::string>& vars, bool chk) {
+  c.vars = vars;
+  c.var_index.clear();
+  for (uint32_t i = 0; i < vars.size(); ++i) c.var_index.emplace(vars[i], i);   // first declaration wins
+  c.check_is_equal = chk;
+  c.functions.clear();
+  c.evaluation_positions.clear();
+}
+
+bool Collection::compile_strings(const std::vector<std::string>& funs, const std::vector<std::string>& vars_,
+                                 bool chk, std::string& err) {
+  init_vars(*this, vars_, chk);
+  if (chk) {
+    uint64_t s = 0x4d595df4d0f33173ULL;
+    chk_pts1_.resize(vars.size());
+    chk_pts2_.resize(vars.size());
+    for (auto& v : chk_pts1_) v = 1 + splitmix64(s) % (P1 - 1);
+    for (auto& v : chk_pts2_) v = 1 + splitmix64(s) % (P0 - 1);
+  }
+  for (size_t i = 0; i < funs.size(); ++i)
+    if (!add_function(funs[i], i, false, err)) return false;
+  return finish(err);
+}
+
+bool Collection::compile_text(const std::string& text, const std::vector<std::string>& vars_, bool chk,
+                              std::string& err) {
+  init_vars(*this, vars_, chk);
+  if (chk) {
+    uint64_t s = 0x4d595df4d0f33173ULL;
+    chk_pts1_.resize(vars.size());
+    chk_pts2_.resize(vars.size());
+    for (auto& v : chk_pts1_) v = 1 + splitmix64(s) % (P1 - 1);
+    for (auto& v : chk_pts2_) v = 1 + splitmix64(s) % (P0 - 1);
+  }
+  size_t start = 0;
+  uint64_t line = 1;
+  while (start <= text.size()) {
+    size_t end = text.find(';', start);
+    if (end == std::string::npos) end = text.size();
+    if (end > start || end < text.size()) {
+      if (!add_function(text.substr(start, end - start), line, true, err)) return false;
+    }
+    ++line;
+    if (end == text.size()) break;
+    start = end + 1;
+  }
+  return finish(err);
+}
+
+bool Collection::resolve(uint64_t p, std::string& err) {
+  if (p < 3 || (p >> 63)) {
+    err = "prime must be below 2^63";
+    return false;
+  }
+  std::vector<uint64_t> val;
+  uint32_t cur = ~0u;
+  for (const ConstPatch& cp : patches) {
+    if (cp.fn != cur) {
+      cur = cp.fn;
+      eval_nodes(functions[cur], p, nullptr, val);
+    }
+    const uint64_t v = val[cp.node];
+    tape[cp.instr].imm = cp.inverse ? ffhost::div(1 % p, v, p) : v;
+  }
+  prime = p;
+  return true;
+}
+
+}  // namespace ffgpu

@@ -1,0 +1,129 @@
+// compiler.hpp -- host-side tape compiler: text -> RPN -> expression trees ->
+// accumulator-machine tape (tape.hpp) + per-prime constants.
+//
+// Behavioural contract (what a user of the reference's ShuntingYardParser sees):
+//   * the same input grammar, including its quirks: ';'-separated files with all
+//     blanks removed (reference: source/ShuntingYardParser.cpp:98-146), "+-" / "-+"
+//     folding and "((..))" collapsing (validate, :778-837), unary signs glued to the
+//     following operand, the synthetic operators '!' (-x^e), '~' (x^(-e)),
+//     ';' (-x^(-e)), and ALL binary operators left associative, '^' included
+//     (parse, :201-313; get_weight, :484-503);
+//   * the same reverse Polish token strings (get_rp_functions, :526-528) -- exposed
+//     through Collection::rpn for parity tests;
+//   * literal handling of precompute (:593-718): tokens longer than 18 characters are
+//     big integers reduced mod p, shorter ones are variables or stoull() numbers with
+//     an optional sign prefix; unknown names are an error;
+//   * check_is_equal duplicate detection (:73-92,125-140) with evaluation_positions
+//     expansion (ShuntingYardParser.hpp:462-478);
+//   * the values: every function evaluates to exactly the residue evaluate_pre returns.
+//
+// What is different is everything after the RPN: instead of a flat token list for a
+// stack machine we build expression trees, fold every constant sub-expression once per
+// prime with the reference's FFInt semantics (ffhost.hpp) -- a superset of the
+// reference's NUM NUM / and VAR NUM / folds (:619-645) -- order sub-trees to minimise
+// spill-stack depth and emit accumulator code (tape.hpp).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "tape.hpp"
+
+namespace ffgpu {
+
+enum NodeKind : uint8_t {
+  N_VAR, N_NEGVAR, N_NUM,
+  N_ADD, N_SUB, N_MUL, N_DIV,
+  N_POW,        // '^'
+  N_NEGPOW,     // '~'  x^(-e)
+  N_POWNEG,     // '!'  -(x^e)
+  N_NEGPOWNEG,  // ';'  -(x^(-e))
+};
+
+struct Node {
+  NodeKind kind;
+  bool is_const;       // no variable below this node
+  uint8_t need;        // spill-stack slots needed to bring this node into ACC
+  uint32_t var;        // N_VAR / N_NEGVAR
+  int32_t l, r;        // children (indices into the function's node array)
+  uint32_t lit;        // N_NUM: index into Function::literals
+};
+
+// a number token exactly as it appears in the RPN ("12", "-3", "+5", "12132132323213213212")
+struct Literal {
+  std::string text;
+};
+
+struct Function {
+  std::vector<std::string> rpn;      // reference-compatible RPN tokens
+  std::vector<Node> nodes;           // post order: children precede parents
+  std::vector<Literal> literals;
+  int32_t root = -1;
+};
+
+// where a per-prime constant has to be written into the tape
+struct ConstPatch {
+  uint32_t instr;      // index into Collection::tape
+  uint32_t fn;         // function
+  int32_t node;        // constant sub-tree root
+  bool inverse;        // store 1/value (division by a constant becomes a multiplication)
+};
+
+// algorithmic work of one probe (all functions), counted on the reference's
+// precomputed tokens as SURVEY.md section 8(d) defines it
+struct WorkCount {
+  uint64_t tokens = 0;      // precomp_tokens the reference's evaluate_pre would walk
+  uint64_t mm = 0;          // modular multiplications (literal powers: floor(log2 e)+popcount(e)-1)
+  uint64_t ma = 0;          // additions / subtractions / negations
+  uint64_t inv = 0;         // inversions (DIV and negative powers)
+  uint64_t max_rpn_depth = 0;
+};
+
+struct Collection {
+  std::vector<std::string> vars;
+  std::unordered_map<std::string, uint32_t> var_index;
+  bool check_is_equal = false;
+  std::vector<Function> functions;            // distinct functions
+  std::vector<uint64_t> evaluation_positions; // out index -> function (only if check_is_equal)
+  size_t n_out = 0;
+
+  std::vector<Instr> tape;                    // prime independent structure (imm = 0)
+  std::vector<ConstPatch> patches;
+  uint32_t stack_depth = 0;                   // spill slots the tape needs
+  uint64_t prime = 0;                         // prime the imm fields are resolved for (0: none)
+  WorkCount work;
+
+  // parse + build trees + emit the tape.  Returns false and sets `err` on malformed input
+  // (where the reference prints ERROR_MSG and exits, or runs into undefined behaviour).
+  bool compile_strings(const std::vector<std::string>& funs, const std::vector<std::string>& vars,
+                       bool check_is_equal, std::string& err);
+  bool compile_text(const std::string& file_text, const std::vector<std::string>& vars, bool check_is_equal,
+                    std::string& err);
+  // recompute every constant for prime p and patch the tape (what prime_changed() ->
+  // precompute_tokens() does in the reference, ShuntingYardParser.cpp:550-591)
+  bool resolve(uint64_t p, std::string& err);
+
+ private:
+  bool add_function(std::string text, uint64_t index, bool strip_blanks, std::string& err);
+  bool build_tree(Function& f, std::string& err);
+  void emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots);
+  void count_work(const Function& f);
+  bool finish(std::string& err);
+  // fingerprints for duplicate detection
+  std::vector<uint64_t> chk_pts1_, chk_pts2_;
+  std::unordered_map<std::string, uint64_t> chk_map_;
+};
+
+// --- pieces exposed for tests -------------------------------------------------------------
+// validate(): "+-"/"-+" folding, "((x))" collapsing, parenthesis balance
+bool validate_expr(std::string& s, uint64_t index, std::string& err);
+// parse(): infix -> reference RPN tokens
+bool parse_expr(std::string& s, std::vector<std::string>& rpn, std::string& err);
+// value of a number token modulo p with the reference's rules
+bool literal_value(const std::string& token, uint64_t p, uint64_t& out, std::string& err);
+// evaluate all constant nodes of f for prime p (val[i] valid where nodes[i].is_const) and, if
+// `point` is non-null, every node at that point (host fingerprinting only)
+void eval_nodes(const Function& f, uint64_t p, const uint64_t* point, std::vector<uint64_t>& val);
+
+}  // namespace ffgpu

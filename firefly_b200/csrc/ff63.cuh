@@ -143,6 +143,28 @@ FF63_HD u64 mul_barrett(u64 a, u64 b, const Barrett& f) {
   return r >> f.k;
 }
 
+// ----- lazy add / sub / neg: any representatives in [0, 2^64), p = 2^63 - c, d = 2c ----------
+// 2^64 = 2p + d, so a wrap of the 64-bit sum is worth +d and a borrow is worth -d.
+FF63_HD u64 add_lazy(u64 a, u64 b, u32 d) {
+  u64 s = a + b;
+  if (s < a) {              // wrapped once: s + 2^64 == s + d
+    u64 t = s + d;
+    if (t < s) t += d;      // wrapped again: t < d now, cannot wrap a third time
+    s = t;
+  }
+  return s;
+}
+FF63_HD u64 sub_lazy(u64 a, u64 b, u32 d, u64 p) {
+  u64 s = a - b;
+  if (a < b) {              // borrowed: s - 2^64 == s - d
+    u64 t = s - d;
+    if (s < d) t += p;      // s - d in (-d, 0): lift by p (mod 2^64 arithmetic does the rest)
+    s = t;
+  }
+  return s;
+}
+FF63_HD u64 neg_lazy(u64 a, u32 d, u64 p) { return sub_lazy(0, a, d, p); }
+
 #if defined(__CUDACC__)
 // ----- device-only tuned variants -------------------------------------------------
 // Same values as mul_pm / sqr_pm; written in PTX so that NVVM cannot "improve"

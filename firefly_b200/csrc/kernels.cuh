@@ -1,0 +1,46 @@
+// kernels.cuh -- launch interface of the sm_100a tape interpreter (kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "tape.hpp"
+
+namespace ffgpu {
+
+struct EvalParams {
+  const Instr* tape;          // device, resolved for prime p, terminated by two OP_HALT
+  const uint64_t* values;     // device, [n_vars][in_stride], canonical residues
+  uint64_t* out;              // device, [n_out][out_stride]
+  uint64_t n_points;
+  uint64_t in_stride;
+  uint64_t out_stride;
+  uint64_t p;                 // 2^63 - c
+  uint32_t c;
+  uint32_t d;                 // 2c
+  uint32_t stack_depth;       // spill slots per lane
+};
+
+// probes per thread / threads per block actually used for a launch
+struct LaunchShape {
+  int k;          // 1, 2 or 4
+  int threads;    // 128, 256 or 512
+  unsigned blocks;
+  size_t smem;
+};
+
+LaunchShape choose_shape(uint64_t n_points, uint32_t stack_depth, int sm_count, int force_k, int force_threads);
+cudaError_t launch_eval(const EvalParams& prm, const LaunchShape& shape, cudaStream_t stream);
+
+// synthetic probe points, identical on host (bench/tests) and device:
+//   x[v][j] = 1 + splitmix64(seed + v * n_points + j) mod (p - 1)        in [1, p-1]
+cudaError_t launch_fill_points(uint64_t* values, uint64_t n_vars, uint64_t n_points, uint64_t stride,
+                               uint64_t first_point, uint64_t total_points, uint64_t seed, uint64_t p,
+                               cudaStream_t stream);
+// out[f] = (sum of column f mod p, xor of column f) over n_points -- compact fingerprints of big outputs
+cudaError_t launch_checksum(const uint64_t* out, uint64_t n_out, uint64_t n_points, uint64_t stride, uint64_t p,
+                            uint64_t* sums /* [n_out][2] */, cudaStream_t stream);
+// field-arithmetic self test: r[i] = op(a[i], b[i]) for the device primitives (tests only call this)
+cudaError_t launch_field_ops(int op, const uint64_t* a, const uint64_t* b, uint64_t* r, uint64_t n, uint64_t p,
+                             cudaStream_t stream);
+
+}  // namespace ffgpu

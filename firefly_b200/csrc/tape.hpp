@@ -1,0 +1,75 @@
+// tape.hpp -- the device instruction tape: format shared by the host-side tape
+// compiler (compiler.cpp) and the sm_100a interpreter kernels (kernels.cu).
+//
+// What it replaces.  The reference pre-compiles every function of a collection
+// into `precomp_tokens`, a vector of (opcode, FFInt) pairs in reverse Polish order
+// (reference: source/include/firefly/ShuntingYardParser.hpp:148,220-238;
+// builder source/ShuntingYardParser.cpp:593-718) and runs a std::stack machine over
+// it per function and per point (ShuntingYardParser.hpp:365-479).
+//
+// This tape is NOT that token list.  It is straight-line code for an
+// ACCUMULATOR machine generated from the expression tree of each function:
+//
+//   * every lane (= one probe point) owns an accumulator ACC that lives in
+//     registers and a small spill stack that lives in shared memory;
+//   * an instruction is `ACC = ACC op SRC` where SRC is a variable of the probe
+//     point, a negated variable, a per-prime constant carried inline in the
+//     instruction, or the top of the spill stack;
+//   * the spill stack is only touched when both operands of a binary operator are
+//     compound expressions; the compiler orders sub-trees (Sethi-Ullman) so that
+//     the depth stays logarithmic;
+//   * all functions of a collection are concatenated into one tape; each ends in a
+//     STORE that writes the canonical residue to out[slot][point].
+//
+// The tape's structure is prime independent; only the 64-bit `imm` fields of
+// constant-carrying instructions change with the prime (the reference keeps
+// `partial_rpn` for the same purpose, ShuntingYardParser.cpp:584-590).
+#pragma once
+#include <cstdint>
+
+namespace ffgpu {
+
+// One instruction = 16 bytes, fetched with a single 128-bit load.
+struct alignas(16) Instr {
+  uint8_t op;      // Op
+  uint8_t src;     // Src
+  uint8_t flags;   // F_*
+  uint8_t rsv;
+  uint32_t arg;    // variable index (SRC_VAR/SRC_NEGVAR) or output slot (OP_STORE)
+  uint64_t imm;    // constant (SRC_CONST, canonical residue mod the current prime)
+};
+static_assert(sizeof(Instr) == 16, "Instr must be 16 bytes");
+
+enum Op : uint8_t {
+  OP_HALT = 0,
+  OP_LOAD,    // ACC = SRC                      (F_PUSH: spill the old ACC first)
+  OP_ADD,     // ACC = ACC + SRC
+  OP_SUB,     // ACC = ACC - SRC                (F_SWAP: ACC = SRC - ACC)
+  OP_MUL,     // ACC = ACC * SRC
+  OP_SQR,     // ACC = ACC * ACC
+  OP_NEG,     // ACC = -ACC
+  OP_INV,     // ACC = 1/ACC with 1/0 := 0      (block-batched inversion)
+  OP_POWU,    // ACC = ACC ^ e, e = imm a residue, same for all lanes; FFInt::pow(const FFInt&) semantics
+  OP_NPOWU,   // ACC = ACC ^ -(int)e, e = imm;   FFInt::pow<int>(to_neg_int()) semantics
+  OP_POWL,    // ACC = ACC ^ SRC, exponent differs per lane (F_SWAP: ACC = SRC ^ ACC)
+  OP_NPOWL,   // ACC = ACC ^ -(int)SRC per lane  (F_SWAP likewise)
+  OP_STORE,   // out[arg][point] = canonical(ACC)
+  OP_MULADD,  // ACC = ACC * var[arg] + imm      (Horner step; src selects var/negvar for the factor)
+  OP_COUNT
+};
+
+enum Src : uint8_t {
+  SRC_NONE = 0,
+  SRC_POP,      // pop the spill stack
+  SRC_VAR,      // values[arg][point]
+  SRC_NEGVAR,   // -values[arg][point]
+  SRC_CONST,    // imm
+};
+
+enum Flags : uint8_t {
+  F_PUSH = 1,   // OP_LOAD: push ACC before loading
+  F_SWAP = 2,   // non-commutative ops: exchange the roles of ACC and SRC
+  F_NEGR = 4,   // negate the result (the parser's `!` and `;` operators)
+};
+
+}  // namespace ffgpu

@@ -1,0 +1,121 @@
+/* ffgpu.h -- C ABI of the B200 probe evaluator (libffgpu.so).
+ *
+ * The drop-in boundary for FireFly's black-box hot path.  Everything FireFly's
+ * Reconstructor asks of a parser-backed black box goes through these calls:
+ *
+ *   reference interface (jklappert/FireFly 2.0.3)                     replaced by
+ *   ---------------------------------------------------------------  -------------------------
+ *   ShuntingYardParser(file | strings, vars, check_is_equal)         ffgpu_compile_file /
+ *     source/include/firefly/ShuntingYardParser.hpp:44,52             ffgpu_compile / _text
+ *   ShuntingYardParser::precompute_tokens()  (prime_changed())       ffgpu_set_prime
+ *     source/ShuntingYardParser.cpp:550-591; BlackBoxBase.hpp:43-45
+ *   ShuntingYardParser::evaluate_pre<FFInt | FFIntVec<N>>(values)    ffgpu_eval
+ *     source/include/firefly/ShuntingYardParser.hpp:94-95,365-479
+ *     via BlackBoxBase::eval, BlackBoxBase.hpp:35-38; call sites
+ *     Reconstructor.hpp:3383,3440, MPIWorker.hpp:475
+ *   ShuntingYardParser::get_rp_function(i)                           ffgpu_rpn
+ *     source/ShuntingYardParser.cpp:534-536
+ *   primes()   source/ReconstHelper.cpp:24-125                       ffgpu_prime / ffgpu_n_primes
+ *
+ * Data layout: flat uint64_t residues, the layout std::vector<FFIntVec<N>> already has in
+ * memory ([variable][point], contiguous) and that MPIWorker ships over the wire
+ * (MPIWorker.hpp:213-228,479-501).  values[v * n_points + j] is variable v of point j,
+ * out[f * n_points + j] is function f at point j.
+ *
+ * Errors: no call throws or exits.  Failing calls return NULL / non-zero and leave a message
+ * for ffgpu_last_error() (thread local).  Where the reference prints ERROR_MSG and calls
+ * std::exit (unknown variable, unbalanced parentheses, empty function) compilation fails.
+ *
+ * Threads: ffgpu_eval is re-entrant; `thread_id` picks one of the per-thread stream/staging
+ * slots (Reconstructor calls the black box from thr_n pool threads, Reconstructor.hpp:2981).
+ * ffgpu_set_prime must not run concurrently with ffgpu_eval on the same tape -- the same
+ * contract prime_changed() has (called only after tp.kill_all(), Reconstructor.hpp:2403,2484).
+ *
+ * There is no CPU evaluation path: every ffgpu_eval* call runs the sm_100a kernels or fails.
+ */
+#ifndef FFGPU_H
+#define FFGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ffgpu_ctx ffgpu_ctx;     /* a set of GPUs + streams + staging */
+typedef struct ffgpu_tape ffgpu_tape;   /* a compiled collection, resident on every GPU of its ctx */
+
+enum { FFGPU_CHECK_IS_EQUAL = 1 };      /* flags for ffgpu_compile*: detect duplicate functions */
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* device_ids == NULL or n_devices == 0: the calling thread's current CUDA device. */
+ffgpu_ctx* ffgpu_create(const int* device_ids, int n_devices);
+void ffgpu_destroy(ffgpu_ctx*);
+int ffgpu_n_devices(const ffgpu_ctx*);
+const char* ffgpu_last_error(void);
+
+/* ---- compile ------------------------------------------------------------------------------ */
+/* ctx may be NULL: the handle then supports inspection (rpn, tape, work, set_prime) but refuses to
+ * evaluate -- used to test the tape compiler on machines without a GPU. */
+ffgpu_tape* ffgpu_compile(ffgpu_ctx*, const char* const* functions, size_t n_functions,
+                          const char* const* vars, size_t n_vars, unsigned flags);
+/* ';'-separated text with blanks/tabs/newlines ignored, as ShuntingYardParser reads a file */
+ffgpu_tape* ffgpu_compile_text(ffgpu_ctx*, const char* text, const char* const* vars, size_t n_vars, unsigned flags);
+ffgpu_tape* ffgpu_compile_file(ffgpu_ctx*, const char* path, const char* const* vars, size_t n_vars, unsigned flags);
+void ffgpu_tape_destroy(ffgpu_tape*);
+
+size_t ffgpu_n_vars(const ffgpu_tape*);
+size_t ffgpu_n_functions(const ffgpu_tape*);   /* distinct functions */
+size_t ffgpu_n_out(const ffgpu_tape*);         /* values per point that ffgpu_eval returns */
+size_t ffgpu_n_instr(const ffgpu_tape*);       /* tape length (without the terminators) */
+size_t ffgpu_stack_depth(const ffgpu_tape*);
+/* RPN of distinct function i, tokens joined by ' '; returns the length needed (without NUL) */
+size_t ffgpu_rpn(const ffgpu_tape*, size_t i, char* buf, size_t cap);
+/* copy up to cap 16-byte instructions of the resolved tape (layout: firefly_b200/csrc/tape.hpp) */
+size_t ffgpu_get_tape(const ffgpu_tape*, void* buf, size_t cap);
+/* algorithmic work of one probe counted on the reference's token list:
+ * w[0]=tokens w[1]=modular multiplications w[2]=add/sub/neg w[3]=inversions w[4]=max RPN stack depth */
+void ffgpu_work(const ffgpu_tape*, uint64_t w[5]);
+
+/* ---- prime -------------------------------------------------------------------------------- */
+/* p must be a prime of the form 2^63 - c, 0 < c < 2^15 (all 300 primes of FireFly's table are). */
+int ffgpu_set_prime(ffgpu_tape*, uint64_t p);
+uint64_t ffgpu_get_prime(const ffgpu_tape*);
+uint32_t ffgpu_n_primes(void);          /* 300 */
+uint64_t ffgpu_prime(uint32_t i);       /* the i-th largest prime below 2^63 */
+
+/* ---- evaluate ----------------------------------------------------------------------------- */
+/* HOST buffers.  values: [n_vars][n_points], out: [n_out][n_points].  Points are sharded over the
+ * GPUs of the ctx by contiguous index range, copies and kernels are pipelined in chunks. */
+int ffgpu_eval(ffgpu_tape*, const uint64_t* values, size_t n_points, uint64_t* out, uint32_t thread_id);
+/* DEVICE buffers on GPU `device_index` of the ctx, row strides in elements; launches on `stream`
+ * (a cudaStream_t, NULL = default stream) and returns without synchronising. */
+int ffgpu_eval_device(ffgpu_tape*, int device_index, const uint64_t* d_values, size_t in_stride, size_t n_points,
+                      uint64_t* d_out, size_t out_stride, void* stream);
+/* pinned host memory for ffgpu_eval buffers (pageable memory works too, slower) */
+void* ffgpu_host_alloc(size_t bytes);
+void ffgpu_host_free(void*);
+
+/* ---- tuning / measurement ----------------------------------------------------------------- */
+/* probes per thread (1, 2, 4; 0 = automatic) and threads per block (128, 256, 512; 0 = automatic) */
+int ffgpu_set_launch(ffgpu_tape*, int probes_per_thread, int threads_per_block);
+/* points per pipelined chunk of ffgpu_eval (0 = automatic) */
+int ffgpu_set_chunk(ffgpu_tape*, size_t points);
+/* kernels launched by this library in this process so far */
+uint64_t ffgpu_launch_count(void);
+/* synthetic probe points on the device: d_values[v*stride + j] = 1 + splitmix64(seed + v*total_points +
+ * first_point + j) mod (p-1), j < n_points */
+int ffgpu_fill_points(ffgpu_ctx*, int device_index, uint64_t* d_values, size_t n_vars, size_t n_points, size_t stride,
+                      uint64_t first_point, uint64_t total_points, uint64_t seed, uint64_t p, void* stream);
+/* d_sums[2f] = sum of row f mod p, d_sums[2f+1] = xor of row f */
+int ffgpu_checksum(ffgpu_ctx*, int device_index, const uint64_t* d_out, size_t n_out, size_t n_points, size_t stride,
+                   uint64_t p, uint64_t* d_sums, void* stream);
+/* device field arithmetic self test (tests only): r[i] = op(a[i], b[i]), HOST buffers.
+ * op: 0 add 1 sub 2 mul 3 neg 4 inverse(Fermat) 5 pow(residue exponent) 6 inverse(block batched)
+ *     7 pow(-(int)b) 8 canonical 9 1/(a*b) through the batched inverse */
+int ffgpu_field_ops(ffgpu_ctx*, int op, const uint64_t* a, const uint64_t* b, uint64_t* r, size_t n, uint64_t p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFGPU_H */

@@ -65,15 +65,16 @@ class mpz_class {
   mpz_class(unsigned x) { __gmpz_init_set_ui(v_, x); }
   mpz_class(unsigned long x) { __gmpz_init_set_ui(v_, x); }
   mpz_class(unsigned long long x) { __gmpz_init_set_ui(v_, (unsigned long)x); }
-  explicit mpz_class(const std::string& s, int base = 10) { init_str(s.c_str(), base); }
-  explicit mpz_class(const char* s, int base = 10) { init_str(s, base); }
+  // real gmpxx defaults to base 0 (0x / 0b / leading-0 octal prefixes are honoured)
+  explicit mpz_class(const std::string& s, int base = 0) { init_str(s.c_str(), base); }
+  explicit mpz_class(const char* s, int base = 0) { init_str(s, base); }
   ~mpz_class() { __gmpz_clear(v_); }
   mpz_class& operator=(const mpz_class& o) {
     if (this != &o) __gmpz_set(v_, o.v_);
     return *this;
   }
   mpz_class& operator=(const std::string& s) {
-    __gmpz_set_str(v_, s.c_str(), 10);
+    __gmpz_set_str(v_, s.c_str(), 0);
     return *this;
   }
   mpz_ptr get_mpz_t() { return v_; }
