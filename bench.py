@@ -1,0 +1,466 @@
+#!/usr/bin/env python
+"""bench.py -- probe-evaluation throughput of the B200 path, one JSON line.
+
+Workload (BASELINE.json configs[1]): the paper's benchmark functions f1-f4 as black boxes.
+One STEP = one pass of the hot path over one batch of synthetic probe points: each of f1, f2, f3,
+f4 evaluated at `--points` points mod p = 2^63 - 25 (one kernel launch per function).  Probes are
+independent, so N GPUs shard the point index range (weak scaling: every rank owns `--points`
+points per function); there is no collective on the data path.
+
+  value      probes/s over all ranks with the points already resident in HBM (device API),
+             CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks
+  e2e        the same metric through ffgpu_eval with HOST buffers (pinned), H2D and D2H inside the
+             timed region
+  roofline   the interpreter kernel against the measured integer-multiply-pipe peak
+             (profiles/r01_pipe_peak_v0.json; MEASURED_PEAKS.json has no integer peak) and HBM
+  cpu_baseline  the reference's own evaluate_pre (oracle/_ref, FFIntVec<128>, all host threads) or the
+             C port, on a bounded sample, rank 0 at N=1 only
+
+`--impl reference` times the reference's CPU implementation on the same metric/config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+FUNCS = ["f1", "f2", "f3", "f4"]
+P0 = 9223372036854775783
+SEED = 0x4D595DF4D0F33173
+METRIC = "mod_p_probe_evals_per_sec"
+UNIT = "probes/s"
+# multiply instructions per modular multiplication (4 product + 2 + 1 fold) and the
+# charge for one inversion in modular multiplications
+IMAD_PER_MM = 7
+MM_PER_INV = 6
+# pipe cycles: IMAD.WIDE issues at half the IMAD rate on B200 (profiles/r01_pipe_peak_v0.json), so the
+# 6 wide + 1 narrow multiplies of one MM occupy 13 IMAD slots
+SLOTS_PER_MM = 13
+
+
+def measured_int_peak():
+    """thread-instructions/s of 32-bit IMAD over the whole chip, measured by bench/pipe_peak.cu"""
+    path = os.path.join(ROOT, "profiles", "r01_pipe_peak_v0.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return d["pipes"]["imad_lo"]["gthread_inst_per_s"] * 1e9, "profiles/r01_pipe_peak_v0.json imad_lo"
+    except Exception:
+        return 148 * 64 * 1.965e9, "nominal 148 SM x 64 IMAD/clk x 1.965 GHz"
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)["hbm_gbs"], "MEASURED_PEAKS.json"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def work_of(par):
+    w = par.work()
+    mm_eq = w["mm"] + MM_PER_INV * w["inv"]
+    return w, mm_eq
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's own CPU evaluate_pre on this box's host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from firefly_b200 import workloads as W
+    import firefly_b200 as ff  # only for synthetic_points (host numpy twin of the device generator)
+    cores = os.cpu_count() or 1
+    from refs import have_ref
+    kind = "reference" if have_ref() else "port"
+    n = args.cpu_points
+    steps, warm = args.steps, args.warmup
+    pars, pts = [], []
+    if kind == "reference":
+        from refs import Ref
+        ref = Ref()
+        ref.set_prime(P0)
+        for name in FUNCS:
+            text, vars_ = W.benchmark(name)
+            pars.append(ref.parse([text], vars_))
+            pts.append(ff.synthetic_points(len(vars_), n, P0, seed=SEED))
+        run = lambda i: pars[i].eval(pts[i], bunch=128, threads=cores)
+        sample = f"{n} points per function, evaluate_pre<FFIntVec<128>>, {cores} threads"
+    else:
+        from oracle_bind import Oracle
+        orc = Oracle()
+        cores = 1
+        for name in FUNCS:
+            text, vars_ = W.benchmark(name)
+            pars.append(orc.parse([text], vars_, P0))
+            pts.append(ff.synthetic_points(len(vars_), n, P0, seed=SEED))
+        run = lambda i: pars[i].eval(pts[i])
+        sample = f"{n} points per function, scalar C port, 1 thread"
+    for _ in range(warm):
+        for i in range(len(FUNCS)):
+            run(i)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for i in range(len(FUNCS)):
+            run(i)
+    dt = time.perf_counter() - t0
+    value = steps * len(FUNCS) * n / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "f1-f4 black-box probes (BASELINE.json configs[1])", "functions": FUNCS,
+                   "prime": str(P0), "points_per_function_per_step": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=int, default=1 << 24, help="points per function per step per GPU (device-resident)")
+    ap.add_argument("--e2e-points", type=int, default=1 << 21, help="points per function per step per GPU (host buffers)")
+    ap.add_argument("--cpu-points", type=int, default=1 << 20, help="CPU baseline sample: points per function")
+    ap.add_argument("--k", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="also report the bunch-size sweep 1..4096 (host API latency)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import firefly_b200 as ff
+    from firefly_b200 import workloads as W
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = ff.Context()
+    n = args.points
+    stride = n + (n & 1)
+    stream = torch.cuda.current_stream().cuda_stream
+    total_points = n * world
+    pars, vals, outs, works = [], [], [], []
+    for name in FUNCS:
+        text, vars_ = W.benchmark(name)
+        par = ff.GpuParser(ctx, [text], vars_)
+        par.set_prime(P0)
+        par.set_launch(args.k, args.threads)
+        v = torch.empty((len(vars_), stride), dtype=torch.int64, device="cuda")
+        o = torch.empty((1, stride), dtype=torch.int64, device="cuda")
+        # this rank's shard of the global point index range, generated on the device
+        rc = ff.lib.ffgpu_fill_points(ctx.h, 0, v.data_ptr(), len(vars_), n, stride, rank * n, total_points, SEED, P0,
+                                      stream)
+        assert rc == 0, ff.last_error()
+        pars.append(par)
+        vals.append(v)
+        outs.append(o)
+        works.append(work_of(par))
+    torch.cuda.synchronize()
+
+    def step():
+        for par, v, o in zip(pars, vals, outs):
+            par.eval_device(v.data_ptr(), stride, n, o.data_ptr(), stride, stream=stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region: device-resident ------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(FUNCS) + 1)] for _ in range(args.steps)]
+    launches0 = ff.launch_count()
+    barrier()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for s in range(args.steps):
+        ev[s][0].record()
+        for i, (par, v, o) in enumerate(zip(pars, vals, outs)):
+            par.eval_device(v.data_ptr(), stride, n, o.data_ptr(), stride, stream=stream)
+            ev[s][i + 1].record()
+    t_end.record()
+    barrier()
+    launches = ff.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = t_start.elapsed_time(t_end)
+    per_fn_ms = [float(np.mean([ev[s][i].elapsed_time(ev[s][i + 1]) for s in range(args.steps)])) for i in range(len(FUNCS))]
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = args.steps * len(FUNCS) * n * world / (ms_total * 1e-3)
+
+    # ---- verification of what was just computed (rank-local sample against the oracle) ----------------------
+    verified = True
+    from oracle_bind import Oracle
+    orc = Oracle()
+    idx = np.unique(np.concatenate([np.arange(0, min(n, 2048)), np.arange(0, n, max(1, n // 2048)), [n - 1]]))
+    for name, par, v, o in zip(FUNCS, pars, vals, outs):
+        text, vars_ = W.benchmark(name)
+        host_pts = ff.synthetic_points(len(vars_), n, P0, seed=SEED, first_point=rank * n, total_points=total_points)[:, idx]
+        want = orc.parse([text], vars_, P0).eval(np.ascontiguousarray(host_pts))
+        got = o[:, :n].cpu().numpy().view(np.uint64)[:, idx]
+        if not np.array_equal(got, want):
+            verified = False
+    vt = torch.tensor([1 if verified else 0], device="cuda")
+    if world > 1:
+        dist.all_reduce(vt, op=dist.ReduceOp.MIN)
+    verified = bool(vt.item())
+
+    # ---- e2e: host buffers through the C ABI -------------------------------------------------------------------
+    ne = args.e2e_points
+    host_in, host_out, h2d, d2h = [], [], 0, 0
+    import ctypes as C
+    for name, par in zip(FUNCS, pars):
+        nv = par.n_vars
+        pin = ff.lib.ffgpu_host_alloc(nv * ne * 8)
+        pout = ff.lib.ffgpu_host_alloc(ne * 8)
+        assert pin and pout, ff.last_error()
+        arr = np.ctypeslib.as_array(C.cast(pin, C.POINTER(C.c_uint64)), shape=(nv, ne))
+        arr[:] = ff.synthetic_points(nv, ne, P0, seed=SEED + 1, first_point=rank * ne, total_points=ne * world)
+        host_in.append((pin, arr))
+        host_out.append((pout, np.ctypeslib.as_array(C.cast(pout, C.POINTER(C.c_uint64)), shape=(1, ne))))
+        h2d += nv * ne * 8
+        d2h += ne * 8
+
+    def e2e_step():
+        for par, (pin, _), (pout, _) in zip(pars, host_in, host_out):
+            par.eval_ptr(pin, ne, pout)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_l0 = ff.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    e2e_launches = ff.launch_count() - e2e_l0
+    te = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = e2e_steps * len(FUNCS) * ne * world / float(te.item())
+    # e2e results checked too
+    for name, par, (pin, arr), (pout, oarr) in zip(FUNCS, pars, host_in, host_out):
+        text, vars_ = W.benchmark(name)
+        sel = np.arange(0, ne, max(1, ne // 1024))
+        want = orc.parse([text], vars_, P0).eval(np.ascontiguousarray(arr[:, sel]))
+        if not np.array_equal(oarr[:, sel], want):
+            verified = False
+
+    # ---- bunch sweep (optional, rank 0) ----------------------------------------------------------------------------
+    sweep = None
+    if args.sweep and rank == 0:
+        sweep = {}
+        par = pars[3]
+        for b in [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096]:
+            pts = ff.synthetic_points(par.n_vars, b, P0, seed=b)
+            for _ in range(20):
+                par.evaluate_pre(pts)
+            t0 = time.perf_counter()
+            reps = 200
+            for _ in range(reps):
+                par.evaluate_pre(pts)
+            sweep[str(b)] = reps * b / (time.perf_counter() - t0)
+
+    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline(args.cpu_points)
+        except Exception as e:  # the baseline is a report, never a reason to lose the GPU numbers
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
+
+    if rank == 0:
+        peak_int, peak_src = measured_int_peak()
+        hbm_peak, hbm_src = measured_hbm_peak()
+        # dominant kernel: the launch with the largest share of the step
+        top = int(np.argmax(per_fn_ms))
+        w, mm_eq = works[top]
+        probes_per_s_top = n / (per_fn_ms[top] * 1e-3)
+        imad = probes_per_s_top * mm_eq * IMAD_PER_MM
+        bytes_per_probe = 8 * (pars[top].n_vars + 1)
+        per_fn = {}
+        for i, name in enumerate(FUNCS):
+            wi, mmi = works[i]
+            rate = n / (per_fn_ms[i] * 1e-3)
+            per_fn[name] = {
+                "ms": per_fn_ms[i], "probes_per_s": rate, "mm_eq_per_probe": mmi, "gmm_eq_per_s": rate * mmi / 1e9,
+                "imad_frac_of_measured": rate * mmi * IMAD_PER_MM / peak_int,
+                "pipe_slot_frac_of_measured": rate * mmi * SLOTS_PER_MM / peak_int,
+                "hbm_gbs": rate * 8 * (pars[i].n_vars + 1) / 1e9,
+            }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {
+                "workload": "f1-f4 black-box probes (BASELINE.json configs[1]): one step = f1,f2,f3,f4 each at "
+                            f"{n} points per GPU, p = 2^63-25",
+                "functions": FUNCS, "prime": str(P0), "points_per_function_per_step_per_gpu": n,
+                "parallelism": f"points sharded by index over {world} GPU(s), no collective",
+                "l2": "inputs larger than L2 (f1 %.0f MB, f2-f4 %.0f MB per launch); no flush needed" %
+                      (20 * 8 * n / 1e6, 5 * 8 * n / 1e6),
+                "launch": {"probes_per_thread": args.k or "auto", "threads_per_block": args.threads or "auto"},
+            },
+            "per_function": per_fn,
+            "verified_bit_exact_vs_oracle": verified,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "points_per_function_per_step_per_gpu": ne, "steps": e2e_steps, "gpu_launches": int(e2e_launches),
+                    "api": "ffgpu_eval (host pinned buffers, chunked H2D/kernel/D2H pipeline)"},
+            "roofline": {
+                "bound": "int_pipe", "kernel": f"eval_tape_kernel on {FUNCS[top]}",
+                "achieved": imad / 1e9, "peak": peak_int / 1e9, "unit": "G IMAD thread-inst/s",
+                "frac": imad / peak_int,
+                "pipe_slot_frac": probes_per_s_top * mm_eq * SLOTS_PER_MM / peak_int,
+                "peak_source": peak_src,
+                "algorithmic": {"mm": w["mm"], "inv": w["inv"], "ma": w["ma"], "mm_eq_per_probe": mm_eq,
+                                "imad_per_mm": IMAD_PER_MM, "mm_per_inv": MM_PER_INV,
+                                "pipe_slots_per_mm": SLOTS_PER_MM},
+                "hbm": {"achieved": probes_per_s_top * bytes_per_probe / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": probes_per_s_top * bytes_per_probe / 1e9 / hbm_peak, "peak_source": hbm_src,
+                        "bytes_per_probe": bytes_per_probe},
+                "traffic": None,
+            },
+            "cpu_baseline": cpu,
+        }
+        if sweep is not None:
+            line["bunch_sweep_f4_probes_per_s"] = sweep
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    if not verified:
+        raise SystemExit("verification against the oracle FAILED")
+
+
+def cpu_baseline(n):
+    """The reference's evaluate_pre on this host's cores, bounded sample (reported, not the target)."""
+    import firefly_b200 as ff
+    from firefly_b200 import workloads as W
+    from refs import have_ref
+    cores = os.cpu_count() or 1
+    t_total = 0.0
+    if have_ref():
+        from refs import Ref
+        ref = Ref()
+        ref.set_prime(P0)
+        for name in FUNCS:
+            text, vars_ = W.benchmark(name)
+            par = ref.parse([text], vars_)
+            pts = ff.synthetic_points(len(vars_), n, P0, seed=SEED)
+            par.eval(pts[:, : min(n, 1 << 14)], bunch=128, threads=cores)
+            best = 1e30
+            for _ in range(3):
+                t0 = time.perf_counter()
+                par.eval(pts, bunch=128, threads=cores)
+                best = min(best, time.perf_counter() - t0)
+            t_total += best
+        return {"value": len(FUNCS) * n / t_total, "unit": UNIT, "cores": cores, "kind": "reference",
+                "sample": f"{n} points per function of f1-f4, reference evaluate_pre<FFIntVec<128>> (DEFAULT arithmetic, "
+                          f"g++ -O3), {cores} threads, best of 3"}
+    from oracle_bind import Oracle
+    orc = Oracle()
+    n = min(n, 1 << 18)
+    for name in FUNCS:
+        text, vars_ = W.benchmark(name)
+        par = orc.parse([text], vars_, P0)
+        pts = ff.synthetic_points(len(vars_), n, P0, seed=SEED)
+        t0 = time.perf_counter()
+        par.eval(pts)
+        t_total += time.perf_counter() - t0
+    return {"value": len(FUNCS) * n / t_total, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n} points per function of f1-f4, scalar C port of evaluate_pre<FFInt>, 1 thread"}
+
+
+if __name__ == "__main__":
+    main()

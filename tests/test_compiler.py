@@ -1,0 +1,193 @@
+"""Host logic of the product without a GPU: the tape compiler against the golden vectors and the
+oracle (the tape is interpreted by tests/tape_interp.py), the C ABI's exports, error behaviour."""
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+import firefly_b200 as ff
+from conftest import ROOT, golden_names, load_golden
+from tape_interp import run
+
+P0 = 9223372036854775783
+
+
+def interp(par, pts, p):
+    tape = par.tape()
+    cols = [run(tape, [int(x) for x in pts[:, j]], p, par.n_out) for j in range(pts.shape[1])]
+    return np.array(cols, dtype=np.uint64).T.reshape(par.n_out, pts.shape[1])
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "ffgpu.h")).read()
+    declared = set(re.findall(r"\b(ffgpu_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(ff.EXPORTS)
+    for name in declared:
+        assert hasattr(ff.lib, name), name
+
+
+def test_no_gpu_means_no_evaluation():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(ff.FFGpuError):
+        ff.Context()
+    par = ff.GpuParser(None, ["x+1"], ["x"])
+    par.set_prime(P0)
+    with pytest.raises(ff.FFGpuError, match="no CPU path|no GPU"):
+        par.evaluate_pre(np.array([[1]], dtype=np.uint64))
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_compiler_matches_golden(name):
+    g = load_golden(name)
+    par = ff.GpuParser(None, g["functions"], g["vars"])
+    assert [par.get_rp_function(i) for i in range(par.n_functions)] == g["rpn"]
+    for case in g["cases"][:2]:
+        par.set_prime(case["prime"])
+        pts = case["points"]
+        n = pts.shape[1] if name != "s_y_4_v" else 4
+        assert np.array_equal(interp(par, pts[:, :n], case["prime"]), case["values"][:, :n]), name
+    par.close()
+
+
+def test_text_mode_and_file_mode(tmp_path):
+    text = " x + 1 ;\n\n y*\t2;;  ;x^2\n"
+    par = ff.GpuParser(None, text=text, vars=["x", "y"])
+    assert par.n_functions == 3 and par.n_out == 3
+    f = tmp_path / "funs.m"
+    f.write_text(text)
+    par2 = ff.GpuParser(None, file=str(f), vars=["x", "y"])
+    assert [par2.get_rp_function(i) for i in range(3)] == [par.get_rp_function(i) for i in range(3)]
+    with pytest.raises(ff.FFGpuError, match="does not exist"):
+        ff.GpuParser(None, file=str(tmp_path / "nope.m"), vars=["x"])
+
+
+@pytest.mark.parametrize("bad,msg", [
+    ("(x", "opening parentheses"), ("x)", "closing parentheses"), ("q+1", "not declared"),
+    ("x*", "lacks operands"), ("", "functional evaluation"), ("()", "functional evaluation"),
+    ("012345678901234567890+x", "cannot read integer"),
+])
+def test_errors_where_the_reference_exits(bad, msg):
+    with pytest.raises(ff.FFGpuError, match=msg):
+        ff.GpuParser(None, [bad], ["x"])
+
+
+def test_unsupported_primes_are_refused():
+    par = ff.GpuParser(None, ["x"], ["x"])
+    for p in (0, 2, (1 << 63) - (1 << 15), (1 << 63) + 29, 1 << 62):
+        with pytest.raises(ff.FFGpuError, match="prime"):
+            par.set_prime(p)
+    for p in ff.primes():
+        par.set_prime(p)
+
+
+def test_check_is_equal(oracle):
+    funs = ["x+y", "y+x", "x*y", "(x+y)", "x*y*1", "x-y"]
+    par = ff.GpuParser(None, funs, ["x", "y"], check_is_equal=True)
+    assert par.n_functions == 3 and par.n_out == 6
+    par.set_prime(P0)
+    pts = ff.synthetic_points(2, 3, P0)
+    want = oracle.parse(funs, ["x", "y"], P0, check_is_equal=True).eval(pts)
+    assert np.array_equal(interp(par, pts, P0), want)
+
+
+def test_spill_stack_is_shallow():
+    g = load_golden("s_y_4_v")
+    par = ff.GpuParser(None, g["functions"], g["vars"])
+    assert par.work()["max_rpn_depth"] == 23      # the reference's std::stack grows to 23
+    assert par.stack_depth <= 4                   # the accumulator tape needs 4 spill slots
+
+
+def test_work_counts_of_the_benchmarks():
+    from firefly_b200 import workloads as W
+    want = {"f1": (159, 201, 38, 1), "f2": (33, 39, 3, 1), "f3": (31, 14, 8, 1), "f4": (31, 14, 8, 1)}
+    for name, (tok, mm, ma, inv) in want.items():
+        text, vars_ = W.benchmark(name)
+        w = ff.GpuParser(None, [text], vars_).work()
+        assert (w["tokens"], w["mm"], w["ma"], w["inv"]) == (tok, mm, ma, inv), name
+
+
+def test_workloads_equal_reference_files():
+    from firefly_b200 import workloads as W
+    for name in W.BENCHMARKS:
+        g = load_golden(name)
+        text, vars_ = W.benchmark(name)
+        assert vars_ == g["vars"]
+        assert ff.GpuParser(None, [text], vars_).get_rp_function(0) == g["rpn"][0], name
+
+
+def test_random_expressions_vs_oracle(oracle):
+    rng = random.Random(3)
+    vars_ = ["a", "b", "c1"]
+
+    def atom():
+        r = rng.random()
+        if r < 0.45:
+            return rng.choice(vars_)
+        if r < 0.8:
+            return str(rng.randint(0, 10 ** rng.randint(1, 17)))
+        return str(rng.randint(10 ** 18, 10 ** 25))
+
+    def expr(d):
+        if d == 0 or rng.random() < 0.2:
+            return atom()
+        r = rng.random()
+        if r < 0.5:
+            return f"{expr(d-1)}{rng.choice('+-*/')}{expr(d-1)}"
+        if r < 0.62:
+            return f"({expr(d-1)})"
+        if r < 0.72:
+            return f"({expr(d-1)})^{rng.randint(0, 40)}"
+        if r < 0.79:
+            return f"{atom()}^(-{rng.randint(1, 9)})"
+        if r < 0.84:
+            return f"(-{atom()})^{rng.randint(1, 5)}"
+        if r < 0.88:
+            return f"(-({expr(d-1)}))"
+        if r < 0.92:
+            return f"({expr(d-1)})^({rng.choice(vars_)})"            # lane-dependent exponent
+        if r < 0.95:
+            return f"({expr(d-1)})^(-{rng.choice(vars_)})"
+        if r < 0.97:
+            return f"({expr(d-1)})^({expr(1)})"
+        return f"(-{rng.choice(vars_)}^{rng.randint(2, 7)}+{expr(d-1)})"
+
+    funs = [expr(4) for _ in range(150)]
+    for p in (P0, ff.primes()[17]):
+        op = oracle.parse(funs, vars_, p)
+        par = ff.GpuParser(None, funs, vars_)
+        par.set_prime(p)
+        assert [par.get_rp_function(i) for i in range(len(funs))] == [op.rpn(i) for i in range(len(funs))]
+        pts = ff.synthetic_points(3, 5, p, seed=9)
+        pts[:, 0] = 0
+        pts[:, 1] = np.array([1, p - 1, 2], dtype=np.uint64)
+        assert np.array_equal(interp(par, pts, p), op.eval(pts))
+
+
+def test_deep_nesting_does_not_recurse(oracle):
+    n = 20000
+    horner = "x"
+    for i in range(n):
+        horner = f"({horner})*x+{i % 97}"
+    par = ff.GpuParser(None, [horner], ["x"])
+    par.set_prime(P0)
+    pts = np.array([[12345]], dtype=np.uint64)
+    assert np.array_equal(interp(par, pts, P0), oracle.parse([horner], ["x"], P0).eval(pts))
+    deep = "(" * 5000 + "x" + "+1)" * 5000
+    par = ff.GpuParser(None, [deep], ["x"])
+    par.set_prime(P0)
+    assert int(interp(par, pts, P0)[0, 0]) == 12345 + 5000
+
+
+def test_synthetic_points_are_canonical_nonzero():
+    for p in (P0, ff.primes()[299]):
+        pts = ff.synthetic_points(4, 1000, p)
+        assert pts.min() >= 1 and pts.max() < p
+    a = ff.synthetic_points(3, 100, P0, first_point=0, total_points=200)
+    b = ff.synthetic_points(3, 100, P0, first_point=100, total_points=200)
+    full = ff.synthetic_points(3, 200, P0)
+    assert np.array_equal(np.concatenate([a, b], axis=1), full)

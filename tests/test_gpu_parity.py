@@ -1,0 +1,248 @@
+"""Parity tests proper: the sm_100a path through the C ABI against the oracle, the committed golden
+vectors and size-independent properties.  All bit-exact (integer arithmetic)."""
+import random
+import threading
+
+import numpy as np
+import pytest
+
+import firefly_b200 as ff
+from conftest import golden_names, load_golden
+from firefly_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+P0 = 9223372036854775783
+
+
+# ---- device field arithmetic against Python integers -------------------------------------------------
+def _edge_values(p, rng, n):
+    edge = [0, 1, 2, 3, p - 1, p - 2, p, p + 1, 2 * p, 2 * p + 1, (1 << 64) - 1, (1 << 64) - 2, (1 << 63),
+            (1 << 63) - 1, (1 << 32), (1 << 32) - 1, 0xFFFFFFFF00000000, p >> 1, (p >> 1) + 1]
+    vals = edge + [rng.randrange(1 << 64) for _ in range(n)] + [rng.randrange(p) for _ in range(n)]
+    return vals
+
+
+@pytest.mark.parametrize("pi", [0, 1, 150, 299])
+def test_field_ops_lazy_inputs(ctx, pi):
+    """add/sub/mul/neg/canon accept ANY 64-bit representative (lazy residues)."""
+    p = ff.primes()[pi]
+    rng = random.Random(pi)
+    vals = _edge_values(p, rng, 2000)
+    a = np.array([rng.choice(vals) for _ in range(20000)], dtype=np.uint64)
+    b = np.array([rng.choice(vals) for _ in range(20000)], dtype=np.uint64)
+    ai, bi = [int(x) for x in a], [int(x) for x in b]
+    for op, fn in [(0, lambda x, y: (x + y) % p), (1, lambda x, y: (x - y) % p), (2, lambda x, y: x * y % p),
+                   (3, lambda x, y: (-x) % p), (8, lambda x, y: x % p)]:
+        got = ctx.field_ops(op, a, b, p)
+        want = np.array([fn(x, y) for x, y in zip(ai, bi)], dtype=np.uint64)
+        assert np.array_equal(got, want), f"op {op} prime {p}"
+
+
+@pytest.mark.parametrize("pi", [0, 299])
+def test_field_inverse_and_powers(ctx, pi):
+    p = ff.primes()[pi]
+    rng = random.Random(100 + pi)
+    vals = _edge_values(p, rng, 500)
+    a = np.array([rng.choice(vals) for _ in range(3000)], dtype=np.uint64)
+    e = np.array([rng.choice([0, 1, 2, 3, 20, p - 1, p - 2, p - 3, (p >> 1), (p >> 1) - 1, 0xFFFFFFFE, 0x80000001,
+                              rng.randrange(p), rng.randrange(1000)]) for _ in range(3000)], dtype=np.uint64)
+    ai, ei = [int(x) for x in a], [int(x) for x in e]
+    inv = lambda x: pow(x % p, p - 2, p)
+    assert np.array_equal(ctx.field_ops(4, a, a, p), np.array([inv(x) for x in ai], dtype=np.uint64))
+    assert np.array_equal(ctx.field_ops(6, a, a, p), np.array([inv(x) for x in ai], dtype=np.uint64))
+    want9 = np.array([inv(x) * inv(y) % p for x, y in zip(ai, ei)], dtype=np.uint64)
+    assert np.array_equal(ctx.field_ops(9, a, e, p), want9)
+    from tape_interp import pow_ff, pow_int, to_neg_int
+    want5 = np.array([pow_ff(x % p, y % p, p) for x, y in zip(ai, ei)], dtype=np.uint64)
+    assert np.array_equal(ctx.field_ops(5, a, e, p), want5)
+    want7 = np.array([pow_int(x % p, to_neg_int(y % p), p) for x, y in zip(ai, ei)], dtype=np.uint64)
+    assert np.array_equal(ctx.field_ops(7, a, e, p), want7)
+
+
+# ---- golden vectors ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names())
+def test_gpu_matches_golden(ctx, name):
+    g = load_golden(name)
+    par = ff.GpuParser(ctx, g["functions"], g["vars"])
+    for case in g["cases"]:
+        par.set_prime(case["prime"])
+        got = par.evaluate_pre(case["points"])
+        assert np.array_equal(got, case["values"]), (name, case["prime"])
+        # bunch of one, the reference's configs[0] way of calling the black box
+        for j in range(case["points"].shape[1]):
+            one = par.evaluate_pre(case["points"][:, j])
+            assert np.array_equal(one, case["values"][:, j]), (name, j)
+    par.close()
+
+
+# ---- oracle on seeded inputs, every launch shape --------------------------------------------------------
+@pytest.mark.parametrize("name", ["s_y_4_v", "edge_cases", "f4", "f1"])
+@pytest.mark.parametrize("k,threads", [(0, 0), (1, 128), (1, 256), (1, 512), (2, 128), (2, 256), (2, 512),
+                                       (4, 128), (4, 256), (4, 512)])
+def test_gpu_matches_oracle_all_shapes(ctx, oracle, name, k, threads):
+    g = load_golden(name)
+    p = ff.primes()[2]
+    par = ff.GpuParser(ctx, g["functions"], g["vars"])
+    par.set_prime(p)
+    par.set_launch(k, threads)
+    op = oracle.parse(g["functions"], g["vars"], p)
+    for n in (1, 2, 3, 31, 257, 1000, 2049):
+        pts = ff.synthetic_points(par.n_vars, n, p, seed=n)
+        if n >= 3:
+            pts[:, 1] = 0                      # zero divisors / zero bases inside a batch of good lanes
+            pts[0, 2] = p - 1
+        assert np.array_equal(par.evaluate_pre(pts), op.eval(pts)), (name, n, k, threads)
+    par.close()
+
+
+def test_gpu_random_expressions_vs_oracle(ctx, oracle):
+    rng = random.Random(21)
+    vars_ = ["a", "b", "c1", "d"]
+
+    def atom():
+        r = rng.random()
+        if r < 0.5:
+            return rng.choice(vars_)
+        if r < 0.85:
+            return str(rng.randint(0, 10 ** rng.randint(1, 17)))
+        return str(rng.randint(10 ** 18, 10 ** 25))
+
+    def expr(d):
+        if d == 0 or rng.random() < 0.2:
+            return atom()
+        r = rng.random()
+        if r < 0.5:
+            return f"{expr(d-1)}{rng.choice('+-*/')}{expr(d-1)}"
+        if r < 0.6:
+            return f"({expr(d-1)})"
+        if r < 0.72:
+            return f"({expr(d-1)})^{rng.randint(0, 40)}"
+        if r < 0.8:
+            return f"{atom()}^(-{rng.randint(1, 9)})"
+        if r < 0.85:
+            return f"(-{atom()})^{rng.randint(1, 5)}"
+        if r < 0.9:
+            return f"(-({expr(d-1)}))"
+        if r < 0.93:
+            return f"({expr(d-1)})^({rng.choice(vars_)})"
+        if r < 0.96:
+            return f"({expr(d-1)})^(-{rng.choice(vars_)})"
+        return f"(-{rng.choice(vars_)}^{rng.randint(2, 7)}+{expr(d-1)})"
+
+    funs = [expr(5) for _ in range(400)]
+    for p in (P0, ff.primes()[123]):
+        op = oracle.parse(funs, vars_, p)
+        par = ff.GpuParser(ctx, funs, vars_)
+        par.set_prime(p)
+        pts = ff.synthetic_points(4, 700, p, seed=33)
+        pts[:, 0] = 0
+        pts[:, 1] = np.array([1, p - 1, 2, 0], dtype=np.uint64)
+        pts[1, 5:40] = np.arange(35, dtype=np.uint64)             # small lane exponents
+        assert np.array_equal(par.evaluate_pre(pts), op.eval(pts))
+        par.close()
+
+
+def test_check_is_equal_and_prime_change(ctx, oracle):
+    funs = ["x+y", "y+x", "x*y/3", "(x+y)", "x*y/3*1", "x-y/7"]
+    par = ff.GpuParser(ctx, funs, ["x", "y"], check_is_equal=True)
+    assert par.n_functions == 3 and par.n_out == 6
+    for p in ff.primes()[:5]:
+        par.set_prime(p)                       # prime_changed(): constants only
+        pts = ff.synthetic_points(2, 100, p)
+        want = oracle.parse(funs, ["x", "y"], p, check_is_equal=True).eval(pts)
+        assert np.array_equal(par.evaluate_pre(pts), want)
+
+
+def test_concurrent_callers(ctx, oracle):
+    """Reconstructor calls the black box from thr_n threads at once (Reconstructor.hpp:2981)."""
+    g = load_golden("s_y_4_v")
+    par = ff.GpuParser(ctx, g["functions"], g["vars"])
+    par.set_prime(P0)
+    op = oracle.parse(g["functions"], g["vars"], P0)
+    errs = []
+
+    def worker(tid):
+        try:
+            for it in range(20):
+                n = [1, 4, 128, 77][it % 4]
+                pts = ff.synthetic_points(4, n, P0, seed=1000 * tid + it)
+                got = par.evaluate_pre(pts, thread_id=tid)
+                if not np.array_equal(got, op.eval(pts)):
+                    errs.append((tid, it))
+        except Exception as e:  # pragma: no cover
+            errs.append((tid, repr(e)))
+
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(12)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+
+
+# ---- full-size properties ----------------------------------------------------------------------------
+def test_large_batch_sample_and_properties(ctx, oracle):
+    """2^22 points of f4 through the chunked host path: a strided sample against the oracle, and the
+    identity N(x)/D(x) * D(x) == N(x) for every point (size-independent, catches any lane mix-up)."""
+    text, vars_ = W.benchmark("f4")
+    p = P0
+    n = 1 << 22
+    par = ff.GpuParser(ctx, [text, "(1+x1+x2+x3+x4+x5)^20-1", "x4-x2+(x1*x2*x3*x4*x5)^10"], vars_)
+    par.set_prime(p)
+    par.set_chunk(1 << 19)
+    pts = ff.synthetic_points(5, n, p, seed=77)
+    out = par.evaluate_pre(pts)
+    idx = np.arange(0, n, 4099)
+    op = oracle.parse([text, "(1+x1+x2+x3+x4+x5)^20-1", "x4-x2+(x1*x2*x3*x4*x5)^10"], vars_, p)
+    assert np.array_equal(out[:, idx], op.eval(np.ascontiguousarray(pts[:, idx])))
+    # q * D == N for all points where D != 0 (object arrays: exact integers)
+    q, N, D = (out[i].astype(object) for i in range(3))
+    assert np.all((q * D - N) % p == 0)
+    par.close()
+
+
+def test_device_resident_path_and_checksum(ctx, oracle):
+    import torch
+    text, vars_ = W.benchmark("f3")
+    p = ff.primes()[4]
+    par = ff.GpuParser(ctx, [text], vars_)
+    par.set_prime(p)
+    for n in (1 << 16, (1 << 16) + 1, 12345):
+        stride = n + (n & 1)
+        vals = torch.empty((5, stride), dtype=torch.int64, device="cuda")
+        out = torch.zeros((1, stride), dtype=torch.int64, device="cuda")
+        s = torch.cuda.current_stream().cuda_stream
+        assert ff.lib.ffgpu_fill_points(ctx.h, 0, vals.data_ptr(), 5, n, stride, 0, n, 99, p, s) == 0
+        par.eval_device(vals.data_ptr(), stride, n, out.data_ptr(), stride, stream=s)
+        sums = torch.zeros(2, dtype=torch.int64, device="cuda")
+        assert ff.lib.ffgpu_checksum(ctx.h, 0, out.data_ptr(), 1, n, stride, p, sums.data_ptr(), s) == 0
+        torch.cuda.synchronize()
+        host_pts = ff.synthetic_points(5, n, p, seed=99)
+        assert np.array_equal(vals[:, :n].cpu().numpy().view(np.uint64), host_pts)
+        want = oracle.parse([text], vars_, p).eval(host_pts)
+        got = out[:, :n].cpu().numpy().view(np.uint64)
+        assert np.array_equal(got, want)
+        sm = sums.cpu().numpy().view(np.uint64)
+        assert int(sm[0]) == sum(int(x) for x in want[0]) % p
+        assert int(sm[1]) == int(np.bitwise_xor.reduce(want[0]))
+
+
+def test_ibp_like_collection(ctx, oracle):
+    funs, vars_ = W.ibp_like_collection(600, 8, seed=5)
+    p = P0
+    par = ff.GpuParser(ctx, funs, vars_)
+    par.set_prime(p)
+    op = oracle.parse(funs, vars_, p)
+    pts = ff.synthetic_points(8, 513, p, seed=4)
+    pts[:, 7] = 0
+    assert np.array_equal(par.evaluate_pre(pts), op.eval(pts))
+
+
+def test_empty_batch_and_missing_prime(ctx):
+    par = ff.GpuParser(ctx, ["x"], ["x"])
+    with pytest.raises(ff.FFGpuError, match="set_prime"):
+        par.evaluate_pre(np.array([[1]], dtype=np.uint64))
+    par.set_prime(P0)
+    out = par.evaluate_pre(np.zeros((1, 0), dtype=np.uint64))
+    assert out.shape == (1, 0)
+    n0 = ff.launch_count()
+    par.evaluate_pre(np.array([[5]], dtype=np.uint64))
+    assert ff.launch_count() == n0 + 1
