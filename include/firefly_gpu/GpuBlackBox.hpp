@@ -1,0 +1,131 @@
+// GpuBlackBox.hpp -- header-only C++ adaptor: a FireFly black box whose evaluation runs on B200s.
+//
+// Drop-in for the parser-backed black boxes FireFly users write, e.g. the one in the reference's
+// benchmarks/benchmarks.cpp:22-38 or AmplitudeParser.hpp:45-68 (FFAmplitudeBlackBox):
+//
+//     class BlackBoxUser : public BlackBoxBase<BlackBoxUser> {
+//       template<typename FFIntTemp> std::vector<FFIntTemp> operator()(const std::vector<FFIntTemp>& values)
+//         { return par.evaluate_pre(values); }
+//       void prime_changed() { par.precompute_tokens(); }
+//       ShuntingYardParser par;
+//     };
+//
+// becomes   firefly::GpuBlackBox bb(file, vars);   Reconstructor<GpuBlackBox> reconst(n, threads, bunch, bb);
+//
+// Keeps the 2.0.3 plugin boundary (reference: source/include/firefly/BlackBoxBase.hpp:35-45):
+// operator()(values) for FFInt and every FFIntVec<N>, prime_changed().  Adds the forward-compatible
+// operator()(values, thread_id) and set_bunch_size() named by newer FireFly interfaces.
+//
+// Zero-copy at the boundary: FFInt is a single uint64_t (FFInt.hpp:89) and FFIntVec<N> a
+// std::array<FFInt, N> (FFIntVec.hpp:32-109), so std::vector<FFIntVec<N>>(n) IS the [variable][lane]
+// uint64 matrix ffgpu_eval wants.
+//
+// Errors follow the reference's convention for this path: ERROR_MSG + std::exit(EXIT_FAILURE)
+// (ShuntingYardParser.hpp:454-459).
+#pragma once
+#include <cstdint>
+#include <cstdlib>
+#include <functional>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "firefly/BlackBoxBase.hpp"
+#include "firefly/FFInt.hpp"
+#include "firefly/FFIntVec.hpp"
+#include "firefly/Logger.hpp"
+
+#include "../ffgpu.h"
+
+namespace firefly {
+
+class GpuBlackBox : public BlackBoxBase<GpuBlackBox> {
+ public:
+  // functions in a ';'-separated file, like ShuntingYardParser(file, vars, check_is_equal)
+  GpuBlackBox(const std::string& file, const std::vector<std::string>& vars, bool check_is_equal = false,
+              const std::vector<int>& devices = {}) {
+    init(devices);
+    std::vector<const char*> v = c_strs(vars);
+    tape_ = ffgpu_compile_file(ctx_, file.c_str(), v.data(), v.size(), check_is_equal ? FFGPU_CHECK_IS_EQUAL : 0);
+    finish();
+  }
+  // functions as strings, like ShuntingYardParser(funs, vars, check_is_equal)
+  GpuBlackBox(const std::vector<std::string>& funs, const std::vector<std::string>& vars, bool check_is_equal = false,
+              const std::vector<int>& devices = {}) {
+    init(devices);
+    std::vector<const char*> f = c_strs(funs), v = c_strs(vars);
+    tape_ = ffgpu_compile(ctx_, f.data(), f.size(), v.data(), v.size(), check_is_equal ? FFGPU_CHECK_IS_EQUAL : 0);
+    finish();
+  }
+  GpuBlackBox(const GpuBlackBox&) = delete;
+  GpuBlackBox& operator=(const GpuBlackBox&) = delete;
+  ~GpuBlackBox() {
+    if (tape_) ffgpu_tape_destroy(tape_);
+    if (ctx_) ffgpu_destroy(ctx_);
+  }
+
+  // FireFly 2.0.3 signature.  Called concurrently from the Reconstructor's thread pool
+  // (Reconstructor.hpp:2981-2983); each calling thread is mapped to its own stream slot.
+  template <typename FFIntTemp>
+  std::vector<FFIntTemp> operator()(const std::vector<FFIntTemp>& values) {
+    const uint32_t slot = (uint32_t)std::hash<std::thread::id>()(std::this_thread::get_id());
+    return (*this)(values, slot);
+  }
+
+  template <typename FFIntTemp>
+  std::vector<FFIntTemp> operator()(const std::vector<FFIntTemp>& values, uint32_t thread_id) {
+    static_assert(sizeof(FFInt) == sizeof(uint64_t), "FFInt must be one 64-bit residue");
+    static_assert(sizeof(FFIntTemp) % sizeof(uint64_t) == 0, "bunch type must be an array of FFInt");
+    constexpr size_t lanes = sizeof(FFIntTemp) / sizeof(uint64_t);      // 1 for FFInt, N for FFIntVec<N>
+    if (values.size() != n_vars_) die("black box called with a wrong number of variables");
+    std::vector<FFIntTemp> result(n_out_);
+    if (ffgpu_eval(tape_, reinterpret_cast<const uint64_t*>(values.data()), lanes,
+                   reinterpret_cast<uint64_t*>(result.data()), thread_id))
+      die(ffgpu_last_error());
+    return result;
+  }
+
+  // Reconstructor calls this after FFInt::set_new_prime (Reconstructor.hpp:2483-2484), never
+  // concurrently with operator().  Same job as par.precompute_tokens(): refresh the constants.
+  void prime_changed() {
+    if (ffgpu_set_prime(tape_, FFInt::p)) die(ffgpu_last_error());
+  }
+
+  // The bunch size is a Reconstructor constructor argument in 2.0.3 (Reconstructor.hpp:73); the GPU
+  // evaluator accepts any batch, so this only records the hint.
+  void set_bunch_size(uint32_t bunch) { bunch_hint_ = bunch; }
+  uint32_t bunch_size() const { return bunch_hint_; }
+
+  size_t n_vars() const { return n_vars_; }
+  size_t n_out() const { return n_out_; }
+  ffgpu_tape* handle() { return tape_; }
+
+ private:
+  static std::vector<const char*> c_strs(const std::vector<std::string>& s) {
+    std::vector<const char*> v;
+    v.reserve(s.size());
+    for (const auto& x : s) v.push_back(x.c_str());
+    return v;
+  }
+  [[noreturn]] static void die(const std::string& msg) {
+    ERROR_MSG(msg);
+    std::exit(EXIT_FAILURE);
+  }
+  void init(const std::vector<int>& devices) {
+    ctx_ = ffgpu_create(devices.empty() ? nullptr : devices.data(), (int)devices.size());
+    if (!ctx_) die(ffgpu_last_error());
+  }
+  void finish() {
+    if (!tape_) die(ffgpu_last_error());
+    n_vars_ = ffgpu_n_vars(tape_);
+    n_out_ = ffgpu_n_out(tape_);
+    prime_changed();      // ShuntingYardParser's constructor precomputes for the current prime (:181)
+  }
+
+  ffgpu_ctx* ctx_ = nullptr;
+  ffgpu_tape* tape_ = nullptr;
+  size_t n_vars_ = 0, n_out_ = 0;
+  uint32_t bunch_hint_ = 1;
+};
+
+}  // namespace firefly

@@ -1,0 +1,35 @@
+"""Identical reconstructions (BASELINE.json configs[0], configs[4]): the unmodified reference
+Reconstructor run over the reference CPU black box and over firefly::GpuBlackBox must return the same
+rational functions.  Uses oracle/_ref/gpu_reconstruct (built from oracle/gpu_reconstruct.cpp where the
+reference sources are available; the binary travels to the GPU box)."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT, load_golden
+
+pytestmark = pytest.mark.gpu
+BIN = os.path.join(ROOT, "oracle", "_ref", "gpu_reconstruct")
+
+
+@pytest.mark.parametrize("name,bunch,threads", [
+    ("s_y_4_v", 1, 4),       # configs[0]: s_y_4_v.m, bunch_size = 1
+    ("s_y_4_v", 4, 4),       # the reference's test_bunch.cpp setting
+    ("s_y_1_v", 128, 2),
+    ("f1", 64, 4),
+    ("factors3", 16, 4),
+])
+def test_reconstruction_identical(tmp_path, name, bunch, threads):
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/gpu_reconstruct not built (needs /root/reference at build time)")
+    g = load_golden(name)
+    f = tmp_path / (name + ".m")
+    f.write_text(";\n".join(g["functions"]) + ";\n")
+    r = subprocess.run([BIN, str(f), str(bunch), str(threads), *g["vars"]], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "0 differ" in r.stdout
+    # the GPU black box really ran on the GPU
+    launches = int(r.stdout.strip().split()[-1])
+    assert launches > 0
