@@ -29,7 +29,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libffgpu.so")
 
 INSTR_DTYPE = np.dtype(
-    [("op", "u1"), ("src", "u1"), ("flags", "u1"), ("rsv", "u1"), ("arg", "<u4"), ("imm", "<u8")]
+    [("op", "u1"), ("src", "u1"), ("flags", "u1"), ("fast", "u1"), ("arg", "<u4"), ("imm", "<u8")]
 )
 # tape.hpp
 OPS = ["HALT", "LOAD", "ADD", "SUB", "MUL", "SQR", "NEG", "INV", "POWU", "NPOWU", "POWL", "NPOWL", "STORE", "MULADD"]

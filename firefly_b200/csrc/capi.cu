@@ -343,7 +343,7 @@ int ffgpu_set_prime(ffgpu_tape* t, uint64_t p) {
 }
 
 int ffgpu_set_launch(ffgpu_tape* t, int k, int threads) {
-  if (!(k == 0 || k == 1 || k == 2 || k == 4)) return fail("probes_per_thread must be 0, 1, 2 or 4");
+  if (!(k == 0 || k == 1 || k == 2 || k == 4 || k == 8)) return fail("probes_per_thread must be 0, 1, 2, 4 or 8");
   if (!(threads == 0 || threads == 128 || threads == 256 || threads == 512))
     return fail("threads_per_block must be 0, 128, 256 or 512");
   t->force_k = k;

@@ -402,7 +402,7 @@ struct Emitter {
     const Node& n = f.nodes[i];
     if (n.is_const) {
       ins.src = SRC_CONST;
-      patches.push_back(ConstPatch{(uint32_t)tape.size(), fn, i, inverse});
+      patches.push_back(ConstPatch{(uint32_t)tape.size(), fn, i, inverse, false});
     } else {
       ins.src = n.kind == N_VAR ? SRC_VAR : SRC_NEGVAR;
       ins.arg = n.var;
@@ -461,7 +461,7 @@ void Collection::emit_function(uint32_t fn, const std::vector<uint32_t>& out_slo
         Instr ins = Emitter::mk((n.kind == N_POW || n.kind == N_POWNEG) ? OP_POWU : OP_NPOWU,
                                 (n.kind == N_POWNEG || n.kind == N_NEGPOWNEG) ? F_NEGR : 0);
         ins.src = SRC_CONST;
-        patches.push_back(ConstPatch{(uint32_t)tape.size(), fn, n.r, false});
+        patches.push_back(ConstPatch{(uint32_t)tape.size(), fn, n.r, false, false});
         em.put(ins);
         continue;
       }
@@ -469,7 +469,7 @@ void Collection::emit_function(uint32_t fn, const std::vector<uint32_t>& out_slo
         const Node& n = f.nodes[it.node];
         Instr ins = Emitter::mk(OP_MUL);
         ins.src = SRC_CONST;
-        patches.push_back(ConstPatch{(uint32_t)tape.size(), fn, n.r, true});
+        patches.push_back(ConstPatch{(uint32_t)tape.size(), fn, n.r, true, false});
         em.put(ins);
         continue;
       }
@@ -593,6 +593,7 @@ bool Collection::finish(std::string& err) {
     emit_function((uint32_t)i, slots[i]);
     count_work(functions[i]);
   }
+  peephole();
   Instr halt{};
   halt.op = OP_HALT;
   tape.push_back(halt);
@@ -600,6 +601,54 @@ bool Collection::finish(std::string& err) {
   prime = 0;
   chk_map_.clear();
   return true;
+}
+
+// Strength reduction on the finished tape and assignment of the dense dispatch codes.
+void Collection::peephole() {
+  std::vector<int32_t> patch_of(tape.size(), -1);
+  for (size_t i = 0; i < patches.size(); ++i) patch_of[patches[i].instr] = (int32_t)i;
+  for (size_t i = 0; i < tape.size(); ++i) {
+    Instr& in = tape[i];
+    // acc - c  ->  acc + (-c);   acc + (-v) -> acc - v;   acc - (-v) -> acc + v
+    if (in.op == OP_SUB && in.src == SRC_CONST && !(in.flags & F_SWAP) && patch_of[i] >= 0) {
+      in.op = OP_ADD;
+      patches[patch_of[i]].negate = !patches[patch_of[i]].negate;
+    } else if (in.op == OP_ADD && in.src == SRC_NEGVAR) {
+      in.op = OP_SUB;
+      in.src = SRC_VAR;
+    } else if (in.op == OP_SUB && in.src == SRC_NEGVAR && !(in.flags & F_SWAP)) {
+      in.op = OP_ADD;
+      in.src = SRC_VAR;
+    }
+    uint8_t fx = FX_GENERIC;
+    const bool swap = in.flags & F_SWAP, push = in.flags & F_PUSH;
+    const uint8_t other = in.flags & ~(F_SWAP | F_PUSH);
+    if (!other) {
+      switch (in.op) {
+        case OP_LOAD:
+          if (in.src == SRC_VAR) fx = push ? FX_PUSH_LOAD_VAR : FX_LOAD_VAR;
+          else if (in.src == SRC_CONST) fx = push ? FX_PUSH_LOAD_CONST : FX_LOAD_CONST;
+          break;
+        case OP_ADD:
+          fx = in.src == SRC_VAR ? FX_ADD_VAR : in.src == SRC_CONST ? FX_ADD_CONST : in.src == SRC_POP ? FX_ADD_POP : FX_GENERIC;
+          break;
+        case OP_SUB:
+          if (in.src == SRC_VAR) fx = swap ? FX_RSUB_VAR : FX_SUB_VAR;
+          else if (in.src == SRC_CONST && swap) fx = FX_RSUB_CONST;
+          else if (in.src == SRC_POP) fx = swap ? FX_RSUB_POP : FX_SUB_POP;
+          break;
+        case OP_MUL:
+          fx = in.src == SRC_VAR ? FX_MUL_VAR : in.src == SRC_CONST ? FX_MUL_CONST : in.src == SRC_POP ? FX_MUL_POP : FX_GENERIC;
+          break;
+        case OP_POWU: fx = FX_POWU; break;
+        case OP_INV: fx = FX_INV; break;
+        case OP_STORE: fx = FX_STORE; break;
+        case OP_SQR: fx = FX_SQR; break;
+        default: break;
+      }
+    }
+    in.fast = fx;
+  }
 }
 
 static void init_vars(Collection& c, const std::vector<std::string>& vars, bool chk) {
@@ -664,7 +713,9 @@ bool Collection::resolve(uint64_t p, std::string& err) {
       eval_nodes(functions[cur], p, nullptr, val);
     }
     const uint64_t v = val[cp.node];
-    tape[cp.instr].imm = cp.inverse ? ffhost::div(1 % p, v, p) : v;
+    uint64_t w = cp.inverse ? ffhost::div(1 % p, v, p) : v;
+    if (cp.negate) w = ffhost::neg(w, p);
+    tape[cp.instr].imm = w;
   }
   prime = p;
   return true;

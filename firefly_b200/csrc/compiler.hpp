@@ -68,6 +68,7 @@ struct ConstPatch {
   uint32_t fn;         // function
   int32_t node;        // constant sub-tree root
   bool inverse;        // store 1/value (division by a constant becomes a multiplication)
+  bool negate;         // store -value (subtraction of a constant becomes an addition)
 };
 
 // algorithmic work of one probe (all functions), counted on the reference's
@@ -109,6 +110,7 @@ struct Collection {
   bool build_tree(Function& f, std::string& err);
   void emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots);
   void count_work(const Function& f);
+  void peephole();
   bool finish(std::string& err);
   // fingerprints for duplicate detection
   std::vector<uint64_t> chk_pts1_, chk_pts2_;

@@ -213,6 +213,89 @@ FF63_D u64 mul_pm_dev(u64 x, u64 y, u32 d) {
       "}" : "=l"(r) : "l"(x), "l"(y), "r"(d));
   return r;
 }
+
+// squaring: x0*x1 is computed once and added twice (5 wide multiplies + 1 narrow instead of 6 + 1)
+FF63_D u64 sqr_pm_dev(u64 x, u32 d) {
+  u64 r;
+  asm("{\n\t"
+      ".reg .u32 x0,x1,w0,w1,w2,w3,u0,u1,v0,v1,r0,r1,r2,t;\n\t"
+      ".reg .u64 t0,m,t3,u,v;\n\t"
+      ".reg .pred p;\n\t"
+      "mov.b64 {x0,x1}, %1;\n\t"
+      "mul.wide.u32 t0, x0, x0;\n\t"
+      "mul.wide.u32 m, x0, x1;\n\t"
+      "mul.wide.u32 t3, x1, x1;\n\t"
+      "mov.b64 {w0,w1}, t0;\n\t"
+      "mov.b64 {w2,w3}, t3;\n\t"
+      "mov.b64 {u0,u1}, m;\n\t"
+      "add.cc.u32 w1, w1, u0;\n\t"
+      "addc.cc.u32 w2, w2, u1;\n\t"
+      "addc.u32 w3, w3, 0;\n\t"
+      "add.cc.u32 w1, w1, u0;\n\t"
+      "addc.cc.u32 w2, w2, u1;\n\t"
+      "addc.u32 w3, w3, 0;\n\t"
+      "mul.wide.u32 u, w2, %2;\n\t"
+      "mul.wide.u32 v, w3, %2;\n\t"
+      "mov.b64 {u0,u1}, u;\n\t"
+      "mov.b64 {v0,v1}, v;\n\t"
+      "add.cc.u32 r0, w0, u0;\n\t"
+      "addc.cc.u32 r1, w1, u1;\n\t"
+      "addc.u32 r2, v1, 0;\n\t"
+      "add.cc.u32 r1, r1, v0;\n\t"
+      "addc.u32 r2, r2, 0;\n\t"
+      "mul.lo.u32 t, r2, %2;\n\t"
+      "add.cc.u32 r0, r0, t;\n\t"
+      "addc.cc.u32 r1, r1, 0;\n\t"
+      "addc.u32 t, 0, 0;\n\t"
+      "setp.ne.u32 p, t, 0;\n\t"
+      "@p add.u32 r0, r0, %2;\n\t"
+      "mov.b64 %0, {r0,r1};\n\t"
+      "}" : "=l"(r) : "l"(x), "r"(d));
+  return r;
+}
+
+// branch-free lazy add / sub / neg (same values as add_lazy / sub_lazy / neg_lazy above)
+FF63_D u64 add_lazy_dev(u64 a, u64 b, u32 d) {
+  u64 r;
+  asm("{\n\t"
+      ".reg .u32 a0,a1,b0,b1,c,t;\n\t"
+      "mov.b64 {a0,a1}, %1;\n\t"
+      "mov.b64 {b0,b1}, %2;\n\t"
+      "add.cc.u32 a0, a0, b0;\n\t"
+      "addc.cc.u32 a1, a1, b1;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "mul.lo.u32 t, c, %3;\n\t"          // first wrap: + d
+      "add.cc.u32 a0, a0, t;\n\t"
+      "addc.cc.u32 a1, a1, 0;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "mad.lo.u32 a0, c, %3, a0;\n\t"     // second wrap: value < d now, + d cannot carry
+      "mov.b64 %0, {a0,a1};\n\t"
+      "}" : "=l"(r) : "l"(a), "l"(b), "r"(d));
+  return r;
+}
+FF63_D u64 sub_lazy_dev(u64 a, u64 b, u32 d, u64 p) {
+  u64 r;
+  asm("{\n\t"
+      ".reg .u32 a0,a1,b0,b1,p0,p1,m,t;\n\t"
+      "mov.b64 {a0,a1}, %1;\n\t"
+      "mov.b64 {b0,b1}, %2;\n\t"
+      "mov.b64 {p0,p1}, %4;\n\t"
+      "sub.cc.u32 a0, a0, b0;\n\t"
+      "subc.cc.u32 a1, a1, b1;\n\t"
+      "subc.u32 m, 0, 0;\n\t"             // m = 0xffffffff on borrow
+      "and.b32 t, m, %3;\n\t"
+      "sub.cc.u32 a0, a0, t;\n\t"         // borrow: - d
+      "subc.cc.u32 a1, a1, 0;\n\t"
+      "subc.u32 m, 0, 0;\n\t"
+      "and.b32 p0, p0, m;\n\t"
+      "and.b32 p1, p1, m;\n\t"
+      "add.cc.u32 a0, a0, p0;\n\t"        // went below zero: + p
+      "addc.u32 a1, a1, p1;\n\t"
+      "mov.b64 %0, {a0,a1};\n\t"
+      "}" : "=l"(r) : "l"(a), "l"(b), "r"(d), "l"(p));
+  return r;
+}
+FF63_D u64 neg_lazy_dev(u64 a, u32 d, u64 p) { return sub_lazy_dev(0, a, d, p); }
 #endif  // __CUDACC__
 
 }  // namespace ff63

@@ -38,7 +38,10 @@ struct Field {
 };
 
 __device__ __forceinline__ u64 fmul(u64 a, u64 b, const Field& F) { return ff63::mul_pm_dev(a, b, F.d); }
-__device__ __forceinline__ u64 fsqr(u64 a, const Field& F) { return ff63::mul_pm_dev(a, a, F.d); }
+__device__ __forceinline__ u64 fsqr(u64 a, const Field& F) { return ff63::sqr_pm_dev(a, F.d); }
+__device__ __forceinline__ u64 fadd(u64 a, u64 b, const Field& F) { return ff63::add_lazy_dev(a, b, F.d); }
+__device__ __forceinline__ u64 fsub(u64 a, u64 b, const Field& F) { return ff63::sub_lazy_dev(a, b, F.d, F.p); }
+__device__ __forceinline__ u64 fneg(u64 a, const Field& F) { return ff63::neg_lazy_dev(a, F.d, F.p); }
 __device__ __forceinline__ u64 fcanon(u64 a, const Field& F) { return ff63::canon_pm(a, F.c, F.p); }
 
 // x^e, e uniform across the warp, left-to-right binary; x^0 = 1 (reference mod_pow, FFInt.cpp:371-383)
@@ -198,36 +201,43 @@ template <int K, int THREADS, bool VEC>
 __global__ void __launch_bounds__(THREADS) eval_tape_kernel(const EvalParams prm) {
   extern __shared__ __align__(16) u64 smem[];
   u64* const scratch = smem;                 // 64 words for block_inverse
-  u64* const stk = smem + 64;                // [slot][k][thread]
+  u64* const stk = smem + 64 + threadIdx.x;  // [slot][k][thread], this thread's column
   const Field F{prm.p, prm.c, prm.d};
-  const unsigned tid = threadIdx.x;
 
-  // point indices owned by this thread: pairs (2t, 2t+1) within a 2*THREADS wide row when VEC
+  // Points owned by this thread.  VEC: pairs (2t, 2t+1) inside rows of 2*THREADS points, so that
+  // every load/store is one 16-byte access per lane and a warp covers 512 contiguous bytes.
   const u64 tile = (u64)blockIdx.x * (u64)(THREADS * K);
-  u64 pt[K];
-  bool ok[K];
-#pragma unroll
-  for (int k = 0; k < K; k++) {
-    if (VEC) pt[k] = tile + (u64)(k >> 1) * (2 * THREADS) + 2 * tid + (k & 1);
-    else pt[k] = tile + (u64)k * THREADS + tid;
-    ok[k] = pt[k] < prm.n_points;
-  }
+  const u64 first = VEC ? tile + 2 * threadIdx.x : tile + threadIdx.x;
+  constexpr u32 STEP = VEC ? 2 * THREADS : THREADS;       // distance between this thread's accesses
+  constexpr int NACC = VEC ? K / 2 : K;                   // accesses per variable
+  const bool full = tile + (u64)(THREADS * K) <= prm.n_points;   // block uniform
+  const u64* const vbase = reinterpret_cast<const u64*>(prm.values) + first;
+  u64* const obase = reinterpret_cast<u64*>(prm.out) + first;
 
+  auto in_range = [&](int j) { return first + (u64)j * STEP < prm.n_points; };
   auto load_var = [&](u32 var, u64 (&b)[K]) {
-    const u64* row = reinterpret_cast<const u64*>(prm.values) + (u64)var * prm.in_stride;
+    const u64* row = vbase + (u64)var * prm.in_stride;
     if (VEC) {
 #pragma unroll
-      for (int k = 0; k < K; k += 2) {
+      for (int j = 0; j < NACC; j++) {
         // n_points is even and rows are 16-byte aligned on this path: a pair is valid or not as a whole
         ulonglong2 v = make_ulonglong2(1, 1);
-        if (ok[k]) v = __ldg(reinterpret_cast<const ulonglong2*>(row + pt[k]));
-        b[k] = v.x;
-        b[k + 1] = v.y;
+        if (full || in_range(j)) v = __ldg(reinterpret_cast<const ulonglong2*>(row + j * STEP));
+        b[2 * j] = v.x;
+        b[2 * j + 1] = v.y;
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < K; k++) b[k] = ok[k] ? __ldg(row + pt[k]) : 1;
+      for (int j = 0; j < NACC; j++) b[j] = (full || in_range(j)) ? __ldg(row + j * STEP) : 1;
     }
+  };
+  auto push = [&](const u64 (&a)[K], u32 sp) {
+#pragma unroll
+    for (int k = 0; k < K; k++) stk[(sp * K + k) * THREADS] = a[k];
+  };
+  auto pop = [&](u64 (&b)[K], u32 sp) {
+#pragma unroll
+    for (int k = 0; k < K; k++) b[k] = stk[(sp * K + k) * THREADS];
   };
 
   u64 acc[K];
@@ -242,81 +252,77 @@ __global__ void __launch_bounds__(THREADS) eval_tape_kernel(const EvalParams prm
   for (;;) {
     nxt.v = __ldg(tape + pc + 1);            // the tape ends in two HALTs: always in bounds
     const Instr ins = cur.i;
-    if (ins.op == OP_HALT) break;
-
-    // ---- operand fetch
     u64 b[K];
-    switch (ins.src) {
-      case SRC_POP:
-        --sp;
-#pragma unroll
-        for (int k = 0; k < K; k++) b[k] = stk[((u64)sp * K + k) * THREADS + tid];
+    switch (ins.fast) {
+      // ---- the common (op, operand) combinations, each working on ACC in place -----------------
+      case FX_PUSH_LOAD_VAR:
+        push(acc, sp++);
+      case FX_LOAD_VAR:
+        load_var(ins.arg, acc);
         break;
-      case SRC_VAR:
+      case FX_PUSH_LOAD_CONST:
+        push(acc, sp++);
+      case FX_LOAD_CONST:
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[k] = ins.imm;
+        break;
+      case FX_ADD_VAR:
         load_var(ins.arg, b);
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[k] = fadd(acc[k], b[k], F);
         break;
-      case SRC_NEGVAR:
+      case FX_ADD_CONST:
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[k] = fadd(acc[k], ins.imm, F);
+        break;
+      case FX_ADD_POP:
+        pop(b, --sp);
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[k] = fadd(acc[k], b[k], F);
+        break;
+      case FX_SUB_VAR:
         load_var(ins.arg, b);
 #pragma unroll
-        for (int k = 0; k < K; k++) b[k] = ff63::neg_lazy(b[k], F.d, F.p);
+        for (int k = 0; k < K; k++) acc[k] = fsub(acc[k], b[k], F);
         break;
-      case SRC_CONST:
+      case FX_RSUB_VAR:
+        load_var(ins.arg, b);
 #pragma unroll
-        for (int k = 0; k < K; k++) b[k] = ins.imm;
+        for (int k = 0; k < K; k++) acc[k] = fsub(b[k], acc[k], F);
         break;
-      default:
+      case FX_RSUB_CONST:
 #pragma unroll
-        for (int k = 0; k < K; k++) b[k] = 0;
+        for (int k = 0; k < K; k++) acc[k] = fsub(ins.imm, acc[k], F);
         break;
-    }
-
-    // ---- execute
-    switch (ins.op) {
-      case OP_LOAD:
-        if (ins.flags & F_PUSH) {
+      case FX_SUB_POP:
+        pop(b, --sp);
 #pragma unroll
-          for (int k = 0; k < K; k++) stk[((u64)sp * K + k) * THREADS + tid] = acc[k];
-          ++sp;
-        }
-#pragma unroll
-        for (int k = 0; k < K; k++) acc[k] = b[k];
+        for (int k = 0; k < K; k++) acc[k] = fsub(acc[k], b[k], F);
         break;
-      case OP_ADD:
+      case FX_RSUB_POP:
+        pop(b, --sp);
 #pragma unroll
-        for (int k = 0; k < K; k++) acc[k] = ff63::add_lazy(acc[k], b[k], F.d);
+        for (int k = 0; k < K; k++) acc[k] = fsub(b[k], acc[k], F);
         break;
-      case OP_SUB:
-        if (ins.flags & F_SWAP) {
-#pragma unroll
-          for (int k = 0; k < K; k++) acc[k] = ff63::sub_lazy(b[k], acc[k], F.d, F.p);
-        } else {
-#pragma unroll
-          for (int k = 0; k < K; k++) acc[k] = ff63::sub_lazy(acc[k], b[k], F.d, F.p);
-        }
-        break;
-      case OP_MUL:
+      case FX_MUL_VAR:
+        load_var(ins.arg, b);
 #pragma unroll
         for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], b[k], F);
         break;
-      case OP_MULADD: {
-        u64 x[K];
-        load_var(ins.arg, x);
+      case FX_MUL_CONST:
 #pragma unroll
-        for (int k = 0; k < K; k++) acc[k] = ff63::add_lazy(fmul(acc[k], x[k], F), ins.imm, F.d);
+        for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], ins.imm, F);
         break;
-      }
-      case OP_SQR:
+      case FX_MUL_POP:
+        pop(b, --sp);
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], b[k], F);
+        break;
+      case FX_SQR:
 #pragma unroll
         for (int k = 0; k < K; k++) acc[k] = fsqr(acc[k], F);
         break;
-      case OP_NEG:
-#pragma unroll
-        for (int k = 0; k < K; k++) acc[k] = ff63::neg_lazy(acc[k], F.d, F.p);
-        break;
-      case OP_INV:
-        block_inverse<K, THREADS>(acc, F, scratch);
-        break;
-      case OP_POWU: {
+      case FX_POWU: {
         // FFInt::pow(const FFInt&) with a lane-uniform exponent residue (FFInt.cpp:155-179)
         const u64 e = ins.imm;
         if (e == 2) {
@@ -330,50 +336,136 @@ __global__ void __launch_bounds__(THREADS) eval_tape_kernel(const EvalParams prm
         }
         break;
       }
-      case OP_NPOWU: {
-        // FFInt::pow<int>(a.to_neg_int()) with a lane-uniform exponent (FFInt.hpp:149-174)
-        const int e = (int)(0u - (u32)ins.imm);
-        if (e == 2) {
-#pragma unroll
-          for (int k = 0; k < K; k++) acc[k] = fsqr(acc[k], F);
-        } else if (e >= 0) {
-          pow_uniform<K>(acc, (u64)e, F);
-        } else {
-          block_inverse<K, THREADS>(acc, F, scratch);
-          pow_uniform<K>(acc, (u64)(-(long long)e), F);
-        }
+      case FX_INV:
+        block_inverse<K, THREADS>(acc, F, scratch);
         break;
-      }
-      case OP_POWL:
-#pragma unroll
-        for (int k = 0; k < K; k++)
-          acc[k] = (ins.flags & F_SWAP) ? pow_ff_lane(b[k], acc[k], F) : pow_ff_lane(acc[k], b[k], F);
-        break;
-      case OP_NPOWL:
-#pragma unroll
-        for (int k = 0; k < K; k++)
-          acc[k] = (ins.flags & F_SWAP) ? pow_negint_lane(b[k], acc[k], F) : pow_negint_lane(acc[k], b[k], F);
-        break;
-      case OP_STORE: {
-        u64* row = reinterpret_cast<u64*>(prm.out) + (u64)ins.arg * prm.out_stride;
+      case FX_STORE: {
+        u64* row = obase + (u64)ins.arg * prm.out_stride;
         if (VEC) {
 #pragma unroll
-          for (int k = 0; k < K; k += 2)
-            if (ok[k])
-              *reinterpret_cast<ulonglong2*>(row + pt[k]) = make_ulonglong2(fcanon(acc[k], F), fcanon(acc[k + 1], F));
+          for (int j = 0; j < NACC; j++)
+            if (full || in_range(j))
+              *reinterpret_cast<ulonglong2*>(row + j * STEP) =
+                  make_ulonglong2(fcanon(acc[2 * j], F), fcanon(acc[2 * j + 1], F));
         } else {
 #pragma unroll
-          for (int k = 0; k < K; k++)
-            if (ok[k]) row[pt[k]] = fcanon(acc[k], F);
+          for (int j = 0; j < NACC; j++)
+            if (full || in_range(j)) row[j * STEP] = fcanon(acc[j], F);
         }
         break;
       }
-      default:
-        break;
-    }
-    if (ins.flags & F_NEGR) {
+
+      // ---- everything else: general two-level decode ------------------------------------------------
+      default: {
+        if (ins.op == OP_HALT) return;
+        switch (ins.src) {
+          case SRC_POP: pop(b, --sp); break;
+          case SRC_VAR: load_var(ins.arg, b); break;
+          case SRC_NEGVAR:
+            load_var(ins.arg, b);
 #pragma unroll
-      for (int k = 0; k < K; k++) acc[k] = ff63::neg_lazy(acc[k], F.d, F.p);
+            for (int k = 0; k < K; k++) b[k] = fneg(b[k], F);
+            break;
+          case SRC_CONST:
+#pragma unroll
+            for (int k = 0; k < K; k++) b[k] = ins.imm;
+            break;
+          default:
+#pragma unroll
+            for (int k = 0; k < K; k++) b[k] = 0;
+            break;
+        }
+        switch (ins.op) {
+          case OP_LOAD:
+            if (ins.flags & F_PUSH) push(acc, sp++);
+#pragma unroll
+            for (int k = 0; k < K; k++) acc[k] = b[k];
+            break;
+          case OP_ADD:
+#pragma unroll
+            for (int k = 0; k < K; k++) acc[k] = fadd(acc[k], b[k], F);
+            break;
+          case OP_SUB:
+#pragma unroll
+            for (int k = 0; k < K; k++) acc[k] = (ins.flags & F_SWAP) ? fsub(b[k], acc[k], F) : fsub(acc[k], b[k], F);
+            break;
+          case OP_MUL:
+#pragma unroll
+            for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], b[k], F);
+            break;
+          case OP_MULADD: {
+            u64 x[K];
+            load_var(ins.arg, x);
+#pragma unroll
+            for (int k = 0; k < K; k++) acc[k] = fadd(fmul(acc[k], x[k], F), ins.imm, F);
+            break;
+          }
+          case OP_SQR:
+#pragma unroll
+            for (int k = 0; k < K; k++) acc[k] = fsqr(acc[k], F);
+            break;
+          case OP_NEG:
+#pragma unroll
+            for (int k = 0; k < K; k++) acc[k] = fneg(acc[k], F);
+            break;
+          case OP_INV:
+            block_inverse<K, THREADS>(acc, F, scratch);
+            break;
+          case OP_POWU: {
+            const u64 e = ins.imm;
+            if (e == 2) {
+#pragma unroll
+              for (int k = 0; k < K; k++) acc[k] = fsqr(acc[k], F);
+            } else if (e < (F.p >> 1)) {
+              pow_uniform<K>(acc, e, F);
+            } else {
+              block_inverse<K, THREADS>(acc, F, scratch);
+              pow_uniform<K>(acc, F.p - e - 1, F);
+            }
+            break;
+          }
+          case OP_NPOWU: {
+            // FFInt::pow<int>(a.to_neg_int()) with a lane-uniform exponent (FFInt.hpp:149-174)
+            const int e = (int)(0u - (u32)ins.imm);
+            if (e == 2) {
+#pragma unroll
+              for (int k = 0; k < K; k++) acc[k] = fsqr(acc[k], F);
+            } else if (e >= 0) {
+              pow_uniform<K>(acc, (u64)e, F);
+            } else {
+              block_inverse<K, THREADS>(acc, F, scratch);
+              pow_uniform<K>(acc, (u64)(-(long long)e), F);
+            }
+            break;
+          }
+          case OP_POWL:
+#pragma unroll
+            for (int k = 0; k < K; k++)
+              acc[k] = (ins.flags & F_SWAP) ? pow_ff_lane(b[k], acc[k], F) : pow_ff_lane(acc[k], b[k], F);
+            break;
+          case OP_NPOWL:
+#pragma unroll
+            for (int k = 0; k < K; k++)
+              acc[k] = (ins.flags & F_SWAP) ? pow_negint_lane(b[k], acc[k], F) : pow_negint_lane(acc[k], b[k], F);
+            break;
+          case OP_STORE: {
+            u64* row = obase + (u64)ins.arg * prm.out_stride;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+              const int j = VEC ? k / 2 : k;
+              if (full || in_range(j)) row[j * STEP + (VEC ? (k & 1) : 0)] = fcanon(acc[k], F);
+            }
+            break;
+          }
+          default:
+            break;
+        }
+        if (ins.flags & F_NEGR) {
+#pragma unroll
+          for (int k = 0; k < K; k++) acc[k] = fneg(acc[k], F);
+        }
+        break;
+      }
     }
     cur = nxt;
     ++pc;
@@ -413,7 +505,7 @@ LaunchShape choose_shape(uint64_t n_points, uint32_t stack_depth, int sm_count, 
   } else {
     // small batches: spread over all SMs first (one point per lane), then add work per thread
     const uint64_t lanes = (uint64_t)sm_count * 1024;      // 4 CTAs of 256 threads per SM
-    s.k = n_points >= 4 * lanes ? 4 : n_points >= 2 * lanes ? 2 : 1;
+    s.k = n_points >= 8 * lanes ? 8 : n_points >= 4 * lanes ? 4 : n_points >= 2 * lanes ? 2 : 1;
   }
   // the spill stack must fit in shared memory: back off K, then the block size
   auto smem_of = [&](int k, int th) { return (size_t)(64 + (size_t)stack_depth * k * th) * sizeof(uint64_t); };
@@ -433,6 +525,7 @@ cudaError_t launch_eval(const EvalParams& prm, const LaunchShape& sh, cudaStream
   FFGPU_CASE(1, 128) FFGPU_CASE(1, 256) FFGPU_CASE(1, 512)
   FFGPU_CASE(2, 128) FFGPU_CASE(2, 256) FFGPU_CASE(2, 512)
   FFGPU_CASE(4, 128) FFGPU_CASE(4, 256) FFGPU_CASE(4, 512)
+  FFGPU_CASE(8, 128) FFGPU_CASE(8, 256) FFGPU_CASE(8, 512)
 #undef FFGPU_CASE
   return cudaErrorInvalidValue;
 }
@@ -489,10 +582,10 @@ __global__ void field_ops_kernel(int op, const u64* a, const u64* b, u64* r, u64
   __shared__ u64 scratch[64];
   u64 v = 0;
   switch (op) {
-    case 0: v = fcanon(ff63::add_lazy(x, y, F.d), F); break;
-    case 1: v = fcanon(ff63::sub_lazy(x, y, F.d, F.p), F); break;
+    case 0: v = fcanon(fadd(x, y, F), F); break;
+    case 1: v = fcanon(fsub(x, y, F), F); break;
     case 2: v = fcanon(fmul(x, y, F), F); break;
-    case 3: v = fcanon(ff63::neg_lazy(x, F.d, F.p), F); break;
+    case 3: v = fcanon(fneg(x, F), F); break;
     case 4: v = fcanon(inv_fermat(x, F), F); break;
     case 5: v = fcanon(pow_ff_lane(x, y, F), F); break;
     case 6: { u64 t[1] = {x}; block_inverse<1, 256>(t, F, scratch); v = fcanon(t[0], F); break; }

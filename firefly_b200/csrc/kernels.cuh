@@ -22,7 +22,7 @@ struct EvalParams {
 
 // probes per thread / threads per block actually used for a launch
 struct LaunchShape {
-  int k;          // 1, 2 or 4
+  int k;          // 1, 2, 4 or 8
   int threads;    // 128, 256 or 512
   unsigned blocks;
   size_t smem;

@@ -34,7 +34,7 @@ struct alignas(16) Instr {
   uint8_t op;      // Op
   uint8_t src;     // Src
   uint8_t flags;   // F_*
-  uint8_t rsv;
+  uint8_t fast;    // Fast: dense dispatch code of the common (op, src, flags) combinations, 0 = generic path
   uint32_t arg;    // variable index (SRC_VAR/SRC_NEGVAR) or output slot (OP_STORE)
   uint64_t imm;    // constant (SRC_CONST, canonical residue mod the current prime)
 };
@@ -56,6 +56,18 @@ enum Op : uint8_t {
   OP_STORE,   // out[arg][point] = canonical(ACC)
   OP_MULADD,  // ACC = ACC * var[arg] + imm      (Horner step; src selects var/negvar for the factor)
   OP_COUNT
+};
+
+// Dense dispatch codes.  Purely an encoding of (op, src, flags) -- the interpreter's first switch
+// goes over these; anything without a code (FX_GENERIC) takes the general two-level decode.
+enum Fast : uint8_t {
+  FX_GENERIC = 0,
+  FX_LOAD_VAR, FX_LOAD_CONST, FX_PUSH_LOAD_VAR, FX_PUSH_LOAD_CONST,
+  FX_ADD_VAR, FX_ADD_CONST, FX_ADD_POP,
+  FX_SUB_VAR, FX_RSUB_VAR, FX_RSUB_CONST, FX_SUB_POP, FX_RSUB_POP,
+  FX_MUL_VAR, FX_MUL_CONST, FX_MUL_POP,
+  FX_POWU, FX_INV, FX_STORE, FX_SQR,
+  FX_COUNT
 };
 
 enum Src : uint8_t {

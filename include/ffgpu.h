@@ -97,7 +97,7 @@ void* ffgpu_host_alloc(size_t bytes);
 void ffgpu_host_free(void*);
 
 /* ---- tuning / measurement ----------------------------------------------------------------- */
-/* probes per thread (1, 2, 4; 0 = automatic) and threads per block (128, 256, 512; 0 = automatic) */
+/* probes per thread (1, 2, 4, 8; 0 = automatic) and threads per block (128, 256, 512; 0 = automatic) */
 int ffgpu_set_launch(ffgpu_tape*, int probes_per_thread, int threads_per_block);
 /* points per pipelined chunk of ffgpu_eval (0 = automatic) */
 int ffgpu_set_chunk(ffgpu_tape*, size_t points);
