@@ -114,6 +114,7 @@ struct ffgpu_tape {
   ffgpu_ctx* ctx = nullptr;
   ffgpu::Collection col;
   std::vector<ffgpu::Instr*> d_tape;   // per device
+  std::vector<uint32_t*> d_chunks;     // per device: Collection::chunk_table
   int force_k = 0, force_threads = 0;
   size_t chunk = 0;
 };
@@ -135,7 +136,10 @@ ffgpu_tape* finish_compile(ffgpu_ctx* ctx, std::unique_ptr<ffgpu_tape> t, bool o
     return nullptr;
   }
   t->ctx = ctx;       // NULL: host-only handle (RPN / tape inspection; evaluation refuses)
-  if (ctx) t->d_tape.assign(ctx->devs.size(), nullptr);
+  if (ctx) {
+    t->d_tape.assign(ctx->devs.size(), nullptr);
+    t->d_chunks.assign(ctx->devs.size(), nullptr);
+  }
   return t.release();
 }
 
@@ -160,8 +164,15 @@ int launch(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, siz
   prm.c = (uint32_t)((1ULL << 63) - c.prime);
   prm.d = 2 * prm.c;
   prm.stack_depth = c.stack_depth;
-  const ffgpu::LaunchShape sh =
-      ffgpu::choose_shape(n_points, c.stack_depth, t->ctx->devs[g].sm_count, t->force_k, t->force_threads);
+  prm.n_instr = (uint32_t)(c.tape.size() - 2);
+  const ffgpu::LaunchShape sh = ffgpu::choose_shape(n_points, c.stack_depth, t->ctx->devs[g].sm_count, t->force_k,
+                                                    t->force_threads, c.max_chunks);
+  prm.chunk_bounds = nullptr;
+  if (sh.chunks > 1) {
+    unsigned idx = 0;
+    while ((1u << idx) < sh.chunks) ++idx;
+    prm.chunk_bounds = t->d_chunks[g] + c.chunk_table_off[idx];
+  }
   cudaError_t e = ffgpu::launch_eval(prm, sh, stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_eval");
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -281,6 +292,7 @@ void ffgpu_tape_destroy(ffgpu_tape* t) {
     DeviceGuard guard(t->ctx->devs[g].id);
     cudaDeviceSynchronize();
     cudaFree(t->d_tape[g]);
+    if (t->d_chunks[g]) cudaFree(t->d_chunks[g]);
   }
   delete t;
 }
@@ -337,6 +349,11 @@ int ffgpu_set_prime(ffgpu_tape* t, uint64_t p) {
     // quiescence is the caller's contract; make it true for our own streams anyway
     FF_CUDA(cudaDeviceSynchronize());
     if (!t->d_tape[g]) FF_CUDA(cudaMalloc(&t->d_tape[g], bytes));
+    if (!t->d_chunks[g]) {
+      FF_CUDA(cudaMalloc(&t->d_chunks[g], t->col.chunk_table.size() * sizeof(uint32_t)));
+      FF_CUDA(cudaMemcpy(t->d_chunks[g], t->col.chunk_table.data(), t->col.chunk_table.size() * sizeof(uint32_t),
+                         cudaMemcpyHostToDevice));
+    }
     FF_CUDA(cudaMemcpy(t->d_tape[g], t->col.tape.data(), bytes, cudaMemcpyHostToDevice));
   }
   return 0;

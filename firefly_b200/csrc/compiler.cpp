@@ -589,11 +589,30 @@ bool Collection::finish(std::string& err) {
   patches.clear();
   stack_depth = 0;
   work = WorkCount{};
+  fn_start.clear();
   for (size_t i = 0; i < functions.size(); ++i) {
+    fn_start.push_back((uint32_t)tape.size());
     emit_function((uint32_t)i, slots[i]);
     count_work(functions[i]);
   }
+  fn_start.push_back((uint32_t)tape.size());
   peephole();
+  // chunk tables for C = 1, 2, 4, ... while a chunk still holds a function
+  chunk_table.clear();
+  chunk_table_off.clear();
+  max_chunks = 1;
+  const uint32_t total = (uint32_t)tape.size();
+  for (unsigned C = 1; C <= 1024 && C <= std::max<size_t>(functions.size(), 1); C <<= 1) {
+    chunk_table_off.push_back((uint32_t)chunk_table.size());
+    size_t f = 0;
+    for (unsigned k = 0; k < C; ++k) {
+      const uint64_t target = (uint64_t)total * k / C;
+      while (f + 1 < fn_start.size() && fn_start[f] < target) ++f;
+      chunk_table.push_back(fn_start[f]);
+    }
+    chunk_table.push_back(total);
+    max_chunks = C;
+  }
   Instr halt{};
   halt.op = OP_HALT;
   tape.push_back(halt);

@@ -92,6 +92,12 @@ struct Collection {
   std::vector<Instr> tape;                    // prime independent structure (imm = 0)
   std::vector<ConstPatch> patches;
   uint32_t stack_depth = 0;                   // spill slots the tape needs
+  std::vector<uint32_t> fn_start;             // tape offset of every distinct function, then the end
+  // chunk tables: for C = 1, 2, 4, ... the C + 1 offsets that cut the tape into C runs of whole
+  // functions with about equal instruction counts (flattened: table c starts at chunk_table_off[c])
+  std::vector<uint32_t> chunk_table;
+  std::vector<uint32_t> chunk_table_off;
+  unsigned max_chunks = 1;
   uint64_t prime = 0;                         // prime the imm fields are resolved for (0: none)
   WorkCount work;
 

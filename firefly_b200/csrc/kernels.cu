@@ -245,11 +245,17 @@ __global__ void __launch_bounds__(THREADS) eval_tape_kernel(const EvalParams prm
   for (int k = 0; k < K; k++) acc[k] = 0;
   u32 sp = 0;                                // spill-stack pointer (uniform)
 
+  // blockIdx.y selects a chunk of the tape (a run of whole functions): many-function collections
+  // evaluated at few points still fill the chip
   const uint4* tape = reinterpret_cast<const uint4*>(prm.tape);
+  u32 pc = 0, pc_end = prm.n_instr;
+  if (prm.chunk_bounds) {
+    pc = __ldg(prm.chunk_bounds + blockIdx.y);
+    pc_end = __ldg(prm.chunk_bounds + blockIdx.y + 1);
+  }
   InstrWord cur, nxt;
-  cur.v = __ldg(tape);
-  u32 pc = 0;
-  for (;;) {
+  cur.v = __ldg(tape + pc);
+  for (; pc < pc_end;) {
     nxt.v = __ldg(tape + pc + 1);            // the tape ends in two HALTs: always in bounds
     const Instr ins = cur.i;
     u64 b[K];
@@ -483,21 +489,22 @@ cudaError_t launch_t(const EvalParams& prm, const LaunchShape& sh, cudaStream_t 
       e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
       if (e != cudaSuccess) return e;
     }
-    kern<<<sh.blocks, THREADS, sh.smem, stream>>>(prm);
+    kern<<<dim3(sh.blocks, sh.chunks), THREADS, sh.smem, stream>>>(prm);
   } else {
     auto kern = eval_tape_kernel<K, THREADS, false>;
     if (sh.smem > 48 * 1024) {
       e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
       if (e != cudaSuccess) return e;
     }
-    kern<<<sh.blocks, THREADS, sh.smem, stream>>>(prm);
+    kern<<<dim3(sh.blocks, sh.chunks), THREADS, sh.smem, stream>>>(prm);
   }
   return cudaGetLastError();
 }
 
 }  // namespace
 
-LaunchShape choose_shape(uint64_t n_points, uint32_t stack_depth, int sm_count, int force_k, int force_threads) {
+LaunchShape choose_shape(uint64_t n_points, uint32_t stack_depth, int sm_count, int force_k, int force_threads,
+                         unsigned max_chunks) {
   LaunchShape s;
   s.threads = force_threads ? force_threads : 256;
   if (force_k) {
@@ -514,6 +521,11 @@ LaunchShape choose_shape(uint64_t n_points, uint32_t stack_depth, int sm_count, 
   s.smem = smem_of(s.k, s.threads);
   const uint64_t per_block = (uint64_t)s.threads * s.k;
   s.blocks = (unsigned)((n_points + per_block - 1) / per_block);
+  // too few point tiles to fill the chip: split the functions of the collection over grid.y
+  s.chunks = 1;
+  const unsigned want = (unsigned)sm_count * 4;
+  while (s.chunks < max_chunks && s.blocks * s.chunks < want) s.chunks <<= 1;
+  if (s.chunks > max_chunks) s.chunks = max_chunks;
   return s;
 }
 

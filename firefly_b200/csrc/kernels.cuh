@@ -18,17 +18,21 @@ struct EvalParams {
   uint32_t c;
   uint32_t d;                 // 2c
   uint32_t stack_depth;       // spill slots per lane
+  uint32_t n_instr;           // tape length without the terminators
+  const uint32_t* chunk_bounds;  // device, n_chunks + 1 tape offsets at function boundaries (NULL: one chunk)
 };
 
 // probes per thread / threads per block actually used for a launch
 struct LaunchShape {
   int k;          // 1, 2, 4 or 8
   int threads;    // 128, 256 or 512
-  unsigned blocks;
+  unsigned blocks;     // point tiles (grid.x)
+  unsigned chunks;     // tape chunks (grid.y): blocks of a tile split the collection's functions
   size_t smem;
 };
 
-LaunchShape choose_shape(uint64_t n_points, uint32_t stack_depth, int sm_count, int force_k, int force_threads);
+LaunchShape choose_shape(uint64_t n_points, uint32_t stack_depth, int sm_count, int force_k, int force_threads,
+                         unsigned max_chunks);
 cudaError_t launch_eval(const EvalParams& prm, const LaunchShape& shape, cudaStream_t stream);
 
 // synthetic probe points, identical on host (bench/tests) and device:
