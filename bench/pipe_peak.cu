@@ -127,6 +127,81 @@ __device__ __forceinline__ u64 mul_l63_asm(u64 x, u64 y, u32 c) {
   return r;
 }
 
+// "b63" family: residues bounded below 2^63 + 2^32 (so both high words are <= 2^31): the two cross
+// products are summed inside one IMAD.WIDE (no overflow), fold 1 at 2^64 = d, fold 2 at 2^63 = c with
+// no conditional correction.  6 wide + 1 narrow multiplies, 11 adds/logic.
+__device__ __forceinline__ u64 mul_b63(u64 x, u64 y, u32 c, u32 d) {
+  u64 r;
+  asm("{\n\t"
+      ".reg .u32 x0,x1,y0,y1,w0,w1,w2,w3,a,ml,mh,tl,th,u0,u1,v0,v1,r0,r1,r2,top,t;\n\t"
+      ".reg .u64 t0,m,t3,u,v;\n\t"
+      "mov.b64 {x0,x1}, %1;\n\t"
+      "mov.b64 {y0,y1}, %2;\n\t"
+      "mul.wide.u32 t0, x0, y0;\n\t"
+      "mul.wide.u32 m, x0, y1;\n\t"
+      "mad.wide.u32 m, x1, y0, m;\n\t"
+      "mul.wide.u32 t3, x1, y1;\n\t"
+      "mov.b64 {w0,a}, t0;\n\t"
+      "mov.b64 {ml,mh}, m;\n\t"
+      "mov.b64 {tl,th}, t3;\n\t"
+      "add.cc.u32 w1, a, ml;\n\t"
+      "addc.cc.u32 w2, tl, mh;\n\t"
+      "addc.u32 w3, th, 0;\n\t"
+      "mul.wide.u32 u, w2, %4;\n\t"
+      "mul.wide.u32 v, w3, %4;\n\t"
+      "mov.b64 {u0,u1}, u;\n\t"
+      "mov.b64 {v0,v1}, v;\n\t"
+      "add.cc.u32 r0, w0, u0;\n\t"
+      "addc.cc.u32 r1, w1, u1;\n\t"
+      "addc.u32 r2, v1, 0;\n\t"
+      "add.cc.u32 r1, r1, v0;\n\t"
+      "addc.u32 r2, r2, 0;\n\t"
+      "shf.l.wrap.b32 top, r1, r2, 1;\n\t"
+      "and.b32 r1, r1, 0x7fffffff;\n\t"
+      "mul.lo.u32 t, top, %3;\n\t"
+      "add.cc.u32 r0, r0, t;\n\t"
+      "addc.u32 r1, r1, 0;\n\t"
+      "mov.b64 %0, {r0,r1};\n\t"
+      "}" : "=l"(r) : "l"(x), "l"(y), "r"(c), "r"(d));
+  return r;
+}
+// squaring in the same representation: one cross product, doubled by a 64-bit add
+__device__ __forceinline__ u64 sqr_b63(u64 x, u32 c, u32 d) {
+  u64 r;
+  asm("{\n\t"
+      ".reg .u32 x0,x1,w0,w1,w2,w3,a,ml,mh,tl,th,u0,u1,v0,v1,r0,r1,r2,top,t;\n\t"
+      ".reg .u64 t0,m,t3,u,v;\n\t"
+      "mov.b64 {x0,x1}, %1;\n\t"
+      "mul.wide.u32 t0, x0, x0;\n\t"
+      "mul.wide.u32 m, x0, x1;\n\t"
+      "mul.wide.u32 t3, x1, x1;\n\t"
+      "mov.b64 {w0,a}, t0;\n\t"
+      "mov.b64 {ml,mh}, m;\n\t"
+      "mov.b64 {tl,th}, t3;\n\t"
+      "add.cc.u32 ml, ml, ml;\n\t"
+      "addc.u32 mh, mh, mh;\n\t"
+      "add.cc.u32 w1, a, ml;\n\t"
+      "addc.cc.u32 w2, tl, mh;\n\t"
+      "addc.u32 w3, th, 0;\n\t"
+      "mul.wide.u32 u, w2, %3;\n\t"
+      "mul.wide.u32 v, w3, %3;\n\t"
+      "mov.b64 {u0,u1}, u;\n\t"
+      "mov.b64 {v0,v1}, v;\n\t"
+      "add.cc.u32 r0, w0, u0;\n\t"
+      "addc.cc.u32 r1, w1, u1;\n\t"
+      "addc.u32 r2, v1, 0;\n\t"
+      "add.cc.u32 r1, r1, v0;\n\t"
+      "addc.u32 r2, r2, 0;\n\t"
+      "shf.l.wrap.b32 top, r1, r2, 1;\n\t"
+      "and.b32 r1, r1, 0x7fffffff;\n\t"
+      "mul.lo.u32 t, top, %2;\n\t"
+      "add.cc.u32 r0, r0, t;\n\t"
+      "addc.u32 r1, r1, 0;\n\t"
+      "mov.b64 %0, {r0,r1};\n\t"
+      "}" : "=l"(r) : "l"(x), "r"(c), "r"(d));
+  return r;
+}
+
 template <int K, int VARIANT>
 __global__ void __launch_bounds__(256) k_mm(u64* out, const u64* in, u32 c, int trips) {
   const u64 p = 0x8000000000000000ULL - c;
@@ -146,6 +221,10 @@ __global__ void __launch_bounds__(256) k_mm(u64* out, const u64* in, u32 c, int 
         if (VARIANT == 2) a[k] = ff63::sqr_pm(a[k], d);
         if (VARIANT == 3) a[k] = ff63::mul_pm_dev(a[k], b, d);
         if (VARIANT == 4) a[k] = mul_l63_asm(a[k], b, c);
+        if (VARIANT == 5) a[k] = mul_b63(a[k], b, c, d);
+        if (VARIANT == 6) a[k] = sqr_b63(a[k], c, d);
+        if (VARIANT == 7) a[k] = mul_b63(a[k], a[k], c, d);
+        if (VARIANT == 8) a[k] = ff63::sqr_pm_dev(a[k], d);
       }
     }
   }
@@ -162,7 +241,7 @@ static u64 host_mm(const u64* in, int lane, u32 c, int trips, int K, int variant
   u64 b = in[lane + 32] % p, r = 0;
   for (int k = 0; k < K; k++) {
     u64 a = (in[lane] + 977ULL * k) % p;
-    for (int t = 0; t < trips * 4; t++) a = (variant == 2) ? (u64)(((u128)a * a) % p) : (u64)(((u128)a * b) % p);
+    for (int t = 0; t < trips * 4; t++) a = (variant == 2 || variant == 6 || variant == 7 || variant == 8) ? (u64)(((u128)a * a) % p) : (u64)(((u128)a * b) % p);
     r ^= a;
   }
   return r;
@@ -278,6 +357,14 @@ int main(int argc, char** argv) {
   run_mm("mul_l63_asm_k1", k_mm<1, 4>, 1, 4);
   run_mm("mul_l63_asm_k2", k_mm<2, 4>, 2, 4);
   run_mm("mul_l63_asm_k4", k_mm<4, 4>, 4, 4);
+  run_mm("mul_b63_k2", k_mm<2, 5>, 2, 5);
+  run_mm("mul_b63_k4", k_mm<4, 5>, 4, 5);
+  run_mm("mul_b63_k8", k_mm<8, 5>, 8, 5);
+  run_mm("sqr_b63_k4", k_mm<4, 6>, 4, 6);
+  run_mm("sqr_b63_k8", k_mm<8, 6>, 8, 6);
+  run_mm("sqr_via_mul_b63_k4", k_mm<4, 7>, 4, 7);
+  run_mm("sqr_pm_dev_k4", k_mm<4, 8>, 4, 8);
+  run_mm("mul_pm_dev_k8", k_mm<8, 3>, 8, 3);
 
   printf("{\"gpu\": \"%s\", \"sms\": %d, \"sm_clock_mhz_under_load\": %.1f, \"blocks\": %d, \"threads\": %d,\n \"pipes\": {",
          prop.name, sms, sm_clock_mhz_under_load, blocks, threads);

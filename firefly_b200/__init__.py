@@ -32,10 +32,12 @@ INSTR_DTYPE = np.dtype(
     [("op", "u1"), ("src", "u1"), ("flags", "u1"), ("fast", "u1"), ("arg", "<u4"), ("imm", "<u8")]
 )
 # tape.hpp
-OPS = ["HALT", "LOAD", "ADD", "SUB", "MUL", "SQR", "NEG", "INV", "POWU", "NPOWU", "POWL", "NPOWL", "STORE", "MULADD"]
-SRCS = ["NONE", "POP", "VAR", "NEGVAR", "CONST"]
-F_PUSH, F_SWAP, F_NEGR = 1, 2, 4
+OPS = ["HALT", "LOAD", "ADD", "SUB", "MUL", "SQR", "NEG", "INV", "POWU", "NPOWU", "POWL", "NPOWL", "STORE", "MULADD",
+       "SAVE", "ACCUM"]
+SRCS = ["NONE", "POP", "VAR", "NEGVAR", "CONST", "TMP"]
+F_PUSH, F_SWAP, F_NEGR, F_INIT = 1, 2, 4, 8
 CHECK_IS_EQUAL = 1
+NO_CSE = 2
 
 
 class FFGpuError(RuntimeError):
@@ -65,6 +67,8 @@ def _load() -> C.CDLL:
         "ffgpu_n_out": (C.c_size_t, [C.c_void_p]),
         "ffgpu_n_instr": (C.c_size_t, [C.c_void_p]),
         "ffgpu_stack_depth": (C.c_size_t, [C.c_void_p]),
+        "ffgpu_n_temps": (C.c_size_t, [C.c_void_p]),
+        "ffgpu_n_slots": (C.c_size_t, [C.c_void_p]),
         "ffgpu_rpn": (C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
         "ffgpu_get_tape": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t]),
         "ffgpu_work": (None, [C.c_void_p, u64p]),
@@ -104,7 +108,7 @@ lib = _load()
 EXPORTS = [
     "ffgpu_create", "ffgpu_destroy", "ffgpu_n_devices", "ffgpu_last_error", "ffgpu_compile", "ffgpu_compile_text",
     "ffgpu_compile_file", "ffgpu_tape_destroy", "ffgpu_n_vars", "ffgpu_n_functions", "ffgpu_n_out", "ffgpu_n_instr",
-    "ffgpu_stack_depth", "ffgpu_rpn", "ffgpu_get_tape", "ffgpu_work", "ffgpu_set_prime", "ffgpu_get_prime",
+    "ffgpu_stack_depth", "ffgpu_n_temps", "ffgpu_n_slots", "ffgpu_rpn", "ffgpu_get_tape", "ffgpu_work", "ffgpu_set_prime", "ffgpu_get_prime",
     "ffgpu_n_primes", "ffgpu_prime", "ffgpu_eval", "ffgpu_eval_device", "ffgpu_host_alloc", "ffgpu_host_free",
     "ffgpu_set_launch", "ffgpu_set_chunk", "ffgpu_launch_count", "ffgpu_fill_points", "ffgpu_checksum",
     "ffgpu_field_ops",
@@ -165,10 +169,11 @@ class GpuParser:
     """
 
     def __init__(self, ctx: Optional[Context], functions=None, vars: Sequence[str] = (), check_is_equal: bool = False,
-                 *, file: Optional[str] = None, text: Optional[str] = None):
+                 *, file: Optional[str] = None, text: Optional[str] = None, cse: bool = True,
+                 temps: int = 0):
         self.ctx = ctx
         ch = ctx.h if ctx is not None else None
-        flags = CHECK_IS_EQUAL if check_is_equal else 0
+        flags = (CHECK_IS_EQUAL if check_is_equal else 0) | (0 if cse else NO_CSE) | ((temps & 15) << 8)
         v = _strs(vars)
         if file is not None:
             self.h = lib.ffgpu_compile_file(ch, file.encode(), v, len(vars), flags)
@@ -214,6 +219,14 @@ class GpuParser:
     @property
     def stack_depth(self) -> int:
         return lib.ffgpu_stack_depth(self.h)
+
+    @property
+    def n_temps(self) -> int:
+        return lib.ffgpu_n_temps(self.h)
+
+    @property
+    def n_slots(self) -> int:
+        return lib.ffgpu_n_slots(self.h)
 
     # -- prime -----------------------------------------------------------------------
     def set_prime(self, p: int):

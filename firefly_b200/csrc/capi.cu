@@ -163,9 +163,9 @@ int launch(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, siz
   prm.p = c.prime;
   prm.c = (uint32_t)((1ULL << 63) - c.prime);
   prm.d = 2 * prm.c;
-  prm.stack_depth = c.stack_depth;
+  prm.n_slots = c.n_slots;
   prm.n_instr = (uint32_t)(c.tape.size() - 2);
-  const ffgpu::LaunchShape sh = ffgpu::choose_shape(n_points, c.stack_depth, t->ctx->devs[g].sm_count, t->force_k,
+  const ffgpu::LaunchShape sh = ffgpu::choose_shape(n_points, c.n_slots, t->ctx->devs[g].sm_count, t->force_k,
                                                     t->force_threads, c.max_chunks);
   prm.chunk_bounds = nullptr;
   if (sh.chunks > 1) {
@@ -260,6 +260,8 @@ ffgpu_tape* ffgpu_compile(ffgpu_ctx* ctx, const char* const* functions, size_t n
                           size_t n_vars, unsigned flags) {
   std::unique_ptr<ffgpu_tape> t(new ffgpu_tape);
   std::string err;
+  t->col.enable_cse = !(flags & FFGPU_NO_CSE);
+  t->col.temp_budget = (int)((flags >> FFGPU_TEMPS_SHIFT) & 15u);
   const bool ok = t->col.compile_strings(to_vec(functions, n_functions), to_vec(vars, n_vars),
                                          (flags & FFGPU_CHECK_IS_EQUAL) != 0, err);
   return finish_compile(ctx, std::move(t), ok, err);
@@ -269,6 +271,8 @@ ffgpu_tape* ffgpu_compile_text(ffgpu_ctx* ctx, const char* text, const char* con
                                unsigned flags) {
   std::unique_ptr<ffgpu_tape> t(new ffgpu_tape);
   std::string err;
+  t->col.enable_cse = !(flags & FFGPU_NO_CSE);
+  t->col.temp_budget = (int)((flags >> FFGPU_TEMPS_SHIFT) & 15u);
   const bool ok = t->col.compile_text(text ? text : "", to_vec(vars, n_vars), (flags & FFGPU_CHECK_IS_EQUAL) != 0, err);
   return finish_compile(ctx, std::move(t), ok, err);
 }
@@ -302,6 +306,8 @@ size_t ffgpu_n_functions(const ffgpu_tape* t) { return t->col.functions.size(); 
 size_t ffgpu_n_out(const ffgpu_tape* t) { return t->col.n_out; }
 size_t ffgpu_n_instr(const ffgpu_tape* t) { return t->col.tape.size() - 2; }
 size_t ffgpu_stack_depth(const ffgpu_tape* t) { return t->col.stack_depth; }
+size_t ffgpu_n_temps(const ffgpu_tape* t) { return t->col.n_temps; }
+size_t ffgpu_n_slots(const ffgpu_tape* t) { return t->col.n_slots; }
 
 size_t ffgpu_rpn(const ffgpu_tape* t, size_t i, char* buf, size_t cap) {
   if (i >= t->col.functions.size()) return 0;

@@ -385,40 +385,211 @@ void Collection::count_work(const Function& f) {
 // ------------------------------------------------------------------------------------------
 // 7. code generation
 // ------------------------------------------------------------------------------------------
+// The expression tree is first turned into a DAG by hash-consing (structurally equal sub-trees get
+// one representative; x+y and y+x are equal).  Code is then generated depth first for the
+// accumulator machine:
+//   * a shared compound value is computed at its first use, parked in a TEMP slot (OP_SAVE) and
+//     read back (SRC_TMP) at the other uses, as long as temp slots are available;
+//   * two sibling sums that share compound terms (f1 of the benchmarks: the numerator and the
+//     denominator are sums over the same twenty powers) are evaluated together: every distinct term
+//     is computed once and accumulated into one temp slot per sum (OP_ACCUM);
+//   * u*u becomes OP_SQR.
+// All of this preserves the value of every node exactly (field operations are exact), it only
+// avoids recomputing equal residues.
 namespace {
-struct Emitter {
+constexpr int MAX_TEMPS = 8;
+constexpr int SLOT_BUDGET = 6;
+
+struct DagKey {
+  uint8_t kind;
+  int32_t a, b;
+  uint32_t extra;
+  bool operator==(const DagKey& o) const { return kind == o.kind && a == o.a && b == o.b && extra == o.extra; }
+};
+struct DagKeyHash {
+  size_t operator()(const DagKey& k) const {
+    uint64_t h = 0x9E3779B97F4A7C15ULL * (k.kind + 1);
+    h ^= (uint64_t)(uint32_t)k.a * 0xBF58476D1CE4E5B9ULL;
+    h = (h << 13) | (h >> 51);
+    h ^= (uint64_t)(uint32_t)k.b * 0x94D049BB133111EBULL;
+    h = (h << 17) | (h >> 47);
+    h ^= k.extra;
+    return (size_t)(h * 0x2545F4914F6CDD1DULL);
+  }
+};
+
+struct FnEmitter {
   const Function& f;
   uint32_t fn;
   std::vector<Instr>& tape;
   std::vector<ConstPatch>& patches;
-  uint32_t depth = 0, max_depth = 0;
+  bool enable_cse;
 
-  bool direct(int32_t i) const {
-    const Node& n = f.nodes[i];
-    return n.is_const || n.kind == N_VAR || n.kind == N_NEGVAR;
+  std::vector<int32_t> rep;        // node -> representative
+  std::vector<int32_t> remaining;  // representative -> consumptions still expected
+  std::vector<int32_t> temp_of;    // representative -> temp slot holding its value, or -1
+  bool slot_busy[MAX_TEMPS] = {};
+  int max_temps = MAX_TEMPS;       // temp slots this function may use
+  uint32_t depth = 0, max_depth = 0, temps_used = 0;
+
+  FnEmitter(const Function& f_, uint32_t fn_, std::vector<Instr>& t, std::vector<ConstPatch>& p, bool cse,
+            int temp_budget)
+      : f(f_), fn(fn_), tape(t), patches(p), enable_cse(cse) {
+    // Spill and temp slots share the kernel's shared memory ([slot][probe][thread], 16 KB per slot at
+    // 8 probes x 256 threads): more than SLOT_BUDGET slots per lane cost resident blocks.  Functions that
+    // already spill deep get fewer temps; two are always allowed (co-evaluated sums need two).
+    if (temp_budget > 0) max_temps = std::min(temp_budget, MAX_TEMPS);
+    else max_temps = std::max(2, std::min(MAX_TEMPS, SLOT_BUDGET - (int)f.nodes[f.root].need));
+    build_dag();
   }
-  // fill the operand fields of `ins` from a directly addressable node
-  void operand(Instr& ins, int32_t i, bool inverse = false) {
-    const Node& n = f.nodes[i];
-    if (n.is_const) {
-      ins.src = SRC_CONST;
-      patches.push_back(ConstPatch{(uint32_t)tape.size(), fn, i, inverse, false});
-    } else {
-      ins.src = n.kind == N_VAR ? SRC_VAR : SRC_NEGVAR;
-      ins.arg = n.var;
+
+  // ---- DAG ----------------------------------------------------------------------------------
+  void build_dag() {
+    const size_t n = f.nodes.size();
+    rep.resize(n);
+    remaining.assign(n, 0);
+    temp_of.assign(n, -1);
+    if (!enable_cse) {
+      for (size_t i = 0; i < n; ++i) { rep[i] = (int32_t)i; remaining[i] = 1; }
+      return;
+    }
+    std::unordered_map<DagKey, int32_t, DagKeyHash> seen;
+    std::unordered_map<std::string, uint32_t> lit_id;
+    seen.reserve(n * 2);
+    for (size_t i = 0; i < n; ++i) {
+      const Node& nd = f.nodes[i];
+      DagKey k{(uint8_t)nd.kind, -1, -1, 0};
+      if (nd.kind == N_VAR || nd.kind == N_NEGVAR) k.extra = nd.var;
+      else if (nd.kind == N_NUM) k.extra = lit_id.emplace(f.literals[nd.lit].text, (uint32_t)lit_id.size()).first->second;
+      else {
+        k.a = rep[nd.l];
+        k.b = rep[nd.r];
+        if ((nd.kind == N_ADD || nd.kind == N_MUL) && k.a > k.b) std::swap(k.a, k.b);
+      }
+      rep[i] = seen.emplace(k, (int32_t)i).first->second;
+    }
+    // references from distinct reachable parents
+    std::vector<char> visited(n, 0);
+    std::vector<int32_t> st{rep[f.root]};
+    visited[rep[f.root]] = 1;
+    remaining[rep[f.root]] = 1;
+    while (!st.empty()) {
+      const int32_t u = st.back();
+      st.pop_back();
+      const Node& nd = f.nodes[u];
+      if (nd.l < 0) continue;
+      for (int32_t c : {rep[nd.l], rep[nd.r]}) {
+        ++remaining[c];
+        if (!visited[c]) { visited[c] = 1; st.push_back(c); }
+      }
     }
   }
-  void put(Instr ins) { tape.push_back(ins); }
+
+  const Node& node(int32_t i) const { return f.nodes[rep[i]]; }
+  bool leaf_like(int32_t i) const {
+    const Node& n = node(i);
+    return n.is_const || n.kind == N_VAR || n.kind == N_NEGVAR;
+  }
+  bool direct(int32_t i) const { return leaf_like(i) || temp_of[rep[i]] >= 0; }
+  bool shared(int32_t i) const { return enable_cse && !leaf_like(i) && remaining[rep[i]] >= 2; }
+
+  int alloc_temp() {
+    for (int s = 0; s < max_temps; ++s)
+      if (!slot_busy[s]) {
+        slot_busy[s] = true;
+        temps_used = std::max<uint32_t>(temps_used, (uint32_t)s + 1);
+        return s;
+      }
+    return -1;
+  }
+  // one expected consumption of node i has happened
+  void consume(int32_t i) {
+    const int32_t u = rep[i];
+    if (--remaining[u] <= 0 && temp_of[u] >= 0) {
+      slot_busy[temp_of[u]] = false;
+      temp_of[u] = -1;
+    }
+  }
+
   static Instr mk(uint8_t op, uint8_t flags = 0) {
     Instr i{};
     i.op = op;
     i.flags = flags;
     return i;
   }
+  void put(Instr ins) { tape.push_back(ins); }
+  // operand fields from a directly addressable node (consumes it)
+  void operand(Instr& ins, int32_t i, bool inverse = false) {
+    const int32_t u = rep[i];
+    const Node& n = f.nodes[u];
+    if (n.is_const) {
+      ins.src = SRC_CONST;
+      patches.push_back(ConstPatch{(uint32_t)tape.size(), fn, u, inverse, false});
+    } else if (n.kind == N_VAR || n.kind == N_NEGVAR) {
+      ins.src = n.kind == N_VAR ? SRC_VAR : SRC_NEGVAR;
+      ins.arg = n.var;
+    } else {
+      ins.src = SRC_TMP;
+      ins.arg = (uint32_t)temp_of[u];
+      consume(u);
+    }
+  }
 
-  void apply(const Node& n, bool acc_is_right, uint8_t src_kind_pop, int32_t other) {
-    // ACC holds one operand; the other is `other` (direct) or the spill-stack top.
-    const bool from_stack = src_kind_pop == SRC_POP;
+  // ---- sums -----------------------------------------------------------------------------------
+  struct Term { int32_t node; bool minus; };
+  bool is_sum(int32_t i) const {
+    const NodeKind k = node(i).kind;
+    return !leaf_like(i) && (k == N_ADD || k == N_SUB);
+  }
+  // signed terms of the maximal unshared +/- chain below sum root i
+  void flatten(int32_t i, std::vector<Term>& out) const {
+    std::vector<Term> st{{rep[i], false}};
+    bool first = true;
+    while (!st.empty()) {
+      const Term t = st.back();
+      st.pop_back();
+      const Node& n = f.nodes[t.node];
+      const bool expand = !leaf_like(t.node) && (n.kind == N_ADD || n.kind == N_SUB) && temp_of[t.node] < 0 &&
+                          (first || remaining[t.node] == 1);
+      first = false;
+      if (!expand) { out.push_back(t); continue; }
+      // right pushed first so that the left term comes out first
+      st.push_back(Term{rep[n.r], n.kind == N_SUB ? !t.minus : t.minus});
+      st.push_back(Term{rep[n.l], t.minus});
+    }
+  }
+  bool reaches(int32_t from, int32_t target) const {
+    std::vector<int32_t> st{rep[from]};
+    std::vector<char> seen(f.nodes.size(), 0);
+    seen[rep[from]] = 1;
+    while (!st.empty()) {
+      const int32_t u = st.back();
+      st.pop_back();
+      if (u == rep[target]) return true;
+      const Node& n = f.nodes[u];
+      if (n.l < 0) continue;
+      for (int32_t c : {rep[n.l], rep[n.r]})
+        if (!seen[c]) { seen[c] = 1; st.push_back(c); }
+    }
+    return false;
+  }
+
+  // ---- generation -------------------------------------------------------------------------------
+  struct Item {
+    uint8_t what;
+    int32_t node;
+    bool push, swap;
+    int32_t other;
+    int32_t aux;
+  };
+  enum { GEN, AFTER, APPLY_POP, APPLY_DIRECT, INVERT, POW_CONST, MUL_INVCONST, SQUARE, PRE, ACCUM, ADOPT };
+  std::vector<Item> work;
+  // accumulate lists of co-evaluated sums: for ACCUM items
+  struct Acc { int slot; bool minus; bool init; };
+  struct AccList { std::vector<Acc> acc; bool post_consume = false; };
+  std::vector<AccList> acc_lists;
+
+  void apply(const Node& n, bool acc_is_right, bool from_stack, int32_t other) {
     auto finish = [&](Instr ins) {
       if (from_stack) { ins.src = SRC_POP; put(ins); --depth; }
       else { operand(ins, other); put(ins); }
@@ -436,101 +607,222 @@ struct Emitter {
     }
   }
 
+  // Two sibling sums sharing compound terms are evaluated in one sweep over their distinct terms.
+  struct Plan {
+    std::vector<int32_t> order;                               // distinct terms, first appearance first
+    std::vector<std::vector<std::pair<int, bool>>> uses;      // per term: (which sum, minus)
+  } plan;
+  bool can_coevaluate(int32_t l, int32_t r) {
+    if (!enable_cse || !is_sum(l) || !is_sum(r) || rep[l] == rep[r]) return false;
+    if (temp_of[rep[l]] >= 0 || temp_of[rep[r]] >= 0) return false;
+    std::vector<Term> tl, tr;
+    flatten(l, tl);
+    flatten(r, tr);
+    if (tl.size() + tr.size() > 4096) return false;
+    plan.order.clear();
+    plan.uses.clear();
+    std::unordered_map<int32_t, size_t> pos;
+    bool any_shared_compound = false;
+    auto add = [&](const std::vector<Term>& ts, int which) {
+      for (const Term& t : ts) {
+        auto it = pos.find(t.node);
+        if (it == pos.end()) {
+          it = pos.emplace(t.node, plan.order.size()).first;
+          plan.order.push_back(t.node);
+          plan.uses.emplace_back();
+        } else if (which == 1 && !leaf_like(t.node)) {
+          for (auto& u : plan.uses[it->second]) any_shared_compound |= (u.first == 0);
+        }
+        plan.uses[it->second].push_back({which, t.minus});
+      }
+    };
+    add(tl, 0);
+    add(tr, 1);
+    if (!any_shared_compound) return false;
+    if (reaches(l, r) || reaches(r, l)) return false;        // neither sum may live inside the other
+    int free_slots = 0;
+    for (int s = 0; s < max_temps; ++s) free_slots += !slot_busy[s];
+    return free_slots >= 2;
+  }
+  void schedule_coevaluation(int32_t l, int32_t r, bool push) {
+    const int sl = alloc_temp(), sr = alloc_temp();
+    // reverse execution order: the two ADOPTs run last
+    work.push_back(Item{ADOPT, rep[r], false, false, -1, sr});
+    work.push_back(Item{ADOPT, rep[l], false, false, -1, sl});
+    bool init[2] = {true, true};
+    std::vector<Item> fwd;
+    for (size_t k = 0; k < plan.order.size(); ++k) {
+      AccList lst;
+      for (auto& u : plan.uses[k]) {
+        lst.acc.push_back(Acc{u.first == 0 ? sl : sr, u.second, init[u.first]});
+        init[u.first] = false;
+      }
+      acc_lists.push_back(std::move(lst));
+      const int32_t li = (int32_t)acc_lists.size() - 1;
+      fwd.push_back(Item{PRE, plan.order[k], false, false, -1, li});
+      fwd.push_back(Item{GEN, plan.order[k], push && k == 0, false, -1, 0});
+      fwd.push_back(Item{ACCUM, plan.order[k], false, false, -1, li});
+    }
+    for (size_t k = fwd.size(); k-- > 0;) work.push_back(fwd[k]);
+  }
+
+  void gen(int32_t root) {
+    work.push_back(Item{GEN, root, false, false, -1, 0});
+    while (!work.empty()) {
+      const Item it = work.back();
+      work.pop_back();
+      switch (it.what) {
+        case INVERT: put(mk(OP_INV)); continue;
+        case SQUARE: put(mk(OP_SQR)); continue;
+        case APPLY_POP: apply(node(it.node), it.swap, true, -1); continue;
+        case APPLY_DIRECT: apply(node(it.node), it.swap, false, it.other); continue;
+        case POW_CONST: {
+          const Node& n = node(it.node);
+          Instr ins = mk((n.kind == N_POW || n.kind == N_POWNEG) ? OP_POWU : OP_NPOWU,
+                         (n.kind == N_POWNEG || n.kind == N_NEGPOWNEG) ? F_NEGR : 0);
+          ins.src = SRC_CONST;
+          patches.push_back(ConstPatch{(uint32_t)tape.size(), fn, rep[n.r], false, false});
+          put(ins);
+          continue;
+        }
+        case MUL_INVCONST: {
+          const Node& n = node(it.node);
+          Instr ins = mk(OP_MUL);
+          ins.src = SRC_CONST;
+          patches.push_back(ConstPatch{(uint32_t)tape.size(), fn, rep[n.r], true, false});
+          put(ins);
+          continue;
+        }
+        case AFTER: {
+          // ACC holds shared node it.node, consumed once by the parent that asked for it
+          const int32_t u = rep[it.node];
+          --remaining[u];
+          if (remaining[u] >= 1 && temp_of[u] < 0) {
+            const int s = alloc_temp();
+            if (s >= 0) {
+              Instr ins = mk(OP_SAVE);
+              ins.arg = (uint32_t)s;
+              put(ins);
+              temp_of[u] = s;
+            }
+          }
+          continue;
+        }
+        case PRE: {
+          // the block serves all its references to this term with one evaluation
+          AccList& al = acc_lists[it.aux];
+          const int32_t t = rep[it.node];
+          const int extra = (int)al.acc.size() - 1;
+          if (leaf_like(t) || extra <= 0) continue;
+          if (temp_of[t] >= 0) al.post_consume = true;       // read from its temp: release after the load
+          else remaining[t] -= extra;
+          continue;
+        }
+        case ACCUM: {
+          if (acc_lists[it.aux].post_consume)
+            for (size_t k = 1; k < acc_lists[it.aux].acc.size(); ++k) consume(it.node);
+          for (const Acc& a : acc_lists[it.aux].acc) {
+            Instr ins = mk(OP_ACCUM, (a.minus ? F_SWAP : 0) | (a.init ? F_INIT : 0));
+            ins.arg = (uint32_t)a.slot;
+            put(ins);
+          }
+          continue;
+        }
+        case ADOPT: {
+          // the sum's value now lives in temp slot it.aux
+          temp_of[it.node] = it.aux;
+          continue;
+        }
+        default: break;
+      }
+      // ---- GEN: bring node it.node into ACC
+      const int32_t u = rep[it.node];
+      const Node& n = f.nodes[u];
+      if (direct(u)) {
+        Instr ins = mk(OP_LOAD, it.push ? F_PUSH : 0);
+        if (it.push) { ++depth; max_depth = std::max(max_depth, depth); }
+        operand(ins, u);
+        put(ins);
+        continue;
+      }
+      const int32_t l = rep[n.l], r = rep[n.r];
+      const bool is_pow = n.kind == N_POW || n.kind == N_POWNEG || n.kind == N_NEGPOW || n.kind == N_NEGPOWNEG;
+      if (!is_pow && can_coevaluate(l, r)) {
+        // sibling sums with common terms: run the joint block first, then come back to this node,
+        // whose operands are then both parked in temps
+        work.push_back(Item{GEN, u, false, false, -1, 0});
+        schedule_coevaluation(l, r, it.push);
+        continue;
+      }
+      if (shared(u)) work.push_back(Item{AFTER, u, false, false, -1, 0});
+      else --remaining[u];
+      if (is_pow && f.nodes[r].is_const) {
+        work.push_back(Item{POW_CONST, u, false, false, -1, 0});
+        work.push_back(Item{GEN, l, it.push, false, -1, 0});
+        continue;
+      }
+      if (n.kind == N_DIV && f.nodes[r].is_const) {
+        work.push_back(Item{MUL_INVCONST, u, false, false, -1, 0});
+        work.push_back(Item{GEN, l, it.push, false, -1, 0});
+        continue;
+      }
+      if (n.kind == N_MUL && l == r && !direct(l)) {
+        work.push_back(Item{SQUARE, u, false, false, -1, 0});
+        work.push_back(Item{GEN, l, it.push, false, -1, 0});
+        --remaining[l];                               // the second reference is served by the square
+        continue;
+      }
+      const bool push = it.push;
+      const bool dl = direct(l), dr = direct(r);
+      const unsigned a = f.nodes[l].need, b = f.nodes[r].need;
+      const bool left_first = std::max(a, b + 1) <= std::max(b, a + 1);
+      if (n.kind == N_DIV) {
+        if (dl) {                      // invert the divisor, multiply by the simple numerator
+          work.push_back(Item{APPLY_DIRECT, u, false, true, l, 0});
+          work.push_back(Item{INVERT, -1, false, false, -1, 0});
+          work.push_back(Item{GEN, r, push, false, -1, 0});
+        } else if (left_first) {
+          work.push_back(Item{APPLY_POP, u, false, true, -1, 0});
+          work.push_back(Item{INVERT, -1, false, false, -1, 0});
+          work.push_back(Item{GEN, r, true, false, -1, 0});
+          work.push_back(Item{GEN, l, push, false, -1, 0});
+        } else {
+          work.push_back(Item{APPLY_POP, u, false, false, -1, 0});
+          work.push_back(Item{GEN, l, true, false, -1, 0});
+          work.push_back(Item{INVERT, -1, false, false, -1, 0});
+          work.push_back(Item{GEN, r, push, false, -1, 0});
+        }
+      } else if (dr) {
+        work.push_back(Item{APPLY_DIRECT, u, false, false, r, 0});
+        work.push_back(Item{GEN, l, push, false, -1, 0});
+      } else if (dl) {
+        work.push_back(Item{APPLY_DIRECT, u, false, true, l, 0});
+        work.push_back(Item{GEN, r, push, false, -1, 0});
+      } else if (left_first) {
+        work.push_back(Item{APPLY_POP, u, false, true, -1, 0});
+        work.push_back(Item{GEN, r, true, false, -1, 0});
+        work.push_back(Item{GEN, l, push, false, -1, 0});
+      } else {
+        work.push_back(Item{APPLY_POP, u, false, false, -1, 0});
+        work.push_back(Item{GEN, l, true, false, -1, 0});
+        work.push_back(Item{GEN, r, push, false, -1, 0});
+      }
+    }
+  }
 };
 }  // namespace
 
 void Collection::emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots) {
-  const Function& f = functions[fn];
-  Emitter em{f, fn, tape, patches};
-  // Explicit work stack (expressions can be nested 10^5 deep: no recursion); items are
-  // pushed in reverse execution order.
-  struct Item { uint8_t what; int32_t node; bool push; bool swap; int32_t other; };
-  enum { GEN, APPLY_POP, APPLY_DIRECT, INVERT, POW_CONST, MUL_INVCONST };
-  std::vector<Item> work;
-  work.push_back(Item{GEN, f.root, false, false, -1});
-  auto direct = [&](int32_t i) { return em.direct(i); };
-  while (!work.empty()) {
-    const Item it = work.back();
-    work.pop_back();
-    switch (it.what) {
-      case INVERT: em.put(Emitter::mk(OP_INV)); continue;
-      case APPLY_POP: em.apply(f.nodes[it.node], it.swap, SRC_POP, -1); continue;
-      case APPLY_DIRECT: em.apply(f.nodes[it.node], it.swap, SRC_NONE, it.other); continue;
-      case POW_CONST: {
-        const Node& n = f.nodes[it.node];
-        Instr ins = Emitter::mk((n.kind == N_POW || n.kind == N_POWNEG) ? OP_POWU : OP_NPOWU,
-                                (n.kind == N_POWNEG || n.kind == N_NEGPOWNEG) ? F_NEGR : 0);
-        ins.src = SRC_CONST;
-        patches.push_back(ConstPatch{(uint32_t)tape.size(), fn, n.r, false, false});
-        em.put(ins);
-        continue;
-      }
-      case MUL_INVCONST: {
-        const Node& n = f.nodes[it.node];
-        Instr ins = Emitter::mk(OP_MUL);
-        ins.src = SRC_CONST;
-        patches.push_back(ConstPatch{(uint32_t)tape.size(), fn, n.r, true, false});
-        em.put(ins);
-        continue;
-      }
-      default: break;
-    }
-    const Node& n = f.nodes[it.node];
-    if (direct(it.node)) {
-      Instr ins = Emitter::mk(OP_LOAD, it.push ? F_PUSH : 0);
-      if (it.push) { ++em.depth; em.max_depth = std::max(em.max_depth, em.depth); }
-      em.operand(ins, it.node);
-      em.put(ins);
-      continue;
-    }
-    const bool dl = direct(n.l), dr = direct(n.r);
-    const bool is_pow = n.kind == N_POW || n.kind == N_POWNEG || n.kind == N_NEGPOW || n.kind == N_NEGPOWNEG;
-    const unsigned a = f.nodes[n.l].need, b = f.nodes[n.r].need;
-    const bool left_first = std::max(a, b + 1) <= std::max(b, a + 1);
-    if (is_pow && f.nodes[n.r].is_const) {
-      work.push_back(Item{POW_CONST, it.node, false, false, -1});
-      work.push_back(Item{GEN, n.l, it.push, false, -1});
-    } else if (n.kind == N_DIV && f.nodes[n.r].is_const) {
-      work.push_back(Item{MUL_INVCONST, it.node, false, false, -1});
-      work.push_back(Item{GEN, n.l, it.push, false, -1});
-    } else if (n.kind == N_DIV) {
-      if (dl) {                      // invert the divisor, multiply by the simple numerator
-        work.push_back(Item{APPLY_DIRECT, it.node, false, true, n.l});
-        work.push_back(Item{INVERT, -1, false, false, -1});
-        work.push_back(Item{GEN, n.r, it.push, false, -1});
-      } else if (left_first) {
-        work.push_back(Item{APPLY_POP, it.node, false, true, -1});
-        work.push_back(Item{INVERT, -1, false, false, -1});
-        work.push_back(Item{GEN, n.r, true, false, -1});
-        work.push_back(Item{GEN, n.l, it.push, false, -1});
-      } else {
-        work.push_back(Item{APPLY_POP, it.node, false, false, -1});
-        work.push_back(Item{GEN, n.l, true, false, -1});
-        work.push_back(Item{INVERT, -1, false, false, -1});
-        work.push_back(Item{GEN, n.r, it.push, false, -1});
-      }
-    } else if (dr) {
-      work.push_back(Item{APPLY_DIRECT, it.node, false, false, n.r});
-      work.push_back(Item{GEN, n.l, it.push, false, -1});
-    } else if (dl) {
-      work.push_back(Item{APPLY_DIRECT, it.node, false, true, n.l});
-      work.push_back(Item{GEN, n.r, it.push, false, -1});
-    } else if (left_first) {
-      work.push_back(Item{APPLY_POP, it.node, false, true, -1});
-      work.push_back(Item{GEN, n.r, true, false, -1});
-      work.push_back(Item{GEN, n.l, it.push, false, -1});
-    } else {
-      work.push_back(Item{APPLY_POP, it.node, false, false, -1});
-      work.push_back(Item{GEN, n.l, true, false, -1});
-      work.push_back(Item{GEN, n.r, it.push, false, -1});
-    }
-  }
+  FnEmitter em(functions[fn], fn, tape, patches, enable_cse, temp_budget);
+  em.gen(functions[fn].root);
   for (uint32_t slot : out_slots) {
-    Instr st = Emitter::mk(OP_STORE);
+    Instr st = FnEmitter::mk(OP_STORE);
     st.arg = slot;
     em.put(st);
   }
   stack_depth = std::max(stack_depth, em.max_depth);
+  n_temps = std::max(n_temps, em.temps_used);
+  n_slots = std::max(n_slots, em.max_depth + em.temps_used);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -588,6 +880,8 @@ bool Collection::finish(std::string& err) {
   tape.clear();
   patches.clear();
   stack_depth = 0;
+  n_temps = 0;
+  n_slots = 0;
   work = WorkCount{};
   fn_start.clear();
   for (size_t i = 0; i < functions.size(); ++i) {
@@ -640,16 +934,23 @@ void Collection::peephole() {
       in.src = SRC_VAR;
     }
     uint8_t fx = FX_GENERIC;
-    const bool swap = in.flags & F_SWAP, push = in.flags & F_PUSH;
-    const uint8_t other = in.flags & ~(F_SWAP | F_PUSH);
+    const bool swap = in.flags & F_SWAP, push = in.flags & F_PUSH, init = in.flags & F_INIT;
+    const uint8_t other = in.flags & ~(F_SWAP | F_PUSH | F_INIT);
     if (!other) {
       switch (in.op) {
         case OP_LOAD:
           if (in.src == SRC_VAR) fx = push ? FX_PUSH_LOAD_VAR : FX_LOAD_VAR;
           else if (in.src == SRC_CONST) fx = push ? FX_PUSH_LOAD_CONST : FX_LOAD_CONST;
+          else if (in.src == SRC_TMP && !push) fx = FX_LOAD_TMP;
           break;
         case OP_ADD:
-          fx = in.src == SRC_VAR ? FX_ADD_VAR : in.src == SRC_CONST ? FX_ADD_CONST : in.src == SRC_POP ? FX_ADD_POP : FX_GENERIC;
+          fx = in.src == SRC_VAR ? FX_ADD_VAR : in.src == SRC_CONST ? FX_ADD_CONST : in.src == SRC_POP ? FX_ADD_POP :
+               in.src == SRC_TMP ? FX_ADD_TMP : FX_GENERIC;
+          break;
+        case OP_SAVE: fx = FX_SAVE; break;
+        case OP_ACCUM:
+          if (init) fx = swap ? FX_GENERIC : FX_ACCUM_INIT;
+          else fx = swap ? FX_ACCUM_SUB : FX_ACCUM_ADD;
           break;
         case OP_SUB:
           if (in.src == SRC_VAR) fx = swap ? FX_RSUB_VAR : FX_SUB_VAR;
@@ -657,7 +958,8 @@ void Collection::peephole() {
           else if (in.src == SRC_POP) fx = swap ? FX_RSUB_POP : FX_SUB_POP;
           break;
         case OP_MUL:
-          fx = in.src == SRC_VAR ? FX_MUL_VAR : in.src == SRC_CONST ? FX_MUL_CONST : in.src == SRC_POP ? FX_MUL_POP : FX_GENERIC;
+          fx = in.src == SRC_VAR ? FX_MUL_VAR : in.src == SRC_CONST ? FX_MUL_CONST : in.src == SRC_POP ? FX_MUL_POP :
+               in.src == SRC_TMP ? FX_MUL_TMP : FX_GENERIC;
           break;
         case OP_POWU: fx = FX_POWU; break;
         case OP_INV: fx = FX_INV; break;

@@ -92,6 +92,11 @@ struct Collection {
   std::vector<Instr> tape;                    // prime independent structure (imm = 0)
   std::vector<ConstPatch> patches;
   uint32_t stack_depth = 0;                   // spill slots the tape needs
+  uint32_t n_temps = 0;                       // temp slots (shared sub-expressions, co-evaluated sums)
+  uint32_t n_slots = 0;                       // shared-memory slots per probe: max over functions of spill + temps
+                                              // (spill slots count up from 0, temp slots down from n_slots - 1)
+  bool enable_cse = true;                     // share structurally equal sub-expressions
+  int temp_budget = 0;                        // temp slots per function (0: automatic, see FnEmitter)
   std::vector<uint32_t> fn_start;             // tape offset of every distinct function, then the end
   // chunk tables: for C = 1, 2, 4, ... the C + 1 offsets that cut the tape into C runs of whole
   // functions with about equal instruction counts (flattened: table c starts at chunk_table_off[c])

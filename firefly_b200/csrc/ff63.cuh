@@ -254,6 +254,85 @@ FF63_D u64 sqr_pm_dev(u64 x, u32 d) {
   return r;
 }
 
+// in-place forms (x <- x*y, x <- x*x): same arithmetic, the accumulator keeps its registers
+FF63_D void mul_pm_ip(u64& x, u64 y, u32 d) {
+  asm("{\n\t"
+      ".reg .u32 x0,x1,y0,y1,w0,w1,w2,w3,u0,u1,v0,v1,r0,r1,r2,t;\n\t"
+      ".reg .u64 t0,ma,mb,t3,u,v;\n\t"
+      ".reg .pred p;\n\t"
+      "mov.b64 {x0,x1}, %0;\n\t"
+      "mov.b64 {y0,y1}, %1;\n\t"
+      "mul.wide.u32 t0, x0, y0;\n\t"
+      "mul.wide.u32 ma, x0, y1;\n\t"
+      "mul.wide.u32 mb, x1, y0;\n\t"
+      "mul.wide.u32 t3, x1, y1;\n\t"
+      "mov.b64 {w0,w1}, t0;\n\t"
+      "mov.b64 {w2,w3}, t3;\n\t"
+      "mov.b64 {u0,u1}, ma;\n\t"
+      "mov.b64 {v0,v1}, mb;\n\t"
+      "add.cc.u32 w1, w1, u0;\n\t"
+      "addc.cc.u32 w2, w2, u1;\n\t"
+      "addc.u32 w3, w3, 0;\n\t"
+      "add.cc.u32 w1, w1, v0;\n\t"
+      "addc.cc.u32 w2, w2, v1;\n\t"
+      "addc.u32 w3, w3, 0;\n\t"
+      // fold 1: (w1:w0) + d*w2 + (d*w3 << 32)
+      "mul.wide.u32 u, w2, %2;\n\t"
+      "mul.wide.u32 v, w3, %2;\n\t"
+      "mov.b64 {u0,u1}, u;\n\t"
+      "mov.b64 {v0,v1}, v;\n\t"
+      "add.cc.u32 r0, w0, u0;\n\t"
+      "addc.cc.u32 r1, w1, u1;\n\t"
+      "addc.u32 r2, v1, 0;\n\t"
+      "add.cc.u32 r1, r1, v0;\n\t"
+      "addc.u32 r2, r2, 0;\n\t"
+      // fold 2: + d*r2 (< 2^32), one conditional +d on wrap
+      "mul.lo.u32 t, r2, %2;\n\t"
+      "add.cc.u32 r0, r0, t;\n\t"
+      "addc.cc.u32 r1, r1, 0;\n\t"
+      "addc.u32 t, 0, 0;\n\t"
+      "setp.ne.u32 p, t, 0;\n\t"
+      "@p add.u32 r0, r0, %2;\n\t"
+      "mov.b64 %0, {r0,r1};\n\t"
+      "}" : "+l"(x) : "l"(y), "r"(d));
+}
+FF63_D void sqr_pm_ip(u64& x, u32 d) {
+  asm("{\n\t"
+      ".reg .u32 x0,x1,w0,w1,w2,w3,u0,u1,v0,v1,r0,r1,r2,t;\n\t"
+      ".reg .u64 t0,m,t3,u,v;\n\t"
+      ".reg .pred p;\n\t"
+      "mov.b64 {x0,x1}, %0;\n\t"
+      "mul.wide.u32 t0, x0, x0;\n\t"
+      "mul.wide.u32 m, x0, x1;\n\t"
+      "mul.wide.u32 t3, x1, x1;\n\t"
+      "mov.b64 {w0,w1}, t0;\n\t"
+      "mov.b64 {w2,w3}, t3;\n\t"
+      "mov.b64 {u0,u1}, m;\n\t"
+      "add.cc.u32 w1, w1, u0;\n\t"
+      "addc.cc.u32 w2, w2, u1;\n\t"
+      "addc.u32 w3, w3, 0;\n\t"
+      "add.cc.u32 w1, w1, u0;\n\t"
+      "addc.cc.u32 w2, w2, u1;\n\t"
+      "addc.u32 w3, w3, 0;\n\t"
+      "mul.wide.u32 u, w2, %1;\n\t"
+      "mul.wide.u32 v, w3, %1;\n\t"
+      "mov.b64 {u0,u1}, u;\n\t"
+      "mov.b64 {v0,v1}, v;\n\t"
+      "add.cc.u32 r0, w0, u0;\n\t"
+      "addc.cc.u32 r1, w1, u1;\n\t"
+      "addc.u32 r2, v1, 0;\n\t"
+      "add.cc.u32 r1, r1, v0;\n\t"
+      "addc.u32 r2, r2, 0;\n\t"
+      "mul.lo.u32 t, r2, %1;\n\t"
+      "add.cc.u32 r0, r0, t;\n\t"
+      "addc.cc.u32 r1, r1, 0;\n\t"
+      "addc.u32 t, 0, 0;\n\t"
+      "setp.ne.u32 p, t, 0;\n\t"
+      "@p add.u32 r0, r0, %1;\n\t"
+      "mov.b64 %0, {r0,r1};\n\t"
+      "}" : "+l"(x) : "r"(d));
+}
+
 // branch-free lazy add / sub / neg (same values as add_lazy / sub_lazy / neg_lazy above)
 FF63_D u64 add_lazy_dev(u64 a, u64 b, u32 d) {
   u64 r;

@@ -23,6 +23,8 @@
 //     Zero divisors are replaced by 1 in the tree and produce 0 (reference: a/0 = 0).
 #include "kernels.cuh"
 
+#include <algorithm>
+
 #include "ff63.cuh"
 
 namespace ffgpu {
@@ -42,6 +44,8 @@ __device__ __forceinline__ u64 fsqr(u64 a, const Field& F) { return ff63::sqr_pm
 __device__ __forceinline__ u64 fadd(u64 a, u64 b, const Field& F) { return ff63::add_lazy_dev(a, b, F.d); }
 __device__ __forceinline__ u64 fsub(u64 a, u64 b, const Field& F) { return ff63::sub_lazy_dev(a, b, F.d, F.p); }
 __device__ __forceinline__ u64 fneg(u64 a, const Field& F) { return ff63::neg_lazy_dev(a, F.d, F.p); }
+__device__ __forceinline__ void fmul_ip(u64& a, u64 b, const Field& F) { ff63::mul_pm_ip(a, b, F.d); }
+__device__ __forceinline__ void fsqr_ip(u64& a, const Field& F) { ff63::sqr_pm_ip(a, F.d); }
 __device__ __forceinline__ u64 fcanon(u64 a, const Field& F) { return ff63::canon_pm(a, F.c, F.p); }
 
 // x^e, e uniform across the warp, left-to-right binary; x^0 = 1 (reference mod_pow, FFInt.cpp:371-383)
@@ -59,10 +63,10 @@ __device__ __forceinline__ void pow_uniform(u64 (&a)[K], u64 e, const Field& F) 
 #pragma unroll 1
   for (; bit >= 0; --bit) {
 #pragma unroll
-    for (int k = 0; k < K; k++) a[k] = fsqr(a[k], F);
+    for (int k = 0; k < K; k++) fsqr_ip(a[k], F);
     if ((e >> bit) & 1) {
 #pragma unroll
-      for (int k = 0; k < K; k++) a[k] = fmul(a[k], base[k], F);
+      for (int k = 0; k < K; k++) fmul_ip(a[k], base[k], F);
     }
   }
 }
@@ -198,7 +202,7 @@ union InstrWord {
 };
 
 template <int K, int THREADS, bool VEC>
-__global__ void __launch_bounds__(THREADS) eval_tape_kernel(const EvalParams prm) {
+__global__ void __launch_bounds__(THREADS, (K == 8 ? 768 : 1024) / THREADS) eval_tape_kernel(const EvalParams prm) {
   extern __shared__ __align__(16) u64 smem[];
   u64* const scratch = smem;                 // 64 words for block_inverse
   u64* const stk = smem + 64 + threadIdx.x;  // [slot][k][thread], this thread's column
@@ -207,30 +211,38 @@ __global__ void __launch_bounds__(THREADS) eval_tape_kernel(const EvalParams prm
   // Points owned by this thread.  VEC: pairs (2t, 2t+1) inside rows of 2*THREADS points, so that
   // every load/store is one 16-byte access per lane and a warp covers 512 contiguous bytes.
   const u64 tile = (u64)blockIdx.x * (u64)(THREADS * K);
-  const u64 first = VEC ? tile + 2 * threadIdx.x : tile + threadIdx.x;
   constexpr u32 STEP = VEC ? 2 * THREADS : THREADS;       // distance between this thread's accesses
   constexpr int NACC = VEC ? K / 2 : K;                   // accesses per variable
-  const bool full = tile + (u64)(THREADS * K) <= prm.n_points;   // block uniform
-  const u64* const vbase = reinterpret_cast<const u64*>(prm.values) + first;
-  u64* const obase = reinterpret_cast<u64*>(prm.out) + first;
+  // Tile-relative offsets of this thread's accesses, clamped into the batch: lanes beyond the end
+  // recompute the last valid point and never store, so the hot loop has no bounds checks.
+  const u64 left64 = prm.n_points - tile;                 // > 0: the grid covers exactly the batch
+  const u32 left = left64 < (u64)(THREADS * K) ? (u32)left64 : (u32)(THREADS * K);
+  const u32 own = VEC ? 2 * threadIdx.x : threadIdx.x;
+  u32 off[NACC];
+#pragma unroll
+  for (int j = 0; j < NACC; j++) {
+    const u32 o = own + j * STEP, last = left - (VEC ? 2 : 1);
+    off[j] = o < last ? o : last;
+  }
+  const u64* const vbase = reinterpret_cast<const u64*>(prm.values) + tile;
+  u64* const obase = reinterpret_cast<u64*>(prm.out) + tile;
 
-  auto in_range = [&](int j) { return first + (u64)j * STEP < prm.n_points; };
   auto load_var = [&](u32 var, u64 (&b)[K]) {
     const u64* row = vbase + (u64)var * prm.in_stride;
     if (VEC) {
 #pragma unroll
       for (int j = 0; j < NACC; j++) {
-        // n_points is even and rows are 16-byte aligned on this path: a pair is valid or not as a whole
-        ulonglong2 v = make_ulonglong2(1, 1);
-        if (full || in_range(j)) v = __ldg(reinterpret_cast<const ulonglong2*>(row + j * STEP));
+        // n_points is even and rows are 16-byte aligned on this path
+        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(row + off[j]));
         b[2 * j] = v.x;
         b[2 * j + 1] = v.y;
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < NACC; j++) b[j] = (full || in_range(j)) ? __ldg(row + j * STEP) : 1;
+      for (int j = 0; j < NACC; j++) b[j] = __ldg(row + off[j]);
     }
   };
+  auto in_range = [&](int j) { return own + j * STEP < left; };
   auto push = [&](const u64 (&a)[K], u32 sp) {
 #pragma unroll
     for (int k = 0; k < K; k++) stk[(sp * K + k) * THREADS] = a[k];
@@ -238,6 +250,19 @@ __global__ void __launch_bounds__(THREADS) eval_tape_kernel(const EvalParams prm
   auto pop = [&](u64 (&b)[K], u32 sp) {
 #pragma unroll
     for (int k = 0; k < K; k++) b[k] = stk[(sp * K + k) * THREADS];
+  };
+
+  // temp slots (shared sub-expressions, co-evaluated sums) count down from the last slot
+  const u32 tmp_top = prm.n_slots - 1;
+  auto tmp_get = [&](u64 (&b)[K], u32 slot) {
+    const u64* t = stk + (size_t)(tmp_top - slot) * (K * THREADS);
+#pragma unroll
+    for (int k = 0; k < K; k++) b[k] = t[k * THREADS];
+  };
+  auto tmp_put = [&](const u64 (&a)[K], u32 slot) {
+    u64* t = stk + (size_t)(tmp_top - slot) * (K * THREADS);
+#pragma unroll
+    for (int k = 0; k < K; k++) t[k * THREADS] = a[k];
   };
 
   u64 acc[K];
@@ -313,27 +338,27 @@ __global__ void __launch_bounds__(THREADS) eval_tape_kernel(const EvalParams prm
       case FX_MUL_VAR:
         load_var(ins.arg, b);
 #pragma unroll
-        for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], b[k], F);
+        for (int k = 0; k < K; k++) fmul_ip(acc[k], b[k], F);
         break;
       case FX_MUL_CONST:
 #pragma unroll
-        for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], ins.imm, F);
+        for (int k = 0; k < K; k++) fmul_ip(acc[k], ins.imm, F);
         break;
       case FX_MUL_POP:
         pop(b, --sp);
 #pragma unroll
-        for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], b[k], F);
+        for (int k = 0; k < K; k++) fmul_ip(acc[k], b[k], F);
         break;
       case FX_SQR:
 #pragma unroll
-        for (int k = 0; k < K; k++) acc[k] = fsqr(acc[k], F);
+        for (int k = 0; k < K; k++) fsqr_ip(acc[k], F);
         break;
       case FX_POWU: {
         // FFInt::pow(const FFInt&) with a lane-uniform exponent residue (FFInt.cpp:155-179)
         const u64 e = ins.imm;
         if (e == 2) {
 #pragma unroll
-          for (int k = 0; k < K; k++) acc[k] = fsqr(acc[k], F);
+          for (int k = 0; k < K; k++) fsqr_ip(acc[k], F);
         } else if (e < (F.p >> 1)) {
           pow_uniform<K>(acc, e, F);
         } else {
@@ -345,18 +370,49 @@ __global__ void __launch_bounds__(THREADS) eval_tape_kernel(const EvalParams prm
       case FX_INV:
         block_inverse<K, THREADS>(acc, F, scratch);
         break;
+      case FX_SAVE:
+        tmp_put(acc, ins.arg);
+        break;
+      case FX_ACCUM_INIT:
+        tmp_put(acc, ins.arg);
+        break;
+      case FX_ACCUM_ADD:
+        tmp_get(b, ins.arg);
+#pragma unroll
+        for (int k = 0; k < K; k++) b[k] = fadd(b[k], acc[k], F);
+        tmp_put(b, ins.arg);
+        break;
+      case FX_ACCUM_SUB:
+        tmp_get(b, ins.arg);
+#pragma unroll
+        for (int k = 0; k < K; k++) b[k] = fsub(b[k], acc[k], F);
+        tmp_put(b, ins.arg);
+        break;
+      case FX_LOAD_TMP:
+        tmp_get(acc, ins.arg);
+        break;
+      case FX_ADD_TMP:
+        tmp_get(b, ins.arg);
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[k] = fadd(acc[k], b[k], F);
+        break;
+      case FX_MUL_TMP:
+        tmp_get(b, ins.arg);
+#pragma unroll
+        for (int k = 0; k < K; k++) fmul_ip(acc[k], b[k], F);
+        break;
       case FX_STORE: {
         u64* row = obase + (u64)ins.arg * prm.out_stride;
         if (VEC) {
 #pragma unroll
           for (int j = 0; j < NACC; j++)
-            if (full || in_range(j))
-              *reinterpret_cast<ulonglong2*>(row + j * STEP) =
+            if (in_range(j))
+              *reinterpret_cast<ulonglong2*>(row + off[j]) =
                   make_ulonglong2(fcanon(acc[2 * j], F), fcanon(acc[2 * j + 1], F));
         } else {
 #pragma unroll
           for (int j = 0; j < NACC; j++)
-            if (full || in_range(j)) row[j * STEP] = fcanon(acc[j], F);
+            if (in_range(j)) row[off[j]] = fcanon(acc[j], F);
         }
         break;
       }
@@ -376,6 +432,7 @@ __global__ void __launch_bounds__(THREADS) eval_tape_kernel(const EvalParams prm
 #pragma unroll
             for (int k = 0; k < K; k++) b[k] = ins.imm;
             break;
+          case SRC_TMP: tmp_get(b, ins.arg); break;
           default:
 #pragma unroll
             for (int k = 0; k < K; k++) b[k] = 0;
@@ -397,7 +454,7 @@ __global__ void __launch_bounds__(THREADS) eval_tape_kernel(const EvalParams prm
             break;
           case OP_MUL:
 #pragma unroll
-            for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], b[k], F);
+            for (int k = 0; k < K; k++) fmul_ip(acc[k], b[k], F);
             break;
           case OP_MULADD: {
             u64 x[K];
@@ -408,7 +465,21 @@ __global__ void __launch_bounds__(THREADS) eval_tape_kernel(const EvalParams prm
           }
           case OP_SQR:
 #pragma unroll
-            for (int k = 0; k < K; k++) acc[k] = fsqr(acc[k], F);
+            for (int k = 0; k < K; k++) fsqr_ip(acc[k], F);
+            break;
+          case OP_SAVE:
+            tmp_put(acc, ins.arg);
+            break;
+          case OP_ACCUM:
+            if (ins.flags & F_INIT) {
+#pragma unroll
+              for (int k = 0; k < K; k++) b[k] = (ins.flags & F_SWAP) ? fneg(acc[k], F) : acc[k];
+            } else {
+              tmp_get(b, ins.arg);
+#pragma unroll
+              for (int k = 0; k < K; k++) b[k] = (ins.flags & F_SWAP) ? fsub(b[k], acc[k], F) : fadd(b[k], acc[k], F);
+            }
+            tmp_put(b, ins.arg);
             break;
           case OP_NEG:
 #pragma unroll
@@ -421,7 +492,7 @@ __global__ void __launch_bounds__(THREADS) eval_tape_kernel(const EvalParams prm
             const u64 e = ins.imm;
             if (e == 2) {
 #pragma unroll
-              for (int k = 0; k < K; k++) acc[k] = fsqr(acc[k], F);
+              for (int k = 0; k < K; k++) fsqr_ip(acc[k], F);
             } else if (e < (F.p >> 1)) {
               pow_uniform<K>(acc, e, F);
             } else {
@@ -435,7 +506,7 @@ __global__ void __launch_bounds__(THREADS) eval_tape_kernel(const EvalParams prm
             const int e = (int)(0u - (u32)ins.imm);
             if (e == 2) {
 #pragma unroll
-              for (int k = 0; k < K; k++) acc[k] = fsqr(acc[k], F);
+              for (int k = 0; k < K; k++) fsqr_ip(acc[k], F);
             } else if (e >= 0) {
               pow_uniform<K>(acc, (u64)e, F);
             } else {
@@ -459,7 +530,7 @@ __global__ void __launch_bounds__(THREADS) eval_tape_kernel(const EvalParams prm
 #pragma unroll
             for (int k = 0; k < K; k++) {
               const int j = VEC ? k / 2 : k;
-              if (full || in_range(j)) row[j * STEP + (VEC ? (k & 1) : 0)] = fcanon(acc[k], F);
+              if (in_range(j)) row[off[j] + (VEC ? (k & 1) : 0)] = fcanon(acc[k], F);
             }
             break;
           }
@@ -503,21 +574,53 @@ cudaError_t launch_t(const EvalParams& prm, const LaunchShape& sh, cudaStream_t 
 
 }  // namespace
 
-LaunchShape choose_shape(uint64_t n_points, uint32_t stack_depth, int sm_count, int force_k, int force_threads,
+LaunchShape choose_shape(uint64_t n_points, uint32_t n_slots, int sm_count, int force_k, int force_threads,
                          unsigned max_chunks) {
   LaunchShape s;
-  s.threads = force_threads ? force_threads : 256;
-  if (force_k) {
-    s.k = force_k;
+  auto smem_of = [&](int k, int th) { return (size_t)(64 + (size_t)n_slots * k * th) * sizeof(uint64_t); };
+  // resident warps per SM for a shape: registers (launch bounds: 80 per thread at 8 probes per thread, 64
+  // below) and shared memory (227 KB per SM, 1 KB reserved per block)
+  auto warps_of = [&](int k, int th) {
+    const int by_regs = (k == 8 ? 768 : 1024) / th;
+    const int by_smem = (int)((227 * 1024) / (smem_of(k, th) + 1024));
+    return std::min(by_regs, by_smem) * th / 32;
+  };
+  if (force_k || force_threads) {
+    s.threads = force_threads ? force_threads : 256;
+    s.k = force_k ? force_k : 8;
+    // the slots must fit in shared memory: back off K, then the block size
+    while (smem_of(s.k, s.threads) > 200 * 1024 && s.k > 1) s.k >>= 1;
+    while (smem_of(s.k, s.threads) > 200 * 1024 && s.threads > 128) s.threads >>= 1;
   } else {
     // small batches: spread over all SMs first (one point per lane), then add work per thread
     const uint64_t lanes = (uint64_t)sm_count * 1024;      // 4 CTAs of 256 threads per SM
-    s.k = n_points >= 8 * lanes ? 8 : n_points >= 4 * lanes ? 4 : n_points >= 2 * lanes ? 2 : 1;
+    // (a many-function collection also spreads over grid.y, one run of functions per block)
+    const uint64_t par = n_points * (uint64_t)(max_chunks ? max_chunks : 1);
+    int kmax = par >= 8 * lanes ? 8 : par >= 4 * lanes ? 4 : par >= 2 * lanes ? 2 : 1;
+    while (kmax > 1 && (uint64_t)kmax * 128 > n_points + 127) kmax >>= 1;   // never more lanes than points
+    // most probes per thread first, but never below 16 resident warps per SM if a smaller shape gets there
+    s.k = 1;
+    s.threads = 128;
+    int best = -1;
+    for (int k = kmax; k >= 1 && best < 0; k >>= 1)
+      for (int th : {256, 128})
+        if (smem_of(k, th) <= 200 * 1024 && warps_of(k, th) >= (k == 8 ? 16 : 24)) {
+          s.k = k;
+          s.threads = th;
+          best = 1;
+          break;
+        }
+    if (best < 0) {
+      // nothing reaches the target: take the shape with the most resident probes
+      long score = -1;
+      for (int k = kmax; k >= 1; k >>= 1)
+        for (int th : {256, 128}) {
+          if (smem_of(k, th) > 200 * 1024) continue;
+          const long sc = (long)warps_of(k, th) * k;
+          if (sc > score) { score = sc; s.k = k; s.threads = th; }
+        }
+    }
   }
-  // the spill stack must fit in shared memory: back off K, then the block size
-  auto smem_of = [&](int k, int th) { return (size_t)(64 + (size_t)stack_depth * k * th) * sizeof(uint64_t); };
-  while (smem_of(s.k, s.threads) > 200 * 1024 && s.k > 1) s.k >>= 1;
-  while (smem_of(s.k, s.threads) > 200 * 1024 && s.threads > 128) s.threads >>= 1;
   s.smem = smem_of(s.k, s.threads);
   const uint64_t per_block = (uint64_t)s.threads * s.k;
   s.blocks = (unsigned)((n_points + per_block - 1) / per_block);

@@ -17,7 +17,7 @@ struct EvalParams {
   uint64_t p;                 // 2^63 - c
   uint32_t c;
   uint32_t d;                 // 2c
-  uint32_t stack_depth;       // spill slots per lane
+  uint32_t n_slots;           // shared-memory slots per probe: spill slots from 0 up, temp slots from n_slots-1 down
   uint32_t n_instr;           // tape length without the terminators
   const uint32_t* chunk_bounds;  // device, n_chunks + 1 tape offsets at function boundaries (NULL: one chunk)
 };
@@ -31,7 +31,7 @@ struct LaunchShape {
   size_t smem;
 };
 
-LaunchShape choose_shape(uint64_t n_points, uint32_t stack_depth, int sm_count, int force_k, int force_threads,
+LaunchShape choose_shape(uint64_t n_points, uint32_t n_slots, int sm_count, int force_k, int force_threads,
                          unsigned max_chunks);
 cudaError_t launch_eval(const EvalParams& prm, const LaunchShape& shape, cudaStream_t stream);
 

@@ -55,6 +55,8 @@ enum Op : uint8_t {
   OP_NPOWL,   // ACC = ACC ^ -(int)SRC per lane  (F_SWAP likewise)
   OP_STORE,   // out[arg][point] = canonical(ACC)
   OP_MULADD,  // ACC = ACC * var[arg] + imm      (Horner step; src selects var/negvar for the factor)
+  OP_SAVE,    // temp[arg] = ACC                 (ACC unchanged)
+  OP_ACCUM,   // temp[arg] += ACC  (F_SWAP: -=;  F_INIT: temp[arg] = +-ACC);  ACC unchanged
   OP_COUNT
 };
 
@@ -67,6 +69,8 @@ enum Fast : uint8_t {
   FX_SUB_VAR, FX_RSUB_VAR, FX_RSUB_CONST, FX_SUB_POP, FX_RSUB_POP,
   FX_MUL_VAR, FX_MUL_CONST, FX_MUL_POP,
   FX_POWU, FX_INV, FX_STORE, FX_SQR,
+  FX_SAVE, FX_ACCUM_INIT, FX_ACCUM_ADD, FX_ACCUM_SUB,
+  FX_LOAD_TMP, FX_ADD_TMP, FX_MUL_TMP,
   FX_COUNT
 };
 
@@ -76,12 +80,14 @@ enum Src : uint8_t {
   SRC_VAR,      // values[arg][point]
   SRC_NEGVAR,   // -values[arg][point]
   SRC_CONST,    // imm
+  SRC_TMP,      // temp slot arg (non-destructive read)
 };
 
 enum Flags : uint8_t {
   F_PUSH = 1,   // OP_LOAD: push ACC before loading
   F_SWAP = 2,   // non-commutative ops: exchange the roles of ACC and SRC
   F_NEGR = 4,   // negate the result (the parser's `!` and `;` operators)
+  F_INIT = 8,   // OP_ACCUM: first contribution, the slot is overwritten
 };
 
 }  // namespace ffgpu

@@ -45,7 +45,12 @@ extern "C" {
 typedef struct ffgpu_ctx ffgpu_ctx;     /* a set of GPUs + streams + staging */
 typedef struct ffgpu_tape ffgpu_tape;   /* a compiled collection, resident on every GPU of its ctx */
 
-enum { FFGPU_CHECK_IS_EQUAL = 1 };      /* flags for ffgpu_compile*: detect duplicate functions */
+/* flags for ffgpu_compile*: */
+enum {
+  FFGPU_CHECK_IS_EQUAL = 1,   /* detect duplicate functions (ShuntingYardParser's check_is_equal) */
+  FFGPU_NO_CSE = 2,           /* do not share equal sub-expressions inside a function (for A/B tests) */
+  FFGPU_TEMPS_SHIFT = 8       /* bits 8..11: temp slots per function for shared sub-expressions (0 = automatic) */
+};
 
 /* ---- context ------------------------------------------------------------------------------ */
 /* device_ids == NULL or n_devices == 0: the calling thread's current CUDA device. */
@@ -68,7 +73,9 @@ size_t ffgpu_n_vars(const ffgpu_tape*);
 size_t ffgpu_n_functions(const ffgpu_tape*);   /* distinct functions */
 size_t ffgpu_n_out(const ffgpu_tape*);         /* values per point that ffgpu_eval returns */
 size_t ffgpu_n_instr(const ffgpu_tape*);       /* tape length (without the terminators) */
-size_t ffgpu_stack_depth(const ffgpu_tape*);
+size_t ffgpu_stack_depth(const ffgpu_tape*);    /* spill slots per probe */
+size_t ffgpu_n_temps(const ffgpu_tape*);        /* temp slots per probe (shared sub-expressions) */
+size_t ffgpu_n_slots(const ffgpu_tape*);        /* shared-memory slots per probe the kernel reserves (spill + temps) */
 /* RPN of distinct function i, tokens joined by ' '; returns the length needed (without NUL) */
 size_t ffgpu_rpn(const ffgpu_tape*, size_t i, char* buf, size_t cap);
 /* copy up to cap 16-byte instructions of the resolved tape (layout: firefly_b200/csrc/tape.hpp) */

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--shapes", default="4x256,4x512,8x128,8x256,2x256,2x512,4x128")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--ibp", type=int, default=0, help="also run an IBP-like collection with this many functions")
+    ap.add_argument("--temps", default="0", help="comma list of temp-slot budgets (0 = automatic, -1 = CSE off)")
     args = ap.parse_args()
     ctx = ff.Context()
     orc = Oracle()
@@ -40,9 +41,11 @@ def main():
     if args.ibp:
         funs, vars_ = W.ibp_like_collection(args.ibp, 8)
         work.append((f"ibp{args.ibp}", funs, vars_, min(n, 1 << 16)))
-    for name, funs, vars_, npts in work:
-        par = ff.GpuParser(ctx, funs, vars_)
+    work = [(f"{name}/t{t}", funs, vars_, npts, int(t)) for name, funs, vars_, npts in work for t in args.temps.split(",")]
+    for name, funs, vars_, npts, temps in work:
+        par = ff.GpuParser(ctx, funs, vars_, cse=temps >= 0, temps=max(temps, 0))
         par.set_prime(P0)
+        print(f"{name}: {par.n_instr} instr, spill {par.stack_depth}, temps {par.n_temps}, slots {par.n_slots}", flush=True)
         w = par.work()
         mm_eq = w["mm"] + 6 * w["inv"]
         vals = torch.empty((len(vars_), npts), dtype=torch.int64, device="cuda")
@@ -52,7 +55,7 @@ def main():
         host = ff.synthetic_points(len(vars_), npts, P0, seed=1)[:, idx]
         want = orc.parse(funs, vars_, P0).eval(np.ascontiguousarray(host))
         for shp in args.shapes.split(","):
-            k, th = (int(x) for x in shp.split("x"))
+            k, th = (0, 0) if shp == "auto" else (int(x) for x in shp.split("x"))
             par.set_launch(k, th)
             out.zero_()
             try:
@@ -73,7 +76,7 @@ def main():
             ok = np.array_equal(out.cpu().numpy().view(np.uint64)[:, idx], want)
             rate = npts / (best * 1e-3)
             res[f"{name}:{shp}"] = {"ms": best, "probes_per_s": rate, "gmm_eq_per_s": rate * mm_eq / 1e9, "ok": ok}
-            print(f"{name:10s} {shp:6s} {best:9.3f} ms  {rate:11.4e} probes/s  {rate*mm_eq/1e9:8.1f} GMMeq/s  ok={ok}", flush=True)
+            print(f"{name:14s} {shp:6s} {best:9.3f} ms  {rate:11.4e} probes/s  {rate*mm_eq/1e9:8.1f} GMMeq/s  ok={ok}", flush=True)
     print(json.dumps(res))
 
 

@@ -7,7 +7,7 @@ Field semantics: reference FFInt DEFAULT arithmetic (source/FFInt.cpp:130-192,22
 """
 import numpy as np
 
-from firefly_b200 import F_NEGR, F_PUSH, F_SWAP, OPS, SRCS
+from firefly_b200 import F_INIT, F_NEGR, F_PUSH, F_SWAP, OPS, SRCS
 
 OP = {n: i for i, n in enumerate(OPS)}
 SRC = {n: i for i, n in enumerate(SRCS)}
@@ -45,6 +45,7 @@ def run(tape: np.ndarray, point, p: int, n_out: int):
     out = [None] * n_out
     acc = 0
     stack = []
+    temps = {}
     for ins in tape:
         op, src, flags, arg, imm = int(ins["op"]), int(ins["src"]), int(ins["flags"]), int(ins["arg"]), int(ins["imm"])
         if op == OP["HALT"]:
@@ -61,6 +62,8 @@ def run(tape: np.ndarray, point, p: int, n_out: int):
             b = (-point[arg]) % p
         elif src == SRC["CONST"]:
             b = imm
+        elif src == SRC["TMP"]:
+            b = temps[arg]
         if op == OP["LOAD"]:
             if flags & F_PUSH:
                 stack.append(acc)
@@ -90,6 +93,11 @@ def run(tape: np.ndarray, point, p: int, n_out: int):
         elif op == OP["MULADD"]:
             x = point[arg] % p
             acc = (acc * x + imm) % p
+        elif op == OP["SAVE"]:
+            temps[arg] = acc
+        elif op == OP["ACCUM"]:
+            v = (-acc) % p if flags & F_SWAP else acc
+            temps[arg] = v if flags & F_INIT else (temps[arg] + v) % p
         else:
             raise ValueError(f"bad opcode {op}")
         if flags & F_NEGR:
