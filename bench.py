@@ -119,8 +119,12 @@ class ClockSampler:
 
 
 def work_of(par):
+    """(reference-token-list work, MM-eq of it, MM-eq the compiled tape executes)"""
     w = par.work()
     mm_eq = w["mm"] + MM_PER_INV * w["inv"]
+    x = par.tape_work()
+    w = dict(w, executed_mm=x["mm"], executed_inv=x["inv"], executed_ma=x["ma"], executed_var_reads=x["var_reads"],
+             executed_mm_eq=x["mm"] + MM_PER_INV * x["inv"])
     return w, mm_eq
 
 
@@ -336,6 +340,53 @@ def main():
         if not np.array_equal(oarr[:, sel], want):
             verified = False
 
+    # ---- e2e, line form: only t crosses PCIe, x_v = a_v*t + s_v is formed on the GPU (what Reconstructor::queue_probes
+    # computes per point, Reconstructor.hpp:2946-2960) --------------------------------------------------------------------
+    rngl = np.random.default_rng(12345 + rank)
+    line_in, line_out, line_as, lh2d, ld2h = [], [], [], 0, 0
+    for name, par in zip(FUNCS, pars):
+        nv = par.n_vars
+        a = (rngl.integers(1, P0 - 1, size=nv, dtype=np.uint64))
+        a[0] = 1
+        sft = rngl.integers(0, P0 - 1, size=nv, dtype=np.uint64)
+        pt = ff.lib.ffgpu_host_alloc(ne * 8)
+        po = ff.lib.ffgpu_host_alloc(ne * 8)
+        assert pt and po, ff.last_error()
+        tarr = np.ctypeslib.as_array(C.cast(pt, C.POINTER(C.c_uint64)), shape=(ne,))
+        tarr[:] = ff.synthetic_points(1, ne, P0, seed=SEED + 2, first_point=rank * ne, total_points=ne * world)[0]
+        line_in.append((pt, tarr))
+        line_out.append((po, np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_uint64)), shape=(1, ne))))
+        line_as.append((a, sft))
+        lh2d += ne * 8 + 2 * nv * 8
+        ld2h += ne * 8
+
+    def line_step():
+        for par, (pt, _), (po, _), (a, sft) in zip(pars, line_in, line_out, line_as):
+            par.eval_line_ptr(a, sft, pt, ne, po)
+
+    for _ in range(2):
+        line_step()
+    barrier()
+    line_l0 = ff.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        line_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    line_launches = ff.launch_count() - line_l0
+    tl = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+    line_value = e2e_steps * len(FUNCS) * ne * world / float(tl.item())
+    for name, par, (pt, tarr), (po, oarr), (a, sft) in zip(FUNCS, pars, line_in, line_out, line_as):
+        text, vars_ = W.benchmark(name)
+        sel = np.arange(0, ne, max(1, ne // 512))
+        pts = np.array([[(int(a[v]) * int(tj) + int(sft[v])) % P0 for tj in tarr[sel]] for v in range(par.n_vars)],
+                       dtype=np.uint64)
+        want = orc.parse([text], vars_, P0).eval(pts)
+        if not np.array_equal(oarr[:, sel], want):
+            verified = False
+
     # ---- bunch sweep (optional, rank 0) ----------------------------------------------------------------------------
     sweep = None
     if args.sweep and rank == 0:
@@ -374,8 +425,10 @@ def main():
             rate = n / (per_fn_ms[i] * 1e-3)
             per_fn[name] = {
                 "ms": per_fn_ms[i], "probes_per_s": rate, "mm_eq_per_probe": mmi, "gmm_eq_per_s": rate * mmi / 1e9,
+                "executed_mm_eq_per_probe": wi["executed_mm_eq"], "executed_gmm_eq_per_s": rate * wi["executed_mm_eq"] / 1e9,
                 "imad_frac_of_measured": rate * mmi * IMAD_PER_MM / peak_int,
                 "pipe_slot_frac_of_measured": rate * mmi * SLOTS_PER_MM / peak_int,
+                "executed_pipe_slot_frac_of_measured": rate * wi["executed_mm_eq"] * SLOTS_PER_MM / peak_int,
                 "hbm_gbs": rate * 8 * (pars[i].n_vars + 1) / 1e9,
             }
         line = {
@@ -398,11 +451,20 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "points_per_function_per_step_per_gpu": ne, "steps": e2e_steps, "gpu_launches": int(e2e_launches),
                     "api": "ffgpu_eval (host pinned buffers, chunked H2D/kernel/D2H pipeline)"},
+            "e2e_line": {"value": line_value, "unit": UNIT, "h2d_bytes_per_step": int(lh2d), "d2h_bytes_per_step": int(ld2h),
+                         "points_per_function_per_step_per_gpu": ne, "steps": e2e_steps, "gpu_launches": int(line_launches),
+                         "api": "ffgpu_eval_line (host pinned t[], x_v = a_v*t + s_v formed on the GPU as "
+                                "Reconstructor::queue_probes does on the host; same values as e2e)"},
             "roofline": {
                 "bound": "int_pipe", "kernel": f"eval_tape_kernel on {FUNCS[top]}",
                 "achieved": imad / 1e9, "peak": peak_int / 1e9, "unit": "G IMAD thread-inst/s",
                 "frac": imad / peak_int,
                 "pipe_slot_frac": probes_per_s_top * mm_eq * SLOTS_PER_MM / peak_int,
+                "executed": {"mm_eq_per_probe": w["executed_mm_eq"],
+                             "note": "the tape shares equal sub-expressions (f1: 20 powers instead of the reference's 40); "
+                                     "frac counts the reference's token list (SURVEY 8d), this block what the kernel ran",
+                             "imad_frac": probes_per_s_top * w["executed_mm_eq"] * IMAD_PER_MM / peak_int,
+                             "pipe_slot_frac": probes_per_s_top * w["executed_mm_eq"] * SLOTS_PER_MM / peak_int},
                 "peak_source": peak_src,
                 "algorithmic": {"mm": w["mm"], "inv": w["inv"], "ma": w["ma"], "mm_eq_per_probe": mm_eq,
                                 "imad_per_mm": IMAD_PER_MM, "mm_per_inv": MM_PER_INV,

@@ -366,6 +366,29 @@ int main(int argc, char** argv) {
   run_mm("sqr_pm_dev_k4", k_mm<4, 8>, 4, 8);
   run_mm("mul_pm_dev_k8", k_mm<8, 3>, 8, 3);
 
+  // occupancy sweep of the shipped multiplication: resident warps per SM limited through dynamic shared memory
+  struct Occ { int k, warps; double gmm; };
+  std::vector<Occ> occ;
+  {
+    auto sweep = [&](auto kern, int K) {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      for (int bps : {1, 2, 3, 4, 6, 8}) {           // blocks of 256 threads per SM
+        size_t smem = (size_t)(227 * 1024 / bps) - 2048;
+        if (smem > 200 * 1024) smem = 200 * 1024;
+        const int nb = sms * bps * 4;
+        double ms = time_ms([&] { kern<<<nb, threads, smem>>>(d64_out, d64_in, c, trips / 4); }, 3);
+        CK(cudaGetLastError());
+        double total = 4.0 * K * (trips / 4) * (double)nb * threads;
+        occ.push_back({K, bps * 8, total / (ms * 1e-3) / 1e9});
+      }
+    };
+    u64* big; CK(cudaMalloc(&big, (size_t)sms * 8 * 4 * threads * 8));
+    u64* keep = d64_out; d64_out = big;
+    sweep(k_mm<4, 5>, 4);
+    sweep(k_mm<8, 5>, 8);
+    d64_out = keep;
+  }
+
   printf("{\"gpu\": \"%s\", \"sms\": %d, \"sm_clock_mhz_under_load\": %.1f, \"blocks\": %d, \"threads\": %d,\n \"pipes\": {",
          prop.name, sms, sm_clock_mhz_under_load, blocks, threads);
   for (size_t i = 0; i < res.size(); i++)
@@ -374,6 +397,9 @@ int main(int argc, char** argv) {
   printf("},\n \"modmul\": {");
   for (size_t i = 0; i < mms.size(); i++)
     printf("%s\n  \"%s\": {\"gmm_per_s\": %.2f, \"ms\": %.3f}", i ? "," : "", mms[i].name.c_str(), mms[i].gmm, mms[i].ms);
-  printf("},\n \"selfcheck_mismatches\": %d}\n", n_bad);
+  printf("},\n \"mul_b63_by_occupancy\": [");
+  for (size_t i = 0; i < occ.size(); i++)
+    printf("%s{\"chains_per_thread\": %d, \"warps_per_sm\": %d, \"gmm_per_s\": %.1f}", i ? ", " : "", occ[i].k, occ[i].warps, occ[i].gmm);
+  printf("],\n \"selfcheck_mismatches\": %d}\n", n_bad);
   return n_bad != 0;
 }

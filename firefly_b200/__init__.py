@@ -69,14 +69,17 @@ def _load() -> C.CDLL:
         "ffgpu_stack_depth": (C.c_size_t, [C.c_void_p]),
         "ffgpu_n_temps": (C.c_size_t, [C.c_void_p]),
         "ffgpu_n_slots": (C.c_size_t, [C.c_void_p]),
+        "ffgpu_cse_fallbacks": (C.c_size_t, [C.c_void_p]),
         "ffgpu_rpn": (C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
         "ffgpu_get_tape": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t]),
         "ffgpu_work": (None, [C.c_void_p, u64p]),
+        "ffgpu_tape_work": (None, [C.c_void_p, u64p]),
         "ffgpu_set_prime": (C.c_int, [C.c_void_p, C.c_uint64]),
         "ffgpu_get_prime": (C.c_uint64, [C.c_void_p]),
         "ffgpu_n_primes": (C.c_uint32, []),
         "ffgpu_prime": (C.c_uint64, [C.c_uint32]),
         "ffgpu_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32]),
+        "ffgpu_eval_line": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32]),
         "ffgpu_eval_device": (
             C.c_int,
             [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p],
@@ -108,8 +111,8 @@ lib = _load()
 EXPORTS = [
     "ffgpu_create", "ffgpu_destroy", "ffgpu_n_devices", "ffgpu_last_error", "ffgpu_compile", "ffgpu_compile_text",
     "ffgpu_compile_file", "ffgpu_tape_destroy", "ffgpu_n_vars", "ffgpu_n_functions", "ffgpu_n_out", "ffgpu_n_instr",
-    "ffgpu_stack_depth", "ffgpu_n_temps", "ffgpu_n_slots", "ffgpu_rpn", "ffgpu_get_tape", "ffgpu_work", "ffgpu_set_prime", "ffgpu_get_prime",
-    "ffgpu_n_primes", "ffgpu_prime", "ffgpu_eval", "ffgpu_eval_device", "ffgpu_host_alloc", "ffgpu_host_free",
+    "ffgpu_stack_depth", "ffgpu_n_temps", "ffgpu_n_slots", "ffgpu_cse_fallbacks", "ffgpu_rpn", "ffgpu_get_tape", "ffgpu_work", "ffgpu_tape_work", "ffgpu_set_prime", "ffgpu_get_prime",
+    "ffgpu_n_primes", "ffgpu_prime", "ffgpu_eval", "ffgpu_eval_line", "ffgpu_eval_device", "ffgpu_host_alloc", "ffgpu_host_free",
     "ffgpu_set_launch", "ffgpu_set_chunk", "ffgpu_launch_count", "ffgpu_fill_points", "ffgpu_checksum",
     "ffgpu_field_ops",
 ]
@@ -212,6 +215,12 @@ class GpuParser:
         lib.ffgpu_work(self.h, w)
         return {"tokens": w[0], "mm": w[1], "ma": w[2], "inv": w[3], "max_rpn_depth": w[4]}
 
+    def tape_work(self) -> dict:
+        """what the compiled tape executes per probe (after folding and sharing)"""
+        w = (C.c_uint64 * 5)()
+        lib.ffgpu_tape_work(self.h, w)
+        return {"instr": w[0], "mm": w[1], "ma": w[2], "inv": w[3], "var_reads": w[4]}
+
     @property
     def n_instr(self) -> int:
         return lib.ffgpu_n_instr(self.h)
@@ -223,6 +232,10 @@ class GpuParser:
     @property
     def n_temps(self) -> int:
         return lib.ffgpu_n_temps(self.h)
+
+    @property
+    def cse_fallbacks(self) -> int:
+        return lib.ffgpu_cse_fallbacks(self.h)
 
     @property
     def n_slots(self) -> int:
@@ -254,6 +267,27 @@ class GpuParser:
         if lib.ffgpu_eval(self.h, a.ctypes.data, n, out.ctypes.data, thread_id):
             raise FFGpuError(last_error())
         return out[:, 0] if single else out
+
+    def evaluate_line(self, a, s, t, thread_id: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Probes on the line x_v = a[v]*t + s[v] (Reconstructor::queue_probes, Reconstructor.hpp:2946-2960);
+        only t is copied to the GPU.  a, s: [n_vars]; t: [n_points] -> uint64 [n_out][n_points]."""
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        s = np.ascontiguousarray(s, dtype=np.uint64)
+        t = np.ascontiguousarray(t, dtype=np.uint64)
+        if a.shape != (self.n_vars,) or s.shape != (self.n_vars,):
+            raise ValueError(f"a and s must have {self.n_vars} entries")
+        n = t.shape[0]
+        if out is None:
+            out = np.empty((self.n_out, n), dtype=np.uint64)
+        if lib.ffgpu_eval_line(self.h, a.ctypes.data, s.ctypes.data, t.ctypes.data, n, out.ctypes.data, thread_id):
+            raise FFGpuError(last_error())
+        return out
+
+    def eval_line_ptr(self, a, s, t_ptr: int, n_points: int, out_ptr: int, thread_id: int = 0):
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        s = np.ascontiguousarray(s, dtype=np.uint64)
+        if lib.ffgpu_eval_line(self.h, a.ctypes.data, s.ctypes.data, t_ptr, n_points, out_ptr, thread_id):
+            raise FFGpuError(last_error())
 
     def eval_ptr(self, values_ptr: int, n_points: int, out_ptr: int, thread_id: int = 0):
         """Host pointers (e.g. pinned memory from ``host_alloc``)."""

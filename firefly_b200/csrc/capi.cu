@@ -49,7 +49,8 @@ struct DevBuf {
   cudaStream_t stream = nullptr;
   uint64_t* d_in = nullptr;
   uint64_t* d_out = nullptr;
-  size_t cap_in = 0, cap_out = 0;   // elements
+  uint64_t* d_as = nullptr;         // line mode: a[n_vars] then s[n_vars]
+  size_t cap_in = 0, cap_out = 0, cap_as = 0;   // elements
 };
 struct SlotDev {
   DevBuf buf[N_BUF];
@@ -247,6 +248,7 @@ void ffgpu_destroy(ffgpu_ctx* ctx) {
         if (b.stream) cudaStreamSynchronize(b.stream);
         if (b.d_in) cudaFree(b.d_in);
         if (b.d_out) cudaFree(b.d_out);
+        if (b.d_as) cudaFree(b.d_as);
         if (b.stream) cudaStreamDestroy(b.stream);
       }
     }
@@ -308,6 +310,7 @@ size_t ffgpu_n_instr(const ffgpu_tape* t) { return t->col.tape.size() - 2; }
 size_t ffgpu_stack_depth(const ffgpu_tape* t) { return t->col.stack_depth; }
 size_t ffgpu_n_temps(const ffgpu_tape* t) { return t->col.n_temps; }
 size_t ffgpu_n_slots(const ffgpu_tape* t) { return t->col.n_slots; }
+size_t ffgpu_cse_fallbacks(const ffgpu_tape* t) { return t->col.cse_fallbacks; }
 
 size_t ffgpu_rpn(const ffgpu_tape* t, size_t i, char* buf, size_t cap) {
   if (i >= t->col.functions.size()) return 0;
@@ -336,6 +339,14 @@ void ffgpu_work(const ffgpu_tape* t, uint64_t w[5]) {
   w[2] = t->col.work.ma;
   w[3] = t->col.work.inv;
   w[4] = t->col.work.max_rpn_depth;
+}
+
+void ffgpu_tape_work(const ffgpu_tape* t, uint64_t w[5]) {
+  w[0] = t->col.executed.tokens;
+  w[1] = t->col.executed.mm;
+  w[2] = t->col.executed.ma;
+  w[3] = t->col.executed.inv;
+  w[4] = t->col.executed.max_rpn_depth;
 }
 
 uint32_t ffgpu_n_primes(void) { return (uint32_t)prime_table().size(); }
@@ -393,7 +404,13 @@ int ffgpu_eval_device(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_
   return launch(t, g, d_values, in_stride, n_points, d_out, out_stride, (cudaStream_t)stream);
 }
 
-int ffgpu_eval(ffgpu_tape* t, const uint64_t* values, size_t n_points, uint64_t* out, uint32_t thread_id) {
+}  // extern "C"
+
+namespace {
+// Host-buffer evaluation shared by ffgpu_eval (values given) and ffgpu_eval_line (values == NULL: the
+// points are built on the device from t[], a[], s[]).
+int eval_host(ffgpu_tape* t, const uint64_t* values, const uint64_t* line_a, const uint64_t* line_s,
+              const uint64_t* line_t, size_t n_points, uint64_t* out, uint32_t thread_id) {
   if (!t) return fail("null tape");
   if (!t->ctx) return fail("tape was compiled without a context: no GPU to evaluate on (there is no CPU path)");
   if (!t->col.prime) return fail("ffgpu_set_prime has not been called");
@@ -408,8 +425,9 @@ int ffgpu_eval(ffgpu_tape* t, const uint64_t* values, size_t n_points, uint64_t*
   const size_t per_dev = (n_points + G - 1) / G;
   size_t chunk = t->chunk;
   if (!chunk) {
-    const size_t bytes_per_point = 8 * (n_vars + n_out);
-    chunk = std::max<size_t>(1 << 16, (32u << 20) / std::max<size_t>(bytes_per_point, 1));
+    // bytes that cross PCIe per point: the line form ships t only
+    const size_t bytes_per_point = 8 * ((values ? n_vars : 1) + n_out);
+    chunk = std::max<size_t>(1 << 16, ((values ? 32u : 16u) << 20) / std::max<size_t>(bytes_per_point, 1));
   }
   chunk = std::min(chunk, per_dev);
   chunk = (chunk + 1) & ~(size_t)1;
@@ -427,10 +445,31 @@ int ffgpu_eval(ffgpu_tape* t, const uint64_t* values, size_t n_points, uint64_t*
       rc = [&]() -> int {
         FF_CUDA(cudaSetDevice(ctx->devs[g].id));
         DevBuf& b = slot.dev[g].buf[ci % N_BUF];
-        if (ensure(b, chunk * std::max<size_t>(n_vars, 1), chunk * std::max<size_t>(n_out, 1))) return -1;
-        if (n_vars)
-          FF_CUDA(cudaMemcpy2DAsync(b.d_in, chunk * 8, values + lo, n_points * 8, cnt * 8, n_vars,
-                                    cudaMemcpyHostToDevice, b.stream));
+        if (ensure(b, chunk * (n_vars + 1), chunk * std::max<size_t>(n_out, 1))) return -1;
+        if (values) {
+          if (n_vars)
+            FF_CUDA(cudaMemcpy2DAsync(b.d_in, chunk * 8, values + lo, n_points * 8, cnt * 8, n_vars,
+                                      cudaMemcpyHostToDevice, b.stream));
+        } else if (n_vars) {
+          // t travels, the coordinates are built here: row n_vars of the staging buffer holds t
+          if (b.cap_as < 2 * n_vars) {
+            FF_CUDA(cudaStreamSynchronize(b.stream));
+            if (b.d_as) FF_CUDA(cudaFree(b.d_as));
+            b.d_as = nullptr;
+            b.cap_as = 0;
+            FF_CUDA(cudaMalloc(&b.d_as, 2 * n_vars * sizeof(uint64_t)));
+            b.cap_as = 2 * n_vars;
+          }
+          uint64_t* d_t = b.d_in + chunk * n_vars;
+          FF_CUDA(cudaMemcpyAsync(b.d_as, line_a, n_vars * 8, cudaMemcpyHostToDevice, b.stream));
+          FF_CUDA(cudaMemcpyAsync(b.d_as + n_vars, line_s, n_vars * 8, cudaMemcpyHostToDevice, b.stream));
+          FF_CUDA(cudaMemcpyAsync(d_t, line_t + lo, cnt * 8, cudaMemcpyHostToDevice, b.stream));
+          if (cnt_even != cnt) FF_CUDA(cudaMemsetAsync(d_t + cnt, 0, 8, b.stream));
+          cudaError_t e = ffgpu::launch_line_points(b.d_in, d_t, b.d_as, b.d_as + n_vars, (uint32_t)n_vars, cnt_even,
+                                                    chunk, t->col.prime, b.stream);
+          if (e != cudaSuccess) return cuda_fail(e, "line_points");
+          g_launches.fetch_add(1, std::memory_order_relaxed);
+        }
         if (launch(t, (int)g, b.d_in, chunk, cnt_even, b.d_out, chunk, b.stream)) return -1;
         if (n_out)
           FF_CUDA(cudaMemcpy2DAsync(out + lo, n_points * 8, b.d_out, chunk * 8, cnt * 8, n_out,
@@ -450,6 +489,25 @@ int ffgpu_eval(ffgpu_tape* t, const uint64_t* values, size_t n_points, uint64_t*
   }
   cudaSetDevice(prev_dev);
   return rc;
+}
+}  // namespace
+
+extern "C" {
+
+int ffgpu_eval(ffgpu_tape* t, const uint64_t* values, size_t n_points, uint64_t* out, uint32_t thread_id) {
+  if (t && n_points && t->col.vars.size() && !values) return fail("null values");
+  static const uint64_t none = 0;
+  return eval_host(t, values ? values : &none, nullptr, nullptr, nullptr, n_points, out, thread_id);
+}
+
+int ffgpu_eval_line(ffgpu_tape* t, const uint64_t* a, const uint64_t* s, const uint64_t* tt, size_t n_points,
+                    uint64_t* out, uint32_t thread_id) {
+  if (t && n_points && (!tt || (t->col.vars.size() && (!a || !s)))) return fail("null line parameters");
+  if (t && t->col.prime) {
+    for (size_t v = 0; v < t->col.vars.size(); ++v)
+      if (a[v] >= t->col.prime || s[v] >= t->col.prime) return fail("line parameters must be residues below the prime");
+  }
+  return eval_host(t, nullptr, a, s, tt, n_points, out, thread_id);
 }
 
 void* ffgpu_host_alloc(size_t bytes) {

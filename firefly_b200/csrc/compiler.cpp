@@ -428,6 +428,9 @@ struct FnEmitter {
   std::vector<int32_t> rep;        // node -> representative
   std::vector<int32_t> remaining;  // representative -> consumptions still expected
   std::vector<int32_t> temp_of;    // representative -> temp slot holding its value, or -1
+  std::vector<int32_t> pins;       // representative -> scheduled direct uses that must still find the temp
+  std::vector<uint8_t> computed;   // representative -> has been brought into ACC at least once
+  bool failed = false;             // an operand was expected in a temp slot that no longer holds it
   bool slot_busy[MAX_TEMPS] = {};
   int max_temps = MAX_TEMPS;       // temp slots this function may use
   uint32_t depth = 0, max_depth = 0, temps_used = 0;
@@ -449,6 +452,8 @@ struct FnEmitter {
     rep.resize(n);
     remaining.assign(n, 0);
     temp_of.assign(n, -1);
+    pins.assign(n, 0);
+    computed.assign(n, 0);
     if (!enable_cse) {
       for (size_t i = 0; i < n; ++i) { rep[i] = (int32_t)i; remaining[i] = 1; }
       return;
@@ -505,10 +510,21 @@ struct FnEmitter {
   // one expected consumption of node i has happened
   void consume(int32_t i) {
     const int32_t u = rep[i];
-    if (--remaining[u] <= 0 && temp_of[u] >= 0) {
+    --remaining[u];
+    maybe_release(u);
+  }
+  void maybe_release(int32_t u) {
+    if (remaining[u] <= 0 && pins[u] == 0 && temp_of[u] >= 0) {
       slot_busy[temp_of[u]] = false;
       temp_of[u] = -1;
     }
+  }
+  // a work item scheduled now will read node i straight from its temp slot later: keep the slot until then
+  void pin(int32_t i) {
+    if (!leaf_like(i)) ++pins[rep[i]];
+  }
+  void unpin(int32_t i) {
+    if (!leaf_like(i)) --pins[rep[i]];
   }
 
   static Instr mk(uint8_t op, uint8_t flags = 0) {
@@ -529,6 +545,7 @@ struct FnEmitter {
       ins.src = n.kind == N_VAR ? SRC_VAR : SRC_NEGVAR;
       ins.arg = n.var;
     } else {
+      if (temp_of[u] < 0) failed = true;
       ins.src = SRC_TMP;
       ins.arg = (uint32_t)temp_of[u];
       consume(u);
@@ -592,7 +609,7 @@ struct FnEmitter {
   void apply(const Node& n, bool acc_is_right, bool from_stack, int32_t other) {
     auto finish = [&](Instr ins) {
       if (from_stack) { ins.src = SRC_POP; put(ins); --depth; }
-      else { operand(ins, other); put(ins); }
+      else { unpin(other); operand(ins, other); put(ins); }
     };
     switch (n.kind) {
       case N_ADD: finish(mk(OP_ADD)); break;
@@ -754,6 +771,13 @@ struct FnEmitter {
         schedule_coevaluation(l, r, it.push);
         continue;
       }
+      if (computed[u]) {
+        // computed before but could not be parked (no free temp slot): this is a recomputation, the
+        // operands are consumed once more than the DAG's edge count says
+        ++remaining[l];
+        ++remaining[r];
+      }
+      computed[u] = 1;
       if (shared(u)) work.push_back(Item{AFTER, u, false, false, -1, 0});
       else --remaining[u];
       if (is_pow && f.nodes[r].is_const) {
@@ -778,6 +802,7 @@ struct FnEmitter {
       const bool left_first = std::max(a, b + 1) <= std::max(b, a + 1);
       if (n.kind == N_DIV) {
         if (dl) {                      // invert the divisor, multiply by the simple numerator
+          pin(l);
           work.push_back(Item{APPLY_DIRECT, u, false, true, l, 0});
           work.push_back(Item{INVERT, -1, false, false, -1, 0});
           work.push_back(Item{GEN, r, push, false, -1, 0});
@@ -793,9 +818,11 @@ struct FnEmitter {
           work.push_back(Item{GEN, r, push, false, -1, 0});
         }
       } else if (dr) {
+        pin(r);
         work.push_back(Item{APPLY_DIRECT, u, false, false, r, 0});
         work.push_back(Item{GEN, l, push, false, -1, 0});
       } else if (dl) {
+        pin(l);
         work.push_back(Item{APPLY_DIRECT, u, false, true, l, 0});
         work.push_back(Item{GEN, r, push, false, -1, 0});
       } else if (left_first) {
@@ -813,16 +840,102 @@ struct FnEmitter {
 }  // namespace
 
 void Collection::emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots) {
-  FnEmitter em(functions[fn], fn, tape, patches, enable_cse, temp_budget);
-  em.gen(functions[fn].root);
-  for (uint32_t slot : out_slots) {
-    Instr st = FnEmitter::mk(OP_STORE);
-    st.arg = slot;
-    em.put(st);
+  const size_t tape0 = tape.size(), patch0 = patches.size();
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const bool cse = enable_cse && !no_cse_fn_[fn];
+    FnEmitter em(functions[fn], fn, tape, patches, cse, temp_budget);
+    em.gen(functions[fn].root);
+    if (em.failed && cse) {
+      // the sharing pass lost track of a temp slot: emit this function as a plain tree instead
+      tape.resize(tape0);
+      patches.resize(patch0);
+      no_cse_fn_[fn] = 1;
+      ++cse_fallbacks;
+      continue;
+    }
+    for (uint32_t slot : out_slots) {
+      Instr st = FnEmitter::mk(OP_STORE);
+      st.arg = slot;
+      em.put(st);
+    }
+    stack_depth = std::max(stack_depth, em.max_depth);
+    n_temps = std::max(n_temps, em.temps_used);
+    n_slots = std::max(n_slots, em.max_depth + em.temps_used);
+    return;
   }
-  stack_depth = std::max(stack_depth, em.max_depth);
-  n_temps = std::max(n_temps, em.temps_used);
-  n_slots = std::max(n_slots, em.max_depth + em.temps_used);
+}
+
+// Translation check: run the emitted code of function fn on the host at one point and compare with the
+// value of its expression tree (eval_nodes).  The tape must be resolved for prime p.
+bool Collection::check_function(uint32_t fn, uint64_t p, const uint64_t* point) const {
+  std::vector<uint64_t> val;
+  eval_nodes(functions[fn], p, point, val);
+  const uint64_t want = val[functions[fn].root];
+  uint64_t acc = 0;
+  std::vector<uint64_t> stack;
+  uint64_t temps[16];
+  bool temp_set[16] = {};
+  bool stored = false;
+  for (uint32_t pc = fn_start[fn]; pc < fn_start[fn + 1]; ++pc) {
+    const Instr& in = tape[pc];
+    uint64_t b = 0;
+    switch (in.src) {
+      case SRC_POP:
+        if (stack.empty()) return false;
+        b = stack.back();
+        stack.pop_back();
+        break;
+      case SRC_VAR: b = point[in.arg] % p; break;
+      case SRC_NEGVAR: b = ffhost::neg(point[in.arg] % p, p); break;
+      case SRC_CONST: b = in.imm; break;
+      case SRC_TMP:
+        if (in.arg >= 16 || !temp_set[in.arg]) return false;
+        b = temps[in.arg];
+        break;
+      default: break;
+    }
+    const bool swap = in.flags & F_SWAP;
+    switch (in.op) {
+      case OP_LOAD:
+        if (in.flags & F_PUSH) stack.push_back(acc);
+        acc = b;
+        break;
+      case OP_ADD: acc = ffhost::add(acc, b, p); break;
+      case OP_SUB: acc = swap ? ffhost::sub(b, acc, p) : ffhost::sub(acc, b, p); break;
+      case OP_MUL: acc = ffhost::mul(acc, b, p); break;
+      case OP_SQR: acc = ffhost::mul(acc, acc, p); break;
+      case OP_NEG: acc = ffhost::neg(acc, p); break;
+      case OP_INV: acc = ffhost::inv(acc, p); break;
+      case OP_POWU: acc = ffhost::pow_ff(acc, in.imm, p); break;
+      case OP_NPOWU: acc = ffhost::pow_int(acc, ffhost::to_neg_int(in.imm), p); break;
+      case OP_POWL: acc = swap ? ffhost::pow_ff(b, acc, p) : ffhost::pow_ff(acc, b, p); break;
+      case OP_NPOWL:
+        acc = swap ? ffhost::pow_int(b, ffhost::to_neg_int(acc), p) : ffhost::pow_int(acc, ffhost::to_neg_int(b), p);
+        break;
+      case OP_MULADD: acc = ffhost::add(ffhost::mul(acc, point[in.arg] % p, p), in.imm, p); break;
+      case OP_SAVE:
+        if (in.arg >= 16) return false;
+        temps[in.arg] = acc;
+        temp_set[in.arg] = true;
+        break;
+      case OP_ACCUM: {
+        if (in.arg >= 16) return false;
+        const uint64_t v = swap ? ffhost::neg(acc, p) : acc;
+        if (in.flags & F_INIT) temps[in.arg] = v;
+        else if (!temp_set[in.arg]) return false;
+        else temps[in.arg] = ffhost::add(temps[in.arg], v, p);
+        temp_set[in.arg] = true;
+        break;
+      }
+      case OP_STORE:
+        if (acc != want) return false;
+        stored = true;
+        break;
+      default: return false;
+    }
+    if (in.flags & F_NEGR) acc = ffhost::neg(acc, p);
+  }
+  return stored && stack.empty();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -877,20 +990,74 @@ bool Collection::finish(std::string& err) {
   } else {
     for (size_t k = 0; k < functions.size(); ++k) slots[k].push_back((uint32_t)k);
   }
-  tape.clear();
-  patches.clear();
-  stack_depth = 0;
-  n_temps = 0;
-  n_slots = 0;
-  work = WorkCount{};
-  fn_start.clear();
-  for (size_t i = 0; i < functions.size(); ++i) {
+  no_cse_fn_.assign(functions.size(), 0);
+  cse_fallbacks = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    tape.clear();
+    patches.clear();
+    stack_depth = 0;
+    n_temps = 0;
+    n_slots = 0;
+    work = WorkCount{};
+    fn_start.clear();
+    for (size_t i = 0; i < functions.size(); ++i) {
+      fn_start.push_back((uint32_t)tape.size());
+      emit_function((uint32_t)i, slots[i]);
+      count_work(functions[i]);
+    }
     fn_start.push_back((uint32_t)tape.size());
-    emit_function((uint32_t)i, slots[i]);
-    count_work(functions[i]);
+    peephole();
+    // Translation check of every function at one pseudo-random point: the tape must reproduce the value of
+    // the expression tree.  A function that fails is re-emitted as a plain tree (no sharing) on the second
+    // pass; if that fails too the compilation is refused -- never a wrong probe value.
+    if (!resolve(P0, err)) return false;
+    std::vector<uint64_t> pt(vars.size());
+    uint64_t seed = 0x243F6A8885A308D3ULL;
+    for (auto& v : pt) v = 1 + splitmix64(seed) % (P0 - 1);
+    bool again = false;
+    for (size_t i = 0; i < functions.size(); ++i) {
+      if (check_function((uint32_t)i, P0, pt.data())) continue;
+      if (pass == 1 || no_cse_fn_[i] || !enable_cse) {
+        err = "internal error: the tape of function " + std::to_string(i) + " does not reproduce its expression";
+        return false;
+      }
+      no_cse_fn_[i] = 1;
+      ++cse_fallbacks;
+      again = true;
+    }
+    if (!again) break;
   }
-  fn_start.push_back((uint32_t)tape.size());
-  peephole();
+  // work the tape executes per probe (the imm fields are resolved for P0 here; exponents of literal powers
+  // do not depend on the prime)
+  executed = WorkCount{};
+  {
+    auto chain = [](uint64_t e) -> uint64_t {
+      return e <= 1 ? 0 : (uint64_t)(63 - __builtin_clzll(e)) + (uint64_t)__builtin_popcountll(e) - 1;
+    };
+    for (const Instr& in : tape) {
+      ++executed.tokens;
+      if (in.src == SRC_VAR || in.src == SRC_NEGVAR) ++executed.max_rpn_depth;   // reused: variable row reads
+      switch (in.op) {
+        case OP_ADD: case OP_SUB: case OP_NEG: case OP_ACCUM: ++executed.ma; break;
+        case OP_MUL: case OP_SQR: ++executed.mm; break;
+        case OP_MULADD: ++executed.mm; ++executed.ma; break;
+        case OP_INV: ++executed.inv; break;
+        case OP_POWU:
+          if (in.imm < (P0 >> 1)) executed.mm += chain(in.imm);
+          else { ++executed.inv; executed.mm += chain(P0 - in.imm - 1); }
+          break;
+        case OP_NPOWU: {
+          const int32_t e = ffhost::to_neg_int(in.imm);
+          if (e >= 0) executed.mm += chain((uint64_t)e);
+          else { ++executed.inv; executed.mm += chain((uint64_t)(-(int64_t)e)); }
+          break;
+        }
+        case OP_POWL: case OP_NPOWL: executed.mm += 94; break;
+        default: break;
+      }
+      if (in.flags & F_NEGR) ++executed.ma;
+    }
+  }
   // chunk tables for C = 1, 2, 4, ... while a chunk still holds a function
   chunk_table.clear();
   chunk_table_off.clear();
@@ -1036,7 +1203,11 @@ bool Collection::resolve(uint64_t p, std::string& err) {
     const uint64_t v = val[cp.node];
     uint64_t w = cp.inverse ? ffhost::div(1 % p, v, p) : v;
     if (cp.negate) w = ffhost::neg(w, p);
-    tape[cp.instr].imm = w;
+    Instr& in = tape[cp.instr];
+    in.imm = w;
+    // the fast dispatch code of a literal power covers exponents below p/2 only (FFInt::pow's direct branch);
+    // a residue above that means a negative power and takes the general code (inversion first)
+    if (in.op == OP_POWU && !(in.flags & ~0)) in.fast = (w < (p >> 1) && in.flags == 0) ? FX_POWU : FX_GENERIC;
   }
   prime = p;
   return true;

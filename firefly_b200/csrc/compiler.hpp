@@ -96,6 +96,7 @@ struct Collection {
   uint32_t n_slots = 0;                       // shared-memory slots per probe: max over functions of spill + temps
                                               // (spill slots count up from 0, temp slots down from n_slots - 1)
   bool enable_cse = true;                     // share structurally equal sub-expressions
+  uint32_t cse_fallbacks = 0;                 // functions emitted without sharing after a failed self-check
   int temp_budget = 0;                        // temp slots per function (0: automatic, see FnEmitter)
   std::vector<uint32_t> fn_start;             // tape offset of every distinct function, then the end
   // chunk tables: for C = 1, 2, 4, ... the C + 1 offsets that cut the tape into C runs of whole
@@ -104,7 +105,9 @@ struct Collection {
   std::vector<uint32_t> chunk_table_off;
   unsigned max_chunks = 1;
   uint64_t prime = 0;                         // prime the imm fields are resolved for (0: none)
-  WorkCount work;
+  WorkCount work;                             // algorithmic: counted on the reference's token list
+  WorkCount executed;                         // what the emitted tape does per probe (tokens = instructions,
+                                              // max_rpn_depth = variable row reads)
 
   // parse + build trees + emit the tape.  Returns false and sets `err` on malformed input
   // (where the reference prints ERROR_MSG and exits, or runs into undefined behaviour).
@@ -120,6 +123,8 @@ struct Collection {
   bool add_function(std::string text, uint64_t index, bool strip_blanks, std::string& err);
   bool build_tree(Function& f, std::string& err);
   void emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots);
+  bool check_function(uint32_t fn, uint64_t p, const uint64_t* point) const;
+  std::vector<uint8_t> no_cse_fn_;
   void count_work(const Function& f);
   void peephole();
   bool finish(std::string& err);

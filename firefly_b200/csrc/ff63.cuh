@@ -254,68 +254,40 @@ FF63_D u64 sqr_pm_dev(u64 x, u32 d) {
   return r;
 }
 
-// in-place forms (x <- x*y, x <- x*x): same arithmetic, the accumulator keeps its registers
-FF63_D void mul_pm_ip(u64& x, u64 y, u32 d) {
+
+// ----- "b63" family: BOUNDED lazy residues, the representation the interpreter computes in -----------
+// Every value v satisfies v < B = 2^63 + 2^32 (so its high word is <= 2^31); canonical residues qualify.
+// Why: with both high words <= 2^31 the two cross products of a 64x64 multiplication sum to less than
+// 2^64, so they are accumulated INSIDE one IMAD.WIDE (no carry chain), the top product limb stays below
+// 2^30 + 1, and the second fold can be done at 2^63 = c with no conditional correction.  Measured on
+// B200 (bench/pipe_peak.cu, profiles/r01_pipe_peak_v1.json): 1134 G modmul/s against 1054 for the
+// unbounded form above (the adds, not the multiplies, were the limiter: IMAD.WIDE also blocks an ALU slot).
+//   mul: 6 IMAD.WIDE + 1 IMAD, 11 add/logic           result < 2^63 + 2^31
+//   sqr: 5 IMAD.WIDE + 1 IMAD, 13 add/logic           result < 2^63 + 2^31
+//   add: 7 add/logic + 1 IMAD                         result < 2^63 + 2^16
+//   sub: 9 add/logic + 1 IMAD                         result < 2^63 + 2^17
+// c < 2^15 (all FireFly primes have c <= 13797), d = 2c.
+// Word-level forms: a residue travels as two separate 32-bit registers (lo, hi).  The interpreter keeps
+// its accumulators that way so that nothing but IMAD.WIDE's own result needs an aligned register pair --
+// with 64-bit accumulators ptxas copied both halves of every accumulator at each tape instruction
+// (16 IMAD.MOV per dispatch at 8 probes per thread, on the multiply pipe).
+FF63_D void mul_b63_w(u32& o0, u32& o1, u32 x0, u32 x1, u32 y0, u32 y1, u32 c, u32 d) {
   asm("{\n\t"
-      ".reg .u32 x0,x1,y0,y1,w0,w1,w2,w3,u0,u1,v0,v1,r0,r1,r2,t;\n\t"
-      ".reg .u64 t0,ma,mb,t3,u,v;\n\t"
-      ".reg .pred p;\n\t"
-      "mov.b64 {x0,x1}, %0;\n\t"
-      "mov.b64 {y0,y1}, %1;\n\t"
-      "mul.wide.u32 t0, x0, y0;\n\t"
-      "mul.wide.u32 ma, x0, y1;\n\t"
-      "mul.wide.u32 mb, x1, y0;\n\t"
-      "mul.wide.u32 t3, x1, y1;\n\t"
-      "mov.b64 {w0,w1}, t0;\n\t"
-      "mov.b64 {w2,w3}, t3;\n\t"
-      "mov.b64 {u0,u1}, ma;\n\t"
-      "mov.b64 {v0,v1}, mb;\n\t"
-      "add.cc.u32 w1, w1, u0;\n\t"
-      "addc.cc.u32 w2, w2, u1;\n\t"
-      "addc.u32 w3, w3, 0;\n\t"
-      "add.cc.u32 w1, w1, v0;\n\t"
-      "addc.cc.u32 w2, w2, v1;\n\t"
-      "addc.u32 w3, w3, 0;\n\t"
-      // fold 1: (w1:w0) + d*w2 + (d*w3 << 32)
-      "mul.wide.u32 u, w2, %2;\n\t"
-      "mul.wide.u32 v, w3, %2;\n\t"
-      "mov.b64 {u0,u1}, u;\n\t"
-      "mov.b64 {v0,v1}, v;\n\t"
-      "add.cc.u32 r0, w0, u0;\n\t"
-      "addc.cc.u32 r1, w1, u1;\n\t"
-      "addc.u32 r2, v1, 0;\n\t"
-      "add.cc.u32 r1, r1, v0;\n\t"
-      "addc.u32 r2, r2, 0;\n\t"
-      // fold 2: + d*r2 (< 2^32), one conditional +d on wrap
-      "mul.lo.u32 t, r2, %2;\n\t"
-      "add.cc.u32 r0, r0, t;\n\t"
-      "addc.cc.u32 r1, r1, 0;\n\t"
-      "addc.u32 t, 0, 0;\n\t"
-      "setp.ne.u32 p, t, 0;\n\t"
-      "@p add.u32 r0, r0, %2;\n\t"
-      "mov.b64 %0, {r0,r1};\n\t"
-      "}" : "+l"(x) : "l"(y), "r"(d));
-}
-FF63_D void sqr_pm_ip(u64& x, u32 d) {
-  asm("{\n\t"
-      ".reg .u32 x0,x1,w0,w1,w2,w3,u0,u1,v0,v1,r0,r1,r2,t;\n\t"
+      ".reg .u32 w0,w1,w2,w3,a,ml,mh,tl,th,u0,u1,v0,v1,r0,r1,r2,top,t;\n\t"
       ".reg .u64 t0,m,t3,u,v;\n\t"
-      ".reg .pred p;\n\t"
-      "mov.b64 {x0,x1}, %0;\n\t"
-      "mul.wide.u32 t0, x0, x0;\n\t"
-      "mul.wide.u32 m, x0, x1;\n\t"
-      "mul.wide.u32 t3, x1, x1;\n\t"
-      "mov.b64 {w0,w1}, t0;\n\t"
-      "mov.b64 {w2,w3}, t3;\n\t"
-      "mov.b64 {u0,u1}, m;\n\t"
-      "add.cc.u32 w1, w1, u0;\n\t"
-      "addc.cc.u32 w2, w2, u1;\n\t"
-      "addc.u32 w3, w3, 0;\n\t"
-      "add.cc.u32 w1, w1, u0;\n\t"
-      "addc.cc.u32 w2, w2, u1;\n\t"
-      "addc.u32 w3, w3, 0;\n\t"
-      "mul.wide.u32 u, w2, %1;\n\t"
-      "mul.wide.u32 v, w3, %1;\n\t"
+      "mul.wide.u32 t0, %2, %4;\n\t"
+      "mul.wide.u32 m, %2, %5;\n\t"
+      "mad.wide.u32 m, %3, %4, m;\n\t"          // < 2^64: both high words are <= 2^31
+      "mul.wide.u32 t3, %3, %5;\n\t"
+      "mov.b64 {w0,a}, t0;\n\t"
+      "mov.b64 {ml,mh}, m;\n\t"
+      "mov.b64 {tl,th}, t3;\n\t"
+      "add.cc.u32 w1, a, ml;\n\t"
+      "addc.cc.u32 w2, tl, mh;\n\t"
+      "addc.u32 w3, th, 0;\n\t"                 // w3 <= 2^30
+      // fold 1 at 2^64 = d: (w1:w0) + d*w2 + (d*w3 << 32)  ->  r2:r1:r0 with r2 <= 2^14 + 2
+      "mul.wide.u32 u, w2, %7;\n\t"
+      "mul.wide.u32 v, w3, %7;\n\t"
       "mov.b64 {u0,u1}, u;\n\t"
       "mov.b64 {v0,v1}, v;\n\t"
       "add.cc.u32 r0, w0, u0;\n\t"
@@ -323,14 +295,116 @@ FF63_D void sqr_pm_ip(u64& x, u32 d) {
       "addc.u32 r2, v1, 0;\n\t"
       "add.cc.u32 r1, r1, v0;\n\t"
       "addc.u32 r2, r2, 0;\n\t"
-      "mul.lo.u32 t, r2, %1;\n\t"
-      "add.cc.u32 r0, r0, t;\n\t"
-      "addc.cc.u32 r1, r1, 0;\n\t"
-      "addc.u32 t, 0, 0;\n\t"
-      "setp.ne.u32 p, t, 0;\n\t"
-      "@p add.u32 r0, r0, %1;\n\t"
-      "mov.b64 %0, {r0,r1};\n\t"
-      "}" : "+l"(x) : "r"(d));
+      // fold 2 at 2^63 = c: everything from bit 63 up (< 2^15 + 6) times c (< 2^31) onto the low 63 bits
+      "shf.l.wrap.b32 top, r1, r2, 1;\n\t"
+      "and.b32 r1, r1, 0x7fffffff;\n\t"
+      "mul.lo.u32 t, top, %6;\n\t"
+      "add.cc.u32 %0, r0, t;\n\t"
+      "addc.u32 %1, r1, 0;\n\t"
+      "}" : "=r"(o0), "=r"(o1) : "r"(x0), "r"(x1), "r"(y0), "r"(y1), "r"(c), "r"(d));
+}
+FF63_D void sqr_b63_w(u32& o0, u32& o1, u32 x0, u32 x1, u32 c, u32 d) {
+  asm("{\n\t"
+      ".reg .u32 w0,w1,w2,w3,a,ml,mh,tl,th,u0,u1,v0,v1,r0,r1,r2,top,t;\n\t"
+      ".reg .u64 t0,m,t3,u,v;\n\t"
+      "mul.wide.u32 t0, %2, %2;\n\t"
+      "mul.wide.u32 m, %2, %3;\n\t"             // < 2^63
+      "mul.wide.u32 t3, %3, %3;\n\t"
+      "mov.b64 {w0,a}, t0;\n\t"
+      "mov.b64 {ml,mh}, m;\n\t"
+      "mov.b64 {tl,th}, t3;\n\t"
+      "add.cc.u32 ml, ml, ml;\n\t"              // the cross product counts twice
+      "addc.u32 mh, mh, mh;\n\t"
+      "add.cc.u32 w1, a, ml;\n\t"
+      "addc.cc.u32 w2, tl, mh;\n\t"
+      "addc.u32 w3, th, 0;\n\t"
+      "mul.wide.u32 u, w2, %5;\n\t"
+      "mul.wide.u32 v, w3, %5;\n\t"
+      "mov.b64 {u0,u1}, u;\n\t"
+      "mov.b64 {v0,v1}, v;\n\t"
+      "add.cc.u32 r0, w0, u0;\n\t"
+      "addc.cc.u32 r1, w1, u1;\n\t"
+      "addc.u32 r2, v1, 0;\n\t"
+      "add.cc.u32 r1, r1, v0;\n\t"
+      "addc.u32 r2, r2, 0;\n\t"
+      "shf.l.wrap.b32 top, r1, r2, 1;\n\t"
+      "and.b32 r1, r1, 0x7fffffff;\n\t"
+      "mul.lo.u32 t, top, %4;\n\t"
+      "add.cc.u32 %0, r0, t;\n\t"
+      "addc.u32 %1, r1, 0;\n\t"
+      "}" : "=r"(o0), "=r"(o1) : "r"(x0), "r"(x1), "r"(c), "r"(d));
+}
+// a + b < 2^64 + 2^33: the carry and bit 63 together are worth (2k + b63) * c
+FF63_D void add_b63_w(u32& o0, u32& o1, u32 a0, u32 a1, u32 b0, u32 b1, u32 c) {
+  asm("{\n\t"
+      ".reg .u32 s0,s1,k,top,t;\n\t"
+      "add.cc.u32 s0, %2, %4;\n\t"
+      "addc.cc.u32 s1, %3, %5;\n\t"
+      "addc.u32 k, 0, 0;\n\t"
+      "shf.l.wrap.b32 top, s1, k, 1;\n\t"       // (k << 1) | (s1 >> 31)  in {0, 1, 2}
+      "and.b32 s1, s1, 0x7fffffff;\n\t"
+      "mul.lo.u32 t, top, %6;\n\t"
+      "add.cc.u32 %0, s0, t;\n\t"
+      "addc.u32 %1, s1, 0;\n\t"
+      "}" : "=r"(o0), "=r"(o1) : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(c));
+}
+// a - b = a + (2p - b); 2p = 2^64 - d.  2p - b < 2^64, the sum < 2^65: top in {0..3}
+FF63_D void sub_b63_w(u32& o0, u32& o1, u32 a0, u32 a1, u32 b0, u32 b1, u32 c, u32 d) {
+  asm("{\n\t"
+      ".reg .u32 n0,m0,m1,s0,s1,k,top,t;\n\t"
+      "neg.s32 n0, %7;\n\t"                     // low word of 2p
+      "sub.cc.u32 m0, n0, %4;\n\t"
+      "subc.u32 m1, 0xffffffff, %5;\n\t"
+      "add.cc.u32 s0, %2, m0;\n\t"
+      "addc.cc.u32 s1, %3, m1;\n\t"
+      "addc.u32 k, 0, 0;\n\t"
+      "shf.l.wrap.b32 top, s1, k, 1;\n\t"
+      "and.b32 s1, s1, 0x7fffffff;\n\t"
+      "mul.lo.u32 t, top, %6;\n\t"
+      "add.cc.u32 %0, s0, t;\n\t"
+      "addc.u32 %1, s1, 0;\n\t"
+      "}" : "=r"(o0), "=r"(o1) : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(c), "r"(d));
+}
+// -a = 2p - a, folded at bit 63 (-0 gives 2p -> p, a lazy zero)
+FF63_D void neg_b63_w(u32& o0, u32& o1, u32 a0, u32 a1, u32 c, u32 d) {
+  asm("{\n\t"
+      ".reg .u32 n0,s0,s1,top,t;\n\t"
+      "neg.s32 n0, %5;\n\t"
+      "sub.cc.u32 s0, n0, %2;\n\t"
+      "subc.u32 s1, 0xffffffff, %3;\n\t"
+      "shr.u32 top, s1, 31;\n\t"
+      "and.b32 s1, s1, 0x7fffffff;\n\t"
+      "mul.lo.u32 t, top, %4;\n\t"
+      "add.cc.u32 %0, s0, t;\n\t"
+      "addc.u32 %1, s1, 0;\n\t"
+      "}" : "=r"(o0), "=r"(o1) : "r"(a0), "r"(a1), "r"(c), "r"(d));
+}
+// 64-bit wrappers
+FF63_D u64 pack_w(u32 lo, u32 hi) { return ((u64)hi << 32) | lo; }
+FF63_D u64 mul_b63(u64 x, u64 y, u32 c, u32 d) {
+  u32 r0, r1;
+  mul_b63_w(r0, r1, lo32(x), hi32(x), lo32(y), hi32(y), c, d);
+  return pack_w(r0, r1);
+}
+FF63_D u64 sqr_b63(u64 x, u32 c, u32 d) {
+  u32 r0, r1;
+  sqr_b63_w(r0, r1, lo32(x), hi32(x), c, d);
+  return pack_w(r0, r1);
+}
+FF63_D u64 add_b63(u64 a, u64 b, u32 c) {
+  u32 r0, r1;
+  add_b63_w(r0, r1, lo32(a), hi32(a), lo32(b), hi32(b), c);
+  return pack_w(r0, r1);
+}
+FF63_D u64 sub_b63(u64 a, u64 b, u32 c, u32 d) {
+  u32 r0, r1;
+  sub_b63_w(r0, r1, lo32(a), hi32(a), lo32(b), hi32(b), c, d);
+  return pack_w(r0, r1);
+}
+FF63_D u64 neg_b63(u64 a, u32 c, u32 d) {
+  u32 r0, r1;
+  neg_b63_w(r0, r1, lo32(a), hi32(a), c, d);
+  return pack_w(r0, r1);
 }
 
 // branch-free lazy add / sub / neg (same values as add_lazy / sub_lazy / neg_lazy above)

@@ -39,39 +39,88 @@ struct Field {
   u32 c, d;
 };
 
-__device__ __forceinline__ u64 fmul(u64 a, u64 b, const Field& F) { return ff63::mul_pm_dev(a, b, F.d); }
-__device__ __forceinline__ u64 fsqr(u64 a, const Field& F) { return ff63::sqr_pm_dev(a, F.d); }
-__device__ __forceinline__ u64 fadd(u64 a, u64 b, const Field& F) { return ff63::add_lazy_dev(a, b, F.d); }
-__device__ __forceinline__ u64 fsub(u64 a, u64 b, const Field& F) { return ff63::sub_lazy_dev(a, b, F.d, F.p); }
-__device__ __forceinline__ u64 fneg(u64 a, const Field& F) { return ff63::neg_lazy_dev(a, F.d, F.p); }
-__device__ __forceinline__ void fmul_ip(u64& a, u64 b, const Field& F) { ff63::mul_pm_ip(a, b, F.d); }
-__device__ __forceinline__ void fsqr_ip(u64& a, const Field& F) { ff63::sqr_pm_ip(a, F.d); }
-__device__ __forceinline__ u64 fcanon(u64 a, const Field& F) { return ff63::canon_pm(a, F.c, F.p); }
+// One residue = two 32-bit words in two independent registers (no aligned pair: see ff63.cuh, word-level
+// forms).  Values are BOUNDED lazy residues (ff63.cuh, "b63" family): below 2^63 + 2^32; canonical inputs
+// qualify, every result qualifies again.
+struct R {
+  u32 lo, hi;
+};
+__device__ __forceinline__ R mkR(u64 v) { return R{(u32)v, (u32)(v >> 32)}; }
+__device__ __forceinline__ u64 toU(R a) { return ((u64)a.hi << 32) | a.lo; }
+
+__device__ __forceinline__ R fmul(R a, R b, const Field& F) {
+  R r;
+  ff63::mul_b63_w(r.lo, r.hi, a.lo, a.hi, b.lo, b.hi, F.c, F.d);
+  return r;
+}
+__device__ __forceinline__ R fsqr(R a, const Field& F) {
+  R r;
+  ff63::sqr_b63_w(r.lo, r.hi, a.lo, a.hi, F.c, F.d);
+  return r;
+}
+__device__ __forceinline__ R fadd(R a, R b, const Field& F) {
+  R r;
+  ff63::add_b63_w(r.lo, r.hi, a.lo, a.hi, b.lo, b.hi, F.c);
+  return r;
+}
+__device__ __forceinline__ R fsub(R a, R b, const Field& F) {
+  R r;
+  ff63::sub_b63_w(r.lo, r.hi, a.lo, a.hi, b.lo, b.hi, F.c, F.d);
+  return r;
+}
+__device__ __forceinline__ R fneg(R a, const Field& F) {
+  R r;
+  ff63::neg_b63_w(r.lo, r.hi, a.lo, a.hi, F.c, F.d);
+  return r;
+}
+__device__ __forceinline__ u64 fcanon(R a, const Field& F) { return ff63::canon_pm(toU(a), F.c, F.p); }
+// a constant the compiler may not hoist or speculate (plain broadcasts of an immediate into all accumulators
+// were moved above the interpreter's dispatch, 16 register moves per tape instruction)
+__device__ __forceinline__ R opaque(u64 v) {
+  R r;
+  asm volatile("mov.b64 {%0,%1}, %2;" : "=r"(r.lo), "=r"(r.hi) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ R shfl_up(R a, unsigned off) {
+  return R{__shfl_up_sync(0xffffffffu, a.lo, off), __shfl_up_sync(0xffffffffu, a.hi, off)};
+}
+__device__ __forceinline__ R shfl_down(R a, unsigned off) {
+  return R{__shfl_down_sync(0xffffffffu, a.lo, off), __shfl_down_sync(0xffffffffu, a.hi, off)};
+}
+__device__ __forceinline__ R shfl_idx(R a, int src) {
+  return R{__shfl_sync(0xffffffffu, a.lo, src), __shfl_sync(0xffffffffu, a.hi, src)};
+}
 
 // x^e, e uniform across the warp, left-to-right binary; x^0 = 1 (reference mod_pow, FFInt.cpp:371-383)
 template <int K>
-__device__ __forceinline__ void pow_uniform(u64 (&a)[K], u64 e, const Field& F) {
-  if (e == 0) {
+__device__ __forceinline__ void pow_uniform(R (&a)[K], u64 e, const Field& F) {
+  if (e <= 1) {
+    if (e == 0) {
 #pragma unroll
-    for (int k = 0; k < K; k++) a[k] = 1;
+      for (int k = 0; k < K; k++) a[k] = opaque(1);
+    }
     return;
   }
-  u64 base[K];
+  // The running power stays in the accumulator's own registers and the base is an explicit copy that the
+  // compiler may not move: with the roles the other way round (or a plain C++ copy) ptxas double-buffered
+  // ALL accumulators at EVERY tape instruction -- 16 IMAD.MOV per dispatch on the multiply pipe.
+  R base[K];
 #pragma unroll
-  for (int k = 0; k < K; k++) base[k] = a[k];
+  for (int k = 0; k < K; k++)
+    asm volatile("mov.b32 %0, %2;\n\tmov.b32 %1, %3;" : "=r"(base[k].lo), "=r"(base[k].hi) : "r"(a[k].lo), "r"(a[k].hi));
   int bit = 62 - __clzll((long long)e);          // index below the leading one
 #pragma unroll 1
   for (; bit >= 0; --bit) {
 #pragma unroll
-    for (int k = 0; k < K; k++) fsqr_ip(a[k], F);
+    for (int k = 0; k < K; k++) a[k] = fsqr(a[k], F);
     if ((e >> bit) & 1) {
 #pragma unroll
-      for (int k = 0; k < K; k++) fmul_ip(a[k], base[k], F);
+      for (int k = 0; k < K; k++) a[k] = fmul(a[k], base[k], F);
     }
   }
 }
 
-__device__ __forceinline__ u64 sqr_n(u64 x, int n, const Field& F) {
+__device__ __forceinline__ R sqr_n(R x, int n, const Field& F) {
 #pragma unroll 1
   for (int i = 0; i < n; i++) x = fsqr(x, F);
   return x;
@@ -80,16 +129,16 @@ __device__ __forceinline__ u64 sqr_n(u64 x, int n, const Field& F) {
 // x^(p-2) for p = 2^63 - c:  p - 2 = (2^47 - 1) * 2^16 + (2^16 - c - 2).
 // 2^47 - 1 by the addition chain 1,2,3,5,10,20,23,46,47 on the run length; then 16 squarings
 // interleaved with the bits of the 16-bit tail.  62 squarings + ~16 multiplications.  0 -> 0.
-__device__ __noinline__ u64 inv_fermat(u64 x, Field F) {
-  const u64 x1 = x;
-  const u64 x2 = fmul(fsqr(x1, F), x1, F);
-  const u64 x3 = fmul(fsqr(x2, F), x1, F);
-  const u64 x5 = fmul(sqr_n(x3, 2, F), x2, F);
-  const u64 x10 = fmul(sqr_n(x5, 5, F), x5, F);
-  const u64 x20 = fmul(sqr_n(x10, 10, F), x10, F);
-  const u64 x23 = fmul(sqr_n(x20, 3, F), x3, F);
-  const u64 x46 = fmul(sqr_n(x23, 23, F), x23, F);
-  u64 r = fmul(fsqr(x46, F), x1, F);             // x^(2^47 - 1)
+__device__ __noinline__ R inv_fermat(R x, Field F) {
+  const R x1 = x;
+  const R x2 = fmul(fsqr(x1, F), x1, F);
+  const R x3 = fmul(fsqr(x2, F), x1, F);
+  const R x5 = fmul(sqr_n(x3, 2, F), x2, F);
+  const R x10 = fmul(sqr_n(x5, 5, F), x5, F);
+  const R x20 = fmul(sqr_n(x10, 10, F), x10, F);
+  const R x23 = fmul(sqr_n(x20, 3, F), x3, F);
+  const R x46 = fmul(sqr_n(x23, 23, F), x23, F);
+  R r = fmul(fsqr(x46, F), x1, F);               // x^(2^47 - 1)
   const u32 tail = 65536u - F.c - 2u;            // c < 2^15: 16 bits
 #pragma unroll 1
   for (int bit = 15; bit >= 0; --bit) {
@@ -100,8 +149,8 @@ __device__ __noinline__ u64 inv_fermat(u64 x, Field F) {
 }
 
 // per-lane power with a lane-dependent exponent (divergent; only for `x^y` style input)
-__device__ __noinline__ u64 pow_lane(u64 b, u64 e, Field F) {
-  u64 r = 1;
+__device__ __noinline__ R pow_lane(R b, u64 e, Field F) {
+  R r = mkR(1);
 #pragma unroll 1
   while (e) {
     if (e & 1) r = fmul(r, b, F);
@@ -111,14 +160,14 @@ __device__ __noinline__ u64 pow_lane(u64 b, u64 e, Field F) {
   return r;
 }
 // FFInt::pow(const FFInt&) per lane (FFInt.cpp:155-179)
-__device__ __forceinline__ u64 pow_ff_lane(u64 b, u64 e_lazy, const Field& F) {
+__device__ __forceinline__ R pow_ff_lane(R b, R e_lazy, const Field& F) {
   const u64 e = fcanon(e_lazy, F);
   if (e == 2) return fsqr(b, F);
   if (e < (F.p >> 1)) return pow_lane(b, e, F);
   return pow_lane(inv_fermat(b, F), F.p - e - 1, F);
 }
 // FFInt::pow<int>(to_neg_int()) per lane (FFInt.hpp:149-174, FFInt.cpp:226-228)
-__device__ __forceinline__ u64 pow_negint_lane(u64 b, u64 e_lazy, const Field& F) {
+__device__ __forceinline__ R pow_negint_lane(R b, R e_lazy, const Field& F) {
   const int e = (int)(0u - (u32)fcanon(e_lazy, F));
   if (e == 2) return fsqr(b, F);
   if (e >= 0) return pow_lane(b, (u64)e, F);
@@ -129,70 +178,66 @@ __device__ __forceinline__ u64 pow_negint_lane(u64 b, u64 e_lazy, const Field& F
 // a[k] <- 1/a[k] (0 -> 0) for the K values of every thread of the block.  scratch: 64 u64 of
 // shared memory.  Must be reached by all threads of the block (the tape is block uniform).
 template <int K, int THREADS>
-__device__ __forceinline__ void block_inverse(u64 (&a)[K], const Field& F, u64* scratch) {
+__device__ __forceinline__ void block_inverse(R (&a)[K], const Field& F, u64* scratch) {
   constexpr int W = THREADS / 32;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned FULL = 0xffffffffu;
   bool z[K];
-  u64 e[K], pre[K];
+  R e[K], pre[K];
 #pragma unroll
   for (int k = 0; k < K; k++) {
     z[k] = fcanon(a[k], F) == 0;
-    e[k] = z[k] ? 1 : a[k];
+    e[k] = z[k] ? mkR(1) : a[k];
   }
   pre[0] = e[0];
 #pragma unroll
   for (int k = 1; k < K; k++) pre[k] = fmul(pre[k - 1], e[k], F);
-  const u64 t = pre[K - 1];
+  const R t = pre[K - 1];
   // inclusive prefix and inclusive suffix products over the lanes of the warp
-  u64 s = t, u = t;
+  R s = t, u = t;
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
-    const u64 so = __shfl_up_sync(FULL, s, off);
-    const u64 uo = __shfl_down_sync(FULL, u, off);
-    const u64 sm = fmul(s, so, F);
-    const u64 um = fmul(u, uo, F);
+    const R sm = fmul(s, shfl_up(s, off), F);
+    const R um = fmul(u, shfl_down(u, off), F);
     if (lane >= (unsigned)off) s = sm;
     if (lane + off < 32) u = um;
   }
-  u64 sx = __shfl_up_sync(FULL, s, 1);      // product of the lanes before this one
-  u64 ux = __shfl_down_sync(FULL, u, 1);    // product of the lanes after this one
-  if (lane == 0) sx = 1;
-  if (lane == 31) ux = 1;
-  u64 inv_upto, before;                     // 1 / (warps 0..warp), product of warps 0..warp-1
+  R sx = shfl_up(s, 1);        // product of the lanes before this one
+  R ux = shfl_down(u, 1);      // product of the lanes after this one
+  if (lane == 0) sx = mkR(1);
+  if (lane == 31) ux = mkR(1);
+  R inv_upto, before;          // 1 / (warps 0..warp), product of warps 0..warp-1
   if (W > 1) {
-    if (lane == 31) scratch[warp] = s;
+    if (lane == 31) scratch[warp] = toU(s);
     __syncthreads();
     if (warp == 0) {
-      u64 S = lane < W ? scratch[lane] : 1;
+      R S = lane < W ? mkR(scratch[lane]) : mkR(1);
 #pragma unroll
       for (int off = 1; off < W; off <<= 1) {
-        const u64 so = __shfl_up_sync(FULL, S, off);
-        const u64 sm = fmul(S, so, F);
+        const R sm = fmul(S, shfl_up(S, off), F);
         if (lane >= (unsigned)off) S = sm;
       }
-      const u64 IS = inv_fermat(S, F);
-      u64 Sx = __shfl_up_sync(FULL, S, 1);
-      if (lane == 0) Sx = 1;
-      scratch[lane] = Sx;
-      scratch[32 + lane] = IS;
+      const R IS = inv_fermat(S, F);
+      R Sx = shfl_up(S, 1);
+      if (lane == 0) Sx = mkR(1);
+      scratch[lane] = toU(Sx);
+      scratch[32 + lane] = toU(IS);
     }
     __syncthreads();
-    before = scratch[warp];
-    inv_upto = scratch[32 + warp];
+    before = mkR(scratch[warp]);
+    inv_upto = mkR(scratch[32 + warp]);
   } else {
-    const u64 total = __shfl_sync(FULL, s, 31);
-    inv_upto = inv_fermat(total, F);
-    before = 1;
+    inv_upto = inv_fermat(shfl_idx(s, 31), F);
+    before = mkR(1);
   }
   // 1/t = 1/(everything up to the end of this warp) * (warps before) * (lanes before) * (lanes after)
-  u64 J = fmul(fmul(inv_upto, ux, F), fmul(before, sx, F), F);
+  R J = fmul(fmul(inv_upto, ux, F), fmul(before, sx, F), F);
 #pragma unroll
   for (int k = K - 1; k >= 1; --k) {
-    a[k] = z[k] ? 0 : fmul(J, pre[k - 1], F);
+    const R q = fmul(J, pre[k - 1], F);
+    a[k] = z[k] ? mkR(0) : q;
     J = fmul(J, e[k], F);
   }
-  a[0] = z[0] ? 0 : J;
+  a[0] = z[0] ? mkR(0) : J;
 }
 
 // ---- the interpreter -------------------------------------------------------------------------
@@ -201,73 +246,245 @@ union InstrWord {
   Instr i;
 };
 
+// Per-thread view of the batch: where this thread's probes are, its column of the shared-memory slots.
 template <int K, int THREADS, bool VEC>
-__global__ void __launch_bounds__(THREADS, (K == 8 ? 768 : 1024) / THREADS) eval_tape_kernel(const EvalParams prm) {
-  extern __shared__ __align__(16) u64 smem[];
-  u64* const scratch = smem;                 // 64 words for block_inverse
-  u64* const stk = smem + 64 + threadIdx.x;  // [slot][k][thread], this thread's column
-  const Field F{prm.p, prm.c, prm.d};
+struct Lane {
+  static constexpr u32 STEP = VEC ? 2 * THREADS : THREADS;   // distance between this thread's accesses
+  static constexpr int NACC = VEC ? K / 2 : K;               // accesses per variable
+  const u64* vbase;      // values + first point of the tile
+  u64* obase;            // out + first point of the tile
+  u64 in_stride, out_stride;
+  uint2* stk;            // [slot][k][thread], this thread's column
+  u64* scratch;          // 64 words for block_inverse
+  u32 off[NACC];         // tile-relative offsets of this thread's accesses, clamped into the batch
+  u32 own, left, tmp_top;
+  Field F;
 
-  // Points owned by this thread.  VEC: pairs (2t, 2t+1) inside rows of 2*THREADS points, so that
-  // every load/store is one 16-byte access per lane and a warp covers 512 contiguous bytes.
-  const u64 tile = (u64)blockIdx.x * (u64)(THREADS * K);
-  constexpr u32 STEP = VEC ? 2 * THREADS : THREADS;       // distance between this thread's accesses
-  constexpr int NACC = VEC ? K / 2 : K;                   // accesses per variable
-  // Tile-relative offsets of this thread's accesses, clamped into the batch: lanes beyond the end
-  // recompute the last valid point and never store, so the hot loop has no bounds checks.
-  const u64 left64 = prm.n_points - tile;                 // > 0: the grid covers exactly the batch
-  const u32 left = left64 < (u64)(THREADS * K) ? (u32)left64 : (u32)(THREADS * K);
-  const u32 own = VEC ? 2 * threadIdx.x : threadIdx.x;
-  u32 off[NACC];
+  // Points owned by this thread.  VEC: pairs (2t, 2t+1) inside rows of 2*THREADS points, so that every
+  // load/store is one 16-byte access per lane and a warp covers 512 contiguous bytes.  Lanes beyond the end
+  // of the batch recompute the last valid point and never store: the hot loop has no bounds checks.
+  __device__ __forceinline__ void init(const EvalParams& prm, u64* smem) {
+    const u64 tile = (u64)blockIdx.x * (u64)(THREADS * K);
+    const u64 left64 = prm.n_points - tile;               // > 0: the grid covers exactly the batch
+    left = left64 < (u64)(THREADS * K) ? (u32)left64 : (u32)(THREADS * K);
+    own = VEC ? 2 * threadIdx.x : threadIdx.x;
 #pragma unroll
-  for (int j = 0; j < NACC; j++) {
-    const u32 o = own + j * STEP, last = left - (VEC ? 2 : 1);
-    off[j] = o < last ? o : last;
+    for (int j = 0; j < NACC; j++) {
+      const u32 o = own + j * STEP, last = left - (VEC ? 2 : 1);
+      off[j] = o < last ? o : last;
+    }
+    vbase = reinterpret_cast<const u64*>(prm.values) + tile;
+    obase = reinterpret_cast<u64*>(prm.out) + tile;
+    in_stride = prm.in_stride;
+    out_stride = prm.out_stride;
+    scratch = smem;
+    stk = reinterpret_cast<uint2*>(smem + 64) + threadIdx.x;
+    tmp_top = prm.n_slots - 1;
+    F = Field{prm.p, prm.c, prm.d};
   }
-  const u64* const vbase = reinterpret_cast<const u64*>(prm.values) + tile;
-  u64* const obase = reinterpret_cast<u64*>(prm.out) + tile;
-
-  auto load_var = [&](u32 var, u64 (&b)[K]) {
-    const u64* row = vbase + (u64)var * prm.in_stride;
+  __device__ __forceinline__ void load_var(u32 var, R (&b)[K]) const {
+    const u64* row = vbase + (u64)var * in_stride;
     if (VEC) {
 #pragma unroll
       for (int j = 0; j < NACC; j++) {
         // n_points is even and rows are 16-byte aligned on this path
-        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(row + off[j]));
-        b[2 * j] = v.x;
-        b[2 * j + 1] = v.y;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + off[j]));
+        b[2 * j] = R{v.x, v.y};
+        b[2 * j + 1] = R{v.z, v.w};
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < NACC; j++) b[j] = __ldg(row + off[j]);
+      for (int j = 0; j < NACC; j++) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(row + off[j]));
+        b[j] = R{v.x, v.y};
+      }
     }
-  };
-  auto in_range = [&](int j) { return own + j * STEP < left; };
-  auto push = [&](const u64 (&a)[K], u32 sp) {
+  }
+  __device__ __forceinline__ bool in_range(int j) const { return own + j * STEP < left; }
+  __device__ __forceinline__ void slot_put(const R (&a)[K], u32 slot) const {
+    uint2* t = stk + (size_t)slot * (K * THREADS);
 #pragma unroll
-    for (int k = 0; k < K; k++) stk[(sp * K + k) * THREADS] = a[k];
-  };
-  auto pop = [&](u64 (&b)[K], u32 sp) {
+    for (int k = 0; k < K; k++) t[k * THREADS] = make_uint2(a[k].lo, a[k].hi);
+  }
+  __device__ __forceinline__ void slot_get(R (&b)[K], u32 slot) const {
+    const uint2* t = stk + (size_t)slot * (K * THREADS);
 #pragma unroll
-    for (int k = 0; k < K; k++) b[k] = stk[(sp * K + k) * THREADS];
-  };
+    for (int k = 0; k < K; k++) {
+      const uint2 v = t[k * THREADS];
+      b[k] = R{v.x, v.y};
+    }
+  }
+  // spill slots count up from 0, temp slots (shared sub-expressions, co-evaluated sums) down from the last slot
+  __device__ __forceinline__ void tmp_put(const R (&a)[K], u32 slot) const { slot_put(a, tmp_top - slot); }
+  __device__ __forceinline__ void tmp_get(R (&b)[K], u32 slot) const { slot_get(b, tmp_top - slot); }
+  __device__ __forceinline__ void store_row(u32 out_slot, const R (&a)[K]) const {
+    u64* row = obase + (u64)out_slot * out_stride;
+    if (VEC) {
+#pragma unroll
+      for (int j = 0; j < NACC; j++)
+        if (in_range(j))
+          *reinterpret_cast<ulonglong2*>(row + off[j]) = make_ulonglong2(fcanon(a[2 * j], F), fcanon(a[2 * j + 1], F));
+    } else {
+#pragma unroll
+      for (int j = 0; j < NACC; j++)
+        if (in_range(j)) row[off[j]] = fcanon(a[j], F);
+    }
+  }
+};
 
-  // temp slots (shared sub-expressions, co-evaluated sums) count down from the last slot
-  const u32 tmp_top = prm.n_slots - 1;
-  auto tmp_get = [&](u64 (&b)[K], u32 slot) {
-    const u64* t = stk + (size_t)(tmp_top - slot) * (K * THREADS);
+#ifndef FFGPU_GENERIC_INLINE
+#define FFGPU_GENERIC_INLINE __forceinline__
+#endif
+// The uncommon instructions (lane exponents, negated variables, negative literal powers, ...), out of line:
+// the accumulators travel through local memory for these, which keeps them out of the register allocation
+// of the hot loop (inlined, they made ptxas copy all accumulators at every tape instruction).
+template <int K, int THREADS, bool VEC>
+__device__ FFGPU_GENERIC_INLINE u32 generic_op(const Lane<K, THREADS, VEC>& L, u32 opword, u32 arg, u64 imm, R (&acc)[K],
+                                       u32 sp) {
+  struct {
+    u32 op, src, flags, arg;
+    u64 imm;
+  } ins = {opword & 0xffu, (opword >> 8) & 0xffu, (opword >> 16) & 0xffu, arg, imm};
+  const Field F = L.F;
+  R b[K];
+  switch (ins.src) {
+    case SRC_POP: L.slot_get(b, --sp); break;
+    case SRC_VAR: L.load_var(ins.arg, b); break;
+    case SRC_NEGVAR:
+      L.load_var(ins.arg, b);
 #pragma unroll
-    for (int k = 0; k < K; k++) b[k] = t[k * THREADS];
-  };
-  auto tmp_put = [&](const u64 (&a)[K], u32 slot) {
-    u64* t = stk + (size_t)(tmp_top - slot) * (K * THREADS);
+      for (int k = 0; k < K; k++) b[k] = fneg(b[k], F);
+      break;
+    case SRC_CONST:
 #pragma unroll
-    for (int k = 0; k < K; k++) t[k * THREADS] = a[k];
-  };
+      for (int k = 0; k < K; k++) b[k] = mkR(ins.imm);
+      break;
+    case SRC_TMP: L.tmp_get(b, ins.arg); break;
+    default:
+#pragma unroll
+      for (int k = 0; k < K; k++) b[k] = mkR(0);
+      break;
+  }
+  switch (ins.op) {
+    case OP_LOAD:
+      if (ins.flags & F_PUSH) L.slot_put(acc, sp++);
+#pragma unroll
+      for (int k = 0; k < K; k++) acc[k] = b[k];
+      break;
+    case OP_ADD:
+#pragma unroll
+      for (int k = 0; k < K; k++) acc[k] = fadd(acc[k], b[k], F);
+      break;
+    case OP_SUB:
+#pragma unroll
+      for (int k = 0; k < K; k++) acc[k] = (ins.flags & F_SWAP) ? fsub(b[k], acc[k], F) : fsub(acc[k], b[k], F);
+      break;
+    case OP_MUL:
+#pragma unroll
+      for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], b[k], F);
+      break;
+    case OP_MULADD: {
+      R x[K];
+      L.load_var(ins.arg, x);
+      const R c = mkR(ins.imm);
+#pragma unroll
+      for (int k = 0; k < K; k++) acc[k] = fadd(fmul(acc[k], x[k], F), c, F);
+      break;
+    }
+    case OP_SQR:
+#pragma unroll
+      for (int k = 0; k < K; k++) acc[k] = fsqr(acc[k], F);
+      break;
+    case OP_SAVE:
+      L.tmp_put(acc, ins.arg);
+      break;
+    case OP_ACCUM:
+      if (ins.flags & F_INIT) {
+#pragma unroll
+        for (int k = 0; k < K; k++) b[k] = (ins.flags & F_SWAP) ? fneg(acc[k], F) : acc[k];
+      } else {
+        L.tmp_get(b, ins.arg);
+#pragma unroll
+        for (int k = 0; k < K; k++) b[k] = (ins.flags & F_SWAP) ? fsub(b[k], acc[k], F) : fadd(b[k], acc[k], F);
+      }
+      L.tmp_put(b, ins.arg);
+      break;
+    case OP_NEG:
+#pragma unroll
+      for (int k = 0; k < K; k++) acc[k] = fneg(acc[k], F);
+      break;
+    case OP_INV:
+      block_inverse<K, THREADS>(acc, F, L.scratch);
+      break;
+    case OP_POWU: {
+      // FFInt::pow(const FFInt&) with a lane-uniform exponent residue (FFInt.cpp:155-179)
+      const u64 e = ins.imm;
+      if (e == 2) {
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[k] = fsqr(acc[k], F);
+      } else if (e < (F.p >> 1)) {
+        pow_uniform<K>(acc, e, F);
+      } else {
+        block_inverse<K, THREADS>(acc, F, L.scratch);
+        pow_uniform<K>(acc, F.p - e - 1, F);
+      }
+      break;
+    }
+    case OP_NPOWU: {
+      // FFInt::pow<int>(a.to_neg_int()) with a lane-uniform exponent (FFInt.hpp:149-174)
+      const int e = (int)(0u - (u32)ins.imm);
+      if (e == 2) {
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[k] = fsqr(acc[k], F);
+      } else if (e >= 0) {
+        pow_uniform<K>(acc, (u64)e, F);
+      } else {
+        block_inverse<K, THREADS>(acc, F, L.scratch);
+        pow_uniform<K>(acc, (u64)(-(long long)e), F);
+      }
+      break;
+    }
+    case OP_POWL:
+#pragma unroll
+      for (int k = 0; k < K; k++)
+        acc[k] = (ins.flags & F_SWAP) ? pow_ff_lane(b[k], acc[k], F) : pow_ff_lane(acc[k], b[k], F);
+      break;
+    case OP_NPOWL:
+#pragma unroll
+      for (int k = 0; k < K; k++)
+        acc[k] = (ins.flags & F_SWAP) ? pow_negint_lane(b[k], acc[k], F) : pow_negint_lane(acc[k], b[k], F);
+      break;
+    case OP_STORE:
+      L.store_row(ins.arg, acc);
+      break;
+    default:
+      break;
+  }
+  if (ins.flags & F_NEGR) {
+#pragma unroll
+    for (int k = 0; k < K; k++) acc[k] = fneg(acc[k], F);
+  }
+  return sp;
+}
 
-  u64 acc[K];
+// Resident blocks per SM the kernel is compiled for (= its register budget).  At 8 probes per thread the
+// interpreter wants ~100 registers: below that ptxas spills the instruction words or double-buffers the
+// accumulators at every dispatch, which costs more than the lost occupancy.
+template <int K, int THREADS>
+constexpr int min_blocks() {
+  return K == 8 ? 768 / THREADS : 1024 / THREADS;
+}
+
+template <int K, int THREADS, bool VEC>
+__global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS>()) eval_tape_kernel(const EvalParams prm) {
+  extern __shared__ __align__(16) u64 smem[];
+  Lane<K, THREADS, VEC> L;
+  L.init(prm, smem);
+  const Field F = L.F;
+
+  R acc[K];
 #pragma unroll
-  for (int k = 0; k < K; k++) acc[k] = 0;
+  for (int k = 0; k < K; k++) acc[k] = opaque(0);
   u32 sp = 0;                                // spill-stack pointer (uniform)
 
   // blockIdx.y selects a chunk of the tape (a run of whole functions): many-function collections
@@ -283,264 +500,132 @@ __global__ void __launch_bounds__(THREADS, (K == 8 ? 768 : 1024) / THREADS) eval
   for (; pc < pc_end;) {
     nxt.v = __ldg(tape + pc + 1);            // the tape ends in two HALTs: always in bounds
     const Instr ins = cur.i;
-    u64 b[K];
+    R b[K];
     switch (ins.fast) {
       // ---- the common (op, operand) combinations, each working on ACC in place -----------------
       case FX_PUSH_LOAD_VAR:
-        push(acc, sp++);
+        L.slot_put(acc, sp++);
       case FX_LOAD_VAR:
-        load_var(ins.arg, acc);
+        L.load_var(ins.arg, acc);
         break;
       case FX_PUSH_LOAD_CONST:
-        push(acc, sp++);
+        L.slot_put(acc, sp++);
       case FX_LOAD_CONST:
 #pragma unroll
-        for (int k = 0; k < K; k++) acc[k] = ins.imm;
+        for (int k = 0; k < K; k++) acc[k] = opaque(ins.imm);
         break;
       case FX_ADD_VAR:
-        load_var(ins.arg, b);
+        L.load_var(ins.arg, b);
 #pragma unroll
         for (int k = 0; k < K; k++) acc[k] = fadd(acc[k], b[k], F);
         break;
-      case FX_ADD_CONST:
+      case FX_ADD_CONST: {
+        const R c = mkR(ins.imm);
 #pragma unroll
-        for (int k = 0; k < K; k++) acc[k] = fadd(acc[k], ins.imm, F);
+        for (int k = 0; k < K; k++) acc[k] = fadd(acc[k], c, F);
         break;
+      }
       case FX_ADD_POP:
-        pop(b, --sp);
+        L.slot_get(b, --sp);
 #pragma unroll
         for (int k = 0; k < K; k++) acc[k] = fadd(acc[k], b[k], F);
         break;
       case FX_SUB_VAR:
-        load_var(ins.arg, b);
+        L.load_var(ins.arg, b);
 #pragma unroll
         for (int k = 0; k < K; k++) acc[k] = fsub(acc[k], b[k], F);
         break;
       case FX_RSUB_VAR:
-        load_var(ins.arg, b);
+        L.load_var(ins.arg, b);
 #pragma unroll
         for (int k = 0; k < K; k++) acc[k] = fsub(b[k], acc[k], F);
         break;
-      case FX_RSUB_CONST:
+      case FX_RSUB_CONST: {
+        const R c = mkR(ins.imm);
 #pragma unroll
-        for (int k = 0; k < K; k++) acc[k] = fsub(ins.imm, acc[k], F);
+        for (int k = 0; k < K; k++) acc[k] = fsub(c, acc[k], F);
         break;
+      }
       case FX_SUB_POP:
-        pop(b, --sp);
+        L.slot_get(b, --sp);
 #pragma unroll
         for (int k = 0; k < K; k++) acc[k] = fsub(acc[k], b[k], F);
         break;
       case FX_RSUB_POP:
-        pop(b, --sp);
+        L.slot_get(b, --sp);
 #pragma unroll
         for (int k = 0; k < K; k++) acc[k] = fsub(b[k], acc[k], F);
         break;
       case FX_MUL_VAR:
-        load_var(ins.arg, b);
+        L.load_var(ins.arg, b);
 #pragma unroll
-        for (int k = 0; k < K; k++) fmul_ip(acc[k], b[k], F);
+        for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], b[k], F);
         break;
-      case FX_MUL_CONST:
+      case FX_MUL_CONST: {
+        const R c = mkR(ins.imm);
 #pragma unroll
-        for (int k = 0; k < K; k++) fmul_ip(acc[k], ins.imm, F);
+        for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], c, F);
         break;
+      }
       case FX_MUL_POP:
-        pop(b, --sp);
+        L.slot_get(b, --sp);
 #pragma unroll
-        for (int k = 0; k < K; k++) fmul_ip(acc[k], b[k], F);
+        for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], b[k], F);
         break;
       case FX_SQR:
 #pragma unroll
-        for (int k = 0; k < K; k++) fsqr_ip(acc[k], F);
+        for (int k = 0; k < K; k++) acc[k] = fsqr(acc[k], F);
         break;
-      case FX_POWU: {
-        // FFInt::pow(const FFInt&) with a lane-uniform exponent residue (FFInt.cpp:155-179)
-        const u64 e = ins.imm;
-        if (e == 2) {
-#pragma unroll
-          for (int k = 0; k < K; k++) fsqr_ip(acc[k], F);
-        } else if (e < (F.p >> 1)) {
-          pow_uniform<K>(acc, e, F);
-        } else {
-          block_inverse<K, THREADS>(acc, F, scratch);
-          pow_uniform<K>(acc, F.p - e - 1, F);
-        }
+      case FX_POWU:
+        // a literal power below p/2 (the compiler gives everything else the generic code)
+        pow_uniform<K>(acc, ins.imm, F);
         break;
-      }
       case FX_INV:
-        block_inverse<K, THREADS>(acc, F, scratch);
+        block_inverse<K, THREADS>(acc, F, L.scratch);
         break;
       case FX_SAVE:
-        tmp_put(acc, ins.arg);
-        break;
       case FX_ACCUM_INIT:
-        tmp_put(acc, ins.arg);
+        L.tmp_put(acc, ins.arg);
         break;
       case FX_ACCUM_ADD:
-        tmp_get(b, ins.arg);
+        L.tmp_get(b, ins.arg);
 #pragma unroll
         for (int k = 0; k < K; k++) b[k] = fadd(b[k], acc[k], F);
-        tmp_put(b, ins.arg);
+        L.tmp_put(b, ins.arg);
         break;
       case FX_ACCUM_SUB:
-        tmp_get(b, ins.arg);
+        L.tmp_get(b, ins.arg);
 #pragma unroll
         for (int k = 0; k < K; k++) b[k] = fsub(b[k], acc[k], F);
-        tmp_put(b, ins.arg);
+        L.tmp_put(b, ins.arg);
         break;
       case FX_LOAD_TMP:
-        tmp_get(acc, ins.arg);
+        L.tmp_get(acc, ins.arg);
         break;
       case FX_ADD_TMP:
-        tmp_get(b, ins.arg);
+        L.tmp_get(b, ins.arg);
 #pragma unroll
         for (int k = 0; k < K; k++) acc[k] = fadd(acc[k], b[k], F);
         break;
       case FX_MUL_TMP:
-        tmp_get(b, ins.arg);
+        L.tmp_get(b, ins.arg);
 #pragma unroll
-        for (int k = 0; k < K; k++) fmul_ip(acc[k], b[k], F);
+        for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], b[k], F);
         break;
-      case FX_STORE: {
-        u64* row = obase + (u64)ins.arg * prm.out_stride;
-        if (VEC) {
-#pragma unroll
-          for (int j = 0; j < NACC; j++)
-            if (in_range(j))
-              *reinterpret_cast<ulonglong2*>(row + off[j]) =
-                  make_ulonglong2(fcanon(acc[2 * j], F), fcanon(acc[2 * j + 1], F));
-        } else {
-#pragma unroll
-          for (int j = 0; j < NACC; j++)
-            if (in_range(j)) row[off[j]] = fcanon(acc[j], F);
-        }
+      case FX_STORE:
+        L.store_row(ins.arg, acc);
         break;
-      }
 
-      // ---- everything else: general two-level decode ------------------------------------------------
+      // ---- everything else, out of line (copies of the state: the originals never have their address taken)
       default: {
         if (ins.op == OP_HALT) return;
-        switch (ins.src) {
-          case SRC_POP: pop(b, --sp); break;
-          case SRC_VAR: load_var(ins.arg, b); break;
-          case SRC_NEGVAR:
-            load_var(ins.arg, b);
+        Lane<K, THREADS, VEC> L2 = L;
+        R t[K];
 #pragma unroll
-            for (int k = 0; k < K; k++) b[k] = fneg(b[k], F);
-            break;
-          case SRC_CONST:
+        for (int k = 0; k < K; k++) t[k] = acc[k];
+        sp = generic_op<K, THREADS, VEC>(L2, cur.v.x, cur.v.y, ins.imm, t, sp);
 #pragma unroll
-            for (int k = 0; k < K; k++) b[k] = ins.imm;
-            break;
-          case SRC_TMP: tmp_get(b, ins.arg); break;
-          default:
-#pragma unroll
-            for (int k = 0; k < K; k++) b[k] = 0;
-            break;
-        }
-        switch (ins.op) {
-          case OP_LOAD:
-            if (ins.flags & F_PUSH) push(acc, sp++);
-#pragma unroll
-            for (int k = 0; k < K; k++) acc[k] = b[k];
-            break;
-          case OP_ADD:
-#pragma unroll
-            for (int k = 0; k < K; k++) acc[k] = fadd(acc[k], b[k], F);
-            break;
-          case OP_SUB:
-#pragma unroll
-            for (int k = 0; k < K; k++) acc[k] = (ins.flags & F_SWAP) ? fsub(b[k], acc[k], F) : fsub(acc[k], b[k], F);
-            break;
-          case OP_MUL:
-#pragma unroll
-            for (int k = 0; k < K; k++) fmul_ip(acc[k], b[k], F);
-            break;
-          case OP_MULADD: {
-            u64 x[K];
-            load_var(ins.arg, x);
-#pragma unroll
-            for (int k = 0; k < K; k++) acc[k] = fadd(fmul(acc[k], x[k], F), ins.imm, F);
-            break;
-          }
-          case OP_SQR:
-#pragma unroll
-            for (int k = 0; k < K; k++) fsqr_ip(acc[k], F);
-            break;
-          case OP_SAVE:
-            tmp_put(acc, ins.arg);
-            break;
-          case OP_ACCUM:
-            if (ins.flags & F_INIT) {
-#pragma unroll
-              for (int k = 0; k < K; k++) b[k] = (ins.flags & F_SWAP) ? fneg(acc[k], F) : acc[k];
-            } else {
-              tmp_get(b, ins.arg);
-#pragma unroll
-              for (int k = 0; k < K; k++) b[k] = (ins.flags & F_SWAP) ? fsub(b[k], acc[k], F) : fadd(b[k], acc[k], F);
-            }
-            tmp_put(b, ins.arg);
-            break;
-          case OP_NEG:
-#pragma unroll
-            for (int k = 0; k < K; k++) acc[k] = fneg(acc[k], F);
-            break;
-          case OP_INV:
-            block_inverse<K, THREADS>(acc, F, scratch);
-            break;
-          case OP_POWU: {
-            const u64 e = ins.imm;
-            if (e == 2) {
-#pragma unroll
-              for (int k = 0; k < K; k++) fsqr_ip(acc[k], F);
-            } else if (e < (F.p >> 1)) {
-              pow_uniform<K>(acc, e, F);
-            } else {
-              block_inverse<K, THREADS>(acc, F, scratch);
-              pow_uniform<K>(acc, F.p - e - 1, F);
-            }
-            break;
-          }
-          case OP_NPOWU: {
-            // FFInt::pow<int>(a.to_neg_int()) with a lane-uniform exponent (FFInt.hpp:149-174)
-            const int e = (int)(0u - (u32)ins.imm);
-            if (e == 2) {
-#pragma unroll
-              for (int k = 0; k < K; k++) fsqr_ip(acc[k], F);
-            } else if (e >= 0) {
-              pow_uniform<K>(acc, (u64)e, F);
-            } else {
-              block_inverse<K, THREADS>(acc, F, scratch);
-              pow_uniform<K>(acc, (u64)(-(long long)e), F);
-            }
-            break;
-          }
-          case OP_POWL:
-#pragma unroll
-            for (int k = 0; k < K; k++)
-              acc[k] = (ins.flags & F_SWAP) ? pow_ff_lane(b[k], acc[k], F) : pow_ff_lane(acc[k], b[k], F);
-            break;
-          case OP_NPOWL:
-#pragma unroll
-            for (int k = 0; k < K; k++)
-              acc[k] = (ins.flags & F_SWAP) ? pow_negint_lane(b[k], acc[k], F) : pow_negint_lane(acc[k], b[k], F);
-            break;
-          case OP_STORE: {
-            u64* row = obase + (u64)ins.arg * prm.out_stride;
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-              const int j = VEC ? k / 2 : k;
-              if (in_range(j)) row[off[j] + (VEC ? (k & 1) : 0)] = fcanon(acc[k], F);
-            }
-            break;
-          }
-          default:
-            break;
-        }
-        if (ins.flags & F_NEGR) {
-#pragma unroll
-          for (int k = 0; k < K; k++) acc[k] = fneg(acc[k], F);
-        }
+        for (int k = 0; k < K; k++) acc[k] = opaque(toU(t[k]));
         break;
       }
     }
@@ -661,6 +746,34 @@ __global__ void fill_points_kernel(u64* values, u64 n_vars, u64 n_points, u64 st
     values[v * stride + j] = 1 + splitmix64_at(seed + v * total + first + j) % (p - 1);
   }
 }
+// probe points on a line: values[v][j] = a[v] * t[j] + s[v]  (canonical).  What Reconstructor::queue_probes
+// computes on the host per point (reference: Reconstructor.hpp:2946-2950 -- values[0] = t + shift[0],
+// values[i] = rand_zi[i-1] * t + shift[i]; the factor-scan variant :2952-2960 is a[v] in {0,1}).
+// Two points per thread, 16-byte accesses; a[] and s[] are read through the uniform path.
+__global__ void __launch_bounds__(256) line_points_kernel(u64* __restrict__ values, const u64* __restrict__ t,
+                                                          const u64* __restrict__ a, const u64* __restrict__ s,
+                                                          u32 n_vars, u64 n_points, u64 stride, u64 p) {
+  const Field F{p, (u32)(0x8000000000000000ULL - p), (u32)(2 * (0x8000000000000000ULL - p))};
+  const bool vec = (n_points % 2 == 0) && (stride % 2 == 0) && ((uintptr_t)values % 16 == 0) && ((uintptr_t)t % 16 == 0);
+  if (vec) {
+    for (u64 j = 2 * ((u64)blockIdx.x * blockDim.x + threadIdx.x); j < n_points; j += 2 * (u64)gridDim.x * blockDim.x) {
+      const ulonglong2 tt = __ldg(reinterpret_cast<const ulonglong2*>(t + j));
+      for (u32 v = 0; v < n_vars; v++) {
+        const u64 av = __ldg(a + v), sv = __ldg(s + v);
+        ulonglong2 x;
+        x.x = fcanon(fadd(fmul(mkR(tt.x), mkR(av), F), mkR(sv), F), F);
+        x.y = fcanon(fadd(fmul(mkR(tt.y), mkR(av), F), mkR(sv), F), F);
+        *reinterpret_cast<ulonglong2*>(values + (u64)v * stride + j) = x;
+      }
+    }
+  } else {
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < n_points; j += (u64)gridDim.x * blockDim.x) {
+      const u64 tj = __ldg(t + j);
+      for (u32 v = 0; v < n_vars; v++)
+        values[(u64)v * stride + j] = fcanon(fadd(fmul(mkR(tj), mkR(__ldg(a + v)), F), mkR(__ldg(s + v)), F), F);
+    }
+  }
+}
 __global__ void checksum_kernel(const u64* out, u64 n_points, u64 stride, u64 p, u64* sums) {
   // one block per output row; sum mod p (p < 2^63: a + b cannot wrap) and xor
   const u64* row = out + (u64)blockIdx.x * stride;
@@ -693,7 +806,7 @@ __global__ void field_ops_kernel(int op, const u64* a, const u64* b, u64* r, u64
   const Field F{p, (u32)(0x8000000000000000ULL - p), (u32)(2 * (0x8000000000000000ULL - p))};
   const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   // all threads stay alive: op 6 uses block-wide barriers
-  const u64 x = i < n ? a[i] : 1, y = i < n ? b[i] : 1;
+  const R x = mkR(i < n ? a[i] : 1), y = mkR(i < n ? b[i] : 1);
   __shared__ u64 scratch[64];
   u64 v = 0;
   switch (op) {
@@ -703,10 +816,15 @@ __global__ void field_ops_kernel(int op, const u64* a, const u64* b, u64* r, u64
     case 3: v = fcanon(fneg(x, F), F); break;
     case 4: v = fcanon(inv_fermat(x, F), F); break;
     case 5: v = fcanon(pow_ff_lane(x, y, F), F); break;
-    case 6: { u64 t[1] = {x}; block_inverse<1, 256>(t, F, scratch); v = fcanon(t[0], F); break; }
+    case 6: { R t[1] = {x}; block_inverse<1, 256>(t, F, scratch); v = fcanon(t[0], F); break; }
     case 7: v = fcanon(pow_negint_lane(x, y, F), F); break;
     case 8: v = fcanon(x, F); break;
-    case 9: { u64 t[2] = {x, y}; block_inverse<2, 256>(t, F, scratch); v = fcanon(fmul(t[0], t[1], F), F); break; }
+    case 9: { R t[2] = {x, y}; block_inverse<2, 256>(t, F, scratch); v = fcanon(fmul(t[0], t[1], F), F); break; }
+    // chains: the result of one operation is the (un-canonicalised) input of the next
+    case 10: v = fcanon(fmul(fadd(x, y, F), y, F), F); break;
+    case 11: v = fcanon(fmul(fsub(x, y, F), y, F), F); break;
+    case 12: { const R m = fmul(x, y, F); v = fcanon(fsub(fsqr(m, F), y, F), F); break; }
+    case 13: v = fcanon(fadd(fmul(fneg(x, F), y, F), x, F), F); break;
     default: break;
   }
   if (i < n) r[i] = v;
@@ -718,6 +836,17 @@ cudaError_t launch_fill_points(uint64_t* values, uint64_t n_vars, uint64_t n_poi
                                cudaStream_t stream) {
   if (n_vars * n_points == 0) return cudaSuccess;
   fill_points_kernel<<<148 * 8, 256, 0, stream>>>(reinterpret_cast<u64*>(values), n_vars, n_points, stride, first_point, total_points, seed, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_line_points(uint64_t* values, const uint64_t* t, const uint64_t* a, const uint64_t* s,
+                               uint32_t n_vars, uint64_t n_points, uint64_t stride, uint64_t p, cudaStream_t stream) {
+  if ((uint64_t)n_vars * n_points == 0) return cudaSuccess;
+  const uint64_t want = (n_points / 2 + 255) / 256;
+  const unsigned blocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>(want, 1), 148 * 16);
+  line_points_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<u64*>(values), reinterpret_cast<const u64*>(t),
+                                                 reinterpret_cast<const u64*>(a), reinterpret_cast<const u64*>(s),
+                                                 n_vars, n_points, stride, p);
   return cudaGetLastError();
 }
 

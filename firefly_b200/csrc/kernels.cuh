@@ -40,6 +40,10 @@ cudaError_t launch_eval(const EvalParams& prm, const LaunchShape& shape, cudaStr
 cudaError_t launch_fill_points(uint64_t* values, uint64_t n_vars, uint64_t n_points, uint64_t stride,
                                uint64_t first_point, uint64_t total_points, uint64_t seed, uint64_t p,
                                cudaStream_t stream);
+// probe points on a line through the anchor: values[v][j] = a[v] * t[j] + s[v] mod p (canonical); what
+// Reconstructor::queue_probes builds per point on the host (reference: Reconstructor.hpp:2946-2960)
+cudaError_t launch_line_points(uint64_t* values, const uint64_t* t, const uint64_t* a, const uint64_t* s,
+                               uint32_t n_vars, uint64_t n_points, uint64_t stride, uint64_t p, cudaStream_t stream);
 // out[f] = (sum of column f mod p, xor of column f) over n_points -- compact fingerprints of big outputs
 cudaError_t launch_checksum(const uint64_t* out, uint64_t n_out, uint64_t n_points, uint64_t stride, uint64_t p,
                             uint64_t* sums /* [n_out][2] */, cudaStream_t stream);

@@ -16,6 +16,8 @@
  *   ShuntingYardParser::get_rp_function(i)                           ffgpu_rpn
  *     source/ShuntingYardParser.cpp:534-536
  *   primes()   source/ReconstHelper.cpp:24-125                       ffgpu_prime / ffgpu_n_primes
+ *   Reconstructor::queue_probes point construction                   ffgpu_eval_line
+ *     source/include/firefly/Reconstructor.hpp:2946-2960               (x_v = a_v * t + s_v on the GPU)
  *
  * Data layout: flat uint64_t residues, the layout std::vector<FFIntVec<N>> already has in
  * memory ([variable][point], contiguous) and that MPIWorker ships over the wire
@@ -75,6 +77,9 @@ size_t ffgpu_n_out(const ffgpu_tape*);         /* values per point that ffgpu_ev
 size_t ffgpu_n_instr(const ffgpu_tape*);       /* tape length (without the terminators) */
 size_t ffgpu_stack_depth(const ffgpu_tape*);    /* spill slots per probe */
 size_t ffgpu_n_temps(const ffgpu_tape*);        /* temp slots per probe (shared sub-expressions) */
+/* functions that failed the compiler's translation self-check with sharing on and were emitted as plain trees
+ * (0 unless the sharing pass has a bug; a function failing as a plain tree too makes ffgpu_compile fail) */
+size_t ffgpu_cse_fallbacks(const ffgpu_tape*);
 size_t ffgpu_n_slots(const ffgpu_tape*);        /* shared-memory slots per probe the kernel reserves (spill + temps) */
 /* RPN of distinct function i, tokens joined by ' '; returns the length needed (without NUL) */
 size_t ffgpu_rpn(const ffgpu_tape*, size_t i, char* buf, size_t cap);
@@ -84,6 +89,10 @@ size_t ffgpu_get_tape(const ffgpu_tape*, void* buf, size_t cap);
  * w[0]=tokens w[1]=modular multiplications w[2]=add/sub/neg w[3]=inversions w[4]=max RPN stack depth */
 void ffgpu_work(const ffgpu_tape*, uint64_t w[5]);
 
+/* work the compiled tape executes per probe (after constant folding and sharing of equal sub-expressions):
+ * w[0]=instructions w[1]=modular multiplications w[2]=add/sub/neg w[3]=inversions w[4]=variable row reads */
+void ffgpu_tape_work(const ffgpu_tape*, uint64_t w[5]);
+
 /* ---- prime -------------------------------------------------------------------------------- */
 /* p must be a prime of the form 2^63 - c, 0 < c < 2^15 (all 300 primes of FireFly's table are). */
 int ffgpu_set_prime(ffgpu_tape*, uint64_t p);
@@ -92,9 +101,16 @@ uint32_t ffgpu_n_primes(void);          /* 300 */
 uint64_t ffgpu_prime(uint32_t i);       /* the i-th largest prime below 2^63 */
 
 /* ---- evaluate ----------------------------------------------------------------------------- */
-/* HOST buffers.  values: [n_vars][n_points], out: [n_out][n_points].  Points are sharded over the
+/* HOST buffers.  values: [n_vars][n_points] residues in [0, p) (what FFInt holds), out: [n_out][n_points].  Points are sharded over the
  * GPUs of the ctx by contiguous index range, copies and kernels are pipelined in chunks. */
 int ffgpu_eval(ffgpu_tape*, const uint64_t* values, size_t n_points, uint64_t* out, uint32_t thread_id);
+/* Probes on a line, the way Reconstructor::queue_probes builds them (Reconstructor.hpp:2946-2960):
+ * point j has coordinates x_v = a[v] * t[j] + s[v] mod p (a[0] = 1 and a[i] = rand_zi[i-1], s = shift for the
+ * normal case; a[v] in {0,1}, s[v] = fixed value for the factor scan).  Only t crosses PCIe (8 bytes per probe
+ * instead of 8 * n_vars); the coordinates are formed on the GPU.  a, s: [n_vars] canonical residues, t: [n_points],
+ * out: [n_out][n_points], all HOST buffers.  Values are identical to ffgpu_eval on the expanded points. */
+int ffgpu_eval_line(ffgpu_tape*, const uint64_t* a, const uint64_t* s, const uint64_t* t, size_t n_points,
+                    uint64_t* out, uint32_t thread_id);
 /* DEVICE buffers on GPU `device_index` of the ctx, row strides in elements; launches on `stream`
  * (a cudaStream_t, NULL = default stream) and returns without synchronising. */
 int ffgpu_eval_device(ffgpu_tape*, int device_index, const uint64_t* d_values, size_t in_stride, size_t n_points,
@@ -119,7 +135,9 @@ int ffgpu_checksum(ffgpu_ctx*, int device_index, const uint64_t* d_out, size_t n
                    uint64_t p, uint64_t* d_sums, void* stream);
 /* device field arithmetic self test (tests only): r[i] = op(a[i], b[i]), HOST buffers.
  * op: 0 add 1 sub 2 mul 3 neg 4 inverse(Fermat) 5 pow(residue exponent) 6 inverse(block batched)
- *     7 pow(-(int)b) 8 canonical 9 1/(a*b) through the batched inverse */
+ *     7 pow(-(int)b) 8 canonical 9 1/(a*b) through the batched inverse
+ *     10 (a+b)*b 11 (a-b)*b 12 (a*b)^2-b 13 (-a)*b+a  (chains on un-canonicalised intermediates)
+ * a, b: any representatives below 2^63 + 2^32 (the interpreter's bounded lazy residues). */
 int ffgpu_field_ops(ffgpu_ctx*, int op, const uint64_t* a, const uint64_t* b, uint64_t* r, size_t n, uint64_t p);
 
 #ifdef __cplusplus

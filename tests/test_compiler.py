@@ -191,3 +191,40 @@ def test_synthetic_points_are_canonical_nonzero():
     b = ff.synthetic_points(3, 100, P0, first_point=100, total_points=200)
     full = ff.synthetic_points(3, 200, P0)
     assert np.array_equal(np.concatenate([a, b], axis=1), full)
+
+
+# ---- shared sub-expressions (hash-consed DAG, temp slots, co-evaluated sums) -----------------------------
+@pytest.mark.parametrize("temps", [0, 1, 2, 4, 8])
+def test_sharing_pass_keeps_every_value(oracle, temps):
+    from test_gpu_parity import _dag_expressions
+    rng = random.Random(99 + temps)
+    vars_ = ["x", "y", "z", "w1", "u"]
+    funs = _dag_expressions(rng, vars_, 120)
+    p = ff.primes()[3]
+    pts = ff.synthetic_points(5, 6, p, seed=temps)
+    pts[:, 1] = 0
+    pts[:, 2] = np.array([1, p - 1, 0, 2, 1], dtype=np.uint64)
+    want = oracle.parse(funs, vars_, p).eval(pts)
+    par = ff.GpuParser(None, funs, vars_, temps=temps)
+    par.set_prime(p)
+    assert 0 < par.n_temps <= (temps or 8)
+    assert par.cse_fallbacks == 0          # the compiler's self-check never had to drop the sharing
+    assert par.n_slots <= par.stack_depth + par.n_temps
+    assert np.array_equal(interp(par, pts, p), want)
+    plain = ff.GpuParser(None, funs, vars_, cse=False)
+    plain.set_prime(p)
+    assert plain.n_temps == 0 and plain.n_instr > par.n_instr
+    assert np.array_equal(interp(plain, pts, p), want)
+
+
+def test_f1_powers_are_computed_once():
+    from firefly_b200 import workloads as W
+    text, vars_ = W.benchmark("f1")
+    par = ff.GpuParser(None, [text], vars_)
+    tape = par.tape()
+    powu = int(np.sum(tape["op"] == ff.OPS.index("POWU")))
+    assert powu == 20                      # the reference's token list has 40 (numerator and denominator)
+    assert par.tape_work()["mm"] == 20 * 5 + 1 and par.tape_work()["inv"] == 1
+    assert par.work()["mm"] == 201         # the algorithmic count stays the reference's
+    plain = ff.GpuParser(None, [text], vars_, cse=False)
+    assert int(np.sum(plain.tape()["op"] == ff.OPS.index("POWU"))) == 40

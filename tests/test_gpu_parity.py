@@ -15,24 +15,37 @@ P0 = 9223372036854775783
 
 
 # ---- device field arithmetic against Python integers -------------------------------------------------
+BOUND = (1 << 63) + (1 << 32)      # the interpreter's value representation: any representative below this
+
+
 def _edge_values(p, rng, n):
-    edge = [0, 1, 2, 3, p - 1, p - 2, p, p + 1, 2 * p, 2 * p + 1, (1 << 64) - 1, (1 << 64) - 2, (1 << 63),
-            (1 << 63) - 1, (1 << 32), (1 << 32) - 1, 0xFFFFFFFF00000000, p >> 1, (p >> 1) + 1]
-    vals = edge + [rng.randrange(1 << 64) for _ in range(n)] + [rng.randrange(p) for _ in range(n)]
+    edge = [0, 1, 2, 3, p - 1, p - 2, p, p + 1, (1 << 63), (1 << 63) - 1, (1 << 63) + 1, BOUND - 1, BOUND - 2,
+            (1 << 63) + (1 << 31), (1 << 63) + (1 << 31) - 1, (1 << 63) + 0xFFFFFFFF, (1 << 32), (1 << 32) - 1,
+            0x7FFFFFFF00000000, 0x7FFFFFFFFFFFFFFF, 0x80000000FFFFFFFF, 0x00000000FFFFFFFF, 0x7FFFFFFF80000000,
+            p >> 1, (p >> 1) + 1, (1 << 62), (1 << 62) - 1]
+    vals = edge + [rng.randrange(BOUND) for _ in range(n)] + [rng.randrange(p) for _ in range(n)]
+    vals += [BOUND - 1 - rng.randrange(1 << 20) for _ in range(n // 4)] + [(1 << 63) - rng.randrange(1 << 20) for _ in range(n // 4)]
     return vals
 
 
 @pytest.mark.parametrize("pi", [0, 1, 150, 299])
 def test_field_ops_lazy_inputs(ctx, pi):
-    """add/sub/mul/neg/canon accept ANY 64-bit representative (lazy residues)."""
+    """add/sub/mul/neg/canon accept ANY representative below 2^63 + 2^32 (bounded lazy residues) and their
+    results stay below that bound (checked by chaining: op(op(a, b), b))."""
     p = ff.primes()[pi]
     rng = random.Random(pi)
     vals = _edge_values(p, rng, 2000)
-    a = np.array([rng.choice(vals) for _ in range(20000)], dtype=np.uint64)
-    b = np.array([rng.choice(vals) for _ in range(20000)], dtype=np.uint64)
+    a = np.array([rng.choice(vals) for _ in range(40000)], dtype=np.uint64)
+    b = np.array([rng.choice(vals) for _ in range(40000)], dtype=np.uint64)
+    # all edge x edge pairs first
+    ne = 27
+    a[: ne * ne] = np.repeat(np.array(vals[:ne], dtype=np.uint64), ne)
+    b[: ne * ne] = np.tile(np.array(vals[:ne], dtype=np.uint64), ne)
     ai, bi = [int(x) for x in a], [int(x) for x in b]
     for op, fn in [(0, lambda x, y: (x + y) % p), (1, lambda x, y: (x - y) % p), (2, lambda x, y: x * y % p),
-                   (3, lambda x, y: (-x) % p), (8, lambda x, y: x % p)]:
+                   (3, lambda x, y: (-x) % p), (8, lambda x, y: x % p),
+                   (10, lambda x, y: ((x + y) * y) % p), (11, lambda x, y: ((x - y) * y) % p),
+                   (12, lambda x, y: ((x * y) * (x * y) - y) % p), (13, lambda x, y: ((-x) * y + x) % p)]:
         got = ctx.field_ops(op, a, b, p)
         want = np.array([fn(x, y) for x, y in zip(ai, bi)], dtype=np.uint64)
         assert np.array_equal(got, want), f"op {op} prime {p}"
@@ -78,7 +91,7 @@ def test_gpu_matches_golden(ctx, name):
 # ---- oracle on seeded inputs, every launch shape --------------------------------------------------------
 @pytest.mark.parametrize("name", ["s_y_4_v", "edge_cases", "f4", "f1"])
 @pytest.mark.parametrize("k,threads", [(0, 0), (1, 128), (1, 256), (1, 512), (2, 128), (2, 256), (2, 512),
-                                       (4, 128), (4, 256), (4, 512)])
+                                       (4, 128), (4, 256), (4, 512), (8, 128), (8, 256), (8, 512)])
 def test_gpu_matches_oracle_all_shapes(ctx, oracle, name, k, threads):
     g = load_golden(name)
     p = ff.primes()[2]
@@ -140,6 +153,106 @@ def test_gpu_random_expressions_vs_oracle(ctx, oracle):
         pts[1, 5:40] = np.arange(35, dtype=np.uint64)             # small lane exponents
         assert np.array_equal(par.evaluate_pre(pts), op.eval(pts))
         par.close()
+
+
+def _dag_expressions(rng, vars_, n):
+    """expressions that repeat sub-expressions on purpose (numerator/denominator sharing sums, repeated
+    powers and products): what the compiler's sharing pass (temp slots, co-evaluated sums) feeds on"""
+    def power():
+        return f"{rng.choice(vars_)}^{rng.randint(2, 30)}"
+
+    def product():
+        return "*".join(rng.sample(vars_, rng.randint(2, len(vars_))))
+
+    out = []
+    for _ in range(n):
+        pool = [power() for _ in range(rng.randint(2, 6))] + [product() for _ in range(rng.randint(1, 3))]
+        pool += [f"({rng.choice(pool)}+{rng.randint(1, 99)})^{rng.randint(2, 9)}" for _ in range(2)]
+
+        def ssum(k):
+            terms = [rng.choice(pool) for _ in range(k)]
+            return terms[0] + "".join(rng.choice("+-") + t for t in terms[1:])
+
+        kind = rng.randrange(5)
+        if kind == 0:
+            e = f"({ssum(rng.randint(2, 8))})/({ssum(rng.randint(2, 8))})"
+        elif kind == 1:
+            e = f"({ssum(4)})*({ssum(4)})-({ssum(3)})*({rng.choice(pool)})"
+        elif kind == 2:
+            s1 = ssum(rng.randint(3, 6))
+            e = f"({s1})*({s1})+({s1})/({ssum(3)})"
+        elif kind == 3:
+            q = rng.choice(pool)
+            e = f"({q})+({q})^2+({q})^3-({q})*({ssum(2)})"
+        else:
+            e = f"(({ssum(5)})-({ssum(5)}))/(({ssum(5)})+({ssum(5)})*({rng.choice(pool)}))"
+        out.append(e)
+    return out
+
+
+@pytest.mark.parametrize("temps", [0, 1, 2, 3, 8])
+def test_shared_subexpressions_vs_oracle(ctx, oracle, temps):
+    rng = random.Random(5150 + temps)
+    vars_ = ["x", "y", "z", "w1", "u"]
+    funs = _dag_expressions(rng, vars_, 300)
+    for name in ("f1", "f2", "factors3", "factors5"):
+        text, v = W.benchmark(name)
+        if len(v) <= 5:
+            funs.append(text.replace("x1", "x").replace("x2", "y").replace("x3", "z").replace("x4", "w1").replace("x5", "u"))
+    p = ff.primes()[7]
+    op = oracle.parse(funs, vars_, p)
+    pts = ff.synthetic_points(5, 515, p, seed=temps)
+    pts[:, 3] = 0
+    pts[:, 4] = np.array([1, 1, p - 1, 2, 0], dtype=np.uint64)
+    want = op.eval(pts)
+    par = ff.GpuParser(ctx, funs, vars_, temps=temps)
+    par.set_prime(p)
+    assert par.n_temps > 0 and par.cse_fallbacks == 0       # the sharing pass found something and held up
+    assert np.array_equal(par.evaluate_pre(pts), want)
+    plain = ff.GpuParser(ctx, funs, vars_, cse=False)
+    plain.set_prime(p)
+    assert plain.n_temps == 0 and plain.n_instr > par.n_instr
+    assert np.array_equal(plain.evaluate_pre(pts), want)
+    par.close()
+    plain.close()
+
+
+@pytest.mark.parametrize("name", ["f1", "f3", "factors4", "s_y_4_v"])
+def test_eval_line_matches_expanded_points(ctx, oracle, name):
+    """ffgpu_eval_line builds x_v = a_v*t + s_v on the GPU (Reconstructor::queue_probes, :2946-2960): same values
+    as evaluating the host-expanded points, and as the oracle."""
+    g = load_golden(name)
+    rng = random.Random(hash(name) & 0xffff)
+    for p in (P0, ff.primes()[200]):
+        par = ff.GpuParser(ctx, g["functions"], g["vars"])
+        par.set_prime(p)
+        par.set_chunk(1 << 12)                  # several pipelined chunks
+        nv = par.n_vars
+        op = oracle.parse(g["functions"], g["vars"], p)
+        for n in (1, 2, 7, 4096, 10001):
+            a = np.array([1] + [rng.randrange(p) for _ in range(nv - 1)], dtype=np.uint64)
+            s = np.array([rng.randrange(p) for _ in range(nv)], dtype=np.uint64)
+            if n == 7:                          # factor-scan shape: a in {0, 1}, fixed values elsewhere
+                a = np.array([rng.randrange(2) for _ in range(nv)], dtype=np.uint64)
+                s = np.where(a == 1, 0, s).astype(np.uint64)
+            t = ff.synthetic_points(1, n, p, seed=n)[0]
+            t[0] = 0
+            if n > 2:
+                t[1], t[2] = p - 1, 1
+            pts = np.array([[(int(a[v]) * int(tj) + int(s[v])) % p for tj in t] for v in range(nv)], dtype=np.uint64)
+            want = op.eval(pts)
+            assert np.array_equal(par.evaluate_pre(pts), want)
+            assert np.array_equal(par.evaluate_line(a, s, t), want), (name, p, n)
+        par.close()
+
+
+def test_eval_line_rejects_bad_parameters(ctx):
+    par = ff.GpuParser(ctx, ["x+y"], ["x", "y"])
+    par.set_prime(P0)
+    with pytest.raises(ff.FFGpuError, match="below the prime"):
+        par.evaluate_line([1, P0], [0, 0], [1, 2, 3])
+    with pytest.raises(ValueError):
+        par.evaluate_line([1], [0, 0], [1, 2, 3])
 
 
 def test_check_is_equal_and_prime_change(ctx, oracle):
