@@ -84,6 +84,15 @@ def _load() -> C.CDLL:
             C.c_int,
             [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p],
         ),
+        "ffgpu_queue_create": (C.c_void_p, [C.c_void_p, C.c_size_t]),
+        "ffgpu_queue_destroy": (None, [C.c_void_p]),
+        "ffgpu_queue_push": (C.c_uint64, [C.c_void_p, C.c_void_p]),
+        "ffgpu_queue_push_many": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_size_t]),
+        "ffgpu_queue_push_line": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+        "ffgpu_queue_pop": (C.c_long, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+        "ffgpu_queue_pending": (C.c_size_t, [C.c_void_p]),
+        "ffgpu_queue_stats": (None, [C.c_void_p, u64p]),
+        "ffgpu_queue_error": (C.c_char_p, [C.c_void_p]),
         "ffgpu_host_alloc": (C.c_void_p, [C.c_size_t]),
         "ffgpu_host_free": (None, [C.c_void_p]),
         "ffgpu_set_launch": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
@@ -113,6 +122,8 @@ EXPORTS = [
     "ffgpu_compile_file", "ffgpu_tape_destroy", "ffgpu_n_vars", "ffgpu_n_functions", "ffgpu_n_out", "ffgpu_n_instr",
     "ffgpu_stack_depth", "ffgpu_n_temps", "ffgpu_n_slots", "ffgpu_cse_fallbacks", "ffgpu_rpn", "ffgpu_get_tape", "ffgpu_work", "ffgpu_tape_work", "ffgpu_set_prime", "ffgpu_get_prime",
     "ffgpu_n_primes", "ffgpu_prime", "ffgpu_eval", "ffgpu_eval_line", "ffgpu_eval_device", "ffgpu_host_alloc", "ffgpu_host_free",
+    "ffgpu_queue_create", "ffgpu_queue_destroy", "ffgpu_queue_push", "ffgpu_queue_push_many", "ffgpu_queue_push_line",
+    "ffgpu_queue_pop", "ffgpu_queue_pending", "ffgpu_queue_stats", "ffgpu_queue_error",
     "ffgpu_set_launch", "ffgpu_set_chunk", "ffgpu_launch_count", "ffgpu_fill_points", "ffgpu_checksum",
     "ffgpu_field_ops",
 ]
@@ -306,6 +317,61 @@ class GpuParser:
 
     def set_chunk(self, points: int = 0):
         lib.ffgpu_set_chunk(self.h, points)
+
+
+class ProbeQueue:
+    """requested_probes / computed_probes around a GpuParser with one GPU-feeding consumer
+    (Reconstructor.hpp:245-246, 2962-2971, 2996-3012, 3326-3477; see include/ffgpu.h, probe queue)."""
+
+    def __init__(self, parser: GpuParser, max_batch: int = 0):
+        self.parser = parser
+        self.h = lib.ffgpu_queue_create(parser.h, max_batch)
+        if not self.h:
+            raise FFGpuError("could not create the probe queue")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.ffgpu_queue_destroy(self.h)
+            self.h = None
+
+    def push(self, values) -> int:
+        v = np.ascontiguousarray(values, dtype=np.uint64)
+        if v.shape != (self.parser.n_vars,):
+            raise ValueError(f"expected {self.parser.n_vars} values")
+        return lib.ffgpu_queue_push(self.h, v.ctypes.data)
+
+    def push_many(self, points) -> int:
+        """points: [n][n_vars] (point-major, like the reference's queue entries); returns the first index"""
+        v = np.ascontiguousarray(points, dtype=np.uint64)
+        if v.ndim != 2 or v.shape[1] != self.parser.n_vars:
+            raise ValueError(f"expected [n][{self.parser.n_vars}] values")
+        return lib.ffgpu_queue_push_many(self.h, v.ctypes.data, v.shape[0])
+
+    def push_line(self, a, s, t) -> int:
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        s = np.ascontiguousarray(s, dtype=np.uint64)
+        t = np.ascontiguousarray(t, dtype=np.uint64)
+        if a.shape != (self.parser.n_vars,) or s.shape != (self.parser.n_vars,):
+            raise ValueError(f"a and s must have {self.parser.n_vars} entries")
+        return lib.ffgpu_queue_push_line(self.h, a.ctypes.data, s.ctypes.data, t.ctypes.data, t.shape[0])
+
+    def pop(self, cap: int = 4096, wait: bool = True):
+        """-> (indices[k], values[n_out][k]) of up to cap finished probes (k = 0: nothing outstanding)"""
+        idx = np.empty(cap, dtype=np.uint64)
+        out = np.empty((self.parser.n_out, cap), dtype=np.uint64)
+        k = lib.ffgpu_queue_pop(self.h, idx.ctypes.data, out.ctypes.data, cap, 1 if wait else 0)
+        if k < 0:
+            raise FFGpuError((lib.ffgpu_queue_error(self.h) or b"").decode())
+        return idx[:k].copy(), out[:, :k].copy()
+
+    @property
+    def pending(self) -> int:
+        return lib.ffgpu_queue_pending(self.h)
+
+    def stats(self) -> dict:
+        s = (C.c_uint64 * 3)()
+        lib.ffgpu_queue_stats(self.h, s)
+        return {"batches": s[0], "probes": s[1], "largest_batch": s[2]}
 
 
 def launch_count() -> int:

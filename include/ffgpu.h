@@ -119,6 +119,33 @@ int ffgpu_eval_device(ffgpu_tape*, int device_index, const uint64_t* d_values, s
 void* ffgpu_host_alloc(size_t bytes);
 void ffgpu_host_free(void*);
 
+/* ---- probe queue ---------------------------------------------------------------------------
+ * The pair of queues Reconstructor keeps around its black box -- requested_probes (index, values) filled by
+ * queue_probes, computed_probes drained by get_probe (Reconstructor.hpp:245-246, 2962-2971, 2996-3012) -- with
+ * ONE consumer in place of the thr_n get_job threads (:3326-3477): a worker thread that takes everything
+ * waiting (up to max_batch probes, 0 = 65536) and evaluates it in one launch.  Where the reference's bunch
+ * policy splits the backlog over threads in bunches of at most 128 (compute_bunch_size, utils.cpp:305-330), this
+ * one lets batches grow with the backlog.  Every probe gets the next running index (Reconstructor's `ind`);
+ * results come back tagged with it.  Thread safe.  Drain the queue before ffgpu_set_prime (as Reconstructor
+ * does with tp.kill_all() before a prime change, :2403). */
+typedef struct ffgpu_queue ffgpu_queue;
+ffgpu_queue* ffgpu_queue_create(ffgpu_tape*, size_t max_batch);
+void ffgpu_queue_destroy(ffgpu_queue*);
+/* queue one point (values[n_vars], residues in [0,p)); returns its index */
+uint64_t ffgpu_queue_push(ffgpu_queue*, const uint64_t* values);
+/* queue n points, point-major values[n][n_vars] (the layout of requested_probes); returns the first index */
+uint64_t ffgpu_queue_push_many(ffgpu_queue*, const uint64_t* values, size_t n);
+/* queue n points on the line x_v = a[v]*t[j] + s[v] (what queue_probes generates, :2946-2960): only t is
+ * shipped to the GPU; returns the first index */
+uint64_t ffgpu_queue_push_line(ffgpu_queue*, const uint64_t* a, const uint64_t* s, const uint64_t* t, size_t n);
+/* fetch up to cap finished probes: indices[i] and out[f * cap + i] (function-major, row stride cap).  wait != 0
+ * blocks until at least one probe is ready or nothing is outstanding.  Returns the count, -1 after an
+ * evaluation error (ffgpu_queue_error). */
+long ffgpu_queue_pop(ffgpu_queue*, uint64_t* indices, uint64_t* out, size_t cap, int wait);
+size_t ffgpu_queue_pending(ffgpu_queue*);                 /* queued + being evaluated */
+void ffgpu_queue_stats(ffgpu_queue*, uint64_t s[3]);      /* launches' worth of batches, probes done, largest batch */
+const char* ffgpu_queue_error(ffgpu_queue*);
+
 /* ---- tuning / measurement ----------------------------------------------------------------- */
 /* probes per thread (1, 2, 4, 8; 0 = automatic) and threads per block (128, 256, 512; 0 = automatic) */
 int ffgpu_set_launch(ffgpu_tape*, int probes_per_thread, int threads_per_block);

@@ -228,3 +228,16 @@ def test_f1_powers_are_computed_once():
     assert par.work()["mm"] == 201         # the algorithmic count stays the reference's
     plain = ff.GpuParser(None, [text], vars_, cse=False)
     assert int(np.sum(plain.tape()["op"] == ff.OPS.index("POWU"))) == 40
+
+
+def test_probe_queue_without_a_gpu_fails_loudly():
+    """the queue's consumer evaluates through ffgpu_eval: on a host-only handle it must surface the error,
+    never compute on the CPU"""
+    par = ff.GpuParser(None, ["x*y+1"], ["x", "y"])
+    par.set_prime(P0)
+    q = ff.ProbeQueue(par)
+    assert q.push([3, 4]) == 0 and q.push([5, 6]) == 1
+    assert q.push_many(np.array([[1, 2], [3, 4], [5, 6]], dtype=np.uint64)) == 2
+    with pytest.raises(ff.FFGpuError, match="no GPU|no CPU path|pinned staging"):
+        q.pop()
+    q.close()

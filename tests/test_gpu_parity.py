@@ -359,3 +359,71 @@ def test_empty_batch_and_missing_prime(ctx):
     n0 = ff.launch_count()
     par.evaluate_pre(np.array([[5]], dtype=np.uint64))
     assert ff.launch_count() == n0 + 1
+
+
+# ---- the probe queue (requested_probes / computed_probes with one GPU-feeding consumer) ---------------------
+def test_probe_queue_matches_oracle_by_index(ctx, oracle):
+    g = load_golden("s_y_4_v")
+    p = ff.primes()[5]
+    par = ff.GpuParser(ctx, g["functions"], g["vars"])
+    par.set_prime(p)
+    op = oracle.parse(g["functions"], g["vars"], p)
+    q = ff.ProbeQueue(par, max_batch=512)
+    n_threads, per_thread = 6, 300
+    pts = ff.synthetic_points(4, n_threads * per_thread + 1000 + 777, p, seed=8)
+    pts[:, 5] = 0
+    owner = {}                                  # index -> column of pts
+    lock = threading.Lock()
+
+    def producer(tid):
+        for i in range(per_thread):
+            col = tid * per_thread + i
+            idx = q.push(pts[:, col])
+            with lock:
+                owner[idx] = col
+
+    ts = [threading.Thread(target=producer, args=(t,)) for t in range(n_threads)]
+    [t.start() for t in ts]
+    # a block of points at once (point-major, the reference's queue layout) while the producers run
+    base = n_threads * per_thread
+    first = q.push_many(np.ascontiguousarray(pts[:, base:base + 1000].T))
+    with lock:
+        for i in range(1000):
+            owner[first + i] = base + i
+    [t.join() for t in ts]
+    # and a line batch: only t travels
+    rng = random.Random(3)
+    a = np.array([1] + [rng.randrange(p) for _ in range(3)], dtype=np.uint64)
+    s = np.array([rng.randrange(p) for _ in range(4)], dtype=np.uint64)
+    tvals = pts[0, base + 1000:base + 1777].copy()
+    first_line = q.push_line(a, s, tvals)
+    line_pts = np.array([[(int(a[v]) * int(tj) + int(s[v])) % p for tj in tvals] for v in range(4)], dtype=np.uint64)
+    total = n_threads * per_thread + 1000 + 777
+    got = {}
+    while len(got) < total:
+        idx, vals = q.pop(cap=257)
+        assert len(idx) > 0, "queue ran dry before all probes came back"
+        for k, i in enumerate(idx):
+            assert int(i) not in got
+            got[int(i)] = vals[:, k]
+    assert q.pending == 0 and len(q.pop(wait=False)[0]) == 0
+    assert sorted(got) == list(range(total))    # every index exactly once
+    want = op.eval(pts[:, :base + 1000])
+    for i, col in owner.items():
+        assert np.array_equal(got[i], want[:, col]), (i, col)
+    want_line = op.eval(line_pts)
+    for k in range(777):
+        assert np.array_equal(got[first_line + k], want_line[:, k])
+    st = q.stats()
+    assert st["probes"] == total and st["largest_batch"] <= 1000 and st["batches"] < total   # batching happened
+    q.close()
+    par.close()
+
+
+def test_probe_queue_reports_evaluation_errors(ctx):
+    par = ff.GpuParser(ctx, ["x+y"], ["x", "y"])      # no prime set: every evaluation fails
+    q = ff.ProbeQueue(par)
+    q.push([1, 2])
+    with pytest.raises(ff.FFGpuError, match="set_prime"):
+        q.pop()
+    q.close()
