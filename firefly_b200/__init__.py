@@ -33,11 +33,13 @@ INSTR_DTYPE = np.dtype(
 )
 # tape.hpp
 OPS = ["HALT", "LOAD", "ADD", "SUB", "MUL", "SQR", "NEG", "INV", "POWU", "NPOWU", "POWL", "NPOWL", "STORE", "MULADD",
-       "SAVE", "ACCUM"]
+       "SAVE", "ACCUM", "TERM", "ACCUM2", "ADDVARS", "MULVARS"]
 SRCS = ["NONE", "POP", "VAR", "NEGVAR", "CONST", "TMP"]
-F_PUSH, F_SWAP, F_NEGR, F_INIT = 1, 2, 4, 8
+F_PUSH, F_SWAP, F_NEGR, F_INIT, F_SWAP2, F_INIT2, F_CMUL = 1, 2, 4, 8, 16, 32, 128
+TM_LOAD, TM_ADD, TM_SUB, TM_RSUB, TM_MUL = 0, 1, 2, 3, 4
 CHECK_IS_EQUAL = 1
 NO_CSE = 2
+NO_FUSE = 4
 
 
 class FFGpuError(RuntimeError):
@@ -184,10 +186,10 @@ class GpuParser:
 
     def __init__(self, ctx: Optional[Context], functions=None, vars: Sequence[str] = (), check_is_equal: bool = False,
                  *, file: Optional[str] = None, text: Optional[str] = None, cse: bool = True,
-                 temps: int = 0):
+                 temps: int = 0, fuse: bool = True):
         self.ctx = ctx
         ch = ctx.h if ctx is not None else None
-        flags = (CHECK_IS_EQUAL if check_is_equal else 0) | (0 if cse else NO_CSE) | ((temps & 15) << 8)
+        flags = (CHECK_IS_EQUAL if check_is_equal else 0) | (0 if cse else NO_CSE) | (0 if fuse else NO_FUSE) | ((temps & 15) << 8)
         v = _strs(vars)
         if file is not None:
             self.h = lib.ffgpu_compile_file(ch, file.encode(), v, len(vars), flags)

@@ -263,6 +263,7 @@ ffgpu_tape* ffgpu_compile(ffgpu_ctx* ctx, const char* const* functions, size_t n
   std::unique_ptr<ffgpu_tape> t(new ffgpu_tape);
   std::string err;
   t->col.enable_cse = !(flags & FFGPU_NO_CSE);
+  t->col.enable_fuse = !(flags & FFGPU_NO_FUSE);
   t->col.temp_budget = (int)((flags >> FFGPU_TEMPS_SHIFT) & 15u);
   const bool ok = t->col.compile_strings(to_vec(functions, n_functions), to_vec(vars, n_vars),
                                          (flags & FFGPU_CHECK_IS_EQUAL) != 0, err);
@@ -274,6 +275,7 @@ ffgpu_tape* ffgpu_compile_text(ffgpu_ctx* ctx, const char* text, const char* con
   std::unique_ptr<ffgpu_tape> t(new ffgpu_tape);
   std::string err;
   t->col.enable_cse = !(flags & FFGPU_NO_CSE);
+  t->col.enable_fuse = !(flags & FFGPU_NO_FUSE);
   t->col.temp_budget = (int)((flags >> FFGPU_TEMPS_SHIFT) & 15u);
   const bool ok = t->col.compile_text(text ? text : "", to_vec(vars, n_vars), (flags & FFGPU_CHECK_IS_EQUAL) != 0, err);
   return finish_compile(ctx, std::move(t), ok, err);

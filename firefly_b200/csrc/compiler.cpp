@@ -599,11 +599,11 @@ struct FnEmitter {
     int32_t other;
     int32_t aux;
   };
-  enum { GEN, AFTER, APPLY_POP, APPLY_DIRECT, INVERT, POW_CONST, MUL_INVCONST, SQUARE, PRE, ACCUM, ADOPT };
+  enum { GEN, AFTER, APPLY_POP, APPLY_DIRECT, INVERT, POW_CONST, MUL_INVCONST, SQUARE, PRE, ACCUM, ADOPT, ADDPOP };
   std::vector<Item> work;
   // accumulate lists of co-evaluated sums: for ACCUM items
   struct Acc { int slot; bool minus; bool init; };
-  struct AccList { std::vector<Acc> acc; bool post_consume = false; };
+  struct AccList { std::vector<Acc> acc; bool post_consume = false; bool emit = true; };
   std::vector<AccList> acc_lists;
 
   void apply(const Node& n, bool acc_is_right, bool from_stack, int32_t other) {
@@ -666,19 +666,54 @@ struct FnEmitter {
     // reverse execution order: the two ADOPTs run last
     work.push_back(Item{ADOPT, rep[r], false, false, -1, sr});
     work.push_back(Item{ADOPT, rep[l], false, false, -1, sl});
+    // Terms are grouped by HOW the two sums use them -- (+,+), (+,-), only the first sum, ... -- and every
+    // group is summed in the accumulator like an ordinary chain before it is added to (or subtracted from)
+    // the sums' temp slots: one pair of ACCUMs per group instead of per term.  f1: numerator = A + U,
+    // denominator = A - U with A the shared first ten powers and U the sum of the other ten.  Addition in
+    // Z_p is associative and commutative, the sums keep their values.
+    typedef std::vector<std::pair<int, bool>> Pattern;
+    std::vector<Pattern> patterns;
+    std::vector<std::vector<size_t>> members;
+    for (size_t k = 0; k < plan.order.size(); ++k) {
+      Pattern pat = plan.uses[k];
+      std::sort(pat.begin(), pat.end());
+      bool simple = true;                       // a term used twice by the same sum stays on its own
+      for (size_t q = 1; q < pat.size(); ++q) simple &= pat[q].first != pat[q - 1].first;
+      size_t g = patterns.size();
+      if (simple)
+        for (size_t q = 0; q < patterns.size(); ++q)
+          if (patterns[q] == pat && !members[q].empty() && plan.uses[members[q][0]].size() == pat.size()) { g = q; break; }
+      if (g == patterns.size() || !simple) {
+        g = patterns.size();
+        patterns.push_back(simple ? pat : Pattern{{-1 - (int)k, false}});   // unique key for the odd ones
+        members.emplace_back();
+      }
+      members[g].push_back(k);
+    }
     bool init[2] = {true, true};
     std::vector<Item> fwd;
-    for (size_t k = 0; k < plan.order.size(); ++k) {
-      AccList lst;
-      for (auto& u : plan.uses[k]) {
+    bool first_overall = true;
+    for (size_t g = 0; g < members.size(); ++g) {
+      for (size_t m = 0; m < members[g].size(); ++m) {
+        const size_t k = members[g][m];
+        AccList uses_only;                       // bookkeeping of this term's uses (nothing emitted)
+        uses_only.emit = false;
+        uses_only.acc.resize(plan.uses[k].size());
+        acc_lists.push_back(std::move(uses_only));
+        const int32_t li = (int32_t)acc_lists.size() - 1;
+        fwd.push_back(Item{PRE, plan.order[k], false, false, -1, li});
+        fwd.push_back(Item{GEN, plan.order[k], first_overall ? push : m > 0, false, -1, 0});
+        fwd.push_back(Item{ACCUM, plan.order[k], false, false, -1, li});
+        if (m > 0) fwd.push_back(Item{ADDPOP, -1, false, false, -1, 0});
+        first_overall = false;
+      }
+      AccList lst;                               // the group's total goes to the sums
+      for (auto& u : plan.uses[members[g][0]]) {
         lst.acc.push_back(Acc{u.first == 0 ? sl : sr, u.second, init[u.first]});
         init[u.first] = false;
       }
       acc_lists.push_back(std::move(lst));
-      const int32_t li = (int32_t)acc_lists.size() - 1;
-      fwd.push_back(Item{PRE, plan.order[k], false, false, -1, li});
-      fwd.push_back(Item{GEN, plan.order[k], push && k == 0, false, -1, 0});
-      fwd.push_back(Item{ACCUM, plan.order[k], false, false, -1, li});
+      fwd.push_back(Item{ACCUM, -1, false, false, -1, (int32_t)acc_lists.size() - 1});
     }
     for (size_t k = fwd.size(); k-- > 0;) work.push_back(fwd[k]);
   }
@@ -735,9 +770,17 @@ struct FnEmitter {
           else remaining[t] -= extra;
           continue;
         }
+        case ADDPOP: {
+          Instr ins = mk(OP_ADD);
+          ins.src = SRC_POP;
+          put(ins);
+          --depth;
+          continue;
+        }
         case ACCUM: {
           if (acc_lists[it.aux].post_consume)
             for (size_t k = 1; k < acc_lists[it.aux].acc.size(); ++k) consume(it.node);
+          if (!acc_lists[it.aux].emit) continue;
           for (const Acc& a : acc_lists[it.aux].acc) {
             Instr ins = mk(OP_ACCUM, (a.minus ? F_SWAP : 0) | (a.init ? F_INIT : 0));
             ins.arg = (uint32_t)a.slot;
@@ -879,7 +922,7 @@ bool Collection::check_function(uint32_t fn, uint64_t p, const uint64_t* point) 
   for (uint32_t pc = fn_start[fn]; pc < fn_start[fn + 1]; ++pc) {
     const Instr& in = tape[pc];
     uint64_t b = 0;
-    switch (in.src) {
+    switch (in.op >= OP_TERM ? (uint8_t)SRC_NONE : in.src) {   // the fused forms decode their own operands
       case SRC_POP:
         if (stack.empty()) return false;
         b = stack.back();
@@ -931,6 +974,45 @@ bool Collection::check_function(uint32_t fn, uint64_t p, const uint64_t* point) 
         if (acc != want) return false;
         stored = true;
         break;
+      case OP_TERM: {
+        const uint8_t mode = (in.flags >> TM_SHIFT) & 7;
+        uint64_t t = ffhost::pow_ff(point[in.arg & 0xffff] % p, in.arg >> 16, p);
+        if (in.flags & F_CMUL) t = ffhost::mul(t, in.imm, p);
+        if (mode == TM_LOAD) {
+          if (in.flags & F_PUSH) stack.push_back(acc);
+          acc = t;
+        } else if (mode == TM_ADD) acc = ffhost::add(acc, t, p);
+        else if (mode == TM_SUB) acc = ffhost::sub(acc, t, p);
+        else if (mode == TM_RSUB) acc = ffhost::sub(t, acc, p);
+        else if (mode == TM_MUL) acc = ffhost::mul(acc, t, p);
+        else return false;
+        continue;                                  // the F_* bits above are not the generic flags
+      }
+      case OP_ACCUM2: {
+        const uint32_t sa = in.arg & 0xff, sb = (in.arg >> 8) & 0xff;
+        if (sa >= 16 || sb >= 16) return false;
+        const uint64_t va = (in.flags & F_SWAP) ? ffhost::neg(acc, p) : acc;
+        const uint64_t vb = (in.flags & F_SWAP2) ? ffhost::neg(acc, p) : acc;
+        if (in.flags & F_INIT) temps[sa] = va;
+        else if (!temp_set[sa]) return false;
+        else temps[sa] = ffhost::add(temps[sa], va, p);
+        temp_set[sa] = true;
+        if (in.flags & F_INIT2) temps[sb] = vb;
+        else if (!temp_set[sb]) return false;
+        else temps[sb] = ffhost::add(temps[sb], vb, p);
+        temp_set[sb] = true;
+        continue;
+      }
+      case OP_ADDVARS:
+      case OP_MULVARS: {
+        const uint32_t cnt = in.arg & 0xff, signs = in.arg >> 8;
+        for (uint32_t k = 0; k < cnt; ++k) {
+          const uint64_t v = point[(in.imm >> (8 * k)) & 0xff] % p;
+          if (in.op == OP_MULVARS) acc = ffhost::mul(acc, v, p);
+          else acc = ((signs >> k) & 1) ? ffhost::sub(acc, v, p) : ffhost::add(acc, v, p);
+        }
+        continue;
+      }
       default: return false;
     }
     if (in.flags & F_NEGR) acc = ffhost::neg(acc, p);
@@ -1007,6 +1089,7 @@ bool Collection::finish(std::string& err) {
     }
     fn_start.push_back((uint32_t)tape.size());
     peephole();
+    if (enable_fuse) fuse();
     // Translation check of every function at one pseudo-random point: the tape must reproduce the value of
     // the expression tree.  A function that fails is re-emitted as a plain tree (no sharing) on the second
     // pass; if that fails too the compilation is refused -- never a wrong probe value.
@@ -1053,9 +1136,18 @@ bool Collection::finish(std::string& err) {
           break;
         }
         case OP_POWL: case OP_NPOWL: executed.mm += 94; break;
+        case OP_TERM: {
+          const uint8_t mode = (in.flags >> TM_SHIFT) & 7;
+          executed.mm += chain(in.arg >> 16) + ((in.flags & F_CMUL) ? 1 : 0) + (mode == TM_MUL ? 1 : 0);
+          if (mode == TM_ADD || mode == TM_SUB || mode == TM_RSUB) ++executed.ma;
+          break;
+        }
+        case OP_ACCUM2: executed.ma += 2; break;
+        case OP_ADDVARS: executed.ma += in.arg & 0xff; executed.max_rpn_depth += (in.arg & 0xff) - 1; break;
+        case OP_MULVARS: executed.mm += in.arg & 0xff; executed.max_rpn_depth += (in.arg & 0xff) - 1; break;
         default: break;
       }
-      if (in.flags & F_NEGR) ++executed.ma;
+      if (in.op < OP_TERM && (in.flags & F_NEGR)) ++executed.ma;
     }
   }
   // chunk tables for C = 1, 2, 4, ... while a chunk still holds a function
@@ -1137,6 +1229,129 @@ void Collection::peephole() {
     }
     in.fast = fx;
   }
+}
+
+// Fusion of frequent instruction runs into one instruction each (one dispatch of the interpreter instead
+// of two to four; the term forms also keep the old ACC out of the explicit spill protocol).  Runs never cross
+// a function boundary (every function ends in a STORE, which is never part of a run).  Purely a re-encoding:
+// the operations and their order are unchanged.
+void Collection::fuse() {
+  const size_t n = tape.size();
+  std::vector<int32_t> patch_of(n, -1);
+  for (size_t i = 0; i < patches.size(); ++i) patch_of[patches[i].instr] = (int32_t)i;
+  std::vector<Instr> out;
+  out.reserve(n);
+  std::vector<uint32_t> new_index(n + 1, 0);
+  std::vector<char> patch_dead(patches.size(), 0);
+
+  // value of a literal exponent if it is the same small number for every prime
+  auto small_literal = [&](int32_t pi, uint32_t& e) -> bool {
+    if (pi < 0) return false;
+    const ConstPatch& cp = patches[pi];
+    if (cp.inverse || cp.negate) return false;
+    const Function& f = functions[cp.fn];
+    const Node& nd = f.nodes[cp.node];
+    if (nd.kind != N_NUM) return false;
+    const std::string& t = f.literals[nd.lit].text;
+    if (t.empty() || t.size() > 6) return false;
+    for (char ch : t)
+      if (ch < '0' || ch > '9') return false;
+    e = (uint32_t)leading_digits(t, 0);
+    return e >= 1 && e < 65536;
+  };
+  auto plain = [](const Instr& in, uint8_t op, uint8_t src) { return in.op == op && in.src == src && in.flags == 0; };
+
+  size_t i = 0;
+  while (i < n) {
+    const Instr& a = tape[i];
+    const size_t first = i;
+    uint32_t e = 0;
+    // ---- LOAD.VAR[.P], POWU e, [MUL.CONST], [ADD/SUB/MUL.POP]  ->  TERM
+    if (a.op == OP_LOAD && a.src == SRC_VAR && (a.flags & ~F_PUSH) == 0 && a.arg < 65536 && i + 1 < n &&
+        plain(tape[i + 1], OP_POWU, SRC_CONST) && small_literal(patch_of[i + 1], e)) {
+      Instr t{};
+      t.op = OP_TERM;
+      t.src = SRC_VAR;
+      t.arg = a.arg | (e << 16);
+      t.flags = a.flags & F_PUSH;
+      t.fast = FX_TERM;
+      patch_dead[patch_of[i + 1]] = 1;                       // the exponent now lives in arg
+      size_t j = i + 2;
+      int32_t moved_patch = -1;
+      if (j < n && plain(tape[j], OP_MUL, SRC_CONST) && patch_of[j] >= 0) {
+        t.flags |= F_CMUL;
+        moved_patch = patch_of[j];
+        ++j;
+      }
+      if ((t.flags & F_PUSH) && j < n && tape[j].src == SRC_POP && (tape[j].flags & ~F_SWAP) == 0 &&
+          (tape[j].op == OP_ADD || tape[j].op == OP_SUB || tape[j].op == OP_MUL)) {
+        // ACC holds the term T, the popped value is the old accumulator A
+        uint8_t mode = TM_ADD;
+        if (tape[j].op == OP_MUL) mode = TM_MUL;
+        else if (tape[j].op == OP_SUB) mode = (tape[j].flags & F_SWAP) ? TM_SUB : TM_RSUB;   // swap: A - T; else T - A
+        t.flags = (uint8_t)((t.flags & ~F_PUSH) | (mode << TM_SHIFT));
+        ++j;
+      }
+      for (size_t k = first; k < j; ++k) new_index[k] = (uint32_t)out.size();
+      if (moved_patch >= 0) patches[moved_patch].instr = (uint32_t)out.size();
+      out.push_back(t);
+      i = j;
+      continue;
+    }
+    // ---- ACCUM, ACCUM (two sums fed by the same term)  ->  ACCUM2
+    if (a.op == OP_ACCUM && i + 1 < n && tape[i + 1].op == OP_ACCUM && a.arg < 256 && tape[i + 1].arg < 256 &&
+        a.arg != tape[i + 1].arg && (a.flags & ~(F_SWAP | F_INIT)) == 0 && (tape[i + 1].flags & ~(F_SWAP | F_INIT)) == 0) {
+      const Instr& b = tape[i + 1];
+      Instr t{};
+      t.op = OP_ACCUM2;
+      t.arg = a.arg | (b.arg << 8);
+      t.flags = (uint8_t)((a.flags & (F_SWAP | F_INIT)) | ((b.flags & F_SWAP) ? F_SWAP2 : 0) | ((b.flags & F_INIT) ? F_INIT2 : 0));
+      t.fast = FX_ACCUM2;
+      new_index[i] = new_index[i + 1] = (uint32_t)out.size();
+      out.push_back(t);
+      i += 2;
+      continue;
+    }
+    // ---- runs of ADD.VAR / SUB.VAR  ->  ADDVARS;  runs of MUL.VAR  ->  MULVARS
+    auto addlike = [&](const Instr& in) { return (in.op == OP_ADD || in.op == OP_SUB) && in.src == SRC_VAR && in.flags == 0 && in.arg < 256; };
+    auto mullike = [&](const Instr& in) { return in.op == OP_MUL && in.src == SRC_VAR && in.flags == 0 && in.arg < 256; };
+    const bool is_add = addlike(a), is_mul = mullike(a);
+    if (is_add || is_mul) {
+      size_t j = i;
+      uint64_t ids = 0;
+      uint32_t signs = 0, cnt = 0;
+      while (j < n && cnt < 8 && (is_add ? addlike(tape[j]) : mullike(tape[j]))) {
+        ids |= (uint64_t)tape[j].arg << (8 * cnt);
+        if (tape[j].op == OP_SUB) signs |= 1u << cnt;
+        ++cnt;
+        ++j;
+      }
+      if (cnt >= 2) {
+        Instr t{};
+        t.op = is_add ? OP_ADDVARS : OP_MULVARS;
+        t.src = SRC_VAR;
+        t.arg = cnt | (signs << 8);
+        t.imm = ids;
+        t.fast = is_add ? FX_ADDVARS : FX_MULVARS;
+        for (size_t k = i; k < j; ++k) new_index[k] = (uint32_t)out.size();
+        out.push_back(t);
+        i = j;
+        continue;
+      }
+    }
+    new_index[i] = (uint32_t)out.size();
+    if (patch_of[i] >= 0) patches[patch_of[i]].instr = (uint32_t)out.size();
+    out.push_back(a);
+    ++i;
+  }
+  new_index[n] = (uint32_t)out.size();
+  for (uint32_t& s0 : fn_start) s0 = new_index[s0];
+  std::vector<ConstPatch> kept;
+  kept.reserve(patches.size());
+  for (size_t k = 0; k < patches.size(); ++k)
+    if (!patch_dead[k]) kept.push_back(patches[k]);
+  patches.swap(kept);
+  tape.swap(out);
 }
 
 static void init_vars(Collection& c, const std::vector<std::string>& vars, bool chk) {

@@ -95,6 +95,7 @@ struct Collection {
   uint32_t n_temps = 0;                       // temp slots (shared sub-expressions, co-evaluated sums)
   uint32_t n_slots = 0;                       // shared-memory slots per probe: max over functions of spill + temps
                                               // (spill slots count up from 0, temp slots down from n_slots - 1)
+  bool enable_fuse = true;                    // fuse frequent instruction runs (TERM, ACCUM2, ADDVARS, MULVARS)
   bool enable_cse = true;                     // share structurally equal sub-expressions
   uint32_t cse_fallbacks = 0;                 // functions emitted without sharing after a failed self-check
   int temp_budget = 0;                        // temp slots per function (0: automatic, see FnEmitter)
@@ -127,6 +128,7 @@ struct Collection {
   std::vector<uint8_t> no_cse_fn_;
   void count_work(const Function& f);
   void peephole();
+  void fuse();
   bool finish(std::string& err);
   // fingerprints for duplicate detection
   std::vector<uint64_t> chk_pts1_, chk_pts2_;

@@ -120,6 +120,34 @@ __device__ __forceinline__ void pow_uniform(R (&a)[K], u64 e, const Field& F) {
   }
 }
 
+// r = base^e for e >= 1, out of place: the base keeps its registers (it was just loaded), the running power is
+// born in r's -- no copies at all
+template <int K>
+__device__ __forceinline__ void pow_from(R (&r)[K], const R (&base)[K], u32 e, const Field& F) {
+  if (e == 1) {
+#pragma unroll
+    for (int k = 0; k < K; k++)
+      asm volatile("mov.b32 %0, %2;\n\tmov.b32 %1, %3;" : "=r"(r[k].lo), "=r"(r[k].hi) : "r"(base[k].lo), "r"(base[k].hi));
+    return;
+  }
+  int bit = 30 - __clz((int)e);                  // index below the leading one, >= 0 here
+#pragma unroll
+  for (int k = 0; k < K; k++) r[k] = fsqr(base[k], F);
+  if ((e >> bit) & 1) {
+#pragma unroll
+    for (int k = 0; k < K; k++) r[k] = fmul(r[k], base[k], F);
+  }
+#pragma unroll 1
+  for (--bit; bit >= 0; --bit) {
+#pragma unroll
+    for (int k = 0; k < K; k++) r[k] = fsqr(r[k], F);
+    if ((e >> bit) & 1) {
+#pragma unroll
+      for (int k = 0; k < K; k++) r[k] = fmul(r[k], base[k], F);
+    }
+  }
+}
+
 __device__ __forceinline__ R sqr_n(R x, int n, const Field& F) {
 #pragma unroll 1
   for (int i = 0; i < n; i++) x = fsqr(x, F);
@@ -458,6 +486,7 @@ __device__ FFGPU_GENERIC_INLINE u32 generic_op(const Lane<K, THREADS, VEC>& L, u
       L.store_row(ins.arg, acc);
       break;
     default:
+      asm volatile("trap;");     // an instruction without code: never compute on with garbage
       break;
   }
   if (ins.flags & F_NEGR) {
@@ -615,6 +644,110 @@ __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS>()) eval_tape_k
       case FX_STORE:
         L.store_row(ins.arg, acc);
         break;
+
+      // ---- fused runs (compiler.cpp, fuse()) -----------------------------------------------------------
+      case FX_TERM: {
+        // T = var^e [* c]; ACC = T | ACC + T | ACC - T | T - ACC | ACC * T.  The old ACC waits in the next free
+        // spill slot while the power runs (the unfused sequence pushed it there too).
+        const u32 mode = (ins.flags >> TM_SHIFT) & 7u;
+        if (mode != TM_LOAD) L.slot_put(acc, sp);
+        else if (ins.flags & F_PUSH) L.slot_put(acc, sp++);
+        L.load_var(ins.arg & 0xffffu, b);
+        pow_from<K>(acc, b, ins.arg >> 16, F);
+        if (ins.flags & F_CMUL) {
+          const R c = mkR(ins.imm);
+#pragma unroll
+          for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], c, F);
+        }
+        if (mode != TM_LOAD) {
+          L.slot_get(b, sp);
+          if (mode == TM_ADD) {
+#pragma unroll
+            for (int k = 0; k < K; k++) acc[k] = fadd(b[k], acc[k], F);
+          } else if (mode == TM_SUB) {
+#pragma unroll
+            for (int k = 0; k < K; k++) acc[k] = fsub(b[k], acc[k], F);
+          } else if (mode == TM_RSUB) {
+#pragma unroll
+            for (int k = 0; k < K; k++) acc[k] = fsub(acc[k], b[k], F);
+          } else {
+#pragma unroll
+            for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], b[k], F);
+          }
+        }
+        break;
+      }
+      case FX_ACCUM2: {
+        // every branch is uniform and sits outside the per-probe loops
+        const u32 sa = ins.arg & 0xffu, sb = (ins.arg >> 8) & 0xffu;
+        if (ins.flags & F_INIT) {
+          if (ins.flags & F_SWAP) {
+#pragma unroll
+            for (int k = 0; k < K; k++) b[k] = fneg(acc[k], F);
+            L.tmp_put(b, sa);
+          } else {
+            L.tmp_put(acc, sa);
+          }
+        } else {
+          L.tmp_get(b, sa);
+          if (ins.flags & F_SWAP) {
+#pragma unroll
+            for (int k = 0; k < K; k++) b[k] = fsub(b[k], acc[k], F);
+          } else {
+#pragma unroll
+            for (int k = 0; k < K; k++) b[k] = fadd(b[k], acc[k], F);
+          }
+          L.tmp_put(b, sa);
+        }
+        if (ins.flags & F_INIT2) {
+          if (ins.flags & F_SWAP2) {
+#pragma unroll
+            for (int k = 0; k < K; k++) b[k] = fneg(acc[k], F);
+            L.tmp_put(b, sb);
+          } else {
+            L.tmp_put(acc, sb);
+          }
+        } else {
+          L.tmp_get(b, sb);
+          if (ins.flags & F_SWAP2) {
+#pragma unroll
+            for (int k = 0; k < K; k++) b[k] = fsub(b[k], acc[k], F);
+          } else {
+#pragma unroll
+            for (int k = 0; k < K; k++) b[k] = fadd(b[k], acc[k], F);
+          }
+          L.tmp_put(b, sb);
+        }
+        break;
+      }
+      case FX_ADDVARS: {
+        const u32 cnt = ins.arg & 0xffu;
+        u32 signs = ins.arg >> 8;
+        u64 ids = ins.imm;
+#pragma unroll 1
+        for (u32 i = 0; i < cnt; i++, ids >>= 8, signs >>= 1) {
+          L.load_var((u32)ids & 0xffu, b);
+          if (signs & 1u) {
+#pragma unroll
+            for (int k = 0; k < K; k++) acc[k] = fsub(acc[k], b[k], F);
+          } else {
+#pragma unroll
+            for (int k = 0; k < K; k++) acc[k] = fadd(acc[k], b[k], F);
+          }
+        }
+        break;
+      }
+      case FX_MULVARS: {
+        const u32 cnt = ins.arg & 0xffu;
+        u64 ids = ins.imm;
+#pragma unroll 1
+        for (u32 i = 0; i < cnt; i++, ids >>= 8) {
+          L.load_var((u32)ids & 0xffu, b);
+#pragma unroll
+          for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], b[k], F);
+        }
+        break;
+      }
 
       // ---- everything else, out of line (copies of the state: the originals never have their address taken)
       default: {

@@ -57,6 +57,14 @@ enum Op : uint8_t {
   OP_MULADD,  // ACC = ACC * var[arg] + imm      (Horner step; src selects var/negvar for the factor)
   OP_SAVE,    // temp[arg] = ACC                 (ACC unchanged)
   OP_ACCUM,   // temp[arg] += ACC  (F_SWAP: -=;  F_INIT: temp[arg] = +-ACC);  ACC unchanged
+  // ---- fused forms (compiler.cpp, fuse()): one dispatch for a frequent run of instructions ----------------
+  OP_TERM,    // T = var[arg & 0xffff] ^ (arg >> 16)  [* imm if F_CMUL];  then by mode (flags bits 4..6):
+              //   TM_LOAD  ACC = T (F_PUSH: spill the old ACC first)      <- LOAD.VAR[.P], POWU, [MUL.CONST]
+              //   TM_ADD   ACC = ACC + T   TM_SUB  ACC = ACC - T          <- LOAD.VAR.P, POWU, [MUL.CONST], ADD/SUB.POP
+              //   TM_RSUB  ACC = T - ACC   TM_MUL  ACC = ACC * T
+  OP_ACCUM2,  // two OP_ACCUMs of the same ACC: slot A = arg & 0xff (F_SWAP, F_INIT), slot B = arg >> 8 (F_SWAP2, F_INIT2)
+  OP_ADDVARS, // ACC = ACC +- var[id_0] +- ... : n = arg & 0xff (2..8), bit i of arg >> 8 set = subtract, ids = bytes of imm
+  OP_MULVARS, // ACC = ACC * var[id_0] * ... : n = arg & 0xff (2..8), ids = bytes of imm
   OP_COUNT
 };
 
@@ -71,6 +79,7 @@ enum Fast : uint8_t {
   FX_POWU, FX_INV, FX_STORE, FX_SQR,
   FX_SAVE, FX_ACCUM_INIT, FX_ACCUM_ADD, FX_ACCUM_SUB,
   FX_LOAD_TMP, FX_ADD_TMP, FX_MUL_TMP,
+  FX_TERM, FX_ACCUM2, FX_ADDVARS, FX_MULVARS,
   FX_COUNT
 };
 
@@ -88,6 +97,12 @@ enum Flags : uint8_t {
   F_SWAP = 2,   // non-commutative ops: exchange the roles of ACC and SRC
   F_NEGR = 4,   // negate the result (the parser's `!` and `;` operators)
   F_INIT = 8,   // OP_ACCUM: first contribution, the slot is overwritten
+  F_SWAP2 = 16, // OP_ACCUM2: F_SWAP of the second slot
+  F_INIT2 = 32, // OP_ACCUM2: F_INIT of the second slot
+  F_CMUL = 128, // OP_TERM: multiply the power by imm
 };
+// OP_TERM: what happens with the term, in flags bits 4..6
+enum TermMode : uint8_t { TM_LOAD = 0, TM_ADD = 1, TM_SUB = 2, TM_RSUB = 3, TM_MUL = 4 };
+constexpr uint8_t TM_SHIFT = 4;
 
 }  // namespace ffgpu

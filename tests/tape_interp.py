@@ -7,7 +7,8 @@ Field semantics: reference FFInt DEFAULT arithmetic (source/FFInt.cpp:130-192,22
 """
 import numpy as np
 
-from firefly_b200 import F_INIT, F_NEGR, F_PUSH, F_SWAP, OPS, SRCS
+from firefly_b200 import (F_CMUL, F_INIT, F_INIT2, F_NEGR, F_PUSH, F_SWAP, F_SWAP2, OPS, SRCS, TM_ADD, TM_LOAD, TM_MUL,
+                          TM_RSUB, TM_SUB)
 
 OP = {n: i for i, n in enumerate(OPS)}
 SRC = {n: i for i, n in enumerate(SRCS)}
@@ -51,9 +52,43 @@ def run(tape: np.ndarray, point, p: int, n_out: int):
         if op == OP["HALT"]:
             break
         b = None
-        pushed = False
-        if op == OP["LOAD"] and flags & F_PUSH:
-            pass
+        if op >= OP["TERM"]:
+            # fused forms decode their own operands
+            if op == OP["TERM"]:
+                mode = (flags >> 4) & 7
+                t = pow_ff(point[arg & 0xFFFF] % p, arg >> 16, p)
+                if flags & F_CMUL:
+                    t = t * imm % p
+                if mode == TM_LOAD:
+                    if flags & F_PUSH:
+                        stack.append(acc)
+                    acc = t
+                elif mode == TM_ADD:
+                    acc = (acc + t) % p
+                elif mode == TM_SUB:
+                    acc = (acc - t) % p
+                elif mode == TM_RSUB:
+                    acc = (t - acc) % p
+                elif mode == TM_MUL:
+                    acc = acc * t % p
+                else:
+                    raise ValueError("bad TERM mode")
+            elif op == OP["ACCUM2"]:
+                for slot, sw, init in ((arg & 0xFF, flags & F_SWAP, flags & F_INIT), ((arg >> 8) & 0xFF, flags & F_SWAP2, flags & F_INIT2)):
+                    v = (-acc) % p if sw else acc
+                    temps[slot] = v if init else (temps[slot] + v) % p
+            elif op in (OP["ADDVARS"], OP["MULVARS"]):
+                for k in range(arg & 0xFF):
+                    v = point[(imm >> (8 * k)) & 0xFF] % p
+                    if op == OP["MULVARS"]:
+                        acc = acc * v % p
+                    elif (arg >> (8 + k)) & 1:
+                        acc = (acc - v) % p
+                    else:
+                        acc = (acc + v) % p
+            else:
+                raise ValueError(f"bad opcode {op}")
+            continue
         if src == SRC["POP"]:
             b = stack.pop()
         elif src == SRC["VAR"]:

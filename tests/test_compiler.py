@@ -222,11 +222,14 @@ def test_f1_powers_are_computed_once():
     text, vars_ = W.benchmark("f1")
     par = ff.GpuParser(None, [text], vars_)
     tape = par.tape()
-    powu = int(np.sum(tape["op"] == ff.OPS.index("POWU")))
+    powu = int(np.sum(tape["op"] == ff.OPS.index("POWU")) + np.sum(tape["op"] == ff.OPS.index("TERM")))
     assert powu == 20                      # the reference's token list has 40 (numerator and denominator)
+    unfused = ff.GpuParser(None, [text], vars_, fuse=False)
+    assert int(np.sum(unfused.tape()["op"] == ff.OPS.index("POWU"))) == 20 and unfused.n_instr > par.n_instr
+    assert unfused.tape_work() == dict(par.tape_work(), instr=unfused.tape_work()["instr"])   # same work, fewer dispatches
     assert par.tape_work()["mm"] == 20 * 5 + 1 and par.tape_work()["inv"] == 1
     assert par.work()["mm"] == 201         # the algorithmic count stays the reference's
-    plain = ff.GpuParser(None, [text], vars_, cse=False)
+    plain = ff.GpuParser(None, [text], vars_, cse=False, fuse=False)
     assert int(np.sum(plain.tape()["op"] == ff.OPS.index("POWU"))) == 40
 
 

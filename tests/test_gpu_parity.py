@@ -213,8 +213,13 @@ def test_shared_subexpressions_vs_oracle(ctx, oracle, temps):
     plain.set_prime(p)
     assert plain.n_temps == 0 and plain.n_instr > par.n_instr
     assert np.array_equal(plain.evaluate_pre(pts), want)
+    unfused = ff.GpuParser(ctx, funs, vars_, temps=temps, fuse=False)      # same tape, one dispatch per operation
+    unfused.set_prime(p)
+    assert unfused.n_instr > par.n_instr
+    assert np.array_equal(unfused.evaluate_pre(pts), want)
     par.close()
     plain.close()
+    unfused.close()
 
 
 @pytest.mark.parametrize("name", ["f1", "f3", "factors4", "s_y_4_v"])
