@@ -82,6 +82,7 @@ def _load() -> C.CDLL:
         "ffgpu_prime": (C.c_uint64, [C.c_uint32]),
         "ffgpu_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32]),
         "ffgpu_eval_line": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32]),
+        "ffgpu_eval_wire": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32]),
         "ffgpu_eval_device": (
             C.c_int,
             [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p],
@@ -123,7 +124,7 @@ EXPORTS = [
     "ffgpu_create", "ffgpu_destroy", "ffgpu_n_devices", "ffgpu_last_error", "ffgpu_compile", "ffgpu_compile_text",
     "ffgpu_compile_file", "ffgpu_tape_destroy", "ffgpu_n_vars", "ffgpu_n_functions", "ffgpu_n_out", "ffgpu_n_instr",
     "ffgpu_stack_depth", "ffgpu_n_temps", "ffgpu_n_slots", "ffgpu_cse_fallbacks", "ffgpu_rpn", "ffgpu_get_tape", "ffgpu_work", "ffgpu_tape_work", "ffgpu_set_prime", "ffgpu_get_prime",
-    "ffgpu_n_primes", "ffgpu_prime", "ffgpu_eval", "ffgpu_eval_line", "ffgpu_eval_device", "ffgpu_host_alloc", "ffgpu_host_free",
+    "ffgpu_n_primes", "ffgpu_prime", "ffgpu_eval", "ffgpu_eval_line", "ffgpu_eval_wire", "ffgpu_eval_device", "ffgpu_host_alloc", "ffgpu_host_free",
     "ffgpu_queue_create", "ffgpu_queue_destroy", "ffgpu_queue_push", "ffgpu_queue_push_many", "ffgpu_queue_push_line",
     "ffgpu_queue_pop", "ffgpu_queue_pending", "ffgpu_queue_stats", "ffgpu_queue_error",
     "ffgpu_set_launch", "ffgpu_set_chunk", "ffgpu_launch_count", "ffgpu_fill_points", "ffgpu_checksum",
@@ -301,6 +302,17 @@ class GpuParser:
         s = np.ascontiguousarray(s, dtype=np.uint64)
         if lib.ffgpu_eval_line(self.h, a.ctypes.data, s.ctypes.data, t_ptr, n_points, out_ptr, thread_id):
             raise FFGpuError(last_error())
+
+    def evaluate_wire(self, values_msg, thread_id: int = 0) -> np.ndarray:
+        """MPIWorker's message format: [index, x_1..x_n] * k -> [index, f_1..f_m] * k (MPIWorker.hpp:213-228, 479-501)"""
+        msg = np.ascontiguousarray(values_msg, dtype=np.uint64).ravel()
+        if msg.size % (self.n_vars + 1):
+            raise ValueError("Corrupted values: the message length is not a multiple of n_vars + 1")
+        k = msg.size // (self.n_vars + 1)
+        res = np.empty(k * (self.n_out + 1), dtype=np.uint64)
+        if lib.ffgpu_eval_wire(self.h, msg.ctypes.data, k, res.ctypes.data, thread_id):
+            raise FFGpuError(last_error())
+        return res
 
     def eval_ptr(self, values_ptr: int, n_points: int, out_ptr: int, thread_id: int = 0):
         """Host pointers (e.g. pinned memory from ``host_alloc``)."""

@@ -155,6 +155,26 @@ struct ffgpu_queue {
 
 extern "C" {
 
+// MPIWorker's wire format in one call (reference: source/include/firefly/MPIWorker.hpp:213-228 receives
+// VALUES = [index, x_1 .. x_n] * k, :479-501 answers RESULT = [index, f_1 .. f_m] * k): transpose the message to
+// [variable][probe], evaluate all k probes in one batch, interleave the answers.  A GPU node can serve an
+// unmodified FireFly MPI master with this and two MPI calls.
+int ffgpu_eval_wire(ffgpu_tape* tape, const uint64_t* values_msg, size_t k, uint64_t* result_msg, uint32_t thread_id) {
+  if (!tape) return -1;
+  if (k == 0) return 0;
+  const size_t n = ffgpu_n_vars(tape), m = ffgpu_n_out(tape);
+  std::vector<uint64_t> in(std::max<size_t>(n * k, 1)), out(std::max<size_t>(m * k, 1));
+  for (size_t j = 0; j < k; ++j)
+    for (size_t v = 0; v < n; ++v) in[v * k + j] = values_msg[j * (n + 1) + 1 + v];
+  const int rc = ffgpu_eval(tape, in.data(), k, out.data(), thread_id);
+  if (rc) return rc;
+  for (size_t j = 0; j < k; ++j) {
+    result_msg[j * (m + 1)] = values_msg[j * (n + 1)];
+    for (size_t f = 0; f < m; ++f) result_msg[j * (m + 1) + 1 + f] = out[f * k + j];
+  }
+  return 0;
+}
+
 ffgpu_queue* ffgpu_queue_create(ffgpu_tape* tape, size_t max_batch) {
   if (!tape) return nullptr;
   ffgpu_queue* q = new ffgpu_queue;

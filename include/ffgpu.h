@@ -112,6 +112,10 @@ int ffgpu_eval(ffgpu_tape*, const uint64_t* values, size_t n_points, uint64_t* o
  * out: [n_out][n_points], all HOST buffers.  Values are identical to ffgpu_eval on the expanded points. */
 int ffgpu_eval_line(ffgpu_tape*, const uint64_t* a, const uint64_t* s, const uint64_t* t, size_t n_points,
                     uint64_t* out, uint32_t thread_id);
+/* The MPI worker's message format (MPIWorker.hpp:213-228, 479-501): values_msg = [index, x_1..x_n] * k as the master
+ * sends it with tag VALUES, result_msg = [index, f_1..f_m] * k as the worker answers with tag RESULT (the caller
+ * appends its free-slot count).  One batch evaluation for all k probes. */
+int ffgpu_eval_wire(ffgpu_tape*, const uint64_t* values_msg, size_t k, uint64_t* result_msg, uint32_t thread_id);
 /* DEVICE buffers on GPU `device_index` of the ctx, row strides in elements; launches on `stream`
  * (a cudaStream_t, NULL = default stream) and returns without synchronising. */
 int ffgpu_eval_device(ffgpu_tape*, int device_index, const uint64_t* d_values, size_t in_stride, size_t n_points,

@@ -244,3 +244,31 @@ def test_probe_queue_without_a_gpu_fails_loudly():
     with pytest.raises(ff.FFGpuError, match="no GPU|no CPU path|pinned staging"):
         q.pop()
     q.close()
+
+
+def test_offline_probe_files_round_trip(tmp_path):
+    """requested_probes.gz / probes/<k>.gz text formats (Reconstructor.hpp:3751-3846)"""
+    from firefly_b200 import offline
+    req = tmp_path / "requested_probes.gz"
+    import gzip
+    with gzip.open(req, "wt") as f:
+        f.write("1 1 | 6303994061519960968 | 11 22 33\n")
+        f.write("2 1 | 5 | 9223372036854775782 0 1\n\n")
+    orders, ts, pts = offline.read_requested(str(req), 3)
+    assert orders == ["1 1", "2 1"] and ts == [6303994061519960968, 5]
+    assert pts.shape == (3, 2) and int(pts[0, 1]) == 9223372036854775782 and int(pts[2, 0]) == 33
+    out = tmp_path / "probes" / "0.gz"
+    vals = np.array([[7, 8], [0, 9223372036854775782]], dtype=np.uint64)
+    offline.write_probes(str(out), orders, ts, vals)
+    with gzip.open(out, "rt") as f:
+        lines = f.read().splitlines()
+    assert lines[0] == "1 1 | 6303994061519960968 | 7 0" and lines[1] == "2 1 | 5 | 8 9223372036854775782"
+    o2, t2, v2 = offline.read_probes(str(out))
+    assert o2 == orders and t2 == ts and np.array_equal(v2, vals)
+    with pytest.raises(ValueError, match="variables"):
+        offline.read_requested(str(req), 4)
+    # the reference's own example file parses (format check only: the functions behind it are not shipped)
+    ex = "/root/reference/examples/firefly_executable/probes/0.gz"
+    if os.path.exists(ex):
+        o, t, v = offline.read_probes(ex)
+        assert len(o) == len(t) == v.shape[1] > 0 and v.shape[0] == 3

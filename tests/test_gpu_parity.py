@@ -432,3 +432,41 @@ def test_probe_queue_reports_evaluation_errors(ctx):
     with pytest.raises(ff.FFGpuError, match="set_prime"):
         q.pop()
     q.close()
+
+
+def test_offline_probe_service(ctx, oracle, tmp_path):
+    """firefly_b200.offline: requested_probes.gz -> probes/<k>.gz for the stock `firefly` executable"""
+    import gzip
+    from firefly_b200 import offline
+    g = load_golden("s_y_4_v")
+    fn = tmp_path / "funs.m"
+    fn.write_text(";\n".join(g["functions"]) + ";\n")
+    k = 3
+    p = ff.primes()[k]
+    pts = ff.synthetic_points(4, 300, p, seed=41)
+    pts[:, 0] = 0
+    with gzip.open(tmp_path / "requested_probes.gz", "wt") as f:
+        for j in range(300):
+            f.write(f"{1 + j % 3} 1 2 | {int(pts[0, j])} | " + " ".join(str(int(x)) for x in pts[:, j]) + "\n")
+    n = offline.serve(str(fn), g["vars"], k, str(tmp_path / "requested_probes.gz"), str(tmp_path / "probes" / f"{k}.gz"))
+    assert n == 300
+    orders, ts, vals = offline.read_probes(str(tmp_path / "probes" / f"{k}.gz"))
+    assert orders[4] == "2 1 2" and ts == [int(x) for x in pts[0]]
+    assert np.array_equal(vals, oracle.parse(g["functions"], g["vars"], p).eval(pts))
+
+
+def test_mpi_wire_format(ctx, oracle):
+    """[index, x_1..x_n]*k in, [index, f_1..f_m]*k out -- what an MPIWorker exchanges with the master"""
+    g = load_golden("s_y_4_v")
+    p = ff.primes()[2]
+    par = ff.GpuParser(ctx, g["functions"], g["vars"])
+    par.set_prime(p)
+    k = 333
+    pts = ff.synthetic_points(4, k, p, seed=17)
+    idx = np.arange(1000, 1000 + k, dtype=np.uint64)[::-1].copy()
+    msg = np.concatenate([idx.reshape(-1, 1), pts.T], axis=1)
+    res = par.evaluate_wire(msg).reshape(k, par.n_out + 1)
+    assert np.array_equal(res[:, 0], idx)
+    assert np.array_equal(res[:, 1:].T, oracle.parse(g["functions"], g["vars"], p).eval(pts))
+    with pytest.raises(ValueError, match="Corrupted"):
+        par.evaluate_wire(np.zeros(7, dtype=np.uint64))
