@@ -118,6 +118,16 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(name):
+    """DRAM bytes per probe (dram__bytes_read.sum + dram__bytes_write.sum over the launch's points) of the function's
+    kernel from the committed `ncu --set full` capture, or None"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(name)
+    except Exception:
+        return None
+
+
 def work_of(par):
     """(reference-token-list work, MM-eq of it, MM-eq the compiled tape executes)"""
     w = par.work()
@@ -129,7 +139,7 @@ def work_of(par):
 
 
 # ------------------------------------------------------------------------------------------------------
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, real_stdout):
     """The reference's own CPU evaluate_pre on this box's host cores (rank 0 only)."""
     if rank != 0:
         return
@@ -179,11 +189,25 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(real_stdout, line)
 
 
 # ------------------------------------------------------------------------------------------------------
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line: keep the real stdout for it and send everything else that any
+    library writes to file descriptor 1 (NCCL prints its version banner there) to stderr"""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def _emit(real_stdout, line):
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -202,7 +226,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, real_stdout)
         return
 
     import torch
@@ -474,13 +498,14 @@ def main():
                 "hbm": {"achieved": probes_per_s_top * bytes_per_probe / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": probes_per_s_top * bytes_per_probe / 1e9 / hbm_peak, "peak_source": hbm_src,
                         "bytes_per_probe": bytes_per_probe},
-                "traffic": None,
+                "traffic": (lambda t: None if t is None else t["bytes_per_probe"] * n)(ncu_traffic(FUNCS[top])),
+                "traffic_source": (lambda t: None if t is None else t["source"])(ncu_traffic(FUNCS[top])),
             },
             "cpu_baseline": cpu,
         }
         if sweep is not None:
             line["bunch_sweep_f4_probes_per_s"] = sweep
-        print(json.dumps(line), flush=True)
+        _emit(real_stdout, line)
     if world > 1:
         dist.destroy_process_group()
     if not verified:

@@ -50,7 +50,8 @@ struct DevBuf {
   uint64_t* d_in = nullptr;
   uint64_t* d_out = nullptr;
   uint64_t* d_as = nullptr;         // line mode: a[n_vars] then s[n_vars]
-  size_t cap_in = 0, cap_out = 0, cap_as = 0;   // elements
+  uint64_t* h_stage = nullptr;      // pinned: small calls travel as one contiguous copy each way
+  size_t cap_in = 0, cap_out = 0, cap_as = 0, cap_stage = 0;   // elements
 };
 struct SlotDev {
   DevBuf buf[N_BUF];
@@ -249,6 +250,7 @@ void ffgpu_destroy(ffgpu_ctx* ctx) {
         if (b.d_in) cudaFree(b.d_in);
         if (b.d_out) cudaFree(b.d_out);
         if (b.d_as) cudaFree(b.d_as);
+        if (b.h_stage) cudaFreeHost(b.h_stage);
         if (b.stream) cudaStreamDestroy(b.stream);
       }
     }
@@ -422,6 +424,42 @@ int eval_host(ffgpu_tape* t, const uint64_t* values, const uint64_t* line_a, con
   const size_t n_vars = t->col.vars.size(), n_out = t->col.n_out;
   Slot& slot = ctx->slots[thread_id % N_SLOTS];
   std::lock_guard<std::mutex> lock(slot.mtx);
+
+  // Small calls -- the Reconstructor's bunches of 1..128 points (Reconstructor.hpp:3330-3354) -- are latency
+  // bound: one GPU, one contiguous pinned copy each way instead of strided copies from pageable memory.
+  constexpr size_t SMALL_WORDS = 32 * 1024;            // 256 KB in + out
+  if (values && (n_vars + n_out) * (n_points + 1) <= SMALL_WORDS) {
+    int prev = 0;
+    cudaGetDevice(&prev);
+    const int rc_small = [&]() -> int {
+      FF_CUDA(cudaSetDevice(ctx->devs[0].id));
+      DevBuf& b = slot.dev[0].buf[0];
+      const size_t n_even = (n_points + 1) & ~(size_t)1;
+      const size_t w_in = std::max<size_t>(n_vars * n_even, 1), w_out = std::max<size_t>(n_out * n_even, 1);
+      if (ensure(b, w_in + n_even, w_out)) return -1;
+      if (b.cap_stage < w_in + w_out) {
+        if (b.h_stage) FF_CUDA(cudaFreeHost(b.h_stage));
+        b.h_stage = nullptr;
+        b.cap_stage = 0;
+        FF_CUDA(cudaHostAlloc(&b.h_stage, std::max<size_t>(w_in + w_out, SMALL_WORDS + 64) * sizeof(uint64_t), cudaHostAllocPortable));
+        b.cap_stage = std::max<size_t>(w_in + w_out, SMALL_WORDS + 64);
+      }
+      uint64_t* h_in = b.h_stage;
+      uint64_t* h_out = b.h_stage + w_in;
+      for (size_t v = 0; v < n_vars; ++v) {
+        std::memcpy(h_in + v * n_even, values + v * n_points, n_points * sizeof(uint64_t));
+        if (n_even != n_points) h_in[v * n_even + n_points] = 0;
+      }
+      if (n_vars) FF_CUDA(cudaMemcpyAsync(b.d_in, h_in, n_vars * n_even * sizeof(uint64_t), cudaMemcpyHostToDevice, b.stream));
+      if (launch(t, 0, b.d_in, n_even, n_even, b.d_out, n_even, b.stream)) return -1;
+      if (n_out) FF_CUDA(cudaMemcpyAsync(h_out, b.d_out, n_out * n_even * sizeof(uint64_t), cudaMemcpyDeviceToHost, b.stream));
+      FF_CUDA(cudaStreamSynchronize(b.stream));
+      for (size_t f = 0; f < n_out; ++f) std::memcpy(out + f * n_points, h_out + f * n_even, n_points * sizeof(uint64_t));
+      return 0;
+    }();
+    cudaSetDevice(prev);
+    return rc_small;
+  }
 
   // contiguous shard per device; chunk size: large enough to amortise launches, small enough to pipeline
   const size_t per_dev = (n_points + G - 1) / G;
