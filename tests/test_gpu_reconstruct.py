@@ -13,13 +13,20 @@ pytestmark = pytest.mark.gpu
 BIN = os.path.join(ROOT, "oracle", "_ref", "gpu_reconstruct")
 
 
-@pytest.mark.parametrize("name,bunch,threads", [
+CASES = [
     ("s_y_4_v", 1, 4),       # configs[0]: s_y_4_v.m, bunch_size = 1
     ("s_y_4_v", 4, 4),       # the reference's test_bunch.cpp setting
     ("s_y_1_v", 128, 2),
     ("f1", 64, 4),
     ("factors3", 16, 4),
-])
+]
+# configs[4]: the full f4 reconstruction (106 668 probes, ~2.5 minutes for the CPU and GPU runs together; measured
+# identical on B200, profiles/r01_cfg5_f4_reconstruct.log).  Too slow for the default suite: FFGPU_SLOW_TESTS=1.
+if os.environ.get("FFGPU_SLOW_TESTS"):
+    CASES.append(("f4", 128, 16))
+
+
+@pytest.mark.parametrize("name,bunch,threads", CASES)
 def test_reconstruction_identical(tmp_path, name, bunch, threads):
     if not os.path.exists(BIN):
         pytest.skip("oracle/_ref/gpu_reconstruct not built (needs /root/reference at build time)")
@@ -27,7 +34,7 @@ def test_reconstruction_identical(tmp_path, name, bunch, threads):
     f = tmp_path / (name + ".m")
     f.write_text(";\n".join(g["functions"]) + ";\n")
     r = subprocess.run([BIN, str(f), str(bunch), str(threads), *g["vars"]], cwd=tmp_path, capture_output=True,
-                       text=True, timeout=600)
+                       text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "0 differ" in r.stdout
     # the GPU black box really ran on the GPU
