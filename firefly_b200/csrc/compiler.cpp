@@ -955,7 +955,11 @@ bool Collection::check_function(uint32_t fn, uint64_t p, const uint64_t* point) 
       case OP_NPOWL:
         acc = swap ? ffhost::pow_int(b, ffhost::to_neg_int(acc), p) : ffhost::pow_int(acc, ffhost::to_neg_int(b), p);
         break;
-      case OP_MULADD: acc = ffhost::add(ffhost::mul(acc, point[in.arg] % p, p), in.imm, p); break;
+      case OP_MULADD: {
+        const uint64_t m = ffhost::mul(acc, point[in.arg] % p, p);
+        acc = swap ? ffhost::sub(in.imm, m, p) : ffhost::add(m, in.imm, p);
+        break;
+      }
       case OP_SAVE:
         if (in.arg >= 16) return false;
         temps[in.arg] = acc;
@@ -1316,6 +1320,12 @@ void Collection::fuse() {
     auto addlike = [&](const Instr& in) { return (in.op == OP_ADD || in.op == OP_SUB) && in.src == SRC_VAR && in.flags == 0 && in.arg < 256; };
     auto mullike = [&](const Instr& in) { return in.op == OP_MUL && in.src == SRC_VAR && in.flags == 0 && in.arg < 256; };
     const bool is_add = addlike(a), is_mul = mullike(a);
+    // a constant added after a multiplication by a variable is a Horner step (the form the FireFly paper
+    // recommends for large inputs): MUL.VAR, ADD.CONST | (c - ACC)  ->  MULADD
+    auto horner_tail = [&](size_t k) {
+      return k < n && tape[k].src == SRC_CONST && patch_of[k] >= 0 &&
+             ((tape[k].op == OP_ADD && tape[k].flags == 0) || (tape[k].op == OP_SUB && tape[k].flags == F_SWAP));
+    };
     if (is_add || is_mul) {
       size_t j = i;
       uint64_t ids = 0;
@@ -1325,6 +1335,23 @@ void Collection::fuse() {
         if (tape[j].op == OP_SUB) signs |= 1u << cnt;
         ++cnt;
         ++j;
+      }
+      if (is_mul && horner_tail(j)) {      // the last multiplication of the run belongs to the Horner step
+        --cnt;
+        --j;
+      }
+      if (is_mul && cnt == 0) {
+        Instr t{};
+        t.op = OP_MULADD;
+        t.src = SRC_VAR;
+        t.arg = tape[j].arg;
+        t.flags = tape[j + 1].op == OP_SUB ? F_SWAP : 0;
+        t.fast = FX_MULADD;
+        new_index[j] = new_index[j + 1] = (uint32_t)out.size();
+        patches[patch_of[j + 1]].instr = (uint32_t)out.size();
+        out.push_back(t);
+        i = j + 2;
+        continue;
       }
       if (cnt >= 2) {
         Instr t{};

@@ -20,8 +20,11 @@
 // What is different is everything after the RPN: instead of a flat token list for a
 // stack machine we build expression trees, fold every constant sub-expression once per
 // prime with the reference's FFInt semantics (ffhost.hpp) -- a superset of the
-// reference's NUM NUM / and VAR NUM / folds (:619-645) -- order sub-trees to minimise
-// spill-stack depth and emit accumulator code (tape.hpp).
+// reference's NUM NUM / and VAR NUM / folds (:619-645) -- hash-cons each tree into a DAG so
+// that equal sub-expressions are evaluated once, order sub-trees to minimise spill-stack
+// depth, emit accumulator code (tape.hpp), fuse frequent instruction runs, and check the
+// result: every function's tape is interpreted on the host at one point and compared with
+// the value of its expression tree before the compilation is accepted.
 #pragma once
 #include <cstdint>
 #include <string>

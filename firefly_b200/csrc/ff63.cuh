@@ -6,19 +6,22 @@
 // produces; HOW they are computed is different:
 //
 //  * FireFly's primes (reference: source/ReconstHelper.cpp:24-125) are all of the
-//    form p = 2^63 - c with 25 <= c <= 13797.  2^63 = c (mod p), so a 128-bit
-//    product folds with two 32x32->64 multiplies by a 16-bit constant instead of
+//    form p = 2^63 - c with 25 <= c <= 13797.  2^63 = c and 2^64 = d = 2c (mod p), so a
+//    128-bit product folds with two 32x32->64 multiplies by a 16-bit constant instead of
 //    a long-double quotient estimate (reference DEFAULT) or a Barrett preinverse
-//    (reference FLINT).  This is the "pm" (pseudo-Mersenne) path, c < 2^15.
-//  * Any other odd modulus 2^62 < p < 2^63 uses the Barrett path ("generic").
-//  * Inside multiplication chains values are kept LAZY: any representative in
-//    [0, 2^64) of the residue class.  mul/sqr accept and return lazy values;
-//    canon() brings one back to [0, p).  add/sub/neg are canonical-in /
-//    canonical-out exactly like FFInt.
+//    (reference FLINT).  c < 2^15 is required.
+//  * What the interpreter (kernels.cu) computes in is the "b63" family below: BOUNDED lazy
+//    residues, any representative under 2^63 + 2^32, as two 32-bit words.  canon_pm()
+//    brings a value back to [0, p) where the reference's semantics need it.
+//  * Also here, for comparison in bench/pipe_peak.cu and for host-side use: the plain
+//    canonical operations, the unbounded lazy forms the first kernel used (mul_pm,
+//    mul_pm_dev, add_lazy ...: any representative under 2^64, 6 more adds per multiplication)
+//    and a Barrett path for moduli that are not of the 2^63 - c form.
 //
-// The B200 integer path: IMAD.WIDE.U32 (32x32+64 -> 64) on the fma pipe, IADD3 /
-// LOP3 / SHF on the alu pipe.  One lazy multiplication is 7 multiply
-// instructions (4 product + 2 fold + 1 fold) and ~10 adds.
+// The B200 integer path (measured, bench/pipe_peak.cu): IMAD.WIDE.U32 (32x32+64 -> 64) occupies
+// the fma-heavy pipe for 4 cycles per warp and blocks one ALU issue slot, a 32-bit IMAD 2 cycles,
+// IADD3 / LOP3 / SHF 2 cycles on the alu pipe.  One bounded multiplication is 6 wide + 1 narrow
+// multiplies and 11 add/logic instructions: 1134 G modular multiplications/s on the chip.
 #pragma once
 #include <cstdint>
 

@@ -5,21 +5,24 @@
 // operators it calls (source/FFInt.cpp:130-192) for ALL probe points of a batch at once.
 //
 // Mapping to the machine
-//   * one probe point per lane, K points per thread (independent multiply chains for ILP);
-//   * the accumulator of the tape machine (tape.hpp) is K 64-bit registers; intermediate
-//     values are LAZY residues (any representative below 2^64, see ff63.cuh) and are made
+//   * one probe point per lane, K points per thread (independent multiply chains for ILP), 80 registers
+//     per thread at K = 8 so that three 256-thread blocks stay resident per SM;
+//   * the accumulator of the tape machine (tape.hpp) is K residues of two 32-bit registers each;
+//     intermediate values are BOUNDED lazy residues (below 2^63 + 2^32, ff63.cuh) and are made
 //     canonical only where the reference's semantics need it: zero tests of divisors, lane
 //     exponents, and stores;
 //   * the tape is warp-uniform: every branch of the interpreter is uniform, instructions are
-//     fetched with one 128-bit load one instruction ahead of execution;
-//   * the spill stack lives in shared memory, laid out [slot][k][thread] so that a warp's
+//     fetched with one 128-bit load one instruction ahead of execution; the frequent instructions
+//     are cases of one switch over a dense code, the rare ones go through generic_op on copies;
+//   * spill and temp slots live in shared memory, laid out [slot][k][thread] so that a warp's
 //     access is one conflict-free 256-byte row;
-//   * probe coordinates are read as 16-byte vectors, [var][point] layout, fully coalesced;
+//   * probe coordinates are read as 16-byte vectors, [var][point] layout, fully coalesced
+//     (DRAM traffic equals the algorithmic 8 * (n_vars + n_out) bytes per probe, profiles/);
 //     results are written [function][point], 16-byte vectors, fully coalesced;
 //   * divisions: ONE Fermat inversion per thread block.  Every lane's divisor enters a
 //     three-level product tree (K values per thread -> 32 lanes by shuffle scans -> the
 //     block's warps through shared memory); lane w of warp 0 inverts the running product of
-//     warps 0..w, so the 32 lanes of the inverting warp all do useful, different work.
+//     warps 0..w, so the lanes of the inverting warp all do useful, different work.
 //     Zero divisors are replaced by 1 in the tree and produce 0 (reference: a/0 = 0).
 #include "kernels.cuh"
 
@@ -411,14 +414,6 @@ __device__ FFGPU_GENERIC_INLINE u32 generic_op(const Lane<K, THREADS, VEC>& L, u
 #pragma unroll
       for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], b[k], F);
       break;
-    case OP_MULADD: {
-      R x[K];
-      L.load_var(ins.arg, x);
-      const R c = mkR(ins.imm);
-#pragma unroll
-      for (int k = 0; k < K; k++) acc[k] = fadd(fmul(acc[k], x[k], F), c, F);
-      break;
-    }
     case OP_SQR:
 #pragma unroll
       for (int k = 0; k < K; k++) acc[k] = fsqr(acc[k], F);
@@ -745,6 +740,22 @@ __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS>()) eval_tape_k
           L.load_var((u32)ids & 0xffu, b);
 #pragma unroll
           for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], b[k], F);
+        }
+        break;
+      }
+
+      case FX_MULADD: {
+        // Horner step: ACC = ACC * var + c  (F_SWAP: c - ACC * var)
+        L.load_var(ins.arg, b);
+        const R c = mkR(ins.imm);
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], b[k], F);
+        if (ins.flags & F_SWAP) {
+#pragma unroll
+          for (int k = 0; k < K; k++) acc[k] = fsub(c, acc[k], F);
+        } else {
+#pragma unroll
+          for (int k = 0; k < K; k++) acc[k] = fadd(acc[k], c, F);
         }
         break;
       }

@@ -18,6 +18,10 @@
 //   * the spill stack is only touched when both operands of a binary operator are
 //     compound expressions; the compiler orders sub-trees (Sethi-Ullman) so that
 //     the depth stays logarithmic;
+//   * values used more than once (equal sub-expressions of one function) are parked
+//     in temp slots, also in shared memory, and read back non-destructively;
+//   * frequent runs of instructions have fused forms (TERM, ACCUM2, ADDVARS, MULVARS,
+//     MULADD) that cost one dispatch of the interpreter;
 //   * all functions of a collection are concatenated into one tape; each ends in a
 //     STORE that writes the canonical residue to out[slot][point].
 //
@@ -35,7 +39,8 @@ struct alignas(16) Instr {
   uint8_t src;     // Src
   uint8_t flags;   // F_*
   uint8_t fast;    // Fast: dense dispatch code of the common (op, src, flags) combinations, 0 = generic path
-  uint32_t arg;    // variable index (SRC_VAR/SRC_NEGVAR) or output slot (OP_STORE)
+  uint32_t arg;    // variable index (SRC_VAR/SRC_NEGVAR), temp slot (SRC_TMP, SAVE, ACCUM), output slot (STORE);
+                   // the fused forms pack their own fields in here (see Op)
   uint64_t imm;    // constant (SRC_CONST, canonical residue mod the current prime)
 };
 static_assert(sizeof(Instr) == 16, "Instr must be 16 bytes");
@@ -54,7 +59,7 @@ enum Op : uint8_t {
   OP_POWL,    // ACC = ACC ^ SRC, exponent differs per lane (F_SWAP: ACC = SRC ^ ACC)
   OP_NPOWL,   // ACC = ACC ^ -(int)SRC per lane  (F_SWAP likewise)
   OP_STORE,   // out[arg][point] = canonical(ACC)
-  OP_MULADD,  // ACC = ACC * var[arg] + imm      (Horner step; src selects var/negvar for the factor)
+  OP_MULADD,  // ACC = ACC * var[arg] + imm      (Horner step; F_SWAP: ACC = imm - ACC * var[arg])
   OP_SAVE,    // temp[arg] = ACC                 (ACC unchanged)
   OP_ACCUM,   // temp[arg] += ACC  (F_SWAP: -=;  F_INIT: temp[arg] = +-ACC);  ACC unchanged
   // ---- fused forms (compiler.cpp, fuse()): one dispatch for a frequent run of instructions ----------------
@@ -79,7 +84,7 @@ enum Fast : uint8_t {
   FX_POWU, FX_INV, FX_STORE, FX_SQR,
   FX_SAVE, FX_ACCUM_INIT, FX_ACCUM_ADD, FX_ACCUM_SUB,
   FX_LOAD_TMP, FX_ADD_TMP, FX_MUL_TMP,
-  FX_TERM, FX_ACCUM2, FX_ADDVARS, FX_MULVARS,
+  FX_TERM, FX_ACCUM2, FX_ADDVARS, FX_MULVARS, FX_MULADD,
   FX_COUNT
 };
 

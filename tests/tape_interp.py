@@ -127,7 +127,7 @@ def run(tape: np.ndarray, point, p: int, n_out: int):
             out[arg] = acc
         elif op == OP["MULADD"]:
             x = point[arg] % p
-            acc = (acc * x + imm) % p
+            acc = (imm - acc * x) % p if flags & F_SWAP else (acc * x + imm) % p
         elif op == OP["SAVE"]:
             temps[arg] = acc
         elif op == OP["ACCUM"]:
