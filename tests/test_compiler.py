@@ -272,3 +272,23 @@ def test_offline_probe_files_round_trip(tmp_path):
     if os.path.exists(ex):
         o, t, v = offline.read_probes(ex)
         assert len(o) == len(t) == v.shape[1] > 0 and v.shape[0] == 3
+
+
+@pytest.mark.parametrize("cse,fuse", [(True, True), (True, False), (False, True), (False, False)])
+def test_fused_and_plain_tapes_agree(oracle, cse, fuse):
+    """Horner nests (MULADD), monomials (TERM), variable runs (ADDVARS / MULVARS): every combination of the
+    sharing and fusion passes gives the oracle's values"""
+    from firefly_b200 import workloads as W
+    funs, vars_ = W.ibp_like_collection(40, 8, seed=77)
+    funs += ["3+x1*(5-x2*(7+x3*(11-x1*(13+x2))))", "x1*x2*x3*x4-x5+x6-x7+x8", "(x1^3*7+x2^5*9-x3^7)*(x1^3+2)-x8^65535",
+             "x1^70000+x2^1", "(x1+x2+x3)^2/(x1*x2*x3+x4^2*5)"]
+    p = ff.primes()[9]
+    pts = ff.synthetic_points(8, 5, p, seed=1)
+    pts[:, 0] = 0
+    want = oracle.parse(funs, vars_, p).eval(pts)
+    par = ff.GpuParser(None, funs, vars_, cse=cse, fuse=fuse)
+    par.set_prime(p)
+    assert par.cse_fallbacks == 0
+    ops = {ff.OPS[o] for o in par.tape()["op"]}
+    assert ({"TERM", "MULADD", "ADDVARS", "MULVARS"} <= ops) == fuse
+    assert np.array_equal(interp(par, pts, p), want)
