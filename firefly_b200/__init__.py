@@ -76,6 +76,7 @@ def _load() -> C.CDLL:
         "ffgpu_get_tape": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t]),
         "ffgpu_work": (None, [C.c_void_p, u64p]),
         "ffgpu_tape_work": (None, [C.c_void_p, u64p]),
+        "ffgpu_set_factors": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), strs, C.c_size_t, strs, C.c_size_t]),
         "ffgpu_set_prime": (C.c_int, [C.c_void_p, C.c_uint64]),
         "ffgpu_get_prime": (C.c_uint64, [C.c_void_p]),
         "ffgpu_n_primes": (C.c_uint32, []),
@@ -123,7 +124,7 @@ lib = _load()
 EXPORTS = [
     "ffgpu_create", "ffgpu_destroy", "ffgpu_n_devices", "ffgpu_last_error", "ffgpu_compile", "ffgpu_compile_text",
     "ffgpu_compile_file", "ffgpu_tape_destroy", "ffgpu_n_vars", "ffgpu_n_functions", "ffgpu_n_out", "ffgpu_n_instr",
-    "ffgpu_stack_depth", "ffgpu_n_temps", "ffgpu_n_slots", "ffgpu_cse_fallbacks", "ffgpu_rpn", "ffgpu_get_tape", "ffgpu_work", "ffgpu_tape_work", "ffgpu_set_prime", "ffgpu_get_prime",
+    "ffgpu_stack_depth", "ffgpu_n_temps", "ffgpu_n_slots", "ffgpu_cse_fallbacks", "ffgpu_rpn", "ffgpu_get_tape", "ffgpu_work", "ffgpu_tape_work", "ffgpu_set_factors", "ffgpu_set_prime", "ffgpu_get_prime",
     "ffgpu_n_primes", "ffgpu_prime", "ffgpu_eval", "ffgpu_eval_line", "ffgpu_eval_wire", "ffgpu_eval_device", "ffgpu_host_alloc", "ffgpu_host_free",
     "ffgpu_queue_create", "ffgpu_queue_destroy", "ffgpu_queue_push", "ffgpu_queue_push_many", "ffgpu_queue_push_line",
     "ffgpu_queue_pop", "ffgpu_queue_pending", "ffgpu_queue_stats", "ffgpu_queue_error",
@@ -254,6 +255,15 @@ class GpuParser:
     @property
     def n_slots(self) -> int:
         return lib.ffgpu_n_slots(self.h)
+
+    def set_factors(self, factors: dict, factor_vars: Sequence[str]):
+        """{output index: factor expression}: output i becomes f_i / factor_i on the device (what Reconstructor does
+        with parsed_factors after bb.eval, Reconstructor.hpp:3449-3457).  Call set_prime again afterwards."""
+        idx = (C.c_uint32 * max(len(factors), 1))(*factors.keys())
+        if lib.ffgpu_set_factors(self.h, idx, _strs(list(factors.values())), len(factors), _strs(factor_vars), len(factor_vars)):
+            raise FFGpuError(last_error())
+        self.n_out = lib.ffgpu_n_out(self.h)
+        self.n_functions = lib.ffgpu_n_functions(self.h)
 
     # -- prime -----------------------------------------------------------------------
     def set_prime(self, p: int):

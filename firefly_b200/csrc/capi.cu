@@ -380,6 +380,25 @@ int ffgpu_set_prime(ffgpu_tape* t, uint64_t p) {
   return 0;
 }
 
+int ffgpu_set_factors(ffgpu_tape* t, const uint32_t* out_index, const char* const* factors, size_t n_factors,
+                      const char* const* factor_vars, size_t n_factor_vars) {
+  if (!t) return fail("null tape");
+  std::vector<std::pair<uint32_t, std::string>> fac;
+  for (size_t i = 0; i < n_factors; ++i) fac.emplace_back(out_index[i], factors[i] ? factors[i] : "");
+  std::string err;
+  if (!t->col.apply_factors(fac, to_vec(factor_vars, n_factor_vars), err)) return fail(err);
+  // the tape changed size: drop the device copies, ffgpu_set_prime uploads the new one
+  for (size_t g = 0; t->ctx && g < t->ctx->devs.size(); ++g) {
+    DeviceGuard guard(t->ctx->devs[g].id);
+    cudaDeviceSynchronize();
+    if (t->d_tape[g]) cudaFree(t->d_tape[g]);
+    if (t->d_chunks[g]) cudaFree(t->d_chunks[g]);
+    t->d_tape[g] = nullptr;
+    t->d_chunks[g] = nullptr;
+  }
+  return 0;
+}
+
 int ffgpu_set_launch(ffgpu_tape* t, int k, int threads) {
   if (!(k == 0 || k == 1 || k == 2 || k == 4 || k == 8)) return fail("probes_per_thread must be 0, 1, 2, 4 or 8");
   if (!(threads == 0 || threads == 128 || threads == 256 || threads == 512))

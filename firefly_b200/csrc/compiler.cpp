@@ -278,7 +278,12 @@ bool Collection::build_tree(Function& f, std::string& err) {
   }
   f.root = st.back();      // evaluate_pre returns the top of the stack
 
-  // spill-stack need (Sethi-Ullman): operands that can be addressed directly cost nothing
+  compute_needs(f);
+  return true;
+}
+
+// spill-stack need (Sethi-Ullman): operands that can be addressed directly cost nothing
+void Collection::compute_needs(Function& f) {
   auto direct = [&](int32_t i) {
     const Node& n = f.nodes[i];
     return n.is_const || n.kind == N_VAR || n.kind == N_NEGVAR;
@@ -297,7 +302,6 @@ bool Collection::build_tree(Function& f, std::string& err) {
       n.need = (uint8_t)std::min(m, 255u);
     }
   }
-  return true;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1427,6 +1431,65 @@ bool Collection::compile_text(const std::string& text, const std::vector<std::st
     if (end == text.size()) break;
     start = end + 1;
   }
+  return finish(err);
+}
+
+// Scanned factors (reference: Reconstructor::get_job divides output i of the black box by
+// parsed_factors[i].evaluate_pre(values)[0], Reconstructor.hpp:3392-3396,3449-3457; MPIWorker.hpp:486-495).
+// Here the division joins the function's expression tree -- out_i = f_i / g_i with FFInt's a/0 = 0 -- so it runs
+// on the device inside the same tape.  The factor expressions have their own variable names (FireFly writes
+// them over x1..xn, ParserUtils.cpp:182-185), matched to the collection's variables by position.
+bool Collection::apply_factors(const std::vector<std::pair<uint32_t, std::string>>& factors,
+                               const std::vector<std::string>& factor_vars, std::string& err) {
+  if (factor_vars.size() != vars.size()) {
+    err = "the factors must be written over as many variables as the collection has";
+    return false;
+  }
+  if (base_functions_.empty() && !functions.empty()) {
+    // one function per OUTPUT from here on: duplicates may get different factors
+    for (size_t k = 0; k < n_out; ++k) base_functions_.push_back(functions[check_is_equal ? evaluation_positions[k] : k]);
+  }
+  std::vector<Function> nf = base_functions_;
+  std::unordered_map<std::string, uint32_t> fidx, saved;
+  for (uint32_t i = 0; i < factor_vars.size(); ++i) fidx.emplace(factor_vars[i], i);
+  for (const auto& fc : factors) {
+    if (fc.first >= nf.size()) {
+      err = "factor for output " + std::to_string(fc.first) + ": the collection returns " + std::to_string(nf.size()) + " values";
+      return false;
+    }
+    std::string text = fc.second;
+    text.erase(std::remove_if(text.begin(), text.end(), [](char c) { return c == ' ' || c == '\t' || c == '\n'; }), text.end());
+    Function g;
+    saved.swap(var_index);
+    var_index = fidx;
+    const bool ok = validate_expr(text, fc.first, err) && parse_expr(text, g.rpn, err) && build_tree(g, err);
+    var_index.swap(saved);
+    saved.clear();
+    if (!ok) return false;
+    Function& f = nf[fc.first];
+    const int32_t off = (int32_t)f.nodes.size();
+    const uint32_t lit_off = (uint32_t)f.literals.size();
+    for (Node nd : g.nodes) {
+      if (nd.l >= 0) nd.l += off;
+      if (nd.r >= 0) nd.r += off;
+      if (nd.kind == N_NUM) nd.lit += lit_off;
+      f.nodes.push_back(nd);
+    }
+    f.literals.insert(f.literals.end(), g.literals.begin(), g.literals.end());
+    Node div{};
+    div.kind = N_DIV;
+    div.l = f.root;
+    div.r = g.root + off;
+    div.is_const = f.nodes[div.l].is_const && f.nodes[div.r].is_const;
+    f.nodes.push_back(div);
+    f.root = (int32_t)f.nodes.size() - 1;
+    f.rpn.insert(f.rpn.end(), g.rpn.begin(), g.rpn.end());
+    f.rpn.emplace_back("/");
+    compute_needs(f);
+  }
+  functions.swap(nf);
+  check_is_equal = false;
+  evaluation_positions.clear();
   return finish(err);
 }
 

@@ -122,10 +122,16 @@ struct Collection {
   // recompute every constant for prime p and patch the tape (what prime_changed() ->
   // precompute_tokens() does in the reference, ShuntingYardParser.cpp:550-591)
   bool resolve(uint64_t p, std::string& err);
+  // divide output `first` by the function `second` (written over factor_vars, matched to vars by position) and
+  // rebuild the tape; replaces factors set earlier.  The prime has to be set again afterwards.
+  bool apply_factors(const std::vector<std::pair<uint32_t, std::string>>& factors,
+                     const std::vector<std::string>& factor_vars, std::string& err);
 
  private:
   bool add_function(std::string text, uint64_t index, bool strip_blanks, std::string& err);
   bool build_tree(Function& f, std::string& err);
+  static void compute_needs(Function& f);
+  std::vector<Function> base_functions_;      // one per output, before any factor was applied
   void emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots);
   bool check_function(uint32_t fn, uint64_t p, const uint64_t* point) const;
   std::vector<uint8_t> no_cse_fn_;

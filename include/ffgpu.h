@@ -94,6 +94,15 @@ void ffgpu_work(const ffgpu_tape*, uint64_t w[5]);
  * w[0]=instructions w[1]=modular multiplications w[2]=add/sub/neg w[3]=inversions w[4]=variable row reads */
 void ffgpu_tape_work(const ffgpu_tape*, uint64_t w[5]);
 
+/* Scanned factors: Reconstructor divides output i of the black box by parsed_factors[i].evaluate_pre(values)[0]
+ * after every evaluation (Reconstructor.hpp:3392-3396, 3449-3457; MPIWorker.hpp:486-495).  Here the division becomes
+ * part of function out_index[k] on the device: out = f / factor with FFInt's a/0 = 0.  The factor expressions are
+ * written over factor_vars (FireFly uses x1..xn, ParserUtils.cpp:182-185), matched to the collection's variables by
+ * position.  Replaces factors set earlier (n_factors = 0 removes them); needs quiescence; ffgpu_set_prime must be
+ * called again afterwards. */
+int ffgpu_set_factors(ffgpu_tape*, const uint32_t* out_index, const char* const* factors, size_t n_factors,
+                      const char* const* factor_vars, size_t n_factor_vars);
+
 /* ---- prime -------------------------------------------------------------------------------- */
 /* p must be a prime of the form 2^63 - c, 0 < c < 2^15 (all 300 primes of FireFly's table are). */
 int ffgpu_set_prime(ffgpu_tape*, uint64_t p);

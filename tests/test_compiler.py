@@ -292,3 +292,36 @@ def test_fused_and_plain_tapes_agree(oracle, cse, fuse):
     ops = {ff.OPS[o] for o in par.tape()["op"]}
     assert ({"TERM", "MULADD", "ADDVARS", "MULVARS"} <= ops) == fuse
     assert np.array_equal(interp(par, pts, p), want)
+
+
+def test_scanned_factors_join_the_tape(oracle):
+    """out_i = f_i / factor_i (Reconstructor.hpp:3449-3457), factors written over x1..xn"""
+    funs = ["(a+b)^3*(a-2*b)", "a*b+c", "a*b+c", "7"]
+    vars_ = ["a", "b", "c"]
+    p = ff.primes()[4]
+    par = ff.GpuParser(None, funs, vars_, check_is_equal=True)
+    assert par.n_functions == 3 and par.n_out == 4
+    par.set_factors({0: "(x1+x2)^2/(x3-1)", 2: "x1*x2+x3"}, ["x1", "x2", "x3"])
+    assert par.n_out == 4 and par.n_functions == 4         # duplicates got different factors
+    par.set_prime(p)
+    pts = ff.synthetic_points(3, 7, p, seed=2)
+    pts[:, 0] = np.array([1, p - 1, 5], dtype=np.uint64)    # a + b = 0: the factor of output 0 vanishes -> 0
+    pts[:, 1] = np.array([3, 4, 1], dtype=np.uint64)        # c - 1 = 0 inside the factor
+    base = oracle.parse(funs, vars_, p).eval(pts)
+    fac = oracle.parse(["(x1+x2)^2/(x3-1)", "x1*x2+x3"], ["x1", "x2", "x3"], p).eval(pts)
+    inv = lambda x: pow(int(x), p - 2, p)
+    want = base.copy()
+    want[0] = [int(b) * inv(f) % p for b, f in zip(base[0], fac[0])]
+    want[2] = [int(b) * inv(f) % p for b, f in zip(base[2], fac[1])]
+    assert np.array_equal(interp(par, pts, p), want)
+    assert par.get_rp_function(0)[-1] == "/"
+    # replacing and removing
+    par.set_factors({}, ["x1", "x2", "x3"])
+    par.set_prime(p)
+    assert np.array_equal(interp(par, pts, p), base)
+    with pytest.raises(ff.FFGpuError, match="returns 4 values"):
+        par.set_factors({9: "x1"}, ["x1", "x2", "x3"])
+    with pytest.raises(ff.FFGpuError, match="not declared"):
+        par.set_factors({0: "a"}, ["x1", "x2", "x3"])
+    with pytest.raises(ff.FFGpuError, match="as many variables"):
+        par.set_factors({0: "x1"}, ["x1"])

@@ -470,3 +470,31 @@ def test_mpi_wire_format(ctx, oracle):
     assert np.array_equal(res[:, 1:].T, oracle.parse(g["functions"], g["vars"], p).eval(pts))
     with pytest.raises(ValueError, match="Corrupted"):
         par.evaluate_wire(np.zeros(7, dtype=np.uint64))
+
+
+def test_scanned_factors_on_device(ctx, oracle):
+    """ffgpu_set_factors: out_i = f_i / factor_i evaluated inside the tape (Reconstructor.hpp:3449-3457)"""
+    g = load_golden("s_y_4_v")
+    p = ff.primes()[6]
+    par = ff.GpuParser(ctx, g["functions"], g["vars"])
+    par.set_prime(p)
+    pts = ff.synthetic_points(4, 1500, p, seed=23)
+    pts[:, 3] = np.array([1, p - 1, 0, 0], dtype=np.uint64)          # x1 + x2 = 0: factor of output 2 vanishes
+    base = oracle.parse(g["functions"], g["vars"], p).eval(pts)
+    assert np.array_equal(par.evaluate_pre(pts), base)
+    facs = {2: "(x1+x2)*(x3^2+1)", 5: "x4/(x1-x2)", 18: "3"}
+    fvars = ["x1", "x2", "x3", "x4"]
+    par.set_factors(facs, fvars)
+    with pytest.raises(ff.FFGpuError, match="set_prime"):
+        par.evaluate_pre(pts)
+    par.set_prime(p)
+    got = par.evaluate_pre(pts)
+    fv = oracle.parse(list(facs.values()), fvars, p).eval(pts)
+    want = base.copy()
+    for row, i in enumerate(facs):
+        want[i] = [int(b) * pow(int(f), p - 2, p) % p for b, f in zip(base[i], fv[row])]
+    assert np.array_equal(got, want)
+    par.set_factors({}, fvars)
+    par.set_prime(p)
+    assert np.array_equal(par.evaluate_pre(pts), base)
+    par.close()
