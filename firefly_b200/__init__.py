@@ -26,7 +26,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libffgpu.so")
+LIB_PATH = os.environ.get("FFGPU_LIB") or os.path.join(_HERE, "lib", "libffgpu.so")   # FFGPU_LIB: A/B builds
 
 INSTR_DTYPE = np.dtype(
     [("op", "u1"), ("src", "u1"), ("flags", "u1"), ("fast", "u1"), ("arg", "<u4"), ("imm", "<u8")]
