@@ -1512,7 +1512,7 @@ bool Collection::resolve(uint64_t p, std::string& err) {
     in.imm = w;
     // the fast dispatch code of a literal power covers exponents below p/2 only (FFInt::pow's direct branch);
     // a residue above that means a negative power and takes the general code (inversion first)
-    if (in.op == OP_POWU && !(in.flags & ~0)) in.fast = (w < (p >> 1) && in.flags == 0) ? FX_POWU : FX_GENERIC;
+    if (in.op == OP_POWU) in.fast = (w < (p >> 1) && in.flags == 0) ? FX_POWU : FX_GENERIC;
   }
   prime = p;
   return true;
