@@ -325,3 +325,12 @@ def test_scanned_factors_join_the_tape(oracle):
         par.set_factors({0: "a"}, ["x1", "x2", "x3"])
     with pytest.raises(ff.FFGpuError, match="as many variables"):
         par.set_factors({0: "x1"}, ["x1"])
+
+
+def test_cpp_headers_compile():
+    """include/ffgpu.h is plain C, include/firefly_gpu/GpuProbeQueue.hpp stands alone as C++14"""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-x", "c", os.path.join(inc, "ffgpu.h")], check=True)
+    subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-Wall", "-x", "c++",
+                    os.path.join(inc, "firefly_gpu", "GpuProbeQueue.hpp")], check=True)
