@@ -119,6 +119,7 @@ struct ffgpu_tape {
   std::vector<uint32_t*> d_chunks;     // per device: Collection::chunk_table
   int force_k = 0, force_threads = 0;
   size_t chunk = 0;
+  bool needs_generic = true;           // the resolved tape has instructions without a fast dispatch code
 };
 
 namespace {
@@ -168,7 +169,7 @@ int launch(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, siz
   prm.n_slots = c.n_slots;
   prm.n_instr = (uint32_t)(c.tape.size() - 2);
   const ffgpu::LaunchShape sh = ffgpu::choose_shape(n_points, c.n_slots, t->ctx->devs[g].sm_count, t->force_k,
-                                                    t->force_threads, c.max_chunks);
+                                                    t->force_threads, c.max_chunks, !t->needs_generic);
   prm.chunk_bounds = nullptr;
   if (sh.chunks > 1) {
     unsigned idx = 0;
@@ -364,6 +365,8 @@ int ffgpu_set_prime(ffgpu_tape* t, uint64_t p) {
     return fail("unsupported prime " + std::to_string(p) + ": need p = 2^63 - c with 0 < c < 2^15");
   std::string err;
   if (!t->col.resolve(p, err)) return fail(err);
+  t->needs_generic = false;
+  for (const ffgpu::Instr& in : t->col.tape) t->needs_generic |= in.fast == ffgpu::FX_GENERIC && in.op != ffgpu::OP_HALT;
   const size_t bytes = t->col.tape.size() * sizeof(ffgpu::Instr);
   for (size_t g = 0; t->ctx && g < t->ctx->devs.size(); ++g) {
     DeviceGuard guard(t->ctx->devs[g].id);

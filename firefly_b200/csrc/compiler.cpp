@@ -1208,7 +1208,7 @@ void Collection::peephole() {
         case OP_LOAD:
           if (in.src == SRC_VAR) fx = push ? FX_PUSH_LOAD_VAR : FX_LOAD_VAR;
           else if (in.src == SRC_CONST) fx = push ? FX_PUSH_LOAD_CONST : FX_LOAD_CONST;
-          else if (in.src == SRC_TMP && !push) fx = FX_LOAD_TMP;
+          else if (in.src == SRC_TMP) fx = push ? FX_PUSH_LOAD_TMP : FX_LOAD_TMP;
           break;
         case OP_ADD:
           fx = in.src == SRC_VAR ? FX_ADD_VAR : in.src == SRC_CONST ? FX_ADD_CONST : in.src == SRC_POP ? FX_ADD_POP :

@@ -29,10 +29,11 @@ struct LaunchShape {
   unsigned blocks;     // point tiles (grid.x)
   unsigned chunks;     // tape chunks (grid.y): blocks of a tile split the collection's functions
   size_t smem;
+  bool lean;           // kernel without the generic instructions, 64 registers at k = 8 (kernels.cu)
 };
 
 LaunchShape choose_shape(uint64_t n_points, uint32_t n_slots, int sm_count, int force_k, int force_threads,
-                         unsigned max_chunks);
+                         unsigned max_chunks, bool lean_ok);
 cudaError_t launch_eval(const EvalParams& prm, const LaunchShape& shape, cudaStream_t stream);
 
 // synthetic probe points, identical on host (bench/tests) and device:

@@ -83,7 +83,7 @@ enum Fast : uint8_t {
   FX_MUL_VAR, FX_MUL_CONST, FX_MUL_POP,
   FX_POWU, FX_INV, FX_STORE, FX_SQR,
   FX_SAVE, FX_ACCUM_INIT, FX_ACCUM_ADD, FX_ACCUM_SUB,
-  FX_LOAD_TMP, FX_ADD_TMP, FX_MUL_TMP,
+  FX_LOAD_TMP, FX_PUSH_LOAD_TMP, FX_ADD_TMP, FX_MUL_TMP,
   FX_TERM, FX_ACCUM2, FX_ADDVARS, FX_MULVARS, FX_MULADD,
   FX_COUNT
 };
