@@ -51,7 +51,7 @@ typedef struct ffgpu_tape ffgpu_tape;   /* a compiled collection, resident on ev
 enum {
   FFGPU_CHECK_IS_EQUAL = 1,   /* detect duplicate functions (ShuntingYardParser's check_is_equal) */
   FFGPU_NO_CSE = 2,           /* do not share equal sub-expressions inside a function (for A/B tests) */
-  FFGPU_NO_FUSE = 4,          /* do not fuse instruction runs into TERM / ACCUM2 / ADDVARS / MULVARS (for A/B tests) */
+  FFGPU_NO_FUSE = 4,          /* do not fuse instruction runs into TERM / MULADD / ACCUM2 / ADDVARS / MULVARS (for A/B tests) */
   FFGPU_TEMPS_SHIFT = 8       /* bits 8..11: temp slots per function for shared sub-expressions (0 = automatic) */
 };
 
