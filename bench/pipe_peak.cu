@@ -129,7 +129,9 @@ __device__ __forceinline__ u64 mul_l63_asm(u64 x, u64 y, u32 c) {
 
 // "b63" family: residues bounded below 2^63 + 2^32 (so both high words are <= 2^31): the two cross
 // products are summed inside one IMAD.WIDE (no overflow), fold 1 at 2^64 = d, fold 2 at 2^63 = c with
-// no conditional correction.  6 wide + 1 narrow multiplies, 11 adds/logic.
+// no conditional correction.  6 wide + 1 narrow multiplies, 11 adds/logic.  These are the FIRST forms, kept here
+// for the comparison: ptxas turns about three of their additions per product into IMAD.X (fma pipe).  What
+// ships is ff63::mul_b63 / sqr_b63 (variants 9 and 10 below).
 __device__ __forceinline__ u64 mul_b63(u64 x, u64 y, u32 c, u32 d) {
   u64 r;
   asm("{\n\t"
@@ -225,6 +227,8 @@ __global__ void __launch_bounds__(256) k_mm(u64* out, const u64* in, u32 c, int 
         if (VARIANT == 6) a[k] = sqr_b63(a[k], c, d);
         if (VARIANT == 7) a[k] = mul_b63(a[k], a[k], c, d);
         if (VARIANT == 8) a[k] = ff63::sqr_pm_dev(a[k], d);
+        if (VARIANT == 9) a[k] = ff63::mul_b63(a[k], b, c, d);        // shipped forms: nothing ptxas can move to the fma pipe
+        if (VARIANT == 10) a[k] = ff63::sqr_b63(a[k], c, d);
       }
     }
   }
@@ -241,7 +245,7 @@ static u64 host_mm(const u64* in, int lane, u32 c, int trips, int K, int variant
   u64 b = in[lane + 32] % p, r = 0;
   for (int k = 0; k < K; k++) {
     u64 a = (in[lane] + 977ULL * k) % p;
-    for (int t = 0; t < trips * 4; t++) a = (variant == 2 || variant == 6 || variant == 7 || variant == 8) ? (u64)(((u128)a * a) % p) : (u64)(((u128)a * b) % p);
+    for (int t = 0; t < trips * 4; t++) a = (variant == 2 || variant == 6 || variant == 7 || variant == 8 || variant == 10) ? (u64)(((u128)a * a) % p) : (u64)(((u128)a * b) % p);
     r ^= a;
   }
   return r;
@@ -365,6 +369,10 @@ int main(int argc, char** argv) {
   run_mm("sqr_via_mul_b63_k4", k_mm<4, 7>, 4, 7);
   run_mm("sqr_pm_dev_k4", k_mm<4, 8>, 4, 8);
   run_mm("mul_pm_dev_k8", k_mm<8, 3>, 8, 3);
+  run_mm("mul_b63_v2_k4", k_mm<4, 9>, 4, 9);
+  run_mm("mul_b63_v2_k8", k_mm<8, 9>, 8, 9);
+  run_mm("sqr_b63_v2_k4", k_mm<4, 10>, 4, 10);
+  run_mm("sqr_b63_v2_k8", k_mm<8, 10>, 8, 10);
 
   // occupancy sweep of the shipped multiplication: resident warps per SM limited through dynamic shared memory
   struct Occ { int k, warps; double gmm; };

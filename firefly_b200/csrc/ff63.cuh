@@ -21,7 +21,8 @@
 // The B200 integer path (measured, bench/pipe_peak.cu): IMAD.WIDE.U32 (32x32+64 -> 64) occupies
 // the fma-heavy pipe for 4 cycles per warp and blocks one ALU issue slot, a 32-bit IMAD 2 cycles,
 // IADD3 / LOP3 / SHF 2 cycles on the alu pipe.  One bounded multiplication is 6 wide + 1 narrow
-// multiplies and 11 add/logic instructions: 1134 G modular multiplications/s on the chip.
+// multiplies, one IMAD.X and 8 add/logic instructions placed on their pipes by hand (see the "b63" family
+// below): 1239 G modular multiplications/s on the chip, squarings 1280.
 #pragma once
 #include <cstdint>
 
@@ -262,79 +263,85 @@ FF63_D u64 sqr_pm_dev(u64 x, u32 d) {
 // Every value v satisfies v < B = 2^63 + 2^32 (so its high word is <= 2^31); canonical residues qualify.
 // Why: with both high words <= 2^31 the two cross products of a 64x64 multiplication sum to less than
 // 2^64, so they are accumulated INSIDE one IMAD.WIDE (no carry chain), the top product limb stays below
-// 2^30 + 1, and the second fold can be done at 2^63 = c with no conditional correction.  Measured on
-// B200 (bench/pipe_peak.cu, profiles/r01_pipe_peak_v1.json): 1134 G modmul/s against 1054 for the
-// unbounded form above (the adds, not the multiplies, were the limiter: IMAD.WIDE also blocks an ALU slot).
-//   mul: 6 IMAD.WIDE + 1 IMAD, 11 add/logic           result < 2^63 + 2^31
-//   sqr: 5 IMAD.WIDE + 1 IMAD, 13 add/logic           result < 2^63 + 2^31
-//   add: 7 add/logic + 1 IMAD                         result < 2^63 + 2^16
-//   sub: 9 add/logic + 1 IMAD                         result < 2^63 + 2^17
+// 2^30 + 1, and the second fold can be done at 2^63 = c with no conditional correction.
+//
+// The machine these forms are written for (bench/pipe_peak.cu, bench/modmul_forms.cu; profiles/r01_pipe_peak_v3.json,
+// r01_modmul_forms_v1.json): per warp and SM sub-partition an IMAD.WIDE holds the fma-heavy pipe for 4 cycles AND
+// the alu pipe for 2 (1 wide + 2 IADD3 take 6 cycles, 1 wide + 1 IMAD 6, 1 wide + 1 IADD3 4.2), +1.25 alu-side
+// when it has a 64-bit addend; any other IMAD* takes 2 fma cycles, IADD3 / LOP3 / SHF / SEL 2 alu cycles.  So
+//     fma = 4 W + 2 F      alu = 2 W + 1.25 W_acc + 2 A      time = max(fma, alu)
+// with W wide multiplies and the remaining instructions split into F (written as IMAD) and A (alu): what counts is
+// the instruction total 3 W + F + A, split evenly.  ptxas balances the two pipes by COUNT (an IMAD.WIDE counts
+// like an IADD3), turning movable additions into IMAD.X; the first b63 forms (6 W + 13.4 others: 32.8 cycles,
+// 1133 G/s) left that to ptxas.  The forms below have fewer instructions (6 W + 10) and fix the split themselves:
+//   * 64-bit accumulations run inside the multiplier, with its carry output where the sum can pass 2^64
+//     (mul.wide + add.cc.u64 fuse into IMAD.WIDE.U32 Rd, P, ...; mul.wide + addc.u64 into IMAD.WIDE.U32.X);
+//   * additions that must stay on the alu pipe are written so that no IMAD can express them: a consumed carry
+//     out (the always-zero carry of a top limb feeds the carry INPUT of the next IMAD.WIDE), three register
+//     operands, or two carry predicates (64-bit three-term sums become IADD3 Rd, P0, P1 / IADD3.X .., P0, P1);
+//   * additions meant for the fma pipe are written as madc.lo (IMAD.X);
+//   * the fold at bit 63 does not mask before it adds: top*c is added to the unmasked low 64 bits (mod 2^64) and
+//     bit 63 is flipped afterwards if it was set (x - 2^63 = x xor 2^63 mod 2^64): one LOP3.
+//   mul: 6 IMAD.WIDE, 1 IMAD, 1 IMAD.X, 8 alu: 30.05 cycles, 1239 G modmul/s (+9 %)
+//   sqr: 5 IMAD.WIDE, 1 IMAD, 1 IMAD.X, 1 IMAD.SHL, 9 alu: 29.08 cycles, 1280 G/s (+8.6 %; all-alu: 33.6)
+//   add / sub / neg: unchanged (1 IMAD + 7 / 9 / 6; ptxas moves two of the additions, which is the even split).
+// Results: mul, sqr < 2^63 + 2^32; add < 2^63 + 2^16; sub < 2^63 + 2^17.
 // c < 2^15 (all FireFly primes have c <= 13797), d = 2c.
 // Word-level forms: a residue travels as two separate 32-bit registers (lo, hi).  The interpreter keeps
 // its accumulators that way so that nothing but IMAD.WIDE's own result needs an aligned register pair --
 // with 64-bit accumulators ptxas copied both halves of every accumulator at each tape instruction
 // (16 IMAD.MOV per dispatch at 8 probes per thread, on the multiply pipe).
+//
+// x*y = t0 + 2^32 m + 2^64 t3  with t0 = x0 y0, m = x0 y1 + x1 y0 < 2^64, t3 = x1 y1 <= 2^62
+//     = t0 + 2^32 ml + d h     (mod p),  h = t3 + mh < 2^62 + 2^32
+//     = A + 2^32 (B + ml) + 2^64 cy,  A = (h0 d + t0) mod 2^64 with carry cy,  B = h1 d < 2^46
+// V = that value (< 2^80), T = V >> 32 = A1 + B + ml + 2^32 cy, top = V >> 63 = T >> 31 (< 2^17):
+// result = (V mod 2^63) + top c = ((V mod 2^64) + top c) xor (bit 63 of V), all mod 2^64.
+#define FF63_MUL_REGS \
+  ".reg .u32 ml,mh,tl,th,h0,h1,A0,A1,r1,top,cy,t,x;\n\t.reg .u64 t0,m,t3,A,B,U,U2,Z,T,X,hi;\n\t"
+// expects t0, ml, and the carry chain h0 = ... (add.cc) just before it; C, DD name the operands c, d
+#define FF63_MUL_TAIL(C, DD)                                                                          \
+  "addc.cc.u32 h1, th, 0;\n\t"              /* carry out always 0 ... */                              \
+  "mul.wide.u32 U2, h1, " DD ";\n\t"                                                                  \
+  "addc.u64 B, U2, 0;\n\t"                  /* ... and consumed here: IMAD.WIDE.U32.X */              \
+  "mul.wide.u32 U, h0, " DD ";\n\t"                                                                   \
+  "add.cc.u64 A, U, t0;\n\t"                /* IMAD.WIDE.U32 with carry out */                        \
+  "addc.u32 cy, 0, 0;\n\t"                                                                            \
+  "shr.u64 hi, A, 32;\n\t"                                                                            \
+  "mov.b64 Z, {ml,cy};\n\t"                                                                           \
+  "add.u64 T, B, hi;\n\t"                                                                             \
+  "add.u64 T, T, Z;\n\t"                    /* IADD3 with two carries out, IADD3.X with two carries in */ \
+  "shr.u64 X, T, 31;\n\t"                                                                             \
+  "cvt.u32.u64 top, X;\n\t"                                                                           \
+  "cvt.u32.u64 r1, T;\n\t"                                                                            \
+  "mov.b64 {A0,A1}, A;\n\t"                                                                           \
+  "mul.lo.u32 t, top, " C ";\n\t"           /* < 2^32 */                                              \
+  "add.cc.u32 %0, A0, t;\n\t"                                                                         \
+  "madc.lo.u32 x, r1, 1, 0;\n\t"            /* IMAD.X: this one runs on the fma pipe */               \
+  "lop3.b32 %1, x, r1, 0x80000000, 0x78;\n\t" /* x ^ (r1 & 0x80000000) */
 FF63_D void mul_b63_w(u32& o0, u32& o1, u32 x0, u32 x1, u32 y0, u32 y1, u32 c, u32 d) {
-  asm("{\n\t"
-      ".reg .u32 w0,w1,w2,w3,a,ml,mh,tl,th,u0,u1,v0,v1,r0,r1,r2,top,t;\n\t"
-      ".reg .u64 t0,m,t3,u,v;\n\t"
-      "mul.wide.u32 t0, %2, %4;\n\t"
+  asm("{\n\t" FF63_MUL_REGS
       "mul.wide.u32 m, %2, %5;\n\t"
       "mad.wide.u32 m, %3, %4, m;\n\t"          // < 2^64: both high words are <= 2^31
+      "mul.wide.u32 t0, %2, %4;\n\t"
       "mul.wide.u32 t3, %3, %5;\n\t"
-      "mov.b64 {w0,a}, t0;\n\t"
       "mov.b64 {ml,mh}, m;\n\t"
       "mov.b64 {tl,th}, t3;\n\t"
-      "add.cc.u32 w1, a, ml;\n\t"
-      "addc.cc.u32 w2, tl, mh;\n\t"
-      "addc.u32 w3, th, 0;\n\t"                 // w3 <= 2^30
-      // fold 1 at 2^64 = d: (w1:w0) + d*w2 + (d*w3 << 32)  ->  r2:r1:r0 with r2 <= 2^14 + 2
-      "mul.wide.u32 u, w2, %7;\n\t"
-      "mul.wide.u32 v, w3, %7;\n\t"
-      "mov.b64 {u0,u1}, u;\n\t"
-      "mov.b64 {v0,v1}, v;\n\t"
-      "add.cc.u32 r0, w0, u0;\n\t"
-      "addc.cc.u32 r1, w1, u1;\n\t"
-      "addc.u32 r2, v1, 0;\n\t"
-      "add.cc.u32 r1, r1, v0;\n\t"
-      "addc.u32 r2, r2, 0;\n\t"
-      // fold 2 at 2^63 = c: everything from bit 63 up (< 2^15 + 6) times c (< 2^31) onto the low 63 bits
-      "shf.l.wrap.b32 top, r1, r2, 1;\n\t"
-      "and.b32 r1, r1, 0x7fffffff;\n\t"
-      "mul.lo.u32 t, top, %6;\n\t"
-      "add.cc.u32 %0, r0, t;\n\t"
-      "addc.u32 %1, r1, 0;\n\t"
+      "add.cc.u32 h0, tl, mh;\n\t"
+      FF63_MUL_TAIL("%6", "%7")
       "}" : "=r"(o0), "=r"(o1) : "r"(x0), "r"(x1), "r"(y0), "r"(y1), "r"(c), "r"(d));
 }
 FF63_D void sqr_b63_w(u32& o0, u32& o1, u32 x0, u32 x1, u32 c, u32 d) {
-  asm("{\n\t"
-      ".reg .u32 w0,w1,w2,w3,a,ml,mh,tl,th,u0,u1,v0,v1,r0,r1,r2,top,t;\n\t"
-      ".reg .u64 t0,m,t3,u,v;\n\t"
-      "mul.wide.u32 t0, %2, %2;\n\t"
+  asm("{\n\t" FF63_MUL_REGS
       "mul.wide.u32 m, %2, %3;\n\t"             // < 2^63
+      "mul.wide.u32 t0, %2, %2;\n\t"
       "mul.wide.u32 t3, %3, %3;\n\t"
-      "mov.b64 {w0,a}, t0;\n\t"
       "mov.b64 {ml,mh}, m;\n\t"
       "mov.b64 {tl,th}, t3;\n\t"
-      "add.cc.u32 ml, ml, ml;\n\t"              // the cross product counts twice
-      "addc.u32 mh, mh, mh;\n\t"
-      "add.cc.u32 w1, a, ml;\n\t"
-      "addc.cc.u32 w2, tl, mh;\n\t"
-      "addc.u32 w3, th, 0;\n\t"
-      "mul.wide.u32 u, w2, %5;\n\t"
-      "mul.wide.u32 v, w3, %5;\n\t"
-      "mov.b64 {u0,u1}, u;\n\t"
-      "mov.b64 {v0,v1}, v;\n\t"
-      "add.cc.u32 r0, w0, u0;\n\t"
-      "addc.cc.u32 r1, w1, u1;\n\t"
-      "addc.u32 r2, v1, 0;\n\t"
-      "add.cc.u32 r1, r1, v0;\n\t"
-      "addc.u32 r2, r2, 0;\n\t"
-      "shf.l.wrap.b32 top, r1, r2, 1;\n\t"
-      "and.b32 r1, r1, 0x7fffffff;\n\t"
-      "mul.lo.u32 t, top, %4;\n\t"
-      "add.cc.u32 %0, r0, t;\n\t"
-      "addc.u32 %1, r1, 0;\n\t"
+      "shf.l.wrap.b32 mh, ml, mh, 1;\n\t"       // the cross product counts twice: high word on the alu pipe,
+      "mul.lo.u32 ml, ml, 2;\n\t"               // low word on the fma pipe (IMAD.SHL)
+      "add.cc.u32 h0, tl, mh;\n\t"
+      FF63_MUL_TAIL("%4", "%5")
       "}" : "=r"(o0), "=r"(o1) : "r"(x0), "r"(x1), "r"(c), "r"(d));
 }
 // a + b < 2^64 + 2^33: the carry and bit 63 together are worth (2k + b63) * c

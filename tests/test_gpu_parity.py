@@ -25,6 +25,11 @@ def _edge_values(p, rng, n):
             p >> 1, (p >> 1) + 1, (1 << 62), (1 << 62) - 1]
     vals = edge + [rng.randrange(BOUND) for _ in range(n)] + [rng.randrange(p) for _ in range(n)]
     vals += [BOUND - 1 - rng.randrange(1 << 20) for _ in range(n // 4)] + [(1 << 63) - rng.randrange(1 << 20) for _ in range(n // 4)]
+    # low words next to 2^32 and high words next to 2^31: x0*y0 + d*h0 passes 2^64 (the carry output of the
+    # multiplier in mul_b63_w / sqr_b63_w), the cross products reach their bound
+    vals += [(rng.randrange(1 << 31) << 32) | (0xFFFFFFFF - rng.randrange(1 << 12)) for _ in range(n // 4)]
+    vals += [((0x7FFFFFFF - rng.randrange(1 << 8)) << 32) | (0xFFFFFFFF - rng.randrange(1 << 8)) for _ in range(n // 4)]
+    vals += [(1 << 63) | (0xFFFFFFFF - rng.randrange(1 << 12)) for _ in range(n // 8)]
     return vals
 
 
