@@ -297,6 +297,11 @@ FF63_D u64 sqr_pm_dev(u64 x, u32 d) {
 //     = A + 2^32 (B + ml) + 2^64 cy,  A = (h0 d + t0) mod 2^64 with carry cy,  B = h1 d < 2^46
 // V = that value (< 2^80), T = V >> 32 = A1 + B + ml + 2^32 cy, top = V >> 63 = T >> 31 (< 2^17):
 // result = (V mod 2^63) + top c = ((V mod 2^64) + top c) xor (bit 63 of V), all mod 2^64.
+#ifdef FF63_CY_ALU
+#define FF63_CY "addc.u32 cy, 0, 0;\n\t"          /* SEL */
+#else
+#define FF63_CY "madc.lo.u32 cy, 0, 0, 0;\n\t"    /* IMAD.X */
+#endif
 #define FF63_MUL_REGS \
   ".reg .u32 ml,mh,tl,th,h0,h1,A0,A1,r1,top,cy,t,x;\n\t.reg .u64 t0,m,t3,A,B,U,U2,Z,T,X,hi;\n\t"
 // expects t0, ml, and the carry chain h0 = ... (add.cc) just before it; C, DD name the operands c, d
@@ -306,7 +311,7 @@ FF63_D u64 sqr_pm_dev(u64 x, u32 d) {
   "addc.u64 B, U2, 0;\n\t"                  /* ... and consumed here: IMAD.WIDE.U32.X */              \
   "mul.wide.u32 U, h0, " DD ";\n\t"                                                                   \
   "add.cc.u64 A, U, t0;\n\t"                /* IMAD.WIDE.U32 with carry out */                        \
-  "addc.u32 cy, 0, 0;\n\t"                                                                            \
+  FF63_CY                                                                                             \
   "shr.u64 hi, A, 32;\n\t"                                                                            \
   "mov.b64 Z, {ml,cy};\n\t"                                                                           \
   "add.u64 T, B, hi;\n\t"                                                                             \
