@@ -57,6 +57,18 @@ def measured_int_peak():
         return 148 * 64 * 1.965e9, "nominal 148 SM x 64 IMAD/clk x 1.965 GHz"
 
 
+def measured_modmul_peak():
+    """G modular multiplications/s of the shipped mul_b63 / sqr_b63 chains alone (bench/modmul_forms.cu): what the
+    arithmetic could do with no tape, no loads and no inversion around it"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_modmul_forms_v1.json")) as f:
+            d = json.load(f)
+        return {"mul": d["mul_x1h0d0"]["gmm_per_s"], "sqr": d["sqr_x1h0d1"]["gmm_per_s"],
+                "source": "profiles/r01_modmul_forms_v1.json (mul_x1h0d0, sqr_x1h0d1)"}
+    except Exception:
+        return None
+
+
 def measured_hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -492,6 +504,9 @@ def main():
                              "imad_frac": probes_per_s_top * w["executed_mm_eq"] * IMAD_PER_MM / peak_int,
                              "pipe_slot_frac": probes_per_s_top * w["executed_mm_eq"] * SLOTS_PER_MM / peak_int},
                 "peak_source": peak_src,
+                "modmul_ceiling": (lambda m: None if m is None else dict(
+                    m, executed_gmm_eq_per_s=probes_per_s_top * w["executed_mm_eq"] / 1e9,
+                    frac_of_mul_chain=probes_per_s_top * w["executed_mm_eq"] / 1e9 / m["mul"]))(measured_modmul_peak()),
                 "algorithmic": {"mm": w["mm"], "inv": w["inv"], "ma": w["ma"], "mm_eq_per_probe": mm_eq,
                                 "imad_per_mm": IMAD_PER_MM, "mm_per_inv": MM_PER_INV,
                                 "pipe_slots_per_mm": SLOTS_PER_MM},

@@ -1,0 +1,99 @@
+// b63_model.c -- word-level C model of the device multiplication and squaring (firefly_b200/csrc/ff63.cuh,
+// mul_b63_w / sqr_b63_w): the same steps with explicit widths, every "cannot overflow" claim of the PTX as an
+// assert, the result compared with (x*y) mod p from unsigned __int128 on edge and random operands below the
+// representation bound 2^63 + 2^32, including operands that force the carry output of the multiplier.
+// Test infrastructure (tests/test_arith_model.py compiles and runs it); not part of the product.
+// usage: b63_model [random cases per prime]
+#include <stdio.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <assert.h>
+typedef unsigned __int128 u128; typedef uint64_t u64; typedef uint32_t u32;
+static u64 P, Bnd = (1ULL<<63) + (1ULL<<32);
+static u32 c, d;
+static long n_carry = 0;
+static u64 W(u32 a, u32 b, u64 C, int cin, int* cout) { u128 s = (u128)a*b + C + cin; if (cout) *cout = (int)(s >> 64); else assert((s >> 64) == 0); return (u64)s; }
+static u64 mulN(u64 x, u64 y) {
+  u32 x0 = (u32)x, x1 = x >> 32, y0 = (u32)y, y1 = y >> 32;
+  u64 m = W(x0, y1, 0, 0, 0); m = W(x1, y0, m, 0, 0);
+  u64 t0 = W(x0, y0, 0, 0, 0), t3 = W(x1, y1, 0, 0, 0);
+  u32 ml = (u32)m, mh = m >> 32;
+  u64 h = t3 + mh; assert(h >= t3);
+  u32 h0 = (u32)h, h1 = h >> 32;
+  int cA; u64 A = W(h0, d, t0, 0, &cA);
+  u64 Bv = W(h1, d, 0, 0, 0);
+  u32 A0 = (u32)A, A1 = A >> 32;
+  u128 R = (u128)Bv + A1 + ml + ((u64)cA << 32); assert((R >> 64) == 0);
+  u32 r1 = (u32)R, r2 = (u32)(R >> 32);
+  u32 top = (r2 << 1) | (r1 >> 31); assert(r2 < (1u << 31));
+  // shipped form: add top*c to the UNMASKED low 64 bits mod 2^64, then flip bit 63 if it was set
+  u32 t = top * c; assert((u64)top * c < (1ULL << 32));
+  u32 o0 = A0 + t; u32 cyo = o0 < A0;
+  u32 xh = r1 + cyo;                                  // madc.lo x, r1, 1, 0
+  u32 o1 = xh ^ (r1 & 0x80000000u);
+  u64 res = ((u64)o1 << 32) | o0;
+  // reference form: mask, then add
+  u64 ref = W(top, c, ((u64)(r1 & 0x7fffffff) << 32) | A0, 0, 0);
+  assert(res == ref);
+  assert(res < Bnd);
+  n_carry += cA;
+  return res;
+}
+static u64 sqrN(u64 x) {
+  u32 x0 = (u32)x, x1 = x >> 32;
+  u64 m = W(x0, x1, 0, 0, 0); assert(m < (1ULL << 63));
+  u64 t0 = W(x0, x0, 0, 0, 0), t3 = W(x1, x1, 0, 0, 0);
+  m <<= 1;
+  u32 ml = (u32)m, mh = m >> 32;
+  u64 h = t3 + mh; assert(h >= t3);
+  u32 h0 = (u32)h, h1 = h >> 32;
+  int cA; u64 A = W(h0, d, t0, 0, &cA);
+  u64 Bv = W(h1, d, 0, 0, 0);
+  u32 A0 = (u32)A, A1 = A >> 32;
+  u128 R = (u128)Bv + A1 + ml + ((u64)cA << 32); assert((R >> 64) == 0);
+  u32 r1 = (u32)R, r2 = (u32)(R >> 32);
+  u32 top = (r2 << 1) | (r1 >> 31); assert(r2 < (1u << 31));
+  // shipped form: add top*c to the UNMASKED low 64 bits mod 2^64, then flip bit 63 if it was set
+  u32 t = top * c; assert((u64)top * c < (1ULL << 32));
+  u32 o0 = A0 + t; u32 cyo = o0 < A0;
+  u32 xh = r1 + cyo;                                  // madc.lo x, r1, 1, 0
+  u32 o1 = xh ^ (r1 & 0x80000000u);
+  u64 res = ((u64)o1 << 32) | o0;
+  // reference form: mask, then add
+  u64 ref = W(top, c, ((u64)(r1 & 0x7fffffff) << 32) | A0, 0, 0);
+  assert(res == ref);
+  assert(res < Bnd);
+  n_carry += cA;
+  return res;
+}
+static u64 rnd(void) { static u64 s = 88172645463325252ULL; s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; }
+int main(int argc, char** argv) {
+  const long n_random = argc > 1 ? atol(argv[1]) : 2000000;
+  u32 cs[] = {25, 165, 13797, 1, 32767};
+  long n = 0, ncA = 0;
+  for (int ci = 0; ci < 5; ci++) {
+    c = cs[ci]; d = 2*c; P = (1ULL<<63) - c;
+    u64 edge[] = {0,1,2,P-1,P,P+1,(1ULL<<63)-1,1ULL<<63,(1ULL<<63)+1,Bnd-1,Bnd-2,0xffffffffULL,0x100000000ULL,0x7fffffffffffffffULL,
+                  0x80000000ffffffffULL,0x7fffffff00000000ULL,0x7fffffffffff0000ULL,0xfffffffeULL,0x80000000fffffffeULL,0x7ffffffffffffffeULL, P-2, (P+1)/2, 0x00000000ffff0001ULL};
+    int ne = sizeof(edge)/sizeof(edge[0]);
+    for (int i = 0; i < ne; i++) for (int j = 0; j < ne; j++) {
+      u64 r = mulN(edge[i], edge[j]); assert(r % P == (u64)(((u128)edge[i] * edge[j]) % P));
+      if (i == j) { u64 s = sqrN(edge[i]); assert(s % P == r % P); }
+      n++;
+    }
+    for (long k = 0; k < n_random; k++) {
+      u64 x = rnd(), y = rnd();
+      int mode = k & 7;
+      if (mode == 1) { x |= 0xffff0000u; y |= 0xffff0000u; }          // low words near 2^32: exercises cA
+      if (mode == 2) { x |= 0xfffffff0u; y |= 0xfffffffeu; x |= 0x7fff000000000000ULL; y |= 0x7fffffff00000000ULL; }
+      if (mode == 3) { x = (x & 0xffffffffULL) | (1ULL << 63); }
+      x %= Bnd; y %= Bnd;
+      u64 r = mulN(x, y); assert(r % P == (u64)(((u128)x * y) % P));
+      u64 s = sqrN(x); assert(s % P == (u64)(((u128)x * x) % P));
+      n++;
+    }
+  }
+  printf("ok %ld cases, multiplier carry taken %ld times\n", n, n_carry);
+  if (n_carry == 0) return 3;
+  return 0;
+}
