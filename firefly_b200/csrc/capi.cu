@@ -11,6 +11,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <memory>
@@ -180,6 +181,15 @@ int launch(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, siz
   if (e != cudaSuccess) return cuda_fail(e, "launch_eval");
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
+}
+
+// small-call path: how much of the transfer the kernel does itself (FFGPU_SMALL_ZERO_COPY = 0 | 1 | 2)
+int small_zero_copy() {
+  static const int mode = [] {
+    const char* e = std::getenv("FFGPU_SMALL_ZERO_COPY");
+    return e && *e ? std::atoi(e) : 1;
+  }();
+  return mode;
 }
 
 int ensure(DevBuf& b, size_t need_in, size_t need_out) {
@@ -463,7 +473,7 @@ int eval_host(ffgpu_tape* t, const uint64_t* values, const uint64_t* line_a, con
         if (b.h_stage) FF_CUDA(cudaFreeHost(b.h_stage));
         b.h_stage = nullptr;
         b.cap_stage = 0;
-        FF_CUDA(cudaHostAlloc(&b.h_stage, std::max<size_t>(w_in + w_out, SMALL_WORDS + 64) * sizeof(uint64_t), cudaHostAllocPortable));
+        FF_CUDA(cudaHostAlloc(&b.h_stage, std::max<size_t>(w_in + w_out, SMALL_WORDS + 64) * sizeof(uint64_t), cudaHostAllocPortable | cudaHostAllocMapped));
         b.cap_stage = std::max<size_t>(w_in + w_out, SMALL_WORDS + 64);
       }
       uint64_t* h_in = b.h_stage;
@@ -472,9 +482,18 @@ int eval_host(ffgpu_tape* t, const uint64_t* values, const uint64_t* line_a, con
         std::memcpy(h_in + v * n_even, values + v * n_points, n_points * sizeof(uint64_t));
         if (n_even != n_points) h_in[v * n_even + n_points] = 0;
       }
-      if (n_vars) FF_CUDA(cudaMemcpyAsync(b.d_in, h_in, n_vars * n_even * sizeof(uint64_t), cudaMemcpyHostToDevice, b.stream));
-      if (launch(t, 0, b.d_in, n_even, n_even, b.d_out, n_even, b.stream)) return -1;
-      if (n_out) FF_CUDA(cudaMemcpyAsync(h_out, b.d_out, n_out * n_even * sizeof(uint64_t), cudaMemcpyDeviceToHost, b.stream));
+      // The staging buffer is pinned, mapped host memory (one address space with the device): the kernel can
+      // read the coordinates from it and write the results into it directly over PCIe, which saves a copy
+      // engine round trip each way.  zero_copy: 0 = copy both ways, 1 = results written by the kernel,
+      // 2 = coordinates read by the kernel as well.
+      const int zc = small_zero_copy();
+      const uint64_t* k_in = b.d_in;
+      uint64_t* k_out = b.d_out;
+      if (zc >= 2) k_in = h_in;
+      else if (n_vars) FF_CUDA(cudaMemcpyAsync(b.d_in, h_in, n_vars * n_even * sizeof(uint64_t), cudaMemcpyHostToDevice, b.stream));
+      if (zc >= 1) k_out = h_out;
+      if (launch(t, 0, k_in, n_even, n_even, k_out, n_even, b.stream)) return -1;
+      if (zc < 1 && n_out) FF_CUDA(cudaMemcpyAsync(h_out, b.d_out, n_out * n_even * sizeof(uint64_t), cudaMemcpyDeviceToHost, b.stream));
       FF_CUDA(cudaStreamSynchronize(b.stream));
       for (size_t f = 0; f < n_out; ++f) std::memcpy(out + f * n_points, h_out + f * n_even, n_points * sizeof(uint64_t));
       return 0;
