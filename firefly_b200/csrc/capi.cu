@@ -44,13 +44,14 @@ int cuda_fail(cudaError_t e, const char* what) {
   } while (0)
 
 constexpr int N_SLOTS = 8;        // concurrent ffgpu_eval callers served without contention
-constexpr int N_BUF = 2;          // double buffering per slot and device
+constexpr int N_BUF = 4;          // chunks in flight per slot and device (H2D / kernels / D2H of different chunks overlap)
 
 struct DevBuf {
   cudaStream_t stream = nullptr;
   uint64_t* d_in = nullptr;
   uint64_t* d_out = nullptr;
   uint64_t* d_as = nullptr;         // line mode: a[n_vars] then s[n_vars]
+  uint64_t* h_as = nullptr;         // pinned copy of a, s: uploaded once per call and buffer, asynchronously
   uint64_t* h_stage = nullptr;      // pinned: small calls travel as one contiguous copy each way
   size_t cap_in = 0, cap_out = 0, cap_as = 0, cap_stage = 0;   // elements
 };
@@ -261,6 +262,7 @@ void ffgpu_destroy(ffgpu_ctx* ctx) {
         if (b.d_in) cudaFree(b.d_in);
         if (b.d_out) cudaFree(b.d_out);
         if (b.d_as) cudaFree(b.d_as);
+        if (b.h_as) cudaFreeHost(b.h_as);
         if (b.h_stage) cudaFreeHost(b.h_stage);
         if (b.stream) cudaStreamDestroy(b.stream);
       }
@@ -508,7 +510,7 @@ int eval_host(ffgpu_tape* t, const uint64_t* values, const uint64_t* line_a, con
   if (!chunk) {
     // bytes that cross PCIe per point: the line form ships t only
     const size_t bytes_per_point = 8 * ((values ? n_vars : 1) + n_out);
-    chunk = std::max<size_t>(1 << 16, ((values ? 32u : 16u) << 20) / std::max<size_t>(bytes_per_point, 1));
+    chunk = std::max<size_t>(1 << 16, ((values ? 32u : 6u) << 20) / std::max<size_t>(bytes_per_point, 1));
   }
   chunk = std::min(chunk, per_dev);
   chunk = (chunk + 1) & ~(size_t)1;
@@ -536,14 +538,22 @@ int eval_host(ffgpu_tape* t, const uint64_t* values, const uint64_t* line_a, con
           if (b.cap_as < 2 * n_vars) {
             FF_CUDA(cudaStreamSynchronize(b.stream));
             if (b.d_as) FF_CUDA(cudaFree(b.d_as));
+            if (b.h_as) FF_CUDA(cudaFreeHost(b.h_as));
             b.d_as = nullptr;
+            b.h_as = nullptr;
             b.cap_as = 0;
             FF_CUDA(cudaMalloc(&b.d_as, 2 * n_vars * sizeof(uint64_t)));
+            FF_CUDA(cudaHostAlloc(&b.h_as, 2 * n_vars * sizeof(uint64_t), cudaHostAllocPortable));
             b.cap_as = 2 * n_vars;
           }
           uint64_t* d_t = b.d_in + chunk * n_vars;
-          FF_CUDA(cudaMemcpyAsync(b.d_as, line_a, n_vars * 8, cudaMemcpyHostToDevice, b.stream));
-          FF_CUDA(cudaMemcpyAsync(b.d_as + n_vars, line_s, n_vars * 8, cudaMemcpyHostToDevice, b.stream));
+          if (ci < (size_t)N_BUF) {
+            // first use of this buffer in this call: a and s go up once, from pinned memory (a copy from the
+            // caller's pageable arrays would synchronise the stream at every chunk and stall the pipeline)
+            std::memcpy(b.h_as, line_a, n_vars * 8);
+            std::memcpy(b.h_as + n_vars, line_s, n_vars * 8);
+            FF_CUDA(cudaMemcpyAsync(b.d_as, b.h_as, 2 * n_vars * 8, cudaMemcpyHostToDevice, b.stream));
+          }
           FF_CUDA(cudaMemcpyAsync(d_t, line_t + lo, cnt * 8, cudaMemcpyHostToDevice, b.stream));
           if (cnt_even != cnt) FF_CUDA(cudaMemsetAsync(d_t + cnt, 0, 8, b.stream));
           cudaError_t e = ffgpu::launch_line_points(b.d_in, d_t, b.d_as, b.d_as + n_vars, (uint32_t)n_vars, cnt_even,
