@@ -349,6 +349,47 @@ FF63_D void sqr_b63_w(u32& o0, u32& o1, u32 x0, u32 x1, u32 c, u32 d) {
       FF63_MUL_TAIL("%4", "%5")
       "}" : "=r"(o0), "=r"(o1) : "r"(x0), "r"(x1), "r"(c), "r"(d));
 }
+#ifdef FF63_ADD_ALU
+// all-alu forms of add / sub (nothing ptxas can turn into IMAD.X), kept for the A/B: S = a + b, top = S >> 63,
+// result = ((S mod 2^64) + top c) xor (bit 63 of S)
+FF63_D void add_b63_w(u32& o0, u32& o1, u32 a0, u32 a1, u32 b0, u32 b1, u32 c) {
+  asm("{\n\t"
+      ".reg .u32 s0,s1,k,top,t,x;\n\t.reg .u64 a,b,tt,S;\n\t"
+      "add.cc.u32 s0, %2, %4;\n\t"
+      "addc.cc.u32 s1, %3, %5;\n\t"
+      "addc.u32 k, 0, 0;\n\t"
+      "shf.l.wrap.b32 top, s1, k, 1;\n\t"
+      "mul.lo.u32 t, top, %6;\n\t"
+      "mov.b64 a, {%2,%3};\n\t"
+      "mov.b64 b, {%4,%5};\n\t"
+      "cvt.u64.u32 tt, t;\n\t"
+      "add.u64 S, a, b;\n\t"
+      "add.u64 S, S, tt;\n\t"
+      "mov.b64 {%0,x}, S;\n\t"
+      "lop3.b32 %1, x, s1, 0x80000000, 0x78;\n\t"
+      "}" : "=r"(o0), "=r"(o1) : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(c));
+}
+FF63_D void sub_b63_w(u32& o0, u32& o1, u32 a0, u32 a1, u32 b0, u32 b1, u32 c, u32 d) {
+  asm("{\n\t"
+      ".reg .u32 nd,m0,m1,s0,s1,k,top,t,x;\n\t.reg .u64 a,M,tt,S;\n\t"
+      "neg.s32 nd, %7;\n\t"
+      "sub.cc.u32 m0, nd, %4;\n\t"
+      "subc.cc.u32 m1, 0xffffffff, %5;\n\t"
+      "addc.cc.u32 s0, %2, m0;\n\t"
+      "addc.cc.u32 s1, %3, m1;\n\t"
+      "addc.u32 k, 0, 0;\n\t"
+      "shf.l.wrap.b32 top, s1, k, 1;\n\t"
+      "mul.lo.u32 t, top, %6;\n\t"
+      "mov.b64 a, {%2,%3};\n\t"
+      "mov.b64 M, {m0,m1};\n\t"
+      "cvt.u64.u32 tt, t;\n\t"
+      "add.u64 S, a, M;\n\t"
+      "add.u64 S, S, tt;\n\t"
+      "mov.b64 {%0,x}, S;\n\t"
+      "lop3.b32 %1, x, s1, 0x80000000, 0x78;\n\t"
+      "}" : "=r"(o0), "=r"(o1) : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(c), "r"(d));
+}
+#else
 // a + b < 2^64 + 2^33: the carry and bit 63 together are worth (2k + b63) * c
 FF63_D void add_b63_w(u32& o0, u32& o1, u32 a0, u32 a1, u32 b0, u32 b1, u32 c) {
   asm("{\n\t"
@@ -380,6 +421,7 @@ FF63_D void sub_b63_w(u32& o0, u32& o1, u32 a0, u32 a1, u32 b0, u32 b1, u32 c, u
       "addc.u32 %1, s1, 0;\n\t"
       "}" : "=r"(o0), "=r"(o1) : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(c), "r"(d));
 }
+#endif
 // -a = 2p - a, folded at bit 63 (-0 gives 2p -> p, a lazy zero)
 FF63_D void neg_b63_w(u32& o0, u32& o1, u32 a0, u32 a1, u32 c, u32 d) {
   asm("{\n\t"

@@ -5,8 +5,9 @@
 // operators it calls (source/FFInt.cpp:130-192) for ALL probe points of a batch at once.
 //
 // Mapping to the machine
-//   * one probe point per lane, K points per thread (independent multiply chains for ILP), 80 registers
-//     per thread at K = 8 so that three 256-thread blocks stay resident per SM;
+//   * one probe point per lane, K points per thread (independent multiply chains for ILP); at K = 8 the
+//     full build takes 80 registers (three resident 256-thread blocks per SM), the LEAN build -- tapes whose
+//     instructions all have a dense dispatch code, i.e. every benchmark function -- 64 (four blocks);
 //   * the accumulator of the tape machine (tape.hpp) is K residues of two 32-bit registers each;
 //     intermediate values are BOUNDED lazy residues (below 2^63 + 2^32, ff63.cuh) and are made
 //     canonical only where the reference's semantics need it: zero tests of divisors, lane
