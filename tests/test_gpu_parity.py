@@ -503,3 +503,35 @@ def test_scanned_factors_on_device(ctx, oracle):
     par.set_prime(p)
     assert np.array_equal(par.evaluate_pre(pts), base)
     par.close()
+
+
+# ---- small-call transfer modes (capi.cu, FFGPU_SMALL_ZERO_COPY) ----------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_small_call_transfer_modes(mode):
+    """Bunches of 1..129 points take the latency path; copying both ways, letting the kernel write the results into
+    mapped pinned memory (default) and letting it read the coordinates from there as well give the golden values."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, 'tests')\n"
+        "import firefly_b200 as ff\n"
+        "from conftest import load_golden\n"
+        "ctx = ff.Context()\n"
+        "for name in ('s_y_4_v', 'edge_cases'):\n"
+        "    g = load_golden(name)\n"
+        "    par = ff.GpuParser(ctx, g['functions'], g['vars'])\n"
+        "    for case in g['cases']:\n"
+        "        par.set_prime(case['prime'])\n"
+        "        for n in (1, 2, 3, case['points'].shape[1]):\n"
+        "            pts = np.ascontiguousarray(case['points'][:, :n])\n"
+        "            assert np.array_equal(par.evaluate_pre(pts), case['values'][:, :n]), (name, n)\n"
+        "        rep = np.ascontiguousarray(np.tile(case['points'], (1, 17))[:, :129])\n"
+        "        assert np.array_equal(par.evaluate_pre(rep), np.tile(case['values'], (1, 17))[:, :129]), name\n"
+        "print('ok')\n")
+    env = dict(os.environ, FFGPU_SMALL_ZERO_COPY=mode)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
