@@ -328,6 +328,7 @@ size_t ffgpu_stack_depth(const ffgpu_tape* t) { return t->col.stack_depth; }
 size_t ffgpu_n_temps(const ffgpu_tape* t) { return t->col.n_temps; }
 size_t ffgpu_n_slots(const ffgpu_tape* t) { return t->col.n_slots; }
 size_t ffgpu_cse_fallbacks(const ffgpu_tape* t) { return t->col.cse_fallbacks; }
+size_t ffgpu_n_structural_duplicates(const ffgpu_tape* t) { return t->col.n_structural_duplicates; }
 
 size_t ffgpu_rpn(const ffgpu_tape* t, size_t i, char* buf, size_t cap) {
   if (i >= t->col.functions.size()) return 0;

@@ -1042,6 +1042,69 @@ inline uint64_t splitmix64(uint64_t& s) {
 }
 }  // namespace
 
+// Structure of a function for duplicate detection ACROSS the functions of a collection: two independent 64-bit
+// fingerprints per node, bottom up (the node array is in post order); x+y and y+x, x*y and y*x are the same.
+// Equal fingerprints are confirmed by an exact comparison before anything is shared.
+namespace {
+struct Fp { uint64_t a, b; };
+inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ULL;
+  x ^= x >> 27; x *= 0x94D049BB133111EBULL;
+  return x ^ (x >> 31);
+}
+void fingerprints(const Function& f, std::vector<Fp>& fp) {
+  fp.resize(f.nodes.size());
+  for (size_t i = 0; i < f.nodes.size(); ++i) {
+    const Node& n = f.nodes[i];
+    Fp h;
+    if (n.kind == N_VAR || n.kind == N_NEGVAR) {
+      h.a = mix64(0x1000 + 2 * (uint64_t)n.var + (n.kind == N_NEGVAR));
+      h.b = mix64(h.a ^ 0x9E3779B97F4A7C15ULL);
+    } else if (n.kind == N_NUM) {
+      uint64_t x = 0xCBF29CE484222325ULL, y = 0x84222325CBF29CE4ULL;
+      for (unsigned char ch : f.literals[n.lit].text) {
+        x = (x ^ ch) * 0x100000001B3ULL;
+        y = mix64(y + ch);
+      }
+      h.a = mix64(x ^ 0x2000);
+      h.b = mix64(y ^ 0x3000);
+    } else {
+      Fp l = fp[n.l], r = fp[n.r];
+      if ((n.kind == N_ADD || n.kind == N_MUL) && (l.a > r.a || (l.a == r.a && l.b > r.b))) std::swap(l, r);
+      h.a = mix64(l.a * 0x9E3779B97F4A7C15ULL + mix64(r.a + 0x51 * (uint64_t)n.kind) + (uint64_t)n.kind);
+      h.b = mix64(r.b * 0xD6E8FEB86659FD93ULL + mix64(l.b ^ (0x77 * (uint64_t)n.kind)) + 3 * (uint64_t)n.kind);
+    }
+    fp[i] = h;
+  }
+}
+bool same_structure(const Function& f, const std::vector<Fp>& ff, const Function& g, const std::vector<Fp>& gf) {
+  std::vector<std::pair<int32_t, int32_t>> st{{f.root, g.root}};
+  while (!st.empty()) {
+    const auto [i, j] = st.back();
+    st.pop_back();
+    const Node& a = f.nodes[i];
+    const Node& b = g.nodes[j];
+    if (a.kind != b.kind || ff[i].a != gf[j].a || ff[i].b != gf[j].b) return false;
+    if (a.kind == N_VAR || a.kind == N_NEGVAR) {
+      if (a.var != b.var) return false;
+    } else if (a.kind == N_NUM) {
+      if (f.literals[a.lit].text != g.literals[b.lit].text) return false;
+    } else {
+      int32_t al = a.l, ar = a.r, bl = b.l, br = b.r;
+      if (a.kind == N_ADD || a.kind == N_MUL) {
+        // pair the children by fingerprint
+        auto less = [](const Fp& x, const Fp& y) { return x.a < y.a || (x.a == y.a && x.b < y.b); };
+        if (less(ff[ar], ff[al])) std::swap(al, ar);
+        if (less(gf[br], gf[bl])) std::swap(bl, br);
+      }
+      st.push_back({al, bl});
+      st.push_back({ar, br});
+    }
+  }
+  return true;
+}
+}  // namespace
+
 bool Collection::add_function(std::string text, uint64_t index, bool strip_blanks, std::string& err) {
   if (strip_blanks) {
     text.erase(std::remove_if(text.begin(), text.end(), [](char c) { return c == ' ' || c == '\t' || c == '\n'; }),
@@ -1080,6 +1143,27 @@ bool Collection::finish(std::string& err) {
   } else {
     for (size_t k = 0; k < functions.size(); ++k) slots[k].push_back((uint32_t)k);
   }
+  // Functions of equal structure are evaluated once and stored to all their outputs -- check_is_equal without
+  // the flag for what is equal as written (the flag compares VALUES at a random point, reference :125-140, and
+  // also finds functions that are equal only algebraically).
+  std::vector<int32_t> dup_of(functions.size(), -1);
+  n_structural_duplicates = 0;
+  if (enable_cse && functions.size() > 1) {
+    std::vector<std::vector<Fp>> fps(functions.size());
+    std::unordered_map<uint64_t, std::vector<uint32_t>> seen;
+    for (size_t i = 0; i < functions.size(); ++i) {
+      fingerprints(functions[i], fps[i]);
+      const Fp h = fps[i][functions[i].root];
+      auto& bucket = seen[h.a ^ mix64(h.b)];
+      for (uint32_t j : bucket)
+        if (same_structure(functions[i], fps[i], functions[j], fps[j])) { dup_of[i] = (int32_t)j; break; }
+      if (dup_of[i] < 0) { bucket.push_back((uint32_t)i); continue; }
+      auto& to = slots[dup_of[i]];
+      to.insert(to.end(), slots[i].begin(), slots[i].end());
+      slots[i].clear();
+      ++n_structural_duplicates;
+    }
+  }
   no_cse_fn_.assign(functions.size(), 0);
   cse_fallbacks = 0;
   for (int pass = 0; pass < 2; ++pass) {
@@ -1092,7 +1176,7 @@ bool Collection::finish(std::string& err) {
     fn_start.clear();
     for (size_t i = 0; i < functions.size(); ++i) {
       fn_start.push_back((uint32_t)tape.size());
-      emit_function((uint32_t)i, slots[i]);
+      if (dup_of[i] < 0) emit_function((uint32_t)i, slots[i]);      // a duplicate's outputs are stored by its twin
       count_work(functions[i]);
     }
     fn_start.push_back((uint32_t)tape.size());
@@ -1107,7 +1191,7 @@ bool Collection::finish(std::string& err) {
     for (auto& v : pt) v = 1 + splitmix64(seed) % (P0 - 1);
     bool again = false;
     for (size_t i = 0; i < functions.size(); ++i) {
-      if (check_function((uint32_t)i, P0, pt.data())) continue;
+      if (dup_of[i] >= 0 || check_function((uint32_t)i, P0, pt.data())) continue;
       if (pass == 1 || no_cse_fn_[i] || !enable_cse) {
         err = "internal error: the tape of function " + std::to_string(i) + " does not reproduce its expression";
         return false;

@@ -101,6 +101,7 @@ struct Collection {
   bool enable_fuse = true;                    // fuse frequent instruction runs (TERM, ACCUM2, ADDVARS, MULVARS)
   bool enable_cse = true;                     // share structurally equal sub-expressions
   uint32_t cse_fallbacks = 0;                 // functions emitted without sharing after a failed self-check
+  uint32_t n_structural_duplicates = 0;       // functions of equal structure: evaluated once, stored to all their outputs
   int temp_budget = 0;                        // temp slots per function (0: automatic, see FnEmitter)
   std::vector<uint32_t> fn_start;             // tape offset of every distinct function, then the end
   // chunk tables: for C = 1, 2, 4, ... the C + 1 offsets that cut the tape into C runs of whole

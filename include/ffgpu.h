@@ -81,6 +81,10 @@ size_t ffgpu_n_temps(const ffgpu_tape*);        /* temp slots per probe (shared 
 /* functions that failed the compiler's translation self-check with sharing on and were emitted as plain trees
  * (0 unless the sharing pass has a bug; a function failing as a plain tree too makes ffgpu_compile fail) */
 size_t ffgpu_cse_fallbacks(const ffgpu_tape*);
+/* functions whose expression is structurally equal to an earlier one of the collection (x+y and y+x are equal):
+ * evaluated once, the value stored to every output -- what check_is_equal (reference ShuntingYardParser.cpp:125-140)
+ * finds for functions equal AS WRITTEN, without the flag; FFGPU_NO_CSE turns it off */
+size_t ffgpu_n_structural_duplicates(const ffgpu_tape*);
 size_t ffgpu_n_slots(const ffgpu_tape*);        /* shared-memory slots per probe the kernel reserves (spill + temps) */
 /* RPN of distinct function i, tokens joined by ' '; returns the length needed (without NUL) */
 size_t ffgpu_rpn(const ffgpu_tape*, size_t i, char* buf, size_t cap);

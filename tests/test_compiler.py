@@ -334,3 +334,55 @@ def test_cpp_headers_compile():
     subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-x", "c", os.path.join(inc, "ffgpu.h")], check=True)
     subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-Wall", "-x", "c++",
                     os.path.join(inc, "firefly_gpu", "GpuProbeQueue.hpp")], check=True)
+
+
+# ---- functions of equal structure are evaluated once (sharing ACROSS functions) -----------------------
+def test_structural_duplicates_are_evaluated_once(oracle):
+    vars_ = ["x", "y", "z"]
+    funs = ["(x+y)*z/(x-3)",            # 0
+            "x^2+y",                    # 1
+            "z*(y+x)/(x-3)",            # 2: = 0 with both commutative operands swapped
+            "(x+y)*z/(x-4)",            # 3: differs in a literal
+            "y+x^2",                    # 4: = 1
+            "(x+y)*z/(x-3)",            # 5: = 0 verbatim
+            "(x-y)*z/(x-3)",            # 6: subtraction does not commute with 7
+            "(y-x)*z/(x-3)",            # 7
+            "x^2+y+0"]                  # 8: equal in value to 1, not in structure
+    p = ff.primes()[1]
+    pts = ff.synthetic_points(3, 9, p, seed=5)
+    pts[:, 0] = np.array([3, 1, 2], dtype=np.uint64)        # x - 3 = 0: a/0 = 0 on every twin alike
+    want = oracle.parse(funs, vars_, p).eval(pts)
+    par = ff.GpuParser(None, funs, vars_)
+    par.set_prime(p)
+    assert par.n_structural_duplicates == 3                  # 2, 4, 5
+    assert par.n_functions == len(funs) and par.n_out == len(funs)
+    assert np.array_equal(interp(par, pts, p), want)
+    # prime change keeps the sharing and the values
+    p2 = ff.primes()[7]
+    par.set_prime(p2)
+    pts2 = ff.synthetic_points(3, 4, p2, seed=6)
+    assert np.array_equal(interp(par, pts2, p2), oracle.parse(funs, vars_, p2).eval(pts2))
+    plain = ff.GpuParser(None, funs, vars_, cse=False)
+    plain.set_prime(p)
+    assert plain.n_structural_duplicates == 0 and plain.n_instr > par.n_instr
+    assert np.array_equal(interp(plain, pts, p), want)
+    # together with check_is_equal (duplicates by VALUE are removed first; what is left has no structural twin)
+    chk = ff.GpuParser(None, funs, vars_, check_is_equal=True)
+    chk.set_prime(p)
+    assert chk.n_out == len(funs) and chk.n_functions < len(funs)
+    assert np.array_equal(interp(chk, pts, p), want)
+
+
+def test_structural_duplicates_with_scanned_factors(oracle):
+    """a factor divides ONE output: twins stop being twins, the values stay right"""
+    vars_ = ["x", "y"]
+    funs = ["x*y+1", "y*x+1", "x*y+1"]
+    p = ff.primes()[0]
+    par = ff.GpuParser(None, funs, vars_)
+    assert par.n_structural_duplicates == 2
+    par.set_factors({1: "x1+5"}, ["x1", "x2"])
+    par.set_prime(p)
+    assert par.n_structural_duplicates == 1
+    pts = ff.synthetic_points(2, 5, p, seed=9)
+    want = oracle.parse(["x*y+1", "(y*x+1)/(x+5)", "x*y+1"], vars_, p).eval(pts)
+    assert np.array_equal(interp(par, pts, p), want)

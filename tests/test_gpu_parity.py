@@ -535,3 +535,23 @@ def test_small_call_transfer_modes(mode):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_structural_duplicates_on_device(ctx, oracle):
+    """functions of equal structure are evaluated once and stored to every output (tests/test_compiler.py has the
+    host-side twin of this test)"""
+    vars_ = ["x", "y", "z"]
+    base = ["(x+y)*z/(x-3)", "x^2+y", "z*(y+x)/(x-3)", "(x+y)*z/(x-4)", "y+x^2", "(x+y)*z/(x-3)", "(x-y)*z/(x-3)"]
+    funs = base * 40                                   # 280 outputs, 4 distinct structures: also crosses tape chunks
+    p = ff.primes()[2]
+    par = ff.GpuParser(ctx, funs, vars_)
+    par.set_prime(p)
+    assert par.n_structural_duplicates == len(funs) - 4
+    for n in (1, 7, 4096, 70001):
+        pts = ff.synthetic_points(3, n, p, seed=n)
+        pts[0, 0] = 3
+        sel = np.unique(np.concatenate([np.arange(min(n, 64)), np.arange(0, n, max(1, n // 97)), [n - 1]]))
+        got = par.evaluate_pre(pts)[:, sel]
+        assert np.array_equal(got, oracle.parse(funs, vars_, p).eval(np.ascontiguousarray(pts[:, sel]))), n
+    par.close()
