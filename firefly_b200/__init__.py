@@ -40,6 +40,7 @@ TM_LOAD, TM_ADD, TM_SUB, TM_RSUB, TM_MUL = 0, 1, 2, 3, 4
 CHECK_IS_EQUAL = 1
 NO_CSE = 2
 NO_FUSE = 4
+NO_CROSS = 16
 
 
 class FFGpuError(RuntimeError):
@@ -73,6 +74,7 @@ def _load() -> C.CDLL:
         "ffgpu_n_slots": (C.c_size_t, [C.c_void_p]),
         "ffgpu_cse_fallbacks": (C.c_size_t, [C.c_void_p]),
         "ffgpu_n_structural_duplicates": (C.c_size_t, [C.c_void_p]),
+        "ffgpu_n_shared_denominators": (C.c_size_t, [C.c_void_p]),
         "ffgpu_rpn": (C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
         "ffgpu_get_tape": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t]),
         "ffgpu_work": (None, [C.c_void_p, u64p]),
@@ -125,7 +127,7 @@ lib = _load()
 EXPORTS = [
     "ffgpu_create", "ffgpu_destroy", "ffgpu_n_devices", "ffgpu_last_error", "ffgpu_compile", "ffgpu_compile_text",
     "ffgpu_compile_file", "ffgpu_tape_destroy", "ffgpu_n_vars", "ffgpu_n_functions", "ffgpu_n_out", "ffgpu_n_instr",
-    "ffgpu_stack_depth", "ffgpu_n_temps", "ffgpu_n_slots", "ffgpu_cse_fallbacks", "ffgpu_n_structural_duplicates", "ffgpu_rpn", "ffgpu_get_tape", "ffgpu_work", "ffgpu_tape_work", "ffgpu_set_factors", "ffgpu_set_prime", "ffgpu_get_prime",
+    "ffgpu_stack_depth", "ffgpu_n_temps", "ffgpu_n_slots", "ffgpu_cse_fallbacks", "ffgpu_n_structural_duplicates", "ffgpu_n_shared_denominators", "ffgpu_rpn", "ffgpu_get_tape", "ffgpu_work", "ffgpu_tape_work", "ffgpu_set_factors", "ffgpu_set_prime", "ffgpu_get_prime",
     "ffgpu_n_primes", "ffgpu_prime", "ffgpu_eval", "ffgpu_eval_line", "ffgpu_eval_wire", "ffgpu_eval_device", "ffgpu_host_alloc", "ffgpu_host_free",
     "ffgpu_queue_create", "ffgpu_queue_destroy", "ffgpu_queue_push", "ffgpu_queue_push_many", "ffgpu_queue_push_line",
     "ffgpu_queue_pop", "ffgpu_queue_pending", "ffgpu_queue_stats", "ffgpu_queue_error",
@@ -189,10 +191,10 @@ class GpuParser:
 
     def __init__(self, ctx: Optional[Context], functions=None, vars: Sequence[str] = (), check_is_equal: bool = False,
                  *, file: Optional[str] = None, text: Optional[str] = None, cse: bool = True,
-                 temps: int = 0, fuse: bool = True):
+                 temps: int = 0, fuse: bool = True, cross: bool = True):
         self.ctx = ctx
         ch = ctx.h if ctx is not None else None
-        flags = (CHECK_IS_EQUAL if check_is_equal else 0) | (0 if cse else NO_CSE) | (0 if fuse else NO_FUSE) | ((temps & 15) << 8)
+        flags = (CHECK_IS_EQUAL if check_is_equal else 0) | (0 if cse else NO_CSE) | (0 if fuse else NO_FUSE) | (0 if cross else NO_CROSS) | ((temps & 15) << 8)
         v = _strs(vars)
         if file is not None:
             self.h = lib.ffgpu_compile_file(ch, file.encode(), v, len(vars), flags)
@@ -256,6 +258,10 @@ class GpuParser:
     @property
     def n_structural_duplicates(self) -> int:
         return lib.ffgpu_n_structural_duplicates(self.h)
+
+    @property
+    def n_shared_denominators(self) -> int:
+        return lib.ffgpu_n_shared_denominators(self.h)
 
     @property
     def n_slots(self) -> int:

@@ -279,6 +279,7 @@ ffgpu_tape* ffgpu_compile(ffgpu_ctx* ctx, const char* const* functions, size_t n
   std::string err;
   t->col.enable_cse = !(flags & FFGPU_NO_CSE);
   t->col.enable_fuse = !(flags & FFGPU_NO_FUSE);
+  t->col.enable_cross = !(flags & FFGPU_NO_CROSS);
   t->col.temp_budget = (int)((flags >> FFGPU_TEMPS_SHIFT) & 15u);
   const bool ok = t->col.compile_strings(to_vec(functions, n_functions), to_vec(vars, n_vars),
                                          (flags & FFGPU_CHECK_IS_EQUAL) != 0, err);
@@ -291,6 +292,7 @@ ffgpu_tape* ffgpu_compile_text(ffgpu_ctx* ctx, const char* text, const char* con
   std::string err;
   t->col.enable_cse = !(flags & FFGPU_NO_CSE);
   t->col.enable_fuse = !(flags & FFGPU_NO_FUSE);
+  t->col.enable_cross = !(flags & FFGPU_NO_CROSS);
   t->col.temp_budget = (int)((flags >> FFGPU_TEMPS_SHIFT) & 15u);
   const bool ok = t->col.compile_text(text ? text : "", to_vec(vars, n_vars), (flags & FFGPU_CHECK_IS_EQUAL) != 0, err);
   return finish_compile(ctx, std::move(t), ok, err);
@@ -329,6 +331,7 @@ size_t ffgpu_n_temps(const ffgpu_tape* t) { return t->col.n_temps; }
 size_t ffgpu_n_slots(const ffgpu_tape* t) { return t->col.n_slots; }
 size_t ffgpu_cse_fallbacks(const ffgpu_tape* t) { return t->col.cse_fallbacks; }
 size_t ffgpu_n_structural_duplicates(const ffgpu_tape* t) { return t->col.n_structural_duplicates; }
+size_t ffgpu_n_shared_denominators(const ffgpu_tape* t) { return t->col.n_shared_denominators; }
 
 size_t ffgpu_rpn(const ffgpu_tape* t, size_t i, char* buf, size_t cap) {
   if (i >= t->col.functions.size()) return 0;

@@ -438,15 +438,26 @@ struct FnEmitter {
   bool slot_busy[MAX_TEMPS] = {};
   int max_temps = MAX_TEMPS;       // temp slots this function may use
   uint32_t depth = 0, max_depth = 0, temps_used = 0;
+  int32_t root;                    // what this emitter evaluates: the function's root, or only its numerator
+  std::vector<Instr> raw;          // instructions scheduled verbatim (EMIT items)
 
+  // den_mode: how the function's top-level division is served (Collection::finish, shared denominators)
+  //   DEN_NONE      the whole expression, as written
+  //   DEN_PRODUCE   1/D is computed once, parked in temp slot 0 for the functions that follow, then N * that
+  //   DEN_CONSUME   N * (temp slot 0): the function before this one has the same denominator
   FnEmitter(const Function& f_, uint32_t fn_, std::vector<Instr>& t, std::vector<ConstPatch>& p, bool cse,
-            int temp_budget)
+            int temp_budget, int den_mode = 0)
       : f(f_), fn(fn_), tape(t), patches(p), enable_cse(cse) {
+    root = den_mode == 2 ? f.nodes[f.root].l : f.root;
     // Spill and temp slots share the kernel's shared memory ([slot][probe][thread], 16 KB per slot at
     // 8 probes x 256 threads): more than SLOT_BUDGET slots per lane cost resident blocks.  Functions that
     // already spill deep get fewer temps; two are always allowed (co-evaluated sums need two).
     if (temp_budget > 0) max_temps = std::min(temp_budget, MAX_TEMPS);
-    else max_temps = std::max(2, std::min(MAX_TEMPS, SLOT_BUDGET - (int)f.nodes[f.root].need));
+    else max_temps = std::max(2, std::min(MAX_TEMPS, SLOT_BUDGET - (int)f.nodes[root].need));
+    if (den_mode) {
+      slot_busy[0] = true;         // temp slot 0 carries 1/D from function to function
+      temps_used = 1;                // it comes out of the function's own budget: the slot count (occupancy) stays
+    }
     build_dag();
   }
 
@@ -479,9 +490,9 @@ struct FnEmitter {
     }
     // references from distinct reachable parents
     std::vector<char> visited(n, 0);
-    std::vector<int32_t> st{rep[f.root]};
-    visited[rep[f.root]] = 1;
-    remaining[rep[f.root]] = 1;
+    std::vector<int32_t> st{rep[root]};
+    visited[rep[root]] = 1;
+    remaining[rep[root]] = 1;
     while (!st.empty()) {
       const int32_t u = st.back();
       st.pop_back();
@@ -603,7 +614,7 @@ struct FnEmitter {
     int32_t other;
     int32_t aux;
   };
-  enum { GEN, AFTER, APPLY_POP, APPLY_DIRECT, INVERT, POW_CONST, MUL_INVCONST, SQUARE, PRE, ACCUM, ADOPT, ADDPOP };
+  enum { GEN, AFTER, APPLY_POP, APPLY_DIRECT, INVERT, POW_CONST, MUL_INVCONST, SQUARE, PRE, ACCUM, ADOPT, ADDPOP, EMIT };
   std::vector<Item> work;
   // accumulate lists of co-evaluated sums: for ACCUM items
   struct Acc { int slot; bool minus; bool init; };
@@ -722,6 +733,34 @@ struct FnEmitter {
     for (size_t k = fwd.size(); k-- > 0;) work.push_back(fwd[k]);
   }
 
+  // ACC = N * (temp slot 0), the parked inverse of the denominator
+  void gen_consume() {
+    Instr m = mk(OP_MUL);
+    m.src = SRC_TMP;
+    m.arg = 0;
+    raw.push_back(m);
+    work.push_back(Item{EMIT, -1, false, false, -1, (int32_t)raw.size() - 1});
+    gen(root);
+  }
+  // temp slot 0 = 1/D (for this function and the ones after it), then ACC = N * that
+  void gen_produce() {
+    const Node& n = f.nodes[rep[root]];
+    const int32_t l = rep[n.l], r = rep[n.r];
+    --remaining[rep[root]];
+    Instr m = mk(OP_MUL);
+    m.src = SRC_TMP;
+    m.arg = 0;
+    raw.push_back(m);
+    Instr sv = mk(OP_SAVE);
+    sv.arg = 0;
+    raw.push_back(sv);
+    // reverse execution order
+    work.push_back(Item{EMIT, -1, false, false, -1, (int32_t)raw.size() - 2});
+    work.push_back(Item{GEN, l, false, false, -1, 0});
+    work.push_back(Item{EMIT, -1, false, false, -1, (int32_t)raw.size() - 1});
+    work.push_back(Item{INVERT, -1, false, false, -1, 0});
+    gen(r);
+  }
   void gen(int32_t root) {
     work.push_back(Item{GEN, root, false, false, -1, 0});
     while (!work.empty()) {
@@ -730,6 +769,7 @@ struct FnEmitter {
       switch (it.what) {
         case INVERT: put(mk(OP_INV)); continue;
         case SQUARE: put(mk(OP_SQR)); continue;
+        case EMIT: put(raw[it.aux]); continue;
         case APPLY_POP: apply(node(it.node), it.swap, true, -1); continue;
         case APPLY_DIRECT: apply(node(it.node), it.swap, false, it.other); continue;
         case POW_CONST: {
@@ -886,12 +926,14 @@ struct FnEmitter {
 };
 }  // namespace
 
-void Collection::emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots) {
+void Collection::emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots, int den_mode) {
   const size_t tape0 = tape.size(), patch0 = patches.size();
   for (int attempt = 0; attempt < 2; ++attempt) {
     const bool cse = enable_cse && !no_cse_fn_[fn];
-    FnEmitter em(functions[fn], fn, tape, patches, cse, temp_budget);
-    em.gen(functions[fn].root);
+    FnEmitter em(functions[fn], fn, tape, patches, cse, temp_budget, den_mode);
+    if (den_mode == 1) em.gen_produce();
+    else if (den_mode == 2) em.gen_consume();
+    else em.gen(functions[fn].root);
     if (em.failed && cse) {
       // the sharing pass lost track of a temp slot: emit this function as a plain tree instead
       tape.resize(tape0);
@@ -914,14 +956,14 @@ void Collection::emit_function(uint32_t fn, const std::vector<uint32_t>& out_slo
 
 // Translation check: run the emitted code of function fn on the host at one point and compare with the
 // value of its expression tree (eval_nodes).  The tape must be resolved for prime p.
-bool Collection::check_function(uint32_t fn, uint64_t p, const uint64_t* point) const {
+bool Collection::check_function(uint32_t fn, uint64_t p, const uint64_t* point, uint64_t* temps, bool* temp_set) const {
   std::vector<uint64_t> val;
   eval_nodes(functions[fn], p, point, val);
   const uint64_t want = val[functions[fn].root];
   uint64_t acc = 0;
   std::vector<uint64_t> stack;
-  uint64_t temps[16];
-  bool temp_set[16] = {};
+  // temps / temp_set (16 entries) belong to the caller: temp slot 0 can carry the inverse of a denominator from
+  // one function to the next (shared denominators), exactly as the shared-memory slot does on the device
   bool stored = false;
   for (uint32_t pc = fn_start[fn]; pc < fn_start[fn + 1]; ++pc) {
     const Instr& in = tape[pc];
@@ -1077,8 +1119,9 @@ void fingerprints(const Function& f, std::vector<Fp>& fp) {
     fp[i] = h;
   }
 }
-bool same_structure(const Function& f, const std::vector<Fp>& ff, const Function& g, const std::vector<Fp>& gf) {
-  std::vector<std::pair<int32_t, int32_t>> st{{f.root, g.root}};
+bool same_structure(const Function& f, const std::vector<Fp>& ff, int32_t fr, const Function& g, const std::vector<Fp>& gf,
+                    int32_t gr) {
+  std::vector<std::pair<int32_t, int32_t>> st{{fr, gr}};
   while (!st.empty()) {
     const auto [i, j] = st.back();
     st.pop_back();
@@ -1148,15 +1191,16 @@ bool Collection::finish(std::string& err) {
   // also finds functions that are equal only algebraically).
   std::vector<int32_t> dup_of(functions.size(), -1);
   n_structural_duplicates = 0;
-  if (enable_cse && functions.size() > 1) {
-    std::vector<std::vector<Fp>> fps(functions.size());
+  std::vector<std::vector<Fp>> fps;
+  if (enable_cse && enable_cross && functions.size() > 1) {
+    fps.resize(functions.size());
     std::unordered_map<uint64_t, std::vector<uint32_t>> seen;
     for (size_t i = 0; i < functions.size(); ++i) {
       fingerprints(functions[i], fps[i]);
       const Fp h = fps[i][functions[i].root];
       auto& bucket = seen[h.a ^ mix64(h.b)];
       for (uint32_t j : bucket)
-        if (same_structure(functions[i], fps[i], functions[j], fps[j])) { dup_of[i] = (int32_t)j; break; }
+        if (same_structure(functions[i], fps[i], functions[i].root, functions[j], fps[j], functions[j].root)) { dup_of[i] = (int32_t)j; break; }
       if (dup_of[i] < 0) { bucket.push_back((uint32_t)i); continue; }
       auto& to = slots[dup_of[i]];
       to.insert(to.end(), slots[i].begin(), slots[i].end());
@@ -1174,9 +1218,40 @@ bool Collection::finish(std::string& err) {
     n_slots = 0;
     work = WorkCount{};
     fn_start.clear();
+    // Shared denominators: a run of consecutive functions N_i / D over the same D (equal structure) inverts D once.
+    // The first function of the run parks 1/D in temp slot 0 (den_mode 1), the others multiply their numerator
+    // by it (den_mode 2) -- no denominator code, no inversion, no barrier.  a/0 = 0 is kept: 1/0 = 0 on the
+    // device (reference FFInt::operator/=).  A chunk of the tape never starts inside a run (chunk tables below).
+    den_mode_.assign(functions.size(), 0);
+    n_shared_denominators = 0;
+    if (enable_cse && !fps.empty()) {
+      auto divisor = [&](size_t i) -> int32_t {
+        const Function& f = functions[i];
+        const Node& rt = f.nodes[f.root];
+        if (no_cse_fn_[i] || rt.kind != N_DIV || rt.is_const || f.nodes[rt.r].is_const) return -1;
+        return rt.r;
+      };
+      int64_t head = -1;                        // first function of the current run
+      for (size_t i = 0; i < functions.size(); ++i) {
+        if (dup_of[i] >= 0) continue;           // emits nothing: transparent
+        const int32_t d = divisor(i);
+        bool joins = false;
+        if (head >= 0 && d >= 0) {
+          const int32_t dh = divisor((size_t)head);
+          joins = same_structure(functions[i], fps[i], d, functions[head], fps[head], dh);
+        }
+        if (joins) {
+          den_mode_[head] = 1;
+          den_mode_[i] = 2;
+          ++n_shared_denominators;
+        } else {
+          head = d >= 0 ? (int64_t)i : -1;
+        }
+      }
+    }
     for (size_t i = 0; i < functions.size(); ++i) {
       fn_start.push_back((uint32_t)tape.size());
-      if (dup_of[i] < 0) emit_function((uint32_t)i, slots[i]);      // a duplicate's outputs are stored by its twin
+      if (dup_of[i] < 0) emit_function((uint32_t)i, slots[i], den_mode_[i]);   // a duplicate's outputs are stored by its twin
       count_work(functions[i]);
     }
     fn_start.push_back((uint32_t)tape.size());
@@ -1190,8 +1265,10 @@ bool Collection::finish(std::string& err) {
     uint64_t seed = 0x243F6A8885A308D3ULL;
     for (auto& v : pt) v = 1 + splitmix64(seed) % (P0 - 1);
     bool again = false;
+    uint64_t chk_temps[16] = {};
+    bool chk_temp_set[16] = {};
     for (size_t i = 0; i < functions.size(); ++i) {
-      if (dup_of[i] >= 0 || check_function((uint32_t)i, P0, pt.data())) continue;
+      if (dup_of[i] >= 0 || check_function((uint32_t)i, P0, pt.data(), chk_temps, chk_temp_set)) continue;
       if (pass == 1 || no_cse_fn_[i] || !enable_cse) {
         err = "internal error: the tape of function " + std::to_string(i) + " does not reproduce its expression";
         return false;
@@ -1253,7 +1330,10 @@ bool Collection::finish(std::string& err) {
     for (unsigned k = 0; k < C; ++k) {
       const uint64_t target = (uint64_t)total * k / C;
       while (f + 1 < fn_start.size() && fn_start[f] < target) ++f;
-      chunk_table.push_back(fn_start[f]);
+      // a chunk starts with temp slot 0 undefined: back up to the function that fills it
+      size_t g = f;
+      while (g > 0 && g < functions.size() && (den_mode_[g] == 2 || dup_of[g] >= 0)) --g;
+      chunk_table.push_back(fn_start[g]);
     }
     chunk_table.push_back(total);
     max_chunks = C;

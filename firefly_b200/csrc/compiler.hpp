@@ -100,8 +100,10 @@ struct Collection {
                                               // (spill slots count up from 0, temp slots down from n_slots - 1)
   bool enable_fuse = true;                    // fuse frequent instruction runs (TERM, ACCUM2, ADDVARS, MULVARS)
   bool enable_cse = true;                     // share structurally equal sub-expressions
+  bool enable_cross = true;                   // ... and across functions: whole functions of equal structure, denominators
   uint32_t cse_fallbacks = 0;                 // functions emitted without sharing after a failed self-check
   uint32_t n_structural_duplicates = 0;       // functions of equal structure: evaluated once, stored to all their outputs
+  uint32_t n_shared_denominators = 0;         // functions that reuse the inverted denominator of the function before them
   int temp_budget = 0;                        // temp slots per function (0: automatic, see FnEmitter)
   std::vector<uint32_t> fn_start;             // tape offset of every distinct function, then the end
   // chunk tables: for C = 1, 2, 4, ... the C + 1 offsets that cut the tape into C runs of whole
@@ -133,8 +135,9 @@ struct Collection {
   bool build_tree(Function& f, std::string& err);
   static void compute_needs(Function& f);
   std::vector<Function> base_functions_;      // one per output, before any factor was applied
-  void emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots);
-  bool check_function(uint32_t fn, uint64_t p, const uint64_t* point) const;
+  void emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots, int den_mode);
+  bool check_function(uint32_t fn, uint64_t p, const uint64_t* point, uint64_t* temps, bool* temp_set) const;
+  std::vector<uint8_t> den_mode_;             // per function: 0 as written, 1 parks 1/D in temp slot 0, 2 uses it
   std::vector<uint8_t> no_cse_fn_;
   void count_work(const Function& f);
   void peephole();

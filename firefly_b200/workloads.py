@@ -55,11 +55,14 @@ BENCHMARKS = ["f1", "f2", "f3", "f4", "factors1", "factors2", "factors3", "facto
 
 
 def ibp_like_collection(n_functions: int = 10000, n_vars: int = 8, seed: int = 20200401,
-                        min_terms: int = 3, max_terms: int = 24):
+                        min_terms: int = 3, max_terms: int = 24, den_run: int = 0):
     """Config 4: random sparse rational functions shaped like IBP reduction coefficients --
     Horner-nested polynomials in a few of the variables with integer and rational coefficients,
     exponents up to 30, at most one division each (numerator / denominator).
-    -> (list of function strings, variable names).  Deterministic in (n_functions, n_vars, seed)."""
+    -> (list of function strings, variable names).  Deterministic in (n_functions, n_vars, seed, den_run).
+    den_run > 0: the coefficients come in runs of 1..den_run consecutive functions over the SAME denominator, the
+    way the coefficients of one integral share their denominator in a reduction table (den_run = 0: every
+    function has its own random denominator -- the collection all earlier measurements used)."""
     rng = random.Random(seed)
     names = [f"x{i}" for i in range(1, n_vars + 1)]
 
@@ -98,10 +101,17 @@ def ibp_like_collection(n_functions: int = 10000, n_vars: int = 8, seed: int = 2
         return "+".join(f"({p})" for p in parts)
 
     funs = []
+    left, den = 0, None
     for _ in range(n_functions):
         t = rng.randint(min_terms, max_terms)
         num = poly(t)
-        if rng.random() < 0.8:
+        if den_run > 0:
+            if left == 0:
+                left = rng.randint(1, den_run)
+                den = poly(max(min_terms, t // 2)) if rng.random() < 0.9 else None
+            left -= 1
+            funs.append(f"({num})/({den})" if den is not None else num)
+        elif rng.random() < 0.8:
             den = poly(max(min_terms, t // 2))
             funs.append(f"({num})/({den})")
         else:

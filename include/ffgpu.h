@@ -52,6 +52,7 @@ enum {
   FFGPU_CHECK_IS_EQUAL = 1,   /* detect duplicate functions (ShuntingYardParser's check_is_equal) */
   FFGPU_NO_CSE = 2,           /* do not share equal sub-expressions inside a function (for A/B tests) */
   FFGPU_NO_FUSE = 4,          /* do not fuse instruction runs into TERM / MULADD / ACCUM2 / ADDVARS / MULVARS (for A/B tests) */
+  FFGPU_NO_CROSS = 16,        /* do not share ACROSS functions: structural duplicates, shared denominators (for A/B tests) */
   FFGPU_TEMPS_SHIFT = 8       /* bits 8..11: temp slots per function for shared sub-expressions (0 = automatic) */
 };
 
@@ -85,6 +86,9 @@ size_t ffgpu_cse_fallbacks(const ffgpu_tape*);
  * evaluated once, the value stored to every output -- what check_is_equal (reference ShuntingYardParser.cpp:125-140)
  * finds for functions equal AS WRITTEN, without the flag; FFGPU_NO_CSE turns it off */
 size_t ffgpu_n_structural_duplicates(const ffgpu_tape*);
+/* functions N/D whose denominator has the structure of the denominator of the function before them: 1/D is
+ * computed once per run of such functions and kept in a temp slot (no denominator code, no inversion for the rest) */
+size_t ffgpu_n_shared_denominators(const ffgpu_tape*);
 size_t ffgpu_n_slots(const ffgpu_tape*);        /* shared-memory slots per probe the kernel reserves (spill + temps) */
 /* RPN of distinct function i, tokens joined by ' '; returns the length needed (without NUL) */
 size_t ffgpu_rpn(const ffgpu_tape*, size_t i, char* buf, size_t cap);

@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--shapes", default="4x256,4x512,8x128,8x256,2x256,2x512,4x128")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--ibp", type=int, default=0, help="also run an IBP-like collection with this many functions")
+    ap.add_argument("--den-run", type=int, default=0, help="IBP-like collection: runs of up to this many functions share a denominator")
+    ap.add_argument("--no-cross", action="store_true", help="no sharing across functions (A/B)")
     ap.add_argument("--temps", default="0", help="comma list of temp-slot budgets (0 = automatic, -1 = CSE off)")
     args = ap.parse_args()
     ctx = ff.Context()
@@ -39,11 +41,11 @@ def main():
         text, vars_ = W.benchmark(name)
         work.append((name, [text], vars_, n))
     if args.ibp:
-        funs, vars_ = W.ibp_like_collection(args.ibp, 8)
-        work.append((f"ibp{args.ibp}", funs, vars_, min(n, 1 << 16)))
+        funs, vars_ = W.ibp_like_collection(args.ibp, 8, den_run=args.den_run)
+        work.append((f"ibp{args.ibp}" + (f"r{args.den_run}" if args.den_run else ""), funs, vars_, min(n, 1 << 16)))
     work = [(f"{name}/t{t}", funs, vars_, npts, int(t)) for name, funs, vars_, npts in work for t in args.temps.split(",")]
     for name, funs, vars_, npts, temps in work:
-        par = ff.GpuParser(ctx, funs, vars_, cse=temps >= 0, temps=max(temps, 0))
+        par = ff.GpuParser(ctx, funs, vars_, cse=temps >= 0, temps=max(temps, 0), cross=not args.no_cross)
         par.set_prime(P0)
         print(f"{name}: {par.n_instr} instr, spill {par.stack_depth}, temps {par.n_temps}, slots {par.n_slots}", flush=True)
         w = par.work()

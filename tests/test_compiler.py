@@ -386,3 +386,41 @@ def test_structural_duplicates_with_scanned_factors(oracle):
     pts = ff.synthetic_points(2, 5, p, seed=9)
     want = oracle.parse(["x*y+1", "(y*x+1)/(x+5)", "x*y+1"], vars_, p).eval(pts)
     assert np.array_equal(interp(par, pts, p), want)
+
+
+def test_shared_denominators_are_inverted_once(oracle):
+    vars_ = ["x", "y", "z"]
+    D1, D2 = "(x*y-z^3+7)", "(z+x*(y-2))"
+    funs = [f"(x+1)/{D1}",                 # 0 run A: parks 1/D1
+            f"(y^2-z)/{D1}",               # 1 uses it
+            f"x/(7+(x*y-z^3))",            # 2 uses it: the sum is the same up to the order of its operands
+            "x*y+z",                       # 3 no division: ends the run
+            f"(x+1)/{D1}",                 # 4 = 0: evaluated once with 0
+            f"5/{D2}",                     # 5 run B
+            f"(x+y)*(x-y)/{D2}",           # 6
+            f"z/{D1}",                     # 7 run of one: as written
+            f"z/{D2}",                     # 8 run of one
+            "(x+1)/3",                     # 9 constant divisor: a multiplication
+            f"{D2}/{D2}",                  # 10 starts a run over D2 ...
+            f"1/{D2}"]                     # 11 ... and this one uses it
+    p = ff.primes()[4]
+    pts = ff.synthetic_points(3, 8, p, seed=11)
+    pts[:, 0] = np.array([1, 1, 2], dtype=np.uint64)        # D1 = 1 - 8 + 7 = 0: a/0 = 0 for the whole run
+    pts[:, 1] = np.array([2, 3, p - 2], dtype=np.uint64)    # D2 = p - 2 + 2 = 0
+    want = oracle.parse(funs, vars_, p).eval(pts)
+    par = ff.GpuParser(None, funs, vars_)
+    par.set_prime(p)
+    assert par.n_structural_duplicates == 1
+    assert par.n_shared_denominators == 4                   # 1, 2, 6, 11
+    assert par.cse_fallbacks == 0
+    assert np.array_equal(interp(par, pts, p), want)
+    n_inv = sum(1 for ins in par.tape() if ff.OPS[int(ins["op"])] == "INV")
+    assert n_inv == 5                                       # runs A, B, 7, 8, 10 -- not one per division
+    plain = ff.GpuParser(None, funs, vars_, cse=False)
+    plain.set_prime(p)
+    assert plain.n_shared_denominators == 0
+    assert np.array_equal(interp(plain, pts, p), want)
+    p2 = ff.primes()[9]
+    par.set_prime(p2)
+    pts2 = ff.synthetic_points(3, 5, p2, seed=12)
+    assert np.array_equal(interp(par, pts2, p2), oracle.parse(funs, vars_, p2).eval(pts2))

@@ -555,3 +555,29 @@ def test_structural_duplicates_on_device(ctx, oracle):
         got = par.evaluate_pre(pts)[:, sel]
         assert np.array_equal(got, oracle.parse(funs, vars_, p).eval(np.ascontiguousarray(pts[:, sel]))), n
     par.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("den_run", [3, 12])
+def test_shared_denominators_on_device(ctx, oracle, den_run):
+    """runs of functions over one denominator invert it once (temp slot 0 carries 1/D from function to function);
+    small batches cut the tape into many chunks (grid.y), which must never start inside a run"""
+    funs, vars_ = W.ibp_like_collection(700, 8, seed=77 + den_run, den_run=den_run)
+    funs = funs[:350] + funs[100:130] + funs[350:]            # and some structural duplicates in between
+    p = ff.primes()[5]
+    par = ff.GpuParser(ctx, funs, vars_)
+    par.set_prime(p)
+    assert par.n_shared_denominators > 100 and par.n_structural_duplicates >= 30 and par.cse_fallbacks == 0
+    orc = oracle.parse(funs, vars_, p)
+    for n in (1, 2, 5, 33, 300, 5000, 40001):
+        pts = ff.synthetic_points(8, n, p, seed=n)
+        sel = np.unique(np.concatenate([np.arange(min(n, 8)), np.arange(0, n, max(1, n // 13)), [n - 1]]))
+        got = par.evaluate_pre(pts)[:, sel]
+        assert np.array_equal(got, orc.eval(np.ascontiguousarray(pts[:, sel]))), n
+    # every launch shape, chunked and not
+    pts = ff.synthetic_points(8, 3000, p, seed=1)
+    want = orc.eval(np.ascontiguousarray(pts[:, :40]))
+    for k, th in [(1, 128), (2, 256), (4, 512), (8, 128), (8, 256)]:
+        par.set_launch(k, th)
+        assert np.array_equal(par.evaluate_pre(pts)[:, :40], want), (k, th)
+    par.close()
