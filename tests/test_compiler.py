@@ -424,3 +424,27 @@ def test_shared_denominators_are_inverted_once(oracle):
     par.set_prime(p2)
     pts2 = ff.synthetic_points(3, 5, p2, seed=12)
     assert np.array_equal(interp(par, pts2, p2), oracle.parse(funs, vars_, p2).eval(pts2))
+
+
+@pytest.mark.parametrize("den_run,temps,fuse,check", [(2, 0, True, False), (6, 1, True, False), (6, 2, False, False),
+                                                      (12, 0, True, True), (3, 3, False, True)])
+def test_cross_function_sharing_keeps_every_value(oracle, den_run, temps, fuse, check):
+    """shared denominators + structural duplicates + every other pass of the compiler, against the oracle"""
+    from firefly_b200 import workloads as W
+    funs, vars_ = W.ibp_like_collection(160, 5, seed=1000 + den_run, den_run=den_run, max_terms=12)
+    rng = random.Random(den_run)
+    for _ in range(20):                                     # duplicates, some inside runs
+        k = rng.randrange(len(funs))
+        funs.insert(rng.randrange(len(funs)), funs[k])
+    p = ff.primes()[den_run]
+    pts = ff.synthetic_points(5, 4, p, seed=den_run)
+    pts[:, 1] = 0
+    want = oracle.parse(funs, vars_, p, check_is_equal=check).eval(pts) if check else oracle.parse(funs, vars_, p).eval(pts)
+    par = ff.GpuParser(None, funs, vars_, check_is_equal=check, temps=temps, fuse=fuse)
+    par.set_prime(p)
+    assert par.cse_fallbacks == 0 and par.n_shared_denominators > 0
+    assert np.array_equal(interp(par, pts, p), want)
+    off = ff.GpuParser(None, funs, vars_, check_is_equal=check, temps=temps, fuse=fuse, cross=False)
+    off.set_prime(p)
+    assert off.n_shared_denominators == 0 and off.n_structural_duplicates == 0 and off.n_instr > par.n_instr
+    assert np.array_equal(interp(off, pts, p), want)
