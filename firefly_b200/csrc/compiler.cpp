@@ -965,7 +965,7 @@ bool Collection::check_function(uint32_t fn, uint64_t p, const uint64_t* point, 
   // temps / temp_set (16 entries) belong to the caller: temp slot 0 can carry the inverse of a denominator from
   // one function to the next (shared denominators), exactly as the shared-memory slot does on the device
   bool stored = false;
-  for (uint32_t pc = fn_start[fn]; pc < fn_start[fn + 1]; ++pc) {
+  for (uint32_t pc = fn_start[pos_of_[fn]]; pc < fn_start[pos_of_[fn] + 1]; ++pc) {
     const Instr& in = tape[pc];
     uint64_t b = 0;
     switch (in.op >= OP_TERM ? (uint8_t)SRC_NONE : in.src) {   // the fused forms decode their own operands
@@ -1208,6 +1208,32 @@ bool Collection::finish(std::string& err) {
       ++n_structural_duplicates;
     }
   }
+  // Evaluation order: functions over the same denominator are brought together (the group takes the place of its
+  // first member), so that a denominator that repeats anywhere in the collection is inverted once.  Outputs are
+  // addressed by their slot, the order of evaluation is free.  fn_start is indexed by POSITION in this order.
+  order_.resize(functions.size());
+  for (size_t i = 0; i < functions.size(); ++i) order_[i] = (uint32_t)i;
+  if (!fps.empty()) {
+    std::unordered_map<uint64_t, std::vector<uint32_t>> groups;
+    std::vector<uint64_t> key(functions.size(), 0);
+    for (size_t i = 0; i < functions.size(); ++i) {
+      const Function& f = functions[i];
+      const Node& rt = f.nodes[f.root];
+      if (dup_of[i] >= 0 || rt.kind != N_DIV || rt.is_const || f.nodes[rt.r].is_const) continue;
+      const Fp h = fps[i][rt.r];
+      key[i] = (h.a ^ mix64(h.b)) | 1;
+      groups[key[i]].push_back((uint32_t)i);
+    }
+    std::vector<char> placed(functions.size(), 0);
+    size_t pos = 0;
+    for (size_t i = 0; i < functions.size(); ++i) {
+      if (placed[i]) continue;
+      if (!key[i]) { order_[pos++] = (uint32_t)i; placed[i] = 1; continue; }
+      for (uint32_t j : groups[key[i]]) { order_[pos++] = j; placed[j] = 1; }
+    }
+  }
+  pos_of_.resize(functions.size());
+  for (size_t k = 0; k < order_.size(); ++k) pos_of_[order_[k]] = (uint32_t)k;
   no_cse_fn_.assign(functions.size(), 0);
   cse_fallbacks = 0;
   for (int pass = 0; pass < 2; ++pass) {
@@ -1232,7 +1258,8 @@ bool Collection::finish(std::string& err) {
         return rt.r;
       };
       int64_t head = -1;                        // first function of the current run
-      for (size_t i = 0; i < functions.size(); ++i) {
+      for (size_t k = 0; k < functions.size(); ++k) {
+        const size_t i = order_[k];
         if (dup_of[i] >= 0) continue;           // emits nothing: transparent
         const int32_t d = divisor(i);
         bool joins = false;
@@ -1249,7 +1276,8 @@ bool Collection::finish(std::string& err) {
         }
       }
     }
-    for (size_t i = 0; i < functions.size(); ++i) {
+    for (size_t k = 0; k < functions.size(); ++k) {
+      const size_t i = order_[k];
       fn_start.push_back((uint32_t)tape.size());
       if (dup_of[i] < 0) emit_function((uint32_t)i, slots[i], den_mode_[i]);   // a duplicate's outputs are stored by its twin
       count_work(functions[i]);
@@ -1267,7 +1295,8 @@ bool Collection::finish(std::string& err) {
     bool again = false;
     uint64_t chk_temps[16] = {};
     bool chk_temp_set[16] = {};
-    for (size_t i = 0; i < functions.size(); ++i) {
+    for (size_t k = 0; k < functions.size(); ++k) {
+      const size_t i = order_[k];
       if (dup_of[i] >= 0 || check_function((uint32_t)i, P0, pt.data(), chk_temps, chk_temp_set)) continue;
       if (pass == 1 || no_cse_fn_[i] || !enable_cse) {
         err = "internal error: the tape of function " + std::to_string(i) + " does not reproduce its expression";
@@ -1332,7 +1361,7 @@ bool Collection::finish(std::string& err) {
       while (f + 1 < fn_start.size() && fn_start[f] < target) ++f;
       // a chunk starts with temp slot 0 undefined: back up to the function that fills it
       size_t g = f;
-      while (g > 0 && g < functions.size() && (den_mode_[g] == 2 || dup_of[g] >= 0)) --g;
+      while (g > 0 && g < functions.size() && (den_mode_[order_[g]] == 2 || dup_of[order_[g]] >= 0)) --g;
       chunk_table.push_back(fn_start[g]);
     }
     chunk_table.push_back(total);

@@ -105,7 +105,7 @@ struct Collection {
   uint32_t n_structural_duplicates = 0;       // functions of equal structure: evaluated once, stored to all their outputs
   uint32_t n_shared_denominators = 0;         // functions that reuse the inverted denominator of the function before them
   int temp_budget = 0;                        // temp slots per function (0: automatic, see FnEmitter)
-  std::vector<uint32_t> fn_start;             // tape offset of every distinct function, then the end
+  std::vector<uint32_t> fn_start;             // tape offset of every distinct function IN EVALUATION ORDER, then the end
   // chunk tables: for C = 1, 2, 4, ... the C + 1 offsets that cut the tape into C runs of whole
   // functions with about equal instruction counts (flattened: table c starts at chunk_table_off[c])
   std::vector<uint32_t> chunk_table;
@@ -138,6 +138,7 @@ struct Collection {
   void emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots, int den_mode);
   bool check_function(uint32_t fn, uint64_t p, const uint64_t* point, uint64_t* temps, bool* temp_set) const;
   std::vector<uint8_t> den_mode_;             // per function: 0 as written, 1 parks 1/D in temp slot 0, 2 uses it
+  std::vector<uint32_t> order_, pos_of_;      // evaluation order (position -> function) and its inverse
   std::vector<uint8_t> no_cse_fn_;
   void count_work(const Function& f);
   void peephole();

@@ -398,11 +398,11 @@ def test_shared_denominators_are_inverted_once(oracle):
             f"(x+1)/{D1}",                 # 4 = 0: evaluated once with 0
             f"5/{D2}",                     # 5 run B
             f"(x+y)*(x-y)/{D2}",           # 6
-            f"z/{D1}",                     # 7 run of one: as written
-            f"z/{D2}",                     # 8 run of one
+            f"z/{D1}",                     # 7 joins run A although it is not next to it
+            f"z/{D2}",                     # 8 joins run B
             "(x+1)/3",                     # 9 constant divisor: a multiplication
-            f"{D2}/{D2}",                  # 10 starts a run over D2 ...
-            f"1/{D2}"]                     # 11 ... and this one uses it
+            f"{D2}/{D2}",                  # 10 run B
+            f"1/{D2}"]                     # 11 run B
     p = ff.primes()[4]
     pts = ff.synthetic_points(3, 8, p, seed=11)
     pts[:, 0] = np.array([1, 1, 2], dtype=np.uint64)        # D1 = 1 - 8 + 7 = 0: a/0 = 0 for the whole run
@@ -411,11 +411,11 @@ def test_shared_denominators_are_inverted_once(oracle):
     par = ff.GpuParser(None, funs, vars_)
     par.set_prime(p)
     assert par.n_structural_duplicates == 1
-    assert par.n_shared_denominators == 4                   # 1, 2, 6, 11
+    assert par.n_shared_denominators == 7                   # 1, 2, 7 join 0; 6, 8, 10, 11 join 5 (the evaluation order groups them)
     assert par.cse_fallbacks == 0
     assert np.array_equal(interp(par, pts, p), want)
     n_inv = sum(1 for ins in par.tape() if ff.OPS[int(ins["op"])] == "INV")
-    assert n_inv == 5                                       # runs A, B, 7, 8, 10 -- not one per division
+    assert n_inv == 2                                       # one per distinct denominator -- not one per division
     plain = ff.GpuParser(None, funs, vars_, cse=False)
     plain.set_prime(p)
     assert plain.n_shared_denominators == 0
@@ -436,6 +436,10 @@ def test_cross_function_sharing_keeps_every_value(oracle, den_run, temps, fuse, 
     for _ in range(20):                                     # duplicates, some inside runs
         k = rng.randrange(len(funs))
         funs.insert(rng.randrange(len(funs)), funs[k])
+    if den_run >= 6:                                        # equal denominators need not be neighbours
+        grouped = ff.GpuParser(None, funs, vars_, check_is_equal=check).n_shared_denominators
+        rng.shuffle(funs)
+        assert ff.GpuParser(None, funs, vars_, check_is_equal=check).n_shared_denominators == grouped
     p = ff.primes()[den_run]
     pts = ff.synthetic_points(5, 4, p, seed=den_run)
     pts[:, 1] = 0

@@ -564,6 +564,8 @@ def test_shared_denominators_on_device(ctx, oracle, den_run):
     small batches cut the tape into many chunks (grid.y), which must never start inside a run"""
     funs, vars_ = W.ibp_like_collection(700, 8, seed=77 + den_run, den_run=den_run)
     funs = funs[:350] + funs[100:130] + funs[350:]            # and some structural duplicates in between
+    if den_run == 12:
+        random.Random(5).shuffle(funs)                        # equal denominators need not be neighbours
     p = ff.primes()[5]
     par = ff.GpuParser(ctx, funs, vars_)
     par.set_prime(p)
