@@ -88,10 +88,10 @@ def run_factors(args):
 def run_ibp(args):
     n_gpu = args.gpus or torch.cuda.device_count()
     p = ff.primes()[0]
-    funs, vars_ = W.ibp_like_collection(args.functions, 8)
+    funs, vars_ = W.ibp_like_collection(args.functions, 8, den_run=args.den_run)
     orc = Oracle()
     ctxs = per_gpu_contexts(n_gpu)
-    pars = [ff.GpuParser(c, funs, vars_) for c in ctxs]
+    pars = [ff.GpuParser(c, funs, vars_, cross=not args.no_cross) for c in ctxs]
     for q in pars:
         q.set_prime(p)
     F = pars[0].n_out
@@ -133,7 +133,10 @@ def run_ibp(args):
     ok &= bool(np.array_equal(sm[:64, 0], chk_sum)) and bool(np.array_equal(sm[:64, 1], np.bitwise_xor.reduce(got_full[:64], axis=1)))
     w = pars[0].work()
     x = pars[0].tape_work()
-    print(json.dumps({"config": "synthetic IBP-like collection (BASELINE.json configs[3])", "n_gpus": n_gpu, "functions": F,
+    print(json.dumps({"config": "synthetic IBP-like collection (BASELINE.json configs[3])" +
+                                (f", denominators shared by runs of up to {args.den_run} functions" if args.den_run else "") +
+                                (", FFGPU_NO_CROSS" if args.no_cross else ""),
+                      "shared_denominators": pars[0].n_shared_denominators, "n_gpus": n_gpu, "functions": F,
                       "variables": 8, "points": n_total, "tile_points": tile, "value": n_total / dt, "unit": "probes/s",
                       "function_values_per_s": n_total * F / dt, "seconds": dt,
                       "tape_instructions": pars[0].n_instr, "mm_eq_per_probe": w["mm"] + 6 * w["inv"],
@@ -178,6 +181,8 @@ if __name__ == "__main__":
     ap.add_argument("--functions", type=int, default=10000)
     ap.add_argument("--tile", type=int, default=1 << 15)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--den-run", type=int, default=0, help="ibp: runs of up to this many functions share a denominator")
+    ap.add_argument("--no-cross", action="store_true", help="ibp: no sharing across functions (A/B)")
     a = ap.parse_args()
     good = {"factors": run_factors, "ibp": run_ibp, "sweep": run_sweep}[a.config](a)
     sys.exit(0 if good else 1)
