@@ -2,7 +2,7 @@
 formulas (arXiv:2004.01463 Eqs. 18-20, 29, 36-40) rather than shipped as files, and the
 synthetic IBP-like collection of config 4.
 
-Reference inputs these reproduce token for token (checked in tests/test_workloads.py when the
+Reference inputs these reproduce token for token (checked by tests/test_compiler.py::test_workloads_equal_reference_files when the
 reference tree is present): benchmarks/f1.m-f4.m, benchmarks/factors1.m-factors5.m
 (reference: benchmarks/benchmarks.cpp:71-84,119-131).
 """
