@@ -6,7 +6,7 @@
 // run the black box, hand back [function][point].  Here the batch is sharded over the GPUs of
 // the context by contiguous point ranges (no communication between GPUs -- probes are
 // independent), and every shard is cut into chunks whose H2D copy, kernel and D2H copy run on
-// two alternating streams so that copies overlap compute.
+// four rotating streams so that copies overlap compute.
 #include <cuda_runtime.h>
 
 #include <atomic>
