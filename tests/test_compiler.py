@@ -452,3 +452,49 @@ def test_cross_function_sharing_keeps_every_value(oracle, den_run, temps, fuse, 
     off.set_prime(p)
     assert off.n_shared_denominators == 0 and off.n_structural_duplicates == 0 and off.n_instr > par.n_instr
     assert np.array_equal(interp(off, pts, p), want)
+
+
+def test_shared_denominator_edge_cases(oracle):
+    """N and D related in every way a run can meet: D/D, D inside N, a variable as denominator, nested divisions"""
+    vars_ = ["x", "y", "z"]
+    D = "(x*y+z^2-3)"
+    p = ff.primes()[3]
+    pts = ff.synthetic_points(3, 6, p, seed=1)
+    pts[:, 0] = np.array([1, 1, 0], dtype=np.uint64)
+    pts[:, 1] = 0
+    for funs in ([f"{D}/{D}", f"1/{D}", f"x/{D}"], [f"(x+{D})/{D}", f"{D}^2/{D}", f"y/{D}"],
+                 ["x/y", "z/y", "(x+1)/y", "y/y"], [f"x/{D}/y", f"z/{D}/y"], [f"x/({D}/y)", f"z/({D}/y)"]):
+        par = ff.GpuParser(None, funs, vars_)
+        par.set_prime(p)
+        assert par.n_shared_denominators == len(funs) - 1 and par.cse_fallbacks == 0, funs
+        assert np.array_equal(interp(par, pts, p), oracle.parse(funs, vars_, p).eval(pts)), funs
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_collections_with_repeated_denominators(oracle, seed):
+    from test_gpu_parity import _dag_expressions
+    vars_ = ["x", "y", "z", "w1", "u"]
+    rng = random.Random(seed)
+    exprs = _dag_expressions(rng, vars_, 40)
+    dens = [rng.choice(exprs) for _ in range(6)]
+    funs = []
+    for _ in range(60):
+        r, n = rng.random(), rng.choice(exprs)
+        if r < 0.6:
+            funs.append(f"({n})/({rng.choice(dens)})")
+        elif r < 0.7:
+            funs.append(f"({n})/({rng.choice(dens)})/({rng.choice(dens)})")
+        elif r < 0.8 and funs:
+            funs.append(rng.choice(funs))
+        else:
+            funs.append(n)
+    p = ff.primes()[17 * seed]
+    pts = ff.synthetic_points(5, 4, p, seed=seed)
+    pts[:, 1] = 0
+    pts[:, 2] = np.array([1, p - 1, 0, 2, 1], dtype=np.uint64)
+    for kw in ({}, {"temps": 1}, {"fuse": False}, {"check_is_equal": True}):
+        par = ff.GpuParser(None, funs, vars_, **kw)
+        par.set_prime(p)
+        want = oracle.parse(funs, vars_, p, check_is_equal=kw.get("check_is_equal", False)).eval(pts)
+        assert par.cse_fallbacks == 0 and par.n_shared_denominators > 0
+        assert np.array_equal(interp(par, pts, p), want), kw
