@@ -436,7 +436,7 @@ static int operand_token(const ffo_parser* P, const char* token, uint64_t p, uin
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* the string-token evaluator (ShuntingYardParser.hpp:240-363), needed for duplicate detection */
+/* the string-token evaluator (ShuntingYardParser.cpp:379-479), needed for duplicate detection */
 /* and for re-evaluating a NUMBER's recipe after a prime change (:584-590)                     */
 /* ------------------------------------------------------------------------------------------ */
 static int evaluate_strings(const ffo_parser* P, const strvec* tokens, const uint64_t* values, uint64_t p,
@@ -446,9 +446,10 @@ static int evaluate_strings(const ffo_parser* P, const strvec* tokens, const uin
   int rc = 0;
   for (size_t i = 0; i < tokens->n && rc == 0; i++) {
     const char* t = tokens->v[i];
-    /* note: '~' and ';' are NOT in this evaluator's operator test (:249); they fall to the operand
-     * branch and end in "not declared" */
-    if (t[1] == 0 && (t[0] == '+' || t[0] == '-' || t[0] == '*' || t[0] == '/' || t[0] == '^' || t[0] == '!')) {
+    /* the operator test of THIS overload (:385) knows '~' and ';'; the public template
+     * evaluate<FFIntTemp>(values) (ShuntingYardParser.hpp:249) does not, but nothing on this path calls it */
+    if (t[1] == 0 && (t[0] == '+' || t[0] == '-' || t[0] == '*' || t[0] == '/' || t[0] == '^' || t[0] == '!' ||
+                      t[0] == '~' || t[0] == ';')) {
       if (sp < 2) { set_err("malformed expression: operator '", t, "' lacks operands"); rc = -1; break; }
       uint64_t a = st[--sp];
       uint64_t* top = &st[sp - 1];
@@ -459,6 +460,8 @@ static int evaluate_strings(const ffo_parser* P, const strvec* tokens, const uin
         case '/': *top = ffo_div(*top, a, p); break;
         case '^': *top = ffo_pow(*top, a, p); break;
         case '!': *top = ffo_neg(ffo_pow(*top, a, p), p); break;
+        case '~': *top = ffo_pow_int(*top, ffo_to_neg_int(a), p); break;                  /* :421-424 */
+        case ';': *top = ffo_neg(ffo_pow_int(*top, ffo_to_neg_int(a), p), p); break;      /* :426-429 */
       }
     } else {
       uint64_t v;

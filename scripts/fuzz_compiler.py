@@ -1,0 +1,254 @@
+"""Randomised campaign over the tape compiler -- TEST INFRASTRUCTURE, runs without a GPU.
+
+Every round draws a collection (free grammar, shared sub-expressions, polynomial tables with repeated
+denominators, duplicated functions, scanned factors), compiles it with a random choice of compiler passes,
+interprets the tape on the host (tests/tape_interp.py) and compares every value and every RPN string with the
+C oracle (oracle/ff_oracle.c) on edge and random points for two primes, the second one reached through
+`set_prime` on the same handle (what `prime_changed_internal` does, BlackBoxBase.hpp:35-45).
+
+    python scripts/fuzz_compiler.py --seconds 600 --seed 1 [--jobs 8]
+
+Prints one line per failure (seed and round reproduce it) and a summary; exit code 1 if anything differed.
+"""
+import argparse
+import multiprocessing as mp
+import os
+import random
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+
+def free_grammar(rng, vars_, n, depth):
+    def atom():
+        r = rng.random()
+        if r < 0.5:
+            return rng.choice(vars_)
+        if r < 0.85:
+            return str(rng.randint(0, 10 ** rng.randint(1, 17)))
+        return str(rng.randint(10 ** 18, 10 ** 25))
+
+    def expr(d):
+        if d == 0 or rng.random() < 0.15:
+            return atom()
+        r = rng.random()
+        if r < 0.5:
+            return f"{expr(d-1)}{rng.choice('+-*/')}{expr(d-1)}"
+        if r < 0.6:
+            return f"({expr(d-1)})"
+        if r < 0.72:
+            return f"({expr(d-1)})^{rng.randint(0, 70)}"
+        if r < 0.78:
+            return f"{atom()}^(-{rng.randint(1, 9)})"
+        if r < 0.82:
+            return f"(-{atom()})^{rng.randint(1, 5)}"
+        if r < 0.87:
+            return f"(-({expr(d-1)}))"
+        if r < 0.91:
+            return f"({expr(d-1)})^({rng.choice(vars_)})"
+        if r < 0.94:
+            return f"({expr(d-1)})^(-{rng.choice(vars_)})"
+        if r < 0.96:
+            return f"({expr(d-1)})^({expr(1)})"
+        if r < 0.98:
+            return f"+{expr(d-1)}"
+        return f"(-{rng.choice(vars_)}^{rng.randint(2, 7)}+{expr(d-1)})"
+
+    return [expr(depth) for _ in range(n)]
+
+
+def table(rng, vars_, n):
+    """sums of monomials over a few denominators that come back in any order (and as factors of each other)"""
+    def mono():
+        k = rng.randint(0, min(3, len(vars_)))
+        parts = [f"{v}^{rng.randint(1, 12)}" if rng.random() < 0.6 else v for v in rng.sample(vars_, k)]
+        c = str(rng.randint(1, 10 ** rng.randint(1, 20)))
+        if rng.random() < 0.3:
+            c = f"{c}/{rng.randint(1, 10 ** 6)}"
+        return "*".join([c] + parts) if rng.random() < 0.8 or not parts else "*".join(parts)
+
+    def poly():
+        ts = [mono() for _ in range(rng.randint(1, 7))]
+        return ts[0] + "".join(rng.choice("+-") + t for t in ts[1:])
+
+    dens = [poly() for _ in range(rng.randint(1, 4))]
+    dens.append("0")                                                   # a/0 = 0 through the shared path
+    dens.append(f"({dens[0]})*({rng.choice(vars_)}-{rng.choice(vars_)})")  # vanishes on equal coordinates
+    out = []
+    for _ in range(n):
+        r = rng.random()
+        num = poly()
+        if r < 0.15:
+            out.append(num)
+        elif r < 0.25 and out:
+            out.append(rng.choice(out))                                # a function equal as written
+        elif r < 0.32:
+            d = rng.choice(dens)
+            out.append(f"({num})/({d})/({rng.choice(dens)})")
+        elif r < 0.4:
+            out.append(f"({num})/({rng.choice(dens)})^{rng.randint(1, 3)}")
+        elif r < 0.45:
+            out.append(f"-({num})/({rng.choice(dens)})")
+        elif r < 0.5:
+            out.append(f"1/({rng.choice(dens)})")
+        else:
+            out.append(f"({num})/({rng.choice(dens)})")
+    return out
+
+
+def rpn_is_well_formed(rpn):
+    depth = 0
+    for t in rpn:
+        if len(t) == 1 and t in "+-*/^!~;":
+            if depth < 2:
+                return False
+            depth -= 1
+        else:
+            depth += 1
+    return depth == 1
+
+
+def one_round(seed, rnd):
+    import firefly_b200 as ff
+    from firefly_b200 import workloads as W
+    from oracle_bind import Oracle
+    from tape_interp import run
+    from test_gpu_parity import _dag_expressions
+
+    rng = random.Random((seed << 20) ^ rnd)
+    orc = Oracle()
+    kind = rng.choice(["free", "free", "dag", "table", "table", "ibp"])
+    nv = rng.randint(1, 6)
+    vars_ = [f"x{i}" for i in range(1, nv + 1)]
+    if kind == "free":
+        funs = free_grammar(rng, vars_, rng.randint(1, 40), rng.randint(1, 5))
+    elif kind == "dag":
+        vars_ = ["x", "y", "z", "w1", "u"][:max(nv, 2)]
+        funs = _dag_expressions(rng, vars_, rng.randint(1, 30))
+    elif kind == "table":
+        funs = table(rng, vars_, rng.randint(2, 40))
+    else:
+        funs, vars_ = W.ibp_like_collection(rng.randint(2, 25), max(nv, 2), seed=rng.randrange(1 << 30),
+                                            den_run=rng.choice([0, 0, 2, 4, 16]))
+    nv = len(vars_)
+    opts = dict(cse=rng.random() < 0.85, fuse=rng.random() < 0.85, cross=rng.random() < 0.85,
+                temps=rng.choice([0, 0, 0, 1, 2, 3, 5, 8]), check_is_equal=rng.random() < 0.2)
+    table_primes = ff.primes()
+    p1, p2 = rng.choice(table_primes), rng.choice(table_primes)
+    npts = 7
+    tag = f"seed={seed} round={rnd} kind={kind} n={len(funs)} opts={opts}"
+    try:
+        par = ff.GpuParser(None, funs, vars_, **opts)
+    except ff.FFGpuError:
+        # The grammar can produce what the reference cannot evaluate: an operator without operands ("x*-y",
+        # "a++b") pops an empty std::stack in the reference (undefined behaviour) and is refused here
+        # (DESIGN.md section 2).  Every refusal must be one of those: the oracle refuses too, or its RPN underflows.
+        kept = []
+        for f in funs:
+            try:
+                ff.GpuParser(None, [f], vars_).close()
+                kept.append(f)
+            except ff.FFGpuError as e:
+                try:
+                    rpn = orc.parse([f], vars_, p1).rpn(0)
+                except ValueError:
+                    continue
+                if rpn_is_well_formed(rpn):
+                    return 0, f"{tag}: compiler refused what the reference evaluates: {f!r}: {e}"
+        funs = kept
+        if not funs:
+            return 0, None
+        par = ff.GpuParser(None, funs, vars_, **opts)
+    factors = None
+    if rng.random() < 0.15 and par.n_out > 0:
+        fv = [f"x{i}" for i in range(1, nv + 1)]
+        idx = rng.sample(range(par.n_out), rng.randint(1, min(3, par.n_out)))
+        factors = {i: free_grammar(rng, fv, 1, 2)[0] for i in idx}
+        try:
+            par.set_factors(factors, fv)
+        except ff.FFGpuError:
+            factors = None
+            par = ff.GpuParser(None, funs, vars_, **opts)
+    checked = 0
+    for p in (p1, p2):
+        par.set_prime(p)
+        if par.cse_fallbacks:
+            return checked, f"{tag}: the compiler's self-check dropped the sharing ({par.cse_fallbacks})"
+        op = orc.parse(funs, vars_, p, check_is_equal=opts["check_is_equal"])
+        if factors is None:
+            n_f = par.n_functions
+            if [par.get_rp_function(i) for i in range(n_f)] != [op.rpn(i) for i in range(n_f)]:
+                return checked, f"{tag}: RPN strings differ"
+        pts = ff.synthetic_points(nv, npts, p, seed=rng.randrange(1 << 60))
+        pts[:, 0] = 0
+        pts[:, 1] = 1
+        pts[:, 2] = p - 1
+        pts[:, 3] = pts[0, 3]                     # all coordinates equal: differences vanish
+        pts[:, 4] = np.array([rng.choice([0, 1, 2, p - 1, p - 2, int(pts[0, 4])]) for _ in range(nv)], dtype=np.uint64)
+        want = op.eval(pts)
+        if factors is not None:
+            fv = [f"x{i}" for i in range(1, nv + 1)]
+            fac = orc.parse(list(factors.values()), fv, p).eval(pts)
+            want = want.copy()
+            for row, i in enumerate(factors):
+                want[i] = [int(b) * (pow(int(f), p - 2, p) if int(f) else 0) % p for b, f in zip(want[i], fac[row])]
+        tape = par.tape()
+        for j in range(npts):
+            got = run(tape, [int(x) for x in pts[:, j]], p, par.n_out)
+            exp = [int(x) for x in want[:, j]]
+            if got != exp:
+                k = next(i for i in range(len(exp)) if got[i] != exp[i])
+                return checked, f"{tag}: value differs, p={p} point {j} output {k}: {funs[k] if k < len(funs) else '?'}"
+            checked += len(exp)
+    par.close()
+    return checked, None
+
+
+def worker(args):
+    seed, seconds, q = args
+    t0 = time.time()
+    rnd = rounds = values = 0
+    fails = []
+    while time.time() - t0 < seconds:
+        try:
+            n, err = one_round(seed, rnd)
+        except Exception as e:       # a crash of the harness is a finding too
+            n, err = 0, f"seed={seed} round={rnd}: {type(e).__name__}: {e}"
+        values += n
+        rounds += 1
+        if err:
+            fails.append(err)
+            print("FAIL", err, flush=True)
+            if len(fails) >= 5:
+                break
+        rnd += 1
+    return rounds, values, fails
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=60)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--jobs", type=int, default=max(1, (os.cpu_count() or 2) - 1))
+    ap.add_argument("--round", type=int, default=None, help="replay one round of --seed and exit")
+    a = ap.parse_args()
+    if a.round is not None:
+        n, err = one_round(a.seed, a.round)
+        print(n, "values checked;", err or "identical")
+        sys.exit(1 if err else 0)
+    with mp.get_context("spawn").Pool(a.jobs) as pool:
+        res = pool.map(worker, [(a.seed * 1000 + j, a.seconds, None) for j in range(a.jobs)])
+    rounds = sum(r[0] for r in res)
+    values = sum(r[1] for r in res)
+    fails = [f for r in res for f in r[2]]
+    print(f"{rounds} collections, {values} function values compared with the oracle, {len(fails)} failure(s)")
+    sys.exit(1 if fails else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -49,6 +49,30 @@ def test_oracle_duplicates(oracle):
     assert v == [7, 7, 12, 7, 12]
 
 
+def test_oracle_duplicates_vs_reference(oracle, ref):
+    """check_is_equal goes through the string evaluator ShuntingYardParser.cpp:379-479, which knows the
+    negative-exponent operators '~' and ';' (the public template evaluate<T>(values) does not): same set of
+    distinct functions, same evaluation positions, same values as the reference"""
+    import firefly_b200 as ff
+    rng = random.Random(23)
+    vars_ = ["x1", "x2", "x3"]
+    base = ["x3^(-7)", "(-x1)^(-3)", "1/x3^7", "(x3)^(x2)*7/(x2-2733)^(-x3)", "x2^(-x1)", "-x2^(-2)+x1", "x1*x2-x3",
+            "x3*(-x2)^3", "(x1+x2)^(-2)*x3", "x1^(-x2^2)", "12345678901234567890123*x1^(-1)"]
+    funs = [rng.choice(base) for _ in range(40)] + ["x3^(-7)+0", "(x1*x2-x3)", "x2*x1-x3"]
+    for k in (0, 7):
+        p = ref.lib.ffref_prime(k)
+        ref.set_prime(p)
+        rp = ref.parse(funs, vars_, check_is_equal=True)
+        op = oracle.parse(funs, vars_, p, check_is_equal=True)
+        assert rp.n_out == op.n_out == len(funs) and rp.n_functions == op.n_functions < len(funs)
+        assert [op.rpn(i) for i in range(op.n_functions)] == [rp.rpn(i) for i in range(rp.n_functions)]
+        pts = ff.synthetic_points(3, 12, p, seed=k)
+        pts[:, 0] = 0
+        pts[:, 1] = np.array([1, p - 1, 2], dtype=np.uint64)
+        assert np.array_equal(op.eval(pts), rp.eval(pts))
+    ref.set_prime(ref.lib.ffref_prime(0))
+
+
 def test_primes_table(oracle):
     L = oracle.lib
     ps = [L.ffo_prime(i) for i in range(300)]
