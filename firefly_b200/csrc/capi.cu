@@ -598,7 +598,7 @@ int ffgpu_eval(ffgpu_tape* t, const uint64_t* values, size_t n_points, uint64_t*
 int ffgpu_eval_line(ffgpu_tape* t, const uint64_t* a, const uint64_t* s, const uint64_t* tt, size_t n_points,
                     uint64_t* out, uint32_t thread_id) {
   if (t && n_points && (!tt || (t->col.vars.size() && (!a || !s)))) return fail("null line parameters");
-  if (t && t->col.prime) {
+  if (t && t->col.prime && n_points) {
     for (size_t v = 0; v < t->col.vars.size(); ++v)
       if (a[v] >= t->col.prime || s[v] >= t->col.prime) return fail("line parameters must be residues below the prime");
   }
@@ -646,12 +646,12 @@ int ffgpu_field_ops(ffgpu_ctx* ctx, int op, const uint64_t* a, const uint64_t* b
   if (p >= two63 || two63 - p >= (1u << 15)) return fail("unsupported prime");
   DeviceGuard guard(ctx->devs[0].id);
   uint64_t *da = nullptr, *db = nullptr, *dr = nullptr;
-  FF_CUDA(cudaMalloc(&da, n * 8));
-  FF_CUDA(cudaMalloc(&db, n * 8));
-  FF_CUDA(cudaMalloc(&dr, n * 8));
-  FF_CUDA(cudaMemcpy(da, a, n * 8, cudaMemcpyHostToDevice));
-  FF_CUDA(cudaMemcpy(db, b, n * 8, cudaMemcpyHostToDevice));
-  cudaError_t e = ffgpu::launch_field_ops(op, da, db, dr, n, p, nullptr);
+  cudaError_t e = cudaMalloc(&da, n * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&db, n * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&dr, n * 8);
+  if (e == cudaSuccess) e = cudaMemcpy(da, a, n * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(db, b, n * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = ffgpu::launch_field_ops(op, da, db, dr, n, p, nullptr);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpy(r, dr, n * 8, cudaMemcpyDeviceToHost);
   cudaFree(da);
