@@ -10,6 +10,7 @@ Mirrors, by name and meaning, the part of the reference API that sits on the hot
 (reference: source/include/firefly/ShuntingYardParser.hpp:44-135):
 
     ShuntingYardParser(file | functions, vars, check_is_equal)  -> GpuParser(...)
+    parser.add_otf / parse_function / add_otf_precompute / trim -> the same names on GpuParser
     parser.precompute_tokens() after FFInt::set_new_prime(p)    -> parser.set_prime(p)
     parser.evaluate_pre(values)                                 -> parser.evaluate_pre(values)
     parser.get_rp_function(i)                                   -> parser.get_rp_function(i)
@@ -41,6 +42,7 @@ CHECK_IS_EQUAL = 1
 NO_CSE = 2
 NO_FUSE = 4
 NO_CROSS = 16
+ADD_PLAIN, ADD_VALIDATE, ADD_NO_DUPLICATES = 1, 2, 4
 
 
 class FFGpuError(RuntimeError):
@@ -64,6 +66,7 @@ def _load() -> C.CDLL:
         "ffgpu_compile": (C.c_void_p, [C.c_void_p, strs, C.c_size_t, strs, C.c_size_t, C.c_uint]),
         "ffgpu_compile_text": (C.c_void_p, [C.c_void_p, C.c_char_p, strs, C.c_size_t, C.c_uint]),
         "ffgpu_compile_file": (C.c_void_p, [C.c_void_p, C.c_char_p, strs, C.c_size_t, C.c_uint]),
+        "ffgpu_tape_clone": (C.c_void_p, [C.c_void_p]),
         "ffgpu_tape_destroy": (None, [C.c_void_p]),
         "ffgpu_n_vars": (C.c_size_t, [C.c_void_p]),
         "ffgpu_n_functions": (C.c_size_t, [C.c_void_p]),
@@ -80,6 +83,10 @@ def _load() -> C.CDLL:
         "ffgpu_work": (None, [C.c_void_p, u64p]),
         "ffgpu_tape_work": (None, [C.c_void_p, u64p]),
         "ffgpu_set_factors": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), strs, C.c_size_t, strs, C.c_size_t]),
+        "ffgpu_add_function": (C.c_long, [C.c_void_p, C.c_char_p, C.c_uint]),
+        "ffgpu_add_function_rpn": (C.c_long, [C.c_void_p, strs, C.c_size_t]),
+        "ffgpu_trim": (C.c_int, [C.c_void_p, u64p, C.c_size_t, u64p]),
+        "ffgpu_is_stale": (C.c_int, [C.c_void_p]),
         "ffgpu_set_prime": (C.c_int, [C.c_void_p, C.c_uint64]),
         "ffgpu_get_prime": (C.c_uint64, [C.c_void_p]),
         "ffgpu_n_primes": (C.c_uint32, []),
@@ -126,8 +133,9 @@ def _load() -> C.CDLL:
 lib = _load()
 EXPORTS = [
     "ffgpu_create", "ffgpu_destroy", "ffgpu_n_devices", "ffgpu_last_error", "ffgpu_compile", "ffgpu_compile_text",
-    "ffgpu_compile_file", "ffgpu_tape_destroy", "ffgpu_n_vars", "ffgpu_n_functions", "ffgpu_n_out", "ffgpu_n_instr",
+    "ffgpu_compile_file", "ffgpu_tape_clone", "ffgpu_tape_destroy", "ffgpu_n_vars", "ffgpu_n_functions", "ffgpu_n_out", "ffgpu_n_instr",
     "ffgpu_stack_depth", "ffgpu_n_temps", "ffgpu_n_slots", "ffgpu_cse_fallbacks", "ffgpu_n_structural_duplicates", "ffgpu_n_shared_denominators", "ffgpu_rpn", "ffgpu_get_tape", "ffgpu_work", "ffgpu_tape_work", "ffgpu_set_factors", "ffgpu_set_prime", "ffgpu_get_prime",
+    "ffgpu_add_function", "ffgpu_add_function_rpn", "ffgpu_trim", "ffgpu_is_stale",
     "ffgpu_n_primes", "ffgpu_prime", "ffgpu_eval", "ffgpu_eval_line", "ffgpu_eval_wire", "ffgpu_eval_device", "ffgpu_host_alloc", "ffgpu_host_free",
     "ffgpu_queue_create", "ffgpu_queue_destroy", "ffgpu_queue_push", "ffgpu_queue_push_many", "ffgpu_queue_push_line",
     "ffgpu_queue_pop", "ffgpu_queue_pending", "ffgpu_queue_stats", "ffgpu_queue_error",
@@ -275,6 +283,47 @@ class GpuParser:
             raise FFGpuError(last_error())
         self.n_out = lib.ffgpu_n_out(self.h)
         self.n_functions = lib.ffgpu_n_functions(self.h)
+
+    # -- changing the collection (ShuntingYardParser.cpp:315-377, 720-776) -----------------
+    def _refresh(self):
+        self.n_out = lib.ffgpu_n_out(self.h)
+        self.n_functions = lib.ffgpu_n_functions(self.h)
+
+    def add_otf(self, fun: str, no_duplicates: bool = False) -> int:
+        """Append a function; returns its position (its twin's on a check_is_equal parser).  set_prime rebuilds."""
+        pos = lib.ffgpu_add_function(self.h, fun.encode(), ADD_NO_DUPLICATES if no_duplicates else 0)
+        if pos < 0:
+            raise FFGpuError(last_error())
+        self._refresh()
+        return pos
+
+    def parse_function(self, fun: str, validate_fun: bool = False) -> int:
+        pos = lib.ffgpu_add_function(self.h, fun.encode(), ADD_PLAIN | (ADD_VALIDATE if validate_fun else 0))
+        if pos < 0:
+            raise FFGpuError(last_error())
+        self._refresh()
+        return pos
+
+    def add_otf_precompute(self, rpn_fun: Sequence[str]) -> int:
+        pos = lib.ffgpu_add_function_rpn(self.h, _strs(rpn_fun), len(rpn_fun))
+        if pos < 0:
+            raise FFGpuError(last_error())
+        self._refresh()
+        return pos
+
+    def trim(self, elements_to_keep) -> dict:
+        """Keep the listed functions (output positions with check_is_equal); returns {old position: new position}."""
+        keep = sorted(set(int(k) for k in elements_to_keep))
+        arr = (C.c_uint64 * max(len(keep), 1))(*keep)
+        new = (C.c_uint64 * max(len(keep), 1))()
+        if lib.ffgpu_trim(self.h, arr, len(keep), new):
+            raise FFGpuError(last_error())
+        self._refresh()
+        return {k: new[i] for i, k in enumerate(keep) if new[i] != 2 ** 64 - 1}
+
+    @property
+    def stale(self) -> bool:
+        return bool(lib.ffgpu_is_stale(self.h))
 
     # -- prime -----------------------------------------------------------------------
     def set_prime(self, p: int):

@@ -193,6 +193,18 @@ int small_zero_copy() {
   return mode;
 }
 
+// the device copies of the tape and its chunk table; ffgpu_set_prime uploads new ones
+void drop_device_copies(ffgpu_tape* t) {
+  for (size_t g = 0; t->ctx && g < t->ctx->devs.size(); ++g) {
+    DeviceGuard guard(t->ctx->devs[g].id);
+    cudaDeviceSynchronize();
+    if (t->d_tape[g]) cudaFree(t->d_tape[g]);
+    if (t->d_chunks[g]) cudaFree(t->d_chunks[g]);
+    t->d_tape[g] = nullptr;
+    t->d_chunks[g] = nullptr;
+  }
+}
+
 int ensure(DevBuf& b, size_t need_in, size_t need_out) {
   if (!b.stream) FF_CUDA(cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
   if (b.cap_in < need_in) {
@@ -310,6 +322,26 @@ ffgpu_tape* ffgpu_compile_file(ffgpu_ctx* ctx, const char* path, const char* con
   return ffgpu_compile_text(ctx, ss.str().c_str(), vars, n_vars, flags);
 }
 
+ffgpu_tape* ffgpu_tape_clone(const ffgpu_tape* t) {
+  if (!t) {
+    g_err = "null tape";
+    return nullptr;
+  }
+  std::unique_ptr<ffgpu_tape> n(new ffgpu_tape);
+  n->ctx = t->ctx;
+  n->col = t->col;
+  n->force_k = t->force_k;
+  n->force_threads = t->force_threads;
+  n->chunk = t->chunk;
+  if (t->ctx) {
+    n->d_tape.assign(t->ctx->devs.size(), nullptr);
+    n->d_chunks.assign(t->ctx->devs.size(), nullptr);
+  }
+  // the copy gets device buffers of its own, for the prime the original is resolved for
+  if (t->col.prime && !t->col.stale && ffgpu_set_prime(n.get(), t->col.prime)) return nullptr;
+  return n.release();
+}
+
 void ffgpu_tape_destroy(ffgpu_tape* t) {
   if (!t) return;
   for (size_t g = 0; g < t->d_tape.size(); ++g) {
@@ -380,7 +412,9 @@ int ffgpu_set_prime(ffgpu_tape* t, uint64_t p) {
   if (p >= two63 || two63 - p >= (1u << 15) || p < 3)
     return fail("unsupported prime " + std::to_string(p) + ": need p = 2^63 - c with 0 < c < 2^15");
   std::string err;
+  const bool rebuilt = t->col.stale;      // functions were added or trimmed: the tape has a new size
   if (!t->col.resolve(p, err)) return fail(err);
+  if (rebuilt) drop_device_copies(t);
   t->needs_generic = false;
   for (const ffgpu::Instr& in : t->col.tape) t->needs_generic |= in.fast == ffgpu::FX_GENERIC && in.op != ffgpu::OP_HALT;
   const size_t bytes = t->col.tape.size() * sizeof(ffgpu::Instr);
@@ -407,16 +441,39 @@ int ffgpu_set_factors(ffgpu_tape* t, const uint32_t* out_index, const char* cons
   std::string err;
   if (!t->col.apply_factors(fac, to_vec(factor_vars, n_factor_vars), err)) return fail(err);
   // the tape changed size: drop the device copies, ffgpu_set_prime uploads the new one
-  for (size_t g = 0; t->ctx && g < t->ctx->devs.size(); ++g) {
-    DeviceGuard guard(t->ctx->devs[g].id);
-    cudaDeviceSynchronize();
-    if (t->d_tape[g]) cudaFree(t->d_tape[g]);
-    if (t->d_chunks[g]) cudaFree(t->d_chunks[g]);
-    t->d_tape[g] = nullptr;
-    t->d_chunks[g] = nullptr;
-  }
+  drop_device_copies(t);
   return 0;
 }
+
+long ffgpu_add_function(ffgpu_tape* t, const char* function, unsigned flags) {
+  if (!t) return fail("null tape");
+  uint64_t pos = 0;
+  std::string err;
+  const bool plain = (flags & FFGPU_ADD_PLAIN) != 0;
+  if (!t->col.append(function ? function : "", plain ? (flags & FFGPU_ADD_VALIDATE) != 0 : true, !plain,
+                     (flags & FFGPU_ADD_NO_DUPLICATES) != 0, pos, err))
+    return fail(err);
+  return (long)pos;
+}
+
+long ffgpu_add_function_rpn(ffgpu_tape* t, const char* const* tokens, size_t n_tokens) {
+  if (!t) return fail("null tape");
+  uint64_t pos = 0;
+  std::string err;
+  if (!t->col.append_rpn(to_vec(tokens, n_tokens), pos, err)) return fail(err);
+  return (long)pos;
+}
+
+int ffgpu_trim(ffgpu_tape* t, const uint64_t* keep, size_t n_keep, uint64_t* new_positions) {
+  if (!t) return fail("null tape");
+  std::vector<uint64_t> k(keep, keep + n_keep), np;
+  std::string err;
+  if (!t->col.trim(k, np, err)) return fail(err);
+  if (new_positions) std::copy(np.begin(), np.end(), new_positions);
+  return 0;
+}
+
+int ffgpu_is_stale(const ffgpu_tape* t) { return t && t->col.stale ? 1 : 0; }
 
 int ffgpu_set_launch(ffgpu_tape* t, int k, int threads) {
   if (!(k == 0 || k == 1 || k == 2 || k == 4 || k == 8)) return fail("probes_per_thread must be 0, 1, 2, 4 or 8");
@@ -439,6 +496,7 @@ int ffgpu_eval_device(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_
   if (!t) return fail("null tape");
   if (!t->ctx) return fail("tape was compiled without a context: no GPU to evaluate on (there is no CPU path)");
   if (g < 0 || g >= (int)t->ctx->devs.size()) return fail("device index out of range");
+  if (t->col.stale) return fail("functions were added or trimmed: call ffgpu_set_prime before evaluating");
   if (!t->col.prime || !t->d_tape[g]) return fail("ffgpu_set_prime has not been called");
   if (in_stride < n_points || out_stride < n_points) return fail("row stride smaller than n_points");
   if (n_points == 0) return 0;
@@ -455,6 +513,7 @@ int eval_host(ffgpu_tape* t, const uint64_t* values, const uint64_t* line_a, con
               const uint64_t* line_t, size_t n_points, uint64_t* out, uint32_t thread_id) {
   if (!t) return fail("null tape");
   if (!t->ctx) return fail("tape was compiled without a context: no GPU to evaluate on (there is no CPU path)");
+  if (t->col.stale) return fail("functions were added or trimmed: call ffgpu_set_prime before evaluating");
   if (!t->col.prime) return fail("ffgpu_set_prime has not been called");
   if (n_points == 0) return 0;
   ffgpu_ctx* ctx = t->ctx;

@@ -1148,17 +1148,18 @@ bool same_structure(const Function& f, const std::vector<Fp>& ff, int32_t fr, co
 }
 }  // namespace
 
-bool Collection::add_function(std::string text, uint64_t index, bool strip_blanks, std::string& err) {
+bool Collection::add_function(std::string text, uint64_t index, bool strip_blanks, std::string& err, bool validate,
+                              bool dedupe, bool no_duplicates, uint64_t* position) {
   if (strip_blanks) {
     text.erase(std::remove_if(text.begin(), text.end(), [](char c) { return c == ' ' || c == '\t' || c == '\n'; }),
                text.end());
     if (text.empty()) return true;          // blank chunk between ';' adds no function
   }
-  if (!validate_expr(text, index, err)) return false;
+  if (validate && !validate_expr(text, index, err)) return false;
   Function f;
   if (!parse_expr(text, f.rpn, err)) return false;
   if (!build_tree(f, err)) return false;
-  if (check_is_equal) {
+  if (check_is_equal && dedupe) {
     // fingerprint = values at one random point in each of two primes (reference: :125-140)
     std::vector<uint64_t> v1, v2;
     eval_nodes(f, P1, chk_pts1_.data(), v1);
@@ -1166,18 +1167,21 @@ bool Collection::add_function(std::string text, uint64_t index, bool strip_blank
     const std::string key = std::to_string(v1[f.root]) + ":" + std::to_string(v2[f.root]);
     auto it = chk_map_.find(key);
     if (it != chk_map_.end()) {
-      evaluation_positions.push_back(it->second);
+      if (!no_duplicates) evaluation_positions.push_back(it->second);
+      if (position) *position = it->second;
       return true;
     }
     chk_map_.emplace(key, (uint64_t)functions.size());
     evaluation_positions.push_back((uint64_t)functions.size());
   }
+  if (position) *position = (uint64_t)functions.size();
   functions.push_back(std::move(f));
   return true;
 }
 
 bool Collection::finish(std::string& err) {
   (void)err;
+  stale = false;                 // resolve() below must not come back here
   n_out = check_is_equal ? evaluation_positions.size() : functions.size();
   // output slots per distinct function
   std::vector<std::vector<uint32_t>> slots(functions.size());
@@ -1372,7 +1376,7 @@ bool Collection::finish(std::string& err) {
   tape.push_back(halt);
   tape.push_back(halt);            // the interpreter prefetches one instruction ahead
   prime = 0;
-  chk_map_.clear();
+  stale = false;
   return true;
 }
 
@@ -1587,16 +1591,21 @@ static void init_vars(Collection& c, const std::vector<std::string>& vars, bool 
   c.evaluation_positions.clear();
 }
 
+void Collection::init_check_points() {
+  chk_map_.clear();
+  base_functions_.clear();
+  if (!check_is_equal) return;
+  uint64_t s = 0x4d595df4d0f33173ULL;
+  chk_pts1_.resize(vars.size());
+  chk_pts2_.resize(vars.size());
+  for (auto& v : chk_pts1_) v = 1 + splitmix64(s) % (P1 - 1);
+  for (auto& v : chk_pts2_) v = 1 + splitmix64(s) % (P0 - 1);
+}
+
 bool Collection::compile_strings(const std::vector<std::string>& funs, const std::vector<std::string>& vars_,
                                  bool chk, std::string& err) {
   init_vars(*this, vars_, chk);
-  if (chk) {
-    uint64_t s = 0x4d595df4d0f33173ULL;
-    chk_pts1_.resize(vars.size());
-    chk_pts2_.resize(vars.size());
-    for (auto& v : chk_pts1_) v = 1 + splitmix64(s) % (P1 - 1);
-    for (auto& v : chk_pts2_) v = 1 + splitmix64(s) % (P0 - 1);
-  }
+  init_check_points();
   for (size_t i = 0; i < funs.size(); ++i)
     if (!add_function(funs[i], i, false, err)) return false;
   return finish(err);
@@ -1605,13 +1614,7 @@ bool Collection::compile_strings(const std::vector<std::string>& funs, const std
 bool Collection::compile_text(const std::string& text, const std::vector<std::string>& vars_, bool chk,
                               std::string& err) {
   init_vars(*this, vars_, chk);
-  if (chk) {
-    uint64_t s = 0x4d595df4d0f33173ULL;
-    chk_pts1_.resize(vars.size());
-    chk_pts2_.resize(vars.size());
-    for (auto& v : chk_pts1_) v = 1 + splitmix64(s) % (P1 - 1);
-    for (auto& v : chk_pts2_) v = 1 + splitmix64(s) % (P0 - 1);
-  }
+  init_check_points();
   size_t start = 0;
   uint64_t line = 1;
   while (start <= text.size()) {
@@ -1638,6 +1641,7 @@ bool Collection::apply_factors(const std::vector<std::pair<uint32_t, std::string
     err = "the factors must be written over as many variables as the collection has";
     return false;
   }
+  if (stale) n_out = check_is_equal ? evaluation_positions.size() : functions.size();
   if (base_functions_.empty() && !functions.empty()) {
     // one function per OUTPUT from here on: duplicates may get different factors
     for (size_t k = 0; k < n_out; ++k) base_functions_.push_back(functions[check_is_equal ? evaluation_positions[k] : k]);
@@ -1686,11 +1690,103 @@ bool Collection::apply_factors(const std::vector<std::pair<uint32_t, std::string
   return finish(err);
 }
 
+// ------------------------------------------------------------------------------------------
+// 9. changing a compiled collection: add_otf, parse_function, add_otf_precompute, trim
+// ------------------------------------------------------------------------------------------
+bool Collection::append(std::string text, bool validate, bool dedupe, bool no_duplicates, uint64_t& position,
+                        std::string& err) {
+  if (!base_functions_.empty()) {
+    err = "functions cannot be added after scanned factors were set";
+    return false;
+  }
+  if (check_is_equal && !dedupe) {
+    // parse_function on a check_is_equal parser leaves the function without an evaluation position: the
+    // reference computes it and never returns its value (ShuntingYardParser.hpp:462-478)
+    err = "parse_function on a parser that checks for equal functions: use add_otf";
+    return false;
+  }
+  const size_t before = functions.size(), outs = evaluation_positions.size();
+  if (!add_function(std::move(text), before, false, err, validate, dedupe, no_duplicates, &position)) return false;
+  if (functions.size() != before || evaluation_positions.size() != outs) stale = true;
+  n_out = check_is_equal ? evaluation_positions.size() : functions.size();
+  return true;
+}
+
+bool Collection::append_rpn(const std::vector<std::string>& rpn, uint64_t& position, std::string& err) {
+  if (!base_functions_.empty()) {
+    err = "functions cannot be added after scanned factors were set";
+    return false;
+  }
+  if (check_is_equal) {
+    err = "add_otf_precompute on a parser that checks for equal functions: the function would have no evaluation position";
+    return false;
+  }
+  Function f;
+  f.rpn = rpn;
+  if (!build_tree(f, err)) return false;
+  position = (uint64_t)functions.size();
+  functions.push_back(std::move(f));
+  n_out = functions.size();
+  stale = true;
+  return true;
+}
+
+bool Collection::trim(const std::vector<uint64_t>& keep, std::vector<uint64_t>& new_pos, std::string& err) {
+  if (!base_functions_.empty()) {
+    err = "a collection with scanned factors cannot be trimmed";
+    return false;
+  }
+  new_pos.assign(keep.size(), ~0ULL);
+  std::unordered_map<uint64_t, size_t> want;                  // old position -> index into keep
+  for (size_t k = 0; k < keep.size(); ++k) want.emplace(keep[k], k);
+  std::vector<Function> nf;
+  if (!check_is_equal) {
+    for (size_t i = 0; i < functions.size(); ++i) {
+      auto it = want.find(i);
+      if (it == want.end()) continue;
+      nf.push_back(std::move(functions[i]));
+      new_pos[it->second] = nf.size() - 1;
+    }
+  } else {
+    // positions are OUTPUT positions; a function that several kept outputs share is copied once
+    std::vector<uint64_t> npos;
+    std::unordered_map<uint64_t, uint64_t> copied;             // old function -> new function
+    for (size_t i = 0; i < evaluation_positions.size(); ++i) {
+      auto it = want.find(i);
+      if (it == want.end()) continue;
+      const uint64_t fn = evaluation_positions[i];
+      auto c = copied.find(fn);
+      if (c == copied.end()) {
+        nf.push_back(std::move(functions[fn]));
+        c = copied.emplace(fn, nf.size() - 1).first;
+      }
+      npos.push_back(c->second);
+      new_pos[it->second] = npos.size() - 1;
+    }
+    evaluation_positions.swap(npos);
+    // the fingerprint map goes with the old numbering (the reference leaves its check_map as it is: a later
+    // add_otf of a trimmed function would return a stale position there); here later additions are compared
+    // with what was kept
+    for (auto it = chk_map_.begin(); it != chk_map_.end();) {
+      auto c = copied.find(it->second);
+      if (c == copied.end()) it = chk_map_.erase(it);
+      else { it->second = c->second; ++it; }
+    }
+  }
+  // duplicates in `keep` name the same element
+  for (size_t k = 0; k < keep.size(); ++k) new_pos[k] = new_pos[want[keep[k]]];
+  functions.swap(nf);
+  n_out = check_is_equal ? evaluation_positions.size() : functions.size();
+  stale = true;
+  return true;
+}
+
 bool Collection::resolve(uint64_t p, std::string& err) {
   if (p < 3 || (p >> 63)) {
     err = "prime must be below 2^63";
     return false;
   }
+  if (stale && !finish(err)) return false;
   std::vector<uint64_t> val;
   uint32_t cur = ~0u;
   for (const ConstPatch& cp : patches) {

@@ -129,9 +129,24 @@ struct Collection {
   // rebuild the tape; replaces factors set earlier.  The prime has to be set again afterwards.
   bool apply_factors(const std::vector<std::pair<uint32_t, std::string>>& factors,
                      const std::vector<std::string>& factor_vars, std::string& err);
+  // --- changing a compiled collection (the rest of ShuntingYardParser's public interface) ---
+  // The tape is not rebuilt by these calls: `stale` is set and the next resolve() rebuilds it first, which is
+  // where the reference pays too (precompute_tokens(true) after add_otf, ShuntingYardParser.cpp:550-591).
+  bool stale = false;
+  // add_otf (:347-377; validate = true, dedupe = true) and parse_function (:315-329; dedupe = false): append one
+  // function.  With check_is_equal and dedupe, a function whose fingerprint is known returns the position of its
+  // twin and gets an output of its own only if !no_duplicates.  `position` indexes `functions`.
+  bool append(std::string text, bool validate, bool dedupe, bool no_duplicates, uint64_t& position, std::string& err);
+  // add_otf_precompute (:331-341): the function arrives as reverse Polish tokens
+  bool append_rpn(const std::vector<std::string>& rpn, uint64_t& position, std::string& err);
+  // trim (:720-776): keep the listed functions (outputs, with check_is_equal) in their old order;
+  // new_pos[k] is the new position of keep[k], ~0 if keep[k] did not exist
+  bool trim(const std::vector<uint64_t>& keep, std::vector<uint64_t>& new_pos, std::string& err);
 
  private:
-  bool add_function(std::string text, uint64_t index, bool strip_blanks, std::string& err);
+  bool add_function(std::string text, uint64_t index, bool strip_blanks, std::string& err, bool validate = true,
+                    bool dedupe = true, bool no_duplicates = false, uint64_t* position = nullptr);
+  void init_check_points();
   bool build_tree(Function& f, std::string& err);
   static void compute_needs(Function& f);
   std::vector<Function> base_functions_;      // one per output, before any factor was applied

@@ -71,6 +71,9 @@ ffgpu_tape* ffgpu_compile(ffgpu_ctx*, const char* const* functions, size_t n_fun
 /* ';'-separated text with blanks/tabs/newlines ignored, as ShuntingYardParser reads a file */
 ffgpu_tape* ffgpu_compile_text(ffgpu_ctx*, const char* text, const char* const* vars, size_t n_vars, unsigned flags);
 ffgpu_tape* ffgpu_compile_file(ffgpu_ctx*, const char* path, const char* const* vars, size_t n_vars, unsigned flags);
+/* an independent copy (ShuntingYardParser is copied by value into black boxes, e.g. test/test_bunch.cpp:33-34):
+ * same functions, same prime, device buffers of its own */
+ffgpu_tape* ffgpu_tape_clone(const ffgpu_tape*);
 void ffgpu_tape_destroy(ffgpu_tape*);
 
 size_t ffgpu_n_vars(const ffgpu_tape*);
@@ -110,6 +113,23 @@ void ffgpu_tape_work(const ffgpu_tape*, uint64_t w[5]);
  * called again afterwards. */
 int ffgpu_set_factors(ffgpu_tape*, const uint32_t* out_index, const char* const* factors, size_t n_factors,
                       const char* const* factor_vars, size_t n_factor_vars);
+
+/* ---- changing a compiled collection (the rest of ShuntingYardParser's public interface) ------
+ * Host-side calls; the tape is rebuilt by the next ffgpu_set_prime (where the reference pays as well:
+ * precompute_tokens(true), ShuntingYardParser.cpp:550-591).  Until then ffgpu_eval* refuses.  Need quiescence. */
+#define FFGPU_ADD_PLAIN 1u          /* parse_function (:315-329): no duplicate check; refused on a check_is_equal tape */
+#define FFGPU_ADD_VALIDATE 2u       /* parse_function's validate_fun; add_otf always validates */
+#define FFGPU_ADD_NO_DUPLICATES 4u  /* add_otf's no_duplicates: a known function gets no further output */
+/* add_otf (:347-377) / parse_function: append one function over the tape's variables.  Returns its position among
+ * the distinct functions (the position of its twin if check_is_equal finds one), -1 on error. */
+long ffgpu_add_function(ffgpu_tape*, const char* function, unsigned flags);
+/* add_otf_precompute (:331-341): the function as reverse Polish tokens (what get_rp_function returns) */
+long ffgpu_add_function_rpn(ffgpu_tape*, const char* const* tokens, size_t n_tokens);
+/* trim (:720-776): keep the listed functions -- OUTPUT positions on a check_is_equal tape -- in their old order.
+ * new_positions[k] = where keep[k] is now, ~0 if it did not exist. */
+int ffgpu_trim(ffgpu_tape*, const uint64_t* keep, size_t n_keep, uint64_t* new_positions);
+/* 1 if functions changed since the tape was built (ffgpu_set_prime pending) */
+int ffgpu_is_stale(const ffgpu_tape*);
 
 /* ---- prime -------------------------------------------------------------------------------- */
 /* p must be a prime of the form 2^63 - c, 0 < c < 2^15 (all 300 primes of FireFly's table are). */

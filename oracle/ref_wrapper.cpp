@@ -13,6 +13,8 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "firefly/FFInt.hpp"
@@ -80,6 +82,31 @@ size_t ffref_n_functions(const ffref_parser* h) { return h->par.get_size(); }
 // what BlackBox::prime_changed() does (reference: benchmarks/benchmarks.cpp:31-33)
 void ffref_prime_changed(ffref_parser* h) { h->par.precompute_tokens(); }
 void ffref_precompute_force(ffref_parser* h) { h->par.precompute_tokens(true); }
+
+// --- the rest of the parser's public interface (reference: ShuntingYardParser.cpp:315-377, 720-776) ---
+size_t ffref_add_otf(ffref_parser* h, const char* fun, int no_duplicates) {
+  std::string f(fun);
+  return h->par.add_otf(f, no_duplicates != 0);
+}
+void ffref_parse_function(ffref_parser* h, const char* fun, const char* const* vars, size_t n_vars, int validate) {
+  std::string f(fun);
+  h->par.parse_function(f, to_vec(vars, n_vars), validate != 0);
+}
+size_t ffref_add_otf_precompute(ffref_parser* h, const char* const* tokens, size_t n) {
+  return h->par.add_otf_precompute(to_vec(tokens, n));
+}
+// new_pos[k] = new position of keep[k], ~0 if it was dropped
+void ffref_trim(ffref_parser* h, const uint64_t* keep, size_t n, uint64_t* new_pos) {
+  std::unordered_set<size_t> k(keep, keep + n);
+  std::unordered_map<size_t, size_t> m = h->par.trim(k);
+  for (size_t i = 0; i < n; ++i) new_pos[i] = m.count(keep[i]) ? (uint64_t)m[keep[i]] : ~0ULL;
+}
+// after a change: rebuild the precomputed tokens (force) and count the outputs again
+void ffref_refresh(ffref_parser* h, int force) {
+  if (force) h->par.precompute_tokens(true);
+  std::vector<FFInt> probe(h->n_vars, FFInt(1));
+  h->n_out = h->par.evaluate_pre(probe).size();
+}
 
 // RPN of function i, tokens joined by ' ' (reference: get_rp_function, ShuntingYardParser.cpp:534-536).
 // Returns the length needed (without NUL); writes at most cap-1 chars.

@@ -57,6 +57,14 @@ class Ref:
         L.ffref_pow_int.argtypes = [C.c_uint64, C.c_int]
         L.ffref_to_neg_int.restype = C.c_int
         L.ffref_to_neg_int.argtypes = [C.c_uint64]
+        strs = C.POINTER(C.c_char_p)
+        L.ffref_add_otf.restype = C.c_size_t
+        L.ffref_add_otf.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.ffref_parse_function.argtypes = [C.c_void_p, C.c_char_p, strs, C.c_size_t, C.c_int]
+        L.ffref_add_otf_precompute.restype = C.c_size_t
+        L.ffref_add_otf_precompute.argtypes = [C.c_void_p, strs, C.c_size_t]
+        L.ffref_trim.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.ffref_refresh.argtypes = [C.c_void_p, C.c_int]
         L.ffref_compute_bunch_size.restype = C.c_uint32
         L.ffref_compute_bunch_size.argtypes = [C.c_uint32] * 3
         L.ffref_compute_job_number.restype = C.c_uint32
@@ -99,6 +107,28 @@ class RefParser:
         else:
             self.ref.lib.ffref_eval(self.h, a.ctypes.data, n, out.ctypes.data, bunch, threads)
         return out
+
+    # the rest of the parser's public interface (ShuntingYardParser.cpp:315-377, 720-776)
+    def add_otf(self, fun, no_duplicates=False):
+        return self.ref.lib.ffref_add_otf(self.h, fun.encode(), int(no_duplicates))
+
+    def parse_function(self, fun, vars, validate=False):
+        self.ref.lib.ffref_parse_function(self.h, fun.encode(), _strs(vars), len(vars), int(validate))
+
+    def add_otf_precompute(self, tokens):
+        return self.ref.lib.ffref_add_otf_precompute(self.h, _strs(tokens), len(tokens))
+
+    def trim(self, keep):
+        keep = sorted(set(keep))
+        a = np.array(keep, dtype=np.uint64)
+        new = np.zeros(max(len(keep), 1), dtype=np.uint64)
+        self.ref.lib.ffref_trim(self.h, a.ctypes.data, len(keep), new.ctypes.data)
+        return {k: int(new[i]) for i, k in enumerate(keep) if int(new[i]) != 2 ** 64 - 1}
+
+    def refresh(self, force=True):
+        self.ref.lib.ffref_refresh(self.h, int(force))
+        self.n_out = self.ref.lib.ffref_n_out(self.h)
+        self.n_functions = self.ref.lib.ffref_n_functions(self.h)
 
     def close(self):
         if self.h:

@@ -334,6 +334,13 @@ def test_cpp_headers_compile():
     subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-x", "c", os.path.join(inc, "ffgpu.h")], check=True)
     subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-Wall", "-x", "c++",
                     os.path.join(inc, "firefly_gpu", "GpuProbeQueue.hpp")], check=True)
+    # the adaptors over FireFly's own headers compile where those are available (this container)
+    ref_inc = "/root/reference/source/include"
+    gen_inc = os.path.join(ROOT, "oracle", "_ref", "inc")
+    if os.path.isdir(ref_inc) and os.path.isdir(gen_inc):
+        for h in ("GpuBlackBox.hpp", "GpuShuntingYardParser.hpp"):
+            subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-Wall", "-x", "c++", "-I", os.path.join(ROOT, "oracle", "shim"),
+                            "-I", gen_inc, "-I", ref_inc, "-I", inc, os.path.join(inc, "firefly_gpu", h)], check=True)
 
 
 # ---- functions of equal structure are evaluated once (sharing ACROSS functions) -----------------------
@@ -498,3 +505,156 @@ def test_random_collections_with_repeated_denominators(oracle, seed):
         want = oracle.parse(funs, vars_, p, check_is_equal=kw.get("check_is_equal", False)).eval(pts)
         assert par.cse_fallbacks == 0 and par.n_shared_denominators > 0
         assert np.array_equal(interp(par, pts, p), want), kw
+
+
+# ---- the rest of ShuntingYardParser's public interface: add_otf, parse_function, add_otf_precompute, trim ----
+def _small_functions(rng, vars_, n):
+    def atom():
+        return rng.choice(vars_) if rng.random() < 0.6 else str(rng.randint(1, 10 ** rng.randint(1, 12)))
+
+    def expr(d):
+        if d == 0 or rng.random() < 0.2:
+            return atom()
+        r = rng.random()
+        if r < 0.6:
+            return f"{expr(d-1)}{rng.choice('+-*/')}{expr(d-1)}"
+        if r < 0.75:
+            return f"({expr(d-1)})^{rng.randint(0, 12)}"
+        if r < 0.85:
+            return f"({expr(d-1)})"
+        return f"{atom()}^(-{rng.randint(1, 5)})"
+
+    return [expr(3) for _ in range(n)]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_add_otf_and_trim_vs_reference(ref, seed):
+    """Functions added on the fly and a trimmed parser give the positions, RPN strings and values of the reference's
+    add_otf / add_otf_precompute / trim (ShuntingYardParser.cpp:331-377, 720-776)."""
+    rng = random.Random(seed)
+    vars_ = ["x", "y", "z1"]
+    funs = _small_functions(rng, vars_, 24)
+    p = ff.primes()[seed]
+    ref.set_prime(p)
+    rp = ref.parse(funs[:8], vars_)
+    gp = ff.GpuParser(None, funs[:8], vars_)
+    for f in funs[8:20]:
+        assert gp.add_otf(f) == rp.add_otf(f)
+    assert gp.stale
+    rp.refresh()
+    gp.set_prime(p)
+    assert not gp.stale and gp.n_out == rp.n_out == 20 and gp.n_functions == rp.n_functions
+    assert [gp.get_rp_function(i) for i in range(20)] == [rp.rpn(i) for i in range(20)]
+    pts = ff.synthetic_points(3, 4, p, seed=seed)
+    pts[:, 0] = 0
+    assert np.array_equal(interp(gp, pts, p), rp.eval(pts))
+    # trim
+    keep = rng.sample(range(20), 11) + [25]              # 25 does not exist: ignored by both
+    assert gp.trim(keep) == rp.trim(keep)
+    rp.refresh()
+    gp.set_prime(p)
+    assert gp.n_out == rp.n_out == 11
+    assert [gp.get_rp_function(i) for i in range(11)] == [rp.rpn(i) for i in range(11)]
+    assert np.array_equal(interp(gp, pts, p), rp.eval(pts))
+    # functions that arrive as RPN tokens
+    for f in funs[20:]:
+        tokens = ff.GpuParser(None, [f], vars_).get_rp_function(0)
+        assert gp.add_otf_precompute(tokens) == rp.add_otf_precompute(tokens)
+    rp.refresh(force=False)                              # precompute_tokens(true) would drop them in the reference
+    gp.set_prime(p)
+    assert gp.n_out == rp.n_out == 15
+    assert np.array_equal(interp(gp, pts, p), rp.eval(pts))
+    # a new prime on the changed collection
+    p2 = ff.primes()[seed + 7]
+    gp.set_prime(p2)
+    want = ff.GpuParser(None, [funs[k] for k in sorted(set(keep) - {25})] + funs[20:], vars_)
+    want.set_prime(p2)
+    pts2 = ff.synthetic_points(3, 3, p2, seed=seed)
+    assert np.array_equal(interp(gp, pts2, p2), interp(want, pts2, p2))
+    rp.close()
+
+
+def test_parse_function_on_an_empty_parser_vs_reference(ref):
+    """The default-constructed parser filled by parse_function -- how Reconstructor builds its factor parsers
+    (Reconstructor.hpp:1873-1874)."""
+    vars_ = ["x1", "x2"]
+    p = P0
+    ref.set_prime(p)
+    rp = ref.parse([], vars_)
+    gp = ff.GpuParser(None, [], vars_)
+    for f, validate in (("(x1+3)*(x2-x1)^2", False), ("x1-+x2", True), ("((x1))/x2", True)):
+        rp.parse_function(f, vars_, validate)
+        gp.parse_function(f, validate)
+    rp.refresh()
+    gp.set_prime(p)
+    assert gp.n_out == rp.n_out == 3
+    assert [gp.get_rp_function(i) for i in range(3)] == [rp.rpn(i) for i in range(3)]
+    pts = ff.synthetic_points(2, 4, p, seed=5)
+    assert np.array_equal(interp(gp, pts, p), rp.eval(pts))
+    # operands missing: undefined behaviour in the reference, refused here
+    with pytest.raises(ff.FFGpuError):
+        gp.parse_function("x1+-x2", False)
+    rp.close()
+
+
+def test_trim_with_check_is_equal_vs_reference(ref, oracle):
+    """On a parser that checks for equal functions trim addresses OUTPUTS; kept outputs that share a function keep
+    sharing it (ShuntingYardParser.cpp:744-765)."""
+    vars_ = ["x", "y"]
+    funs = ["x+y", "x*y", "y+x", "(x+y)^2", "x^2+2*x*y+y^2", "x-y", "x*y", "3"]
+    p = P0
+    ref.set_prime(p)
+    rp = ref.parse(funs, vars_, True)
+    gp = ff.GpuParser(None, funs, vars_, True)
+    assert gp.n_functions == rp.n_functions == 5 and gp.n_out == rp.n_out == 8
+    keep = [2, 3, 4, 6, 7]
+    assert gp.trim(keep) == rp.trim(keep) == {2: 0, 3: 1, 4: 2, 6: 3, 7: 4}
+    rp.refresh(force=False)
+    gp.set_prime(p)
+    assert gp.n_functions == rp.n_functions == 4 and gp.n_out == rp.n_out == 5
+    pts = ff.synthetic_points(2, 4, p, seed=2)
+    want = oracle.parse([funs[k] for k in keep], vars_, p).eval(pts)
+    assert np.array_equal(interp(gp, pts, p), want)
+    assert np.array_equal(rp.eval(pts), want)
+    # on-the-fly additions on this parser: a twin returns its position and (unless no_duplicates) one more output.
+    # (The reference cannot be asked: its constructor clears the check points, ShuntingYardParser.cpp:557-559,
+    # so add_otf reads an empty vector there.)
+    assert gp.add_otf("y*x") == 2 and gp.n_out == 6
+    assert gp.add_otf("y+x", no_duplicates=True) == 0 and gp.n_out == 6
+    assert gp.add_otf("x^3") == 4 and gp.n_out == 7 and gp.n_functions == 5
+    gp.set_prime(p)
+    want = oracle.parse([funs[k] for k in keep] + ["y*x", "x^3"], vars_, p).eval(pts)
+    assert np.array_equal(interp(gp, pts, p), want)
+    with pytest.raises(ff.FFGpuError):
+        gp.parse_function("x")
+    rp.close()
+
+
+def test_changed_collection_needs_set_prime():
+    gp = ff.GpuParser(None, ["x"], ["x"])
+    gp.set_prime(P0)
+    gp.add_otf("x^2")
+    assert gp.stale
+    gp.set_factors({}, ["x"])                            # factors on a stale collection rebuild it as well
+    assert not gp.stale and gp.n_out == 2
+    gp.set_factors({1: "x"}, ["x"])
+    with pytest.raises(ff.FFGpuError):
+        gp.add_otf("x^3")
+    with pytest.raises(ff.FFGpuError):
+        gp.trim([0])
+
+
+def test_cpp_parser_mirror_host_logic(tmp_path):
+    """firefly::GpuShuntingYardParser against the reference ShuntingYardParser without evaluating anything: sizes, RPN
+    strings, add_otf positions, trim maps, copies, parse_function on an empty parser (oracle/parser_dropin.cpp)."""
+    import subprocess
+    binary = os.path.join(ROOT, "oracle", "_ref", "parser_dropin")
+    if not os.path.exists(binary):
+        pytest.skip("oracle/_ref/parser_dropin not built (needs /root/reference at build time)")
+    for name in ("s_y_4_v", "f2"):
+        g = load_golden(name)
+        f = tmp_path / (name + ".m")
+        f.write_text(";\n".join(g["functions"]) + ";\n")
+        r = subprocess.run([binary, "host", str(f), *g["vars"]], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert "0 differ" in r.stdout

@@ -40,3 +40,23 @@ def test_reconstruction_identical(tmp_path, name, bunch, threads):
     # the GPU black box really ran on the GPU
     launches = int(r.stdout.strip().split()[-1])
     assert launches > 0
+
+
+PARSER_BIN = os.path.join(ROOT, "oracle", "_ref", "parser_dropin")
+
+
+@pytest.mark.parametrize("name", ["s_y_4_v", "f2", "factors3"])
+def test_parser_mirror_matches_reference(tmp_path, name):
+    """firefly::GpuShuntingYardParser, the class a user black box holds instead of ShuntingYardParser: the values of
+    evaluate_pre<FFInt / FFIntVec<4> / FFIntVec<128>> over two primes, on copies, after add_otf, trim,
+    add_otf_precompute and parse_function, and (s_y_4_v) the reference's test_bunch black box reconstructed over it."""
+    if not os.path.exists(PARSER_BIN):
+        pytest.skip("oracle/_ref/parser_dropin not built (needs /root/reference at build time)")
+    g = load_golden(name)
+    f = tmp_path / (name + ".m")
+    f.write_text(";\n".join(g["functions"]) + ";\n")
+    r = subprocess.run([PARSER_BIN, "gpu", str(f), *g["vars"]], cwd=tmp_path, capture_output=True, text=True,
+                       timeout=1200)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "0 differ" in r.stdout
+    assert int(r.stdout.strip().split()[-1]) > 0
