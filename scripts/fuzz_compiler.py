@@ -14,6 +14,7 @@ import argparse
 import multiprocessing as mp
 import os
 import random
+import re
 import sys
 import time
 
@@ -138,6 +139,12 @@ def one_round(seed, rnd):
     nv = len(vars_)
     opts = dict(cse=rng.random() < 0.85, fuse=rng.random() < 0.85, cross=rng.random() < 0.85,
                 temps=rng.choice([0, 0, 0, 1, 2, 3, 5, 8]), check_is_equal=rng.random() < 0.2)
+    # Equality by value at one random point (check_is_equal, ShuntingYardParser.cpp:125-140) is not a property of two
+    # functions once an exponent depends on a variable: (-x)^(x) and (x)^(x) agree exactly when the check point is
+    # even, so the reference (time-seeded points) merges them in one run and not in the next.  Such collections are
+    # compared without the flag.
+    if opts["check_is_equal"] and any(re.search(r"\^\((?!-?\d+\))", f) for f in funs):
+        opts["check_is_equal"] = False
     table_primes = ff.primes()
     p1, p2 = rng.choice(table_primes), rng.choice(table_primes)
     npts = 7
