@@ -41,9 +41,53 @@ def functions_of(path):
     return out
 
 
+def executable_example(ref, primes):
+    """examples/firefly_executable/: the reference's own recorded probes (probes/<prime>.gz, one line per probe
+    `zi_order | t | f_1 f_2 f_3`) with the anchor points and shifts they were taken at -- the only numbers the
+    reference ships for this path.  The black box behind them is not shipped; the records are those of {0, 1, x1}
+    over three variables (f_3 - t is shift[0] of the prime in every line, with the modular wrap on three of them),
+    which is what the fixture assumes.  Points as Reconstructor::queue_probes builds them (Reconstructor.hpp:2946-2950):
+    x_1 = t + shift_1, x_i = anchor_{i-1}^{zi_{i-1}} * t + shift_i."""
+    import gzip
+    d = os.path.join(REF, "examples", "firefly_executable")
+    anchors = [[int(x) for x in ln.split()] for ln in open(os.path.join(d, "anchor_points")) if ln.strip()]
+    shifts = [[int(x) for x in ln.split()] for ln in open(os.path.join(d, "shifts")) if ln.strip()]
+    vars_, funs = ["x1", "x2", "x3"], ["0", "1", "x1"]
+    doc = {"source": "examples/firefly_executable (anchor_points, shifts, probes/*.gz); black box inferred: {0, 1, x1}",
+           "vars": vars_, "functions": funs, "rpn": None, "anchor_points": [[str(x) for x in r] for r in anchors],
+           "shifts": [[str(x) for x in r] for r in shifts], "cases": []}
+    for pi in range(3):
+        p = primes[pi]
+        ref.set_prime(p)
+        par = ref.parse(funs, vars_)
+        if doc["rpn"] is None:
+            doc["rpn"] = [par.rpn(i) for i in range(par.n_functions)]
+        lines = [ln for ln in gzip.open(os.path.join(d, "probes", f"{pi}.gz"), "rt").read().split("\n") if ln.strip()]
+        pts, vals, probes = [], [], []
+        for ln in lines:
+            zi, t, fv = ln.split("|")
+            zi, t, fv = [int(x) for x in zi.split()], int(t), [int(x) for x in fv.split()]
+            a = [1] + [pow(anchors[pi][i], zi[i], p) for i in range(2)]
+            pts.append([(a[i] * t + shifts[pi][i]) % p for i in range(3)])
+            vals.append(fv)
+            probes.append({"zi_order": zi, "t": str(t), "line": ln})
+        pts = np.array(pts, dtype=np.uint64).T.copy()
+        vals = np.array(vals, dtype=np.uint64).T.copy()
+        assert np.array_equal(par.eval(pts), vals), "the recorded probes are not those of {0, 1, x1}"
+        doc["cases"].append({"prime": str(p), "points": [[str(int(x)) for x in row] for row in pts],
+                             "values": [[str(int(x)) for x in row] for row in vals], "probes": probes})
+        par.close()
+    with open(os.path.join(HERE, "firefly_executable.json"), "w") as f:
+        json.dump(doc, f, indent=0, separators=(",", ":"))
+    print("firefly_executable: recorded probes per prime", [len(c["probes"]) for c in doc["cases"]])
+
+
 def main():
     ref = Ref()
     primes = [ref.lib.ffref_prime(i) for i in range(300)]
+    executable_example(ref, primes)
+    if len(sys.argv) > 1 and sys.argv[1] == "--example-only":
+        return
     sets = {
         "s_y_4_v": ("parser_test/s_y_4_v.m", ["x1", "y", "zZ", "W"]),
         "s_y_1_v": ("parser_test/s_y_1_v.m", ["x"]),

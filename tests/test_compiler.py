@@ -267,11 +267,21 @@ def test_offline_probe_files_round_trip(tmp_path):
     assert o2 == orders and t2 == ts and np.array_equal(v2, vals)
     with pytest.raises(ValueError, match="variables"):
         offline.read_requested(str(req), 4)
-    # the reference's own example file parses (format check only: the functions behind it are not shipped)
-    ex = "/root/reference/examples/firefly_executable/probes/0.gz"
-    if os.path.exists(ex):
-        o, t, v = offline.read_probes(ex)
-        assert len(o) == len(t) == v.shape[1] > 0 and v.shape[0] == 3
+    # the reference's own recorded probe lines (tests/golden/firefly_executable.json) parse to their numbers and are
+    # written back character for character
+    g = load_golden("firefly_executable")
+    for k, case in enumerate(g["cases"]):
+        lines = [pr["line"] for pr in case["probes"]]
+        src = tmp_path / f"ref_{k}.gz"
+        with gzip.open(src, "wt") as f:
+            f.write("\n".join(lines) + "\n")
+        o, t, v = offline.read_probes(str(src))
+        assert o == [" ".join(str(z) for z in pr["zi_order"]) for pr in case["probes"]]
+        assert t == [int(pr["t"]) for pr in case["probes"]] and np.array_equal(v, case["values"])
+        back = tmp_path / f"back_{k}.gz"
+        offline.write_probes(str(back), o, t, v)
+        with gzip.open(back, "rt") as f:
+            assert f.read().splitlines() == lines
 
 
 @pytest.mark.parametrize("cse,fuse", [(True, True), (True, False), (False, True), (False, False)])
