@@ -14,7 +14,9 @@
 // exit 0 = identical, 1 = different, 2 = usage
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
+#include <stdexcept>
 #include <string>
 #include <unordered_set>
 #include <vector>
@@ -42,7 +44,7 @@ namespace firefly {
 template <typename Parser>
 class BlackBoxUser : public BlackBoxBase<BlackBoxUser<Parser>> {
  public:
-  BlackBoxUser(const Parser& par_) : par(par_) {}
+  BlackBoxUser(const Parser& par_, int abort_at_ = 0) : par(par_), abort_at(abort_at_) {}
   template <typename FFIntTemp>
   std::vector<FFIntTemp> operator()(const std::vector<FFIntTemp>& values) {
     std::vector<FFIntTemp> result = par.evaluate_pre(values);
@@ -53,10 +55,15 @@ class BlackBoxUser : public BlackBoxBase<BlackBoxUser<Parser>> {
     result.emplace_back(calc_determinant_lu(mat, p, 2));
     return result;
   }
-  inline void prime_changed() { par.precompute_tokens(); }
+  inline void prime_changed() {
+    par.precompute_tokens();
+    // test/test_save_write.cpp:51-60: give up when a later prime starts, the states are on disk by then
+    if (abort_at && ++c == abort_at) throw std::runtime_error("Abort for save test.");
+  }
 
  private:
   Parser par;
+  int abort_at = 0, c = 0;
 };
 }  // namespace firefly
 
@@ -110,10 +117,86 @@ static std::vector<std::string> reconstruct_all(BB& bb, uint32_t n, const std::v
   return out;
 }
 
+// RationalFunction::to_string lists the monomials in hash-map order, which differs between a resumed and an
+// uninterrupted run: sort the '+'-separated terms of every top-level parenthesis.
+static std::string canon(const std::string& f) {
+  std::string out;
+  std::vector<std::string> terms;
+  std::string cur;
+  int depth = 0;
+  for (char ch : f) {
+    if (ch == '(' && depth++ == 0) { out += ch; continue; }
+    if (ch == ')' && --depth == 0) {
+      terms.push_back(cur);
+      cur.clear();
+      std::sort(terms.begin(), terms.end());
+      for (size_t i = 0; i < terms.size(); ++i) out += (i ? "+" : "") + terms[i];
+      terms.clear();
+      out += ch;
+      continue;
+    }
+    if (depth == 0) out += ch;
+    else if (depth == 1 && ch == '+') { terms.push_back(cur); cur.clear(); }
+    else cur += ch;
+  }
+  return out;
+}
+
+// The reference's save / resume flow (test/test_save_write.cpp:139-157): a run over the CPU parser writes its states
+// (ff_save/ in the working directory) and aborts when the second prime starts; a second Reconstructor resumes from
+// them over `Resumed` -- which first has to reproduce ff_save/validation.gz, the reference's own known-answer check
+// of the black box (Reconstructor.hpp:626-657) -- and must finish with the functions of the uninterrupted run.
+template <typename Resumed>
+static void save_and_resume(const std::string& file, const std::vector<std::string>& vars,
+                            const std::vector<std::string>& want) {
+  const uint32_t n = (uint32_t)vars.size();
+  bool aborted = false;
+  FFInt::set_new_prime(primes()[0]);
+  try {
+    ShuntingYardParser p(file, vars);
+    BlackBoxUser<ShuntingYardParser> b(p, 2);
+    Reconstructor<BlackBoxUser<ShuntingYardParser>> r(n, 4, 4, b, Reconstructor<BlackBoxUser<ShuntingYardParser>>::SILENT);
+    r.enable_shift_scan();
+    r.set_tags();
+    r.reconstruct();
+  } catch (std::exception& e) {
+    aborted = true;
+  }
+  RatReconst::reset();
+  CHECK(aborted, "save/resume: the first run finished in one prime, nothing was resumed");
+  if (!aborted) return;
+  Resumed p2(file, vars);
+  BlackBoxUser<Resumed> b2(p2);
+  Reconstructor<BlackBoxUser<Resumed>> r2(n, 4, 4, b2, Reconstructor<BlackBoxUser<Resumed>>::SILENT);
+  r2.set_tags();
+  r2.resume_from_saved_state();
+  r2.reconstruct();
+  std::vector<std::string> got;
+  for (const auto& rf : r2.get_result()) got.push_back(rf.to_string(vars));
+  RatReconst::reset();
+  CHECK(want.size() == got.size(), "save/resume: %zu vs %zu functions", want.size(), got.size());
+  for (size_t i = 0; i < want.size() && i < got.size(); ++i)
+    CHECK(canon(want[i]) == canon(got[i]), "save/resume: function %zu differs:\n  %.300s\n  %.300s", i,
+          canon(want[i]).c_str(), canon(got[i]).c_str());
+  std::printf("resumed from the saved states: %zu functions\n", got.size());
+}
+
 int main(int argc, char** argv) {
-  if (argc < 4 || (std::strcmp(argv[1], "host") && std::strcmp(argv[1], "gpu"))) {
-    std::fprintf(stderr, "usage: parser_dropin host|gpu <file.m> <var>...\n");
+  if (argc < 4 || (std::strcmp(argv[1], "host") && std::strcmp(argv[1], "gpu") && std::strcmp(argv[1], "resume-cpu"))) {
+    std::fprintf(stderr, "usage: parser_dropin host|gpu|resume-cpu <file.m> <var>...\n");
     return 2;
+  }
+  if (!std::strcmp(argv[1], "resume-cpu")) {
+    // the harness of the save / resume check with the reference parser on both sides (runs without a GPU)
+    std::vector<std::string> vars;
+    for (int i = 3; i < argc; ++i) vars.emplace_back(argv[i]);
+    FFInt::set_new_prime(primes()[0]);
+    ShuntingYardParser pc(argv[2], vars);
+    BlackBoxUser<ShuntingYardParser> bc(pc);
+    const std::vector<std::string> want = reconstruct_all(bc, (uint32_t)vars.size(), vars);
+    save_and_resume<ShuntingYardParser>(argv[2], vars, want);
+    std::printf("resume-cpu checks done, %d differ, gpu kernel launches 0\n", bad);
+    return bad ? 1 : 0;
   }
   const bool gpu = !std::strcmp(argv[1], "gpu");
   const std::string file = argv[2];
@@ -215,6 +298,7 @@ int main(int argc, char** argv) {
     CHECK(want.size() == got.size(), "reconstruction: %zu vs %zu functions", want.size(), got.size());
     for (size_t i = 0; i < want.size() && i < got.size(); ++i) CHECK(want[i] == got[i], "reconstructed function %zu differs", i);
     std::printf("%zu functions reconstructed over the GPU parser\n", got.size());
+    save_and_resume<GpuShuntingYardParser>(file, vars, want);
   }
 
   std::printf("%s checks done, %d differ, gpu kernel launches %llu\n", argv[1], bad, (unsigned long long)ffgpu_launch_count());

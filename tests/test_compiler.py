@@ -668,3 +668,8 @@ def test_cpp_parser_mirror_host_logic(tmp_path):
         r = subprocess.run([binary, "host", str(f), *g["vars"]], cwd=tmp_path, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         assert "0 differ" in r.stdout
+    # the save / resume harness of the GPU suite, here with the reference parser on both sides
+    g = load_golden("s_y_4_v")
+    r = subprocess.run([binary, "resume-cpu", str(tmp_path / "s_y_4_v.m"), *g["vars"]], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "resumed from the saved states: 21 functions" in r.stdout, r.stdout[-2000:]

@@ -49,7 +49,9 @@ PARSER_BIN = os.path.join(ROOT, "oracle", "_ref", "parser_dropin")
 def test_parser_mirror_matches_reference(tmp_path, name):
     """firefly::GpuShuntingYardParser, the class a user black box holds instead of ShuntingYardParser: the values of
     evaluate_pre<FFInt / FFIntVec<4> / FFIntVec<128>> over two primes, on copies, after add_otf, trim,
-    add_otf_precompute and parse_function, and (s_y_4_v) the reference's test_bunch black box reconstructed over it."""
+    add_otf_precompute and parse_function, and (s_y_4_v) the reference's test_bunch black box reconstructed over it,
+    uninterrupted and resumed from states a CPU run saved (test/test_save_write.cpp's flow: the GPU black box has to
+    reproduce ff_save/validation.gz, the reference's own known-answer check, Reconstructor.hpp:626-657)."""
     if not os.path.exists(PARSER_BIN):
         pytest.skip("oracle/_ref/parser_dropin not built (needs /root/reference at build time)")
     g = load_golden(name)
