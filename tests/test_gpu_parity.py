@@ -460,38 +460,6 @@ def test_offline_probe_service(ctx, oracle, tmp_path):
     assert np.array_equal(vals, oracle.parse(g["functions"], g["vars"], p).eval(pts))
 
 
-def test_reference_recorded_probes(ctx, tmp_path):
-    """The probes the reference ships (examples/firefly_executable/probes/*.gz, three primes) come out of the offline
-    service line for line, and out of ffgpu_eval_line from (anchor points, shifts, zi_order, t) alone."""
-    import gzip
-    from firefly_b200 import offline
-    g = load_golden("firefly_executable")
-    fn = tmp_path / "funs.m"
-    fn.write_text(";\n".join(g["functions"]) + ";\n")
-    par = ff.GpuParser(ctx, g["functions"], g["vars"])
-    for k, case in enumerate(g["cases"]):
-        p = case["prime"]
-        assert p == ff.primes()[k]
-        req = tmp_path / f"requested_{k}.gz"
-        with gzip.open(req, "wt") as f:
-            for j, pr in enumerate(case["probes"]):
-                f.write(" ".join(str(z) for z in pr["zi_order"]) + f" | {pr['t']} | "
-                        + " ".join(str(int(x)) for x in case["points"][:, j]) + "\n")
-        out = tmp_path / "probes" / f"{k}.gz"
-        assert offline.serve(str(fn), g["vars"], k, str(req), str(out)) == len(case["probes"])
-        with gzip.open(out, "rt") as f:
-            assert f.read().splitlines() == [pr["line"] for pr in case["probes"]]
-        # the same probes from the line parameters: x_1 = t + s_1, x_i = anchor_{i-1}^zi_{i-1} * t + s_i
-        par.set_prime(p)
-        anchors = [int(x) for x in g["anchor_points"][k]]
-        shifts = np.array([int(x) for x in g["shifts"][k]], dtype=np.uint64)
-        for j, pr in enumerate(case["probes"]):
-            a = np.array([1] + [pow(anchors[i], pr["zi_order"][i], p) for i in range(2)], dtype=np.uint64)
-            t = np.array([int(pr["t"])], dtype=np.uint64)
-            assert np.array_equal(par.evaluate_line(a, shifts, t)[:, 0], case["values"][:, j]), (k, j)
-    par.close()
-
-
 def test_mpi_wire_format(ctx, oracle):
     """[index, x_1..x_n]*k in, [index, f_1..f_m]*k out -- what an MPIWorker exchanges with the master"""
     g = load_golden("s_y_4_v")
