@@ -15,6 +15,16 @@
  *     Reconstructor.hpp:3383,3440, MPIWorker.hpp:475
  *   ShuntingYardParser::get_rp_function(i)                           ffgpu_rpn
  *     source/ShuntingYardParser.cpp:534-536
+ *   ShuntingYardParser::add_otf / parse_function                     ffgpu_add_function
+ *     source/ShuntingYardParser.cpp:347-377, 315-329
+ *   ShuntingYardParser::add_otf_precompute   :331-341                ffgpu_add_function_rpn
+ *   ShuntingYardParser::trim                 :720-776                ffgpu_trim
+ *   copying a parser (black boxes hold one by value)                 ffgpu_tape_clone
+ *   parsed_factors[i].evaluate_pre(values)[0] divided out            ffgpu_set_factors
+ *     Reconstructor.hpp:3392-3396, 3449-3457                           (the division joins the tape)
+ *   MPIWorker VALUES / RESULT messages  MPIWorker.hpp:213-228,479-501  ffgpu_eval_wire
+ *   requested_probes / computed_probes, get_job, get_probe           ffgpu_queue_*
+ *     Reconstructor.hpp:245-246, 2962-3012, 3326-3477
  *   primes()   source/ReconstHelper.cpp:24-125                       ffgpu_prime / ffgpu_n_primes
  *   Reconstructor::queue_probes point construction                   ffgpu_eval_line
  *     source/include/firefly/Reconstructor.hpp:2946-2960               (x_v = a_v * t + s_v on the GPU)
