@@ -1,5 +1,5 @@
-// b63_model.c -- word-level C model of the device multiplication and squaring (firefly_b200/csrc/ff63.cuh,
-// mul_b63_w / sqr_b63_w): the same steps with explicit widths, every "cannot overflow" claim of the PTX as an
+// b63_model.c -- word-level C model of the device arithmetic (firefly_b200/csrc/ff63.cuh: mul_b63_w / sqr_b63_w,
+// add_b63_w / sub_b63_w / neg_b63_w, canon_pm): the same steps with explicit widths, every "cannot overflow" claim of the PTX as an
 // assert, the result compared with (x*y) mod p from unsigned __int128 on edge and random operands below the
 // representation bound 2^63 + 2^32, including operands that force the carry output of the multiplier.
 // Test infrastructure (tests/test_arith_model.py compiles and runs it); not part of the product.
@@ -66,6 +66,59 @@ static u64 sqrN(u64 x) {
   n_carry += cA;
   return res;
 }
+// add_b63_w: s = a + b with carry k; the carry and bit 63 together are worth (2k + b63) * c
+static u64 addN(u64 a, u64 b) {
+  u32 a0 = (u32)a, a1 = a >> 32, b0 = (u32)b, b1 = b >> 32;
+  u64 lo = (u64)a0 + b0; u32 s0 = (u32)lo;
+  u64 hi = (u64)a1 + b1 + (lo >> 32); u32 s1 = (u32)hi; u32 k = (u32)(hi >> 32);
+  u32 top = (k << 1) | (s1 >> 31); assert(top <= 2);
+  s1 &= 0x7fffffffu;
+  u32 t = top * c; assert((u64)top * c < (1ULL << 32));
+  u64 r0 = (u64)s0 + t; u64 r1 = (u64)s1 + (r0 >> 32); assert((r1 >> 32) == 0);
+  u64 res = (r1 << 32) | (u32)r0;
+  assert(res < (1ULL << 63) + (1ULL << 16));               // the bound ff63.cuh states
+  assert(res < Bnd);
+  return res;
+}
+// sub_b63_w: a - b = a + (2p - b), 2p = 2^64 - d; the sum is below 2^65: top in {0..3}
+static u64 subN(u64 a, u64 b) {
+  u32 a0 = (u32)a, a1 = a >> 32, b0 = (u32)b, b1 = b >> 32;
+  u32 n0 = 0u - d;                                         // low word of 2p
+  u64 m = (((u64)0xffffffffu << 32) | n0) - b;             // sub.cc / subc: no borrow out, b <= 2p
+  assert(b <= (((u64)0xffffffffu << 32) | n0));
+  u32 m0 = (u32)m, m1 = m >> 32; (void)b0; (void)b1;
+  u64 lo = (u64)a0 + m0; u32 s0 = (u32)lo;
+  u64 hi = (u64)a1 + m1 + (lo >> 32); u32 s1 = (u32)hi; u32 k = (u32)(hi >> 32);
+  u32 top = (k << 1) | (s1 >> 31); assert(top <= 3);
+  s1 &= 0x7fffffffu;
+  u32 t = top * c;
+  u64 r0 = (u64)s0 + t; u64 r1 = (u64)s1 + (r0 >> 32); assert((r1 >> 32) == 0);
+  u64 res = (r1 << 32) | (u32)r0;
+  assert(res < (1ULL << 63) + (1ULL << 17));
+  assert(res < Bnd);
+  return res;
+}
+// neg_b63_w: -a = 2p - a, folded at bit 63
+static u64 negN(u64 a) {
+  u32 n0 = 0u - d;
+  u64 s = (((u64)0xffffffffu << 32) | n0) - a;
+  u32 s0 = (u32)s, s1 = s >> 32;
+  u32 top = s1 >> 31;
+  s1 &= 0x7fffffffu;
+  u32 t = top * c;
+  u64 r0 = (u64)s0 + t; u64 r1 = (u64)s1 + (r0 >> 32); assert((r1 >> 32) == 0);
+  u64 res = (r1 << 32) | (u32)r0;
+  assert(res < Bnd);
+  return res;
+}
+// canon_pm: v = b * 2^63 + l  ->  l + b * c < 2^63 + c < 2p, one conditional subtraction
+static u64 canonN(u64 v) {
+  u64 l = (v & 0x7fffffffffffffffULL) + ((v >> 63) ? (u64)c : 0ULL);
+  assert(l < 2 * P);
+  u64 r = l >= P ? l - P : l;
+  assert(r < P && r == v % P);
+  return r;
+}
 static u64 rnd(void) { static u64 s = 88172645463325252ULL; s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; }
 int main(int argc, char** argv) {
   const long n_random = argc > 1 ? atol(argv[1]) : 2000000;
@@ -79,6 +132,10 @@ int main(int argc, char** argv) {
     for (int i = 0; i < ne; i++) for (int j = 0; j < ne; j++) {
       u64 r = mulN(edge[i], edge[j]); assert(r % P == (u64)(((u128)edge[i] * edge[j]) % P));
       if (i == j) { u64 s = sqrN(edge[i]); assert(s % P == r % P); }
+      const u64 x = edge[i], y = edge[j];
+      assert(addN(x, y) % P == (u64)(((u128)x + y) % P));
+      assert(subN(x, y) % P == (u64)(((u128)x + 2 * (u128)P - y) % P));
+      if (i == j) { assert(negN(x) % P == (u64)((2 * (u128)P - x) % P)); canonN(x); canonN(r); }
       n++;
     }
     for (long k = 0; k < n_random; k++) {
@@ -90,6 +147,15 @@ int main(int argc, char** argv) {
       x %= Bnd; y %= Bnd;
       u64 r = mulN(x, y); assert(r % P == (u64)(((u128)x * y) % P));
       u64 s = sqrN(x); assert(s % P == (u64)(((u128)x * x) % P));
+      // additions and subtractions of results of every kind stay inside the representation
+      u64 ad = addN(x, y), sb = subN(x, y), ng = negN(x);
+      assert(ad % P == (u64)(((u128)x + y) % P));
+      assert(sb % P == (u64)(((u128)x + 2 * (u128)P - y) % P));
+      assert(ng % P == (u64)((2 * (u128)P - x) % P));
+      assert(addN(ad, sb) % P == (u64)(((u128)ad + sb) % P));
+      assert(subN(ng, r) % P == (u64)(((u128)ng + 2 * (u128)P - r) % P));
+      assert(mulN(ad, sb) % P == (u64)(((u128)ad * sb) % P));
+      canonN(ad); canonN(sb); canonN(ng); canonN(r); canonN(s);
       n++;
     }
   }

@@ -1,5 +1,6 @@
-"""The word-level algorithm of the device multiplication (ff63.cuh, mul_b63_w / sqr_b63_w) restated in C with
-every no-overflow claim as an assert, against unsigned __int128 -- runs without a GPU.  The GPU side of the same
+"""The word-level algorithms of the device arithmetic (ff63.cuh: mul_b63_w / sqr_b63_w, add_b63_w / sub_b63_w /
+neg_b63_w, canon_pm) restated in C with every no-overflow claim and every stated bound of the lazy representation as
+an assert (results of one operation are fed into the next), against unsigned __int128 -- runs without a GPU.  The GPU side of the same
 check is test_field_ops_lazy_inputs."""
 import os
 import subprocess
