@@ -119,6 +119,26 @@ static u64 canonN(u64 v) {
   assert(r < P && r == v % P);
   return r;
 }
+// inv_fermat (kernels.cu): x^(p-2), p - 2 = (2^47 - 1) * 2^16 + (2^16 - c - 2); 2^47 - 1 by the addition chain
+// 1,2,3,5,10,20,23,46,47 on the run length, then 16 squarings interleaved with the bits of the tail
+static u64 sqr_n(u64 x, int n) { while (n--) x = sqrN(x); return x; }
+static u64 invN(u64 x) {
+  const u64 x1 = x;
+  const u64 x2 = mulN(sqrN(x1), x1);
+  const u64 x3 = mulN(sqrN(x2), x1);
+  const u64 x5 = mulN(sqr_n(x3, 2), x2);
+  const u64 x10 = mulN(sqr_n(x5, 5), x5);
+  const u64 x20 = mulN(sqr_n(x10, 10), x10);
+  const u64 x23 = mulN(sqr_n(x20, 3), x3);
+  const u64 x46 = mulN(sqr_n(x23, 23), x23);
+  u64 r = mulN(sqrN(x46), x1);
+  const u32 tail = 65536u - c - 2u;
+  for (int bit = 15; bit >= 0; --bit) {
+    r = sqrN(r);
+    if ((tail >> bit) & 1) r = mulN(r, x1);
+  }
+  return r;
+}
 static u64 rnd(void) { static u64 s = 88172645463325252ULL; s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; }
 int main(int argc, char** argv) {
   const long n_random = argc > 1 ? atol(argv[1]) : 2000000;
@@ -135,7 +155,11 @@ int main(int argc, char** argv) {
       const u64 x = edge[i], y = edge[j];
       assert(addN(x, y) % P == (u64)(((u128)x + y) % P));
       assert(subN(x, y) % P == (u64)(((u128)x + 2 * (u128)P - y) % P));
-      if (i == j) { assert(negN(x) % P == (u64)((2 * (u128)P - x) % P)); canonN(x); canonN(r); }
+      if (i == j) {
+        assert(negN(x) % P == (u64)((2 * (u128)P - x) % P)); canonN(x); canonN(r);
+        const u64 iv = invN(x);                              // 0 -> 0, else x * x^(p-2) = 1
+        assert((u64)(((u128)(iv % P) * (x % P)) % P) == (x % P ? 1 : 0));
+      }
       n++;
     }
     for (long k = 0; k < n_random; k++) {
@@ -156,6 +180,7 @@ int main(int argc, char** argv) {
       assert(subN(ng, r) % P == (u64)(((u128)ng + 2 * (u128)P - r) % P));
       assert(mulN(ad, sb) % P == (u64)(((u128)ad * sb) % P));
       canonN(ad); canonN(sb); canonN(ng); canonN(r); canonN(s);
+      if ((k & 1023) == 0) { const u64 iv = invN(x); assert((u64)(((u128)(iv % P) * (x % P)) % P) == (x % P ? 1 : 0)); }
       n++;
     }
   }
