@@ -142,7 +142,7 @@ static u64 invN(u64 x) {
 static u64 rnd(void) { static u64 s = 88172645463325252ULL; s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; }
 int main(int argc, char** argv) {
   const long n_random = argc > 1 ? atol(argv[1]) : 2000000;
-  u32 cs[] = {25, 165, 13797, 1, 32767};
+  u32 cs[] = {25, 165, 13797, 1, 32767};     // the first three are primes of FireFly's table, the others stress the widths
   long n = 0, ncA = 0;
   for (int ci = 0; ci < 5; ci++) {
     c = cs[ci]; d = 2*c; P = (1ULL<<63) - c;
@@ -157,8 +157,8 @@ int main(int argc, char** argv) {
       assert(subN(x, y) % P == (u64)(((u128)x + 2 * (u128)P - y) % P));
       if (i == j) {
         assert(negN(x) % P == (u64)((2 * (u128)P - x) % P)); canonN(x); canonN(r);
-        const u64 iv = invN(x);                              // 0 -> 0, else x * x^(p-2) = 1
-        assert((u64)(((u128)(iv % P) * (x % P)) % P) == (x % P ? 1 : 0));
+        const u64 iv = ci < 3 ? invN(x) : 0;                 // 0 -> 0, else x * x^(p-2) = 1 (the prime moduli only)
+        assert(ci >= 3 || (u64)(((u128)(iv % P) * (x % P)) % P) == (x % P ? 1 : 0));
       }
       n++;
     }
@@ -180,7 +180,7 @@ int main(int argc, char** argv) {
       assert(subN(ng, r) % P == (u64)(((u128)ng + 2 * (u128)P - r) % P));
       assert(mulN(ad, sb) % P == (u64)(((u128)ad * sb) % P));
       canonN(ad); canonN(sb); canonN(ng); canonN(r); canonN(s);
-      if ((k & 1023) == 0) { const u64 iv = invN(x); assert((u64)(((u128)(iv % P) * (x % P)) % P) == (x % P ? 1 : 0)); }
+      if (ci < 3 && (k & 1023) == 0) { const u64 iv = invN(x); assert((u64)(((u128)(iv % P) * (x % P)) % P) == (x % P ? 1 : 0)); }
       n++;
     }
   }
