@@ -197,7 +197,7 @@ class GpuShuntingYardParser {
     ERROR_MSG(msg);
     std::exit(EXIT_FAILURE);
   }
-  unsigned flags() const { return check_is_equal ? FFGPU_CHECK_IS_EQUAL : 0u; }
+  unsigned flags() const { return check_is_equal ? static_cast<unsigned>(FFGPU_CHECK_IS_EQUAL) : 0u; }
   void need_tape(const char* what) const {
     if (!tape_) die(std::string(what) + " on a parser without variables: construct it with vars or call parse_function first");
   }
