@@ -34,27 +34,52 @@ while time.time()-t0 < float(sys.argv[2]):
     chk = rng.random()<0.4 and not any(__import__('re').search(r"\^\((?!-?\d+\))", f) for f in funs)
     k = rng.randint(0,len(funs)-1)
     opts=dict(cse=rng.random()<0.8, fuse=rng.random()<0.8, cross=rng.random()<0.8, temps=rng.choice([0,0,2,5]))
-    par = ff.GpuParser(None, funs[:k], vars_, chk, **opts)
+    head = 0 if chk else k                                  # without the flag the head goes through the constructor
+    par = ff.GpuParser(None, funs[:head], vars_, chk, **opts)
     p = rng.choice(ff.primes())
     if rng.random()<0.5: par.set_prime(p)
-    cur = list(funs[:k])       # expected OUTPUT list
-    for f in funs[k:]:
-        nd = chk and rng.random()<0.3
+    # Model of what the parser holds: the texts of its distinct functions and, per output, which of them it returns.
+    # With check_is_equal the parser decides by VALUE at a random point which functions are the same (as the
+    # reference does: x2/x2 and (..)^0 are "equal" although they differ at x2 = 0), so the model takes that decision
+    # from the returned position and checks everything else: positions handed out, outputs kept by trim, the
+    # renumbering, the values.
+    texts, outs = list(funs[:head]), list(range(head))
+
+    def model_add(f, pos, n_out_before):
+        if pos == len(texts):
+            texts.append(f)
+        assert pos < len(texts), (pos, len(texts))
+        if par.n_out > n_out_before:
+            outs.append(pos)
+
+    for f in funs[head:]:
+        nd = chk and rng.random() < 0.3
         before = par.n_out
-        par.add_otf(f, nd)
-        if par.n_out>before: cur.append(f)
-    if rng.random()<0.7 and cur:
-        keep = sorted(rng.sample(range(len(cur)), rng.randint(1,len(cur))))
+        pos = par.add_otf(f, nd)
+        if not chk:
+            assert pos == len(texts)
+        model_add(f, pos, before)
+        if rng.random() < 0.1:
+            par.set_prime(p)                          # a rebuild in between
+    if rng.random() < 0.7 and outs:
+        keep = sorted(rng.sample(range(len(outs)), rng.randint(1, len(outs))))
         m = par.trim(keep)
-        assert sorted(m.keys())==keep and [m[q] for q in keep]==list(range(len(keep))), (m, keep)
-        cur=[cur[q] for q in keep]
-        # more additions after the trim
-        for f in rng.sample(funs, min(3,len(funs))):
+        assert sorted(m.keys()) == keep and [m[q] for q in keep] == list(range(len(keep))), (m, keep)
+        nt, no, copied = [], [], {}
+        for i in keep:
+            fn = outs[i]
+            if fn not in copied:
+                copied[fn] = len(nt)
+                nt.append(texts[fn])
+            no.append(copied[fn])
+        texts, outs = nt, no
+        assert par.n_functions == len(texts), (par.n_functions, len(texts))
+        for f in rng.sample(funs, min(3, len(funs))):
             before = par.n_out
-            par.add_otf(f, False)
-            if par.n_out>before: cur.append(f)
+            model_add(f, par.add_otf(f, False), before)
     par.set_prime(p)
-    assert par.n_out==len(cur), (par.n_out, len(cur))
+    assert par.n_out == len(outs) and par.n_functions == len(texts), (par.n_out, len(outs), par.n_functions, len(texts))
+    cur = [texts[i] for i in outs]
     pts = ff.synthetic_points(nv, 4, p, seed=rounds); pts[:,0]=0; pts[:,1]=1
     want = orc.parse(cur, vars_, p).eval(pts)
     tape = par.tape()
