@@ -1786,7 +1786,11 @@ bool Collection::resolve(uint64_t p, std::string& err) {
     err = "prime must be below 2^63";
     return false;
   }
-  if (stale && !finish(err)) return false;
+  if (stale && !finish(err)) {
+    stale = true;              // nothing usable was built: evaluation keeps refusing
+    prime = 0;
+    return false;
+  }
   std::vector<uint64_t> val;
   uint32_t cur = ~0u;
   for (const ConstPatch& cp : patches) {
