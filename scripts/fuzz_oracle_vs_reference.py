@@ -4,8 +4,9 @@ INFRASTRUCTURE, runs without a GPU, needs `make -C oracle ref`.
 Random collections from the grammar of scripts/fuzz_compiler.py (inputs the reference cannot evaluate -- an operator
 without operands pops an empty std::stack there -- are dropped first, using the product's compiler as the filter);
 RPN strings and values of evaluate_pre<FFInt> and evaluate_pre<FFIntVec<4>> are compared on edge and random points
-for two primes, the second one reached through precompute_tokens() on the same parser -- unless a function holds
-`x/(a/b)`: the reference's recipe for that fold keeps only `a` after a prime change (ShuntingYardParser.cpp:641,
+for two primes, the second one reached through precompute_tokens() on the same parser -- unless a function holds a
+quotient of constants, as in `x/(a/b)` or `x/((a/b)/c)`: the reference's recipe for that fold keeps only `a` after a
+prime change (ShuntingYardParser.cpp:641,
 DESIGN.md section 2 (ii)), so those collections are parsed afresh for the second prime.  Variable exponents are left
 out of the bunched comparison (FFIntVec::to_neg_int reads lane 0 only, DESIGN.md section 2).
 
@@ -60,8 +61,20 @@ def main():
             return t.lstrip("+-")[:1].isdigit()
 
         rpns = [rp.rpn(i) for i in range(len(funs))]
-        stale_fold = any(is_num(r[i]) and is_num(r[i + 1]) and r[i + 2] == "/" and r[i + 3] == "/"
-                         for r in rpns for i in range(len(r) - 3))
+
+        def has_constant_quotient(r):
+            st = []                                    # True = constant sub-expression
+            for t in r:
+                if len(t) == 1 and t in "+-*/^!~;":
+                    b, a = st.pop(), st.pop()
+                    if t == "/" and a and b:
+                        return True
+                    st.append(a and b)
+                else:
+                    st.append(is_num(t))
+            return False
+
+        stale_fold = any(has_constant_quotient(r) for r in rpns)
         for k, p in enumerate((p1, p2)):
             if k:
                 ref.set_prime(p)
