@@ -661,7 +661,7 @@ def test_cpp_parser_mirror_host_logic(tmp_path):
     binary = os.path.join(ROOT, "oracle", "_ref", "parser_dropin")
     if not os.path.exists(binary):
         pytest.skip("oracle/_ref/parser_dropin not built (needs /root/reference at build time)")
-    for name in ("s_y_4_v", "f2"):
+    for name in ("s_y_4_v", "f2", "factors3"):
         g = load_golden(name)
         f = tmp_path / (name + ".m")
         f.write_text(";\n".join(g["functions"]) + ";\n")
