@@ -321,6 +321,16 @@ class GpuParser:
         self._refresh()
         return {k: new[i] for i, k in enumerate(keep) if new[i] != 2 ** 64 - 1}
 
+    def clone(self) -> "GpuParser":
+        """An independent copy: same functions and prime, device buffers of its own (a parser copied by value)."""
+        h = lib.ffgpu_tape_clone(self.h)
+        if not h:
+            raise FFGpuError(last_error())
+        q = object.__new__(GpuParser)
+        q.ctx, q.h, q.n_vars = self.ctx, h, self.n_vars
+        q._refresh()
+        return q
+
     @property
     def stale(self) -> bool:
         return bool(lib.ffgpu_is_stale(self.h))

@@ -640,6 +640,25 @@ def test_trim_with_check_is_equal_vs_reference(ref, oracle):
     rp.close()
 
 
+def test_clone_is_independent(oracle):
+    vars_ = ["x", "y"]
+    a = ff.GpuParser(None, ["x+y", "x*y"], vars_)
+    a.set_prime(P0)
+    b = a.clone()
+    assert b.prime == P0 and not b.stale and b.n_out == 2
+    b.add_otf("x-y")
+    b.set_prime(ff.primes()[4])
+    assert a.n_out == 2 and a.prime == P0 and b.n_out == 3
+    pts = ff.synthetic_points(2, 3, P0, seed=1)
+    assert np.array_equal(interp(a, pts, P0), oracle.parse(["x+y", "x*y"], vars_, P0).eval(pts))
+    p4 = ff.primes()[4]
+    pts4 = ff.synthetic_points(2, 3, p4, seed=1)
+    assert np.array_equal(interp(b, pts4, p4), oracle.parse(["x+y", "x*y", "x-y"], vars_, p4).eval(pts4))
+    a.close()
+    assert np.array_equal(interp(b, pts4, p4), oracle.parse(["x+y", "x*y", "x-y"], vars_, p4).eval(pts4))
+    b.close()
+
+
 def test_changed_collection_needs_set_prime():
     gp = ff.GpuParser(None, ["x"], ["x"])
     gp.set_prime(P0)

@@ -76,6 +76,47 @@ def test_reference_recorded_probes(ctx, tmp_path):
     par.close()
 
 
+def test_added_trimmed_and_cloned_collections_on_device(ctx, oracle):
+    """ffgpu_add_function / ffgpu_trim / ffgpu_tape_clone with a GPU behind them: a stale tape refuses to evaluate,
+    set_prime rebuilds and uploads it (new device buffers), small and chunked calls give the oracle's values."""
+    g = load_golden("s_y_4_v")
+    funs, vars_ = g["functions"], g["vars"]
+    p = ff.primes()[1]
+    pts = ff.synthetic_points(4, 300, p, seed=3)
+    pts[:, 0] = 0
+    big = ff.synthetic_points(4, 70001, p, seed=4)
+
+    def want(fs, x):
+        return oracle.parse(fs, vars_, p).eval(x)
+
+    par = ff.GpuParser(ctx, funs[:10], vars_)
+    par.set_prime(p)
+    assert np.array_equal(par.evaluate_pre(pts), want(funs[:10], pts))
+    for f in funs[10:]:
+        par.add_otf(f)
+    with pytest.raises(ff.FFGpuError, match="set_prime"):
+        par.evaluate_pre(pts)
+    par.set_prime(p)
+    assert par.n_out == len(funs)
+    assert np.array_equal(par.evaluate_pre(pts), want(funs, pts))
+    twin = par.clone()
+    keep = [0, 3, 4, 11, 18]
+    assert par.trim(keep) == {k: i for i, k in enumerate(keep)}
+    par.set_prime(p)
+    kept = [funs[k] for k in keep]
+    assert np.array_equal(par.evaluate_pre(pts), want(kept, pts))
+    par.set_chunk(1 << 14)                              # several pipelined chunks on the rebuilt tape
+    assert np.array_equal(par.evaluate_pre(big), want(kept, big))
+    # the clone kept the untrimmed collection, and outlives the original
+    par.close()
+    assert np.array_equal(twin.evaluate_pre(pts), want(funs, pts))
+    p2 = ff.primes()[6]
+    twin.set_prime(p2)
+    pts2 = ff.synthetic_points(4, 129, p2, seed=5)
+    assert np.array_equal(twin.evaluate_pre(pts2), oracle.parse(funs, vars_, p2).eval(pts2))
+    twin.close()
+
+
 PARSER_BIN = os.path.join(ROOT, "oracle", "_ref", "parser_dropin")
 
 
