@@ -120,6 +120,8 @@ struct ffgpu_tape {
   std::vector<ffgpu::Instr*> d_tape;   // per device
   std::vector<uint32_t*> d_chunks;     // per device: Collection::chunk_table
   int force_k = 0, force_threads = 0;
+  int defer_mode = -1;                 // -1: FFGPU_DEFER / default
+  unsigned defer_stack = 0, defer_max_blocks = 0;
   size_t chunk = 0;
   bool needs_generic = true;           // the resolved tape has instructions without a fast dispatch code
 };
@@ -155,13 +157,31 @@ std::vector<std::string> to_vec(const char* const* s, size_t n) {
   return v;
 }
 
+// FFGPU_DEFER = 0 | 1 | 2: never / when it pays (default) / whenever possible run the kernel that inverts the parked
+// divisors of a thread with one Fermat chain (kernels.cu); FFGPU_DEFER_STACK: entries of its product stack (default 8)
+int defer_mode() {
+  static const int mode = [] {
+    const char* e = std::getenv("FFGPU_DEFER");
+    return e && *e ? std::atoi(e) : 1;
+  }();
+  return mode;
+}
+unsigned defer_stack() {
+  static const unsigned n = [] {
+    const char* e = std::getenv("FFGPU_DEFER_STACK");
+    return e && *e ? (unsigned)std::atoi(e) : 0u;
+  }();
+  return n;
+}
+
 int launch(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, size_t n_points, uint64_t* d_out,
-           size_t out_stride, cudaStream_t stream) {
+           size_t out_stride, cudaStream_t stream, uint64_t* d_park = nullptr) {
   const ffgpu::Collection& c = t->col;
   ffgpu::EvalParams prm;
   prm.tape = t->d_tape[g];
   prm.values = d_values;
   prm.out = d_out;
+  prm.park = d_park;
   prm.n_points = n_points;
   prm.in_stride = in_stride;
   prm.out_stride = out_stride;
@@ -170,8 +190,14 @@ int launch(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, siz
   prm.d = 2 * prm.c;
   prm.n_slots = c.n_slots;
   prm.n_instr = (uint32_t)(c.tape.size() - 2);
+  ffgpu::DeferInfo df;
+  df.parks = c.defer_parks;
+  df.single = c.defer_single;
+  df.mode = t->defer_mode >= 0 ? t->defer_mode : defer_mode();
+  df.tiles_max = t->defer_stack ? t->defer_stack : defer_stack();
+  df.max_blocks = t->defer_max_blocks;
   const ffgpu::LaunchShape sh = ffgpu::choose_shape(n_points, c.n_slots, t->ctx->devs[g].sm_count, t->force_k,
-                                                    t->force_threads, c.max_chunks, !t->needs_generic);
+                                                    t->force_threads, c.max_chunks, !t->needs_generic, df);
   prm.chunk_bounds = nullptr;
   if (sh.chunks > 1) {
     unsigned idx = 0;
@@ -203,6 +229,21 @@ void drop_device_copies(ffgpu_tape* t) {
     t->d_tape[g] = nullptr;
     t->d_chunks[g] = nullptr;
   }
+}
+
+// rows x cnt words between two row-major matrices.  One strided copy while both pitches are within the
+// limit of cudaMemcpy2D (cudaDeviceProp::memPitch, 2^31 - 1 bytes); beyond it -- a single call with 2^28
+// points or more -- one contiguous copy per row.
+int copy_rows(uint64_t* dst, size_t dst_stride, const uint64_t* src, size_t src_stride, size_t cnt, size_t rows,
+              cudaMemcpyKind kind, cudaStream_t stream) {
+  constexpr size_t MAX_PITCH = 0x7fffffffULL;
+  if (dst_stride * 8 <= MAX_PITCH && src_stride * 8 <= MAX_PITCH) {
+    FF_CUDA(cudaMemcpy2DAsync(dst, dst_stride * 8, src, src_stride * 8, cnt * 8, rows, kind, stream));
+    return 0;
+  }
+  for (size_t r = 0; r < rows; ++r)
+    FF_CUDA(cudaMemcpyAsync(dst + r * dst_stride, src + r * src_stride, cnt * 8, kind, stream));
+  return 0;
 }
 
 int ensure(DevBuf& b, size_t need_in, size_t need_out) {
@@ -292,6 +333,7 @@ ffgpu_tape* ffgpu_compile(ffgpu_ctx* ctx, const char* const* functions, size_t n
   t->col.enable_cse = !(flags & FFGPU_NO_CSE);
   t->col.enable_fuse = !(flags & FFGPU_NO_FUSE);
   t->col.enable_cross = !(flags & FFGPU_NO_CROSS);
+  t->col.enable_defer = !(flags & FFGPU_NO_DEFER);
   t->col.temp_budget = (int)((flags >> FFGPU_TEMPS_SHIFT) & 15u);
   const bool ok = t->col.compile_strings(to_vec(functions, n_functions), to_vec(vars, n_vars),
                                          (flags & FFGPU_CHECK_IS_EQUAL) != 0, err);
@@ -305,6 +347,7 @@ ffgpu_tape* ffgpu_compile_text(ffgpu_ctx* ctx, const char* text, const char* con
   t->col.enable_cse = !(flags & FFGPU_NO_CSE);
   t->col.enable_fuse = !(flags & FFGPU_NO_FUSE);
   t->col.enable_cross = !(flags & FFGPU_NO_CROSS);
+  t->col.enable_defer = !(flags & FFGPU_NO_DEFER);
   t->col.temp_budget = (int)((flags >> FFGPU_TEMPS_SHIFT) & 15u);
   const bool ok = t->col.compile_text(text ? text : "", to_vec(vars, n_vars), (flags & FFGPU_CHECK_IS_EQUAL) != 0, err);
   return finish_compile(ctx, std::move(t), ok, err);
@@ -332,6 +375,9 @@ ffgpu_tape* ffgpu_tape_clone(const ffgpu_tape* t) {
   n->col = t->col;
   n->force_k = t->force_k;
   n->force_threads = t->force_threads;
+  n->defer_mode = t->defer_mode;
+  n->defer_stack = t->defer_stack;
+  n->defer_max_blocks = t->defer_max_blocks;
   n->chunk = t->chunk;
   if (t->ctx) {
     n->d_tape.assign(t->ctx->devs.size(), nullptr);
@@ -364,6 +410,7 @@ size_t ffgpu_n_slots(const ffgpu_tape* t) { return t->col.n_slots; }
 size_t ffgpu_cse_fallbacks(const ffgpu_tape* t) { return t->col.cse_fallbacks; }
 size_t ffgpu_n_structural_duplicates(const ffgpu_tape* t) { return t->col.n_structural_duplicates; }
 size_t ffgpu_n_shared_denominators(const ffgpu_tape* t) { return t->col.n_shared_denominators; }
+size_t ffgpu_n_deferred_divisions(const ffgpu_tape* t) { return t->col.n_deferred; }
 
 size_t ffgpu_rpn(const ffgpu_tape* t, size_t i, char* buf, size_t cap) {
   if (i >= t->col.functions.size()) return 0;
@@ -484,6 +531,16 @@ int ffgpu_set_launch(ffgpu_tape* t, int k, int threads) {
   return 0;
 }
 
+int ffgpu_set_defer(ffgpu_tape* t, int mode, unsigned stack_entries, unsigned max_blocks) {
+  if (!t) return fail("null tape");
+  if (mode < 0 || mode > 2) return fail("defer mode must be 0, 1 or 2");
+  if (stack_entries > 64) return fail("at most 64 product-stack entries");
+  t->defer_mode = mode;
+  t->defer_stack = stack_entries;
+  t->defer_max_blocks = max_blocks;
+  return 0;
+}
+
 int ffgpu_set_chunk(ffgpu_tape* t, size_t points) {
   t->chunk = points;
   return 0;
@@ -557,7 +614,8 @@ int eval_host(ffgpu_tape* t, const uint64_t* values, const uint64_t* line_a, con
       if (zc >= 2) k_in = h_in;
       else if (n_vars) FF_CUDA(cudaMemcpyAsync(b.d_in, h_in, n_vars * n_even * sizeof(uint64_t), cudaMemcpyHostToDevice, b.stream));
       if (zc >= 1) k_out = h_out;
-      if (launch(t, 0, k_in, n_even, n_even, k_out, n_even, b.stream)) return -1;
+      // results written over PCIe: parked divisors (deferred divisions) wait in device memory instead
+      if (launch(t, 0, k_in, n_even, n_even, k_out, n_even, b.stream, zc >= 1 ? b.d_out : nullptr)) return -1;
       if (zc < 1 && n_out) FF_CUDA(cudaMemcpyAsync(h_out, b.d_out, n_out * n_even * sizeof(uint64_t), cudaMemcpyDeviceToHost, b.stream));
       FF_CUDA(cudaStreamSynchronize(b.stream));
       for (size_t f = 0; f < n_out; ++f) std::memcpy(out + f * n_points, h_out + f * n_even, n_points * sizeof(uint64_t));
@@ -593,9 +651,11 @@ int eval_host(ffgpu_tape* t, const uint64_t* values, const uint64_t* line_a, con
         DevBuf& b = slot.dev[g].buf[ci % N_BUF];
         if (ensure(b, chunk * (n_vars + 1), chunk * std::max<size_t>(n_out, 1))) return -1;
         if (values) {
-          if (n_vars)
-            FF_CUDA(cudaMemcpy2DAsync(b.d_in, chunk * 8, values + lo, n_points * 8, cnt * 8, n_vars,
-                                      cudaMemcpyHostToDevice, b.stream));
+          if (n_vars) {
+            if (copy_rows(b.d_in, chunk, values + lo, n_points, cnt, n_vars, cudaMemcpyHostToDevice, b.stream)) return -1;
+            // the pad lane of an odd chunk must hold a residue: its divisor enters the block's product tree
+            if (cnt_even != cnt) FF_CUDA(cudaMemset2DAsync(b.d_in + cnt, chunk * 8, 0, 8, n_vars, b.stream));
+          }
         } else if (n_vars) {
           // t travels, the coordinates are built here: row n_vars of the staging buffer holds t
           if (b.cap_as < 2 * n_vars) {
@@ -625,9 +685,7 @@ int eval_host(ffgpu_tape* t, const uint64_t* values, const uint64_t* line_a, con
           g_launches.fetch_add(1, std::memory_order_relaxed);
         }
         if (launch(t, (int)g, b.d_in, chunk, cnt_even, b.d_out, chunk, b.stream)) return -1;
-        if (n_out)
-          FF_CUDA(cudaMemcpy2DAsync(out + lo, n_points * 8, b.d_out, chunk * 8, cnt * 8, n_out,
-                                    cudaMemcpyDeviceToHost, b.stream));
+        if (n_out && copy_rows(out + lo, n_points, b.d_out, chunk, cnt, n_out, cudaMemcpyDeviceToHost, b.stream)) return -1;
         return 0;
       }();
     }

@@ -445,16 +445,18 @@ struct FnEmitter {
   //   DEN_NONE      the whole expression, as written
   //   DEN_PRODUCE   1/D is computed once, parked in temp slot 0 for the functions that follow, then N * that
   //   DEN_CONSUME   N * (temp slot 0): the function before this one has the same denominator
+  //   3             only the divisor D of the top-level division (deferred divisions: it is parked by OP_DPARK)
+  //   4             ACC * N: ACC holds 1/D on entry (after OP_DUNPARK)
   FnEmitter(const Function& f_, uint32_t fn_, std::vector<Instr>& t, std::vector<ConstPatch>& p, bool cse,
             int temp_budget, int den_mode = 0)
       : f(f_), fn(fn_), tape(t), patches(p), enable_cse(cse) {
-    root = den_mode == 2 ? f.nodes[f.root].l : f.root;
+    root = (den_mode == 2 || den_mode == 4) ? f.nodes[f.root].l : den_mode == 3 ? f.nodes[f.root].r : f.root;
     // Spill and temp slots share the kernel's shared memory ([slot][probe][thread], 16 KB per slot at
     // 8 probes x 256 threads): more than SLOT_BUDGET slots per lane cost resident blocks.  Functions that
     // already spill deep get fewer temps; two are always allowed (co-evaluated sums need two).
     if (temp_budget > 0) max_temps = std::min(temp_budget, MAX_TEMPS);
     else max_temps = std::max(2, std::min(MAX_TEMPS, SLOT_BUDGET - (int)f.nodes[root].need));
-    if (den_mode) {
+    if (den_mode == 1 || den_mode == 2) {
       slot_busy[0] = true;         // temp slot 0 carries 1/D from function to function
       temps_used = 1;                // it comes out of the function's own budget: the slot count (occupancy) stays
     }
@@ -614,7 +616,7 @@ struct FnEmitter {
     int32_t other;
     int32_t aux;
   };
-  enum { GEN, AFTER, APPLY_POP, APPLY_DIRECT, INVERT, POW_CONST, MUL_INVCONST, SQUARE, PRE, ACCUM, ADOPT, ADDPOP, EMIT };
+  enum { GEN, AFTER, APPLY_POP, APPLY_DIRECT, INVERT, POW_CONST, MUL_INVCONST, SQUARE, PRE, ACCUM, ADOPT, ADDPOP, MULPOP, EMIT };
   std::vector<Item> work;
   // accumulate lists of co-evaluated sums: for ACCUM items
   struct Acc { int slot; bool minus; bool init; };
@@ -761,8 +763,19 @@ struct FnEmitter {
     work.push_back(Item{INVERT, -1, false, false, -1, 0});
     gen(r);
   }
-  void gen(int32_t root) {
-    work.push_back(Item{GEN, root, false, false, -1, 0});
+  // ACC = ACC * N for the numerator N of the top-level division: ACC (the inverted divisor) waits on the spill stack
+  void gen_times_acc() {
+    if (leaf_like(root)) {
+      Instr m = mk(OP_MUL);
+      operand(m, root);
+      put(m);
+      return;
+    }
+    work.push_back(Item{MULPOP, -1, false, false, -1, 0});
+    gen(root, true);
+  }
+  void gen(int32_t root, bool push_first = false) {
+    work.push_back(Item{GEN, root, push_first, false, -1, 0});
     while (!work.empty()) {
       const Item it = work.back();
       work.pop_back();
@@ -814,8 +827,9 @@ struct FnEmitter {
           else remaining[t] -= extra;
           continue;
         }
-        case ADDPOP: {
-          Instr ins = mk(OP_ADD);
+        case ADDPOP:
+        case MULPOP: {
+          Instr ins = mk(it.what == ADDPOP ? OP_ADD : OP_MUL);
           ins.src = SRC_POP;
           put(ins);
           --depth;
@@ -933,6 +947,8 @@ void Collection::emit_function(uint32_t fn, const std::vector<uint32_t>& out_slo
     FnEmitter em(functions[fn], fn, tape, patches, cse, temp_budget, den_mode);
     if (den_mode == 1) em.gen_produce();
     else if (den_mode == 2) em.gen_consume();
+    else if (den_mode == 3) em.gen(em.root);
+    else if (den_mode == 4) em.gen_times_acc();
     else em.gen(functions[fn].root);
     if (em.failed && cse) {
       // the sharing pass lost track of a temp slot: emit this function as a plain tree instead
@@ -954,23 +970,44 @@ void Collection::emit_function(uint32_t fn, const std::vector<uint32_t>& out_slo
   }
 }
 
-// Translation check: run the emitted code of function fn on the host at one point and compare with the
-// value of its expression tree (eval_nodes).  The tape must be resolved for prime p.
-bool Collection::check_function(uint32_t fn, uint64_t p, const uint64_t* point, uint64_t* temps, bool* temp_set) const {
+// Translation check: run the emitted tape on the host at one point and compare every stored value with the
+// value of the expression tree (eval_nodes) of the function that owns the output slot.  The tape must be resolved
+// for prime p.  Temp slot 0 can carry the inverse of a denominator from one function to the next (shared
+// denominators) and parked divisors wait in their output rows (deferred divisions), exactly as on the device, so
+// the tape is run as a whole.  Returns false if the tape is malformed; bad[f] marks functions with a wrong value.
+bool Collection::check_tape(uint64_t p, const uint64_t* point, const std::vector<int32_t>& owner,
+                            std::vector<char>& bad) const {
+  bad.assign(functions.size(), 0);
+  std::vector<uint64_t> want(functions.size(), 0);
+  std::vector<char> have(functions.size(), 0);
   std::vector<uint64_t> val;
-  eval_nodes(functions[fn], p, point, val);
-  const uint64_t want = val[functions[fn].root];
+  auto expected = [&](int32_t fn) {
+    if (!have[fn]) {
+      eval_nodes(functions[fn], p, point, val);
+      want[fn] = val[functions[fn].root];
+      have[fn] = 1;
+    }
+    return want[fn];
+  };
   uint64_t acc = 0;
   std::vector<uint64_t> stack;
-  // temps / temp_set (16 entries) belong to the caller: temp slot 0 can carry the inverse of a denominator from
-  // one function to the next (shared denominators), exactly as the shared-memory slot does on the device
-  bool stored = false;
-  for (uint32_t pc = fn_start[pos_of_[fn]]; pc < fn_start[pos_of_[fn] + 1]; ++pc) {
+  uint64_t temps[16] = {};
+  bool temp_set[16] = {};
+  std::vector<uint64_t> rows(n_out, 0);
+  std::vector<char> row_state(n_out, 0);          // 0 empty, 1 holds a parked divisor, 2 stored
+  bool ok = true;
+  auto blame = [&](uint32_t slot) {
+    if (slot < owner.size() && owner[slot] >= 0) bad[owner[slot]] = 1;
+    else ok = false;
+  };
+  for (size_t pc = 0; pc < tape.size() && ok; ++pc) {
     const Instr& in = tape[pc];
+    if (in.op == OP_HALT) break;
     uint64_t b = 0;
+    bool operand_ok = true;
     switch (in.op >= OP_TERM ? (uint8_t)SRC_NONE : in.src) {   // the fused forms decode their own operands
       case SRC_POP:
-        if (stack.empty()) return false;
+        if (stack.empty()) { operand_ok = false; break; }
         b = stack.back();
         stack.pop_back();
         break;
@@ -978,11 +1015,12 @@ bool Collection::check_function(uint32_t fn, uint64_t p, const uint64_t* point, 
       case SRC_NEGVAR: b = ffhost::neg(point[in.arg] % p, p); break;
       case SRC_CONST: b = in.imm; break;
       case SRC_TMP:
-        if (in.arg >= 16 || !temp_set[in.arg]) return false;
+        if (in.arg >= 16 || !temp_set[in.arg]) { operand_ok = false; break; }
         b = temps[in.arg];
         break;
       default: break;
     }
+    if (!operand_ok) return false;
     const bool swap = in.flags & F_SWAP;
     switch (in.op) {
       case OP_LOAD:
@@ -1021,9 +1059,26 @@ bool Collection::check_function(uint32_t fn, uint64_t p, const uint64_t* point, 
         break;
       }
       case OP_STORE:
-        if (acc != want) return false;
-        stored = true;
+        if (in.arg >= n_out || !stack.empty()) return false;
+        if (owner[in.arg] < 0 || acc != expected(owner[in.arg])) blame(in.arg);
+        rows[in.arg] = acc;
+        row_state[in.arg] = 2;
         break;
+      case OP_DPARK:
+        // the divisor waits in an output row that nothing has stored yet; the spill stack is empty at this point
+        if (in.arg >= n_out || !stack.empty() || row_state[in.arg] != 0) return false;
+        rows[in.arg] = acc;
+        row_state[in.arg] = 1;
+        continue;
+      case OP_DUNPARK:
+        if (in.arg >= n_out || !stack.empty() || row_state[in.arg] != 1) return false;
+        acc = ffhost::inv(rows[in.arg], p);
+        row_state[in.arg] = 0;
+        continue;
+      case OP_DCHAIN:
+      case OP_DEND:
+        if (!stack.empty()) return false;
+        continue;
       case OP_TERM: {
         const uint8_t mode = (in.flags >> TM_SHIFT) & 7;
         uint64_t t = ffhost::pow_ff(point[in.arg & 0xffff] % p, in.arg >> 16, p);
@@ -1067,7 +1122,14 @@ bool Collection::check_function(uint32_t fn, uint64_t p, const uint64_t* point, 
     }
     if (in.flags & F_NEGR) acc = ffhost::neg(acc, p);
   }
-  return stored && stack.empty();
+  if (!ok || !stack.empty()) return false;
+  // every output has been stored (a row still holding a parked divisor means a group without its second half)
+  for (size_t k = 0; k < n_out; ++k)
+    if (row_state[k] != 2) {
+      if (owner[k] >= 0) bad[owner[k]] = 1;
+      else return false;
+    }
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1280,28 +1342,121 @@ bool Collection::finish(std::string& err) {
         }
       }
     }
+    // Units of emission, in evaluation order: a function on its own, or a run of functions over one denominator
+    // (head first).  A unit whose top-level division can wait -- numerator and denominator share no code, so the
+    // two halves can be emitted apart -- is DEFERRED: consecutive deferred units form a group
+    //     [D_1] DPARK r_1 ... [D_g] DPARK r_g   DCHAIN   DUNPARK r_g [numerators of unit g] ... DUNPARK r_1 [...]   DEND
+    // (tape.hpp).  The divisor of a unit waits in the first output row of its head.
+    struct Unit { std::vector<uint32_t> members; bool deferred; };
+    std::vector<Unit> units;
     for (size_t k = 0; k < functions.size(); ++k) {
       const size_t i = order_[k];
-      fn_start.push_back((uint32_t)tape.size());
-      if (dup_of[i] < 0) emit_function((uint32_t)i, slots[i], den_mode_[i]);   // a duplicate's outputs are stored by its twin
-      count_work(functions[i]);
+      if (dup_of[i] >= 0 || slots[i].empty()) continue;      // a duplicate's outputs are stored by its twin
+      if (den_mode_[i] == 2 && !units.empty()) { units.back().members.push_back((uint32_t)i); continue; }
+      units.push_back(Unit{{(uint32_t)i}, false});
     }
+    n_deferred = 0;
+    defer_parks = 0;
+    if (enable_defer) {
+      for (Unit& u : units) {
+        const uint32_t i = u.members[0];
+        const Function& f = functions[i];
+        const Node& rt = f.nodes[f.root];
+        if (no_cse_fn_[i] || rt.kind != N_DIV || rt.is_const || f.nodes[rt.r].is_const) continue;
+        if (u.members.size() > 1) { u.deferred = true; continue; }          // a run never shares code with its divisor
+        // numerator and denominator must not share a compound sub-expression (it would be computed twice)
+        std::vector<Fp> local;
+        const std::vector<Fp>& fp = fps.empty() ? (fingerprints(f, local), local) : fps[i];
+        std::unordered_map<uint64_t, char> in_den;
+        std::vector<int32_t> st{rt.r};
+        while (!st.empty()) {
+          const int32_t x = st.back();
+          st.pop_back();
+          const Node& nd = f.nodes[x];
+          if (nd.l < 0 || nd.is_const) continue;
+          in_den.emplace(fp[x].a ^ mix64(fp[x].b), 1);
+          st.push_back(nd.l);
+          st.push_back(nd.r);
+        }
+        bool shares = false;
+        st.assign(1, rt.l);
+        while (!st.empty() && !shares) {
+          const int32_t x = st.back();
+          st.pop_back();
+          const Node& nd = f.nodes[x];
+          if (nd.l < 0 || nd.is_const) continue;
+          shares = in_den.count(fp[x].a ^ mix64(fp[x].b)) != 0;
+          st.push_back(nd.l);
+          st.push_back(nd.r);
+        }
+        u.deferred = !shares;
+      }
+    }
+    constexpr size_t GROUP_MAX = 8;             // DPARKs per group: entries of the kernel's per-thread product stack
+    size_t n_groups = 0, n_plain = 0;
+    auto put = [&](uint8_t op, uint32_t arg, uint8_t flags) {
+      Instr in{};
+      in.op = op;
+      in.arg = arg;
+      in.flags = flags;
+      tape.push_back(in);
+    };
+    for (size_t a = 0; a < units.size();) {
+      fn_start.push_back((uint32_t)tape.size());
+      if (!units[a].deferred) {
+        for (uint32_t i : units[a].members) emit_function(i, slots[i], den_mode_[i]);
+        ++n_plain;
+        ++a;
+        continue;
+      }
+      size_t b = a;
+      while (b < units.size() && units[b].deferred && b - a < GROUP_MAX) ++b;
+      for (size_t q = a; q < b; ++q) {
+        const uint32_t head = units[q].members[0];
+        emit_function(head, {}, 3);
+        put(OP_DPARK, slots[head][0], q + 1 == b ? F_LAST : 0);
+      }
+      put(OP_DCHAIN, 0, 0);
+      for (size_t q = b; q-- > a;) {
+        const Unit& u = units[q];
+        const uint32_t head = u.members[0];
+        put(OP_DUNPARK, slots[head][0], 0);
+        if (u.members.size() == 1) {
+          emit_function(head, slots[head], 4);
+        } else {
+          put(OP_SAVE, 0, 0);                   // temp slot 0 = 1/D for all functions of the run
+          for (uint32_t i : u.members) emit_function(i, slots[i], 2);
+        }
+        ++n_deferred;
+      }
+      put(OP_DEND, 0, 0);
+      defer_parks = std::max<uint32_t>(defer_parks, (uint32_t)(b - a));
+      ++n_groups;
+      a = b;
+    }
+    defer_single = n_groups == 1 && n_plain == 0;
+    for (size_t k = 0; k < functions.size(); ++k) count_work(functions[k]);
     fn_start.push_back((uint32_t)tape.size());
     peephole();
     if (enable_fuse) fuse();
     // Translation check of every function at one pseudo-random point: the tape must reproduce the value of
-    // the expression tree.  A function that fails is re-emitted as a plain tree (no sharing) on the second
-    // pass; if that fails too the compilation is refused -- never a wrong probe value.
+    // the expression tree.  A function that fails is re-emitted as a plain tree (no sharing, no deferral) on the
+    // second pass; if that fails too the compilation is refused -- never a wrong probe value.
     if (!resolve(P0, err)) return false;
     std::vector<uint64_t> pt(vars.size());
     uint64_t seed = 0x243F6A8885A308D3ULL;
     for (auto& v : pt) v = 1 + splitmix64(seed) % (P0 - 1);
+    std::vector<int32_t> owner(n_out, -1);
+    for (size_t i = 0; i < functions.size(); ++i)
+      for (uint32_t sl : slots[i]) owner[sl] = (int32_t)i;
+    std::vector<char> bad;
+    if (!check_tape(P0, pt.data(), owner, bad)) {
+      err = "internal error: the emitted tape is malformed";
+      return false;
+    }
     bool again = false;
-    uint64_t chk_temps[16] = {};
-    bool chk_temp_set[16] = {};
-    for (size_t k = 0; k < functions.size(); ++k) {
-      const size_t i = order_[k];
-      if (dup_of[i] >= 0 || check_function((uint32_t)i, P0, pt.data(), chk_temps, chk_temp_set)) continue;
+    for (size_t i = 0; i < functions.size(); ++i) {
+      if (!bad[i]) continue;
       if (pass == 1 || no_cse_fn_[i] || !enable_cse) {
         err = "internal error: the tape of function " + std::to_string(i) + " does not reproduce its expression";
         return false;
@@ -1326,7 +1481,7 @@ bool Collection::finish(std::string& err) {
         case OP_ADD: case OP_SUB: case OP_NEG: case OP_ACCUM: ++executed.ma; break;
         case OP_MUL: case OP_SQR: ++executed.mm; break;
         case OP_MULADD: ++executed.mm; ++executed.ma; break;
-        case OP_INV: ++executed.inv; break;
+        case OP_INV: case OP_DUNPARK: ++executed.inv; break;
         case OP_POWU:
           if (in.imm < (P0 >> 1)) executed.mm += chain(in.imm);
           else { ++executed.inv; executed.mm += chain(P0 - in.imm - 1); }
@@ -1352,21 +1507,21 @@ bool Collection::finish(std::string& err) {
       if (in.op < OP_TERM && (in.flags & F_NEGR)) ++executed.ma;
     }
   }
-  // chunk tables for C = 1, 2, 4, ... while a chunk still holds a function
+  // chunk tables for C = 1, 2, 4, ... while a chunk still holds a unit: the C + 1 tape offsets that cut the tape into
+  // C runs of about equal length.  A chunk starts where nothing is carried over from earlier code (fn_start): never
+  // inside a run of functions over one denominator, never inside a group of deferred divisions.
   chunk_table.clear();
   chunk_table_off.clear();
   max_chunks = 1;
   const uint32_t total = (uint32_t)tape.size();
-  for (unsigned C = 1; C <= 1024 && C <= std::max<size_t>(functions.size(), 1); C <<= 1) {
+  const size_t n_starts = fn_start.empty() ? 0 : fn_start.size() - 1;
+  for (unsigned C = 1; C <= 1024 && C <= std::max<size_t>(n_starts, 1); C <<= 1) {
     chunk_table_off.push_back((uint32_t)chunk_table.size());
     size_t f = 0;
     for (unsigned k = 0; k < C; ++k) {
       const uint64_t target = (uint64_t)total * k / C;
       while (f + 1 < fn_start.size() && fn_start[f] < target) ++f;
-      // a chunk starts with temp slot 0 undefined: back up to the function that fills it
-      size_t g = f;
-      while (g > 0 && g < functions.size() && (den_mode_[order_[g]] == 2 || dup_of[order_[g]] >= 0)) --g;
-      chunk_table.push_back(fn_start[g]);
+      chunk_table.push_back(fn_start.empty() ? 0 : fn_start[f]);
     }
     chunk_table.push_back(total);
     max_chunks = C;
@@ -1429,6 +1584,10 @@ void Collection::peephole() {
         case OP_INV: fx = FX_INV; break;
         case OP_STORE: fx = FX_STORE; break;
         case OP_SQR: fx = FX_SQR; break;
+        case OP_DPARK: fx = FX_DPARK; break;
+        case OP_DCHAIN: fx = FX_DCHAIN; break;
+        case OP_DUNPARK: fx = FX_DUNPARK; break;
+        case OP_DEND: fx = FX_DEND; break;
         default: break;
       }
     }

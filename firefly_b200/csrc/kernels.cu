@@ -217,8 +217,11 @@ __device__ __forceinline__ void block_inverse(R (&a)[K], const Field& F, u64* sc
   R e[K], pre[K];
 #pragma unroll
   for (int k = 0; k < K; k++) {
-    z[k] = fcanon(a[k], F) == 0;
-    e[k] = z[k] ? mkR(1) : a[k];
+    // the canonical value goes into the tree: a lane holding something out of bounds (a raw caller value)
+    // can then only spoil its own result, never the inverses of the other probes of the block
+    const u64 cv = fcanon(a[k], F);
+    z[k] = cv == 0;
+    e[k] = z[k] ? mkR(1) : mkR(cv);
   }
   pre[0] = e[0];
 #pragma unroll
@@ -285,8 +288,10 @@ struct Lane {
   static constexpr int NACC = VEC ? K / 2 : K;               // accesses per variable
   const u64* vbase;      // values + first point of the tile
   u64* obase;            // out + first point of the tile
+  u64* pbase;            // parked divisors (rows like out) + first point of the tile
   u64 in_stride, out_stride;
   uint2* stk;            // [slot][k][thread], this thread's column
+  u64* qstk;             // [entry][thread]: running products of the parked divisors (deferring kernel)
   u64* scratch;          // 64 words for block_inverse
   u32 off[NACC];         // tile-relative offsets of this thread's accesses, clamped into the batch
   u32 own, left, tmp_top;
@@ -296,10 +301,20 @@ struct Lane {
   // load/store is one 16-byte access per lane and a warp covers 512 contiguous bytes.  Lanes beyond the end
   // of the batch recompute the last valid point and never store: the hot loop has no bounds checks.
   __device__ __forceinline__ void init(const EvalParams& prm, u64* smem) {
-    const u64 tile = (u64)blockIdx.x * (u64)(THREADS * K);
-    const u64 left64 = prm.n_points - tile;               // > 0: the grid covers exactly the batch
-    left = left64 < (u64)(THREADS * K) ? (u32)left64 : (u32)(THREADS * K);
+    in_stride = prm.in_stride;
+    out_stride = prm.out_stride;
+    scratch = smem;
+    stk = reinterpret_cast<uint2*>(smem + 64) + threadIdx.x;
+    qstk = smem + 64 + (size_t)prm.n_slots * (K * THREADS) + threadIdx.x;
+    tmp_top = prm.n_slots - 1;
+    F = Field{prm.p, prm.c, prm.d};
     own = VEC ? 2 * threadIdx.x : threadIdx.x;
+  }
+  // place the thread on tile number `tile` (THREADS * K consecutive points)
+  __device__ __forceinline__ void set_tile(const EvalParams& prm, u64 tile_index) {
+    const u64 tile = tile_index * (u64)(THREADS * K);
+    const u64 left64 = prm.n_points - tile;               // > 0: the tiles cover exactly the batch
+    left = left64 < (u64)(THREADS * K) ? (u32)left64 : (u32)(THREADS * K);
 #pragma unroll
     for (int j = 0; j < NACC; j++) {
       const u32 o = own + j * STEP, last = left - (VEC ? 2 : 1);
@@ -307,12 +322,7 @@ struct Lane {
     }
     vbase = reinterpret_cast<const u64*>(prm.values) + tile;
     obase = reinterpret_cast<u64*>(prm.out) + tile;
-    in_stride = prm.in_stride;
-    out_stride = prm.out_stride;
-    scratch = smem;
-    stk = reinterpret_cast<uint2*>(smem + 64) + threadIdx.x;
-    tmp_top = prm.n_slots - 1;
-    F = Field{prm.p, prm.c, prm.d};
+    pbase = reinterpret_cast<u64*>(prm.park ? prm.park : prm.out) + tile;
   }
   __device__ __forceinline__ void load_var(u32 var, R (&b)[K]) const {
     const u64* row = vbase + (u64)var * in_stride;
@@ -333,6 +343,22 @@ struct Lane {
     }
   }
   __device__ __forceinline__ bool in_range(int j) const { return own + j * STEP < left; }
+  __device__ __forceinline__ bool probe_in_range(int k) const { return in_range(VEC ? k / 2 : k); }
+  // a row of out[] that this thread has written before (OP_DPARK): plain loads, not the read-only path
+  __device__ __forceinline__ void load_row(u32 out_slot, u64 (&v)[K]) const {
+    const u64* row = pbase + (u64)out_slot * out_stride;
+    if (VEC) {
+#pragma unroll
+      for (int j = 0; j < NACC; j++) {
+        const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(row + off[j]);
+        v[2 * j] = w.x;
+        v[2 * j + 1] = w.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NACC; j++) v[j] = row[off[j]];
+    }
+  }
   __device__ __forceinline__ void slot_put(const R (&a)[K], u32 slot) const {
     uint2* t = stk + (size_t)slot * (K * THREADS);
 #pragma unroll
@@ -349,8 +375,10 @@ struct Lane {
   // spill slots count up from 0, temp slots (shared sub-expressions, co-evaluated sums) down from the last slot
   __device__ __forceinline__ void tmp_put(const R (&a)[K], u32 slot) const { slot_put(a, tmp_top - slot); }
   __device__ __forceinline__ void tmp_get(R (&b)[K], u32 slot) const { slot_get(b, tmp_top - slot); }
-  __device__ __forceinline__ void store_row(u32 out_slot, const R (&a)[K]) const {
-    u64* row = obase + (u64)out_slot * out_stride;
+  __device__ __forceinline__ void store_row(u32 out_slot, const R (&a)[K]) const { store_to(obase, out_slot, a); }
+  __device__ __forceinline__ void park_row(u32 out_slot, const R (&a)[K]) const { store_to(pbase, out_slot, a); }
+  __device__ __forceinline__ void store_to(u64* base, u32 out_slot, const R (&a)[K]) const {
+    u64* row = base + (u64)out_slot * out_stride;
     if (VEC) {
 #pragma unroll
       for (int j = 0; j < NACC; j++)
@@ -363,6 +391,74 @@ struct Lane {
     }
   }
 };
+
+// ---- deferred divisions: one inversion per THREAD over everything the thread parks ------------------
+// Montgomery's trick on two levels, all in the thread's own registers, global rows and product stack -- no
+// shuffles, no barrier.  OP_DPARK writes the K canonical divisors of the current tile into the function's output
+// row and pushes the running product of everything parked so far; OP_DCHAIN inverts the final product (one Fermat
+// chain per thread); OP_DUNPARK, executed in exactly the reverse order of the DPARKs, reloads its K divisors,
+// peels their inverses off the running inverse.  Zero divisors (and lanes past the end of the batch, which never
+// store) enter the products as 1; a zero divisor gives 0 (reference: a/0 = 0, FFInt.cpp:146-153).
+//   cost per probe: (K - 1 + 1) + (K - 1 + 2 + 2 (K - 1)) multiplications per K probes = 3.9 at K = 8, plus the
+//   chain's 78 divided by the number of divisors the thread parked (K x functions of the group x tiles).
+template <int K, int THREADS, bool VEC>
+__device__ __forceinline__ void defer_park(const Lane<K, THREADS, VEC>& L, u32 row, const R (&acc)[K], R& run, u32& qsp) {
+  const Field F = L.F;
+  L.park_row(row, acc);
+  R e[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const u64 cv = fcanon(acc[k], F);
+    e[k] = (cv != 0 && L.probe_in_range(k)) ? mkR(cv) : mkR(1);
+  }
+  // product of the K divisors, pairwise (depth log2 K)
+#pragma unroll
+  for (int w = 1; w < K; w <<= 1) {
+#pragma unroll
+    for (int k = 0; k + w < K; k += 2 * w) e[k] = fmul(e[k], e[k + w], F);
+  }
+  run = qsp ? fmul(run, e[0], F) : e[0];
+  L.qstk[(size_t)qsp * THREADS] = toU(run);
+  ++qsp;
+}
+template <int K, int THREADS, bool VEC>
+__device__ __forceinline__ void defer_unpark(const Lane<K, THREADS, VEC>& L, u32 row, R (&acc)[K], R& run, u32& qsp) {
+  const Field F = L.F;
+  u64 cv[K];
+  L.load_row(row, cv);
+  bool z[K];
+  R e[K], pre[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    z[k] = !(cv[k] != 0 && L.probe_in_range(k));
+    e[k] = z[k] ? mkR(1) : mkR(cv[k]);
+  }
+  pre[0] = e[0];
+#pragma unroll
+  for (int k = 1; k < K; k++) pre[k] = fmul(pre[k - 1], e[k], F);
+  --qsp;
+  R I = run;                                   // 1 / (everything parked up to and including this row)
+  if (qsp) {
+    I = fmul(run, mkR(L.qstk[(size_t)(qsp - 1) * THREADS]), F);     // times everything parked before it
+    run = fmul(run, pre[K - 1], F);
+  }
+#pragma unroll
+  for (int k = K - 1; k >= 1; --k) {
+    const R q = fmul(I, pre[k - 1], F);
+    acc[k] = z[k] ? mkR(0) : q;
+    I = fmul(I, e[k], F);
+  }
+  acc[0] = z[0] ? mkR(0) : I;
+}
+// the same instructions in the kernel that does not defer: DPARK stores, DUNPARK reloads and inverts per block
+template <int K, int THREADS, bool VEC>
+__device__ __forceinline__ void plain_unpark(const Lane<K, THREADS, VEC>& L, u32 row, R (&acc)[K]) {
+  u64 cv[K];
+  L.load_row(row, cv);
+#pragma unroll
+  for (int k = 0; k < K; k++) acc[k] = L.probe_in_range(k) ? mkR(cv[k]) : mkR(1);   // lanes past the end never stored
+  block_inverse<K, THREADS>(acc, L.F, L.scratch);
+}
 
 #ifndef FFGPU_GENERIC_INLINE
 #define FFGPU_GENERIC_INLINE __forceinline__
@@ -482,7 +578,7 @@ __device__ FFGPU_GENERIC_INLINE u32 generic_op(const Lane<K, THREADS, VEC>& L, u
       L.store_row(ins.arg, acc);
       break;
     default:
-      asm volatile("trap;");     // an instruction without code: never compute on with garbage
+      asm volatile("trap;");     // an instruction without code (the deferred-division ops always have a fast code)
       break;
   }
   if (ins.flags & F_NEGR) {
@@ -503,26 +599,47 @@ constexpr int min_blocks() {
   return (K == 8 && !LEAN) ? 768 / THREADS : 1024 / THREADS;
 }
 
-template <int K, int THREADS, bool VEC, bool LEAN>
+template <int K, int THREADS, bool VEC, bool LEAN, bool DEFER>
 __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_tape_kernel(const EvalParams prm) {
   extern __shared__ __align__(16) u64 smem[];
   Lane<K, THREADS, VEC> L;
   L.init(prm, smem);
   const Field F = L.F;
 
-  R acc[K];
-#pragma unroll
-  for (int k = 0; k < K; k++) acc[k] = opaque(0);
-  u32 sp = 0;                                // spill-stack pointer (uniform)
-
   // blockIdx.y selects a chunk of the tape (a run of whole functions): many-function collections
   // evaluated at few points still fill the chip
   const uint4* tape = reinterpret_cast<const uint4*>(prm.tape);
-  u32 pc = 0, pc_end = prm.n_instr;
+  u32 pc_begin = 0, pc_end = prm.n_instr;
   if (prm.chunk_bounds) {
-    pc = __ldg(prm.chunk_bounds + blockIdx.y);
+    pc_begin = __ldg(prm.chunk_bounds + blockIdx.y);
     pc_end = __ldg(prm.chunk_bounds + blockIdx.y + 1);
   }
+  // Tiles of this block.  The plain kernel has one tile per block.  The deferring kernel takes a contiguous range
+  // of tiles (the grid is sized to the resident blocks, the ranges are balanced) and walks it in SETS of up to
+  // prm.tiles_per_set tiles: a tape that is one group of deferred divisions runs its first half for every tile of
+  // the set, inverts once, and runs its second half for the tiles in reverse order.
+  u64 tile_lo = blockIdx.x, tile_hi = (u64)blockIdx.x + 1;
+  u32 set_len = 1;
+  if (DEFER) {
+    tile_lo = prm.n_tiles * (u64)blockIdx.x / gridDim.x;
+    tile_hi = prm.n_tiles * ((u64)blockIdx.x + 1) / gridDim.x;
+    const u32 cnt = (u32)(tile_hi - tile_lo);
+    const u32 sets = (cnt + prm.tiles_per_set - 1) / prm.tiles_per_set;
+    set_len = sets ? (cnt + sets - 1) / sets : 1;
+  }
+
+  R acc[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) acc[k] = opaque(0);
+
+  for (u64 set_lo = tile_lo; set_lo < tile_hi; set_lo += set_len) {
+  const u32 set_n = DEFER ? (u32)((tile_hi - set_lo) < (u64)set_len ? (tile_hi - set_lo) : (u64)set_len) : 1u;
+  u32 t_in_set = 0;                          // tile of the set the tape is running on
+  L.set_tile(prm, set_lo);
+  u32 sp = 0;                                // spill-stack pointer (uniform)
+  u32 qsp = 0, unpark_pc = 0;                // deferred divisions: product-stack pointer, first instruction after DCHAIN
+  R run = opaque(1);                         // ... running product, then running inverse
+  u32 pc = pc_begin;
   InstrWord cur, nxt;
   cur.v = __ldg(tape + pc);
   for (; pc < pc_end;) {
@@ -766,9 +883,49 @@ __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_
         break;
       }
 
+      // ---- deferred top-level divisions (tape.hpp) ----------------------------------------------------------
+      case FX_DPARK:
+        if (DEFER) {
+          defer_park<K, THREADS, VEC>(L, ins.arg, acc, run, qsp);
+          if ((ins.flags & F_LAST) && t_in_set + 1 < set_n) {
+            // the group's first half is done for this tile: the same code for the next tile of the set
+            ++t_in_set;
+            L.set_tile(prm, set_lo + t_in_set);
+            pc = pc_begin;
+            cur.v = __ldg(tape + pc);
+            continue;
+          }
+        } else {
+          L.park_row(ins.arg, acc);
+        }
+        break;
+      case FX_DCHAIN:
+        if (DEFER) {
+          run = inv_fermat(run, F);
+          unpark_pc = pc + 1;
+        }
+        break;
+      case FX_DUNPARK:
+        if (DEFER) defer_unpark<K, THREADS, VEC>(L, ins.arg, acc, run, qsp);
+        else plain_unpark<K, THREADS, VEC>(L, ins.arg, acc);
+        break;
+      case FX_DEND:
+        if (DEFER && t_in_set > 0) {
+          // second half done for this tile: the tile before it (the divisors come off the stack in reverse order)
+          --t_in_set;
+          L.set_tile(prm, set_lo + t_in_set);
+          pc = unpark_pc;
+          cur.v = __ldg(tape + pc);
+          continue;
+        }
+        break;
+
       // ---- everything else, out of line (copies of the state: the originals never have their address taken)
       default: {
-        if (ins.op == OP_HALT) return;
+        if (ins.op == OP_HALT) {
+          pc = pc_end;                 // (never reached through the loop condition; a stray HALT ends the pass)
+          continue;
+        }
         if (LEAN) {
           asm volatile("trap;");       // the launcher only picks a lean kernel for tapes without generic instructions
           break;
@@ -786,11 +943,12 @@ __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_
     cur = nxt;
     ++pc;
   }
+  }  // sets
 }
 
-template <int K, int THREADS, bool VEC, bool LEAN>
+template <int K, int THREADS, bool VEC, bool LEAN, bool DEFER>
 cudaError_t launch_k(const EvalParams& prm, const LaunchShape& sh, cudaStream_t stream) {
-  auto kern = eval_tape_kernel<K, THREADS, VEC, LEAN>;
+  auto kern = eval_tape_kernel<K, THREADS, VEC, LEAN, DEFER>;
   if (sh.smem > 48 * 1024) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
     if (e != cudaSuccess) return e;
@@ -799,25 +957,37 @@ cudaError_t launch_k(const EvalParams& prm, const LaunchShape& sh, cudaStream_t 
   return cudaGetLastError();
 }
 
+inline bool vec_ok(const EvalParams& prm) {
+  return (prm.n_points % 2 == 0) && (prm.in_stride % 2 == 0) && (prm.out_stride % 2 == 0) &&
+         ((uintptr_t)prm.values % 16 == 0) && ((uintptr_t)prm.out % 16 == 0) && ((uintptr_t)prm.park % 16 == 0);
+}
+
 template <int K, int THREADS>
 cudaError_t launch_t(const EvalParams& prm, const LaunchShape& sh, cudaStream_t stream) {
-  const bool vec = K >= 2 && (prm.n_points % 2 == 0) && (prm.in_stride % 2 == 0) && (prm.out_stride % 2 == 0) &&
-                   ((uintptr_t)prm.values % 16 == 0) && ((uintptr_t)prm.out % 16 == 0);
+  const bool vec = K >= 2 && vec_ok(prm);
   constexpr bool HAS_LEAN = K == 8 && THREADS <= 256;      // the only shapes whose register budget differs
-  if (sh.lean && HAS_LEAN) {
-    if (vec) return launch_k<K, THREADS, (K >= 2), HAS_LEAN>(prm, sh, stream);
-    return launch_k<K, THREADS, false, HAS_LEAN>(prm, sh, stream);
+  // the deferring kernel exists for the shapes big batches run in (16-byte accesses only)
+  constexpr bool HAS_DEFER = (K == 8 || K == 4) && THREADS <= 256;
+  if (sh.defer) {
+    if (!HAS_DEFER || !vec) return cudaErrorInvalidValue;    // choose_shape / launch_eval never ask for this
+    if (sh.lean && HAS_LEAN) return launch_k<K, THREADS, (K >= 2), HAS_LEAN, HAS_DEFER>(prm, sh, stream);
+    return launch_k<K, THREADS, (K >= 2), false, HAS_DEFER>(prm, sh, stream);
   }
-  if (vec) return launch_k<K, THREADS, (K >= 2), false>(prm, sh, stream);
-  return launch_k<K, THREADS, false, false>(prm, sh, stream);
+  if (sh.lean && HAS_LEAN) {
+    if (vec) return launch_k<K, THREADS, (K >= 2), HAS_LEAN, false>(prm, sh, stream);
+    return launch_k<K, THREADS, false, HAS_LEAN, false>(prm, sh, stream);
+  }
+  if (vec) return launch_k<K, THREADS, (K >= 2), false, false>(prm, sh, stream);
+  return launch_k<K, THREADS, false, false, false>(prm, sh, stream);
 }
 
 }  // namespace
 
 LaunchShape choose_shape(uint64_t n_points, uint32_t n_slots, int sm_count, int force_k, int force_threads,
-                         unsigned max_chunks, bool lean_ok) {
+                         unsigned max_chunks, bool lean_ok, const DeferInfo& df) {
   LaunchShape s;
-  auto smem_of = [&](int k, int th) { return (size_t)(64 + (size_t)n_slots * k * th) * sizeof(uint64_t); };
+  auto smem_words = [&](int k, int th, unsigned q) { return (size_t)64 + (size_t)n_slots * k * th + (size_t)q * th; };
+  auto smem_of = [&](int k, int th) { return smem_words(k, th, 0) * sizeof(uint64_t); };
   // resident warps per SM for a shape: registers (launch bounds: 80 per thread at 8 probes per thread, 64
   // below) and shared memory (227 KB per SM, 1 KB reserved per block)
   auto blocks_by_smem = [&](int k, int th) { return (int)((227 * 1024) / (smem_of(k, th) + 1024)); };
@@ -866,18 +1036,64 @@ LaunchShape choose_shape(uint64_t n_points, uint32_t n_slots, int sm_count, int 
   s.smem = smem_of(s.k, s.threads);
   s.lean = lean_of(s.k, s.threads);
   const uint64_t per_block = (uint64_t)s.threads * s.k;
-  s.blocks = (unsigned)((n_points + per_block - 1) / per_block);
+  s.n_tiles = (n_points + per_block - 1) / per_block;
+  s.blocks = (unsigned)s.n_tiles;
   // too few point tiles to fill the chip: split the functions of the collection over grid.y
   s.chunks = 1;
   const unsigned want = (unsigned)sm_count * 4;
   while (s.chunks < max_chunks && s.blocks * s.chunks < want) s.chunks <<= 1;
   if (s.chunks > max_chunks) s.chunks = max_chunks;
+  // Deferred divisions: the kernel that inverts once per thread pays one Fermat chain (78 multiplications) per
+  // thread for all the divisors the thread parks -- K probes x the functions of a group x the tiles of a set.  Worth
+  // it from about 32 divisors per chain (2.4 extra multiplications per division, no barrier).  A tape that is ONE
+  // group runs several tiles per set: then the grid is the resident blocks and every block takes a balanced range
+  // of tiles.
+  s.defer = false;
+  s.tiles = 1;
+  s.q_cap = 0;
+  if (df.parks && df.mode != 0 && (s.k == 8 || s.k == 4) && s.threads <= 256 && s.chunks == 1) {
+    unsigned resident = (unsigned)sm_count * (unsigned)std::max(1, std::min((s.k == 8 && !s.lean ? 768 : 1024) / s.threads,
+                                                                              blocks_by_smem(s.k, s.threads)));
+    if (df.max_blocks) resident = std::min(resident, df.max_blocks);
+    unsigned tiles = 1;
+    if (df.single) {
+      const uint64_t per = s.n_tiles / resident;                 // tiles per resident block
+      const unsigned tmax = df.tiles_max ? df.tiles_max : 8u;
+      tiles = (unsigned)std::min<uint64_t>(std::max<uint64_t>(per, 1), std::max(1u, tmax / std::max(1u, df.parks)));
+    }
+    const unsigned per_chain = (unsigned)s.k * tiles * df.parks;
+    if (per_chain >= 32 || df.mode == 2) {
+      const unsigned q = tiles * df.parks;
+      if (smem_words(s.k, s.threads, q) * sizeof(uint64_t) <= 200 * 1024) {
+        s.defer = true;
+        s.tiles = tiles;
+        s.q_cap = q;
+        s.smem = smem_words(s.k, s.threads, q) * sizeof(uint64_t);
+        // the grid of a multi-tile launch is what is resident WITH the product stack in shared memory
+        const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>((s.k == 8 && !s.lean ? 768 : 1024) / s.threads,
+                                                                                 (227 * 1024) / (s.smem + 1024)));
+        unsigned grid = (unsigned)sm_count * per_sm;
+        if (df.max_blocks) grid = std::min(grid, df.max_blocks);
+        if (df.single && s.n_tiles > grid) s.blocks = grid;
+      }
+    }
+  }
   return s;
 }
 
-cudaError_t launch_eval(const EvalParams& prm, const LaunchShape& sh, cudaStream_t stream) {
-  if (prm.n_points == 0) return cudaSuccess;
-  if (sh.smem > 227 * 1024) return cudaErrorInvalidValue;
+cudaError_t launch_eval(const EvalParams& prm_in, const LaunchShape& sh_in, cudaStream_t stream) {
+  if (prm_in.n_points == 0) return cudaSuccess;
+  if (sh_in.smem > 227 * 1024) return cudaErrorInvalidValue;
+  EvalParams prm = prm_in;
+  LaunchShape sh = sh_in;
+  if (sh.defer && !(sh.k >= 2 && vec_ok(prm))) {
+    // odd batch or unaligned rows: the same tape on the plain kernel (DUNPARK = load + block inversion)
+    sh.defer = false;
+    sh.tiles = 1;
+    sh.blocks = (unsigned)sh.n_tiles;
+  }
+  prm.n_tiles = sh.n_tiles;
+  prm.tiles_per_set = sh.defer ? sh.tiles : 1;
 #define FFGPU_CASE(KK, TT) \
   if (sh.k == KK && sh.threads == TT) return launch_t<KK, TT>(prm, sh, stream);
   FFGPU_CASE(1, 128) FFGPU_CASE(1, 256) FFGPU_CASE(1, 512)
@@ -915,7 +1131,9 @@ __global__ void __launch_bounds__(256) line_points_kernel(u64* __restrict__ valu
   const bool vec = (n_points % 2 == 0) && (stride % 2 == 0) && ((uintptr_t)values % 16 == 0) && ((uintptr_t)t % 16 == 0);
   if (vec) {
     for (u64 j = 2 * ((u64)blockIdx.x * blockDim.x + threadIdx.x); j < n_points; j += 2 * (u64)gridDim.x * blockDim.x) {
-      const ulonglong2 tt = __ldg(reinterpret_cast<const ulonglong2*>(t + j));
+      ulonglong2 tt = __ldg(reinterpret_cast<const ulonglong2*>(t + j));
+      tt.x = ff63::canon_pm(tt.x, F.c, F.p);        // any 64-bit t is reduced first: the product needs bounded operands
+      tt.y = ff63::canon_pm(tt.y, F.c, F.p);
       for (u32 v = 0; v < n_vars; v++) {
         const u64 av = __ldg(a + v), sv = __ldg(s + v);
         ulonglong2 x;
@@ -926,7 +1144,7 @@ __global__ void __launch_bounds__(256) line_points_kernel(u64* __restrict__ valu
     }
   } else {
     for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < n_points; j += (u64)gridDim.x * blockDim.x) {
-      const u64 tj = __ldg(t + j);
+      const u64 tj = ff63::canon_pm(__ldg(t + j), F.c, F.p);
       for (u32 v = 0; v < n_vars; v++)
         values[(u64)v * stride + j] = fcanon(fadd(fmul(mkR(tj), mkR(__ldg(a + v)), F), mkR(__ldg(s + v)), F), F);
     }
@@ -989,11 +1207,19 @@ __global__ void field_ops_kernel(int op, const u64* a, const u64* b, u64* r, u64
 }
 }  // namespace
 
+// SMs of the calling thread's current device (grid sizes of the grid-stride kernels)
+static unsigned current_sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+    return 148;
+  return (unsigned)n;
+}
+
 cudaError_t launch_fill_points(uint64_t* values, uint64_t n_vars, uint64_t n_points, uint64_t stride,
                                uint64_t first_point, uint64_t total_points, uint64_t seed, uint64_t p,
                                cudaStream_t stream) {
   if (n_vars * n_points == 0) return cudaSuccess;
-  fill_points_kernel<<<148 * 8, 256, 0, stream>>>(reinterpret_cast<u64*>(values), n_vars, n_points, stride, first_point, total_points, seed, p);
+  fill_points_kernel<<<current_sm_count() * 8, 256, 0, stream>>>(reinterpret_cast<u64*>(values), n_vars, n_points, stride, first_point, total_points, seed, p);
   return cudaGetLastError();
 }
 
@@ -1001,7 +1227,7 @@ cudaError_t launch_line_points(uint64_t* values, const uint64_t* t, const uint64
                                uint32_t n_vars, uint64_t n_points, uint64_t stride, uint64_t p, cudaStream_t stream) {
   if ((uint64_t)n_vars * n_points == 0) return cudaSuccess;
   const uint64_t want = (n_points / 2 + 255) / 256;
-  const unsigned blocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>(want, 1), 148 * 16);
+  const unsigned blocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)current_sm_count() * 16);
   line_points_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<u64*>(values), reinterpret_cast<const u64*>(t),
                                                  reinterpret_cast<const u64*>(a), reinterpret_cast<const u64*>(s),
                                                  n_vars, n_points, stride, p);

@@ -11,6 +11,8 @@ struct EvalParams {
   const Instr* tape;          // device, resolved for prime p, terminated by two OP_HALT
   const uint64_t* values;     // device, [n_vars][in_stride], canonical residues
   uint64_t* out;              // device, [n_out][out_stride]
+  uint64_t* park;             // where deferred divisors wait: rows laid out like out (NULL: in out itself).  Set when
+                              // out is mapped host memory, so that parked values do not cross PCIe twice.
   uint64_t n_points;
   uint64_t in_stride;
   uint64_t out_stride;
@@ -20,6 +22,17 @@ struct EvalParams {
   uint32_t n_slots;           // shared-memory slots per probe: spill slots from 0 up, temp slots from n_slots-1 down
   uint32_t n_instr;           // tape length without the terminators
   const uint32_t* chunk_bounds;  // device, n_chunks + 1 tape offsets at function boundaries (NULL: one chunk)
+  uint64_t n_tiles;           // tiles of threads * k points that cover the batch (set by launch_eval)
+  uint32_t tiles_per_set;     // deferring kernel: tiles a block runs between two inversions (set by launch_eval)
+};
+
+// what the tape offers the deferring kernel (Collection::defer_parks / defer_single) and how the caller wants it used
+struct DeferInfo {
+  unsigned parks = 0;         // most OP_DPARKs in one group of the tape; 0: the tape has no deferred division
+  bool single = false;        // the whole tape is one group: several tiles per inversion are possible
+  int mode = 1;               // 0 never, 1 when it pays (>= 32 divisors per chain), 2 whenever the shape allows it
+  unsigned tiles_max = 0;     // upper bound of the product stack in entries (0: 8)
+  unsigned max_blocks = 0;    // upper bound of the grid of a multi-tile launch (0: the resident blocks)
 };
 
 // probes per thread / threads per block actually used for a launch
@@ -30,10 +43,14 @@ struct LaunchShape {
   unsigned chunks;     // tape chunks (grid.y): blocks of a tile split the collection's functions
   size_t smem;
   bool lean;           // kernel without the generic instructions, 64 registers at k = 8 (kernels.cu)
+  uint64_t n_tiles;    // point tiles of the batch
+  bool defer;          // the kernel that inverts parked divisors once per thread (no barrier)
+  unsigned tiles;      // ... tiles per set (1 unless the tape is one group)
+  unsigned q_cap;      // ... entries of the per-thread product stack
 };
 
 LaunchShape choose_shape(uint64_t n_points, uint32_t n_slots, int sm_count, int force_k, int force_threads,
-                         unsigned max_chunks, bool lean_ok);
+                         unsigned max_chunks, bool lean_ok, const DeferInfo& df = DeferInfo());
 cudaError_t launch_eval(const EvalParams& prm, const LaunchShape& shape, cudaStream_t stream);
 
 // synthetic probe points, identical on host (bench/tests) and device:

@@ -109,8 +109,12 @@ struct ffgpu_queue {
       size_t n = 0;
       for (const Request& r : batch) n += r.n;
       std::string err;
-      bool ok = ensure(std::max<size_t>(n * std::max<size_t>(n_vars, 1), 1), std::max<size_t>(n * std::max<size_t>(n_out, 1), 1));
-      if (!ok) err = "pinned staging allocation failed";
+      // the tape may have been rebuilt since the queue was created (ffgpu_add_function / ffgpu_trim /
+      // ffgpu_set_factors + ffgpu_set_prime): requests and staging are laid out for the shape seen at creation
+      const bool same_shape = ffgpu_n_vars(tape) == n_vars && ffgpu_n_out(tape) == n_out;
+      if (!same_shape) err = "the collection changed its number of variables or outputs while a queue was attached";
+      bool ok = same_shape && ensure(std::max<size_t>(n * std::max<size_t>(n_vars, 1), 1), std::max<size_t>(n * std::max<size_t>(n_out, 1), 1));
+      if (!ok && err.empty()) err = "pinned staging allocation failed";
       if (ok) {
         if (batch[0].line) {
           const Request& r = batch[0];
@@ -128,18 +132,24 @@ struct ffgpu_queue {
         }
         if (!ok) err = ffgpu_last_error();
       }
+      // results are unpacked before the lock is taken: producers and consumers only wait for the hand-over
+      std::vector<Result> done;
+      if (ok) {
+        done.reserve(n);
+        size_t j = 0;
+        for (const Request& r : batch)
+          for (size_t q = 0; q < r.n; ++q, ++j) {
+            Result res;
+            res.index = r.first_index + q;
+            res.values.resize(n_out);
+            for (size_t f = 0; f < n_out; ++f) res.values[f] = h_out[f * n + j];
+            done.push_back(std::move(res));
+          }
+      }
       {
         std::lock_guard<std::mutex> lk(mtx);
         if (ok) {
-          size_t j = 0;
-          for (const Request& r : batch)
-            for (size_t q = 0; q < r.n; ++q, ++j) {
-              Result res;
-              res.index = r.first_index + q;
-              res.values.resize(n_out);
-              for (size_t f = 0; f < n_out; ++f) res.values[f] = h_out[f * n + j];
-              computed.push_back(std::move(res));
-            }
+          for (Result& res : done) computed.push_back(std::move(res));
           ++batches;
           probes_done += n;
           if (n > largest_batch) largest_batch = n;
@@ -160,7 +170,7 @@ extern "C" {
 // [variable][probe], evaluate all k probes in one batch, interleave the answers.  A GPU node can serve an
 // unmodified FireFly MPI master with this and two MPI calls.
 int ffgpu_eval_wire(ffgpu_tape* tape, const uint64_t* values_msg, size_t k, uint64_t* result_msg, uint32_t thread_id) {
-  if (!tape) return -1;
+  if (!tape) return ffgpu_eval(nullptr, nullptr, 0, nullptr, thread_id);   // sets ffgpu_last_error ("null tape")
   if (k == 0) return 0;
   const size_t n = ffgpu_n_vars(tape), m = ffgpu_n_out(tape);
   std::vector<uint64_t> in(std::max<size_t>(n * k, 1)), out(std::max<size_t>(m * k, 1));
