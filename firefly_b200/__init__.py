@@ -112,7 +112,7 @@ def _load() -> C.CDLL:
         "ffgpu_host_alloc": (C.c_void_p, [C.c_size_t]),
         "ffgpu_host_free": (None, [C.c_void_p]),
         "ffgpu_set_launch": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
-        "ffgpu_set_defer": (C.c_int, [C.c_void_p, C.c_int, C.c_uint, C.c_uint]),
+        "ffgpu_set_defer": (C.c_int, [C.c_void_p, C.c_int, C.c_uint]),
         "ffgpu_set_chunk": (C.c_int, [C.c_void_p, C.c_size_t]),
         "ffgpu_launch_count": (C.c_uint64, []),
         "ffgpu_fill_points": (
@@ -416,9 +416,9 @@ class GpuParser:
         if lib.ffgpu_set_launch(self.h, probes_per_thread, threads_per_block):
             raise FFGpuError(last_error())
 
-    def set_defer(self, mode: int = 1, stack_entries: int = 0, max_blocks: int = 0):
+    def set_defer(self, mode: int = 1, max_blocks: int = 0):
         """which kernel serves the deferred divisions (include/ffgpu.h, ffgpu_set_defer)"""
-        if lib.ffgpu_set_defer(self.h, mode, stack_entries, max_blocks):
+        if lib.ffgpu_set_defer(self.h, mode, max_blocks):
             raise FFGpuError(last_error())
 
     def set_chunk(self, points: int = 0):

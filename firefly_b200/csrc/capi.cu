@@ -121,7 +121,7 @@ struct ffgpu_tape {
   std::vector<uint32_t*> d_chunks;     // per device: Collection::chunk_table
   int force_k = 0, force_threads = 0;
   int defer_mode = -1;                 // -1: FFGPU_DEFER / default
-  unsigned defer_stack = 0, defer_max_blocks = 0;
+  unsigned defer_max_blocks = 0;
   size_t chunk = 0;
   bool needs_generic = true;           // the resolved tape has instructions without a fast dispatch code
 };
@@ -157,8 +157,8 @@ std::vector<std::string> to_vec(const char* const* s, size_t n) {
   return v;
 }
 
-// FFGPU_DEFER = 0 | 1 | 2: never / when it pays (default) / whenever possible run the kernel that inverts the parked
-// divisors of a thread with one Fermat chain (kernels.cu); FFGPU_DEFER_STACK: entries of its product stack (default 8)
+// FFGPU_DEFER = 0 | 1 | 2: never / when it pays (default) / whenever possible run the kernel that pipelines the
+// deferred divisions (kernels.cu)
 int defer_mode() {
   static const int mode = [] {
     const char* e = std::getenv("FFGPU_DEFER");
@@ -166,14 +166,6 @@ int defer_mode() {
   }();
   return mode;
 }
-unsigned defer_stack() {
-  static const unsigned n = [] {
-    const char* e = std::getenv("FFGPU_DEFER_STACK");
-    return e && *e ? (unsigned)std::atoi(e) : 0u;
-  }();
-  return n;
-}
-
 int launch(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, size_t n_points, uint64_t* d_out,
            size_t out_stride, cudaStream_t stream, uint64_t* d_park = nullptr) {
   const ffgpu::Collection& c = t->col;
@@ -192,10 +184,12 @@ int launch(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, siz
   prm.n_instr = (uint32_t)(c.tape.size() - 2);
   ffgpu::DeferInfo df;
   df.parks = c.defer_parks;
+  df.groups = c.defer_groups;
+  df.tape_instr = (unsigned)c.tape.size();
   df.single = c.defer_single;
   df.mode = t->defer_mode >= 0 ? t->defer_mode : defer_mode();
-  df.tiles_max = t->defer_stack ? t->defer_stack : defer_stack();
   df.max_blocks = t->defer_max_blocks;
+  prm.defer_parks = c.defer_parks;
   const ffgpu::LaunchShape sh = ffgpu::choose_shape(n_points, c.n_slots, t->ctx->devs[g].sm_count, t->force_k,
                                                     t->force_threads, c.max_chunks, !t->needs_generic, df);
   prm.chunk_bounds = nullptr;
@@ -376,7 +370,6 @@ ffgpu_tape* ffgpu_tape_clone(const ffgpu_tape* t) {
   n->force_k = t->force_k;
   n->force_threads = t->force_threads;
   n->defer_mode = t->defer_mode;
-  n->defer_stack = t->defer_stack;
   n->defer_max_blocks = t->defer_max_blocks;
   n->chunk = t->chunk;
   if (t->ctx) {
@@ -531,12 +524,10 @@ int ffgpu_set_launch(ffgpu_tape* t, int k, int threads) {
   return 0;
 }
 
-int ffgpu_set_defer(ffgpu_tape* t, int mode, unsigned stack_entries, unsigned max_blocks) {
+int ffgpu_set_defer(ffgpu_tape* t, int mode, unsigned max_blocks) {
   if (!t) return fail("null tape");
   if (mode < 0 || mode > 2) return fail("defer mode must be 0, 1 or 2");
-  if (stack_entries > 64) return fail("at most 64 product-stack entries");
   t->defer_mode = mode;
-  t->defer_stack = stack_entries;
   t->defer_max_blocks = max_blocks;
   return 0;
 }

@@ -1435,10 +1435,18 @@ bool Collection::finish(std::string& err) {
       a = b;
     }
     defer_single = n_groups == 1 && n_plain == 0;
+    defer_groups = (uint32_t)n_groups;
     for (size_t k = 0; k < functions.size(); ++k) count_work(functions[k]);
     fn_start.push_back((uint32_t)tape.size());
     peephole();
     if (enable_fuse) fuse();
+    // every DCHAIN carries the tape offset behind its group's DEND: the deferring kernel goes on there while the
+    // inversion runs, and comes back for the group's second half later
+    uint32_t after_dend = 0;
+    for (size_t i = tape.size(); i-- > 0;) {
+      if (tape[i].op == OP_DEND) after_dend = (uint32_t)i + 1;
+      else if (tape[i].op == OP_DCHAIN) tape[i].arg = after_dend;
+    }
     // Translation check of every function at one pseudo-random point: the tape must reproduce the value of
     // the expression tree.  A function that fails is re-emitted as a plain tree (no sharing, no deferral) on the
     // second pass; if that fails too the compilation is refused -- never a wrong probe value.

@@ -111,7 +111,8 @@ struct Collection {
   bool enable_defer = true;
   uint32_t n_deferred = 0;                    // divisions served that way
   uint32_t defer_parks = 0;                   // most DPARKs in one group (0: the tape has no group)
-  bool defer_single = false;                  // the whole tape is ONE group: the kernel may loop it over several tiles
+  uint32_t defer_groups = 0;                  // groups in the tape
+  bool defer_single = false;                  // the whole tape is ONE group: a block pipelines over tiles of points
   std::vector<uint32_t> fn_start;             // tape offsets at which a chunk of the tape may start (a function that
                                               // depends on no earlier one, or a group), in order, then the end
   // chunk tables: for C = 1, 2, 4, ... the C + 1 offsets that cut the tape into C runs of whole

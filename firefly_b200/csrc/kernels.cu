@@ -291,7 +291,6 @@ struct Lane {
   u64* pbase;            // parked divisors (rows like out) + first point of the tile
   u64 in_stride, out_stride;
   uint2* stk;            // [slot][k][thread], this thread's column
-  u64* qstk;             // [entry][thread]: running products of the parked divisors (deferring kernel)
   u64* scratch;          // 64 words for block_inverse
   u32 off[NACC];         // tile-relative offsets of this thread's accesses, clamped into the batch
   u32 own, left, tmp_top;
@@ -305,7 +304,6 @@ struct Lane {
     out_stride = prm.out_stride;
     scratch = smem;
     stk = reinterpret_cast<uint2*>(smem + 64) + threadIdx.x;
-    qstk = smem + 64 + (size_t)prm.n_slots * (K * THREADS) + threadIdx.x;
     tmp_top = prm.n_slots - 1;
     F = Field{prm.p, prm.c, prm.d};
     own = VEC ? 2 * threadIdx.x : threadIdx.x;
@@ -392,18 +390,78 @@ struct Lane {
   }
 };
 
-// ---- deferred divisions: one inversion per THREAD over everything the thread parks ------------------
-// Montgomery's trick on two levels, all in the thread's own registers, global rows and product stack -- no
-// shuffles, no barrier.  OP_DPARK writes the K canonical divisors of the current tile into the function's output
-// row and pushes the running product of everything parked so far; OP_DCHAIN inverts the final product (one Fermat
-// chain per thread); OP_DUNPARK, executed in exactly the reverse order of the DPARKs, reloads its K divisors,
-// peels their inverses off the running inverse.  Zero divisors (and lanes past the end of the batch, which never
-// store) enter the products as 1; a zero divisor gives 0 (reference: a/0 = 0, FFInt.cpp:146-153).
-//   cost per probe: (K - 1 + 1) + (K - 1 + 2 + 2 (K - 1)) multiplications per K probes = 3.9 at K = 8, plus the
-//   chain's 78 divided by the number of divisors the thread parked (K x functions of the group x tiles).
+// ---- deferred divisions, pipelined ---------------------------------------------------------------
+// A work item = one group of deferred divisions (tape.hpp) on one tile of points.  Its first half leaves the K
+// canonical divisors of every function of the group in the functions' output rows (OP_DPARK) and, per thread, the
+// product of everything the thread parked.  OP_DCHAIN then starts the block's inversion for the item WITHOUT waiting
+// for it: warp scans give every thread the product of the other lanes, the warps' products go to shared memory, all
+// warps but one announce themselves on a named barrier and walk on to the first half of the NEXT items; the one
+// duty warp of the item (they take turns) waits for the others' products, runs the Fermat chain on W lanes and
+// publishes 1 / (product of warp w) for every warp.  The item's second half (OP_DUNPARK ...) runs kDeferPipe - 1
+// items later, by which time the chain is long done: one multiplication gives the thread the inverse of its own
+// product, and Montgomery's trick peels the divisors off it in reverse order.  Nothing ever waits on a block-wide
+// barrier while the chain runs.  Zero divisors (and lanes past the end of the batch, which never store) enter the
+// products as 1; a zero divisor gives 0 (reference: a/0 = 0, FFInt.cpp:146-153).
+// Shared memory of the deferring kernel behind the slots, per work item in flight (slot = item mod kDeferPipe):
+//   Q[slot][park][thread]   running products of the divisors a thread parked in the item (only if a group has > 1)
+//   M[slot][thread]         product of the other lanes of the thread's warp
+//   SG[slot][2][W]          the warps' products, then per warp 1 / (its product)
+//   FIFO[warp][kDeferPipe]  the warp's items whose second half is still to run (tile | pc << 32 | DPARKs << 60)
+//   CTRL[warp][..]          the warp's pipeline state (u32 words, DeferCtrl): warps run independently of each other
+// Addresses are computed from the launch parameters where they are used and the pipeline state is touched only by
+// the deferred-division instructions: none of this lives in registers across the interpreter's dispatch.
+template <int K, int THREADS>
+struct DeferMem {
+  static constexpr u32 W = THREADS / 32;
+  static __device__ __forceinline__ u64* base(const EvalParams& prm) {
+    extern __shared__ __align__(16) u64 dyn_smem[];
+    return dyn_smem + 64 + (size_t)prm.n_slots * (K * THREADS);
+  }
+  static __device__ __forceinline__ u32 qwords(const EvalParams& prm) {
+    return prm.defer_parks > 1 ? (u32)kDeferPipe * prm.defer_parks * THREADS : 0u;
+  }
+  static __device__ __forceinline__ u64* q(const EvalParams& prm, u32 slot, u32 j) {
+    return base(prm) + (slot * prm.defer_parks + j) * THREADS + threadIdx.x;
+  }
+  static __device__ __forceinline__ u64* m(const EvalParams& prm, u32 slot) {
+    return base(prm) + qwords(prm) + slot * THREADS + threadIdx.x;
+  }
+  static __device__ __forceinline__ u64* sg(const EvalParams& prm, u32 slot) {
+    return base(prm) + qwords(prm) + kDeferPipe * THREADS + slot * (2 * W);
+  }
+  static __device__ __forceinline__ u64* fifo(const EvalParams& prm) {
+    return base(prm) + qwords(prm) + kDeferPipe * THREADS + kDeferPipe * (2 * W) + (threadIdx.x >> 5) * kDeferPipe;
+  }
+  static __device__ __forceinline__ volatile u32* ctrl(const EvalParams& prm) {
+    return reinterpret_cast<volatile u32*>(base(prm) + qwords(prm) + kDeferPipe * THREADS + kDeferPipe * (2 * W) + W * kDeferPipe) +
+           (threadIdx.x >> 5) * 16;
+  }
+  static size_t words(u32 parks) {
+    return (parks > 1 ? (size_t)kDeferPipe * parks * THREADS : 0) + (size_t)kDeferPipe * THREADS + (size_t)kDeferPipe * 2 * W +
+           (size_t)W * kDeferPipe + (size_t)W * 8;
+  }
+};
+// words of CTRL: every lane of the warp writes the same value, so every lane reads what it wrote
+enum DeferCtrl : u32 {
+  DC_TILE_LO = 0, DC_TILE_HI,   // first tile of the block's range
+  DC_MY_TILES,                  // tiles in the range
+  DC_CUR_TILE,                  // tile (relative) the FIRST halves are running on
+  DC_ITEMS,                     // first halves finished so far (item i lives in slot i mod kDeferPipe)
+  DC_PEND,                      // items whose second half is still to run
+  DC_RET_PC,                    // where the tape goes on after the second half that is running
+  DC_CSLOT,                     // slot of the item whose second half is running
+  DC_QSP,                       // DPARKs of the running first half / divisors still parked in the running second half
+};
+
+__device__ __forceinline__ void named_sync(u32 id, u32 n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_arrive(u32 id, u32 n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
 template <int K, int THREADS, bool VEC>
-__device__ __forceinline__ void defer_park(const Lane<K, THREADS, VEC>& L, u32 row, const R (&acc)[K], R& run, u32& qsp) {
+__device__ __forceinline__ void defer_park(const EvalParams& prm, const Lane<K, THREADS, VEC>& L, u32 row, const R (&acc)[K]) {
+  typedef DeferMem<K, THREADS> DM;
   const Field F = L.F;
+  volatile u32* ctrl = DM::ctrl(prm);
+  const u32 slot = ctrl[DC_ITEMS] % kDeferPipe, qsp = ctrl[DC_QSP];
   L.park_row(row, acc);
   R e[K];
 #pragma unroll
@@ -417,13 +475,19 @@ __device__ __forceinline__ void defer_park(const Lane<K, THREADS, VEC>& L, u32 r
 #pragma unroll
     for (int k = 0; k + w < K; k += 2 * w) e[k] = fmul(e[k], e[k + w], F);
   }
-  run = qsp ? fmul(run, e[0], F) : e[0];
-  L.qstk[(size_t)qsp * THREADS] = toU(run);
-  ++qsp;
+  // the running product of the item waits in M[slot] (and, for the way back, on the product stack)
+  const R run = qsp ? fmul(mkR(*DM::m(prm, slot)), e[0], F) : e[0];
+  *DM::m(prm, slot) = toU(run);
+  if (prm.defer_parks > 1) *DM::q(prm, slot, qsp) = toU(run);
+  ctrl[DC_QSP] = qsp + 1;
 }
 template <int K, int THREADS, bool VEC>
-__device__ __forceinline__ void defer_unpark(const Lane<K, THREADS, VEC>& L, u32 row, R (&acc)[K], R& run, u32& qsp) {
+__device__ __forceinline__ void defer_unpark(const EvalParams& prm, const Lane<K, THREADS, VEC>& L, u32 row, R (&acc)[K]) {
+  typedef DeferMem<K, THREADS> DM;
   const Field F = L.F;
+  volatile u32* ctrl = DM::ctrl(prm);
+  const u32 slot = ctrl[DC_CSLOT], qsp = ctrl[DC_QSP] - 1;
+  ctrl[DC_QSP] = qsp;
   u64 cv[K];
   L.load_row(row, cv);
   bool z[K];
@@ -436,11 +500,11 @@ __device__ __forceinline__ void defer_unpark(const Lane<K, THREADS, VEC>& L, u32
   pre[0] = e[0];
 #pragma unroll
   for (int k = 1; k < K; k++) pre[k] = fmul(pre[k - 1], e[k], F);
-  --qsp;
-  R I = run;                                   // 1 / (everything parked up to and including this row)
+  const R run = mkR(*DM::m(prm, slot));        // 1 / (everything the thread parked up to and including this row)
+  R I = run;
   if (qsp) {
-    I = fmul(run, mkR(L.qstk[(size_t)(qsp - 1) * THREADS]), F);     // times everything parked before it
-    run = fmul(run, pre[K - 1], F);
+    I = fmul(run, mkR(*DM::q(prm, slot, qsp - 1)), F);     // times everything parked before it
+    *DM::m(prm, slot) = toU(fmul(run, pre[K - 1], F));
   }
 #pragma unroll
   for (int k = K - 1; k >= 1; --k) {
@@ -450,14 +514,73 @@ __device__ __forceinline__ void defer_unpark(const Lane<K, THREADS, VEC>& L, u32
   }
   acc[0] = z[0] ? mkR(0) : I;
 }
-// the same instructions in the kernel that does not defer: DPARK stores, DUNPARK reloads and inverts per block
+// first half of an item done: `run` = product of all divisors this thread parked.  Never blocks (except the duty warp).
 template <int K, int THREADS, bool VEC>
-__device__ __forceinline__ void plain_unpark(const Lane<K, THREADS, VEC>& L, u32 row, R (&acc)[K]) {
-  u64 cv[K];
-  L.load_row(row, cv);
+__device__ __forceinline__ void defer_chain_begin(const EvalParams& prm, const Lane<K, THREADS, VEC>& L, u32 slot, u32 duty) {
+  constexpr int W = THREADS / 32;
+  const Field F = L.F;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const R run = mkR(*DeferMem<K, THREADS>::m(prm, slot));
+  R s = run, u = run;
 #pragma unroll
-  for (int k = 0; k < K; k++) acc[k] = L.probe_in_range(k) ? mkR(cv[k]) : mkR(1);   // lanes past the end never stored
-  block_inverse<K, THREADS>(acc, L.F, L.scratch);
+  for (int off = 1; off < 32; off <<= 1) {
+    const R sm = fmul(s, shfl_up(s, off), F);
+    const R um = fmul(u, shfl_down(u, off), F);
+    if (lane >= (unsigned)off) s = sm;
+    if (lane + off < 32) u = um;
+  }
+  R sx = shfl_up(s, 1);        // product of the lanes before this one
+  R ux = shfl_down(u, 1);      // product of the lanes after this one
+  if (lane == 0) sx = mkR(1);
+  if (lane == 31) ux = mkR(1);
+  *DeferMem<K, THREADS>::m(prm, slot) = toU(fmul(sx, ux, F));
+  u64* S = DeferMem<K, THREADS>::sg(prm, slot);
+  if (lane == 31) S[warp] = toU(s);
+  __threadfence_block();
+  if (warp != duty) {
+    named_arrive(1 + slot, THREADS);
+    return;
+  }
+  named_sync(1 + slot, THREADS);               // all warps' products are in S
+  R P = lane < (unsigned)W ? mkR(S[lane]) : mkR(1);
+#pragma unroll
+  for (int off = 1; off < W; off <<= 1) {
+    const R pm = fmul(P, shfl_up(P, off), F);
+    if (lane >= (unsigned)off) P = pm;
+  }
+  const R IP = inv_fermat(P, F);               // lane w: 1 / (warps 0..w)
+  R Px = shfl_up(P, 1);                        // warps 0..w-1
+  if (lane == 0) Px = mkR(1);
+  if (lane < (unsigned)W) S[W + lane] = toU(fmul(IP, Px, F));    // 1 / (warp w)
+  __threadfence_block();
+  named_arrive(1 + kDeferPipe + slot, THREADS);
+}
+// second half of an item starts: M[slot] = 1 / (product of all divisors this thread parked in the item)
+template <int K, int THREADS, bool VEC>
+__device__ __forceinline__ void defer_chain_end(const EvalParams& prm, const Lane<K, THREADS, VEC>& L, u32 slot, u32 duty) {
+  constexpr int W = THREADS / 32;
+  const unsigned warp = threadIdx.x >> 5;
+  if (warp != duty) named_sync(1 + kDeferPipe + slot, THREADS);
+  else __syncwarp();
+  const u64* S = DeferMem<K, THREADS>::sg(prm, slot);
+  u64* m = DeferMem<K, THREADS>::m(prm, slot);
+  *m = toU(fmul(mkR(S[W + warp]), mkR(*m), L.F));
+}
+// Pipeline control at the two places where a second half can start (OP_DCHAIN with a full pipeline, end of the tape
+// with nothing left to start): takes the oldest waiting item, moves the thread to its tile, returns its first pc.
+template <int K, int THREADS, bool VEC>
+__device__ __forceinline__ u32 defer_start_second_half(const EvalParams& prm, Lane<K, THREADS, VEC>& L, u32 ret_pc) {
+  typedef DeferMem<K, THREADS> DM;
+  volatile u32* ctrl = DM::ctrl(prm);
+  const u32 n_pend = ctrl[DC_PEND], oldest = ctrl[DC_ITEMS] - n_pend, slot = oldest % kDeferPipe;
+  const u64 e = DM::fifo(prm)[slot];
+  L.set_tile(prm, (((u64)ctrl[DC_TILE_HI] << 32) | ctrl[DC_TILE_LO]) + (u32)e);
+  defer_chain_end<K, THREADS, VEC>(prm, L, slot, oldest % (THREADS / 32));
+  ctrl[DC_CSLOT] = slot;
+  ctrl[DC_QSP] = (u32)(e >> 60);
+  ctrl[DC_RET_PC] = ret_pc;
+  ctrl[DC_PEND] = n_pend - 1;
+  return (u32)(e >> 32) & 0x0fffffffu;
 }
 
 #ifndef FFGPU_GENERIC_INLINE
@@ -577,8 +700,23 @@ __device__ FFGPU_GENERIC_INLINE u32 generic_op(const Lane<K, THREADS, VEC>& L, u
     case OP_STORE:
       L.store_row(ins.arg, acc);
       break;
+    // deferred divisions on the kernel that does not defer: the divisor waits in its row, the block inverts it
+    case OP_DPARK:
+      L.park_row(ins.arg, acc);
+      break;
+    case OP_DUNPARK: {
+      u64 cv[K];
+      L.load_row(ins.arg, cv);
+#pragma unroll
+      for (int k = 0; k < K; k++) acc[k] = L.probe_in_range(k) ? mkR(cv[k]) : mkR(1);   // lanes past the end never stored
+      block_inverse<K, THREADS>(acc, F, L.scratch);
+      break;
+    }
+    case OP_DCHAIN:
+    case OP_DEND:
+      break;
     default:
-      asm volatile("trap;");     // an instruction without code (the deferred-division ops always have a fast code)
+      asm volatile("trap;");     // an instruction without code: never compute on with garbage
       break;
   }
   if (ins.flags & F_NEGR) {
@@ -615,34 +753,51 @@ __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_
     pc_end = __ldg(prm.chunk_bounds + blockIdx.y + 1);
   }
   // Tiles of this block.  The plain kernel has one tile per block.  The deferring kernel takes a contiguous range
-  // of tiles (the grid is sized to the resident blocks, the ranges are balanced) and walks it in SETS of up to
-  // prm.tiles_per_set tiles: a tape that is one group of deferred divisions runs its first half for every tile of
-  // the set, inverts once, and runs its second half for the tiles in reverse order.
-  u64 tile_lo = blockIdx.x, tile_hi = (u64)blockIdx.x + 1;
-  u32 set_len = 1;
+  // of tiles (a tape that is one group of deferred divisions is launched with as many blocks as are resident, the
+  // ranges balanced) and runs the tape once per tile; second halves of groups run kDeferPipe - 1 work items late.
+  u64 tile = blockIdx.x;
   if (DEFER) {
-    tile_lo = prm.n_tiles * (u64)blockIdx.x / gridDim.x;
-    tile_hi = prm.n_tiles * ((u64)blockIdx.x + 1) / gridDim.x;
-    const u32 cnt = (u32)(tile_hi - tile_lo);
-    const u32 sets = (cnt + prm.tiles_per_set - 1) / prm.tiles_per_set;
-    set_len = sets ? (cnt + sets - 1) / sets : 1;
+    tile = prm.n_tiles * (u64)blockIdx.x / gridDim.x;
+    const u32 my_tiles = (u32)(prm.n_tiles * ((u64)blockIdx.x + 1) / gridDim.x - tile);
+    if (my_tiles == 0) return;
+    volatile u32* ctrl = DeferMem<K, THREADS>::ctrl(prm);
+    ctrl[DC_TILE_LO] = (u32)tile;
+    ctrl[DC_TILE_HI] = (u32)(tile >> 32);
+    ctrl[DC_MY_TILES] = my_tiles;
+    ctrl[DC_CUR_TILE] = 0;
+    ctrl[DC_ITEMS] = 0;
+    ctrl[DC_PEND] = 0;
+    ctrl[DC_QSP] = 0;
   }
 
   R acc[K];
 #pragma unroll
   for (int k = 0; k < K; k++) acc[k] = opaque(0);
 
-  for (u64 set_lo = tile_lo; set_lo < tile_hi; set_lo += set_len) {
-  const u32 set_n = DEFER ? (u32)((tile_hi - set_lo) < (u64)set_len ? (tile_hi - set_lo) : (u64)set_len) : 1u;
-  u32 t_in_set = 0;                          // tile of the set the tape is running on
-  L.set_tile(prm, set_lo);
+  L.set_tile(prm, tile);
   u32 sp = 0;                                // spill-stack pointer (uniform)
-  u32 qsp = 0, unpark_pc = 0;                // deferred divisions: product-stack pointer, first instruction after DCHAIN
-  R run = opaque(1);                         // ... running product, then running inverse
   u32 pc = pc_begin;
   InstrWord cur, nxt;
   cur.v = __ldg(tape + pc);
-  for (; pc < pc_end;) {
+  for (;;) {
+    if (pc >= pc_end) {
+      if (!DEFER) break;
+      volatile u32* ctrl = DeferMem<K, THREADS>::ctrl(prm);
+      const u32 cur_tile = ctrl[DC_CUR_TILE];
+      if (cur_tile + 1 < ctrl[DC_MY_TILES]) {
+        // the same tape on the next tile of the range
+        ctrl[DC_CUR_TILE] = cur_tile + 1;
+        L.set_tile(prm, (((u64)ctrl[DC_TILE_HI] << 32) | ctrl[DC_TILE_LO]) + cur_tile + 1);
+        pc = pc_begin;
+      } else if (ctrl[DC_PEND]) {
+        // nothing left to start: the second halves still waiting, oldest first
+        pc = defer_start_second_half<K, THREADS, VEC>(prm, L, pc_end);
+      } else {
+        break;
+      }
+      cur.v = __ldg(tape + pc);
+      continue;
+    }
     nxt.v = __ldg(tape + pc + 1);            // the tape ends in two HALTs: always in bounds
     const Instr ins = cur.i;
     R b[K];
@@ -884,50 +1039,58 @@ __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_
       }
 
       // ---- deferred top-level divisions (tape.hpp) ----------------------------------------------------------
+      // (the kernel that does not defer takes all four through the generic path below)
       case FX_DPARK:
-        if (DEFER) {
-          defer_park<K, THREADS, VEC>(L, ins.arg, acc, run, qsp);
-          if ((ins.flags & F_LAST) && t_in_set + 1 < set_n) {
-            // the group's first half is done for this tile: the same code for the next tile of the set
-            ++t_in_set;
-            L.set_tile(prm, set_lo + t_in_set);
-            pc = pc_begin;
-            cur.v = __ldg(tape + pc);
-            continue;
-          }
-        } else {
-          L.park_row(ins.arg, acc);
-        }
+        if (!DEFER) goto generic;
+        defer_park<K, THREADS, VEC>(prm, L, ins.arg, acc);
         break;
-      case FX_DCHAIN:
-        if (DEFER) {
-          run = inv_fermat(run, F);
-          unpark_pc = pc + 1;
-        }
-        break;
+      case FX_DCHAIN: {
+        if (!DEFER) goto generic;
+        // first half of an item done: start its inversion, do not wait for it.  ACC is dead here (its value is
+        // parked): say so, the scans need the registers.
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[k] = opaque(0);
+        volatile u32* ctrl = DeferMem<K, THREADS>::ctrl(prm);
+        const u32 item = ctrl[DC_ITEMS], n_pend = ctrl[DC_PEND] + 1;
+        defer_chain_begin<K, THREADS, VEC>(prm, L, item % kDeferPipe, item % (THREADS / 32));
+        DeferMem<K, THREADS>::fifo(prm)[item % kDeferPipe] =
+            (u64)ctrl[DC_CUR_TILE] | ((u64)(pc + 1) << 32) | ((u64)ctrl[DC_QSP] << 60);
+        ctrl[DC_ITEMS] = item + 1;
+        ctrl[DC_PEND] = n_pend;
+        ctrl[DC_QSP] = 0;
+        // a full pipeline: the oldest item's inversion has had kDeferPipe - 1 first halves of time, its second half
+        // runs now; then the tape goes on behind this group (ins.arg = the instruction after its DEND)
+        if (n_pend == (u32)kDeferPipe) pc = defer_start_second_half<K, THREADS, VEC>(prm, L, ins.arg);
+        else pc = ins.arg;
+        cur.v = __ldg(tape + pc);
+        continue;
+      }
       case FX_DUNPARK:
-        if (DEFER) defer_unpark<K, THREADS, VEC>(L, ins.arg, acc, run, qsp);
-        else plain_unpark<K, THREADS, VEC>(L, ins.arg, acc);
+        if (!DEFER) goto generic;
+        defer_unpark<K, THREADS, VEC>(prm, L, ins.arg, acc);
         break;
-      case FX_DEND:
-        if (DEFER && t_in_set > 0) {
-          // second half done for this tile: the tile before it (the divisors come off the stack in reverse order)
-          --t_in_set;
-          L.set_tile(prm, set_lo + t_in_set);
-          pc = unpark_pc;
-          cur.v = __ldg(tape + pc);
-          continue;
-        }
-        break;
+      case FX_DEND: {
+        if (!DEFER) goto generic;
+        // second half done: back to the tile and the place the first halves have reached
+        volatile u32* ctrl = DeferMem<K, THREADS>::ctrl(prm);
+        L.set_tile(prm, (((u64)ctrl[DC_TILE_HI] << 32) | ctrl[DC_TILE_LO]) + ctrl[DC_CUR_TILE]);
+        ctrl[DC_QSP] = 0;
+        pc = ctrl[DC_RET_PC];
+        cur.v = __ldg(tape + pc);
+        continue;
+      }
 
       // ---- everything else, out of line (copies of the state: the originals never have their address taken)
-      default: {
+      default:
+      generic: {
         if (ins.op == OP_HALT) {
           pc = pc_end;                 // (never reached through the loop condition; a stray HALT ends the pass)
           continue;
         }
         if (LEAN) {
-          asm volatile("trap;");       // the launcher only picks a lean kernel for tapes without generic instructions
+          // the launcher only picks a lean kernel for tapes without generic instructions (and, unless it defers, without
+          // deferred divisions)
+          asm volatile("trap;");
           break;
         }
         Lane<K, THREADS, VEC> L2 = L;
@@ -943,7 +1106,6 @@ __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_
     cur = nxt;
     ++pc;
   }
-  }  // sets
 }
 
 template <int K, int THREADS, bool VEC, bool LEAN, bool DEFER>
@@ -1043,39 +1205,27 @@ LaunchShape choose_shape(uint64_t n_points, uint32_t n_slots, int sm_count, int 
   const unsigned want = (unsigned)sm_count * 4;
   while (s.chunks < max_chunks && s.blocks * s.chunks < want) s.chunks <<= 1;
   if (s.chunks > max_chunks) s.chunks = max_chunks;
-  // Deferred divisions: the kernel that inverts once per thread pays one Fermat chain (78 multiplications) per
-  // thread for all the divisors the thread parks -- K probes x the functions of a group x the tiles of a set.  Worth
-  // it from about 32 divisors per chain (2.4 extra multiplications per division, no barrier).  A tape that is ONE
-  // group runs several tiles per set: then the grid is the resident blocks and every block takes a balanced range
-  // of tiles.
+  // Deferred divisions: the deferring kernel overlaps the block's Fermat chain of one work item (a group of deferred
+  // divisions on one tile) with the first halves of the next kDeferPipe - 1 items.  It needs items to pipeline over:
+  // a tape that is ONE group gets as many blocks as are resident and every block a balanced range of tiles; a tape
+  // of several groups keeps one tile per block and pipelines over its groups.
   s.defer = false;
-  s.tiles = 1;
-  s.q_cap = 0;
-  if (df.parks && df.mode != 0 && (s.k == 8 || s.k == 4) && s.threads <= 256 && s.chunks == 1) {
-    unsigned resident = (unsigned)sm_count * (unsigned)std::max(1, std::min((s.k == 8 && !s.lean ? 768 : 1024) / s.threads,
-                                                                              blocks_by_smem(s.k, s.threads)));
-    if (df.max_blocks) resident = std::min(resident, df.max_blocks);
-    unsigned tiles = 1;
-    if (df.single) {
-      const uint64_t per = s.n_tiles / resident;                 // tiles per resident block
-      const unsigned tmax = df.tiles_max ? df.tiles_max : 8u;
-      tiles = (unsigned)std::min<uint64_t>(std::max<uint64_t>(per, 1), std::max(1u, tmax / std::max(1u, df.parks)));
-    }
-    const unsigned per_chain = (unsigned)s.k * tiles * df.parks;
-    if (per_chain >= 32 || df.mode == 2) {
-      const unsigned q = tiles * df.parks;
-      if (smem_words(s.k, s.threads, q) * sizeof(uint64_t) <= 200 * 1024) {
-        s.defer = true;
-        s.tiles = tiles;
-        s.q_cap = q;
-        s.smem = smem_words(s.k, s.threads, q) * sizeof(uint64_t);
-        // the grid of a multi-tile launch is what is resident WITH the product stack in shared memory
-        const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>((s.k == 8 && !s.lean ? 768 : 1024) / s.threads,
-                                                                                 (227 * 1024) / (s.smem + 1024)));
-        unsigned grid = (unsigned)sm_count * per_sm;
-        if (df.max_blocks) grid = std::min(grid, df.max_blocks);
-        if (df.single && s.n_tiles > grid) s.blocks = grid;
-      }
+  if (df.parks) s.lean = false;        // the plain lean kernel has no code for the deferred-division instructions ...
+  if (df.parks && df.mode != 0 && (s.k == 8 || s.k == 4) && s.threads <= 256 && df.tape_instr < (1u << 28)) {
+    const size_t words = smem_words(s.k, s.threads, 0) +
+                         (s.threads == 256 ? DeferMem<8, 256>::words(df.parks) : DeferMem<8, 128>::words(df.parks));
+    const size_t bytes = words * sizeof(uint64_t);
+    const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>((s.k == 8 && !s.lean ? 768 : 1024) / s.threads,
+                                                                             (227 * 1024) / (bytes + 1024)));
+    unsigned grid = (unsigned)sm_count * per_sm;
+    if (df.max_blocks) grid = std::min(grid, df.max_blocks);
+    const uint64_t tiles_per_block = df.single ? std::max<uint64_t>(1, s.n_tiles / grid) : 1;
+    const uint64_t items = tiles_per_block * std::max(1u, df.groups / s.chunks);
+    if (bytes <= 200 * 1024 && (items >= 2 * (uint64_t)kDeferPipe || df.mode == 2)) {
+      s.defer = true;
+      s.lean = lean_of(s.k, s.threads);    // ... the deferring lean kernel has
+      s.smem = bytes;
+      if (df.single && s.n_tiles > grid) s.blocks = grid;
     }
   }
   return s;
@@ -1089,11 +1239,10 @@ cudaError_t launch_eval(const EvalParams& prm_in, const LaunchShape& sh_in, cuda
   if (sh.defer && !(sh.k >= 2 && vec_ok(prm))) {
     // odd batch or unaligned rows: the same tape on the plain kernel (DUNPARK = load + block inversion)
     sh.defer = false;
-    sh.tiles = 1;
+    sh.lean = false;
     sh.blocks = (unsigned)sh.n_tiles;
   }
   prm.n_tiles = sh.n_tiles;
-  prm.tiles_per_set = sh.defer ? sh.tiles : 1;
 #define FFGPU_CASE(KK, TT) \
   if (sh.k == KK && sh.threads == TT) return launch_t<KK, TT>(prm, sh, stream);
   FFGPU_CASE(1, 128) FFGPU_CASE(1, 256) FFGPU_CASE(1, 512)

@@ -23,15 +23,23 @@ struct EvalParams {
   uint32_t n_instr;           // tape length without the terminators
   const uint32_t* chunk_bounds;  // device, n_chunks + 1 tape offsets at function boundaries (NULL: one chunk)
   uint64_t n_tiles;           // tiles of threads * k points that cover the batch (set by launch_eval)
-  uint32_t tiles_per_set;     // deferring kernel: tiles a block runs between two inversions (set by launch_eval)
+  uint32_t defer_parks;       // deferring kernel: most OP_DPARKs of one group (rows of the per-thread product stack)
 };
+
+// Deferring kernel: work items (a group of deferred divisions on one tile of points) in flight per block -- the second
+// half of an item runs after the first halves of the next kDeferPipe - 1 items, which is the time its inversion has
+#ifndef FFGPU_PIPE
+#define FFGPU_PIPE 3
+#endif
+constexpr int kDeferPipe = FFGPU_PIPE;
 
 // what the tape offers the deferring kernel (Collection::defer_parks / defer_single) and how the caller wants it used
 struct DeferInfo {
   unsigned parks = 0;         // most OP_DPARKs in one group of the tape; 0: the tape has no deferred division
-  bool single = false;        // the whole tape is one group: several tiles per inversion are possible
-  int mode = 1;               // 0 never, 1 when it pays (>= 32 divisors per chain), 2 whenever the shape allows it
-  unsigned tiles_max = 0;     // upper bound of the product stack in entries (0: 8)
+  unsigned groups = 0;        // groups of deferred divisions in the tape
+  unsigned tape_instr = 0;    // tape length (the pipeline keeps tape offsets in 28 bits)
+  bool single = false;        // the whole tape is one group: a block pipelines over the tiles of its range
+  int mode = 1;               // 0 never, 1 when a block has enough work items to pipeline, 2 whenever the shape allows it
   unsigned max_blocks = 0;    // upper bound of the grid of a multi-tile launch (0: the resident blocks)
 };
 
@@ -44,9 +52,7 @@ struct LaunchShape {
   size_t smem;
   bool lean;           // kernel without the generic instructions, 64 registers at k = 8 (kernels.cu)
   uint64_t n_tiles;    // point tiles of the batch
-  bool defer;          // the kernel that inverts parked divisors once per thread (no barrier)
-  unsigned tiles;      // ... tiles per set (1 unless the tape is one group)
-  unsigned q_cap;      // ... entries of the per-thread product stack
+  bool defer;          // the kernel that pipelines deferred divisions (inversions overlap the next items' work)
 };
 
 LaunchShape choose_shape(uint64_t n_points, uint32_t n_slots, int sm_count, int force_k, int force_threads,

@@ -1,6 +1,7 @@
 """Deferred top-level divisions on the device (tape.hpp OP_DPARK / OP_DCHAIN / OP_DUNPARK / OP_DEND): the kernel that
-inverts everything a thread has parked with ONE Fermat chain -- over the functions of a group and over several tiles of
-points -- must return exactly what the plain kernel (one inversion per thread block) and the oracle return.
+runs the block's inversion of one work item behind the evaluation of the next ones -- over the groups of a collection
+and over several tiles of points -- must return exactly what the plain kernel (the block waits for its inversion) and
+the oracle return.
 Reference semantics at stake: a/0 = 0 per probe (reference: source/FFInt.cpp:146-153), evaluate_pre's value for every
 function (source/include/firefly/ShuntingYardParser.hpp:365-479)."""
 import numpy as np
@@ -47,14 +48,14 @@ def test_deferring_kernel_matches_oracle(ctx, oracle, name, k, threads):
     par.set_launch(k, threads)
     op = oracle.parse(funs, vars_, p)
     nv = len(vars_)
-    for n, stack, max_blocks in [(2, 0, 0), (1000, 1, 0), (2050, 0, 0), (4097, 3, 1), (12346, 8, 3), (20000, 16, 2), (9001, 2, 4)]:
+    for n, max_blocks in [(2, 0), (1000, 0), (2050, 0), (4097, 1), (12346, 3), (20000, 2), (9001, 4), (70000, 1), (50001, 5)]:
         pts = ff.synthetic_points(nv, n, p, seed=n)
         pts[:, 1] = 0
         if nv >= 2:
             pts[1, 0::7] = pts[0, 0::7]            # x = y: divisors vanish in scattered lanes
             pts[:, n // 2] = pts[0, n // 2]        # ... and all variables equal in one probe
         want = op.eval(pts)
-        par.set_defer(2, stack, max_blocks)        # the deferring kernel whenever the shape has one
+        par.set_defer(2, max_blocks)               # the deferring kernel whenever the shape has one
         assert np.array_equal(par.evaluate_pre(pts), want), (name, n, k, threads, "deferring kernel")
         par.set_defer(0)                           # the same tape on the plain kernel
         assert np.array_equal(par.evaluate_pre(pts), want), (name, n, k, threads, "plain kernel, deferred tape")
@@ -68,8 +69,8 @@ def test_deferring_kernel_matches_oracle(ctx, oracle, name, k, threads):
 
 @pytest.mark.parametrize("name", ["f2", "f4"])
 def test_deferring_kernel_full_size(ctx, oracle, name):
-    """2^23 + 2 points, device resident, automatic launch: the multi-tile deferring kernel (8 tiles per inversion)
-    against the plain kernel on EVERY point, and against the oracle on a sample."""
+    """2^23 + 2 points, device resident, automatic launch: the deferring kernel (persistent blocks pipelining over
+    their tiles) against the plain kernel on EVERY point, and against the oracle on a sample."""
     import torch
     text, vars_ = W.benchmark(name)
     p = P0
