@@ -34,7 +34,7 @@ INSTR_DTYPE = np.dtype(
 )
 # tape.hpp
 OPS = ["HALT", "LOAD", "ADD", "SUB", "MUL", "SQR", "NEG", "INV", "POWU", "NPOWU", "POWL", "NPOWL", "STORE", "MULADD",
-       "SAVE", "ACCUM", "TERM", "ACCUM2", "ADDVARS", "MULVARS", "DPARK", "DCHAIN", "DUNPARK", "DEND"]
+       "SAVE", "ACCUM", "TERM", "ACCUM2", "ADDVARS", "MULVARS", "DPARK", "DCHAIN", "DUNPARK", "DEND", "NPARK", "NMUL"]
 SRCS = ["NONE", "POP", "VAR", "NEGVAR", "CONST", "TMP"]
 F_PUSH, F_SWAP, F_NEGR, F_INIT, F_SWAP2, F_INIT2, F_CMUL = 1, 2, 4, 8, 16, 32, 128
 TM_LOAD, TM_ADD, TM_SUB, TM_RSUB, TM_MUL = 0, 1, 2, 3, 4

@@ -186,6 +186,7 @@ int launch(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, siz
   df.parks = c.defer_parks;
   df.groups = c.defer_groups;
   df.tape_instr = (unsigned)c.tape.size();
+  df.numerators = c.defer_numerators;
   df.single = c.defer_single;
   df.mode = t->defer_mode >= 0 ? t->defer_mode : defer_mode();
   df.max_blocks = t->defer_max_blocks;
@@ -198,7 +199,15 @@ int launch(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, siz
     while ((1u << idx) < sh.chunks) ++idx;
     prm.chunk_bounds = t->d_chunks[g] + c.chunk_table_off[idx];
   }
+  // parked numerators of the deferring kernel: stream-ordered scratch (the pool keeps it between launches)
+  prm.nscratch = nullptr;
+  if (sh.defer && sh.nscratch_words)
+    FF_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&prm.nscratch), sh.nscratch_words * sizeof(uint64_t), stream));
   cudaError_t e = ffgpu::launch_eval(prm, sh, stream);
+  if (prm.nscratch) {
+    const cudaError_t ef = cudaFreeAsync(prm.nscratch, stream);
+    if (e == cudaSuccess) e = ef;
+  }
   if (e != cudaSuccess) return cuda_fail(e, "launch_eval");
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
@@ -293,6 +302,12 @@ ffgpu_ctx* ffgpu_create(const int* device_ids, int n_devices) {
     d.id = id;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, id) == cudaSuccess) d.sm_count = prop.multiProcessorCount;
+    // stream-ordered scratch (launch(): parked numerators) stays in the device's pool between launches
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, id) == cudaSuccess) {
+      uint64_t keep = ~0ULL;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     ctx->devs.push_back(d);
   }
   for (auto& s : ctx->slots) s.dev.resize(ctx->devs.size());

@@ -447,6 +447,9 @@ struct FnEmitter {
   //   DEN_CONSUME   N * (temp slot 0): the function before this one has the same denominator
   //   3             only the divisor D of the top-level division (deferred divisions: it is parked by OP_DPARK)
   //   4             ACC * N: ACC holds 1/D on entry (after OP_DUNPARK)
+  //   5             the whole function with its top-level division deferred: [N] NPARK [D] DPARK (N and D share code)
+  bool defer_full = false;
+  uint32_t park_row = 0;
   FnEmitter(const Function& f_, uint32_t fn_, std::vector<Instr>& t, std::vector<ConstPatch>& p, bool cse,
             int temp_budget, int den_mode = 0)
       : f(f_), fn(fn_), tape(t), patches(p), enable_cse(cse) {
@@ -456,6 +459,7 @@ struct FnEmitter {
     // already spill deep get fewer temps; two are always allowed (co-evaluated sums need two).
     if (temp_budget > 0) max_temps = std::min(temp_budget, MAX_TEMPS);
     else max_temps = std::max(2, std::min(MAX_TEMPS, SLOT_BUDGET - (int)f.nodes[root].need));
+    defer_full = den_mode == 5;
     if (den_mode == 1 || den_mode == 2) {
       slot_busy[0] = true;         // temp slot 0 carries 1/D from function to function
       temps_used = 1;                // it comes out of the function's own budget: the slot count (occupancy) stays
@@ -616,7 +620,7 @@ struct FnEmitter {
     int32_t other;
     int32_t aux;
   };
-  enum { GEN, AFTER, APPLY_POP, APPLY_DIRECT, INVERT, POW_CONST, MUL_INVCONST, SQUARE, PRE, ACCUM, ADOPT, ADDPOP, MULPOP, EMIT };
+  enum { GEN, AFTER, APPLY_POP, APPLY_DIRECT, INVERT, POW_CONST, MUL_INVCONST, SQUARE, PRE, ACCUM, ADOPT, ADDPOP, MULPOP, EMIT, NPARK };
   std::vector<Item> work;
   // accumulate lists of co-evaluated sums: for ACCUM items
   struct Acc { int slot; bool minus; bool init; };
@@ -783,6 +787,12 @@ struct FnEmitter {
         case INVERT: put(mk(OP_INV)); continue;
         case SQUARE: put(mk(OP_SQR)); continue;
         case EMIT: put(raw[it.aux]); continue;
+        case NPARK:
+          // the numerator waits: on the spill stack in the plain kernel (one more slot), in a scratch row otherwise
+          put(mk(OP_NPARK));
+          ++depth;
+          max_depth = std::max(max_depth, depth);
+          continue;
         case APPLY_POP: apply(node(it.node), it.swap, true, -1); continue;
         case APPLY_DIRECT: apply(node(it.node), it.swap, false, it.other); continue;
         case POW_CONST: {
@@ -901,7 +911,17 @@ struct FnEmitter {
       const bool dl = direct(l), dr = direct(r);
       const unsigned a = f.nodes[l].need, b = f.nodes[r].need;
       const bool left_first = std::max(a, b + 1) <= std::max(b, a + 1);
-      if (n.kind == N_DIV) {
+      if (n.kind == N_DIV && defer_full && u == rep[this->root]) {
+        // the function's own division, deferred: numerator and divisor are both parked (the group's second half,
+        // emitted by Collection::finish, is DUNPARK NMUL STORE)
+        Instr dp = mk(OP_DPARK, F_LAST);
+        dp.arg = park_row;
+        raw.push_back(dp);
+        work.push_back(Item{EMIT, -1, false, false, -1, (int32_t)raw.size() - 1});
+        work.push_back(Item{GEN, r, false, false, -1, 0});
+        work.push_back(Item{NPARK, -1, false, false, -1, 0});
+        work.push_back(Item{GEN, l, push, false, -1, 0});
+      } else if (n.kind == N_DIV) {
         if (dl) {                      // invert the divisor, multiply by the simple numerator
           pin(l);
           work.push_back(Item{APPLY_DIRECT, u, false, true, l, 0});
@@ -940,16 +960,17 @@ struct FnEmitter {
 };
 }  // namespace
 
-void Collection::emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots, int den_mode) {
+void Collection::emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots, int den_mode, uint32_t park_row) {
   const size_t tape0 = tape.size(), patch0 = patches.size();
   for (int attempt = 0; attempt < 2; ++attempt) {
     const bool cse = enable_cse && !no_cse_fn_[fn];
     FnEmitter em(functions[fn], fn, tape, patches, cse, temp_budget, den_mode);
+    em.park_row = park_row;
     if (den_mode == 1) em.gen_produce();
     else if (den_mode == 2) em.gen_consume();
     else if (den_mode == 3) em.gen(em.root);
     else if (den_mode == 4) em.gen_times_acc();
-    else em.gen(functions[fn].root);
+    else em.gen(functions[fn].root);      // (mode 5: the root is the deferred division, handled in gen)
     if (em.failed && cse) {
       // the sharing pass lost track of a temp slot: emit this function as a plain tree instead
       tape.resize(tape0);
@@ -958,7 +979,7 @@ void Collection::emit_function(uint32_t fn, const std::vector<uint32_t>& out_slo
       ++cse_fallbacks;
       continue;
     }
-    for (uint32_t slot : out_slots) {
+    for (uint32_t slot : (den_mode == 5 ? std::vector<uint32_t>() : out_slots)) {
       Instr st = FnEmitter::mk(OP_STORE);
       st.arg = slot;
       em.put(st);
@@ -995,6 +1016,7 @@ bool Collection::check_tape(uint64_t p, const uint64_t* point, const std::vector
   bool temp_set[16] = {};
   std::vector<uint64_t> rows(n_out, 0);
   std::vector<char> row_state(n_out, 0);          // 0 empty, 1 holds a parked divisor, 2 stored
+  std::vector<uint64_t> numerators;               // OP_NPARK ... OP_NMUL
   bool ok = true;
   auto blame = [&](uint32_t slot) {
     if (slot < owner.size() && owner[slot] >= 0) bad[owner[slot]] = 1;
@@ -1079,6 +1101,15 @@ bool Collection::check_tape(uint64_t p, const uint64_t* point, const std::vector
       case OP_DEND:
         if (!stack.empty()) return false;
         continue;
+      case OP_NPARK:
+        if (!stack.empty()) return false;          // the plain kernel keeps it at the bottom of the spill stack
+        numerators.push_back(acc);
+        continue;
+      case OP_NMUL:
+        if (numerators.empty() || !stack.empty()) return false;
+        acc = ffhost::mul(acc, numerators.back(), p);
+        numerators.pop_back();
+        continue;
       case OP_TERM: {
         const uint8_t mode = (in.flags >> TM_SHIFT) & 7;
         uint64_t t = ffhost::pow_ff(point[in.arg & 0xffff] % p, in.arg >> 16, p);
@@ -1122,7 +1153,7 @@ bool Collection::check_tape(uint64_t p, const uint64_t* point, const std::vector
     }
     if (in.flags & F_NEGR) acc = ffhost::neg(acc, p);
   }
-  if (!ok || !stack.empty()) return false;
+  if (!ok || !stack.empty() || !numerators.empty()) return false;
   // every output has been stored (a row still holding a parked divisor means a group without its second half)
   for (size_t k = 0; k < n_out; ++k)
     if (row_state[k] != 2) {
@@ -1392,6 +1423,17 @@ bool Collection::finish(std::string& err) {
         u.deferred = !shares;
       }
     }
+    // A collection that is ONE function N / D (one unit, one member): numerator and divisor are both parked, they may
+    // share code, and the second half is DUNPARK NMUL STORE (tape.hpp).
+    defer_numerators = 0;
+    bool full = false;
+    if (enable_defer && units.size() == 1 && units[0].members.size() == 1) {
+      const uint32_t i = units[0].members[0];
+      const Function& f = functions[i];
+      const Node& rt = f.nodes[f.root];
+      full = !no_cse_fn_[i] && rt.kind == N_DIV && !rt.is_const && !f.nodes[rt.r].is_const;
+      if (full) units[0].deferred = true;
+    }
     constexpr size_t GROUP_MAX = 8;             // DPARKs per group: entries of the kernel's per-thread product stack
     size_t n_groups = 0, n_plain = 0;
     auto put = [&](uint8_t op, uint32_t arg, uint8_t flags) {
@@ -1406,6 +1448,21 @@ bool Collection::finish(std::string& err) {
       if (!units[a].deferred) {
         for (uint32_t i : units[a].members) emit_function(i, slots[i], den_mode_[i]);
         ++n_plain;
+        ++a;
+        continue;
+      }
+      if (full) {
+        const uint32_t head = units[0].members[0];
+        emit_function(head, slots[head], 5, slots[head][0]);      // [N] NPARK [D] DPARK
+        put(OP_DCHAIN, 0, 0);
+        put(OP_DUNPARK, slots[head][0], 0);
+        put(OP_NMUL, 0, 0);
+        for (uint32_t sl : slots[head]) put(OP_STORE, sl, 0);
+        put(OP_DEND, 0, 0);
+        n_deferred = 1;
+        defer_parks = 1;
+        defer_numerators = 1;
+        ++n_groups;
         ++a;
         continue;
       }
@@ -1487,7 +1544,7 @@ bool Collection::finish(std::string& err) {
       if (in.src == SRC_VAR || in.src == SRC_NEGVAR) ++executed.max_rpn_depth;   // reused: variable row reads
       switch (in.op) {
         case OP_ADD: case OP_SUB: case OP_NEG: case OP_ACCUM: ++executed.ma; break;
-        case OP_MUL: case OP_SQR: ++executed.mm; break;
+        case OP_MUL: case OP_SQR: case OP_NMUL: ++executed.mm; break;
         case OP_MULADD: ++executed.mm; ++executed.ma; break;
         case OP_INV: case OP_DUNPARK: ++executed.inv; break;
         case OP_POWU:
@@ -1596,6 +1653,8 @@ void Collection::peephole() {
         case OP_DCHAIN: fx = FX_DCHAIN; break;
         case OP_DUNPARK: fx = FX_DUNPARK; break;
         case OP_DEND: fx = FX_DEND; break;
+        case OP_NPARK: fx = FX_NPARK; break;
+        case OP_NMUL: fx = FX_NMUL; break;
         default: break;
       }
     }

@@ -112,6 +112,7 @@ struct Collection {
   uint32_t n_deferred = 0;                    // divisions served that way
   uint32_t defer_parks = 0;                   // most DPARKs in one group (0: the tape has no group)
   uint32_t defer_groups = 0;                  // groups in the tape
+  uint32_t defer_numerators = 0;              // numerators parked next to their divisors (OP_NPARK; 0 or 1)
   bool defer_single = false;                  // the whole tape is ONE group: a block pipelines over tiles of points
   std::vector<uint32_t> fn_start;             // tape offsets at which a chunk of the tape may start (a function that
                                               // depends on no earlier one, or a group), in order, then the end
@@ -159,7 +160,7 @@ struct Collection {
   bool build_tree(Function& f, std::string& err);
   static void compute_needs(Function& f);
   std::vector<Function> base_functions_;      // one per output, before any factor was applied
-  void emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots, int den_mode);
+  void emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots, int den_mode, uint32_t park_row = 0);
   // translation check: the whole tape run on the host at one point; bad[f] is set for every function whose stored
   // value differs from its expression tree's.  owner[slot] = function that stores output slot `slot`.
   bool check_tape(uint64_t p, const uint64_t* point, const std::vector<int32_t>& owner, std::vector<char>& bad) const;

@@ -206,10 +206,14 @@ __device__ __forceinline__ R pow_negint_lane(R b, R e_lazy, const Field& F) {
   return pow_lane(inv_fermat(b, F), (u64)(-(long long)e), F);
 }
 
+__device__ __forceinline__ void named_sync(u32 id, u32 n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_arrive(u32 id, u32 n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
 // ---- block-batched inversion -----------------------------------------------------------------
 // a[k] <- 1/a[k] (0 -> 0) for the K values of every thread of the block.  scratch: 64 u64 of
-// shared memory.  Must be reached by all threads of the block (the tape is block uniform).
-template <int K, int THREADS>
+// shared memory.  Must be reached by all THREADS threads that evaluate (the tape is block uniform); NAMED: these
+// are not the whole block (the deferring kernel has a helper warp), they meet on named barrier 15.
+template <int K, int THREADS, bool NAMED = false>
 __device__ __forceinline__ void block_inverse(R (&a)[K], const Field& F, u64* scratch) {
   constexpr int W = THREADS / 32;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -243,7 +247,7 @@ __device__ __forceinline__ void block_inverse(R (&a)[K], const Field& F, u64* sc
   R inv_upto, before;          // 1 / (warps 0..warp), product of warps 0..warp-1
   if (W > 1) {
     if (lane == 31) scratch[warp] = toU(s);
-    __syncthreads();
+    if (NAMED) named_sync(15, THREADS); else __syncthreads();
     if (warp == 0) {
       R S = lane < W ? mkR(scratch[lane]) : mkR(1);
 #pragma unroll
@@ -257,7 +261,7 @@ __device__ __forceinline__ void block_inverse(R (&a)[K], const Field& F, u64* sc
       scratch[lane] = toU(Sx);
       scratch[32 + lane] = toU(IS);
     }
-    __syncthreads();
+    if (NAMED) named_sync(15, THREADS); else __syncthreads();
     before = mkR(scratch[warp]);
     inv_upto = mkR(scratch[32 + warp]);
   } else {
@@ -342,6 +346,30 @@ struct Lane {
   }
   __device__ __forceinline__ bool in_range(int j) const { return own + j * STEP < left; }
   __device__ __forceinline__ bool probe_in_range(int k) const { return in_range(VEC ? k / 2 : k); }
+  // a tile-sized chunk of scratch memory (parked numerators): this thread's K values, raw (bounded lazy residues)
+  __device__ __forceinline__ void chunk_put(u64* chunk, const R (&a)[K]) const {
+    if (VEC) {
+#pragma unroll
+      for (int j = 0; j < NACC; j++)
+        *reinterpret_cast<ulonglong2*>(chunk + own + j * STEP) = make_ulonglong2(toU(a[2 * j]), toU(a[2 * j + 1]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < NACC; j++) chunk[own + j * STEP] = toU(a[j]);
+    }
+  }
+  __device__ __forceinline__ void chunk_get(const u64* chunk, R (&b)[K]) const {
+    if (VEC) {
+#pragma unroll
+      for (int j = 0; j < NACC; j++) {
+        const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(chunk + own + j * STEP);
+        b[2 * j] = mkR(w.x);
+        b[2 * j + 1] = mkR(w.y);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NACC; j++) b[j] = mkR(chunk[own + j * STEP]);
+    }
+  }
   // a row of out[] that this thread has written before (OP_DPARK): plain loads, not the read-only path
   __device__ __forceinline__ void load_row(u32 out_slot, u64 (&v)[K]) const {
     const u64* row = pbase + (u64)out_slot * out_stride;
@@ -436,9 +464,14 @@ struct DeferMem {
     return reinterpret_cast<volatile u32*>(base(prm) + qwords(prm) + kDeferPipe * THREADS + kDeferPipe * (2 * W) + W * kDeferPipe) +
            (threadIdx.x >> 5) * 16;
   }
+  // one word behind the evaluating warps' control blocks: set when the evaluating warps are done (helper: return)
+  static __device__ __forceinline__ volatile u32* quit(const EvalParams& prm) {
+    return reinterpret_cast<volatile u32*>(base(prm) + qwords(prm) + kDeferPipe * THREADS + kDeferPipe * (2 * W) + W * kDeferPipe) +
+           W * 16;
+  }
   static size_t words(u32 parks) {
     return (parks > 1 ? (size_t)kDeferPipe * parks * THREADS : 0) + (size_t)kDeferPipe * THREADS + (size_t)kDeferPipe * 2 * W +
-           (size_t)W * kDeferPipe + (size_t)W * 8;
+           (size_t)W * kDeferPipe + (size_t)W * 8 + 2;
   }
 };
 // words of CTRL: every lane of the warp writes the same value, so every lane reads what it wrote
@@ -453,8 +486,6 @@ enum DeferCtrl : u32 {
   DC_QSP,                       // DPARKs of the running first half / divisors still parked in the running second half
 };
 
-__device__ __forceinline__ void named_sync(u32 id, u32 n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void named_arrive(u32 id, u32 n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 template <int K, int THREADS, bool VEC>
 __device__ __forceinline__ void defer_park(const EvalParams& prm, const Lane<K, THREADS, VEC>& L, u32 row, const R (&acc)[K]) {
@@ -514,9 +545,10 @@ __device__ __forceinline__ void defer_unpark(const EvalParams& prm, const Lane<K
   }
   acc[0] = z[0] ? mkR(0) : I;
 }
-// first half of an item done: `run` = product of all divisors this thread parked.  Never blocks (except the duty warp).
+// first half of an item done (M[slot] = product of all divisors this thread parked): hand the warp's product to the
+// helper warp.  Never blocks.  BLOCK = threads of the whole block (the THREADS evaluating ones + the helper warp).
 template <int K, int THREADS, bool VEC>
-__device__ __forceinline__ void defer_chain_begin(const EvalParams& prm, const Lane<K, THREADS, VEC>& L, u32 slot, u32 duty) {
+__device__ __forceinline__ void defer_chain_begin(const EvalParams& prm, const Lane<K, THREADS, VEC>& L, u32 slot) {
   constexpr int W = THREADS / 32;
   const Field F = L.F;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -537,34 +569,44 @@ __device__ __forceinline__ void defer_chain_begin(const EvalParams& prm, const L
   u64* S = DeferMem<K, THREADS>::sg(prm, slot);
   if (lane == 31) S[warp] = toU(s);
   __threadfence_block();
-  if (warp != duty) {
-    named_arrive(1 + slot, THREADS);
-    return;
-  }
-  named_sync(1 + slot, THREADS);               // all warps' products are in S
-  R P = lane < (unsigned)W ? mkR(S[lane]) : mkR(1);
-#pragma unroll
-  for (int off = 1; off < W; off <<= 1) {
-    const R pm = fmul(P, shfl_up(P, off), F);
-    if (lane >= (unsigned)off) P = pm;
-  }
-  const R IP = inv_fermat(P, F);               // lane w: 1 / (warps 0..w)
-  R Px = shfl_up(P, 1);                        // warps 0..w-1
-  if (lane == 0) Px = mkR(1);
-  if (lane < (unsigned)W) S[W + lane] = toU(fmul(IP, Px, F));    // 1 / (warp w)
-  __threadfence_block();
-  named_arrive(1 + kDeferPipe + slot, THREADS);
+  named_arrive(1 + slot, THREADS + 32);
 }
 // second half of an item starts: M[slot] = 1 / (product of all divisors this thread parked in the item)
 template <int K, int THREADS, bool VEC>
-__device__ __forceinline__ void defer_chain_end(const EvalParams& prm, const Lane<K, THREADS, VEC>& L, u32 slot, u32 duty) {
+__device__ __forceinline__ void defer_chain_end(const EvalParams& prm, const Lane<K, THREADS, VEC>& L, u32 slot) {
   constexpr int W = THREADS / 32;
   const unsigned warp = threadIdx.x >> 5;
-  if (warp != duty) named_sync(1 + kDeferPipe + slot, THREADS);
-  else __syncwarp();
+  named_sync(1 + kDeferPipe + slot, THREADS + 32);       // the helper has published the item's inverses
   const u64* S = DeferMem<K, THREADS>::sg(prm, slot);
   u64* m = DeferMem<K, THREADS>::m(prm, slot);
   *m = toU(fmul(mkR(S[W + warp]), mkR(*m), L.F));
+}
+// The helper warp (the block's last): for every work item, in order, wait for the evaluating warps' products, invert
+// -- lane w runs the Fermat chain on the product of warps 0..w --, publish 1 / (product of warp w).  It has nothing
+// else to do, so no evaluating warp ever waits for a chain unless the helper falls kDeferPipe - 1 items behind.
+template <int K, int THREADS>
+__device__ __forceinline__ void defer_helper(const EvalParams& prm, const Field& F) {
+  constexpr int W = THREADS / 32;
+  const unsigned lane = threadIdx.x & 31;
+  volatile u32* quit = DeferMem<K, THREADS>::quit(prm);
+  for (u32 item = 0;; ++item) {
+    const u32 slot = item % kDeferPipe;
+    named_sync(1 + slot, THREADS + 32);          // all warps' products of the item are in S (or: nothing more will come)
+    if (*quit) return;
+    u64* S = DeferMem<K, THREADS>::sg(prm, slot);
+    R P = lane < (unsigned)W ? mkR(S[lane]) : mkR(1);
+#pragma unroll
+    for (int off = 1; off < W; off <<= 1) {
+      const R pm = fmul(P, shfl_up(P, off), F);
+      if (lane >= (unsigned)off) P = pm;
+    }
+    const R IP = inv_fermat(P, F);               // lane w: 1 / (warps 0..w)
+    R Px = shfl_up(P, 1);                        // warps 0..w-1
+    if (lane == 0) Px = mkR(1);
+    if (lane < (unsigned)W) S[W + lane] = toU(fmul(IP, Px, F));    // 1 / (warp w)
+    __threadfence_block();
+    named_arrive(1 + kDeferPipe + slot, THREADS + 32);
+  }
 }
 // Pipeline control at the two places where a second half can start (OP_DCHAIN with a full pipeline, end of the tape
 // with nothing left to start): takes the oldest waiting item, moves the thread to its tile, returns its first pc.
@@ -575,7 +617,7 @@ __device__ __forceinline__ u32 defer_start_second_half(const EvalParams& prm, La
   const u32 n_pend = ctrl[DC_PEND], oldest = ctrl[DC_ITEMS] - n_pend, slot = oldest % kDeferPipe;
   const u64 e = DM::fifo(prm)[slot];
   L.set_tile(prm, (((u64)ctrl[DC_TILE_HI] << 32) | ctrl[DC_TILE_LO]) + (u32)e);
-  defer_chain_end<K, THREADS, VEC>(prm, L, slot, oldest % (THREADS / 32));
+  defer_chain_end<K, THREADS, VEC>(prm, L, slot);
   ctrl[DC_CSLOT] = slot;
   ctrl[DC_QSP] = (u32)(e >> 60);
   ctrl[DC_RET_PC] = ret_pc;
@@ -589,7 +631,7 @@ __device__ __forceinline__ u32 defer_start_second_half(const EvalParams& prm, La
 // The uncommon instructions (lane exponents, negated variables, negative literal powers, ...), out of line:
 // the accumulators travel through local memory for these, which keeps them out of the register allocation
 // of the hot loop (inlined, they made ptxas copy all accumulators at every tape instruction).
-template <int K, int THREADS, bool VEC>
+template <int K, int THREADS, bool VEC, bool NAMED>
 __device__ FFGPU_GENERIC_INLINE u32 generic_op(const Lane<K, THREADS, VEC>& L, u32 opword, u32 arg, u64 imm, R (&acc)[K],
                                        u32 sp) {
   struct {
@@ -657,7 +699,7 @@ __device__ FFGPU_GENERIC_INLINE u32 generic_op(const Lane<K, THREADS, VEC>& L, u
       for (int k = 0; k < K; k++) acc[k] = fneg(acc[k], F);
       break;
     case OP_INV:
-      block_inverse<K, THREADS>(acc, F, L.scratch);
+      block_inverse<K, THREADS, NAMED>(acc, F, L.scratch);
       break;
     case OP_POWU: {
       // FFInt::pow(const FFInt&) with a lane-uniform exponent residue (FFInt.cpp:155-179)
@@ -668,7 +710,7 @@ __device__ FFGPU_GENERIC_INLINE u32 generic_op(const Lane<K, THREADS, VEC>& L, u
       } else if (e < (F.p >> 1)) {
         pow_uniform<K>(acc, e, F);
       } else {
-        block_inverse<K, THREADS>(acc, F, L.scratch);
+        block_inverse<K, THREADS, NAMED>(acc, F, L.scratch);
         pow_uniform<K>(acc, F.p - e - 1, F);
       }
       break;
@@ -682,7 +724,7 @@ __device__ FFGPU_GENERIC_INLINE u32 generic_op(const Lane<K, THREADS, VEC>& L, u
       } else if (e >= 0) {
         pow_uniform<K>(acc, (u64)e, F);
       } else {
-        block_inverse<K, THREADS>(acc, F, L.scratch);
+        block_inverse<K, THREADS, NAMED>(acc, F, L.scratch);
         pow_uniform<K>(acc, (u64)(-(long long)e), F);
       }
       break;
@@ -709,11 +751,19 @@ __device__ FFGPU_GENERIC_INLINE u32 generic_op(const Lane<K, THREADS, VEC>& L, u
       L.load_row(ins.arg, cv);
 #pragma unroll
       for (int k = 0; k < K; k++) acc[k] = L.probe_in_range(k) ? mkR(cv[k]) : mkR(1);   // lanes past the end never stored
-      block_inverse<K, THREADS>(acc, F, L.scratch);
+      block_inverse<K, THREADS, NAMED>(acc, F, L.scratch);
       break;
     }
     case OP_DCHAIN:
     case OP_DEND:
+      break;
+    case OP_NPARK:               // the numerator waits on the spill stack
+      L.slot_put(acc, sp++);
+      break;
+    case OP_NMUL:
+      L.slot_get(b, --sp);
+#pragma unroll
+      for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], b[k], F);
       break;
     default:
       asm volatile("trap;");     // an instruction without code: never compute on with garbage
@@ -737,9 +787,17 @@ constexpr int min_blocks() {
   return (K == 8 && !LEAN) ? 768 / THREADS : 1024 / THREADS;
 }
 
-template <int K, int THREADS, bool VEC, bool LEAN, bool DEFER>
-__global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_tape_kernel(const EvalParams prm) {
+// BLOCK threads per block.  The deferring kernel's last warp is the helper that inverts (defer_helper); the other
+// THREADS = BLOCK - 32 threads evaluate, and a tile is THREADS * K points.
+template <int K, int BLOCK, bool VEC, bool LEAN, bool DEFER>
+__global__ void __launch_bounds__(BLOCK, min_blocks<K, BLOCK, LEAN>()) eval_tape_kernel(const EvalParams prm) {
+  constexpr int THREADS = DEFER ? BLOCK - 32 : BLOCK;
   extern __shared__ __align__(16) u64 smem[];
+  if (DEFER && threadIdx.x >= THREADS) {
+    if (prm.n_tiles * ((u64)blockIdx.x + 1) / gridDim.x == prm.n_tiles * (u64)blockIdx.x / gridDim.x) return;   // no tile: nobody works
+    defer_helper<K, THREADS>(prm, Field{prm.p, prm.c, prm.d});
+    return;
+  }
   Lane<K, THREADS, VEC> L;
   L.init(prm, smem);
   const Field F = L.F;
@@ -768,6 +826,7 @@ __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_
     ctrl[DC_ITEMS] = 0;
     ctrl[DC_PEND] = 0;
     ctrl[DC_QSP] = 0;
+    *DeferMem<K, THREADS>::quit(prm) = 0;
   }
 
   R acc[K];
@@ -881,7 +940,7 @@ __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_
         pow_uniform<K>(acc, ins.imm, F);
         break;
       case FX_INV:
-        block_inverse<K, THREADS>(acc, F, L.scratch);
+        block_inverse<K, THREADS, DEFER>(acc, F, L.scratch);
         break;
       case FX_SAVE:
       case FX_ACCUM_INIT:
@@ -1052,7 +1111,7 @@ __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_
         for (int k = 0; k < K; k++) acc[k] = opaque(0);
         volatile u32* ctrl = DeferMem<K, THREADS>::ctrl(prm);
         const u32 item = ctrl[DC_ITEMS], n_pend = ctrl[DC_PEND] + 1;
-        defer_chain_begin<K, THREADS, VEC>(prm, L, item % kDeferPipe, item % (THREADS / 32));
+        defer_chain_begin<K, THREADS, VEC>(prm, L, item % kDeferPipe);
         DeferMem<K, THREADS>::fifo(prm)[item % kDeferPipe] =
             (u64)ctrl[DC_CUR_TILE] | ((u64)(pc + 1) << 32) | ((u64)ctrl[DC_QSP] << 60);
         ctrl[DC_ITEMS] = item + 1;
@@ -1069,6 +1128,21 @@ __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_
         if (!DEFER) goto generic;
         defer_unpark<K, THREADS, VEC>(prm, L, ins.arg, acc);
         break;
+      case FX_NPARK: {
+        if (!DEFER) goto generic;
+        // the numerator of the running first half: into the scratch chunk of its item
+        const u32 slot = DeferMem<K, THREADS>::ctrl(prm)[DC_ITEMS] % kDeferPipe;
+        L.chunk_put(reinterpret_cast<u64*>(prm.nscratch) + ((u64)blockIdx.x * kDeferPipe + slot) * (u64)(THREADS * K), acc);
+        break;
+      }
+      case FX_NMUL: {
+        if (!DEFER) goto generic;
+        const u32 slot = DeferMem<K, THREADS>::ctrl(prm)[DC_CSLOT];
+        L.chunk_get(reinterpret_cast<const u64*>(prm.nscratch) + ((u64)blockIdx.x * kDeferPipe + slot) * (u64)(THREADS * K), b);
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], b[k], F);
+        break;
+      }
       case FX_DEND: {
         if (!DEFER) goto generic;
         // second half done: back to the tile and the place the first halves have reached
@@ -1097,7 +1171,7 @@ __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_
         R t[K];
 #pragma unroll
         for (int k = 0; k < K; k++) t[k] = acc[k];
-        sp = generic_op<K, THREADS, VEC>(L2, cur.v.x, cur.v.y, ins.imm, t, sp);
+        sp = generic_op<K, THREADS, VEC, DEFER>(L2, cur.v.x, cur.v.y, ins.imm, t, sp);
 #pragma unroll
         for (int k = 0; k < K; k++) acc[k] = opaque(toU(t[k]));
         break;
@@ -1105,6 +1179,12 @@ __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_
     }
     cur = nxt;
     ++pc;
+  }
+  if (DEFER) {
+    // no more work items: release the helper warp, which waits for the products of the next one
+    *DeferMem<K, THREADS>::quit(prm) = 1;
+    __threadfence_block();
+    named_arrive(1 + DeferMem<K, THREADS>::ctrl(prm)[DC_ITEMS] % kDeferPipe, THREADS + 32);
   }
 }
 
@@ -1129,7 +1209,7 @@ cudaError_t launch_t(const EvalParams& prm, const LaunchShape& sh, cudaStream_t 
   const bool vec = K >= 2 && vec_ok(prm);
   constexpr bool HAS_LEAN = K == 8 && THREADS <= 256;      // the only shapes whose register budget differs
   // the deferring kernel exists for the shapes big batches run in (16-byte accesses only)
-  constexpr bool HAS_DEFER = (K == 8 || K == 4) && THREADS <= 256;
+  constexpr bool HAS_DEFER = (K == 8 || K == 4) && THREADS == 256;     // 7 evaluating warps + the helper warp
   if (sh.defer) {
     if (!HAS_DEFER || !vec) return cudaErrorInvalidValue;    // choose_shape / launch_eval never ask for this
     if (sh.lean && HAS_LEAN) return launch_k<K, THREADS, (K >= 2), HAS_LEAN, HAS_DEFER>(prm, sh, stream);
@@ -1210,22 +1290,28 @@ LaunchShape choose_shape(uint64_t n_points, uint32_t n_slots, int sm_count, int 
   // a tape that is ONE group gets as many blocks as are resident and every block a balanced range of tiles; a tape
   // of several groups keeps one tile per block and pipelines over its groups.
   s.defer = false;
+  s.nscratch_words = 0;
   if (df.parks) s.lean = false;        // the plain lean kernel has no code for the deferred-division instructions ...
-  if (df.parks && df.mode != 0 && (s.k == 8 || s.k == 4) && s.threads <= 256 && df.tape_instr < (1u << 28)) {
-    const size_t words = smem_words(s.k, s.threads, 0) +
-                         (s.threads == 256 ? DeferMem<8, 256>::words(df.parks) : DeferMem<8, 128>::words(df.parks));
-    const size_t bytes = words * sizeof(uint64_t);
-    const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>((s.k == 8 && !s.lean ? 768 : 1024) / s.threads,
+  if (df.parks && df.mode != 0 && (s.k == 8 || s.k == 4) && s.threads == 256 && df.tape_instr < (1u << 28)) {
+    // one warp of the block is the helper: 224 threads evaluate, a tile is 224 * k points
+    constexpr int WT = 256 - 32;
+    const size_t bytes = (smem_words(s.k, WT, 0) + DeferMem<8, WT>::words(df.parks)) * sizeof(uint64_t);
+    const bool lean = lean_ok && s.k == 8 && (227 * 1024) / (bytes + 1024) >= 4;
+    const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>((s.k == 8 && !lean ? 768 : 1024) / 256,
                                                                              (227 * 1024) / (bytes + 1024)));
     unsigned grid = (unsigned)sm_count * per_sm;
     if (df.max_blocks) grid = std::min(grid, df.max_blocks);
-    const uint64_t tiles_per_block = df.single ? std::max<uint64_t>(1, s.n_tiles / grid) : 1;
+    const uint64_t n_tiles = (n_points + (uint64_t)WT * s.k - 1) / ((uint64_t)WT * s.k);
+    const uint64_t tiles_per_block = std::max<uint64_t>(1, n_tiles / grid);
     const uint64_t items = tiles_per_block * std::max(1u, df.groups / s.chunks);
     if (bytes <= 200 * 1024 && (items >= 2 * (uint64_t)kDeferPipe || df.mode == 2)) {
       s.defer = true;
-      s.lean = lean_of(s.k, s.threads);    // ... the deferring lean kernel has
+      s.lean = lean;                   // ... the deferring lean kernel has
       s.smem = bytes;
-      if (df.single && s.n_tiles > grid) s.blocks = grid;
+      s.n_tiles = n_tiles;
+      // every block walks a balanced range of tiles
+      s.blocks = (unsigned)std::min<uint64_t>(n_tiles, grid);
+      s.nscratch_words = df.numerators ? (size_t)s.blocks * s.chunks * kDeferPipe * WT * s.k : 0;
     }
   }
   return s;
@@ -1240,6 +1326,7 @@ cudaError_t launch_eval(const EvalParams& prm_in, const LaunchShape& sh_in, cuda
     // odd batch or unaligned rows: the same tape on the plain kernel (DUNPARK = load + block inversion)
     sh.defer = false;
     sh.lean = false;
+    sh.n_tiles = (prm.n_points + (uint64_t)sh.threads * sh.k - 1) / ((uint64_t)sh.threads * sh.k);
     sh.blocks = (unsigned)sh.n_tiles;
   }
   prm.n_tiles = sh.n_tiles;

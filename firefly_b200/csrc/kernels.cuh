@@ -24,6 +24,7 @@ struct EvalParams {
   const uint32_t* chunk_bounds;  // device, n_chunks + 1 tape offsets at function boundaries (NULL: one chunk)
   uint64_t n_tiles;           // tiles of threads * k points that cover the batch (set by launch_eval)
   uint32_t defer_parks;       // deferring kernel: most OP_DPARKs of one group (rows of the per-thread product stack)
+  uint64_t* nscratch;         // deferring kernel: [block][kDeferPipe][tile] parked numerators (OP_NPARK), or NULL
 };
 
 // Deferring kernel: work items (a group of deferred divisions on one tile of points) in flight per block -- the second
@@ -38,6 +39,7 @@ struct DeferInfo {
   unsigned parks = 0;         // most OP_DPARKs in one group of the tape; 0: the tape has no deferred division
   unsigned groups = 0;        // groups of deferred divisions in the tape
   unsigned tape_instr = 0;    // tape length (the pipeline keeps tape offsets in 28 bits)
+  unsigned numerators = 0;    // numerators the tape parks per work item (Collection::defer_numerators)
   bool single = false;        // the whole tape is one group: a block pipelines over the tiles of its range
   int mode = 1;               // 0 never, 1 when a block has enough work items to pipeline, 2 whenever the shape allows it
   unsigned max_blocks = 0;    // upper bound of the grid of a multi-tile launch (0: the resident blocks)
@@ -53,6 +55,7 @@ struct LaunchShape {
   bool lean;           // kernel without the generic instructions, 64 registers at k = 8 (kernels.cu)
   uint64_t n_tiles;    // point tiles of the batch
   bool defer;          // the kernel that pipelines deferred divisions (inversions overlap the next items' work)
+  size_t nscratch_words;   // ... words of scratch it needs for parked numerators (EvalParams::nscratch)
 };
 
 LaunchShape choose_shape(uint64_t n_points, uint32_t n_slots, int sm_count, int force_k, int force_threads,

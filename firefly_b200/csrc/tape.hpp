@@ -78,7 +78,13 @@ enum Op : uint8_t {
   OP_DPARK,   // out[arg][point] = canonical(ACC); ACC joins the thread's running product   (F_LAST: last of its group)
   OP_DCHAIN,  // the thread's running product is inverted (deferring kernel; nothing to do otherwise)
   OP_DUNPARK, // ACC = 1 / out[arg][point], 1/0 := 0
-  OP_DEND,    // end of the group (loop tail of the deferring kernel's tile loop)
+  OP_DEND,    // end of the group
+  // A collection that is ONE function N / D parks its numerator too, so that the second half of a work item is only
+  // "unpark, multiply, store" and N and D can share code:  [N] NPARK [D] DPARK DCHAIN DUNPARK NMUL STORE DEND.
+  // The plain kernel keeps the numerator on the spill stack (NPARK = push, NMUL = multiply by the popped value), the
+  // deferring kernel in a scratch buffer of the launch (its second halves run several tiles later).
+  OP_NPARK,   // the numerator of the deferred division waits
+  OP_NMUL,    // ACC = ACC * (the waiting numerator)
   OP_COUNT
 };
 
@@ -94,7 +100,7 @@ enum Fast : uint8_t {
   FX_SAVE, FX_ACCUM_INIT, FX_ACCUM_ADD, FX_ACCUM_SUB,
   FX_LOAD_TMP, FX_PUSH_LOAD_TMP, FX_ADD_TMP, FX_MUL_TMP,
   FX_TERM, FX_ACCUM2, FX_ADDVARS, FX_MULVARS, FX_MULADD,
-  FX_DPARK, FX_DCHAIN, FX_DUNPARK, FX_DEND,
+  FX_DPARK, FX_DCHAIN, FX_DUNPARK, FX_DEND, FX_NPARK, FX_NMUL,
   FX_COUNT
 };
 

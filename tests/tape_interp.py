@@ -48,6 +48,7 @@ def run(tape: np.ndarray, point, p: int, n_out: int):
     stack = []
     temps = {}
     parked = {}
+    numerators = []
     for ins in tape:
         op, src, flags, arg, imm = int(ins["op"]), int(ins["src"]), int(ins["flags"]), int(ins["arg"]), int(ins["imm"])
         if op == OP["HALT"]:
@@ -63,6 +64,12 @@ def run(tape: np.ndarray, point, p: int, n_out: int):
                 acc = inv(parked.pop(arg), p)
             elif op in (OP["DCHAIN"], OP["DEND"]):
                 assert not stack
+            elif op == OP["NPARK"]:
+                assert not stack
+                numerators.append(acc)
+            elif op == OP["NMUL"]:
+                assert not stack
+                acc = acc * numerators.pop() % p
             else:
                 raise ValueError(f"bad opcode {op}")
             continue
@@ -152,5 +159,5 @@ def run(tape: np.ndarray, point, p: int, n_out: int):
         if flags & F_NEGR:
             acc = (-acc) % p
     assert not stack, "spill stack not empty at HALT"
-    assert not parked, "a parked divisor was never used"
+    assert not parked and not numerators, "a parked divisor or numerator was never used"
     return out
