@@ -166,6 +166,15 @@ int defer_mode() {
   }();
   return mode;
 }
+// FFGPU_STAGGER_NS: start offset between the blocks of the first wave that share an SM (plain kernel), nanoseconds
+uint32_t stagger_ns() {
+  static const uint32_t v = [] {
+    const char* e = std::getenv("FFGPU_STAGGER_NS");
+    return e && *e ? (uint32_t)std::atoi(e) : 0u;
+  }();
+  return v;
+}
+
 int launch(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, size_t n_points, uint64_t* d_out,
            size_t out_stride, cudaStream_t stream, uint64_t* d_park = nullptr) {
   const ffgpu::Collection& c = t->col;
@@ -191,6 +200,8 @@ int launch(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, siz
   df.mode = t->defer_mode >= 0 ? t->defer_mode : defer_mode();
   df.max_blocks = t->defer_max_blocks;
   prm.defer_parks = c.defer_parks;
+  prm.sm_count = (uint32_t)t->ctx->devs[g].sm_count;
+  prm.stagger_ns = stagger_ns();
   const ffgpu::LaunchShape sh = ffgpu::choose_shape(n_points, c.n_slots, t->ctx->devs[g].sm_count, t->force_k,
                                                     t->force_threads, c.max_chunks, !t->needs_generic, df);
   prm.chunk_bounds = nullptr;

@@ -441,31 +441,39 @@ struct Lane {
 template <int K, int THREADS>
 struct DeferMem {
   static constexpr u32 W = THREADS / 32;
-  static __device__ __forceinline__ u64* base(const EvalParams& prm) {
+  template <class PRM>
+  static __device__ __forceinline__ u64* base(const PRM& prm) {
     extern __shared__ __align__(16) u64 dyn_smem[];
     return dyn_smem + 64 + (size_t)prm.n_slots * (K * THREADS);
   }
-  static __device__ __forceinline__ u32 qwords(const EvalParams& prm) {
+  template <class PRM>
+  static __device__ __forceinline__ u32 qwords(const PRM& prm) {
     return prm.defer_parks > 1 ? (u32)kDeferPipe * prm.defer_parks * THREADS : 0u;
   }
-  static __device__ __forceinline__ u64* q(const EvalParams& prm, u32 slot, u32 j) {
+  template <class PRM>
+  static __device__ __forceinline__ u64* q(const PRM& prm, u32 slot, u32 j) {
     return base(prm) + (slot * prm.defer_parks + j) * THREADS + threadIdx.x;
   }
-  static __device__ __forceinline__ u64* m(const EvalParams& prm, u32 slot) {
+  template <class PRM>
+  static __device__ __forceinline__ u64* m(const PRM& prm, u32 slot) {
     return base(prm) + qwords(prm) + slot * THREADS + threadIdx.x;
   }
-  static __device__ __forceinline__ u64* sg(const EvalParams& prm, u32 slot) {
+  template <class PRM>
+  static __device__ __forceinline__ u64* sg(const PRM& prm, u32 slot) {
     return base(prm) + qwords(prm) + kDeferPipe * THREADS + slot * (2 * W);
   }
-  static __device__ __forceinline__ u64* fifo(const EvalParams& prm) {
+  template <class PRM>
+  static __device__ __forceinline__ u64* fifo(const PRM& prm) {
     return base(prm) + qwords(prm) + kDeferPipe * THREADS + kDeferPipe * (2 * W) + (threadIdx.x >> 5) * kDeferPipe;
   }
-  static __device__ __forceinline__ volatile u32* ctrl(const EvalParams& prm) {
+  template <class PRM>
+  static __device__ __forceinline__ volatile u32* ctrl(const PRM& prm) {
     return reinterpret_cast<volatile u32*>(base(prm) + qwords(prm) + kDeferPipe * THREADS + kDeferPipe * (2 * W) + W * kDeferPipe) +
            (threadIdx.x >> 5) * 16;
   }
   // one word behind the evaluating warps' control blocks: set when the evaluating warps are done (helper: return)
-  static __device__ __forceinline__ volatile u32* quit(const EvalParams& prm) {
+  template <class PRM>
+  static __device__ __forceinline__ volatile u32* quit(const PRM& prm) {
     return reinterpret_cast<volatile u32*>(base(prm) + qwords(prm) + kDeferPipe * THREADS + kDeferPipe * (2 * W) + W * kDeferPipe) +
            W * 16;
   }
@@ -473,6 +481,13 @@ struct DeferMem {
     return (parks > 1 ? (size_t)kDeferPipe * parks * THREADS : 0) + (size_t)kDeferPipe * THREADS + (size_t)kDeferPipe * 2 * W +
            (size_t)W * kDeferPipe + (size_t)W * 8 + 2;
   }
+};
+// what the out-of-line deferred-division code needs of the launch parameters (passed by value: taking the address of
+// the kernel's parameter block would copy all of it to local memory)
+struct DeferPrm {
+  u32 n_slots, defer_parks;
+  u64 p;
+  u32 c, d;
 };
 // words of CTRL: every lane of the warp writes the same value, so every lane reads what it wrote
 enum DeferCtrl : u32 {
@@ -484,11 +499,12 @@ enum DeferCtrl : u32 {
   DC_RET_PC,                    // where the tape goes on after the second half that is running
   DC_CSLOT,                     // slot of the item whose second half is running
   DC_QSP,                       // DPARKs of the running first half / divisors still parked in the running second half
+  DC_RUN_TILE,                  // tile (relative) the interpreter is to be on after a jump of the pipeline
 };
 
 
 template <int K, int THREADS, bool VEC>
-__device__ __forceinline__ void defer_park(const EvalParams& prm, const Lane<K, THREADS, VEC>& L, u32 row, const R (&acc)[K]) {
+__device__ __forceinline__ void defer_park(const DeferPrm& prm, const Lane<K, THREADS, VEC>& L, u32 row, const R (&acc)[K]) {
   typedef DeferMem<K, THREADS> DM;
   const Field F = L.F;
   volatile u32* ctrl = DM::ctrl(prm);
@@ -513,7 +529,7 @@ __device__ __forceinline__ void defer_park(const EvalParams& prm, const Lane<K, 
   ctrl[DC_QSP] = qsp + 1;
 }
 template <int K, int THREADS, bool VEC>
-__device__ __forceinline__ void defer_unpark(const EvalParams& prm, const Lane<K, THREADS, VEC>& L, u32 row, R (&acc)[K]) {
+__device__ __forceinline__ void defer_unpark(const DeferPrm& prm, const Lane<K, THREADS, VEC>& L, u32 row, R (&acc)[K]) {
   typedef DeferMem<K, THREADS> DM;
   const Field F = L.F;
   volatile u32* ctrl = DM::ctrl(prm);
@@ -548,7 +564,7 @@ __device__ __forceinline__ void defer_unpark(const EvalParams& prm, const Lane<K
 // first half of an item done (M[slot] = product of all divisors this thread parked): hand the warp's product to the
 // helper warp.  Never blocks.  BLOCK = threads of the whole block (the THREADS evaluating ones + the helper warp).
 template <int K, int THREADS, bool VEC>
-__device__ __forceinline__ void defer_chain_begin(const EvalParams& prm, const Lane<K, THREADS, VEC>& L, u32 slot) {
+__device__ __forceinline__ void defer_chain_begin(const DeferPrm& prm, const Lane<K, THREADS, VEC>& L, u32 slot) {
   constexpr int W = THREADS / 32;
   const Field F = L.F;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -570,16 +586,6 @@ __device__ __forceinline__ void defer_chain_begin(const EvalParams& prm, const L
   if (lane == 31) S[warp] = toU(s);
   __threadfence_block();
   named_arrive(1 + slot, THREADS + 32);
-}
-// second half of an item starts: M[slot] = 1 / (product of all divisors this thread parked in the item)
-template <int K, int THREADS, bool VEC>
-__device__ __forceinline__ void defer_chain_end(const EvalParams& prm, const Lane<K, THREADS, VEC>& L, u32 slot) {
-  constexpr int W = THREADS / 32;
-  const unsigned warp = threadIdx.x >> 5;
-  named_sync(1 + kDeferPipe + slot, THREADS + 32);       // the helper has published the item's inverses
-  const u64* S = DeferMem<K, THREADS>::sg(prm, slot);
-  u64* m = DeferMem<K, THREADS>::m(prm, slot);
-  *m = toU(fmul(mkR(S[W + warp]), mkR(*m), L.F));
 }
 // The helper warp (the block's last): for every work item, in order, wait for the evaluating warps' products, invert
 // -- lane w runs the Fermat chain on the product of warps 0..w --, publish 1 / (product of warp w).  It has nothing
@@ -608,21 +614,68 @@ __device__ __forceinline__ void defer_helper(const EvalParams& prm, const Field&
     named_arrive(1 + kDeferPipe + slot, THREADS + 32);
   }
 }
-// Pipeline control at the two places where a second half can start (OP_DCHAIN with a full pipeline, end of the tape
-// with nothing left to start): takes the oldest waiting item, moves the thread to its tile, returns its first pc.
-template <int K, int THREADS, bool VEC>
-__device__ __forceinline__ u32 defer_start_second_half(const EvalParams& prm, Lane<K, THREADS, VEC>& L, u32 ret_pc) {
+// Pipeline control at the two places where a second half can start (a group's last OP_DPARK with a full pipeline, end
+// of the tape with nothing left to start): takes the oldest waiting item, notes its tile in CTRL (the interpreter moves
+// there), returns its first pc.
+template <int K, int THREADS>
+__device__ __forceinline__ u32 defer_start_second_half(const DeferPrm& prm, u32 ret_pc) {
   typedef DeferMem<K, THREADS> DM;
   volatile u32* ctrl = DM::ctrl(prm);
   const u32 n_pend = ctrl[DC_PEND], oldest = ctrl[DC_ITEMS] - n_pend, slot = oldest % kDeferPipe;
   const u64 e = DM::fifo(prm)[slot];
-  L.set_tile(prm, (((u64)ctrl[DC_TILE_HI] << 32) | ctrl[DC_TILE_LO]) + (u32)e);
-  defer_chain_end<K, THREADS, VEC>(prm, L, slot);
+  // M[slot] = 1 / (product of all divisors this thread parked in the item), once the helper has published the
+  // item's inverses
+  named_sync(1 + kDeferPipe + slot, THREADS + 32);
+  const u64* S = DM::sg(prm, slot);
+  u64* m = DM::m(prm, slot);
+  const Field F{prm.p, prm.c, prm.d};
+  *m = toU(fmul(mkR(S[THREADS / 32 + (threadIdx.x >> 5)]), mkR(*m), F));
+  ctrl[DC_RUN_TILE] = (u32)e;
   ctrl[DC_CSLOT] = slot;
   ctrl[DC_QSP] = (u32)(e >> 60);
   ctrl[DC_RET_PC] = ret_pc;
   ctrl[DC_PEND] = n_pend - 1;
   return (u32)(e >> 32) & 0x0fffffffu;
+}
+// The deferred-division instructions with real work in them, OUT OF LINE on copies of the interpreter's state: inlined,
+// their register needs (scans, prefix products) made ptxas spill the instruction words at every dispatch of the tape.
+//   DS_PARK     OP_DPARK; with F_LAST also the OP_DCHAIN behind it (next_arg = its skip target): returns the pc to go
+//               on at (the oldest item's second half if the pipeline is full), CTRL[DC_RUN_TILE] = the tile to be on
+//   DS_UNPARK   OP_DUNPARK: t = the inverses
+//   DS_DRAIN    end of the tape, nothing left to start: like the tail of DS_PARK
+enum DeferSlow : u32 { DS_PARK = 0, DS_UNPARK, DS_DRAIN };
+constexpr u32 DS_NEXT = 0xffffffffu;
+template <int K, int THREADS, bool VEC>
+__device__ __noinline__ u32 defer_slow(const DeferPrm prm, const Lane<K, THREADS, VEC> L, u32 what, u32 flags, u32 arg,
+                                       u32 next_arg, u32 pc, R* tp) {
+  R(&t)[K] = *reinterpret_cast<R(*)[K]>(tp);
+  typedef DeferMem<K, THREADS> DM;
+  volatile u32* ctrl = DM::ctrl(prm);
+  if (what == DS_UNPARK) {
+    defer_unpark<K, THREADS, VEC>(prm, L, arg, t);
+    return DS_NEXT;
+  }
+  if (what == DS_DRAIN) return defer_start_second_half<K, THREADS>(prm, next_arg);
+  defer_park<K, THREADS, VEC>(prm, L, arg, t);
+  if (!(flags & F_LAST)) return DS_NEXT;
+  // first half of an item done (the OP_DCHAIN at pc + 1): start its inversion, do not wait for it
+#ifndef FFGPU_NO_ITEM_SYNC
+  // The evaluating warps meet here once per item.  Nothing they exchange needs it -- but warps that drift apart are
+  // spread over all of the interpreter's code at once, and its hot part then no longer fits the instruction cache
+  // (measured: no-instruction stalls 3.0 per issue without this barrier against 0.6 in the plain kernel).
+  named_sync(14, THREADS);
+#endif
+  const u32 item = ctrl[DC_ITEMS], n_pend = ctrl[DC_PEND] + 1;
+  defer_chain_begin<K, THREADS, VEC>(prm, L, item % kDeferPipe);
+  DM::fifo(prm)[item % kDeferPipe] = (u64)ctrl[DC_CUR_TILE] | ((u64)(pc + 2) << 32) | ((u64)ctrl[DC_QSP] << 60);
+  ctrl[DC_ITEMS] = item + 1;
+  ctrl[DC_PEND] = n_pend;
+  ctrl[DC_QSP] = 0;
+  ctrl[DC_RUN_TILE] = ctrl[DC_CUR_TILE];
+  // a full pipeline: the oldest item's inversion has had kDeferPipe - 1 first halves of time, its second half runs
+  // now; then the tape goes on behind this group (next_arg = the instruction after its DEND)
+  if (n_pend == (u32)kDeferPipe) return defer_start_second_half<K, THREADS>(prm, next_arg);
+  return next_arg;
 }
 
 #ifndef FFGPU_GENERIC_INLINE
@@ -801,6 +854,14 @@ __global__ void __launch_bounds__(BLOCK, min_blocks<K, BLOCK, LEAN>()) eval_tape
   Lane<K, THREADS, VEC> L;
   L.init(prm, smem);
   const Field F = L.F;
+  // Blocks that share an SM and start together stay in step for the whole launch: they reach their block-wide
+  // inversion at the same moment, and while their chains run the SM has nothing else to issue.  The blocks of the
+  // FIRST wave therefore start a fraction of a tile's time apart (by their slot on the SM); every later block starts
+  // when an earlier one ends and inherits the offset.
+  if (!DEFER && prm.stagger_ns) {
+    const u32 slot = (blockIdx.x + blockIdx.y * gridDim.x) / prm.sm_count;
+    if (slot && slot < 8) __nanosleep(slot * prm.stagger_ns);
+  }
 
   // blockIdx.y selects a chunk of the tape (a run of whole functions): many-function collections
   // evaluated at few points still fill the chip
@@ -850,7 +911,9 @@ __global__ void __launch_bounds__(BLOCK, min_blocks<K, BLOCK, LEAN>()) eval_tape
         pc = pc_begin;
       } else if (ctrl[DC_PEND]) {
         // nothing left to start: the second halves still waiting, oldest first
-        pc = defer_start_second_half<K, THREADS, VEC>(prm, L, pc_end);
+        R t[K];
+        pc = defer_slow<K, THREADS, VEC>(DeferPrm{prm.n_slots, prm.defer_parks, prm.p, prm.c, prm.d}, L, DS_DRAIN, 0, 0, pc_end, pc, t);
+        L.set_tile(prm, (((u64)ctrl[DC_TILE_HI] << 32) | ctrl[DC_TILE_LO]) + ctrl[DC_RUN_TILE]);
       } else {
         break;
       }
@@ -1099,35 +1162,35 @@ __global__ void __launch_bounds__(BLOCK, min_blocks<K, BLOCK, LEAN>()) eval_tape
 
       // ---- deferred top-level divisions (tape.hpp) ----------------------------------------------------------
       // (the kernel that does not defer takes all four through the generic path below)
-      case FX_DPARK:
+      case FX_DPARK: {
         if (!DEFER) goto generic;
-        defer_park<K, THREADS, VEC>(prm, L, ins.arg, acc);
-        break;
-      case FX_DCHAIN: {
-        if (!DEFER) goto generic;
-        // first half of an item done: start its inversion, do not wait for it.  ACC is dead here (its value is
-        // parked): say so, the scans need the registers.
+        // (with F_LAST this is also the DCHAIN behind it: nxt.i.arg = its skip target)
+        R t[K];
 #pragma unroll
-        for (int k = 0; k < K; k++) acc[k] = opaque(0);
+        for (int k = 0; k < K; k++) t[k] = acc[k];
+        const u32 to = defer_slow<K, THREADS, VEC>(DeferPrm{prm.n_slots, prm.defer_parks, prm.p, prm.c, prm.d}, L, DS_PARK, ins.flags,
+                                                    ins.arg, nxt.i.arg, pc, t);
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[k] = opaque(0);      // ACC is dead: its value is parked
+        if (to == DS_NEXT) break;
         volatile u32* ctrl = DeferMem<K, THREADS>::ctrl(prm);
-        const u32 item = ctrl[DC_ITEMS], n_pend = ctrl[DC_PEND] + 1;
-        defer_chain_begin<K, THREADS, VEC>(prm, L, item % kDeferPipe);
-        DeferMem<K, THREADS>::fifo(prm)[item % kDeferPipe] =
-            (u64)ctrl[DC_CUR_TILE] | ((u64)(pc + 1) << 32) | ((u64)ctrl[DC_QSP] << 60);
-        ctrl[DC_ITEMS] = item + 1;
-        ctrl[DC_PEND] = n_pend;
-        ctrl[DC_QSP] = 0;
-        // a full pipeline: the oldest item's inversion has had kDeferPipe - 1 first halves of time, its second half
-        // runs now; then the tape goes on behind this group (ins.arg = the instruction after its DEND)
-        if (n_pend == (u32)kDeferPipe) pc = defer_start_second_half<K, THREADS, VEC>(prm, L, ins.arg);
-        else pc = ins.arg;
+        L.set_tile(prm, (((u64)ctrl[DC_TILE_HI] << 32) | ctrl[DC_TILE_LO]) + ctrl[DC_RUN_TILE]);
+        pc = to;
         cur.v = __ldg(tape + pc);
         continue;
       }
-      case FX_DUNPARK:
+      case FX_DCHAIN:
         if (!DEFER) goto generic;
-        defer_unpark<K, THREADS, VEC>(prm, L, ins.arg, acc);
+        asm volatile("trap;");         // never dispatched: the group's last DPARK does its work and jumps
         break;
+      case FX_DUNPARK: {
+        if (!DEFER) goto generic;
+        R t[K];
+        defer_slow<K, THREADS, VEC>(DeferPrm{prm.n_slots, prm.defer_parks, prm.p, prm.c, prm.d}, L, DS_UNPARK, 0, ins.arg, 0, pc, t);
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[k] = opaque(toU(t[k]));
+        break;
+      }
       case FX_NPARK: {
         if (!DEFER) goto generic;
         // the numerator of the running first half: into the scratch chunk of its item

@@ -23,6 +23,8 @@ struct EvalParams {
   uint32_t n_instr;           // tape length without the terminators
   const uint32_t* chunk_bounds;  // device, n_chunks + 1 tape offsets at function boundaries (NULL: one chunk)
   uint64_t n_tiles;           // tiles of threads * k points that cover the batch (set by launch_eval)
+  uint32_t stagger_ns;        // plain kernel: the blocks of the first wave start (slot on the SM) * stagger_ns late, see kernels.cu
+  uint32_t sm_count;
   uint32_t defer_parks;       // deferring kernel: most OP_DPARKs of one group (rows of the per-thread product stack)
   uint64_t* nscratch;         // deferring kernel: [block][kDeferPipe][tile] parked numerators (OP_NPARK), or NULL
 };
