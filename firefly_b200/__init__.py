@@ -34,7 +34,7 @@ INSTR_DTYPE = np.dtype(
 )
 # tape.hpp
 OPS = ["HALT", "LOAD", "ADD", "SUB", "MUL", "SQR", "NEG", "INV", "POWU", "NPOWU", "POWL", "NPOWL", "STORE", "MULADD",
-       "SAVE", "ACCUM", "TERM", "ACCUM2", "ADDVARS", "MULVARS", "DPARK", "DCHAIN", "DUNPARK", "DEND", "NPARK", "NMUL"]
+       "SAVE", "ACCUM", "TERM", "ACCUM2", "ADDVARS", "MULVARS"]
 SRCS = ["NONE", "POP", "VAR", "NEGVAR", "CONST", "TMP"]
 F_PUSH, F_SWAP, F_NEGR, F_INIT, F_SWAP2, F_INIT2, F_CMUL = 1, 2, 4, 8, 16, 32, 128
 TM_LOAD, TM_ADD, TM_SUB, TM_RSUB, TM_MUL = 0, 1, 2, 3, 4
@@ -42,7 +42,6 @@ CHECK_IS_EQUAL = 1
 NO_CSE = 2
 NO_FUSE = 4
 NO_CROSS = 16
-NO_DEFER = 32
 ADD_PLAIN, ADD_VALIDATE, ADD_NO_DUPLICATES = 1, 2, 4
 
 
@@ -79,7 +78,6 @@ def _load() -> C.CDLL:
         "ffgpu_cse_fallbacks": (C.c_size_t, [C.c_void_p]),
         "ffgpu_n_structural_duplicates": (C.c_size_t, [C.c_void_p]),
         "ffgpu_n_shared_denominators": (C.c_size_t, [C.c_void_p]),
-        "ffgpu_n_deferred_divisions": (C.c_size_t, [C.c_void_p]),
         "ffgpu_rpn": (C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
         "ffgpu_get_tape": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t]),
         "ffgpu_work": (None, [C.c_void_p, u64p]),
@@ -112,7 +110,6 @@ def _load() -> C.CDLL:
         "ffgpu_host_alloc": (C.c_void_p, [C.c_size_t]),
         "ffgpu_host_free": (None, [C.c_void_p]),
         "ffgpu_set_launch": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
-        "ffgpu_set_defer": (C.c_int, [C.c_void_p, C.c_int, C.c_uint]),
         "ffgpu_set_chunk": (C.c_int, [C.c_void_p, C.c_size_t]),
         "ffgpu_launch_count": (C.c_uint64, []),
         "ffgpu_fill_points": (
@@ -137,12 +134,12 @@ lib = _load()
 EXPORTS = [
     "ffgpu_create", "ffgpu_destroy", "ffgpu_n_devices", "ffgpu_last_error", "ffgpu_compile", "ffgpu_compile_text",
     "ffgpu_compile_file", "ffgpu_tape_clone", "ffgpu_tape_destroy", "ffgpu_n_vars", "ffgpu_n_functions", "ffgpu_n_out", "ffgpu_n_instr",
-    "ffgpu_stack_depth", "ffgpu_n_temps", "ffgpu_n_slots", "ffgpu_cse_fallbacks", "ffgpu_n_structural_duplicates", "ffgpu_n_shared_denominators", "ffgpu_n_deferred_divisions", "ffgpu_rpn", "ffgpu_get_tape", "ffgpu_work", "ffgpu_tape_work", "ffgpu_set_factors", "ffgpu_set_prime", "ffgpu_get_prime",
+    "ffgpu_stack_depth", "ffgpu_n_temps", "ffgpu_n_slots", "ffgpu_cse_fallbacks", "ffgpu_n_structural_duplicates", "ffgpu_n_shared_denominators", "ffgpu_rpn", "ffgpu_get_tape", "ffgpu_work", "ffgpu_tape_work", "ffgpu_set_factors", "ffgpu_set_prime", "ffgpu_get_prime",
     "ffgpu_add_function", "ffgpu_add_function_rpn", "ffgpu_trim", "ffgpu_is_stale",
     "ffgpu_n_primes", "ffgpu_prime", "ffgpu_eval", "ffgpu_eval_line", "ffgpu_eval_wire", "ffgpu_eval_device", "ffgpu_host_alloc", "ffgpu_host_free",
     "ffgpu_queue_create", "ffgpu_queue_destroy", "ffgpu_queue_push", "ffgpu_queue_push_many", "ffgpu_queue_push_line",
     "ffgpu_queue_pop", "ffgpu_queue_pending", "ffgpu_queue_stats", "ffgpu_queue_error",
-    "ffgpu_set_launch", "ffgpu_set_defer", "ffgpu_set_chunk", "ffgpu_launch_count", "ffgpu_fill_points", "ffgpu_checksum",
+    "ffgpu_set_launch", "ffgpu_set_chunk", "ffgpu_launch_count", "ffgpu_fill_points", "ffgpu_checksum",
     "ffgpu_field_ops",
 ]
 
@@ -202,10 +199,10 @@ class GpuParser:
 
     def __init__(self, ctx: Optional[Context], functions=None, vars: Sequence[str] = (), check_is_equal: bool = False,
                  *, file: Optional[str] = None, text: Optional[str] = None, cse: bool = True,
-                 temps: int = 0, fuse: bool = True, cross: bool = True, defer: bool = True):
+                 temps: int = 0, fuse: bool = True, cross: bool = True):
         self.ctx = ctx
         ch = ctx.h if ctx is not None else None
-        flags = (CHECK_IS_EQUAL if check_is_equal else 0) | (0 if cse else NO_CSE) | (0 if fuse else NO_FUSE) | (0 if cross else NO_CROSS) | (0 if defer else NO_DEFER) | ((temps & 15) << 8)
+        flags = (CHECK_IS_EQUAL if check_is_equal else 0) | (0 if cse else NO_CSE) | (0 if fuse else NO_FUSE) | (0 if cross else NO_CROSS) | ((temps & 15) << 8)
         v = _strs(vars)
         if file is not None:
             self.h = lib.ffgpu_compile_file(ch, file.encode(), v, len(vars), flags)
@@ -273,10 +270,6 @@ class GpuParser:
     @property
     def n_shared_denominators(self) -> int:
         return lib.ffgpu_n_shared_denominators(self.h)
-
-    @property
-    def n_deferred_divisions(self) -> int:
-        return lib.ffgpu_n_deferred_divisions(self.h)
 
     @property
     def n_slots(self) -> int:
@@ -414,11 +407,6 @@ class GpuParser:
 
     def set_launch(self, probes_per_thread: int = 0, threads_per_block: int = 0):
         if lib.ffgpu_set_launch(self.h, probes_per_thread, threads_per_block):
-            raise FFGpuError(last_error())
-
-    def set_defer(self, mode: int = 1, max_blocks: int = 0):
-        """which kernel serves the deferred divisions (include/ffgpu.h, ffgpu_set_defer)"""
-        if lib.ffgpu_set_defer(self.h, mode, max_blocks):
             raise FFGpuError(last_error())
 
     def set_chunk(self, points: int = 0):

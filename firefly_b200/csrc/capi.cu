@@ -120,8 +120,6 @@ struct ffgpu_tape {
   std::vector<ffgpu::Instr*> d_tape;   // per device
   std::vector<uint32_t*> d_chunks;     // per device: Collection::chunk_table
   int force_k = 0, force_threads = 0;
-  int defer_mode = -1;                 // -1: FFGPU_DEFER / default
-  unsigned defer_max_blocks = 0;
   size_t chunk = 0;
   bool needs_generic = true;           // the resolved tape has instructions without a fast dispatch code
 };
@@ -157,32 +155,13 @@ std::vector<std::string> to_vec(const char* const* s, size_t n) {
   return v;
 }
 
-// FFGPU_DEFER = 0 | 1 | 2: never / when it pays (default) / whenever possible run the kernel that pipelines the
-// deferred divisions (kernels.cu)
-int defer_mode() {
-  static const int mode = [] {
-    const char* e = std::getenv("FFGPU_DEFER");
-    return e && *e ? std::atoi(e) : 1;
-  }();
-  return mode;
-}
-// FFGPU_STAGGER_NS: start offset between the blocks of the first wave that share an SM (plain kernel), nanoseconds
-uint32_t stagger_ns() {
-  static const uint32_t v = [] {
-    const char* e = std::getenv("FFGPU_STAGGER_NS");
-    return e && *e ? (uint32_t)std::atoi(e) : 0u;
-  }();
-  return v;
-}
-
 int launch(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, size_t n_points, uint64_t* d_out,
-           size_t out_stride, cudaStream_t stream, uint64_t* d_park = nullptr) {
+           size_t out_stride, cudaStream_t stream) {
   const ffgpu::Collection& c = t->col;
   ffgpu::EvalParams prm;
   prm.tape = t->d_tape[g];
   prm.values = d_values;
   prm.out = d_out;
-  prm.park = d_park;
   prm.n_points = n_points;
   prm.in_stride = in_stride;
   prm.out_stride = out_stride;
@@ -191,34 +170,15 @@ int launch(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, siz
   prm.d = 2 * prm.c;
   prm.n_slots = c.n_slots;
   prm.n_instr = (uint32_t)(c.tape.size() - 2);
-  ffgpu::DeferInfo df;
-  df.parks = c.defer_parks;
-  df.groups = c.defer_groups;
-  df.tape_instr = (unsigned)c.tape.size();
-  df.numerators = c.defer_numerators;
-  df.single = c.defer_single;
-  df.mode = t->defer_mode >= 0 ? t->defer_mode : defer_mode();
-  df.max_blocks = t->defer_max_blocks;
-  prm.defer_parks = c.defer_parks;
-  prm.sm_count = (uint32_t)t->ctx->devs[g].sm_count;
-  prm.stagger_ns = stagger_ns();
   const ffgpu::LaunchShape sh = ffgpu::choose_shape(n_points, c.n_slots, t->ctx->devs[g].sm_count, t->force_k,
-                                                    t->force_threads, c.max_chunks, !t->needs_generic, df);
+                                                    t->force_threads, c.max_chunks, !t->needs_generic);
   prm.chunk_bounds = nullptr;
   if (sh.chunks > 1) {
     unsigned idx = 0;
     while ((1u << idx) < sh.chunks) ++idx;
     prm.chunk_bounds = t->d_chunks[g] + c.chunk_table_off[idx];
   }
-  // parked numerators of the deferring kernel: stream-ordered scratch (the pool keeps it between launches)
-  prm.nscratch = nullptr;
-  if (sh.defer && sh.nscratch_words)
-    FF_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&prm.nscratch), sh.nscratch_words * sizeof(uint64_t), stream));
   cudaError_t e = ffgpu::launch_eval(prm, sh, stream);
-  if (prm.nscratch) {
-    const cudaError_t ef = cudaFreeAsync(prm.nscratch, stream);
-    if (e == cudaSuccess) e = ef;
-  }
   if (e != cudaSuccess) return cuda_fail(e, "launch_eval");
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
@@ -313,12 +273,6 @@ ffgpu_ctx* ffgpu_create(const int* device_ids, int n_devices) {
     d.id = id;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, id) == cudaSuccess) d.sm_count = prop.multiProcessorCount;
-    // stream-ordered scratch (launch(): parked numerators) stays in the device's pool between launches
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, id) == cudaSuccess) {
-      uint64_t keep = ~0ULL;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
     ctx->devs.push_back(d);
   }
   for (auto& s : ctx->slots) s.dev.resize(ctx->devs.size());
@@ -353,7 +307,6 @@ ffgpu_tape* ffgpu_compile(ffgpu_ctx* ctx, const char* const* functions, size_t n
   t->col.enable_cse = !(flags & FFGPU_NO_CSE);
   t->col.enable_fuse = !(flags & FFGPU_NO_FUSE);
   t->col.enable_cross = !(flags & FFGPU_NO_CROSS);
-  t->col.enable_defer = !(flags & FFGPU_NO_DEFER);
   t->col.temp_budget = (int)((flags >> FFGPU_TEMPS_SHIFT) & 15u);
   const bool ok = t->col.compile_strings(to_vec(functions, n_functions), to_vec(vars, n_vars),
                                          (flags & FFGPU_CHECK_IS_EQUAL) != 0, err);
@@ -367,7 +320,6 @@ ffgpu_tape* ffgpu_compile_text(ffgpu_ctx* ctx, const char* text, const char* con
   t->col.enable_cse = !(flags & FFGPU_NO_CSE);
   t->col.enable_fuse = !(flags & FFGPU_NO_FUSE);
   t->col.enable_cross = !(flags & FFGPU_NO_CROSS);
-  t->col.enable_defer = !(flags & FFGPU_NO_DEFER);
   t->col.temp_budget = (int)((flags >> FFGPU_TEMPS_SHIFT) & 15u);
   const bool ok = t->col.compile_text(text ? text : "", to_vec(vars, n_vars), (flags & FFGPU_CHECK_IS_EQUAL) != 0, err);
   return finish_compile(ctx, std::move(t), ok, err);
@@ -395,8 +347,6 @@ ffgpu_tape* ffgpu_tape_clone(const ffgpu_tape* t) {
   n->col = t->col;
   n->force_k = t->force_k;
   n->force_threads = t->force_threads;
-  n->defer_mode = t->defer_mode;
-  n->defer_max_blocks = t->defer_max_blocks;
   n->chunk = t->chunk;
   if (t->ctx) {
     n->d_tape.assign(t->ctx->devs.size(), nullptr);
@@ -429,7 +379,6 @@ size_t ffgpu_n_slots(const ffgpu_tape* t) { return t->col.n_slots; }
 size_t ffgpu_cse_fallbacks(const ffgpu_tape* t) { return t->col.cse_fallbacks; }
 size_t ffgpu_n_structural_duplicates(const ffgpu_tape* t) { return t->col.n_structural_duplicates; }
 size_t ffgpu_n_shared_denominators(const ffgpu_tape* t) { return t->col.n_shared_denominators; }
-size_t ffgpu_n_deferred_divisions(const ffgpu_tape* t) { return t->col.n_deferred; }
 
 size_t ffgpu_rpn(const ffgpu_tape* t, size_t i, char* buf, size_t cap) {
   if (i >= t->col.functions.size()) return 0;
@@ -550,14 +499,6 @@ int ffgpu_set_launch(ffgpu_tape* t, int k, int threads) {
   return 0;
 }
 
-int ffgpu_set_defer(ffgpu_tape* t, int mode, unsigned max_blocks) {
-  if (!t) return fail("null tape");
-  if (mode < 0 || mode > 2) return fail("defer mode must be 0, 1 or 2");
-  t->defer_mode = mode;
-  t->defer_max_blocks = max_blocks;
-  return 0;
-}
-
 int ffgpu_set_chunk(ffgpu_tape* t, size_t points) {
   t->chunk = points;
   return 0;
@@ -631,8 +572,7 @@ int eval_host(ffgpu_tape* t, const uint64_t* values, const uint64_t* line_a, con
       if (zc >= 2) k_in = h_in;
       else if (n_vars) FF_CUDA(cudaMemcpyAsync(b.d_in, h_in, n_vars * n_even * sizeof(uint64_t), cudaMemcpyHostToDevice, b.stream));
       if (zc >= 1) k_out = h_out;
-      // results written over PCIe: parked divisors (deferred divisions) wait in device memory instead
-      if (launch(t, 0, k_in, n_even, n_even, k_out, n_even, b.stream, zc >= 1 ? b.d_out : nullptr)) return -1;
+      if (launch(t, 0, k_in, n_even, n_even, k_out, n_even, b.stream)) return -1;
       if (zc < 1 && n_out) FF_CUDA(cudaMemcpyAsync(h_out, b.d_out, n_out * n_even * sizeof(uint64_t), cudaMemcpyDeviceToHost, b.stream));
       FF_CUDA(cudaStreamSynchronize(b.stream));
       for (size_t f = 0; f < n_out; ++f) std::memcpy(out + f * n_points, h_out + f * n_even, n_points * sizeof(uint64_t));

@@ -445,22 +445,16 @@ struct FnEmitter {
   //   DEN_NONE      the whole expression, as written
   //   DEN_PRODUCE   1/D is computed once, parked in temp slot 0 for the functions that follow, then N * that
   //   DEN_CONSUME   N * (temp slot 0): the function before this one has the same denominator
-  //   3             only the divisor D of the top-level division (deferred divisions: it is parked by OP_DPARK)
-  //   4             ACC * N: ACC holds 1/D on entry (after OP_DUNPARK)
-  //   5             the whole function with its top-level division deferred: [N] NPARK [D] DPARK (N and D share code)
-  bool defer_full = false;
-  uint32_t park_row = 0;
   FnEmitter(const Function& f_, uint32_t fn_, std::vector<Instr>& t, std::vector<ConstPatch>& p, bool cse,
             int temp_budget, int den_mode = 0)
       : f(f_), fn(fn_), tape(t), patches(p), enable_cse(cse) {
-    root = (den_mode == 2 || den_mode == 4) ? f.nodes[f.root].l : den_mode == 3 ? f.nodes[f.root].r : f.root;
+    root = den_mode == 2 ? f.nodes[f.root].l : f.root;
     // Spill and temp slots share the kernel's shared memory ([slot][probe][thread], 16 KB per slot at
     // 8 probes x 256 threads): more than SLOT_BUDGET slots per lane cost resident blocks.  Functions that
     // already spill deep get fewer temps; two are always allowed (co-evaluated sums need two).
     if (temp_budget > 0) max_temps = std::min(temp_budget, MAX_TEMPS);
     else max_temps = std::max(2, std::min(MAX_TEMPS, SLOT_BUDGET - (int)f.nodes[root].need));
-    defer_full = den_mode == 5;
-    if (den_mode == 1 || den_mode == 2) {
+    if (den_mode) {
       slot_busy[0] = true;         // temp slot 0 carries 1/D from function to function
       temps_used = 1;                // it comes out of the function's own budget: the slot count (occupancy) stays
     }
@@ -620,7 +614,7 @@ struct FnEmitter {
     int32_t other;
     int32_t aux;
   };
-  enum { GEN, AFTER, APPLY_POP, APPLY_DIRECT, INVERT, POW_CONST, MUL_INVCONST, SQUARE, PRE, ACCUM, ADOPT, ADDPOP, MULPOP, EMIT, NPARK };
+  enum { GEN, AFTER, APPLY_POP, APPLY_DIRECT, INVERT, POW_CONST, MUL_INVCONST, SQUARE, PRE, ACCUM, ADOPT, ADDPOP, EMIT };
   std::vector<Item> work;
   // accumulate lists of co-evaluated sums: for ACCUM items
   struct Acc { int slot; bool minus; bool init; };
@@ -767,19 +761,8 @@ struct FnEmitter {
     work.push_back(Item{INVERT, -1, false, false, -1, 0});
     gen(r);
   }
-  // ACC = ACC * N for the numerator N of the top-level division: ACC (the inverted divisor) waits on the spill stack
-  void gen_times_acc() {
-    if (leaf_like(root)) {
-      Instr m = mk(OP_MUL);
-      operand(m, root);
-      put(m);
-      return;
-    }
-    work.push_back(Item{MULPOP, -1, false, false, -1, 0});
-    gen(root, true);
-  }
-  void gen(int32_t root, bool push_first = false) {
-    work.push_back(Item{GEN, root, push_first, false, -1, 0});
+  void gen(int32_t root) {
+    work.push_back(Item{GEN, root, false, false, -1, 0});
     while (!work.empty()) {
       const Item it = work.back();
       work.pop_back();
@@ -787,12 +770,6 @@ struct FnEmitter {
         case INVERT: put(mk(OP_INV)); continue;
         case SQUARE: put(mk(OP_SQR)); continue;
         case EMIT: put(raw[it.aux]); continue;
-        case NPARK:
-          // the numerator waits: on the spill stack in the plain kernel (one more slot), in a scratch row otherwise
-          put(mk(OP_NPARK));
-          ++depth;
-          max_depth = std::max(max_depth, depth);
-          continue;
         case APPLY_POP: apply(node(it.node), it.swap, true, -1); continue;
         case APPLY_DIRECT: apply(node(it.node), it.swap, false, it.other); continue;
         case POW_CONST: {
@@ -837,9 +814,8 @@ struct FnEmitter {
           else remaining[t] -= extra;
           continue;
         }
-        case ADDPOP:
-        case MULPOP: {
-          Instr ins = mk(it.what == ADDPOP ? OP_ADD : OP_MUL);
+        case ADDPOP: {
+          Instr ins = mk(OP_ADD);
           ins.src = SRC_POP;
           put(ins);
           --depth;
@@ -911,17 +887,7 @@ struct FnEmitter {
       const bool dl = direct(l), dr = direct(r);
       const unsigned a = f.nodes[l].need, b = f.nodes[r].need;
       const bool left_first = std::max(a, b + 1) <= std::max(b, a + 1);
-      if (n.kind == N_DIV && defer_full && u == rep[this->root]) {
-        // the function's own division, deferred: numerator and divisor are both parked (the group's second half,
-        // emitted by Collection::finish, is DUNPARK NMUL STORE)
-        Instr dp = mk(OP_DPARK, F_LAST);
-        dp.arg = park_row;
-        raw.push_back(dp);
-        work.push_back(Item{EMIT, -1, false, false, -1, (int32_t)raw.size() - 1});
-        work.push_back(Item{GEN, r, false, false, -1, 0});
-        work.push_back(Item{NPARK, -1, false, false, -1, 0});
-        work.push_back(Item{GEN, l, push, false, -1, 0});
-      } else if (n.kind == N_DIV) {
+      if (n.kind == N_DIV) {
         if (dl) {                      // invert the divisor, multiply by the simple numerator
           pin(l);
           work.push_back(Item{APPLY_DIRECT, u, false, true, l, 0});
@@ -960,17 +926,14 @@ struct FnEmitter {
 };
 }  // namespace
 
-void Collection::emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots, int den_mode, uint32_t park_row) {
+void Collection::emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots, int den_mode) {
   const size_t tape0 = tape.size(), patch0 = patches.size();
   for (int attempt = 0; attempt < 2; ++attempt) {
     const bool cse = enable_cse && !no_cse_fn_[fn];
     FnEmitter em(functions[fn], fn, tape, patches, cse, temp_budget, den_mode);
-    em.park_row = park_row;
     if (den_mode == 1) em.gen_produce();
     else if (den_mode == 2) em.gen_consume();
-    else if (den_mode == 3) em.gen(em.root);
-    else if (den_mode == 4) em.gen_times_acc();
-    else em.gen(functions[fn].root);      // (mode 5: the root is the deferred division, handled in gen)
+    else em.gen(functions[fn].root);
     if (em.failed && cse) {
       // the sharing pass lost track of a temp slot: emit this function as a plain tree instead
       tape.resize(tape0);
@@ -979,7 +942,7 @@ void Collection::emit_function(uint32_t fn, const std::vector<uint32_t>& out_slo
       ++cse_fallbacks;
       continue;
     }
-    for (uint32_t slot : (den_mode == 5 ? std::vector<uint32_t>() : out_slots)) {
+    for (uint32_t slot : out_slots) {
       Instr st = FnEmitter::mk(OP_STORE);
       st.arg = slot;
       em.put(st);
@@ -991,45 +954,23 @@ void Collection::emit_function(uint32_t fn, const std::vector<uint32_t>& out_slo
   }
 }
 
-// Translation check: run the emitted tape on the host at one point and compare every stored value with the
-// value of the expression tree (eval_nodes) of the function that owns the output slot.  The tape must be resolved
-// for prime p.  Temp slot 0 can carry the inverse of a denominator from one function to the next (shared
-// denominators) and parked divisors wait in their output rows (deferred divisions), exactly as on the device, so
-// the tape is run as a whole.  Returns false if the tape is malformed; bad[f] marks functions with a wrong value.
-bool Collection::check_tape(uint64_t p, const uint64_t* point, const std::vector<int32_t>& owner,
-                            std::vector<char>& bad) const {
-  bad.assign(functions.size(), 0);
-  std::vector<uint64_t> want(functions.size(), 0);
-  std::vector<char> have(functions.size(), 0);
+// Translation check: run the emitted code of function fn on the host at one point and compare with the
+// value of its expression tree (eval_nodes).  The tape must be resolved for prime p.
+bool Collection::check_function(uint32_t fn, uint64_t p, const uint64_t* point, uint64_t* temps, bool* temp_set) const {
   std::vector<uint64_t> val;
-  auto expected = [&](int32_t fn) {
-    if (!have[fn]) {
-      eval_nodes(functions[fn], p, point, val);
-      want[fn] = val[functions[fn].root];
-      have[fn] = 1;
-    }
-    return want[fn];
-  };
+  eval_nodes(functions[fn], p, point, val);
+  const uint64_t want = val[functions[fn].root];
   uint64_t acc = 0;
   std::vector<uint64_t> stack;
-  uint64_t temps[16] = {};
-  bool temp_set[16] = {};
-  std::vector<uint64_t> rows(n_out, 0);
-  std::vector<char> row_state(n_out, 0);          // 0 empty, 1 holds a parked divisor, 2 stored
-  std::vector<uint64_t> numerators;               // OP_NPARK ... OP_NMUL
-  bool ok = true;
-  auto blame = [&](uint32_t slot) {
-    if (slot < owner.size() && owner[slot] >= 0) bad[owner[slot]] = 1;
-    else ok = false;
-  };
-  for (size_t pc = 0; pc < tape.size() && ok; ++pc) {
+  // temps / temp_set (16 entries) belong to the caller: temp slot 0 can carry the inverse of a denominator from
+  // one function to the next (shared denominators), exactly as the shared-memory slot does on the device
+  bool stored = false;
+  for (uint32_t pc = fn_start[pos_of_[fn]]; pc < fn_start[pos_of_[fn] + 1]; ++pc) {
     const Instr& in = tape[pc];
-    if (in.op == OP_HALT) break;
     uint64_t b = 0;
-    bool operand_ok = true;
     switch (in.op >= OP_TERM ? (uint8_t)SRC_NONE : in.src) {   // the fused forms decode their own operands
       case SRC_POP:
-        if (stack.empty()) { operand_ok = false; break; }
+        if (stack.empty()) return false;
         b = stack.back();
         stack.pop_back();
         break;
@@ -1037,12 +978,11 @@ bool Collection::check_tape(uint64_t p, const uint64_t* point, const std::vector
       case SRC_NEGVAR: b = ffhost::neg(point[in.arg] % p, p); break;
       case SRC_CONST: b = in.imm; break;
       case SRC_TMP:
-        if (in.arg >= 16 || !temp_set[in.arg]) { operand_ok = false; break; }
+        if (in.arg >= 16 || !temp_set[in.arg]) return false;
         b = temps[in.arg];
         break;
       default: break;
     }
-    if (!operand_ok) return false;
     const bool swap = in.flags & F_SWAP;
     switch (in.op) {
       case OP_LOAD:
@@ -1081,35 +1021,9 @@ bool Collection::check_tape(uint64_t p, const uint64_t* point, const std::vector
         break;
       }
       case OP_STORE:
-        if (in.arg >= n_out || !stack.empty()) return false;
-        if (owner[in.arg] < 0 || acc != expected(owner[in.arg])) blame(in.arg);
-        rows[in.arg] = acc;
-        row_state[in.arg] = 2;
+        if (acc != want) return false;
+        stored = true;
         break;
-      case OP_DPARK:
-        // the divisor waits in an output row that nothing has stored yet; the spill stack is empty at this point
-        if (in.arg >= n_out || !stack.empty() || row_state[in.arg] != 0) return false;
-        rows[in.arg] = acc;
-        row_state[in.arg] = 1;
-        continue;
-      case OP_DUNPARK:
-        if (in.arg >= n_out || !stack.empty() || row_state[in.arg] != 1) return false;
-        acc = ffhost::inv(rows[in.arg], p);
-        row_state[in.arg] = 0;
-        continue;
-      case OP_DCHAIN:
-      case OP_DEND:
-        if (!stack.empty()) return false;
-        continue;
-      case OP_NPARK:
-        if (!stack.empty()) return false;          // the plain kernel keeps it at the bottom of the spill stack
-        numerators.push_back(acc);
-        continue;
-      case OP_NMUL:
-        if (numerators.empty() || !stack.empty()) return false;
-        acc = ffhost::mul(acc, numerators.back(), p);
-        numerators.pop_back();
-        continue;
       case OP_TERM: {
         const uint8_t mode = (in.flags >> TM_SHIFT) & 7;
         uint64_t t = ffhost::pow_ff(point[in.arg & 0xffff] % p, in.arg >> 16, p);
@@ -1153,14 +1067,7 @@ bool Collection::check_tape(uint64_t p, const uint64_t* point, const std::vector
     }
     if (in.flags & F_NEGR) acc = ffhost::neg(acc, p);
   }
-  if (!ok || !stack.empty() || !numerators.empty()) return false;
-  // every output has been stored (a row still holding a parked divisor means a group without its second half)
-  for (size_t k = 0; k < n_out; ++k)
-    if (row_state[k] != 2) {
-      if (owner[k] >= 0) bad[owner[k]] = 1;
-      else return false;
-    }
-  return true;
+  return stored && stack.empty();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1373,155 +1280,28 @@ bool Collection::finish(std::string& err) {
         }
       }
     }
-    // Units of emission, in evaluation order: a function on its own, or a run of functions over one denominator
-    // (head first).  A unit whose top-level division can wait -- numerator and denominator share no code, so the
-    // two halves can be emitted apart -- is DEFERRED: consecutive deferred units form a group
-    //     [D_1] DPARK r_1 ... [D_g] DPARK r_g   DCHAIN   DUNPARK r_g [numerators of unit g] ... DUNPARK r_1 [...]   DEND
-    // (tape.hpp).  The divisor of a unit waits in the first output row of its head.
-    struct Unit { std::vector<uint32_t> members; bool deferred; };
-    std::vector<Unit> units;
     for (size_t k = 0; k < functions.size(); ++k) {
       const size_t i = order_[k];
-      if (dup_of[i] >= 0 || slots[i].empty()) continue;      // a duplicate's outputs are stored by its twin
-      if (den_mode_[i] == 2 && !units.empty()) { units.back().members.push_back((uint32_t)i); continue; }
-      units.push_back(Unit{{(uint32_t)i}, false});
-    }
-    n_deferred = 0;
-    defer_parks = 0;
-    if (enable_defer) {
-      for (Unit& u : units) {
-        const uint32_t i = u.members[0];
-        const Function& f = functions[i];
-        const Node& rt = f.nodes[f.root];
-        if (no_cse_fn_[i] || rt.kind != N_DIV || rt.is_const || f.nodes[rt.r].is_const) continue;
-        if (u.members.size() > 1) { u.deferred = true; continue; }          // a run never shares code with its divisor
-        // numerator and denominator must not share a compound sub-expression (it would be computed twice)
-        std::vector<Fp> local;
-        const std::vector<Fp>& fp = fps.empty() ? (fingerprints(f, local), local) : fps[i];
-        std::unordered_map<uint64_t, char> in_den;
-        std::vector<int32_t> st{rt.r};
-        while (!st.empty()) {
-          const int32_t x = st.back();
-          st.pop_back();
-          const Node& nd = f.nodes[x];
-          if (nd.l < 0 || nd.is_const) continue;
-          in_den.emplace(fp[x].a ^ mix64(fp[x].b), 1);
-          st.push_back(nd.l);
-          st.push_back(nd.r);
-        }
-        bool shares = false;
-        st.assign(1, rt.l);
-        while (!st.empty() && !shares) {
-          const int32_t x = st.back();
-          st.pop_back();
-          const Node& nd = f.nodes[x];
-          if (nd.l < 0 || nd.is_const) continue;
-          shares = in_den.count(fp[x].a ^ mix64(fp[x].b)) != 0;
-          st.push_back(nd.l);
-          st.push_back(nd.r);
-        }
-        u.deferred = !shares;
-      }
-    }
-    // A collection that is ONE function N / D (one unit, one member): numerator and divisor are both parked, they may
-    // share code, and the second half is DUNPARK NMUL STORE (tape.hpp).
-    defer_numerators = 0;
-    bool full = false;
-    if (enable_defer && units.size() == 1 && units[0].members.size() == 1) {
-      const uint32_t i = units[0].members[0];
-      const Function& f = functions[i];
-      const Node& rt = f.nodes[f.root];
-      full = !no_cse_fn_[i] && rt.kind == N_DIV && !rt.is_const && !f.nodes[rt.r].is_const;
-      if (full) units[0].deferred = true;
-    }
-    constexpr size_t GROUP_MAX = 8;             // DPARKs per group: entries of the kernel's per-thread product stack
-    size_t n_groups = 0, n_plain = 0;
-    auto put = [&](uint8_t op, uint32_t arg, uint8_t flags) {
-      Instr in{};
-      in.op = op;
-      in.arg = arg;
-      in.flags = flags;
-      tape.push_back(in);
-    };
-    for (size_t a = 0; a < units.size();) {
       fn_start.push_back((uint32_t)tape.size());
-      if (!units[a].deferred) {
-        for (uint32_t i : units[a].members) emit_function(i, slots[i], den_mode_[i]);
-        ++n_plain;
-        ++a;
-        continue;
-      }
-      if (full) {
-        const uint32_t head = units[0].members[0];
-        emit_function(head, slots[head], 5, slots[head][0]);      // [N] NPARK [D] DPARK
-        put(OP_DCHAIN, 0, 0);
-        put(OP_DUNPARK, slots[head][0], 0);
-        put(OP_NMUL, 0, 0);
-        for (uint32_t sl : slots[head]) put(OP_STORE, sl, 0);
-        put(OP_DEND, 0, 0);
-        n_deferred = 1;
-        defer_parks = 1;
-        defer_numerators = 1;
-        ++n_groups;
-        ++a;
-        continue;
-      }
-      size_t b = a;
-      while (b < units.size() && units[b].deferred && b - a < GROUP_MAX) ++b;
-      for (size_t q = a; q < b; ++q) {
-        const uint32_t head = units[q].members[0];
-        emit_function(head, {}, 3);
-        put(OP_DPARK, slots[head][0], q + 1 == b ? F_LAST : 0);
-      }
-      put(OP_DCHAIN, 0, 0);
-      for (size_t q = b; q-- > a;) {
-        const Unit& u = units[q];
-        const uint32_t head = u.members[0];
-        put(OP_DUNPARK, slots[head][0], 0);
-        if (u.members.size() == 1) {
-          emit_function(head, slots[head], 4);
-        } else {
-          put(OP_SAVE, 0, 0);                   // temp slot 0 = 1/D for all functions of the run
-          for (uint32_t i : u.members) emit_function(i, slots[i], 2);
-        }
-        ++n_deferred;
-      }
-      put(OP_DEND, 0, 0);
-      defer_parks = std::max<uint32_t>(defer_parks, (uint32_t)(b - a));
-      ++n_groups;
-      a = b;
+      if (dup_of[i] < 0) emit_function((uint32_t)i, slots[i], den_mode_[i]);   // a duplicate's outputs are stored by its twin
+      count_work(functions[i]);
     }
-    defer_single = n_groups == 1 && n_plain == 0;
-    defer_groups = (uint32_t)n_groups;
-    for (size_t k = 0; k < functions.size(); ++k) count_work(functions[k]);
     fn_start.push_back((uint32_t)tape.size());
     peephole();
     if (enable_fuse) fuse();
-    // every DCHAIN carries the tape offset behind its group's DEND: the deferring kernel goes on there while the
-    // inversion runs, and comes back for the group's second half later
-    uint32_t after_dend = 0;
-    for (size_t i = tape.size(); i-- > 0;) {
-      if (tape[i].op == OP_DEND) after_dend = (uint32_t)i + 1;
-      else if (tape[i].op == OP_DCHAIN) tape[i].arg = after_dend;
-    }
     // Translation check of every function at one pseudo-random point: the tape must reproduce the value of
-    // the expression tree.  A function that fails is re-emitted as a plain tree (no sharing, no deferral) on the
-    // second pass; if that fails too the compilation is refused -- never a wrong probe value.
+    // the expression tree.  A function that fails is re-emitted as a plain tree (no sharing) on the second
+    // pass; if that fails too the compilation is refused -- never a wrong probe value.
     if (!resolve(P0, err)) return false;
     std::vector<uint64_t> pt(vars.size());
     uint64_t seed = 0x243F6A8885A308D3ULL;
     for (auto& v : pt) v = 1 + splitmix64(seed) % (P0 - 1);
-    std::vector<int32_t> owner(n_out, -1);
-    for (size_t i = 0; i < functions.size(); ++i)
-      for (uint32_t sl : slots[i]) owner[sl] = (int32_t)i;
-    std::vector<char> bad;
-    if (!check_tape(P0, pt.data(), owner, bad)) {
-      err = "internal error: the emitted tape is malformed";
-      return false;
-    }
     bool again = false;
-    for (size_t i = 0; i < functions.size(); ++i) {
-      if (!bad[i]) continue;
+    uint64_t chk_temps[16] = {};
+    bool chk_temp_set[16] = {};
+    for (size_t k = 0; k < functions.size(); ++k) {
+      const size_t i = order_[k];
+      if (dup_of[i] >= 0 || check_function((uint32_t)i, P0, pt.data(), chk_temps, chk_temp_set)) continue;
       if (pass == 1 || no_cse_fn_[i] || !enable_cse) {
         err = "internal error: the tape of function " + std::to_string(i) + " does not reproduce its expression";
         return false;
@@ -1544,9 +1324,9 @@ bool Collection::finish(std::string& err) {
       if (in.src == SRC_VAR || in.src == SRC_NEGVAR) ++executed.max_rpn_depth;   // reused: variable row reads
       switch (in.op) {
         case OP_ADD: case OP_SUB: case OP_NEG: case OP_ACCUM: ++executed.ma; break;
-        case OP_MUL: case OP_SQR: case OP_NMUL: ++executed.mm; break;
+        case OP_MUL: case OP_SQR: ++executed.mm; break;
         case OP_MULADD: ++executed.mm; ++executed.ma; break;
-        case OP_INV: case OP_DUNPARK: ++executed.inv; break;
+        case OP_INV: ++executed.inv; break;
         case OP_POWU:
           if (in.imm < (P0 >> 1)) executed.mm += chain(in.imm);
           else { ++executed.inv; executed.mm += chain(P0 - in.imm - 1); }
@@ -1572,21 +1352,21 @@ bool Collection::finish(std::string& err) {
       if (in.op < OP_TERM && (in.flags & F_NEGR)) ++executed.ma;
     }
   }
-  // chunk tables for C = 1, 2, 4, ... while a chunk still holds a unit: the C + 1 tape offsets that cut the tape into
-  // C runs of about equal length.  A chunk starts where nothing is carried over from earlier code (fn_start): never
-  // inside a run of functions over one denominator, never inside a group of deferred divisions.
+  // chunk tables for C = 1, 2, 4, ... while a chunk still holds a function
   chunk_table.clear();
   chunk_table_off.clear();
   max_chunks = 1;
   const uint32_t total = (uint32_t)tape.size();
-  const size_t n_starts = fn_start.empty() ? 0 : fn_start.size() - 1;
-  for (unsigned C = 1; C <= 1024 && C <= std::max<size_t>(n_starts, 1); C <<= 1) {
+  for (unsigned C = 1; C <= 1024 && C <= std::max<size_t>(functions.size(), 1); C <<= 1) {
     chunk_table_off.push_back((uint32_t)chunk_table.size());
     size_t f = 0;
     for (unsigned k = 0; k < C; ++k) {
       const uint64_t target = (uint64_t)total * k / C;
       while (f + 1 < fn_start.size() && fn_start[f] < target) ++f;
-      chunk_table.push_back(fn_start.empty() ? 0 : fn_start[f]);
+      // a chunk starts with temp slot 0 undefined: back up to the function that fills it
+      size_t g = f;
+      while (g > 0 && g < functions.size() && (den_mode_[order_[g]] == 2 || dup_of[order_[g]] >= 0)) --g;
+      chunk_table.push_back(fn_start[g]);
     }
     chunk_table.push_back(total);
     max_chunks = C;
@@ -1649,12 +1429,6 @@ void Collection::peephole() {
         case OP_INV: fx = FX_INV; break;
         case OP_STORE: fx = FX_STORE; break;
         case OP_SQR: fx = FX_SQR; break;
-        case OP_DPARK: fx = FX_DPARK; break;
-        case OP_DCHAIN: fx = FX_DCHAIN; break;
-        case OP_DUNPARK: fx = FX_DUNPARK; break;
-        case OP_DEND: fx = FX_DEND; break;
-        case OP_NPARK: fx = FX_NPARK; break;
-        case OP_NMUL: fx = FX_NMUL; break;
         default: break;
       }
     }

@@ -105,17 +105,7 @@ struct Collection {
   uint32_t n_structural_duplicates = 0;       // functions of equal structure: evaluated once, stored to all their outputs
   uint32_t n_shared_denominators = 0;         // functions that reuse the inverted denominator of the function before them
   int temp_budget = 0;                        // temp slots per function (0: automatic, see FnEmitter)
-  // Deferred top-level divisions (tape.hpp, OP_DPARK ...): functions N / D whose numerator and denominator share no
-  // code are laid out in groups -- all denominators first, then one inversion point, then the numerators -- so that
-  // a thread inverts everything it parked with ONE Fermat chain and no block-wide barrier.
-  bool enable_defer = true;
-  uint32_t n_deferred = 0;                    // divisions served that way
-  uint32_t defer_parks = 0;                   // most DPARKs in one group (0: the tape has no group)
-  uint32_t defer_groups = 0;                  // groups in the tape
-  uint32_t defer_numerators = 0;              // numerators parked next to their divisors (OP_NPARK; 0 or 1)
-  bool defer_single = false;                  // the whole tape is ONE group: a block pipelines over tiles of points
-  std::vector<uint32_t> fn_start;             // tape offsets at which a chunk of the tape may start (a function that
-                                              // depends on no earlier one, or a group), in order, then the end
+  std::vector<uint32_t> fn_start;             // tape offset of every distinct function IN EVALUATION ORDER, then the end
   // chunk tables: for C = 1, 2, 4, ... the C + 1 offsets that cut the tape into C runs of whole
   // functions with about equal instruction counts (flattened: table c starts at chunk_table_off[c])
   std::vector<uint32_t> chunk_table;
@@ -160,10 +150,8 @@ struct Collection {
   bool build_tree(Function& f, std::string& err);
   static void compute_needs(Function& f);
   std::vector<Function> base_functions_;      // one per output, before any factor was applied
-  void emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots, int den_mode, uint32_t park_row = 0);
-  // translation check: the whole tape run on the host at one point; bad[f] is set for every function whose stored
-  // value differs from its expression tree's.  owner[slot] = function that stores output slot `slot`.
-  bool check_tape(uint64_t p, const uint64_t* point, const std::vector<int32_t>& owner, std::vector<char>& bad) const;
+  void emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots, int den_mode);
+  bool check_function(uint32_t fn, uint64_t p, const uint64_t* point, uint64_t* temps, bool* temp_set) const;
   std::vector<uint8_t> den_mode_;             // per function: 0 as written, 1 parks 1/D in temp slot 0, 2 uses it
   std::vector<uint32_t> order_, pos_of_;      // evaluation order (position -> function) and its inverse
   std::vector<uint8_t> no_cse_fn_;

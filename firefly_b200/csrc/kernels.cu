@@ -206,14 +206,10 @@ __device__ __forceinline__ R pow_negint_lane(R b, R e_lazy, const Field& F) {
   return pow_lane(inv_fermat(b, F), (u64)(-(long long)e), F);
 }
 
-__device__ __forceinline__ void named_sync(u32 id, u32 n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void named_arrive(u32 id, u32 n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
 // ---- block-batched inversion -----------------------------------------------------------------
 // a[k] <- 1/a[k] (0 -> 0) for the K values of every thread of the block.  scratch: 64 u64 of
-// shared memory.  Must be reached by all THREADS threads that evaluate (the tape is block uniform); NAMED: these
-// are not the whole block (the deferring kernel has a helper warp), they meet on named barrier 15.
-template <int K, int THREADS, bool NAMED = false>
+// shared memory.  Must be reached by all threads of the block (the tape is block uniform).
+template <int K, int THREADS>
 __device__ __forceinline__ void block_inverse(R (&a)[K], const Field& F, u64* scratch) {
   constexpr int W = THREADS / 32;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -247,7 +243,7 @@ __device__ __forceinline__ void block_inverse(R (&a)[K], const Field& F, u64* sc
   R inv_upto, before;          // 1 / (warps 0..warp), product of warps 0..warp-1
   if (W > 1) {
     if (lane == 31) scratch[warp] = toU(s);
-    if (NAMED) named_sync(15, THREADS); else __syncthreads();
+    __syncthreads();
     if (warp == 0) {
       R S = lane < W ? mkR(scratch[lane]) : mkR(1);
 #pragma unroll
@@ -261,7 +257,7 @@ __device__ __forceinline__ void block_inverse(R (&a)[K], const Field& F, u64* sc
       scratch[lane] = toU(Sx);
       scratch[32 + lane] = toU(IS);
     }
-    if (NAMED) named_sync(15, THREADS); else __syncthreads();
+    __syncthreads();
     before = mkR(scratch[warp]);
     inv_upto = mkR(scratch[32 + warp]);
   } else {
@@ -292,7 +288,6 @@ struct Lane {
   static constexpr int NACC = VEC ? K / 2 : K;               // accesses per variable
   const u64* vbase;      // values + first point of the tile
   u64* obase;            // out + first point of the tile
-  u64* pbase;            // parked divisors (rows like out) + first point of the tile
   u64 in_stride, out_stride;
   uint2* stk;            // [slot][k][thread], this thread's column
   u64* scratch;          // 64 words for block_inverse
@@ -304,19 +299,10 @@ struct Lane {
   // load/store is one 16-byte access per lane and a warp covers 512 contiguous bytes.  Lanes beyond the end
   // of the batch recompute the last valid point and never store: the hot loop has no bounds checks.
   __device__ __forceinline__ void init(const EvalParams& prm, u64* smem) {
-    in_stride = prm.in_stride;
-    out_stride = prm.out_stride;
-    scratch = smem;
-    stk = reinterpret_cast<uint2*>(smem + 64) + threadIdx.x;
-    tmp_top = prm.n_slots - 1;
-    F = Field{prm.p, prm.c, prm.d};
-    own = VEC ? 2 * threadIdx.x : threadIdx.x;
-  }
-  // place the thread on tile number `tile` (THREADS * K consecutive points)
-  __device__ __forceinline__ void set_tile(const EvalParams& prm, u64 tile_index) {
-    const u64 tile = tile_index * (u64)(THREADS * K);
-    const u64 left64 = prm.n_points - tile;               // > 0: the tiles cover exactly the batch
+    const u64 tile = (u64)blockIdx.x * (u64)(THREADS * K);
+    const u64 left64 = prm.n_points - tile;               // > 0: the grid covers exactly the batch
     left = left64 < (u64)(THREADS * K) ? (u32)left64 : (u32)(THREADS * K);
+    own = VEC ? 2 * threadIdx.x : threadIdx.x;
 #pragma unroll
     for (int j = 0; j < NACC; j++) {
       const u32 o = own + j * STEP, last = left - (VEC ? 2 : 1);
@@ -324,7 +310,12 @@ struct Lane {
     }
     vbase = reinterpret_cast<const u64*>(prm.values) + tile;
     obase = reinterpret_cast<u64*>(prm.out) + tile;
-    pbase = reinterpret_cast<u64*>(prm.park ? prm.park : prm.out) + tile;
+    in_stride = prm.in_stride;
+    out_stride = prm.out_stride;
+    scratch = smem;
+    stk = reinterpret_cast<uint2*>(smem + 64) + threadIdx.x;
+    tmp_top = prm.n_slots - 1;
+    F = Field{prm.p, prm.c, prm.d};
   }
   __device__ __forceinline__ void load_var(u32 var, R (&b)[K]) const {
     const u64* row = vbase + (u64)var * in_stride;
@@ -345,46 +336,6 @@ struct Lane {
     }
   }
   __device__ __forceinline__ bool in_range(int j) const { return own + j * STEP < left; }
-  __device__ __forceinline__ bool probe_in_range(int k) const { return in_range(VEC ? k / 2 : k); }
-  // a tile-sized chunk of scratch memory (parked numerators): this thread's K values, raw (bounded lazy residues)
-  __device__ __forceinline__ void chunk_put(u64* chunk, const R (&a)[K]) const {
-    if (VEC) {
-#pragma unroll
-      for (int j = 0; j < NACC; j++)
-        *reinterpret_cast<ulonglong2*>(chunk + own + j * STEP) = make_ulonglong2(toU(a[2 * j]), toU(a[2 * j + 1]));
-    } else {
-#pragma unroll
-      for (int j = 0; j < NACC; j++) chunk[own + j * STEP] = toU(a[j]);
-    }
-  }
-  __device__ __forceinline__ void chunk_get(const u64* chunk, R (&b)[K]) const {
-    if (VEC) {
-#pragma unroll
-      for (int j = 0; j < NACC; j++) {
-        const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(chunk + own + j * STEP);
-        b[2 * j] = mkR(w.x);
-        b[2 * j + 1] = mkR(w.y);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < NACC; j++) b[j] = mkR(chunk[own + j * STEP]);
-    }
-  }
-  // a row of out[] that this thread has written before (OP_DPARK): plain loads, not the read-only path
-  __device__ __forceinline__ void load_row(u32 out_slot, u64 (&v)[K]) const {
-    const u64* row = pbase + (u64)out_slot * out_stride;
-    if (VEC) {
-#pragma unroll
-      for (int j = 0; j < NACC; j++) {
-        const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(row + off[j]);
-        v[2 * j] = w.x;
-        v[2 * j + 1] = w.y;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < NACC; j++) v[j] = row[off[j]];
-    }
-  }
   __device__ __forceinline__ void slot_put(const R (&a)[K], u32 slot) const {
     uint2* t = stk + (size_t)slot * (K * THREADS);
 #pragma unroll
@@ -401,10 +352,8 @@ struct Lane {
   // spill slots count up from 0, temp slots (shared sub-expressions, co-evaluated sums) down from the last slot
   __device__ __forceinline__ void tmp_put(const R (&a)[K], u32 slot) const { slot_put(a, tmp_top - slot); }
   __device__ __forceinline__ void tmp_get(R (&b)[K], u32 slot) const { slot_get(b, tmp_top - slot); }
-  __device__ __forceinline__ void store_row(u32 out_slot, const R (&a)[K]) const { store_to(obase, out_slot, a); }
-  __device__ __forceinline__ void park_row(u32 out_slot, const R (&a)[K]) const { store_to(pbase, out_slot, a); }
-  __device__ __forceinline__ void store_to(u64* base, u32 out_slot, const R (&a)[K]) const {
-    u64* row = base + (u64)out_slot * out_stride;
+  __device__ __forceinline__ void store_row(u32 out_slot, const R (&a)[K]) const {
+    u64* row = obase + (u64)out_slot * out_stride;
     if (VEC) {
 #pragma unroll
       for (int j = 0; j < NACC; j++)
@@ -418,273 +367,13 @@ struct Lane {
   }
 };
 
-// ---- deferred divisions, pipelined ---------------------------------------------------------------
-// A work item = one group of deferred divisions (tape.hpp) on one tile of points.  Its first half leaves the K
-// canonical divisors of every function of the group in the functions' output rows (OP_DPARK) and, per thread, the
-// product of everything the thread parked.  OP_DCHAIN then starts the block's inversion for the item WITHOUT waiting
-// for it: warp scans give every thread the product of the other lanes, the warps' products go to shared memory, all
-// warps but one announce themselves on a named barrier and walk on to the first half of the NEXT items; the one
-// duty warp of the item (they take turns) waits for the others' products, runs the Fermat chain on W lanes and
-// publishes 1 / (product of warp w) for every warp.  The item's second half (OP_DUNPARK ...) runs kDeferPipe - 1
-// items later, by which time the chain is long done: one multiplication gives the thread the inverse of its own
-// product, and Montgomery's trick peels the divisors off it in reverse order.  Nothing ever waits on a block-wide
-// barrier while the chain runs.  Zero divisors (and lanes past the end of the batch, which never store) enter the
-// products as 1; a zero divisor gives 0 (reference: a/0 = 0, FFInt.cpp:146-153).
-// Shared memory of the deferring kernel behind the slots, per work item in flight (slot = item mod kDeferPipe):
-//   Q[slot][park][thread]   running products of the divisors a thread parked in the item (only if a group has > 1)
-//   M[slot][thread]         product of the other lanes of the thread's warp
-//   SG[slot][2][W]          the warps' products, then per warp 1 / (its product)
-//   FIFO[warp][kDeferPipe]  the warp's items whose second half is still to run (tile | pc << 32 | DPARKs << 60)
-//   CTRL[warp][..]          the warp's pipeline state (u32 words, DeferCtrl): warps run independently of each other
-// Addresses are computed from the launch parameters where they are used and the pipeline state is touched only by
-// the deferred-division instructions: none of this lives in registers across the interpreter's dispatch.
-template <int K, int THREADS>
-struct DeferMem {
-  static constexpr u32 W = THREADS / 32;
-  template <class PRM>
-  static __device__ __forceinline__ u64* base(const PRM& prm) {
-    extern __shared__ __align__(16) u64 dyn_smem[];
-    return dyn_smem + 64 + (size_t)prm.n_slots * (K * THREADS);
-  }
-  template <class PRM>
-  static __device__ __forceinline__ u32 qwords(const PRM& prm) {
-    return prm.defer_parks > 1 ? (u32)kDeferPipe * prm.defer_parks * THREADS : 0u;
-  }
-  template <class PRM>
-  static __device__ __forceinline__ u64* q(const PRM& prm, u32 slot, u32 j) {
-    return base(prm) + (slot * prm.defer_parks + j) * THREADS + threadIdx.x;
-  }
-  template <class PRM>
-  static __device__ __forceinline__ u64* m(const PRM& prm, u32 slot) {
-    return base(prm) + qwords(prm) + slot * THREADS + threadIdx.x;
-  }
-  template <class PRM>
-  static __device__ __forceinline__ u64* sg(const PRM& prm, u32 slot) {
-    return base(prm) + qwords(prm) + kDeferPipe * THREADS + slot * (2 * W);
-  }
-  template <class PRM>
-  static __device__ __forceinline__ u64* fifo(const PRM& prm) {
-    return base(prm) + qwords(prm) + kDeferPipe * THREADS + kDeferPipe * (2 * W) + (threadIdx.x >> 5) * kDeferPipe;
-  }
-  template <class PRM>
-  static __device__ __forceinline__ volatile u32* ctrl(const PRM& prm) {
-    return reinterpret_cast<volatile u32*>(base(prm) + qwords(prm) + kDeferPipe * THREADS + kDeferPipe * (2 * W) + W * kDeferPipe) +
-           (threadIdx.x >> 5) * 16;
-  }
-  // one word behind the evaluating warps' control blocks: set when the evaluating warps are done (helper: return)
-  template <class PRM>
-  static __device__ __forceinline__ volatile u32* quit(const PRM& prm) {
-    return reinterpret_cast<volatile u32*>(base(prm) + qwords(prm) + kDeferPipe * THREADS + kDeferPipe * (2 * W) + W * kDeferPipe) +
-           W * 16;
-  }
-  static size_t words(u32 parks) {
-    return (parks > 1 ? (size_t)kDeferPipe * parks * THREADS : 0) + (size_t)kDeferPipe * THREADS + (size_t)kDeferPipe * 2 * W +
-           (size_t)W * kDeferPipe + (size_t)W * 8 + 2;
-  }
-};
-// what the out-of-line deferred-division code needs of the launch parameters (passed by value: taking the address of
-// the kernel's parameter block would copy all of it to local memory)
-struct DeferPrm {
-  u32 n_slots, defer_parks;
-  u64 p;
-  u32 c, d;
-};
-// words of CTRL: every lane of the warp writes the same value, so every lane reads what it wrote
-enum DeferCtrl : u32 {
-  DC_TILE_LO = 0, DC_TILE_HI,   // first tile of the block's range
-  DC_MY_TILES,                  // tiles in the range
-  DC_CUR_TILE,                  // tile (relative) the FIRST halves are running on
-  DC_ITEMS,                     // first halves finished so far (item i lives in slot i mod kDeferPipe)
-  DC_PEND,                      // items whose second half is still to run
-  DC_RET_PC,                    // where the tape goes on after the second half that is running
-  DC_CSLOT,                     // slot of the item whose second half is running
-  DC_QSP,                       // DPARKs of the running first half / divisors still parked in the running second half
-  DC_RUN_TILE,                  // tile (relative) the interpreter is to be on after a jump of the pipeline
-};
-
-
-template <int K, int THREADS, bool VEC>
-__device__ __forceinline__ void defer_park(const DeferPrm& prm, const Lane<K, THREADS, VEC>& L, u32 row, const R (&acc)[K]) {
-  typedef DeferMem<K, THREADS> DM;
-  const Field F = L.F;
-  volatile u32* ctrl = DM::ctrl(prm);
-  const u32 slot = ctrl[DC_ITEMS] % kDeferPipe, qsp = ctrl[DC_QSP];
-  L.park_row(row, acc);
-  R e[K];
-#pragma unroll
-  for (int k = 0; k < K; k++) {
-    const u64 cv = fcanon(acc[k], F);
-    e[k] = (cv != 0 && L.probe_in_range(k)) ? mkR(cv) : mkR(1);
-  }
-  // product of the K divisors, pairwise (depth log2 K)
-#pragma unroll
-  for (int w = 1; w < K; w <<= 1) {
-#pragma unroll
-    for (int k = 0; k + w < K; k += 2 * w) e[k] = fmul(e[k], e[k + w], F);
-  }
-  // the running product of the item waits in M[slot] (and, for the way back, on the product stack)
-  const R run = qsp ? fmul(mkR(*DM::m(prm, slot)), e[0], F) : e[0];
-  *DM::m(prm, slot) = toU(run);
-  if (prm.defer_parks > 1) *DM::q(prm, slot, qsp) = toU(run);
-  ctrl[DC_QSP] = qsp + 1;
-}
-template <int K, int THREADS, bool VEC>
-__device__ __forceinline__ void defer_unpark(const DeferPrm& prm, const Lane<K, THREADS, VEC>& L, u32 row, R (&acc)[K]) {
-  typedef DeferMem<K, THREADS> DM;
-  const Field F = L.F;
-  volatile u32* ctrl = DM::ctrl(prm);
-  const u32 slot = ctrl[DC_CSLOT], qsp = ctrl[DC_QSP] - 1;
-  ctrl[DC_QSP] = qsp;
-  u64 cv[K];
-  L.load_row(row, cv);
-  bool z[K];
-  R e[K], pre[K];
-#pragma unroll
-  for (int k = 0; k < K; k++) {
-    z[k] = !(cv[k] != 0 && L.probe_in_range(k));
-    e[k] = z[k] ? mkR(1) : mkR(cv[k]);
-  }
-  pre[0] = e[0];
-#pragma unroll
-  for (int k = 1; k < K; k++) pre[k] = fmul(pre[k - 1], e[k], F);
-  const R run = mkR(*DM::m(prm, slot));        // 1 / (everything the thread parked up to and including this row)
-  R I = run;
-  if (qsp) {
-    I = fmul(run, mkR(*DM::q(prm, slot, qsp - 1)), F);     // times everything parked before it
-    *DM::m(prm, slot) = toU(fmul(run, pre[K - 1], F));
-  }
-#pragma unroll
-  for (int k = K - 1; k >= 1; --k) {
-    const R q = fmul(I, pre[k - 1], F);
-    acc[k] = z[k] ? mkR(0) : q;
-    I = fmul(I, e[k], F);
-  }
-  acc[0] = z[0] ? mkR(0) : I;
-}
-// first half of an item done (M[slot] = product of all divisors this thread parked): hand the warp's product to the
-// helper warp.  Never blocks.  BLOCK = threads of the whole block (the THREADS evaluating ones + the helper warp).
-template <int K, int THREADS, bool VEC>
-__device__ __forceinline__ void defer_chain_begin(const DeferPrm& prm, const Lane<K, THREADS, VEC>& L, u32 slot) {
-  constexpr int W = THREADS / 32;
-  const Field F = L.F;
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const R run = mkR(*DeferMem<K, THREADS>::m(prm, slot));
-  R s = run, u = run;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const R sm = fmul(s, shfl_up(s, off), F);
-    const R um = fmul(u, shfl_down(u, off), F);
-    if (lane >= (unsigned)off) s = sm;
-    if (lane + off < 32) u = um;
-  }
-  R sx = shfl_up(s, 1);        // product of the lanes before this one
-  R ux = shfl_down(u, 1);      // product of the lanes after this one
-  if (lane == 0) sx = mkR(1);
-  if (lane == 31) ux = mkR(1);
-  *DeferMem<K, THREADS>::m(prm, slot) = toU(fmul(sx, ux, F));
-  u64* S = DeferMem<K, THREADS>::sg(prm, slot);
-  if (lane == 31) S[warp] = toU(s);
-  __threadfence_block();
-  named_arrive(1 + slot, THREADS + 32);
-}
-// The helper warp (the block's last): for every work item, in order, wait for the evaluating warps' products, invert
-// -- lane w runs the Fermat chain on the product of warps 0..w --, publish 1 / (product of warp w).  It has nothing
-// else to do, so no evaluating warp ever waits for a chain unless the helper falls kDeferPipe - 1 items behind.
-template <int K, int THREADS>
-__device__ __forceinline__ void defer_helper(const EvalParams& prm, const Field& F) {
-  constexpr int W = THREADS / 32;
-  const unsigned lane = threadIdx.x & 31;
-  volatile u32* quit = DeferMem<K, THREADS>::quit(prm);
-  for (u32 item = 0;; ++item) {
-    const u32 slot = item % kDeferPipe;
-    named_sync(1 + slot, THREADS + 32);          // all warps' products of the item are in S (or: nothing more will come)
-    if (*quit) return;
-    u64* S = DeferMem<K, THREADS>::sg(prm, slot);
-    R P = lane < (unsigned)W ? mkR(S[lane]) : mkR(1);
-#pragma unroll
-    for (int off = 1; off < W; off <<= 1) {
-      const R pm = fmul(P, shfl_up(P, off), F);
-      if (lane >= (unsigned)off) P = pm;
-    }
-    const R IP = inv_fermat(P, F);               // lane w: 1 / (warps 0..w)
-    R Px = shfl_up(P, 1);                        // warps 0..w-1
-    if (lane == 0) Px = mkR(1);
-    if (lane < (unsigned)W) S[W + lane] = toU(fmul(IP, Px, F));    // 1 / (warp w)
-    __threadfence_block();
-    named_arrive(1 + kDeferPipe + slot, THREADS + 32);
-  }
-}
-// Pipeline control at the two places where a second half can start (a group's last OP_DPARK with a full pipeline, end
-// of the tape with nothing left to start): takes the oldest waiting item, notes its tile in CTRL (the interpreter moves
-// there), returns its first pc.
-template <int K, int THREADS>
-__device__ __forceinline__ u32 defer_start_second_half(const DeferPrm& prm, u32 ret_pc) {
-  typedef DeferMem<K, THREADS> DM;
-  volatile u32* ctrl = DM::ctrl(prm);
-  const u32 n_pend = ctrl[DC_PEND], oldest = ctrl[DC_ITEMS] - n_pend, slot = oldest % kDeferPipe;
-  const u64 e = DM::fifo(prm)[slot];
-  // M[slot] = 1 / (product of all divisors this thread parked in the item), once the helper has published the
-  // item's inverses
-  named_sync(1 + kDeferPipe + slot, THREADS + 32);
-  const u64* S = DM::sg(prm, slot);
-  u64* m = DM::m(prm, slot);
-  const Field F{prm.p, prm.c, prm.d};
-  *m = toU(fmul(mkR(S[THREADS / 32 + (threadIdx.x >> 5)]), mkR(*m), F));
-  ctrl[DC_RUN_TILE] = (u32)e;
-  ctrl[DC_CSLOT] = slot;
-  ctrl[DC_QSP] = (u32)(e >> 60);
-  ctrl[DC_RET_PC] = ret_pc;
-  ctrl[DC_PEND] = n_pend - 1;
-  return (u32)(e >> 32) & 0x0fffffffu;
-}
-// The deferred-division instructions with real work in them, OUT OF LINE on copies of the interpreter's state: inlined,
-// their register needs (scans, prefix products) made ptxas spill the instruction words at every dispatch of the tape.
-//   DS_PARK     OP_DPARK; with F_LAST also the OP_DCHAIN behind it (next_arg = its skip target): returns the pc to go
-//               on at (the oldest item's second half if the pipeline is full), CTRL[DC_RUN_TILE] = the tile to be on
-//   DS_UNPARK   OP_DUNPARK: t = the inverses
-//   DS_DRAIN    end of the tape, nothing left to start: like the tail of DS_PARK
-enum DeferSlow : u32 { DS_PARK = 0, DS_UNPARK, DS_DRAIN };
-constexpr u32 DS_NEXT = 0xffffffffu;
-template <int K, int THREADS, bool VEC>
-__device__ __noinline__ u32 defer_slow(const DeferPrm prm, const Lane<K, THREADS, VEC> L, u32 what, u32 flags, u32 arg,
-                                       u32 next_arg, u32 pc, R* tp) {
-  R(&t)[K] = *reinterpret_cast<R(*)[K]>(tp);
-  typedef DeferMem<K, THREADS> DM;
-  volatile u32* ctrl = DM::ctrl(prm);
-  if (what == DS_UNPARK) {
-    defer_unpark<K, THREADS, VEC>(prm, L, arg, t);
-    return DS_NEXT;
-  }
-  if (what == DS_DRAIN) return defer_start_second_half<K, THREADS>(prm, next_arg);
-  defer_park<K, THREADS, VEC>(prm, L, arg, t);
-  if (!(flags & F_LAST)) return DS_NEXT;
-  // first half of an item done (the OP_DCHAIN at pc + 1): start its inversion, do not wait for it
-#ifndef FFGPU_NO_ITEM_SYNC
-  // The evaluating warps meet here once per item.  Nothing they exchange needs it -- but warps that drift apart are
-  // spread over all of the interpreter's code at once, and its hot part then no longer fits the instruction cache
-  // (measured: no-instruction stalls 3.0 per issue without this barrier against 0.6 in the plain kernel).
-  named_sync(14, THREADS);
-#endif
-  const u32 item = ctrl[DC_ITEMS], n_pend = ctrl[DC_PEND] + 1;
-  defer_chain_begin<K, THREADS, VEC>(prm, L, item % kDeferPipe);
-  DM::fifo(prm)[item % kDeferPipe] = (u64)ctrl[DC_CUR_TILE] | ((u64)(pc + 2) << 32) | ((u64)ctrl[DC_QSP] << 60);
-  ctrl[DC_ITEMS] = item + 1;
-  ctrl[DC_PEND] = n_pend;
-  ctrl[DC_QSP] = 0;
-  ctrl[DC_RUN_TILE] = ctrl[DC_CUR_TILE];
-  // a full pipeline: the oldest item's inversion has had kDeferPipe - 1 first halves of time, its second half runs
-  // now; then the tape goes on behind this group (next_arg = the instruction after its DEND)
-  if (n_pend == (u32)kDeferPipe) return defer_start_second_half<K, THREADS>(prm, next_arg);
-  return next_arg;
-}
-
 #ifndef FFGPU_GENERIC_INLINE
 #define FFGPU_GENERIC_INLINE __forceinline__
 #endif
 // The uncommon instructions (lane exponents, negated variables, negative literal powers, ...), out of line:
 // the accumulators travel through local memory for these, which keeps them out of the register allocation
 // of the hot loop (inlined, they made ptxas copy all accumulators at every tape instruction).
-template <int K, int THREADS, bool VEC, bool NAMED>
+template <int K, int THREADS, bool VEC>
 __device__ FFGPU_GENERIC_INLINE u32 generic_op(const Lane<K, THREADS, VEC>& L, u32 opword, u32 arg, u64 imm, R (&acc)[K],
                                        u32 sp) {
   struct {
@@ -752,7 +441,7 @@ __device__ FFGPU_GENERIC_INLINE u32 generic_op(const Lane<K, THREADS, VEC>& L, u
       for (int k = 0; k < K; k++) acc[k] = fneg(acc[k], F);
       break;
     case OP_INV:
-      block_inverse<K, THREADS, NAMED>(acc, F, L.scratch);
+      block_inverse<K, THREADS>(acc, F, L.scratch);
       break;
     case OP_POWU: {
       // FFInt::pow(const FFInt&) with a lane-uniform exponent residue (FFInt.cpp:155-179)
@@ -763,7 +452,7 @@ __device__ FFGPU_GENERIC_INLINE u32 generic_op(const Lane<K, THREADS, VEC>& L, u
       } else if (e < (F.p >> 1)) {
         pow_uniform<K>(acc, e, F);
       } else {
-        block_inverse<K, THREADS, NAMED>(acc, F, L.scratch);
+        block_inverse<K, THREADS>(acc, F, L.scratch);
         pow_uniform<K>(acc, F.p - e - 1, F);
       }
       break;
@@ -777,7 +466,7 @@ __device__ FFGPU_GENERIC_INLINE u32 generic_op(const Lane<K, THREADS, VEC>& L, u
       } else if (e >= 0) {
         pow_uniform<K>(acc, (u64)e, F);
       } else {
-        block_inverse<K, THREADS, NAMED>(acc, F, L.scratch);
+        block_inverse<K, THREADS>(acc, F, L.scratch);
         pow_uniform<K>(acc, (u64)(-(long long)e), F);
       }
       break;
@@ -794,29 +483,6 @@ __device__ FFGPU_GENERIC_INLINE u32 generic_op(const Lane<K, THREADS, VEC>& L, u
       break;
     case OP_STORE:
       L.store_row(ins.arg, acc);
-      break;
-    // deferred divisions on the kernel that does not defer: the divisor waits in its row, the block inverts it
-    case OP_DPARK:
-      L.park_row(ins.arg, acc);
-      break;
-    case OP_DUNPARK: {
-      u64 cv[K];
-      L.load_row(ins.arg, cv);
-#pragma unroll
-      for (int k = 0; k < K; k++) acc[k] = L.probe_in_range(k) ? mkR(cv[k]) : mkR(1);   // lanes past the end never stored
-      block_inverse<K, THREADS, NAMED>(acc, F, L.scratch);
-      break;
-    }
-    case OP_DCHAIN:
-    case OP_DEND:
-      break;
-    case OP_NPARK:               // the numerator waits on the spill stack
-      L.slot_put(acc, sp++);
-      break;
-    case OP_NMUL:
-      L.slot_get(b, --sp);
-#pragma unroll
-      for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], b[k], F);
       break;
     default:
       asm volatile("trap;");     // an instruction without code: never compute on with garbage
@@ -840,86 +506,29 @@ constexpr int min_blocks() {
   return (K == 8 && !LEAN) ? 768 / THREADS : 1024 / THREADS;
 }
 
-// BLOCK threads per block.  The deferring kernel's last warp is the helper that inverts (defer_helper); the other
-// THREADS = BLOCK - 32 threads evaluate, and a tile is THREADS * K points.
-template <int K, int BLOCK, bool VEC, bool LEAN, bool DEFER>
-__global__ void __launch_bounds__(BLOCK, min_blocks<K, BLOCK, LEAN>()) eval_tape_kernel(const EvalParams prm) {
-  constexpr int THREADS = DEFER ? BLOCK - 32 : BLOCK;
+template <int K, int THREADS, bool VEC, bool LEAN>
+__global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_tape_kernel(const EvalParams prm) {
   extern __shared__ __align__(16) u64 smem[];
-  if (DEFER && threadIdx.x >= THREADS) {
-    if (prm.n_tiles * ((u64)blockIdx.x + 1) / gridDim.x == prm.n_tiles * (u64)blockIdx.x / gridDim.x) return;   // no tile: nobody works
-    defer_helper<K, THREADS>(prm, Field{prm.p, prm.c, prm.d});
-    return;
-  }
   Lane<K, THREADS, VEC> L;
   L.init(prm, smem);
   const Field F = L.F;
-  // Blocks that share an SM and start together stay in step for the whole launch: they reach their block-wide
-  // inversion at the same moment, and while their chains run the SM has nothing else to issue.  The blocks of the
-  // FIRST wave therefore start a fraction of a tile's time apart (by their slot on the SM); every later block starts
-  // when an earlier one ends and inherits the offset.
-  if (!DEFER && prm.stagger_ns) {
-    const u32 slot = (blockIdx.x + blockIdx.y * gridDim.x) / prm.sm_count;
-    if (slot && slot < 8) __nanosleep(slot * prm.stagger_ns);
-  }
-
-  // blockIdx.y selects a chunk of the tape (a run of whole functions): many-function collections
-  // evaluated at few points still fill the chip
-  const uint4* tape = reinterpret_cast<const uint4*>(prm.tape);
-  u32 pc_begin = 0, pc_end = prm.n_instr;
-  if (prm.chunk_bounds) {
-    pc_begin = __ldg(prm.chunk_bounds + blockIdx.y);
-    pc_end = __ldg(prm.chunk_bounds + blockIdx.y + 1);
-  }
-  // Tiles of this block.  The plain kernel has one tile per block.  The deferring kernel takes a contiguous range
-  // of tiles (a tape that is one group of deferred divisions is launched with as many blocks as are resident, the
-  // ranges balanced) and runs the tape once per tile; second halves of groups run kDeferPipe - 1 work items late.
-  u64 tile = blockIdx.x;
-  if (DEFER) {
-    tile = prm.n_tiles * (u64)blockIdx.x / gridDim.x;
-    const u32 my_tiles = (u32)(prm.n_tiles * ((u64)blockIdx.x + 1) / gridDim.x - tile);
-    if (my_tiles == 0) return;
-    volatile u32* ctrl = DeferMem<K, THREADS>::ctrl(prm);
-    ctrl[DC_TILE_LO] = (u32)tile;
-    ctrl[DC_TILE_HI] = (u32)(tile >> 32);
-    ctrl[DC_MY_TILES] = my_tiles;
-    ctrl[DC_CUR_TILE] = 0;
-    ctrl[DC_ITEMS] = 0;
-    ctrl[DC_PEND] = 0;
-    ctrl[DC_QSP] = 0;
-    *DeferMem<K, THREADS>::quit(prm) = 0;
-  }
 
   R acc[K];
 #pragma unroll
   for (int k = 0; k < K; k++) acc[k] = opaque(0);
-
-  L.set_tile(prm, tile);
   u32 sp = 0;                                // spill-stack pointer (uniform)
-  u32 pc = pc_begin;
+
+  // blockIdx.y selects a chunk of the tape (a run of whole functions): many-function collections
+  // evaluated at few points still fill the chip
+  const uint4* tape = reinterpret_cast<const uint4*>(prm.tape);
+  u32 pc = 0, pc_end = prm.n_instr;
+  if (prm.chunk_bounds) {
+    pc = __ldg(prm.chunk_bounds + blockIdx.y);
+    pc_end = __ldg(prm.chunk_bounds + blockIdx.y + 1);
+  }
   InstrWord cur, nxt;
   cur.v = __ldg(tape + pc);
-  for (;;) {
-    if (pc >= pc_end) {
-      if (!DEFER) break;
-      volatile u32* ctrl = DeferMem<K, THREADS>::ctrl(prm);
-      const u32 cur_tile = ctrl[DC_CUR_TILE];
-      if (cur_tile + 1 < ctrl[DC_MY_TILES]) {
-        // the same tape on the next tile of the range
-        ctrl[DC_CUR_TILE] = cur_tile + 1;
-        L.set_tile(prm, (((u64)ctrl[DC_TILE_HI] << 32) | ctrl[DC_TILE_LO]) + cur_tile + 1);
-        pc = pc_begin;
-      } else if (ctrl[DC_PEND]) {
-        // nothing left to start: the second halves still waiting, oldest first
-        R t[K];
-        pc = defer_slow<K, THREADS, VEC>(DeferPrm{prm.n_slots, prm.defer_parks, prm.p, prm.c, prm.d}, L, DS_DRAIN, 0, 0, pc_end, pc, t);
-        L.set_tile(prm, (((u64)ctrl[DC_TILE_HI] << 32) | ctrl[DC_TILE_LO]) + ctrl[DC_RUN_TILE]);
-      } else {
-        break;
-      }
-      cur.v = __ldg(tape + pc);
-      continue;
-    }
+  for (; pc < pc_end;) {
     nxt.v = __ldg(tape + pc + 1);            // the tape ends in two HALTs: always in bounds
     const Instr ins = cur.i;
     R b[K];
@@ -1003,7 +612,7 @@ __global__ void __launch_bounds__(BLOCK, min_blocks<K, BLOCK, LEAN>()) eval_tape
         pow_uniform<K>(acc, ins.imm, F);
         break;
       case FX_INV:
-        block_inverse<K, THREADS, DEFER>(acc, F, L.scratch);
+        block_inverse<K, THREADS>(acc, F, L.scratch);
         break;
       case FX_SAVE:
       case FX_ACCUM_INIT:
@@ -1160,81 +769,18 @@ __global__ void __launch_bounds__(BLOCK, min_blocks<K, BLOCK, LEAN>()) eval_tape
         break;
       }
 
-      // ---- deferred top-level divisions (tape.hpp) ----------------------------------------------------------
-      // (the kernel that does not defer takes all four through the generic path below)
-      case FX_DPARK: {
-        if (!DEFER) goto generic;
-        // (with F_LAST this is also the DCHAIN behind it: nxt.i.arg = its skip target)
-        R t[K];
-#pragma unroll
-        for (int k = 0; k < K; k++) t[k] = acc[k];
-        const u32 to = defer_slow<K, THREADS, VEC>(DeferPrm{prm.n_slots, prm.defer_parks, prm.p, prm.c, prm.d}, L, DS_PARK, ins.flags,
-                                                    ins.arg, nxt.i.arg, pc, t);
-#pragma unroll
-        for (int k = 0; k < K; k++) acc[k] = opaque(0);      // ACC is dead: its value is parked
-        if (to == DS_NEXT) break;
-        volatile u32* ctrl = DeferMem<K, THREADS>::ctrl(prm);
-        L.set_tile(prm, (((u64)ctrl[DC_TILE_HI] << 32) | ctrl[DC_TILE_LO]) + ctrl[DC_RUN_TILE]);
-        pc = to;
-        cur.v = __ldg(tape + pc);
-        continue;
-      }
-      case FX_DCHAIN:
-        if (!DEFER) goto generic;
-        asm volatile("trap;");         // never dispatched: the group's last DPARK does its work and jumps
-        break;
-      case FX_DUNPARK: {
-        if (!DEFER) goto generic;
-        R t[K];
-        defer_slow<K, THREADS, VEC>(DeferPrm{prm.n_slots, prm.defer_parks, prm.p, prm.c, prm.d}, L, DS_UNPARK, 0, ins.arg, 0, pc, t);
-#pragma unroll
-        for (int k = 0; k < K; k++) acc[k] = opaque(toU(t[k]));
-        break;
-      }
-      case FX_NPARK: {
-        if (!DEFER) goto generic;
-        // the numerator of the running first half: into the scratch chunk of its item
-        const u32 slot = DeferMem<K, THREADS>::ctrl(prm)[DC_ITEMS] % kDeferPipe;
-        L.chunk_put(reinterpret_cast<u64*>(prm.nscratch) + ((u64)blockIdx.x * kDeferPipe + slot) * (u64)(THREADS * K), acc);
-        break;
-      }
-      case FX_NMUL: {
-        if (!DEFER) goto generic;
-        const u32 slot = DeferMem<K, THREADS>::ctrl(prm)[DC_CSLOT];
-        L.chunk_get(reinterpret_cast<const u64*>(prm.nscratch) + ((u64)blockIdx.x * kDeferPipe + slot) * (u64)(THREADS * K), b);
-#pragma unroll
-        for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], b[k], F);
-        break;
-      }
-      case FX_DEND: {
-        if (!DEFER) goto generic;
-        // second half done: back to the tile and the place the first halves have reached
-        volatile u32* ctrl = DeferMem<K, THREADS>::ctrl(prm);
-        L.set_tile(prm, (((u64)ctrl[DC_TILE_HI] << 32) | ctrl[DC_TILE_LO]) + ctrl[DC_CUR_TILE]);
-        ctrl[DC_QSP] = 0;
-        pc = ctrl[DC_RET_PC];
-        cur.v = __ldg(tape + pc);
-        continue;
-      }
-
       // ---- everything else, out of line (copies of the state: the originals never have their address taken)
-      default:
-      generic: {
-        if (ins.op == OP_HALT) {
-          pc = pc_end;                 // (never reached through the loop condition; a stray HALT ends the pass)
-          continue;
-        }
+      default: {
+        if (ins.op == OP_HALT) return;
         if (LEAN) {
-          // the launcher only picks a lean kernel for tapes without generic instructions (and, unless it defers, without
-          // deferred divisions)
-          asm volatile("trap;");
+          asm volatile("trap;");       // the launcher only picks a lean kernel for tapes without generic instructions
           break;
         }
         Lane<K, THREADS, VEC> L2 = L;
         R t[K];
 #pragma unroll
         for (int k = 0; k < K; k++) t[k] = acc[k];
-        sp = generic_op<K, THREADS, VEC, DEFER>(L2, cur.v.x, cur.v.y, ins.imm, t, sp);
+        sp = generic_op<K, THREADS, VEC>(L2, cur.v.x, cur.v.y, ins.imm, t, sp);
 #pragma unroll
         for (int k = 0; k < K; k++) acc[k] = opaque(toU(t[k]));
         break;
@@ -1243,17 +789,11 @@ __global__ void __launch_bounds__(BLOCK, min_blocks<K, BLOCK, LEAN>()) eval_tape
     cur = nxt;
     ++pc;
   }
-  if (DEFER) {
-    // no more work items: release the helper warp, which waits for the products of the next one
-    *DeferMem<K, THREADS>::quit(prm) = 1;
-    __threadfence_block();
-    named_arrive(1 + DeferMem<K, THREADS>::ctrl(prm)[DC_ITEMS] % kDeferPipe, THREADS + 32);
-  }
 }
 
-template <int K, int THREADS, bool VEC, bool LEAN, bool DEFER>
+template <int K, int THREADS, bool VEC, bool LEAN>
 cudaError_t launch_k(const EvalParams& prm, const LaunchShape& sh, cudaStream_t stream) {
-  auto kern = eval_tape_kernel<K, THREADS, VEC, LEAN, DEFER>;
+  auto kern = eval_tape_kernel<K, THREADS, VEC, LEAN>;
   if (sh.smem > 48 * 1024) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
     if (e != cudaSuccess) return e;
@@ -1262,37 +802,25 @@ cudaError_t launch_k(const EvalParams& prm, const LaunchShape& sh, cudaStream_t 
   return cudaGetLastError();
 }
 
-inline bool vec_ok(const EvalParams& prm) {
-  return (prm.n_points % 2 == 0) && (prm.in_stride % 2 == 0) && (prm.out_stride % 2 == 0) &&
-         ((uintptr_t)prm.values % 16 == 0) && ((uintptr_t)prm.out % 16 == 0) && ((uintptr_t)prm.park % 16 == 0);
-}
-
 template <int K, int THREADS>
 cudaError_t launch_t(const EvalParams& prm, const LaunchShape& sh, cudaStream_t stream) {
-  const bool vec = K >= 2 && vec_ok(prm);
+  const bool vec = K >= 2 && (prm.n_points % 2 == 0) && (prm.in_stride % 2 == 0) && (prm.out_stride % 2 == 0) &&
+                   ((uintptr_t)prm.values % 16 == 0) && ((uintptr_t)prm.out % 16 == 0);
   constexpr bool HAS_LEAN = K == 8 && THREADS <= 256;      // the only shapes whose register budget differs
-  // the deferring kernel exists for the shapes big batches run in (16-byte accesses only)
-  constexpr bool HAS_DEFER = (K == 8 || K == 4) && THREADS == 256;     // 7 evaluating warps + the helper warp
-  if (sh.defer) {
-    if (!HAS_DEFER || !vec) return cudaErrorInvalidValue;    // choose_shape / launch_eval never ask for this
-    if (sh.lean && HAS_LEAN) return launch_k<K, THREADS, (K >= 2), HAS_LEAN, HAS_DEFER>(prm, sh, stream);
-    return launch_k<K, THREADS, (K >= 2), false, HAS_DEFER>(prm, sh, stream);
-  }
   if (sh.lean && HAS_LEAN) {
-    if (vec) return launch_k<K, THREADS, (K >= 2), HAS_LEAN, false>(prm, sh, stream);
-    return launch_k<K, THREADS, false, HAS_LEAN, false>(prm, sh, stream);
+    if (vec) return launch_k<K, THREADS, (K >= 2), HAS_LEAN>(prm, sh, stream);
+    return launch_k<K, THREADS, false, HAS_LEAN>(prm, sh, stream);
   }
-  if (vec) return launch_k<K, THREADS, (K >= 2), false, false>(prm, sh, stream);
-  return launch_k<K, THREADS, false, false, false>(prm, sh, stream);
+  if (vec) return launch_k<K, THREADS, (K >= 2), false>(prm, sh, stream);
+  return launch_k<K, THREADS, false, false>(prm, sh, stream);
 }
 
 }  // namespace
 
 LaunchShape choose_shape(uint64_t n_points, uint32_t n_slots, int sm_count, int force_k, int force_threads,
-                         unsigned max_chunks, bool lean_ok, const DeferInfo& df) {
+                         unsigned max_chunks, bool lean_ok) {
   LaunchShape s;
-  auto smem_words = [&](int k, int th, unsigned q) { return (size_t)64 + (size_t)n_slots * k * th + (size_t)q * th; };
-  auto smem_of = [&](int k, int th) { return smem_words(k, th, 0) * sizeof(uint64_t); };
+  auto smem_of = [&](int k, int th) { return (size_t)(64 + (size_t)n_slots * k * th) * sizeof(uint64_t); };
   // resident warps per SM for a shape: registers (launch bounds: 80 per thread at 8 probes per thread, 64
   // below) and shared memory (227 KB per SM, 1 KB reserved per block)
   auto blocks_by_smem = [&](int k, int th) { return (int)((227 * 1024) / (smem_of(k, th) + 1024)); };
@@ -1341,58 +869,18 @@ LaunchShape choose_shape(uint64_t n_points, uint32_t n_slots, int sm_count, int 
   s.smem = smem_of(s.k, s.threads);
   s.lean = lean_of(s.k, s.threads);
   const uint64_t per_block = (uint64_t)s.threads * s.k;
-  s.n_tiles = (n_points + per_block - 1) / per_block;
-  s.blocks = (unsigned)s.n_tiles;
+  s.blocks = (unsigned)((n_points + per_block - 1) / per_block);
   // too few point tiles to fill the chip: split the functions of the collection over grid.y
   s.chunks = 1;
   const unsigned want = (unsigned)sm_count * 4;
   while (s.chunks < max_chunks && s.blocks * s.chunks < want) s.chunks <<= 1;
   if (s.chunks > max_chunks) s.chunks = max_chunks;
-  // Deferred divisions: the deferring kernel overlaps the block's Fermat chain of one work item (a group of deferred
-  // divisions on one tile) with the first halves of the next kDeferPipe - 1 items.  It needs items to pipeline over:
-  // a tape that is ONE group gets as many blocks as are resident and every block a balanced range of tiles; a tape
-  // of several groups keeps one tile per block and pipelines over its groups.
-  s.defer = false;
-  s.nscratch_words = 0;
-  if (df.parks) s.lean = false;        // the plain lean kernel has no code for the deferred-division instructions ...
-  if (df.parks && df.mode != 0 && (s.k == 8 || s.k == 4) && s.threads == 256 && df.tape_instr < (1u << 28)) {
-    // one warp of the block is the helper: 224 threads evaluate, a tile is 224 * k points
-    constexpr int WT = 256 - 32;
-    const size_t bytes = (smem_words(s.k, WT, 0) + DeferMem<8, WT>::words(df.parks)) * sizeof(uint64_t);
-    const bool lean = lean_ok && s.k == 8 && (227 * 1024) / (bytes + 1024) >= 4;
-    const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>((s.k == 8 && !lean ? 768 : 1024) / 256,
-                                                                             (227 * 1024) / (bytes + 1024)));
-    unsigned grid = (unsigned)sm_count * per_sm;
-    if (df.max_blocks) grid = std::min(grid, df.max_blocks);
-    const uint64_t n_tiles = (n_points + (uint64_t)WT * s.k - 1) / ((uint64_t)WT * s.k);
-    const uint64_t tiles_per_block = std::max<uint64_t>(1, n_tiles / grid);
-    const uint64_t items = tiles_per_block * std::max(1u, df.groups / s.chunks);
-    if (bytes <= 200 * 1024 && (items >= 2 * (uint64_t)kDeferPipe || df.mode == 2)) {
-      s.defer = true;
-      s.lean = lean;                   // ... the deferring lean kernel has
-      s.smem = bytes;
-      s.n_tiles = n_tiles;
-      // every block walks a balanced range of tiles
-      s.blocks = (unsigned)std::min<uint64_t>(n_tiles, grid);
-      s.nscratch_words = df.numerators ? (size_t)s.blocks * s.chunks * kDeferPipe * WT * s.k : 0;
-    }
-  }
   return s;
 }
 
-cudaError_t launch_eval(const EvalParams& prm_in, const LaunchShape& sh_in, cudaStream_t stream) {
-  if (prm_in.n_points == 0) return cudaSuccess;
-  if (sh_in.smem > 227 * 1024) return cudaErrorInvalidValue;
-  EvalParams prm = prm_in;
-  LaunchShape sh = sh_in;
-  if (sh.defer && !(sh.k >= 2 && vec_ok(prm))) {
-    // odd batch or unaligned rows: the same tape on the plain kernel (DUNPARK = load + block inversion)
-    sh.defer = false;
-    sh.lean = false;
-    sh.n_tiles = (prm.n_points + (uint64_t)sh.threads * sh.k - 1) / ((uint64_t)sh.threads * sh.k);
-    sh.blocks = (unsigned)sh.n_tiles;
-  }
-  prm.n_tiles = sh.n_tiles;
+cudaError_t launch_eval(const EvalParams& prm, const LaunchShape& sh, cudaStream_t stream) {
+  if (prm.n_points == 0) return cudaSuccess;
+  if (sh.smem > 227 * 1024) return cudaErrorInvalidValue;
 #define FFGPU_CASE(KK, TT) \
   if (sh.k == KK && sh.threads == TT) return launch_t<KK, TT>(prm, sh, stream);
   FFGPU_CASE(1, 128) FFGPU_CASE(1, 256) FFGPU_CASE(1, 512)

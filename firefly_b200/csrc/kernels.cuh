@@ -11,8 +11,6 @@ struct EvalParams {
   const Instr* tape;          // device, resolved for prime p, terminated by two OP_HALT
   const uint64_t* values;     // device, [n_vars][in_stride], canonical residues
   uint64_t* out;              // device, [n_out][out_stride]
-  uint64_t* park;             // where deferred divisors wait: rows laid out like out (NULL: in out itself).  Set when
-                              // out is mapped host memory, so that parked values do not cross PCIe twice.
   uint64_t n_points;
   uint64_t in_stride;
   uint64_t out_stride;
@@ -22,29 +20,6 @@ struct EvalParams {
   uint32_t n_slots;           // shared-memory slots per probe: spill slots from 0 up, temp slots from n_slots-1 down
   uint32_t n_instr;           // tape length without the terminators
   const uint32_t* chunk_bounds;  // device, n_chunks + 1 tape offsets at function boundaries (NULL: one chunk)
-  uint64_t n_tiles;           // tiles of threads * k points that cover the batch (set by launch_eval)
-  uint32_t stagger_ns;        // plain kernel: the blocks of the first wave start (slot on the SM) * stagger_ns late, see kernels.cu
-  uint32_t sm_count;
-  uint32_t defer_parks;       // deferring kernel: most OP_DPARKs of one group (rows of the per-thread product stack)
-  uint64_t* nscratch;         // deferring kernel: [block][kDeferPipe][tile] parked numerators (OP_NPARK), or NULL
-};
-
-// Deferring kernel: work items (a group of deferred divisions on one tile of points) in flight per block -- the second
-// half of an item runs after the first halves of the next kDeferPipe - 1 items, which is the time its inversion has
-#ifndef FFGPU_PIPE
-#define FFGPU_PIPE 3
-#endif
-constexpr int kDeferPipe = FFGPU_PIPE;
-
-// what the tape offers the deferring kernel (Collection::defer_parks / defer_single) and how the caller wants it used
-struct DeferInfo {
-  unsigned parks = 0;         // most OP_DPARKs in one group of the tape; 0: the tape has no deferred division
-  unsigned groups = 0;        // groups of deferred divisions in the tape
-  unsigned tape_instr = 0;    // tape length (the pipeline keeps tape offsets in 28 bits)
-  unsigned numerators = 0;    // numerators the tape parks per work item (Collection::defer_numerators)
-  bool single = false;        // the whole tape is one group: a block pipelines over the tiles of its range
-  int mode = 1;               // 0 never, 1 when a block has enough work items to pipeline, 2 whenever the shape allows it
-  unsigned max_blocks = 0;    // upper bound of the grid of a multi-tile launch (0: the resident blocks)
 };
 
 // probes per thread / threads per block actually used for a launch
@@ -55,13 +30,10 @@ struct LaunchShape {
   unsigned chunks;     // tape chunks (grid.y): blocks of a tile split the collection's functions
   size_t smem;
   bool lean;           // kernel without the generic instructions, 64 registers at k = 8 (kernels.cu)
-  uint64_t n_tiles;    // point tiles of the batch
-  bool defer;          // the kernel that pipelines deferred divisions (inversions overlap the next items' work)
-  size_t nscratch_words;   // ... words of scratch it needs for parked numerators (EvalParams::nscratch)
 };
 
 LaunchShape choose_shape(uint64_t n_points, uint32_t n_slots, int sm_count, int force_k, int force_threads,
-                         unsigned max_chunks, bool lean_ok, const DeferInfo& df = DeferInfo());
+                         unsigned max_chunks, bool lean_ok);
 cudaError_t launch_eval(const EvalParams& prm, const LaunchShape& shape, cudaStream_t stream);
 
 // synthetic probe points, identical on host (bench/tests) and device:

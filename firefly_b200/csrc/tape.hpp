@@ -70,21 +70,6 @@ enum Op : uint8_t {
   OP_ACCUM2,  // two OP_ACCUMs of the same ACC: slot A = arg & 0xff (F_SWAP, F_INIT), slot B = arg >> 8 (F_SWAP2, F_INIT2)
   OP_ADDVARS, // ACC = ACC +- var[id_0] +- ... : n = arg & 0xff (2..8), bit i of arg >> 8 set = subtract, ids = bytes of imm
   OP_MULVARS, // ACC = ACC * var[id_0] * ... : n = arg & 0xff (2..8), ids = bytes of imm
-  // ---- deferred top-level divisions (compiler.cpp, Collection::finish): a GROUP of functions N_i / D_i is laid out
-  // as  [D_1] DPARK r_1 ... [D_g] DPARK r_g (F_LAST)  DCHAIN  DUNPARK r_g [* N_g, STORE] ... DUNPARK r_1 [* N_1, STORE]  DEND
-  // The divisors wait in their functions' own output rows.  The deferring kernel inverts all divisors a THREAD has
-  // parked -- over the group's functions and over several tiles of points -- with one Fermat chain per thread
-  // (Montgomery's trick, no barrier); the plain kernel treats DUNPARK as load + block inversion.
-  OP_DPARK,   // out[arg][point] = canonical(ACC); ACC joins the thread's running product   (F_LAST: last of its group)
-  OP_DCHAIN,  // the thread's running product is inverted (deferring kernel; nothing to do otherwise)
-  OP_DUNPARK, // ACC = 1 / out[arg][point], 1/0 := 0
-  OP_DEND,    // end of the group
-  // A collection that is ONE function N / D parks its numerator too, so that the second half of a work item is only
-  // "unpark, multiply, store" and N and D can share code:  [N] NPARK [D] DPARK DCHAIN DUNPARK NMUL STORE DEND.
-  // The plain kernel keeps the numerator on the spill stack (NPARK = push, NMUL = multiply by the popped value), the
-  // deferring kernel in a scratch buffer of the launch (its second halves run several tiles later).
-  OP_NPARK,   // the numerator of the deferred division waits
-  OP_NMUL,    // ACC = ACC * (the waiting numerator)
   OP_COUNT
 };
 
@@ -100,7 +85,6 @@ enum Fast : uint8_t {
   FX_SAVE, FX_ACCUM_INIT, FX_ACCUM_ADD, FX_ACCUM_SUB,
   FX_LOAD_TMP, FX_PUSH_LOAD_TMP, FX_ADD_TMP, FX_MUL_TMP,
   FX_TERM, FX_ACCUM2, FX_ADDVARS, FX_MULVARS, FX_MULADD,
-  FX_DPARK, FX_DCHAIN, FX_DUNPARK, FX_DEND, FX_NPARK, FX_NMUL,
   FX_COUNT
 };
 
@@ -121,7 +105,6 @@ enum Flags : uint8_t {
   F_SWAP2 = 16, // OP_ACCUM2: F_SWAP of the second slot
   F_INIT2 = 32, // OP_ACCUM2: F_INIT of the second slot
   F_CMUL = 128, // OP_TERM: multiply the power by imm
-  F_LAST = 1,   // OP_DPARK: the last divisor of its group
 };
 // OP_TERM: what happens with the term, in flags bits 4..6
 enum TermMode : uint8_t { TM_LOAD = 0, TM_ADD = 1, TM_SUB = 2, TM_RSUB = 3, TM_MUL = 4 };

@@ -63,7 +63,6 @@ enum {
   FFGPU_NO_CSE = 2,           /* do not share equal sub-expressions inside a function (for A/B tests) */
   FFGPU_NO_FUSE = 4,          /* do not fuse instruction runs into TERM / MULADD / ACCUM2 / ADDVARS / MULVARS (for A/B tests) */
   FFGPU_NO_CROSS = 16,        /* do not share ACROSS functions: structural duplicates, shared denominators (for A/B tests) */
-  FFGPU_NO_DEFER = 32,        /* do not defer top-level divisions (one inversion per thread over many parked divisors); for A/B tests */
   FFGPU_TEMPS_SHIFT = 8       /* bits 8..11: temp slots per function for shared sub-expressions (0 = automatic) */
 };
 
@@ -103,10 +102,6 @@ size_t ffgpu_n_structural_duplicates(const ffgpu_tape*);
 /* functions N/D whose denominator has the structure of the denominator of the function before them: 1/D is
  * computed once per run of such functions and kept in a temp slot (no denominator code, no inversion for the rest) */
 size_t ffgpu_n_shared_denominators(const ffgpu_tape*);
-/* top-level divisions N/D whose divisor is parked in the function's output row while the block's inversion for it
- * runs behind the evaluation of the next work items (tape.hpp OP_DPARK ..; kernels.cu, deferring kernel);
- * FFGPU_NO_DEFER turns it off */
-size_t ffgpu_n_deferred_divisions(const ffgpu_tape*);
 size_t ffgpu_n_slots(const ffgpu_tape*);        /* shared-memory slots per probe the kernel reserves (spill + temps) */
 /* RPN of distinct function i, tokens joined by ' '; returns the length needed (without NUL) */
 size_t ffgpu_rpn(const ffgpu_tape*, size_t i, char* buf, size_t cap);
@@ -206,14 +201,6 @@ const char* ffgpu_queue_error(ffgpu_queue*);
 /* ---- tuning / measurement ----------------------------------------------------------------- */
 /* probes per thread (1, 2, 4, 8; 0 = automatic) and threads per block (128, 256, 512; 0 = automatic) */
 int ffgpu_set_launch(ffgpu_tape*, int probes_per_thread, int threads_per_block);
-/* deferred divisions (ffgpu_n_deferred_divisions): which kernel serves them.  mode 0: the plain kernel (the block
- * waits for its one inversion); 1: the deferring kernel (the block's inversion of one work item overlaps the next
- * items' evaluation, no block-wide wait) when a block has enough work items to pipeline over -- the default;
- * 2: the deferring kernel whenever the launch shape has one.
- * max_blocks: upper bound of the grid when a block walks several tiles (0 = the resident blocks of the device; tests
- * use small values to reach the multi-tile code with small batches).
- * The values are the same either way.  Default mode: environment FFGPU_DEFER, else 1. */
-int ffgpu_set_defer(ffgpu_tape*, int mode, unsigned max_blocks);
 /* points per pipelined chunk of ffgpu_eval (0 = automatic) */
 int ffgpu_set_chunk(ffgpu_tape*, size_t points);
 /* kernels launched by this library in this process so far */

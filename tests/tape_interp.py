@@ -47,32 +47,11 @@ def run(tape: np.ndarray, point, p: int, n_out: int):
     acc = 0
     stack = []
     temps = {}
-    parked = {}
-    numerators = []
     for ins in tape:
         op, src, flags, arg, imm = int(ins["op"]), int(ins["src"]), int(ins["flags"]), int(ins["arg"]), int(ins["imm"])
         if op == OP["HALT"]:
             break
         b = None
-        if op >= OP["DPARK"]:
-            # deferred top-level divisions: the divisor waits in its function's output row (tape.hpp)
-            if op == OP["DPARK"]:
-                assert not stack and arg not in parked and out[arg] is None
-                parked[arg] = acc
-            elif op == OP["DUNPARK"]:
-                assert not stack
-                acc = inv(parked.pop(arg), p)
-            elif op in (OP["DCHAIN"], OP["DEND"]):
-                assert not stack
-            elif op == OP["NPARK"]:
-                assert not stack
-                numerators.append(acc)
-            elif op == OP["NMUL"]:
-                assert not stack
-                acc = acc * numerators.pop() % p
-            else:
-                raise ValueError(f"bad opcode {op}")
-            continue
         if op >= OP["TERM"]:
             # fused forms decode their own operands
             if op == OP["TERM"]:
@@ -159,5 +138,4 @@ def run(tape: np.ndarray, point, p: int, n_out: int):
         if flags & F_NEGR:
             acc = (-acc) % p
     assert not stack, "spill stack not empty at HALT"
-    assert not parked and not numerators, "a parked divisor or numerator was never used"
     return out

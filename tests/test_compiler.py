@@ -431,7 +431,7 @@ def test_shared_denominators_are_inverted_once(oracle):
     assert par.n_shared_denominators == 7                   # 1, 2, 7 join 0; 6, 8, 10, 11 join 5 (the evaluation order groups them)
     assert par.cse_fallbacks == 0
     assert np.array_equal(interp(par, pts, p), want)
-    n_inv = sum(1 for ins in par.tape() if ff.OPS[int(ins["op"])] in ("INV", "DUNPARK"))
+    n_inv = sum(1 for ins in par.tape() if ff.OPS[int(ins["op"])] == "INV")
     assert n_inv == 2                                       # one per distinct denominator -- not one per division
     plain = ff.GpuParser(None, funs, vars_, cse=False)
     plain.set_prime(p)
