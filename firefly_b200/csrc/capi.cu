@@ -166,12 +166,16 @@ int launch(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, siz
   prm.in_stride = in_stride;
   prm.out_stride = out_stride;
   prm.p = c.prime;
-  prm.c = (uint32_t)((1ULL << 63) - c.prime);
+  prm.generic = ffgpu::is_table_form(c.prime) ? 0u : 1u;
+  prm.c = prm.generic ? 0u : (uint32_t)((1ULL << 63) - c.prime);
   prm.d = 2 * prm.c;
+  prm.pinv = 0;
+  prm.pshift = 0;
+  if (prm.generic) ffgpu::barrett_constants(c.prime, &prm.pinv, &prm.pshift);
   prm.n_slots = c.n_slots;
   prm.n_instr = (uint32_t)(c.tape.size() - 2);
   const ffgpu::LaunchShape sh = ffgpu::choose_shape(n_points, c.n_slots, t->ctx->devs[g].sm_count, t->force_k,
-                                                    t->force_threads, c.max_chunks, !t->needs_generic);
+                                                    t->force_threads, c.max_chunks, !t->needs_generic, prm.generic != 0);
   prm.chunk_bounds = nullptr;
   if (sh.chunks > 1) {
     unsigned idx = 0;
@@ -423,9 +427,11 @@ uint64_t ffgpu_get_prime(const ffgpu_tape* t) { return t->col.prime; }
 
 int ffgpu_set_prime(ffgpu_tape* t, uint64_t p) {
   if (!t) return fail("null tape");
-  const uint64_t two63 = 1ULL << 63;
-  if (p >= two63 || two63 - p >= (1u << 15) || p < 3)
-    return fail("unsupported prime " + std::to_string(p) + ": need p = 2^63 - c with 0 < c < 2^15");
+  // any odd prime below 2^63 (FFInt::set_new_prime, reference FFInt.cpp:344-353): p = 2^63 - c with c < 2^15 -- all of
+  // FireFly's table -- runs on the tuned arithmetic, everything else on the generic (Barrett) kernels.  Primality is
+  // the caller's business as it is in the reference, but an even or tiny modulus is certainly a mistake.
+  if (p >= (1ULL << 63) || p < 3 || !(p & 1))
+    return fail("unsupported modulus " + std::to_string(p) + ": need an odd prime below 2^63");
   std::string err;
   const bool rebuilt = t->col.stale;      // functions were added or trimmed: the tape has a new size
   if (!t->col.resolve(p, err)) return fail(err);
@@ -716,8 +722,7 @@ int ffgpu_checksum(ffgpu_ctx* ctx, int g, const uint64_t* d_out, size_t n_out, s
 int ffgpu_field_ops(ffgpu_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t* r, size_t n, uint64_t p) {
   if (!ctx) return fail("null context");
   if (n == 0) return 0;
-  const uint64_t two63 = 1ULL << 63;
-  if (p >= two63 || two63 - p >= (1u << 15)) return fail("unsupported prime");
+  if (p >= (1ULL << 63) || p < 3 || !(p & 1)) return fail("unsupported modulus: need an odd prime below 2^63");
   DeviceGuard guard(ctx->devs[0].id);
   uint64_t *da = nullptr, *db = nullptr, *dr = nullptr;
   cudaError_t e = cudaMalloc(&da, n * 8);

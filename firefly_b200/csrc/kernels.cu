@@ -38,10 +38,26 @@ using ff63::u64;
 
 namespace {
 
+// Two arithmetics, chosen per launch (EvalParams::generic):
+//   Field    p = 2^63 - c, c < 2^15 -- every prime of FireFly's table (reference: source/ReconstHelper.cpp:24-125).
+//            Bounded lazy residues, folds by c (ff63.cuh, "b63" family).  The tuned path.
+//   FieldB   any odd prime below 2^63 (FFInt::set_new_prime takes any, reference: source/FFInt.cpp:344-353; its
+//            mod_mul is generic, :356-369).  Canonical residues, Barrett reduction with a normalised divisor
+//            (ff63::mul_barrett): about three times the multiply instructions of the tuned path.
 struct Field {
   u64 p;
   u32 c, d;
 };
+struct FieldB {
+  u64 p, pn, pinv;
+  u32 k;
+};
+template <class FT>
+__device__ __forceinline__ FT make_field(const EvalParams& prm);
+template <>
+__device__ __forceinline__ Field make_field<Field>(const EvalParams& prm) { return Field{prm.p, prm.c, prm.d}; }
+template <>
+__device__ __forceinline__ FieldB make_field<FieldB>(const EvalParams& prm) { return FieldB{prm.p, prm.p << prm.pshift, prm.pinv, prm.pshift}; }
 
 // One residue = two 32-bit words in two independent registers (no aligned pair: see ff63.cuh, word-level
 // forms).  Values are BOUNDED lazy residues (ff63.cuh, "b63" family): below 2^63 + 2^32; canonical inputs
@@ -78,6 +94,21 @@ __device__ __forceinline__ R fneg(R a, const Field& F) {
   return r;
 }
 __device__ __forceinline__ u64 fcanon(R a, const Field& F) { return ff63::canon_pm(toU(a), F.c, F.p); }
+// what a caller hands in (documented: canonical residues): the tuned path computes with anything below 2^63 + 2^32
+__device__ __forceinline__ R fin(R a, const Field&) { return a; }
+// ---- generic modulus: canonical residues throughout
+__device__ __forceinline__ ff63::Barrett barrett_of(const FieldB& F) { return ff63::Barrett{F.p, F.pn, F.pinv, F.k}; }
+__device__ __forceinline__ R fmul(R a, R b, const FieldB& F) { return mkR(ff63::mul_barrett(toU(a), toU(b), barrett_of(F))); }
+__device__ __forceinline__ R fsqr(R a, const FieldB& F) { return mkR(ff63::mul_barrett(toU(a), toU(a), barrett_of(F))); }
+__device__ __forceinline__ R fadd(R a, R b, const FieldB& F) { return mkR(ff63::add(toU(a), toU(b), F.p)); }
+__device__ __forceinline__ R fsub(R a, R b, const FieldB& F) { return mkR(ff63::sub(toU(a), toU(b), F.p)); }
+__device__ __forceinline__ R fneg(R a, const FieldB& F) { return mkR(ff63::neg(toU(a), F.p)); }
+__device__ __forceinline__ u64 fcanon(R a, const FieldB&) { return toU(a); }
+__device__ __forceinline__ R fin(R a, const FieldB& F) {
+  u64 v = toU(a);
+  if (v >= F.p) v %= F.p;        // a caller value that is not a residue: reduce it, never compute on with it
+  return mkR(v);
+}
 // a constant the compiler may not hoist or speculate (plain broadcasts of an immediate into all accumulators
 // were moved above the interpreter's dispatch, 16 register moves per tape instruction)
 __device__ __forceinline__ R opaque(u64 v) {
@@ -96,8 +127,8 @@ __device__ __forceinline__ R shfl_idx(R a, int src) {
 }
 
 // x^e, e uniform across the warp, left-to-right binary; x^0 = 1 (reference mod_pow, FFInt.cpp:371-383)
-template <int K>
-__device__ __forceinline__ void pow_uniform(R (&a)[K], u64 e, const Field& F) {
+template <int K, class FT>
+__device__ __forceinline__ void pow_uniform(R (&a)[K], u64 e, const FT& F) {
   if (e <= 1) {
     if (e == 0) {
 #pragma unroll
@@ -126,8 +157,8 @@ __device__ __forceinline__ void pow_uniform(R (&a)[K], u64 e, const Field& F) {
 
 // r = base^e for e >= 1, out of place: the base keeps its registers (it was just loaded), the running power is
 // born in r's -- no copies at all
-template <int K>
-__device__ __forceinline__ void pow_from(R (&r)[K], const R (&base)[K], u32 e, const Field& F) {
+template <int K, class FT>
+__device__ __forceinline__ void pow_from(R (&r)[K], const R (&base)[K], u32 e, const FT& F) {
   if (e == 1) {
 #pragma unroll
     for (int k = 0; k < K; k++)
@@ -152,7 +183,8 @@ __device__ __forceinline__ void pow_from(R (&r)[K], const R (&base)[K], u32 e, c
   }
 }
 
-__device__ __forceinline__ R sqr_n(R x, int n, const Field& F) {
+template <class FT>
+__device__ __forceinline__ R sqr_n(R x, int n, const FT& F) {
 #pragma unroll 1
   for (int i = 0; i < n; i++) x = fsqr(x, F);
   return x;
@@ -180,8 +212,22 @@ __device__ __noinline__ R inv_fermat(R x, Field F) {
   return r;
 }
 
+// x^(p-2) for any odd prime p: left-to-right binary ladder over the bits of p - 2.  0 -> 0.
+__device__ __noinline__ R inv_fermat(R x, FieldB F) {
+  const u64 e = F.p - 2;
+  if (e == 1) return x;                           // p = 3
+  R r = x;
+#pragma unroll 1
+  for (int bit = 62 - __clzll((long long)e); bit >= 0; --bit) {
+    r = fsqr(r, F);
+    if ((e >> bit) & 1) r = fmul(r, x, F);
+  }
+  return r;
+}
+
 // per-lane power with a lane-dependent exponent (divergent; only for `x^y` style input)
-__device__ __noinline__ R pow_lane(R b, u64 e, Field F) {
+template <class FT>
+__device__ __noinline__ R pow_lane(R b, u64 e, FT F) {
   R r = mkR(1);
 #pragma unroll 1
   while (e) {
@@ -192,14 +238,16 @@ __device__ __noinline__ R pow_lane(R b, u64 e, Field F) {
   return r;
 }
 // FFInt::pow(const FFInt&) per lane (FFInt.cpp:155-179)
-__device__ __forceinline__ R pow_ff_lane(R b, R e_lazy, const Field& F) {
+template <class FT>
+__device__ __forceinline__ R pow_ff_lane(R b, R e_lazy, const FT& F) {
   const u64 e = fcanon(e_lazy, F);
   if (e == 2) return fsqr(b, F);
   if (e < (F.p >> 1)) return pow_lane(b, e, F);
   return pow_lane(inv_fermat(b, F), F.p - e - 1, F);
 }
 // FFInt::pow<int>(to_neg_int()) per lane (FFInt.hpp:149-174, FFInt.cpp:226-228)
-__device__ __forceinline__ R pow_negint_lane(R b, R e_lazy, const Field& F) {
+template <class FT>
+__device__ __forceinline__ R pow_negint_lane(R b, R e_lazy, const FT& F) {
   const int e = (int)(0u - (u32)fcanon(e_lazy, F));
   if (e == 2) return fsqr(b, F);
   if (e >= 0) return pow_lane(b, (u64)e, F);
@@ -209,8 +257,8 @@ __device__ __forceinline__ R pow_negint_lane(R b, R e_lazy, const Field& F) {
 // ---- block-batched inversion -----------------------------------------------------------------
 // a[k] <- 1/a[k] (0 -> 0) for the K values of every thread of the block.  scratch: 64 u64 of
 // shared memory.  Must be reached by all threads of the block (the tape is block uniform).
-template <int K, int THREADS>
-__device__ __forceinline__ void block_inverse(R (&a)[K], const Field& F, u64* scratch) {
+template <int K, int THREADS, class FT>
+__device__ __forceinline__ void block_inverse(R (&a)[K], const FT& F, u64* scratch) {
   constexpr int W = THREADS / 32;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   bool z[K];
@@ -282,7 +330,7 @@ union InstrWord {
 };
 
 // Per-thread view of the batch: where this thread's probes are, its column of the shared-memory slots.
-template <int K, int THREADS, bool VEC>
+template <int K, int THREADS, bool VEC, class FT>
 struct Lane {
   static constexpr u32 STEP = VEC ? 2 * THREADS : THREADS;   // distance between this thread's accesses
   static constexpr int NACC = VEC ? K / 2 : K;               // accesses per variable
@@ -293,7 +341,7 @@ struct Lane {
   u64* scratch;          // 64 words for block_inverse
   u32 off[NACC];         // tile-relative offsets of this thread's accesses, clamped into the batch
   u32 own, left, tmp_top;
-  Field F;
+  FT F;
 
   // Points owned by this thread.  VEC: pairs (2t, 2t+1) inside rows of 2*THREADS points, so that every
   // load/store is one 16-byte access per lane and a warp covers 512 contiguous bytes.  Lanes beyond the end
@@ -315,7 +363,7 @@ struct Lane {
     scratch = smem;
     stk = reinterpret_cast<uint2*>(smem + 64) + threadIdx.x;
     tmp_top = prm.n_slots - 1;
-    F = Field{prm.p, prm.c, prm.d};
+    F = make_field<FT>(prm);
   }
   __device__ __forceinline__ void load_var(u32 var, R (&b)[K]) const {
     const u64* row = vbase + (u64)var * in_stride;
@@ -324,14 +372,14 @@ struct Lane {
       for (int j = 0; j < NACC; j++) {
         // n_points is even and rows are 16-byte aligned on this path
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + off[j]));
-        b[2 * j] = R{v.x, v.y};
-        b[2 * j + 1] = R{v.z, v.w};
+        b[2 * j] = fin(R{v.x, v.y}, F);
+        b[2 * j + 1] = fin(R{v.z, v.w}, F);
       }
     } else {
 #pragma unroll
       for (int j = 0; j < NACC; j++) {
         const uint2 v = __ldg(reinterpret_cast<const uint2*>(row + off[j]));
-        b[j] = R{v.x, v.y};
+        b[j] = fin(R{v.x, v.y}, F);
       }
     }
   }
@@ -373,14 +421,14 @@ struct Lane {
 // The uncommon instructions (lane exponents, negated variables, negative literal powers, ...), out of line:
 // the accumulators travel through local memory for these, which keeps them out of the register allocation
 // of the hot loop (inlined, they made ptxas copy all accumulators at every tape instruction).
-template <int K, int THREADS, bool VEC>
-__device__ FFGPU_GENERIC_INLINE u32 generic_op(const Lane<K, THREADS, VEC>& L, u32 opword, u32 arg, u64 imm, R (&acc)[K],
+template <int K, int THREADS, bool VEC, class FT>
+__device__ FFGPU_GENERIC_INLINE u32 generic_op(const Lane<K, THREADS, VEC, FT>& L, u32 opword, u32 arg, u64 imm, R (&acc)[K],
                                        u32 sp) {
   struct {
     u32 op, src, flags, arg;
     u64 imm;
   } ins = {opword & 0xffu, (opword >> 8) & 0xffu, (opword >> 16) & 0xffu, arg, imm};
-  const Field F = L.F;
+  const FT F = L.F;
   R b[K];
   switch (ins.src) {
     case SRC_POP: L.slot_get(b, --sp); break;
@@ -506,12 +554,12 @@ constexpr int min_blocks() {
   return (K == 8 && !LEAN) ? 768 / THREADS : 1024 / THREADS;
 }
 
-template <int K, int THREADS, bool VEC, bool LEAN>
+template <int K, int THREADS, bool VEC, bool LEAN, class FT>
 __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_tape_kernel(const EvalParams prm) {
   extern __shared__ __align__(16) u64 smem[];
-  Lane<K, THREADS, VEC> L;
+  Lane<K, THREADS, VEC, FT> L;
   L.init(prm, smem);
-  const Field F = L.F;
+  const FT F = L.F;
 
   R acc[K];
 #pragma unroll
@@ -776,11 +824,11 @@ __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_
           asm volatile("trap;");       // the launcher only picks a lean kernel for tapes without generic instructions
           break;
         }
-        Lane<K, THREADS, VEC> L2 = L;
+        Lane<K, THREADS, VEC, FT> L2 = L;
         R t[K];
 #pragma unroll
         for (int k = 0; k < K; k++) t[k] = acc[k];
-        sp = generic_op<K, THREADS, VEC>(L2, cur.v.x, cur.v.y, ins.imm, t, sp);
+        sp = generic_op<K, THREADS, VEC, FT>(L2, cur.v.x, cur.v.y, ins.imm, t, sp);
 #pragma unroll
         for (int k = 0; k < K; k++) acc[k] = opaque(toU(t[k]));
         break;
@@ -791,9 +839,9 @@ __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_
   }
 }
 
-template <int K, int THREADS, bool VEC, bool LEAN>
+template <int K, int THREADS, bool VEC, bool LEAN, class FT = Field>
 cudaError_t launch_k(const EvalParams& prm, const LaunchShape& sh, cudaStream_t stream) {
-  auto kern = eval_tape_kernel<K, THREADS, VEC, LEAN>;
+  auto kern = eval_tape_kernel<K, THREADS, VEC, LEAN, FT>;
   if (sh.smem > 48 * 1024) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
     if (e != cudaSuccess) return e;
@@ -807,6 +855,13 @@ cudaError_t launch_t(const EvalParams& prm, const LaunchShape& sh, cudaStream_t 
   const bool vec = K >= 2 && (prm.n_points % 2 == 0) && (prm.in_stride % 2 == 0) && (prm.out_stride % 2 == 0) &&
                    ((uintptr_t)prm.values % 16 == 0) && ((uintptr_t)prm.out % 16 == 0);
   constexpr bool HAS_LEAN = K == 8 && THREADS <= 256;      // the only shapes whose register budget differs
+  if (prm.generic) {
+    // any odd prime: the shapes small and medium batches run in (choose_shape keeps to them)
+    constexpr bool HAS_GENERIC = K <= 4 && THREADS <= 256;
+    if (!HAS_GENERIC) return cudaErrorInvalidValue;
+    if (vec) return launch_k<(HAS_GENERIC ? K : 1), (HAS_GENERIC ? THREADS : 128), (K >= 2 && HAS_GENERIC), false, FieldB>(prm, sh, stream);
+    return launch_k<(HAS_GENERIC ? K : 1), (HAS_GENERIC ? THREADS : 128), false, false, FieldB>(prm, sh, stream);
+  }
   if (sh.lean && HAS_LEAN) {
     if (vec) return launch_k<K, THREADS, (K >= 2), HAS_LEAN>(prm, sh, stream);
     return launch_k<K, THREADS, false, HAS_LEAN>(prm, sh, stream);
@@ -818,8 +873,14 @@ cudaError_t launch_t(const EvalParams& prm, const LaunchShape& sh, cudaStream_t 
 }  // namespace
 
 LaunchShape choose_shape(uint64_t n_points, uint32_t n_slots, int sm_count, int force_k, int force_threads,
-                         unsigned max_chunks, bool lean_ok) {
+                         unsigned max_chunks, bool lean_ok, bool generic_field) {
   LaunchShape s;
+  if (generic_field) {
+    // the generic-modulus kernels exist for 1, 2 and 4 probes per thread and blocks of 128 or 256 threads
+    lean_ok = false;
+    if (force_k > 4) force_k = 4;
+    if (force_threads > 256) force_threads = 256;
+  }
   auto smem_of = [&](int k, int th) { return (size_t)(64 + (size_t)n_slots * k * th) * sizeof(uint64_t); };
   // resident warps per SM for a shape: registers (launch bounds: 80 per thread at 8 probes per thread, 64
   // below) and shared memory (227 KB per SM, 1 KB reserved per block)
@@ -842,6 +903,7 @@ LaunchShape choose_shape(uint64_t n_points, uint32_t n_slots, int sm_count, int 
     // (a many-function collection also spreads over grid.y, one run of functions per block)
     const uint64_t par = n_points * (uint64_t)(max_chunks ? max_chunks : 1);
     int kmax = par >= 8 * lanes ? 8 : par >= 4 * lanes ? 4 : par >= 2 * lanes ? 2 : 1;
+    if (generic_field && kmax > 4) kmax = 4;
     while (kmax > 1 && (uint64_t)kmax * 128 > n_points + 127) kmax >>= 1;   // never more lanes than points
     // most probes per thread first, but never below 16 resident warps per SM if a smaller shape gets there
     s.k = 1;
@@ -907,20 +969,22 @@ __global__ void fill_points_kernel(u64* values, u64 n_vars, u64 n_points, u64 st
     values[v * stride + j] = 1 + splitmix64_at(seed + v * total + first + j) % (p - 1);
   }
 }
+__device__ __forceinline__ u64 reduce_any(u64 v, const Field& F) { return ff63::canon_pm(v, F.c, F.p); }
+__device__ __forceinline__ u64 reduce_any(u64 v, const FieldB& F) { return v >= F.p ? v % F.p : v; }
 // probe points on a line: values[v][j] = a[v] * t[j] + s[v]  (canonical).  What Reconstructor::queue_probes
 // computes on the host per point (reference: Reconstructor.hpp:2946-2950 -- values[0] = t + shift[0],
 // values[i] = rand_zi[i-1] * t + shift[i]; the factor-scan variant :2952-2960 is a[v] in {0,1}).
 // Two points per thread, 16-byte accesses; a[] and s[] are read through the uniform path.
+template <class FT>
 __global__ void __launch_bounds__(256) line_points_kernel(u64* __restrict__ values, const u64* __restrict__ t,
                                                           const u64* __restrict__ a, const u64* __restrict__ s,
-                                                          u32 n_vars, u64 n_points, u64 stride, u64 p) {
-  const Field F{p, (u32)(0x8000000000000000ULL - p), (u32)(2 * (0x8000000000000000ULL - p))};
+                                                          u32 n_vars, u64 n_points, u64 stride, const FT F) {
   const bool vec = (n_points % 2 == 0) && (stride % 2 == 0) && ((uintptr_t)values % 16 == 0) && ((uintptr_t)t % 16 == 0);
   if (vec) {
     for (u64 j = 2 * ((u64)blockIdx.x * blockDim.x + threadIdx.x); j < n_points; j += 2 * (u64)gridDim.x * blockDim.x) {
       ulonglong2 tt = __ldg(reinterpret_cast<const ulonglong2*>(t + j));
-      tt.x = ff63::canon_pm(tt.x, F.c, F.p);        // any 64-bit t is reduced first: the product needs bounded operands
-      tt.y = ff63::canon_pm(tt.y, F.c, F.p);
+      tt.x = reduce_any(tt.x, F);                   // any 64-bit t is reduced first: the product needs bounded operands
+      tt.y = reduce_any(tt.y, F);
       for (u32 v = 0; v < n_vars; v++) {
         const u64 av = __ldg(a + v), sv = __ldg(s + v);
         ulonglong2 x;
@@ -931,7 +995,7 @@ __global__ void __launch_bounds__(256) line_points_kernel(u64* __restrict__ valu
     }
   } else {
     for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < n_points; j += (u64)gridDim.x * blockDim.x) {
-      const u64 tj = ff63::canon_pm(__ldg(t + j), F.c, F.p);
+      const u64 tj = reduce_any(__ldg(t + j), F);
       for (u32 v = 0; v < n_vars; v++)
         values[(u64)v * stride + j] = fcanon(fadd(fmul(mkR(tj), mkR(__ldg(a + v)), F), mkR(__ldg(s + v)), F), F);
     }
@@ -965,11 +1029,11 @@ __global__ void checksum_kernel(const u64* out, u64 n_points, u64 stride, u64 p,
     sums[2 * blockIdx.x + 1] = xs[0];
   }
 }
-__global__ void field_ops_kernel(int op, const u64* a, const u64* b, u64* r, u64 n, u64 p) {
-  const Field F{p, (u32)(0x8000000000000000ULL - p), (u32)(2 * (0x8000000000000000ULL - p))};
+template <class FT>
+__global__ void field_ops_kernel(int op, const u64* a, const u64* b, u64* r, u64 n, const FT F) {
   const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   // all threads stay alive: op 6 uses block-wide barriers
-  const R x = mkR(i < n ? a[i] : 1), y = mkR(i < n ? b[i] : 1);
+  const R x = fin(mkR(i < n ? a[i] : 1), F), y = fin(mkR(i < n ? b[i] : 1), F);
   __shared__ u64 scratch[64];
   u64 v = 0;
   switch (op) {
@@ -994,6 +1058,24 @@ __global__ void field_ops_kernel(int op, const u64* a, const u64* b, u64* r, u64
 }
 }  // namespace
 
+bool is_table_form(uint64_t p) {
+  const uint64_t two63 = 1ULL << 63;
+  return p < two63 && two63 - p < (1u << 15);
+}
+static Field host_field(uint64_t p) {
+  const u32 c = (u32)((1ULL << 63) - p);
+  return Field{p, c, 2 * c};
+}
+static FieldB host_field_b(uint64_t p) {
+  const ff63::Barrett b = ff63::make_barrett(p);
+  return FieldB{b.p, b.pn, b.pinv, b.k};
+}
+void barrett_constants(uint64_t p, uint64_t* pinv, uint32_t* shift) {
+  const ff63::Barrett b = ff63::make_barrett(p);
+  *pinv = b.pinv;
+  *shift = b.k;
+}
+
 // SMs of the calling thread's current device (grid sizes of the grid-stride kernels)
 static unsigned current_sm_count() {
   int dev = 0, n = 0;
@@ -1015,9 +1097,14 @@ cudaError_t launch_line_points(uint64_t* values, const uint64_t* t, const uint64
   if ((uint64_t)n_vars * n_points == 0) return cudaSuccess;
   const uint64_t want = (n_points / 2 + 255) / 256;
   const unsigned blocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)current_sm_count() * 16);
-  line_points_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<u64*>(values), reinterpret_cast<const u64*>(t),
-                                                 reinterpret_cast<const u64*>(a), reinterpret_cast<const u64*>(s),
-                                                 n_vars, n_points, stride, p);
+  if (is_table_form(p))
+    line_points_kernel<Field><<<blocks, 256, 0, stream>>>(reinterpret_cast<u64*>(values), reinterpret_cast<const u64*>(t),
+                                                          reinterpret_cast<const u64*>(a), reinterpret_cast<const u64*>(s),
+                                                          n_vars, n_points, stride, host_field(p));
+  else
+    line_points_kernel<FieldB><<<blocks, 256, 0, stream>>>(reinterpret_cast<u64*>(values), reinterpret_cast<const u64*>(t),
+                                                           reinterpret_cast<const u64*>(a), reinterpret_cast<const u64*>(s),
+                                                           n_vars, n_points, stride, host_field_b(p));
   return cudaGetLastError();
 }
 
@@ -1032,9 +1119,13 @@ cudaError_t launch_checksum(const uint64_t* out, uint64_t n_out, uint64_t n_poin
 cudaError_t launch_field_ops(int op, const uint64_t* a, const uint64_t* b, uint64_t* r, uint64_t n, uint64_t p,
                              cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
-  field_ops_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(op, reinterpret_cast<const u64*>(a),
-                                                                     reinterpret_cast<const u64*>(b),
-                                                                     reinterpret_cast<u64*>(r), n, p);
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (is_table_form(p))
+    field_ops_kernel<Field><<<blocks, 256, 0, stream>>>(op, reinterpret_cast<const u64*>(a), reinterpret_cast<const u64*>(b),
+                                                        reinterpret_cast<u64*>(r), n, host_field(p));
+  else
+    field_ops_kernel<FieldB><<<blocks, 256, 0, stream>>>(op, reinterpret_cast<const u64*>(a), reinterpret_cast<const u64*>(b),
+                                                         reinterpret_cast<u64*>(r), n, host_field_b(p));
   return cudaGetLastError();
 }
 

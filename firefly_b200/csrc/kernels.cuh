@@ -14,9 +14,12 @@ struct EvalParams {
   uint64_t n_points;
   uint64_t in_stride;
   uint64_t out_stride;
-  uint64_t p;                 // 2^63 - c
-  uint32_t c;
-  uint32_t d;                 // 2c
+  uint64_t p;                 // the prime
+  uint32_t c;                 // p = 2^63 - c ...
+  uint32_t d;                 // ... and 2c, if the prime has the form of FireFly's table (generic == 0)
+  uint32_t generic;           // any other odd prime below 2^63: Barrett arithmetic on canonical residues
+  uint32_t pshift;            // ... p << pshift is in [2^62, 2^63)
+  uint64_t pinv;              // ... floor((2^126 - 1) / (p << pshift))
   uint32_t n_slots;           // shared-memory slots per probe: spill slots from 0 up, temp slots from n_slots-1 down
   uint32_t n_instr;           // tape length without the terminators
   const uint32_t* chunk_bounds;  // device, n_chunks + 1 tape offsets at function boundaries (NULL: one chunk)
@@ -33,7 +36,11 @@ struct LaunchShape {
 };
 
 LaunchShape choose_shape(uint64_t n_points, uint32_t n_slots, int sm_count, int force_k, int force_threads,
-                         unsigned max_chunks, bool lean_ok);
+                         unsigned max_chunks, bool lean_ok, bool generic_field = false);
+// p = 2^63 - c with 0 < c < 2^15: the tuned arithmetic applies
+bool is_table_form(uint64_t p);
+// Barrett constants of any modulus below 2^63 (EvalParams::pinv, pshift)
+void barrett_constants(uint64_t p, uint64_t* pinv, uint32_t* shift);
 cudaError_t launch_eval(const EvalParams& prm, const LaunchShape& shape, cudaStream_t stream);
 
 // synthetic probe points, identical on host (bench/tests) and device:

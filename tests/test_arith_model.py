@@ -82,3 +82,14 @@ def test_block_inverse_tree_model():
                 for k in range(K):
                     v = a[w][l][k] % p
                     assert got[w][l][k] == (pow(v, p - 2, p) if v else 0), (K, W, w, l, k)
+
+
+def test_barrett_multiplication_model(tmp_path):
+    """ff63::mul_barrett -- the multiplication of the generic-modulus kernels (any odd prime below 2^63, reference:
+    FFInt::set_new_prime source/FFInt.cpp:344-353, mod_mul :356-369) -- compiled for the host from the same source the
+    device uses, against unsigned __int128 for 265 moduli of every bit length."""
+    exe = str(tmp_path / "barrett_model")
+    subprocess.run(["g++", "-O2", "-o", exe, os.path.join(HERE, "cmodel", "barrett_model.cpp")], check=True)
+    out = subprocess.run([exe, "2000000"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("ok ")
