@@ -111,6 +111,8 @@ def _load() -> C.CDLL:
         "ffgpu_host_free": (None, [C.c_void_p]),
         "ffgpu_set_launch": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
         "ffgpu_set_chunk": (C.c_int, [C.c_void_p, C.c_size_t]),
+        "ffgpu_set_coalesce": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t]),
+        "ffgpu_coalesce_stats": (None, [C.c_void_p, C.POINTER(C.c_uint64)]),
         "ffgpu_launch_count": (C.c_uint64, []),
         "ffgpu_fill_points": (
             C.c_int,
@@ -139,7 +141,7 @@ EXPORTS = [
     "ffgpu_n_primes", "ffgpu_prime", "ffgpu_eval", "ffgpu_eval_line", "ffgpu_eval_wire", "ffgpu_eval_device", "ffgpu_host_alloc", "ffgpu_host_free",
     "ffgpu_queue_create", "ffgpu_queue_destroy", "ffgpu_queue_push", "ffgpu_queue_push_many", "ffgpu_queue_push_line",
     "ffgpu_queue_pop", "ffgpu_queue_pending", "ffgpu_queue_stats", "ffgpu_queue_error",
-    "ffgpu_set_launch", "ffgpu_set_chunk", "ffgpu_launch_count", "ffgpu_fill_points", "ffgpu_checksum",
+    "ffgpu_set_launch", "ffgpu_set_coalesce", "ffgpu_coalesce_stats", "ffgpu_set_chunk", "ffgpu_launch_count", "ffgpu_fill_points", "ffgpu_checksum",
     "ffgpu_field_ops",
 ]
 
@@ -411,6 +413,16 @@ class GpuParser:
 
     def set_chunk(self, points: int = 0):
         lib.ffgpu_set_chunk(self.h, points)
+
+    def set_coalesce(self, enable: int = 1, max_points: int = 0):
+        """aggregator of concurrent small calls (include/ffgpu.h, ffgpu_set_coalesce)"""
+        if lib.ffgpu_set_coalesce(self.h, enable, max_points):
+            raise FFGpuError(last_error())
+
+    def coalesce_stats(self) -> dict:
+        s = (C.c_uint64 * 3)()
+        lib.ffgpu_coalesce_stats(self.h, s)
+        return {"launches": s[0], "calls": s[1], "points": s[2]}
 
 
 class ProbeQueue:

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -114,8 +115,39 @@ struct ffgpu_ctx {
   Slot slots[N_SLOTS];
 };
 
+// Aggregator of concurrent small calls (ffgpu_eval with a few points each, from many threads -- what Reconstructor's
+// thread pool does: get_job hands every pool thread a bunch of <= 128 points, reference: Reconstructor.hpp:3325-3477,
+// utils.cpp:305-330).  Callers deposit their points into the batch that is OPEN; the first one in becomes its leader,
+// waits until the batch before it has left the GPU -- every call that arrives meanwhile joins --, closes it, runs
+// ONE launch for everybody and wakes the others; each caller takes its slice.  A caller that is alone is its own
+// leader at once: nothing waits for company.  Two batches alternate (one fills while the other runs), each with
+// pinned, mapped staging and device buffers of its own; on a context with several GPUs the two use different ones.
+struct CoBatch {
+  uint64_t *h_in = nullptr, *h_out = nullptr, *d_in = nullptr;      // h_*: one pinned mapped allocation (h_in)
+  cudaStream_t stream = nullptr;
+  size_t cap = 0, n_vars = 0, n_out = 0;     // layout [row][cap] the buffers were allocated for
+  int dev = -1;                              // index into ctx->devs of d_in / stream
+  size_t count = 0;                          // points deposited
+  unsigned users = 0;                        // callers that still have to take their slice
+  bool has_leader = false, closed = false, done = false;
+  uint64_t seq = 0;
+  int rc = 0;
+  std::string err;
+};
+struct Coalescer {
+  std::mutex m;
+  std::condition_variable cv;
+  CoBatch b[2];
+  int open = 0;
+  bool busy = false;                         // a batch is on the GPU
+  uint64_t next_seq = 1, batches = 0, calls = 0, points = 0;
+};
+
 struct ffgpu_tape {
   ffgpu_ctx* ctx = nullptr;
+  std::unique_ptr<Coalescer> co{new Coalescer};
+  int coalesce = -1;                   // -1: FFGPU_COALESCE / default on
+  size_t coalesce_cap = 0;             // points per batch (0: automatic)
   ffgpu::Collection col;
   std::vector<ffgpu::Instr*> d_tape;   // per device
   std::vector<uint32_t*> d_chunks;     // per device: Collection::chunk_table
@@ -222,6 +254,22 @@ int copy_rows(uint64_t* dst, size_t dst_stride, const uint64_t* src, size_t src_
   for (size_t r = 0; r < rows; ++r)
     FF_CUDA(cudaMemcpyAsync(dst + r * dst_stride, src + r * src_stride, cnt * 8, kind, stream));
   return 0;
+}
+
+void free_batch(ffgpu_ctx* ctx, CoBatch& b) {
+  if (b.dev >= 0 && ctx) {
+    DeviceGuard guard(ctx->devs[b.dev].id);
+    if (b.stream) {
+      cudaStreamSynchronize(b.stream);
+      cudaStreamDestroy(b.stream);
+    }
+    if (b.d_in) cudaFree(b.d_in);
+    if (b.h_in) cudaFreeHost(b.h_in);
+  }
+  b.h_in = b.h_out = b.d_in = nullptr;
+  b.stream = nullptr;
+  b.cap = 0;
+  b.dev = -1;
 }
 
 int ensure(DevBuf& b, size_t need_in, size_t need_out) {
@@ -352,6 +400,8 @@ ffgpu_tape* ffgpu_tape_clone(const ffgpu_tape* t) {
   n->force_k = t->force_k;
   n->force_threads = t->force_threads;
   n->chunk = t->chunk;
+  n->coalesce = t->coalesce;
+  n->coalesce_cap = t->coalesce_cap;
   if (t->ctx) {
     n->d_tape.assign(t->ctx->devs.size(), nullptr);
     n->d_chunks.assign(t->ctx->devs.size(), nullptr);
@@ -363,6 +413,7 @@ ffgpu_tape* ffgpu_tape_clone(const ffgpu_tape* t) {
 
 void ffgpu_tape_destroy(ffgpu_tape* t) {
   if (!t) return;
+  for (CoBatch& b : t->co->b) free_batch(t->ctx, b);
   for (size_t g = 0; g < t->d_tape.size(); ++g) {
     if (!t->d_tape[g]) continue;
     DeviceGuard guard(t->ctx->devs[g].id);
@@ -505,6 +556,21 @@ int ffgpu_set_launch(ffgpu_tape* t, int k, int threads) {
   return 0;
 }
 
+int ffgpu_set_coalesce(ffgpu_tape* t, int enable, size_t max_points) {
+  if (!t) return fail("null tape");
+  if (max_points > (1u << 20)) return fail("at most 2^20 points per coalesced batch");
+  t->coalesce = enable < 0 ? -1 : (enable ? 1 : 0);
+  t->coalesce_cap = max_points;
+  return 0;
+}
+
+void ffgpu_coalesce_stats(const ffgpu_tape* t, uint64_t s[3]) {
+  std::lock_guard<std::mutex> lk(t->co->m);
+  s[0] = t->co->batches;
+  s[1] = t->co->calls;
+  s[2] = t->co->points;
+}
+
 int ffgpu_set_chunk(ffgpu_tape* t, size_t points) {
   t->chunk = points;
   return 0;
@@ -528,6 +594,113 @@ int ffgpu_eval_device(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_
 }  // extern "C"
 
 namespace {
+int coalesce_default() {
+  static const int v = [] {
+    const char* e = std::getenv("FFGPU_COALESCE");
+    return e && *e ? std::atoi(e) : 1;
+  }();
+  return v;
+}
+
+// (re)allocate the staging of one batch for `cap` points of the tape's current shape on device `dev`
+int prepare_batch(ffgpu_tape* t, CoBatch& b, size_t cap, int dev) {
+  const size_t n_vars = t->col.vars.size(), n_out = t->col.n_out;
+  if (b.cap == cap && b.n_vars == n_vars && b.n_out == n_out && b.dev == dev) return 0;
+  free_batch(t->ctx, b);
+  DeviceGuard guard(t->ctx->devs[dev].id);
+  const size_t w_in = std::max<size_t>(n_vars * cap, 1), w_out = std::max<size_t>(n_out * cap, 1);
+  FF_CUDA(cudaHostAlloc(&b.h_in, (w_in + w_out) * sizeof(uint64_t), cudaHostAllocPortable | cudaHostAllocMapped));
+  b.h_out = b.h_in + w_in;
+  FF_CUDA(cudaMalloc(&b.d_in, w_in * sizeof(uint64_t)));
+  FF_CUDA(cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
+  b.cap = cap;
+  b.n_vars = n_vars;
+  b.n_out = n_out;
+  b.dev = dev;
+  return 0;
+}
+
+// One small call through the aggregator (struct CoBatch).  Returns like ffgpu_eval.
+int coalesced_eval(ffgpu_tape* t, const uint64_t* values, size_t n_points, uint64_t* out) {
+  Coalescer& co = *t->co;
+  const size_t n_vars = t->col.vars.size(), n_out = t->col.n_out;
+  const size_t G = t->ctx->devs.size();
+  size_t cap = t->coalesce_cap ? t->coalesce_cap : std::min<size_t>(4096, std::max<size_t>(512, (size_t)(128 * 1024) / (n_vars + n_out + 1)));
+  cap = (std::max(cap, n_points) + 1) & ~(size_t)1;
+  std::unique_lock<std::mutex> lk(co.m);
+  CoBatch* B = nullptr;
+  for (;;) {
+    B = &co.b[co.open];
+    if (!B->closed && B->users == 0 && B->count == 0) {
+      // first caller of a fresh batch: make sure its buffers fit the tape's shape (it may have been rebuilt)
+      if (prepare_batch(t, *B, std::max(cap, B->cap), (int)((size_t)co.open % G))) return -1;
+      B->seq = co.next_seq++;
+      B->done = false;
+      B->has_leader = false;
+      B->rc = 0;
+    }
+    if (!B->closed && B->count + n_points <= B->cap) break;
+    co.cv.wait(lk);                       // the open batch is full or already on its way: wait for the next one
+  }
+  const size_t off = B->count;
+  B->count += n_points;
+  ++B->users;
+  ++co.calls;
+  co.points += n_points;
+  for (size_t v = 0; v < n_vars; ++v) std::memcpy(B->h_in + v * B->cap + off, values + v * n_points, n_points * sizeof(uint64_t));
+  const uint64_t my_seq = B->seq;
+  if (!B->has_leader) {
+    B->has_leader = true;
+    // leader: wait for the GPU (callers arriving meanwhile join this batch), then close and run it
+    co.cv.wait(lk, [&] { return !co.busy && co.b[co.open ^ 1].users == 0; });
+    B->closed = true;
+    co.busy = true;
+    co.open ^= 1;
+    CoBatch& nb = co.b[co.open];          // the other batch has been taken by all its callers: it fills next
+    nb.count = 0;
+    nb.closed = false;
+    nb.done = false;
+    nb.has_leader = false;
+    ++co.batches;
+    const size_t cnt = B->count, cnt_even = (cnt + 1) & ~(size_t)1;
+    lk.unlock();
+    co.cv.notify_all();
+    int prev = 0;
+    cudaGetDevice(&prev);
+    const int rc = [&]() -> int {
+      FF_CUDA(cudaSetDevice(t->ctx->devs[B->dev].id));
+      if (cnt_even != cnt)
+        for (size_t v = 0; v < n_vars; ++v) B->h_in[v * B->cap + cnt] = 0;       // the pad lane holds a residue
+      if (n_vars)
+        FF_CUDA(cudaMemcpy2DAsync(B->d_in, B->cap * 8, B->h_in, B->cap * 8, cnt_even * 8, n_vars, cudaMemcpyHostToDevice, B->stream));
+      // results are written by the kernel straight into the mapped pinned staging (no copy back)
+      if (launch(t, B->dev, B->d_in, B->cap, cnt_even, B->h_out, B->cap, B->stream)) return -1;
+      FF_CUDA(cudaStreamSynchronize(B->stream));
+      return 0;
+    }();
+    cudaSetDevice(prev);
+    lk.lock();
+    B->rc = rc;
+    if (rc) B->err = g_err;
+    B->done = true;
+    co.busy = false;
+    co.cv.notify_all();
+  } else {
+    co.cv.wait(lk, [&] { return B->done && B->seq == my_seq; });
+  }
+  const int rc = B->rc;
+  if (rc) g_err = B->err;
+  lk.unlock();
+  // the batch is not reused before every caller has left it (users), so the slice is read without the lock
+  if (rc == 0)
+    for (size_t f = 0; f < n_out; ++f) std::memcpy(out + f * n_points, B->h_out + f * B->cap + off, n_points * sizeof(uint64_t));
+  lk.lock();
+  --B->users;
+  lk.unlock();
+  co.cv.notify_all();
+  return rc;
+}
+
 // Host-buffer evaluation shared by ffgpu_eval (values given) and ffgpu_eval_line (values == NULL: the
 // points are built on the device from t[], a[], s[]).
 int eval_host(ffgpu_tape* t, const uint64_t* values, const uint64_t* line_a, const uint64_t* line_s,
@@ -540,13 +713,18 @@ int eval_host(ffgpu_tape* t, const uint64_t* values, const uint64_t* line_a, con
   ffgpu_ctx* ctx = t->ctx;
   const size_t G = ctx->devs.size();
   const size_t n_vars = t->col.vars.size(), n_out = t->col.n_out;
+  // Small calls -- the Reconstructor's bunches of 1..128 points (Reconstructor.hpp:3330-3354) -- are latency
+  // bound; concurrent ones share a launch (coalesced_eval)
+  constexpr size_t SMALL_WORDS = 32 * 1024;            // 256 KB in + out
+  const bool small = values && (n_vars + n_out) * (n_points + 1) <= SMALL_WORDS;
+  if (small && (t->coalesce >= 0 ? t->coalesce : coalesce_default()) && n_vars + n_out > 0)
+    return coalesced_eval(t, values, n_points, out);
   Slot& slot = ctx->slots[thread_id % N_SLOTS];
   std::lock_guard<std::mutex> lock(slot.mtx);
 
-  // Small calls -- the Reconstructor's bunches of 1..128 points (Reconstructor.hpp:3330-3354) -- are latency
-  // bound: one GPU, one contiguous pinned copy each way instead of strided copies from pageable memory.
-  constexpr size_t SMALL_WORDS = 32 * 1024;            // 256 KB in + out
-  if (values && (n_vars + n_out) * (n_points + 1) <= SMALL_WORDS) {
+  // without the aggregator: one GPU, one contiguous pinned copy each way instead of strided copies from pageable
+  // memory, one launch per call
+  if (small) {
     int prev = 0;
     cudaGetDevice(&prev);
     const int rc_small = [&]() -> int {

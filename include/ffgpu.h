@@ -201,6 +201,14 @@ const char* ffgpu_queue_error(ffgpu_queue*);
 /* ---- tuning / measurement ----------------------------------------------------------------- */
 /* probes per thread (1, 2, 4, 8; 0 = automatic) and threads per block (128, 256, 512; 0 = automatic) */
 int ffgpu_set_launch(ffgpu_tape*, int probes_per_thread, int threads_per_block);
+/* Aggregator of concurrent small ffgpu_eval calls (a few hundred points at most per call, many caller threads -- the
+ * Reconstructor's thread pool, Reconstructor.hpp:3325-3477 with bunches from utils.cpp:305-330): calls that arrive while
+ * the batch before them is on the GPU share ONE launch; a lone caller is served at once.  enable: 1 on (default), 0 off
+ * (every call its own launch), -1 environment FFGPU_COALESCE / default.  max_points: points per shared launch (0 =
+ * automatic, 512..4096 by the collection's width) -- what GpuBlackBox::set_bunch_size steers.  The values are the same
+ * either way.  Stats: launches shared so far, calls served by them, points. */
+int ffgpu_set_coalesce(ffgpu_tape*, int enable, size_t max_points);
+void ffgpu_coalesce_stats(const ffgpu_tape*, uint64_t stats[3]);
 /* points per pipelined chunk of ffgpu_eval (0 = automatic) */
 int ffgpu_set_chunk(ffgpu_tape*, size_t points);
 /* kernels launched by this library in this process so far */

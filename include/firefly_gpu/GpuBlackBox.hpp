@@ -23,6 +23,7 @@
 // Errors follow the reference's convention for this path: ERROR_MSG + std::exit(EXIT_FAILURE)
 // (ShuntingYardParser.hpp:454-459).
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <functional>
@@ -91,10 +92,17 @@ class GpuBlackBox : public BlackBoxBase<GpuBlackBox> {
     if (ffgpu_set_prime(tape_, FFInt::p)) die(ffgpu_last_error());
   }
 
-  // The bunch size is a Reconstructor constructor argument in 2.0.3 (Reconstructor.hpp:73); the GPU
-  // evaluator accepts any batch, so this only records the hint.
-  void set_bunch_size(uint32_t bunch) { bunch_hint_ = bunch; }
+  // The bunch size is a Reconstructor constructor argument in 2.0.3 (Reconstructor.hpp:73): every pool thread calls
+  // with up to `bunch` points.  The GPU evaluator accepts any batch; concurrent small calls share a launch
+  // (ffgpu_set_coalesce), and the bunch size sets how many points such a shared launch may hold -- room for 32
+  // callers' bunches, at least 512 points.
+  void set_bunch_size(uint32_t bunch) {
+    bunch_hint_ = bunch ? bunch : 1;
+    if (ffgpu_set_coalesce(tape_, -1, std::max<size_t>(512, (size_t)32 * bunch_hint_))) die(ffgpu_last_error());
+  }
   uint32_t bunch_size() const { return bunch_hint_; }
+  // launches that the aggregator shared among callers so far, calls they served, points
+  void coalesce_stats(uint64_t stats[3]) const { ffgpu_coalesce_stats(tape_, stats); }
 
   size_t n_vars() const { return n_vars_; }
   size_t n_out() const { return n_out_; }

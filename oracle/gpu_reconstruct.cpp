@@ -7,8 +7,14 @@
 // term by term.  Built by `make -C oracle ref` into oracle/_ref/ against libfirefly_ref.so and
 // firefly_b200/lib/libffgpu.so; run on the GPU box by tests/test_gpu_reconstruct.py.
 //
+// It also reports, for both runs, the quantity the reference itself prints as "Average time of the black-box probe"
+// (Reconstructor.hpp:3381-3411, 3438-3472: wall time around every bb.eval call, summed, divided by the number of
+// probes), measured the same way by a wrapper around each black box.
+//
 //   gpu_reconstruct <file.m> <bunch> <threads> <var> [<var> ...]
 //   exit 0 = identical, 1 = different, 2 = usage
+#include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -27,6 +33,27 @@ class CpuBlackBox : public BlackBoxBase<CpuBlackBox> {
   inline void prime_changed() { par.precompute_tokens(); }
  private:
   ShuntingYardParser par;
+};
+// wall time around every call of the wrapped black box and the probes it evaluated (lanes of the bunch type)
+template <typename Inner>
+class Timed : public BlackBoxBase<Timed<Inner>> {
+ public:
+  explicit Timed(Inner& inner_) : inner(inner_) {}
+  template <typename FFIntTemp>
+  std::vector<FFIntTemp> operator()(const std::vector<FFIntTemp>& values) {
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    std::vector<FFIntTemp> r = inner(values);
+    const auto t1 = std::chrono::high_resolution_clock::now();
+    ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count());
+    probes.fetch_add(sizeof(FFIntTemp) / sizeof(FFInt));
+    calls.fetch_add(1);
+    return r;
+  }
+  inline void prime_changed() { inner.prime_changed(); }
+  double average_black_box_time() const { return probes.load() ? 1e-9 * (double)ns.load() / (double)probes.load() : 0.; }
+  std::atomic<uint64_t> ns{0}, probes{0}, calls{0};
+ private:
+  Inner& inner;
 };
 }  // namespace firefly
 
@@ -61,12 +88,27 @@ int main(int argc, char** argv) {
 
   FFInt::set_new_prime(primes()[0]);
   ShuntingYardParser par(file, vars);
-  CpuBlackBox cpu(par);
+  CpuBlackBox cpu_bb(par);
+  Timed<CpuBlackBox> cpu(cpu_bb);
+  const auto c0 = std::chrono::steady_clock::now();
   const std::vector<std::string> want = reconstruct_all(cpu, n, threads, bunch, vars, &pc);
+  const double cpu_wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count();
 
   FFInt::set_new_prime(primes()[0]);
-  GpuBlackBox gpu(file, vars);
+  GpuBlackBox gpu_bb(file, vars);
+  gpu_bb.set_bunch_size(bunch);
+  Timed<GpuBlackBox> gpu(gpu_bb);
+  const auto g0 = std::chrono::steady_clock::now();
   const std::vector<std::string> got = reconstruct_all(gpu, n, threads, bunch, vars, &pg);
+  const double gpu_wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - g0).count();
+  uint64_t co[3];
+  gpu_bb.coalesce_stats(co);
+  std::printf("black box  cpu: %llu probes in %llu calls, average time of the black-box probe %.3e s, reconstruct() %.2f s\n",
+              (unsigned long long)cpu.probes.load(), (unsigned long long)cpu.calls.load(), cpu.average_black_box_time(), cpu_wall);
+  std::printf("black box  gpu: %llu probes in %llu calls, average time of the black-box probe %.3e s, reconstruct() %.2f s, "
+              "%llu shared launches for %llu calls\n",
+              (unsigned long long)gpu.probes.load(), (unsigned long long)gpu.calls.load(), gpu.average_black_box_time(), gpu_wall,
+              (unsigned long long)co[0], (unsigned long long)co[1]);
 
   int bad = want.size() != got.size();
   for (size_t i = 0; i < want.size() && i < got.size(); ++i) {

@@ -276,29 +276,62 @@ def test_check_is_equal_and_prime_change(ctx, oracle):
         assert np.array_equal(par.evaluate_pre(pts), want)
 
 
-def test_concurrent_callers(ctx, oracle):
-    """Reconstructor calls the black box from thr_n threads at once (Reconstructor.hpp:2981)."""
+@pytest.mark.parametrize("coalesce,cap", [(1, 0), (1, 130), (0, 0)])
+def test_concurrent_callers(ctx, oracle, coalesce, cap):
+    """Reconstructor calls the black box from thr_n threads at once (Reconstructor.hpp:2981), each with a bunch of at
+    most 128 points (utils.cpp:305-330).  With the aggregator on, calls that arrive while a launch is in flight share
+    the next one: every caller must still get exactly its own values -- also when the shared batch is too small for
+    all of them (cap 130: two bunches of 77 do not fit, the second waits for the next batch)."""
     g = load_golden("s_y_4_v")
     par = ff.GpuParser(ctx, g["functions"], g["vars"])
     par.set_prime(P0)
+    par.set_coalesce(coalesce, cap)
     op = oracle.parse(g["functions"], g["vars"], P0)
     errs = []
+    n_threads, n_iter = 32, 25
+    l0 = ff.launch_count()
 
     def worker(tid):
         try:
-            for it in range(20):
-                n = [1, 4, 128, 77][it % 4]
+            for it in range(n_iter):
+                n = [1, 4, 128, 77, 2, 33][(it + tid) % 6]
                 pts = ff.synthetic_points(4, n, P0, seed=1000 * tid + it)
+                if n > 2:
+                    pts[:, 1] = 0                  # a zero divisor in somebody's slice must stay in that slice
                 got = par.evaluate_pre(pts, thread_id=tid)
                 if not np.array_equal(got, op.eval(pts)):
                     errs.append((tid, it))
         except Exception as e:  # pragma: no cover
             errs.append((tid, repr(e)))
 
-    ts = [threading.Thread(target=worker, args=(t,)) for t in range(12)]
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert not errs, errs
+    st = par.coalesce_stats()
+    launches = ff.launch_count() - l0
+    if coalesce:
+        assert st["calls"] == n_threads * n_iter and st["launches"] == launches
+        assert launches < n_threads * n_iter, "32 concurrent callers never shared a launch"
+    else:
+        assert st["calls"] == 0 and launches == n_threads * n_iter
+    par.close()
+
+
+def test_aggregator_follows_a_rebuilt_collection(ctx, oracle):
+    """add_otf / trim change the number of outputs: the aggregator's staging is laid out again for the new shape"""
+    funs, vars_ = ["x+y", "x*y/(x-y)"], ["x", "y"]
+    par = ff.GpuParser(ctx, funs, vars_)
+    par.set_prime(P0)
+    pts = ff.synthetic_points(2, 17, P0, seed=3)
+    assert np.array_equal(par.evaluate_pre(pts), oracle.parse(funs, vars_, P0).eval(pts))
+    par.add_otf("x^3-y")
+    par.set_prime(P0)
+    funs2 = funs + ["x^3-y"]
+    for n in (17, 200):
+        pts = ff.synthetic_points(2, n, P0, seed=n)
+        assert np.array_equal(par.evaluate_pre(pts), oracle.parse(funs2, vars_, P0).eval(pts))
+    par.close()
 
 
 # ---- full-size properties ----------------------------------------------------------------------------

@@ -22,9 +22,10 @@ CASES = [
     ("f1", 64, 4),
     ("factors3", 16, 4),
 ]
-# configs[4]: the full f4 reconstruction (106 668 probes, ~2.5 minutes for the CPU and GPU runs together; measured
-# identical on B200, profiles/r01_cfg5_f4_reconstruct.log).  Too slow for the default suite: FFGPU_SLOW_TESTS=1.
-if os.environ.get("FFGPU_SLOW_TESTS"):
+# configs[4]: the full f4 reconstruction (106 668 probes, about 2.5 minutes for the CPU and the GPU run together --
+# the interpolation is sequential host work).  Runs wherever the box has the cores the reference's thread pool is
+# given here; FFGPU_SKIP_SLOW_TESTS=1 leaves it out.
+if (os.cpu_count() or 1) >= 8 and not os.environ.get("FFGPU_SKIP_SLOW_TESTS"):
     CASES.append(("f4", 128, 16))
 
 
@@ -42,6 +43,19 @@ def test_reconstruction_identical(tmp_path, name, bunch, threads):
     # the GPU black box really ran on the GPU
     launches = int(r.stdout.strip().split()[-1])
     assert launches > 0
+    # the reference's own "average time of the black-box probe" for both black boxes, kept for the record
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("black box")]
+    assert len(lines) == 2, r.stdout[-2000:]
+    print("\n".join([f"[{name} bunch {bunch} threads {threads}] " + ln for ln in lines]))
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, "reconstruct_black_box_times.log"), "a") as log:
+        for ln in lines:
+            log.write(f"{name} bunch={bunch} threads={threads} launches={launches} {ln}\n")
+    if name == "f4":
+        # 16 pool threads with bunches of up to 128 points: concurrent calls share launches (ffgpu_set_coalesce);
+        # round 1 needed 28 767 launches for this run
+        assert launches * 5 <= 28767, f"{launches} launches: the aggregator did not coalesce the pool's calls"
 
 
 def test_reference_recorded_probes(ctx, tmp_path):
