@@ -484,16 +484,4 @@ def launch_count() -> int:
     return lib.ffgpu_launch_count()
 
 
-def synthetic_points(n_vars: int, n_points: int, p: int, seed: int = 0x4D595DF4D0F33173, first_point: int = 0,
-                     total_points: Optional[int] = None) -> np.ndarray:
-    """Host twin of ffgpu_fill_points: x[v][j] = 1 + splitmix64(seed + v*total + first + j) mod (p-1)."""
-    total = n_points if total_points is None else total_points
-    with np.errstate(over="ignore"):
-        v = np.arange(n_vars, dtype=np.uint64).reshape(-1, 1)
-        j = np.arange(n_points, dtype=np.uint64).reshape(1, -1)
-        z = np.uint64(seed) + v * np.uint64(total) + np.uint64(first_point) + j
-        z = z + np.uint64(0x9E3779B97F4A7C15)
-        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-        z = z ^ (z >> np.uint64(31))
-        return np.uint64(1) + z % np.uint64(p - 1)
+from .points import synthetic_points  # noqa: E402,F401  (pure numpy; kept importable on its own)

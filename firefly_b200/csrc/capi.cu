@@ -19,6 +19,7 @@
 #include <mutex>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ffgpu.h"
@@ -131,6 +132,7 @@ struct CoBatch {
   unsigned users = 0;                        // callers that still have to take their slice
   bool has_leader = false, closed = false, done = false;
   uint64_t seq = 0;
+  std::atomic<uint64_t> done_seq{0};         // = seq once the batch's results are in h_out (followers spin on it)
   int rc = 0;
   std::string err;
 };
@@ -594,6 +596,14 @@ int ffgpu_eval_device(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_
 }  // extern "C"
 
 namespace {
+inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#else
+  std::this_thread::yield();
+#endif
+}
+
 int coalesce_default() {
   static const int v = [] {
     const char* e = std::getenv("FFGPU_COALESCE");
@@ -683,9 +693,15 @@ int coalesced_eval(ffgpu_tape* t, const uint64_t* values, size_t n_points, uint6
     B->rc = rc;
     if (rc) B->err = g_err;
     B->done = true;
+    B->done_seq.store(my_seq, std::memory_order_release);
     co.busy = false;
     co.cv.notify_all();
   } else {
+    // a launch takes tens of microseconds, a sleeping thread longer than that to wake up: look for the result a few
+    // thousand times before going to sleep on the condition variable
+    lk.unlock();
+    for (int spin = 0; spin < 20000 && B->done_seq.load(std::memory_order_acquire) != my_seq; ++spin) cpu_relax();
+    lk.lock();
     co.cv.wait(lk, [&] { return B->done && B->seq == my_seq; });
   }
   const int rc = B->rc;
