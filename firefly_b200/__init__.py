@@ -42,6 +42,7 @@ CHECK_IS_EQUAL = 1
 NO_CSE = 2
 NO_FUSE = 4
 NO_CROSS = 16
+NO_TABLE = 32
 ADD_PLAIN, ADD_VALIDATE, ADD_NO_DUPLICATES = 1, 2, 4
 
 
@@ -78,6 +79,8 @@ def _load() -> C.CDLL:
         "ffgpu_cse_fallbacks": (C.c_size_t, [C.c_void_p]),
         "ffgpu_n_structural_duplicates": (C.c_size_t, [C.c_void_p]),
         "ffgpu_n_shared_denominators": (C.c_size_t, [C.c_void_p]),
+        "ffgpu_n_table_rows": (C.c_size_t, [C.c_void_p]),
+        "ffgpu_get_table_tape": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t]),
         "ffgpu_rpn": (C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
         "ffgpu_get_tape": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t]),
         "ffgpu_work": (None, [C.c_void_p, u64p]),
@@ -136,7 +139,7 @@ lib = _load()
 EXPORTS = [
     "ffgpu_create", "ffgpu_destroy", "ffgpu_n_devices", "ffgpu_last_error", "ffgpu_compile", "ffgpu_compile_text",
     "ffgpu_compile_file", "ffgpu_tape_clone", "ffgpu_tape_destroy", "ffgpu_n_vars", "ffgpu_n_functions", "ffgpu_n_out", "ffgpu_n_instr",
-    "ffgpu_stack_depth", "ffgpu_n_temps", "ffgpu_n_slots", "ffgpu_cse_fallbacks", "ffgpu_n_structural_duplicates", "ffgpu_n_shared_denominators", "ffgpu_rpn", "ffgpu_get_tape", "ffgpu_work", "ffgpu_tape_work", "ffgpu_set_factors", "ffgpu_set_prime", "ffgpu_get_prime",
+    "ffgpu_stack_depth", "ffgpu_n_temps", "ffgpu_n_slots", "ffgpu_cse_fallbacks", "ffgpu_n_structural_duplicates", "ffgpu_n_shared_denominators", "ffgpu_n_table_rows", "ffgpu_get_table_tape", "ffgpu_rpn", "ffgpu_get_tape", "ffgpu_work", "ffgpu_tape_work", "ffgpu_set_factors", "ffgpu_set_prime", "ffgpu_get_prime",
     "ffgpu_add_function", "ffgpu_add_function_rpn", "ffgpu_trim", "ffgpu_is_stale",
     "ffgpu_n_primes", "ffgpu_prime", "ffgpu_eval", "ffgpu_eval_line", "ffgpu_eval_wire", "ffgpu_eval_device", "ffgpu_host_alloc", "ffgpu_host_free",
     "ffgpu_queue_create", "ffgpu_queue_destroy", "ffgpu_queue_push", "ffgpu_queue_push_many", "ffgpu_queue_push_line",
@@ -201,10 +204,10 @@ class GpuParser:
 
     def __init__(self, ctx: Optional[Context], functions=None, vars: Sequence[str] = (), check_is_equal: bool = False,
                  *, file: Optional[str] = None, text: Optional[str] = None, cse: bool = True,
-                 temps: int = 0, fuse: bool = True, cross: bool = True):
+                 temps: int = 0, fuse: bool = True, cross: bool = True, table: bool = True):
         self.ctx = ctx
         ch = ctx.h if ctx is not None else None
-        flags = (CHECK_IS_EQUAL if check_is_equal else 0) | (0 if cse else NO_CSE) | (0 if fuse else NO_FUSE) | (0 if cross else NO_CROSS) | ((temps & 15) << 8)
+        flags = (CHECK_IS_EQUAL if check_is_equal else 0) | (0 if cse else NO_CSE) | (0 if fuse else NO_FUSE) | (0 if cross else NO_CROSS) | (0 if table else NO_TABLE) | ((temps & 15) << 8)
         v = _strs(vars)
         if file is not None:
             self.h = lib.ffgpu_compile_file(ch, file.encode(), v, len(vars), flags)
@@ -237,6 +240,18 @@ class GpuParser:
         arr = np.zeros(n, dtype=INSTR_DTYPE)
         lib.ffgpu_get_tape(self.h, arr.ctypes.data, n)
         return arr
+
+    def table_tape(self) -> np.ndarray:
+        """the tape of the shared rows (output r = row r = variable n_vars + r of tape()); empty if there are none"""
+        n = lib.ffgpu_get_table_tape(self.h, None, 0)
+        arr = np.zeros(n, dtype=INSTR_DTYPE)
+        if n:
+            lib.ffgpu_get_table_tape(self.h, arr.ctypes.data, n)
+        return arr
+
+    @property
+    def n_table_rows(self) -> int:
+        return lib.ffgpu_n_table_rows(self.h)
 
     def work(self) -> dict:
         w = (C.c_uint64 * 5)()

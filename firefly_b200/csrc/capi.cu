@@ -153,6 +153,9 @@ struct ffgpu_tape {
   ffgpu::Collection col;
   std::vector<ffgpu::Instr*> d_tape;   // per device
   std::vector<uint32_t*> d_chunks;     // per device: Collection::chunk_table
+  std::vector<ffgpu::Instr*> d_pre;    // per device: the tape of the shared rows (Collection::pre), if the collection has any
+  std::vector<uint32_t*> d_pre_chunks;
+  bool pre_needs_generic = true;
   int force_k = 0, force_threads = 0;
   size_t chunk = 0;
   bool needs_generic = true;           // the resolved tape has instructions without a fast dispatch code
@@ -178,6 +181,8 @@ ffgpu_tape* finish_compile(ffgpu_ctx* ctx, std::unique_ptr<ffgpu_tape> t, bool o
   if (ctx) {
     t->d_tape.assign(ctx->devs.size(), nullptr);
     t->d_chunks.assign(ctx->devs.size(), nullptr);
+    t->d_pre.assign(ctx->devs.size(), nullptr);
+    t->d_pre_chunks.assign(ctx->devs.size(), nullptr);
   }
   return t.release();
 }
@@ -189,11 +194,12 @@ std::vector<std::string> to_vec(const char* const* s, size_t n) {
   return v;
 }
 
-int launch(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, size_t n_points, uint64_t* d_out,
-           size_t out_stride, cudaStream_t stream) {
-  const ffgpu::Collection& c = t->col;
+// one kernel launch: collection `c` (tape and chunk table on device g) at n_points points
+int launch_one(ffgpu_tape* t, const ffgpu::Collection& c, const ffgpu::Instr* d_tape, const uint32_t* d_chunks,
+               bool needs_generic, int g, const uint64_t* d_values, size_t in_stride, size_t n_points, uint64_t* d_out,
+               size_t out_stride, const uint64_t* d_table, size_t table_stride, cudaStream_t stream) {
   ffgpu::EvalParams prm;
-  prm.tape = t->d_tape[g];
+  prm.tape = d_tape;
   prm.values = d_values;
   prm.out = d_out;
   prm.n_points = n_points;
@@ -208,18 +214,52 @@ int launch(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, siz
   if (prm.generic) ffgpu::barrett_constants(c.prime, &prm.pinv, &prm.pshift);
   prm.n_slots = c.n_slots;
   prm.n_instr = (uint32_t)(c.tape.size() - 2);
+  prm.n_vars = (uint32_t)c.vars.size();
+  prm.table = d_table;
+  prm.table_stride = table_stride;
   const ffgpu::LaunchShape sh = ffgpu::choose_shape(n_points, c.n_slots, t->ctx->devs[g].sm_count, t->force_k,
-                                                    t->force_threads, c.max_chunks, !t->needs_generic, prm.generic != 0);
+                                                    t->force_threads, c.max_chunks, !needs_generic, prm.generic != 0);
   prm.chunk_bounds = nullptr;
   if (sh.chunks > 1) {
     unsigned idx = 0;
     while ((1u << idx) < sh.chunks) ++idx;
-    prm.chunk_bounds = t->d_chunks[g] + c.chunk_table_off[idx];
+    prm.chunk_bounds = d_chunks + c.chunk_table_off[idx];
   }
   cudaError_t e = ffgpu::launch_eval(prm, sh, stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_eval");
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
+}
+
+// Evaluate the collection on device g.  A collection with shared rows (Collection::pre) runs two kernels per range of
+// points: the rows' own tape writes them into a stream-ordered scratch allocation, the functions' tape reads them as
+// extra variables.  The ranges are sized so that the rows stay L2 resident between the two.
+int launch(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, size_t n_points, uint64_t* d_out,
+           size_t out_stride, cudaStream_t stream) {
+  const ffgpu::Collection& c = t->col;
+  if (c.pre.empty())
+    return launch_one(t, c, t->d_tape[g], t->d_chunks[g], t->needs_generic, g, d_values, in_stride, n_points, d_out,
+                      out_stride, nullptr, 0, stream);
+  const ffgpu::Collection& pc = c.pre[0];
+  const size_t rows = pc.n_out;
+  constexpr size_t BUDGET = 96u << 20;
+  size_t sub = n_points;
+  if (rows * n_points * 8 > BUDGET) sub = std::max<size_t>((BUDGET / (rows * 8)) & ~(size_t)2047, 16384);
+  const size_t stride = (std::min(sub, n_points) + 1) & ~(size_t)1;
+  uint64_t* tab = nullptr;
+  FF_CUDA(cudaMallocAsync(&tab, rows * stride * 8, stream));
+  int rc = 0;
+  for (size_t off = 0; off < n_points && !rc; off += sub) {
+    const size_t cnt = std::min(sub, n_points - off);
+    rc = launch_one(t, pc, t->d_pre[g], t->d_pre_chunks[g], t->pre_needs_generic, g, d_values + off, in_stride, cnt, tab,
+                    stride, nullptr, 0, stream);
+    if (!rc)
+      rc = launch_one(t, c, t->d_tape[g], t->d_chunks[g], t->needs_generic, g, d_values + off, in_stride, cnt,
+                      d_out + off, out_stride, tab, stride, stream);
+  }
+  const cudaError_t e = cudaFreeAsync(tab, stream);
+  if (!rc && e != cudaSuccess) return cuda_fail(e, "cudaFreeAsync");
+  return rc;
 }
 
 // small-call path: how much of the transfer the kernel does itself (FFGPU_SMALL_ZERO_COPY = 0 | 1 | 2)
@@ -238,8 +278,12 @@ void drop_device_copies(ffgpu_tape* t) {
     cudaDeviceSynchronize();
     if (t->d_tape[g]) cudaFree(t->d_tape[g]);
     if (t->d_chunks[g]) cudaFree(t->d_chunks[g]);
+    if (t->d_pre[g]) cudaFree(t->d_pre[g]);
+    if (t->d_pre_chunks[g]) cudaFree(t->d_pre_chunks[g]);
     t->d_tape[g] = nullptr;
     t->d_chunks[g] = nullptr;
+    t->d_pre[g] = nullptr;
+    t->d_pre_chunks[g] = nullptr;
   }
 }
 
@@ -327,6 +371,13 @@ ffgpu_ctx* ffgpu_create(const int* device_ids, int n_devices) {
     d.id = id;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, id) == cudaSuccess) d.sm_count = prop.multiProcessorCount;
+    // the scratch rows of collections with shared sub-expressions are stream-ordered allocations: keep the pool's
+    // memory instead of returning it to the driver at every synchronisation
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, id) == cudaSuccess) {
+      uint64_t keep = ~0ULL;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     ctx->devs.push_back(d);
   }
   for (auto& s : ctx->slots) s.dev.resize(ctx->devs.size());
@@ -361,6 +412,7 @@ ffgpu_tape* ffgpu_compile(ffgpu_ctx* ctx, const char* const* functions, size_t n
   t->col.enable_cse = !(flags & FFGPU_NO_CSE);
   t->col.enable_fuse = !(flags & FFGPU_NO_FUSE);
   t->col.enable_cross = !(flags & FFGPU_NO_CROSS);
+  t->col.enable_table = !(flags & FFGPU_NO_TABLE) && !std::getenv("FFGPU_NO_TABLE");
   t->col.temp_budget = (int)((flags >> FFGPU_TEMPS_SHIFT) & 15u);
   const bool ok = t->col.compile_strings(to_vec(functions, n_functions), to_vec(vars, n_vars),
                                          (flags & FFGPU_CHECK_IS_EQUAL) != 0, err);
@@ -374,6 +426,7 @@ ffgpu_tape* ffgpu_compile_text(ffgpu_ctx* ctx, const char* text, const char* con
   t->col.enable_cse = !(flags & FFGPU_NO_CSE);
   t->col.enable_fuse = !(flags & FFGPU_NO_FUSE);
   t->col.enable_cross = !(flags & FFGPU_NO_CROSS);
+  t->col.enable_table = !(flags & FFGPU_NO_TABLE) && !std::getenv("FFGPU_NO_TABLE");
   t->col.temp_budget = (int)((flags >> FFGPU_TEMPS_SHIFT) & 15u);
   const bool ok = t->col.compile_text(text ? text : "", to_vec(vars, n_vars), (flags & FFGPU_CHECK_IS_EQUAL) != 0, err);
   return finish_compile(ctx, std::move(t), ok, err);
@@ -407,6 +460,8 @@ ffgpu_tape* ffgpu_tape_clone(const ffgpu_tape* t) {
   if (t->ctx) {
     n->d_tape.assign(t->ctx->devs.size(), nullptr);
     n->d_chunks.assign(t->ctx->devs.size(), nullptr);
+    n->d_pre.assign(t->ctx->devs.size(), nullptr);
+    n->d_pre_chunks.assign(t->ctx->devs.size(), nullptr);
   }
   // the copy gets device buffers of its own, for the prime the original is resolved for
   if (t->col.prime && !t->col.stale && ffgpu_set_prime(n.get(), t->col.prime)) return nullptr;
@@ -422,6 +477,8 @@ void ffgpu_tape_destroy(ffgpu_tape* t) {
     cudaDeviceSynchronize();
     cudaFree(t->d_tape[g]);
     if (t->d_chunks[g]) cudaFree(t->d_chunks[g]);
+    if (t->d_pre[g]) cudaFree(t->d_pre[g]);
+    if (t->d_pre_chunks[g]) cudaFree(t->d_pre_chunks[g]);
   }
   delete t;
 }
@@ -436,6 +493,15 @@ size_t ffgpu_n_slots(const ffgpu_tape* t) { return t->col.n_slots; }
 size_t ffgpu_cse_fallbacks(const ffgpu_tape* t) { return t->col.cse_fallbacks; }
 size_t ffgpu_n_structural_duplicates(const ffgpu_tape* t) { return t->col.n_structural_duplicates; }
 size_t ffgpu_n_shared_denominators(const ffgpu_tape* t) { return t->col.n_shared_denominators; }
+
+size_t ffgpu_n_table_rows(const ffgpu_tape* t) { return t->col.n_table_rows; }
+size_t ffgpu_get_table_tape(const ffgpu_tape* t, void* buf, size_t cap) {
+  if (t->col.pre.empty()) return 0;
+  const std::vector<ffgpu::Instr>& tp = t->col.pre[0].tape;
+  const size_t n = std::min(cap, tp.size());
+  if (buf && n) std::memcpy(buf, tp.data(), n * sizeof(ffgpu::Instr));
+  return tp.size();
+}
 
 size_t ffgpu_rpn(const ffgpu_tape* t, size_t i, char* buf, size_t cap) {
   if (i >= t->col.functions.size()) return 0;
@@ -491,6 +557,9 @@ int ffgpu_set_prime(ffgpu_tape* t, uint64_t p) {
   if (rebuilt) drop_device_copies(t);
   t->needs_generic = false;
   for (const ffgpu::Instr& in : t->col.tape) t->needs_generic |= in.fast == ffgpu::FX_GENERIC && in.op != ffgpu::OP_HALT;
+  t->pre_needs_generic = false;
+  if (!t->col.pre.empty())
+    for (const ffgpu::Instr& in : t->col.pre[0].tape) t->pre_needs_generic |= in.fast == ffgpu::FX_GENERIC && in.op != ffgpu::OP_HALT;
   const size_t bytes = t->col.tape.size() * sizeof(ffgpu::Instr);
   for (size_t g = 0; t->ctx && g < t->ctx->devs.size(); ++g) {
     DeviceGuard guard(t->ctx->devs[g].id);
@@ -503,6 +572,17 @@ int ffgpu_set_prime(ffgpu_tape* t, uint64_t p) {
                          cudaMemcpyHostToDevice));
     }
     FF_CUDA(cudaMemcpy(t->d_tape[g], t->col.tape.data(), bytes, cudaMemcpyHostToDevice));
+    if (!t->col.pre.empty()) {
+      const ffgpu::Collection& pc = t->col.pre[0];
+      const size_t pbytes = pc.tape.size() * sizeof(ffgpu::Instr);
+      if (!t->d_pre[g]) FF_CUDA(cudaMalloc(&t->d_pre[g], pbytes));
+      if (!t->d_pre_chunks[g]) {
+        FF_CUDA(cudaMalloc(&t->d_pre_chunks[g], pc.chunk_table.size() * sizeof(uint32_t)));
+        FF_CUDA(cudaMemcpy(t->d_pre_chunks[g], pc.chunk_table.data(), pc.chunk_table.size() * sizeof(uint32_t),
+                           cudaMemcpyHostToDevice));
+      }
+      FF_CUDA(cudaMemcpy(t->d_pre[g], pc.tape.data(), pbytes, cudaMemcpyHostToDevice));
+    }
   }
   return 0;
 }
@@ -551,8 +631,8 @@ int ffgpu_is_stale(const ffgpu_tape* t) { return t && t->col.stale ? 1 : 0; }
 
 int ffgpu_set_launch(ffgpu_tape* t, int k, int threads) {
   if (!(k == 0 || k == 1 || k == 2 || k == 4 || k == 8)) return fail("probes_per_thread must be 0, 1, 2, 4 or 8");
-  if (!(threads == 0 || threads == 128 || threads == 256 || threads == 512))
-    return fail("threads_per_block must be 0, 128, 256 or 512");
+  if (!(threads == 0 || threads == 128 || threads == 256 || threads == 512 || threads == 1024))
+    return fail("threads_per_block must be 0, 128, 256, 512 or 1024");
   t->force_k = k;
   t->force_threads = threads;
   return 0;

@@ -930,10 +930,10 @@ void Collection::emit_function(uint32_t fn, const std::vector<uint32_t>& out_slo
   const size_t tape0 = tape.size(), patch0 = patches.size();
   for (int attempt = 0; attempt < 2; ++attempt) {
     const bool cse = enable_cse && !no_cse_fn_[fn];
-    FnEmitter em(functions[fn], fn, tape, patches, cse, temp_budget, den_mode);
+    FnEmitter em(efn(fn), fn, tape, patches, cse, temp_budget, den_mode);
     if (den_mode == 1) em.gen_produce();
     else if (den_mode == 2) em.gen_consume();
-    else em.gen(functions[fn].root);
+    else em.gen(efn(fn).root);
     if (em.failed && cse) {
       // the sharing pass lost track of a temp slot: emit this function as a plain tree instead
       tape.resize(tape0);
@@ -1148,6 +1148,231 @@ bool same_structure(const Function& f, const std::vector<Fp>& ff, int32_t fr, co
 }
 }  // namespace
 
+// ---- shared rows ---------------------------------------------------------------------------------------------
+// Sub-expressions that occur in SEVERAL places of a collection -- the powers x^e of a reduction table, common
+// factors of denominators, numerators shared by different functions -- are evaluated once per probe instead of once
+// per occurrence: each becomes an extra variable row (variable index n_vars + r), filled by a small collection of its
+// own (`pre`, one function per row, over the same variables) that is evaluated before this tape at the same points.
+// The functions' tape then reads the row like any other coordinate of the probe.  Unlike temp slots, rows live in
+// device memory: they survive the tape's chunk boundaries (grid.y) and cost no shared memory, hence no occupancy.
+// (The reference shares nothing between functions except whole duplicates under check_is_equal,
+// ShuntingYardParser.cpp:125-140.)  Values are unchanged: equal sub-trees give equal residues in exact arithmetic, and
+// the translation check in finish() compares every function's tape -- rows included -- with its ORIGINAL expression.
+namespace {
+uint32_t literal_exponent(const Function& f, const Node& n) {      // 0: not a small plain literal
+  if (n.kind != N_NUM) return 0;
+  const std::string& t = f.literals[n.lit].text;
+  if (t.empty() || t.size() > 6) return 0;
+  for (char ch : t)
+    if (ch < '0' || ch > '9') return 0;
+  return (uint32_t)std::min<uint64_t>(leading_digits(t, 0), 0xffffffu);
+}
+// multiplications one evaluation of node i costs by itself (its operands not counted); inversions count as 6
+uint32_t own_cost(const Function& f, const Node& n) {
+  auto chain = [](uint64_t e) -> uint32_t {
+    return e <= 1 ? 0u : (uint32_t)(63 - __builtin_clzll(e)) + (uint32_t)__builtin_popcountll(e) - 1u;
+  };
+  if (n.is_const) return 0;
+  switch (n.kind) {
+    case N_MUL: return 1;
+    case N_DIV: return f.nodes[n.r].is_const ? 1 : 7;
+    case N_POW: case N_POWNEG: {
+      const uint32_t e = literal_exponent(f, f.nodes[n.r]);
+      return e ? chain(e) : 94;
+    }
+    case N_NEGPOW: case N_NEGPOWNEG: {
+      const uint32_t e = literal_exponent(f, f.nodes[n.r]);
+      return e ? chain(e) + 6 : 100;
+    }
+    default: return 0;
+  }
+}
+struct FpKey {
+  uint64_t a, b;
+  bool operator==(const FpKey& o) const { return a == o.a && b == o.b; }
+};
+struct FpKeyHash {
+  size_t operator()(const FpKey& k) const { return (size_t)(k.a ^ mix64(k.b)); }
+};
+// copy the part of f reachable from `root` into g; nodes for which `leaf_var(i)` returns a variable index are
+// replaced by that variable (and not descended into).  Children precede parents in both arrays.
+template <class LeafVar>
+void copy_tree(const Function& f, int32_t root, Function& g, LeafVar leaf_var) {
+  std::vector<int32_t> reach, st{root};
+  std::vector<int32_t> as_var(f.nodes.size(), -2);       // -2 unseen, -1 kept, >= 0 variable
+  while (!st.empty()) {
+    const int32_t i = st.back();
+    st.pop_back();
+    if (as_var[i] != -2) continue;                       // (a tree: cannot happen; a DAG-shaped input would)
+    const int64_t v = leaf_var(i);
+    as_var[i] = v >= 0 ? (int32_t)v : -1;
+    reach.push_back(i);
+    if (v >= 0 || f.nodes[i].l < 0) continue;
+    st.push_back(f.nodes[i].l);
+    st.push_back(f.nodes[i].r);
+  }
+  std::sort(reach.begin(), reach.end());
+  std::vector<int32_t> remap(f.nodes.size(), -1);
+  g.nodes.clear();
+  g.literals.clear();
+  g.nodes.reserve(reach.size());
+  for (int32_t i : reach) {
+    Node n = f.nodes[i];
+    if (as_var[i] >= 0) {
+      n = Node{};
+      n.kind = N_VAR;
+      n.is_const = false;
+      n.var = (uint32_t)as_var[i];
+      n.l = n.r = -1;
+    } else if (n.kind == N_NUM) {
+      n.lit = (uint32_t)g.literals.size();
+      g.literals.push_back(f.literals[f.nodes[i].lit]);
+    } else if (n.l >= 0) {
+      n.l = remap[n.l];
+      n.r = remap[n.r];
+    }
+    remap[i] = (int32_t)g.nodes.size();
+    g.nodes.push_back(n);
+  }
+  g.root = remap[root];
+}
+}  // namespace
+
+void Collection::build_table(const std::vector<int32_t>& dup_of) {
+  lowered_.clear();
+  pre.clear();
+  n_table_rows = 0;
+  const size_t nf = functions.size();
+  if (!enable_cse || !enable_cross || !enable_table || nf < 2 || vars.size() >= 60000) return;
+  struct Cand {
+    uint32_t fn;
+    int32_t node;
+    uint32_t cost;       // multiplications of one evaluation of the whole sub-tree
+    uint32_t refs;       // occurrences not covered by a larger selected sub-tree
+    bool selected;
+    int32_t row;
+  };
+  std::vector<std::vector<Fp>> fps(nf);
+  std::unordered_map<FpKey, Cand, FpKeyHash> cands;
+  std::vector<uint32_t> cost;
+  for (size_t i = 0; i < nf; ++i) {
+    if (dup_of[i] >= 0) continue;
+    const Function& f = functions[i];
+    fingerprints(f, fps[i]);
+    cost.assign(f.nodes.size(), 0);
+    for (size_t k = 0; k < f.nodes.size(); ++k) {
+      const Node& n = f.nodes[k];
+      if (n.l < 0 || n.is_const) continue;
+      cost[k] = own_cost(f, n) + cost[n.l] + cost[n.r];
+      if (cost[k] == 0) continue;                        // sums of variables: a row would save nothing
+      auto it = cands.find(FpKey{fps[i][k].a, fps[i][k].b});
+      if (it == cands.end()) cands.emplace(FpKey{fps[i][k].a, fps[i][k].b}, Cand{(uint32_t)i, (int32_t)k, cost[k], 1, false, -1});
+      else ++it->second.refs;
+    }
+  }
+  // first selection: everything that occurs at least twice anywhere
+  for (auto& kv : cands) kv.second.selected = kv.second.refs >= 2;
+  // occurrences, top down: below a selected sub-tree nothing is counted (its inside is evaluated by the row's own
+  // function).  Candidates that are left with fewer than two uses, or save less than two multiplications, are
+  // dropped, which exposes what they contain -- repeat until nothing changes.
+  auto count_refs = [&]() {
+    for (auto& kv : cands) kv.second.refs = 0;
+    std::vector<int32_t> st;
+    for (size_t i = 0; i < nf; ++i) {
+      if (dup_of[i] >= 0) continue;
+      const Function& f = functions[i];
+      st.assign(1, f.root);
+      while (!st.empty()) {
+        const int32_t k = st.back();
+        st.pop_back();
+        const Node& n = f.nodes[k];
+        if (n.l < 0 || n.is_const) continue;
+        auto it = cands.find(FpKey{fps[i][k].a, fps[i][k].b});
+        if (it != cands.end() && it->second.selected) { ++it->second.refs; continue; }
+        st.push_back(n.l);
+        st.push_back(n.r);
+      }
+    }
+  };
+  for (int round = 0; round < 64; ++round) {
+    count_refs();
+    bool changed = false;
+    for (auto& kv : cands) {
+      Cand& c = kv.second;
+      if (c.selected && (c.refs < 2 || (uint64_t)(c.refs - 1) * c.cost < 2)) { c.selected = false; changed = true; }
+    }
+    if (!changed) break;
+  }
+  std::vector<Cand*> chosen;
+  for (auto& kv : cands)
+    if (kv.second.selected) chosen.push_back(&kv.second);
+  if (chosen.empty()) return;
+  auto benefit = [](const Cand* c) { return (uint64_t)(c->refs - 1) * c->cost; };
+  std::sort(chosen.begin(), chosen.end(), [&](const Cand* x, const Cand* y) {
+    if (benefit(x) != benefit(y)) return benefit(x) > benefit(y);
+    return x->fn != y->fn ? x->fn < y->fn : x->node < y->node;       // deterministic
+  });
+  const size_t limit = table_row_limit ? table_row_limit : 192;
+  if (chosen.size() > limit) {
+    for (size_t k = limit; k < chosen.size(); ++k) chosen[k]->selected = false;
+    chosen.resize(limit);
+    count_refs();
+    std::vector<Cand*> kept;
+    for (Cand* c : chosen) {
+      if (c->refs >= 2) kept.push_back(c);
+      else c->selected = false;
+    }
+    chosen.swap(kept);
+    if (chosen.empty()) return;
+  }
+  // rows in the order of first appearance (deterministic tapes)
+  std::sort(chosen.begin(), chosen.end(), [](const Cand* x, const Cand* y) { return x->fn != y->fn ? x->fn < y->fn : x->node < y->node; });
+  std::vector<Function> table(chosen.size());
+  for (size_t r = 0; r < chosen.size(); ++r) {
+    chosen[r]->row = (int32_t)r;
+    copy_tree(functions[chosen[r]->fn], chosen[r]->node, table[r], [](int32_t) { return (int64_t)-1; });
+    compute_needs(table[r]);
+  }
+  std::vector<std::vector<Fp>> tfps(table.size());
+  for (size_t r = 0; r < table.size(); ++r) fingerprints(table[r], tfps[r]);
+  // the functions with every selected occurrence replaced by its row; equal fingerprints are confirmed exactly
+  const uint32_t n_base = (uint32_t)vars.size();
+  lowered_.resize(nf);
+  for (size_t i = 0; i < nf; ++i) {
+    const Function& f = functions[i];
+    if (dup_of[i] >= 0) { lowered_[i] = f; continue; }
+    copy_tree(f, f.root, lowered_[i], [&](int32_t k) -> int64_t {
+      const Node& n = f.nodes[k];
+      if (n.l < 0 || n.is_const) return -1;
+      auto it = cands.find(FpKey{fps[i][k].a, fps[i][k].b});
+      if (it == cands.end() || !it->second.selected) return -1;
+      const int32_t r = it->second.row;
+      if (!same_structure(f, fps[i], k, table[r], tfps[r], table[r].root)) return -1;
+      return (int64_t)n_base + r;
+    });
+    lowered_[i].rpn = f.rpn;
+    compute_needs(lowered_[i]);
+  }
+  pre.emplace_back();
+  Collection& pc = pre[0];
+  pc.vars = vars;
+  pc.var_index = var_index;
+  pc.check_is_equal = false;
+  pc.functions = std::move(table);
+  pc.enable_fuse = enable_fuse;
+  pc.enable_cse = enable_cse;
+  pc.enable_cross = enable_cross;
+  pc.enable_table = false;
+  pc.temp_budget = temp_budget;
+  std::string perr;
+  if (!pc.finish(perr)) {          // never expected; the functions are then compiled as written
+    pre.clear();
+    lowered_.clear();
+    return;
+  }
+  n_table_rows = (uint32_t)pc.functions.size();
+}
+
 bool Collection::add_function(std::string text, uint64_t index, bool strip_blanks, std::string& err, bool validate,
                               bool dedupe, bool no_duplicates, uint64_t* position) {
   if (strip_blanks) {
@@ -1212,6 +1437,11 @@ bool Collection::finish(std::string& err) {
       ++n_structural_duplicates;
     }
   }
+  // sub-expressions shared by several functions become extra variable rows (build_table); from here on the
+  // functions are the lowered ones (efn)
+  build_table(dup_of);
+  if (!lowered_.empty())
+    for (size_t i = 0; i < functions.size(); ++i) fingerprints(efn(i), fps[i]);
   // Evaluation order: functions over the same denominator are brought together (the group takes the place of its
   // first member), so that a denominator that repeats anywhere in the collection is inverted once.  Outputs are
   // addressed by their slot, the order of evaluation is free.  fn_start is indexed by POSITION in this order.
@@ -1221,7 +1451,7 @@ bool Collection::finish(std::string& err) {
     std::unordered_map<uint64_t, std::vector<uint32_t>> groups;
     std::vector<uint64_t> key(functions.size(), 0);
     for (size_t i = 0; i < functions.size(); ++i) {
-      const Function& f = functions[i];
+      const Function& f = efn(i);
       const Node& rt = f.nodes[f.root];
       if (dup_of[i] >= 0 || rt.kind != N_DIV || rt.is_const || f.nodes[rt.r].is_const) continue;
       const Fp h = fps[i][rt.r];
@@ -1256,7 +1486,7 @@ bool Collection::finish(std::string& err) {
     n_shared_denominators = 0;
     if (enable_cse && !fps.empty()) {
       auto divisor = [&](size_t i) -> int32_t {
-        const Function& f = functions[i];
+        const Function& f = efn(i);
         const Node& rt = f.nodes[f.root];
         if (no_cse_fn_[i] || rt.kind != N_DIV || rt.is_const || f.nodes[rt.r].is_const) return -1;
         return rt.r;
@@ -1269,7 +1499,7 @@ bool Collection::finish(std::string& err) {
         bool joins = false;
         if (head >= 0 && d >= 0) {
           const int32_t dh = divisor((size_t)head);
-          joins = same_structure(functions[i], fps[i], d, functions[head], fps[head], dh);
+          joins = same_structure(efn(i), fps[i], d, efn(head), fps[head], dh);
         }
         if (joins) {
           den_mode_[head] = 1;
@@ -1296,6 +1526,15 @@ bool Collection::finish(std::string& err) {
     std::vector<uint64_t> pt(vars.size());
     uint64_t seed = 0x243F6A8885A308D3ULL;
     for (auto& v : pt) v = 1 + splitmix64(seed) % (P0 - 1);
+    if (!pre.empty()) {
+      // the shared rows at that point, from their own expression trees (the pre-pass tape has been checked
+      // against them by its own finish())
+      std::vector<uint64_t> val;
+      for (const Function& tf : pre[0].functions) {
+        eval_nodes(tf, P0, pt.data(), val);
+        pt.push_back(val[tf.root]);
+      }
+    }
     bool again = false;
     uint64_t chk_temps[16] = {};
     bool chk_temp_set[16] = {};
@@ -1351,6 +1590,14 @@ bool Collection::finish(std::string& err) {
       }
       if (in.op < OP_TERM && (in.flags & F_NEGR)) ++executed.ma;
     }
+  }
+  if (!pre.empty()) {
+    const WorkCount& w = pre[0].executed;
+    executed.tokens += w.tokens;
+    executed.mm += w.mm;
+    executed.ma += w.ma;
+    executed.inv += w.inv;
+    executed.max_rpn_depth += w.max_rpn_depth;
   }
   // chunk tables for C = 1, 2, 4, ... while a chunk still holds a function
   chunk_table.clear();
@@ -1454,7 +1701,7 @@ void Collection::fuse() {
     if (pi < 0) return false;
     const ConstPatch& cp = patches[pi];
     if (cp.inverse || cp.negate) return false;
-    const Function& f = functions[cp.fn];
+    const Function& f = efn(cp.fn);
     const Node& nd = f.nodes[cp.node];
     if (nd.kind != N_NUM) return false;
     const std::string& t = f.literals[nd.lit].text;
@@ -1501,6 +1748,27 @@ void Collection::fuse() {
       if (moved_patch >= 0) patches[moved_patch].instr = (uint32_t)out.size();
       out.push_back(t);
       i = j;
+      continue;
+    }
+    // ---- LOAD.VAR.P, MUL.CONST, ADD/SUB/MUL.POP  ->  TERM with exponent 1 (c * x as a term of a sum; with shared
+    //      rows the powers of a polynomial's monomials arrive as plain variables)
+    if (a.op == OP_LOAD && a.src == SRC_VAR && a.flags == F_PUSH && a.arg < 65536 && i + 2 < n &&
+        plain(tape[i + 1], OP_MUL, SRC_CONST) && patch_of[i + 1] >= 0 && tape[i + 2].src == SRC_POP &&
+        (tape[i + 2].flags & ~F_SWAP) == 0 &&
+        (tape[i + 2].op == OP_ADD || tape[i + 2].op == OP_SUB || tape[i + 2].op == OP_MUL)) {
+      Instr t{};
+      t.op = OP_TERM;
+      t.src = SRC_VAR;
+      t.arg = a.arg | (1u << 16);
+      t.fast = FX_TERM;
+      uint8_t mode = TM_ADD;
+      if (tape[i + 2].op == OP_MUL) mode = TM_MUL;
+      else if (tape[i + 2].op == OP_SUB) mode = (tape[i + 2].flags & F_SWAP) ? TM_SUB : TM_RSUB;
+      t.flags = (uint8_t)(F_CMUL | (mode << TM_SHIFT));
+      for (size_t k = i; k < i + 3; ++k) new_index[k] = (uint32_t)out.size();
+      patches[patch_of[i + 1]].instr = (uint32_t)out.size();
+      out.push_back(t);
+      i += 3;
       continue;
     }
     // ---- ACCUM, ACCUM (two sums fed by the same term)  ->  ACCUM2
@@ -1796,7 +2064,7 @@ bool Collection::resolve(uint64_t p, std::string& err) {
   for (const ConstPatch& cp : patches) {
     if (cp.fn != cur) {
       cur = cp.fn;
-      eval_nodes(functions[cur], p, nullptr, val);
+      eval_nodes(efn(cur), p, nullptr, val);
     }
     const uint64_t v = val[cp.node];
     uint64_t w = cp.inverse ? ffhost::div(1 % p, v, p) : v;
@@ -1807,6 +2075,8 @@ bool Collection::resolve(uint64_t p, std::string& err) {
     // a residue above that means a negative power and takes the general code (inversion first)
     if (in.op == OP_POWU) in.fast = (w < (p >> 1) && in.flags == 0) ? FX_POWU : FX_GENERIC;
   }
+  for (Collection& pc : pre)
+    if (!pc.resolve(p, err)) return false;
   prime = p;
   return true;
 }

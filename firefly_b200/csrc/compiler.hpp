@@ -101,6 +101,12 @@ struct Collection {
   bool enable_fuse = true;                    // fuse frequent instruction runs (TERM, ACCUM2, ADDVARS, MULVARS)
   bool enable_cse = true;                     // share structurally equal sub-expressions
   bool enable_cross = true;                   // ... and across functions: whole functions of equal structure, denominators
+  bool enable_table = true;                   // ... and sub-expressions used by SEVERAL functions (powers of a variable, common
+                                              // factors, numerators): computed once per probe into extra variable rows
+  uint32_t table_row_limit = 0;               // most shared rows (0: automatic)
+  uint32_t n_table_rows = 0;                  // shared rows in use: the tape addresses them as variables n_vars, n_vars + 1, ...
+  std::vector<Collection> pre;                // empty, or ONE collection over the same variables whose outputs are the shared
+                                              // rows; it is evaluated before this tape, at the same points
   uint32_t cse_fallbacks = 0;                 // functions emitted without sharing after a failed self-check
   uint32_t n_structural_duplicates = 0;       // functions of equal structure: evaluated once, stored to all their outputs
   uint32_t n_shared_denominators = 0;         // functions that reuse the inverted denominator of the function before them
@@ -150,6 +156,10 @@ struct Collection {
   bool build_tree(Function& f, std::string& err);
   static void compute_needs(Function& f);
   std::vector<Function> base_functions_;      // one per output, before any factor was applied
+  // what the tape is generated from: `functions` with every occurrence of a shared row replaced by a variable leaf
+  std::vector<Function> lowered_;
+  const Function& efn(size_t i) const { return lowered_.empty() ? functions[i] : lowered_[i]; }
+  void build_table(const std::vector<int32_t>& dup_of);
   void emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots, int den_mode);
   bool check_function(uint32_t fn, uint64_t p, const uint64_t* point, uint64_t* temps, bool* temp_set) const;
   std::vector<uint8_t> den_mode_;             // per function: 0 as written, 1 parks 1/D in temp slot 0, 2 uses it

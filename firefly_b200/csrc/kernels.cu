@@ -341,6 +341,9 @@ struct Lane {
   u64* scratch;          // 64 words for block_inverse
   u32 off[NACC];         // tile-relative offsets of this thread's accesses, clamped into the batch
   u32 own, left, tmp_top;
+  const u64* tbase;      // shared rows (variables n_base, n_base + 1, ...) + first point of the tile
+  u64 t_stride;
+  u32 n_base;
   FT F;
 
   // Points owned by this thread.  VEC: pairs (2t, 2t+1) inside rows of 2*THREADS points, so that every
@@ -360,13 +363,16 @@ struct Lane {
     obase = reinterpret_cast<u64*>(prm.out) + tile;
     in_stride = prm.in_stride;
     out_stride = prm.out_stride;
+    tbase = reinterpret_cast<const u64*>(prm.table) + tile;
+    t_stride = prm.table_stride;
+    n_base = prm.table ? prm.n_vars : 0xffffffffu;
     scratch = smem;
     stk = reinterpret_cast<uint2*>(smem + 64) + threadIdx.x;
     tmp_top = prm.n_slots - 1;
     F = make_field<FT>(prm);
   }
   __device__ __forceinline__ void load_var(u32 var, R (&b)[K]) const {
-    const u64* row = vbase + (u64)var * in_stride;
+    const u64* row = var < n_base ? vbase + (u64)var * in_stride : tbase + (u64)(var - n_base) * t_stride;
     if (VEC) {
 #pragma unroll
       for (int j = 0; j < NACC; j++) {
@@ -561,6 +567,24 @@ __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_
   L.init(prm, smem);
   const FT F = L.F;
 
+#ifdef FFGPU_PREFETCH
+  // experiment: ask for every variable row of the tile before the tape starts
+  if (K == 8) {
+    const u32 nv = prm.n_vars < 32u ? prm.n_vars : 32u;
+#pragma unroll 1
+    for (u32 v = 0; v < nv; v++) {
+      const u64* row = L.vbase + (u64)v * L.in_stride;
+#pragma unroll
+      for (int j = 0; j < Lane<K, THREADS, VEC, FT>::NACC; j++) {
+#if FFGPU_PREFETCH == 2
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(row + L.off[j]));
+#else
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + L.off[j]));
+#endif
+      }
+    }
+  }
+#endif
   R acc[K];
 #pragma unroll
   for (int k = 0; k < K; k++) acc[k] = opaque(0);
@@ -702,6 +726,29 @@ __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_
         // T = var^e [* c]; ACC = T | ACC + T | ACC - T | T - ACC | ACC * T.  The old ACC waits in the next free
         // spill slot while the power runs (the unfused sequence pushed it there too).
         const u32 mode = (ins.flags >> TM_SHIFT) & 7u;
+        if ((ins.arg >> 16) == 1u && mode != TM_LOAD) {
+          // c * x as a term: nothing to park
+          L.load_var(ins.arg & 0xffffu, b);
+          if (ins.flags & F_CMUL) {
+            const R c = mkR(ins.imm);
+#pragma unroll
+            for (int k = 0; k < K; k++) b[k] = fmul(b[k], c, F);
+          }
+          if (mode == TM_ADD) {
+#pragma unroll
+            for (int k = 0; k < K; k++) acc[k] = fadd(acc[k], b[k], F);
+          } else if (mode == TM_SUB) {
+#pragma unroll
+            for (int k = 0; k < K; k++) acc[k] = fsub(acc[k], b[k], F);
+          } else if (mode == TM_RSUB) {
+#pragma unroll
+            for (int k = 0; k < K; k++) acc[k] = fsub(b[k], acc[k], F);
+          } else {
+#pragma unroll
+            for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], b[k], F);
+          }
+          break;
+        }
         if (mode != TM_LOAD) L.slot_put(acc, sp);
         else if (ins.flags & F_PUSH) L.slot_put(acc, sp++);
         L.load_var(ins.arg & 0xffffu, b);
@@ -853,8 +900,10 @@ cudaError_t launch_k(const EvalParams& prm, const LaunchShape& sh, cudaStream_t 
 template <int K, int THREADS>
 cudaError_t launch_t(const EvalParams& prm, const LaunchShape& sh, cudaStream_t stream) {
   const bool vec = K >= 2 && (prm.n_points % 2 == 0) && (prm.in_stride % 2 == 0) && (prm.out_stride % 2 == 0) &&
-                   ((uintptr_t)prm.values % 16 == 0) && ((uintptr_t)prm.out % 16 == 0);
-  constexpr bool HAS_LEAN = K == 8 && THREADS <= 256;      // the only shapes whose register budget differs
+                   ((uintptr_t)prm.values % 16 == 0) && ((uintptr_t)prm.out % 16 == 0) &&
+                   (!prm.table || (prm.table_stride % 2 == 0 && (uintptr_t)prm.table % 16 == 0));
+  constexpr bool HAS_LEAN = K == 8;                        // the only shapes whose register budget differs
+  constexpr bool HAS_FULL = !(K == 8 && THREADS > 768);    // 1024 threads leave 64 registers: lean tapes only
   if (prm.generic) {
     // any odd prime: the shapes small and medium batches run in (choose_shape keeps to them)
     constexpr bool HAS_GENERIC = K <= 4 && THREADS <= 256;
@@ -866,8 +915,9 @@ cudaError_t launch_t(const EvalParams& prm, const LaunchShape& sh, cudaStream_t 
     if (vec) return launch_k<K, THREADS, (K >= 2), HAS_LEAN>(prm, sh, stream);
     return launch_k<K, THREADS, false, HAS_LEAN>(prm, sh, stream);
   }
-  if (vec) return launch_k<K, THREADS, (K >= 2), false>(prm, sh, stream);
-  return launch_k<K, THREADS, false, false>(prm, sh, stream);
+  if (!HAS_FULL) return cudaErrorInvalidValue;
+  if (vec) return launch_k<(HAS_FULL ? K : 1), THREADS, (K >= 2 && HAS_FULL), false>(prm, sh, stream);
+  return launch_k<(HAS_FULL ? K : 1), THREADS, false, false>(prm, sh, stream);
 }
 
 }  // namespace
@@ -886,7 +936,7 @@ LaunchShape choose_shape(uint64_t n_points, uint32_t n_slots, int sm_count, int 
   // below) and shared memory (227 KB per SM, 1 KB reserved per block)
   auto blocks_by_smem = [&](int k, int th) { return (int)((227 * 1024) / (smem_of(k, th) + 1024)); };
   // a lean kernel (64 registers at k = 8) pays off only if shared memory lets the fourth block in
-  auto lean_of = [&](int k, int th) { return lean_ok && k == 8 && th <= 256 && blocks_by_smem(k, th) >= 1024 / th; };
+  auto lean_of = [&](int k, int th) { return lean_ok && k == 8 && blocks_by_smem(k, th) >= 1024 / th; };
   auto warps_of = [&](int k, int th) {
     const int by_regs = (k == 8 && !lean_of(k, th) ? 768 : 1024) / th;
     return std::min(by_regs, blocks_by_smem(k, th)) * th / 32;
@@ -949,6 +999,7 @@ cudaError_t launch_eval(const EvalParams& prm, const LaunchShape& sh, cudaStream
   FFGPU_CASE(2, 128) FFGPU_CASE(2, 256) FFGPU_CASE(2, 512)
   FFGPU_CASE(4, 128) FFGPU_CASE(4, 256) FFGPU_CASE(4, 512)
   FFGPU_CASE(8, 128) FFGPU_CASE(8, 256) FFGPU_CASE(8, 512)
+  FFGPU_CASE(1, 1024) FFGPU_CASE(2, 1024) FFGPU_CASE(4, 1024) FFGPU_CASE(8, 1024)
 #undef FFGPU_CASE
   return cudaErrorInvalidValue;
 }

@@ -22,13 +22,16 @@ struct EvalParams {
   uint64_t pinv;              // ... floor((2^126 - 1) / (p << pshift))
   uint32_t n_slots;           // shared-memory slots per probe: spill slots from 0 up, temp slots from n_slots-1 down
   uint32_t n_instr;           // tape length without the terminators
+  uint32_t n_vars;            // rows of `values`; the tape's variables n_vars, n_vars + 1, ... are the shared rows:
+  const uint64_t* table;      // device, [n_table_rows][table_stride], written by the collection's pre-pass tape
+  uint64_t table_stride;      //   (compiler.cpp, build_table) at the same points; NULL if the collection has none
   const uint32_t* chunk_bounds;  // device, n_chunks + 1 tape offsets at function boundaries (NULL: one chunk)
 };
 
 // probes per thread / threads per block actually used for a launch
 struct LaunchShape {
   int k;          // 1, 2, 4 or 8
-  int threads;    // 128, 256 or 512
+  int threads;    // 128, 256, 512 or 1024
   unsigned blocks;     // point tiles (grid.x)
   unsigned chunks;     // tape chunks (grid.y): blocks of a tile split the collection's functions
   size_t smem;

@@ -62,7 +62,8 @@ enum {
   FFGPU_CHECK_IS_EQUAL = 1,   /* detect duplicate functions (ShuntingYardParser's check_is_equal) */
   FFGPU_NO_CSE = 2,           /* do not share equal sub-expressions inside a function (for A/B tests) */
   FFGPU_NO_FUSE = 4,          /* do not fuse instruction runs into TERM / MULADD / ACCUM2 / ADDVARS / MULVARS (for A/B tests) */
-  FFGPU_NO_CROSS = 16,        /* do not share ACROSS functions: structural duplicates, shared denominators (for A/B tests) */
+  FFGPU_NO_CROSS = 16,        /* do not share ACROSS functions: structural duplicates, shared denominators, shared rows (for A/B tests) */
+  FFGPU_NO_TABLE = 32,        /* no shared rows (sub-expressions of several functions evaluated once per probe; for A/B tests) */
   FFGPU_TEMPS_SHIFT = 8       /* bits 8..11: temp slots per function for shared sub-expressions (0 = automatic) */
 };
 
@@ -102,6 +103,13 @@ size_t ffgpu_n_structural_duplicates(const ffgpu_tape*);
 /* functions N/D whose denominator has the structure of the denominator of the function before them: 1/D is
  * computed once per run of such functions and kept in a temp slot (no denominator code, no inversion for the rest) */
 size_t ffgpu_n_shared_denominators(const ffgpu_tape*);
+/* shared rows: sub-expressions that occur in several places of the collection (powers of a variable, common
+ * factors, numerators of different functions) are evaluated once per probe by a small tape of their own and read by
+ * the functions' tape as extra variables n_vars, n_vars + 1, ... (the reference shares nothing between functions,
+ * ShuntingYardParser.hpp:365-479 walks every token of every function).  ffgpu_get_table_tape copies that tape
+ * (output r = row r); 0 rows: the collection has nothing to share.  FFGPU_NO_TABLE turns the pass off. */
+size_t ffgpu_n_table_rows(const ffgpu_tape*);
+size_t ffgpu_get_table_tape(const ffgpu_tape*, void* buf, size_t cap);
 size_t ffgpu_n_slots(const ffgpu_tape*);        /* shared-memory slots per probe the kernel reserves (spill + temps) */
 /* RPN of distinct function i, tokens joined by ' '; returns the length needed (without NUL) */
 size_t ffgpu_rpn(const ffgpu_tape*, size_t i, char* buf, size_t cap);

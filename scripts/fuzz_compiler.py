@@ -137,7 +137,7 @@ def one_round(seed, rnd):
         funs, vars_ = W.ibp_like_collection(rng.randint(2, 25), max(nv, 2), seed=rng.randrange(1 << 30),
                                             den_run=rng.choice([0, 0, 2, 4, 16]))
     nv = len(vars_)
-    opts = dict(cse=rng.random() < 0.85, fuse=rng.random() < 0.85, cross=rng.random() < 0.85,
+    opts = dict(cse=rng.random() < 0.85, fuse=rng.random() < 0.85, cross=rng.random() < 0.85, table=rng.random() < 0.8,
                 temps=rng.choice([0, 0, 0, 1, 2, 3, 5, 8]), check_is_equal=rng.random() < 0.2)
     # Equality by value at one random point (check_is_equal, ShuntingYardParser.cpp:125-140) is not a property of two
     # functions once an exponent depends on a variable: (-x)^(x) and (x)^(x) agree exactly when the check point is
@@ -205,8 +205,12 @@ def one_round(seed, rnd):
             for row, i in enumerate(factors):
                 want[i] = [int(b) * (pow(int(f), p - 2, p) if int(f) else 0) % p for b, f in zip(want[i], fac[row])]
         tape = par.tape()
+        pre, rows = par.table_tape(), par.n_table_rows
         for j in range(npts):
-            got = run(tape, [int(x) for x in pts[:, j]], p, par.n_out)
+            pt = [int(x) for x in pts[:, j]]
+            if rows:
+                pt = pt + run(pre, pt, p, rows)      # the shared rows are variables n_vars, n_vars + 1, ...
+            got = run(tape, pt, p, par.n_out)
             exp = [int(x) for x in want[:, j]]
             if got != exp:
                 k = next(i for i in range(len(exp)) if got[i] != exp[i])

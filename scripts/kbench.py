@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--ibp", type=int, default=0, help="also run an IBP-like collection with this many functions")
     ap.add_argument("--den-run", type=int, default=0, help="IBP-like collection: runs of up to this many functions share a denominator")
     ap.add_argument("--no-cross", action="store_true", help="no sharing across functions (A/B)")
+    ap.add_argument("--no-table", action="store_true", help="no shared rows (A/B)")
+    ap.add_argument("--ibp-points", type=int, default=1 << 16)
     ap.add_argument("--temps", default="0", help="comma list of temp-slot budgets (0 = automatic, -1 = CSE off)")
     args = ap.parse_args()
     ctx = ff.Context()
@@ -42,14 +44,16 @@ def main():
         work.append((name, [text], vars_, n))
     if args.ibp:
         funs, vars_ = W.ibp_like_collection(args.ibp, 8, den_run=args.den_run)
-        work.append((f"ibp{args.ibp}" + (f"r{args.den_run}" if args.den_run else ""), funs, vars_, min(n, 1 << 16)))
+        work.append((f"ibp{args.ibp}" + (f"r{args.den_run}" if args.den_run else ""), funs, vars_, min(n, args.ibp_points)))
     work = [(f"{name}/t{t}", funs, vars_, npts, int(t)) for name, funs, vars_, npts in work for t in args.temps.split(",")]
     for name, funs, vars_, npts, temps in work:
-        par = ff.GpuParser(ctx, funs, vars_, cse=temps >= 0, temps=max(temps, 0), cross=not args.no_cross)
+        par = ff.GpuParser(ctx, funs, vars_, cse=temps >= 0, temps=max(temps, 0), cross=not args.no_cross, table=not args.no_table)
         par.set_prime(P0)
-        print(f"{name}: {par.n_instr} instr, spill {par.stack_depth}, temps {par.n_temps}, slots {par.n_slots}", flush=True)
         w = par.work()
         mm_eq = w["mm"] + 6 * w["inv"]
+        tw = par.tape_work()
+        print(f"{name}: {par.n_instr} instr, spill {par.stack_depth}, temps {par.n_temps}, slots {par.n_slots}, "
+              f"shared rows {par.n_table_rows}, MM-eq per probe {mm_eq} (reference tokens) / {tw['mm'] + 6 * tw['inv']} (executed)", flush=True)
         vals = torch.empty((len(vars_), npts), dtype=torch.int64, device="cuda")
         out = torch.empty((par.n_out, npts), dtype=torch.int64, device="cuda")
         ff.lib.ffgpu_fill_points(ctx.h, 0, vals.data_ptr(), len(vars_), npts, npts, 0, npts, 1, P0, stream)

@@ -16,7 +16,12 @@ P0 = 9223372036854775783
 
 def interp(par, pts, p):
     tape = par.tape()
-    cols = [run(tape, [int(x) for x in pts[:, j]], p, par.n_out) for j in range(pts.shape[1])]
+    pre, rows = par.table_tape(), par.n_table_rows
+
+    def one(pt):
+        # the shared rows first (their own tape), then the functions with the rows as extra variables
+        return run(tape, pt + run(pre, pt, p, rows) if rows else pt, p, par.n_out)
+    cols = [one([int(x) for x in pts[:, j]]) for j in range(pts.shape[1])]
     return np.array(cols, dtype=np.uint64).T.reshape(par.n_out, pts.shape[1])
 
 
@@ -299,7 +304,7 @@ def test_fused_and_plain_tapes_agree(oracle, cse, fuse):
     par = ff.GpuParser(None, funs, vars_, cse=cse, fuse=fuse)
     par.set_prime(p)
     assert par.cse_fallbacks == 0
-    ops = {ff.OPS[o] for o in par.tape()["op"]}
+    ops = {ff.OPS[o] for o in par.tape()["op"]} | {ff.OPS[o] for o in par.table_tape()["op"]}
     assert ({"TERM", "MULADD", "ADDVARS", "MULVARS"} <= ops) == fuse
     assert np.array_equal(interp(par, pts, p), want)
 
@@ -469,6 +474,87 @@ def test_cross_function_sharing_keeps_every_value(oracle, den_run, temps, fuse, 
     off.set_prime(p)
     assert off.n_shared_denominators == 0 and off.n_structural_duplicates == 0 and off.n_instr > par.n_instr
     assert np.array_equal(interp(off, pts, p), want)
+
+
+def test_shared_rows_are_evaluated_once(oracle):
+    """sub-expressions of SEVERAL functions become extra variable rows computed by a pre-pass tape: counts on a
+    hand-written collection, values against the oracle (zeros included), prime change, the pass switched off"""
+    vars_ = ["x", "y", "z"]
+    funs = ["x^30*y+1", "x^30*z-2", "(x^30*y)/(z+x^30)", "y^2+z", "3*y^2"]
+    par = ff.GpuParser(None, funs, vars_)
+    # x^30*y (twice), x^30 (twice more outside of it); y^2 twice saves one multiplication: below the threshold
+    assert par.n_table_rows == 2 and par.n_structural_duplicates == 0
+    off = ff.GpuParser(None, funs, vars_, table=False)
+    assert off.n_table_rows == 0 and len(off.table_tape()) == 0
+    for p in (ff.primes()[0], ff.primes()[17]):
+        par.set_prime(p)
+        off.set_prime(p)
+        pts = ff.synthetic_points(3, 6, p, seed=5)
+        pts[:, 0] = 0
+        pts[:, 1] = np.array([0, 5, p - 1], dtype=np.uint64)
+        want = oracle.parse(funs, vars_, p).eval(pts)
+        assert par.cse_fallbacks == 0
+        assert np.array_equal(interp(par, pts, p), want) and np.array_equal(interp(off, pts, p), want)
+    assert par.tape_work()["mm"] < off.tape_work()["mm"]
+    # the rows read as variables beyond the collection's own
+    t = par.tape()
+    srcs = {int(a) for o, s_, a in zip(t["op"], t["src"], t["arg"]) if ff.SRCS[s_] == "VAR" and ff.OPS[o] in ("LOAD", "MUL", "ADD")}
+    assert any(a >= 3 for a in srcs)
+
+
+@pytest.mark.parametrize("check,den_run", [(False, 0), (True, 0), (False, 4)])
+def test_shared_rows_on_a_reduction_table(oracle, check, den_run):
+    """the IBP-like collection: powers of the variables and common factors are shared rows; fewer multiplications,
+    fewer shared-memory slots, identical values; with duplicates, check_is_equal, shared denominators and factors"""
+    from firefly_b200 import workloads as W
+    funs, vars_ = W.ibp_like_collection(120, 6, seed=4242, den_run=den_run)
+    funs.insert(7, funs[3])
+    p = ff.primes()[2]
+    pts = ff.synthetic_points(6, 4, p, seed=3)
+    pts[:, 1] = 0
+    pts[:, 2] = 1
+    op = oracle.parse(funs, vars_, p, check_is_equal=check) if check else oracle.parse(funs, vars_, p)
+    want = op.eval(pts)
+    par = ff.GpuParser(None, funs, vars_, check_is_equal=check)
+    off = ff.GpuParser(None, funs, vars_, check_is_equal=check, table=False)
+    par.set_prime(p)
+    off.set_prime(p)
+    assert par.n_table_rows > 10 and par.cse_fallbacks == 0
+    assert np.array_equal(interp(par, pts, p), want) and np.array_equal(interp(off, pts, p), want)
+    w_on, w_off = par.tape_work(), off.tape_work()
+    assert w_on["mm"] + 6 * w_on["inv"] < 0.85 * (w_off["mm"] + 6 * w_off["inv"])
+    assert par.n_slots <= off.n_slots
+    # scanned factors and a prime change rebuild tape and rows together
+    fv = [f"x{i}" for i in range(1, 7)]
+    par.set_factors({0: "x1^13*x2", 5: "(x3-1)"}, fv)
+    p2 = ff.primes()[40]
+    par.set_prime(p2)
+    pts2 = ff.synthetic_points(6, 3, p2, seed=4)
+    op2 = oracle.parse(funs, vars_, p2, check_is_equal=check) if check else oracle.parse(funs, vars_, p2)
+    want2 = op2.eval(pts2).copy()
+    fac = oracle.parse(["x1^13*x2", "(x3-1)"], fv, p2).eval(pts2)
+    for row, i in enumerate((0, 5)):
+        want2[i] = [int(b) * pow(int(f), p2 - 2, p2) % p2 for b, f in zip(want2[i], fac[row])]
+    assert np.array_equal(interp(par, pts2, p2), want2)
+
+
+def test_shared_rows_follow_added_and_trimmed_functions(oracle):
+    """add_otf / trim mark the tape stale; the rebuild recomputes the rows"""
+    vars_ = ["a", "b"]
+    par = ff.GpuParser(None, ["a^7*b", "b+1"], vars_)
+    assert par.n_table_rows == 0
+    par.add_otf("a^7*b+b^9")
+    par.add_otf("b^9-a")
+    p = ff.primes()[1]
+    par.set_prime(p)
+    assert par.n_table_rows == 2
+    funs = ["a^7*b", "b+1", "a^7*b+b^9", "b^9-a"]
+    pts = ff.synthetic_points(2, 5, p, seed=9)
+    assert np.array_equal(interp(par, pts, p), oracle.parse(funs, vars_, p).eval(pts))
+    par.trim([0, 1, 3])
+    par.set_prime(p)
+    assert par.n_table_rows == 0
+    assert np.array_equal(interp(par, pts, p), oracle.parse([funs[0], funs[1], funs[3]], vars_, p).eval(pts))
 
 
 def test_shared_denominator_edge_cases(oracle):

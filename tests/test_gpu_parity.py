@@ -309,7 +309,8 @@ def test_concurrent_callers(ctx, oracle, coalesce, cap):
     [t.join() for t in ts]
     assert not errs, errs
     st = par.coalesce_stats()
-    launches = ff.launch_count() - l0
+    kernels = 2 if par.n_table_rows else 1       # a collection with shared rows runs their tape first
+    launches = (ff.launch_count() - l0) // kernels
     if coalesce:
         assert st["calls"] == n_threads * n_iter and st["launches"] == launches
         assert launches < n_threads * n_iter, "32 concurrent callers never shared a launch"
@@ -616,3 +617,56 @@ def test_shared_denominators_on_device(ctx, oracle, den_run):
         par.set_launch(k, th)
         assert np.array_equal(par.evaluate_pre(pts)[:, :40], want), (k, th)
     par.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("generic", [False, True])
+def test_shared_rows_on_device(ctx, oracle, generic):
+    """sub-expressions of several functions (powers of the variables, common factors) are evaluated once per probe
+    into scratch rows by a pre-pass kernel and read by the functions' tape as extra variables: every path that
+    launches (small call, chunked host call, caller's device memory, ranges of a big batch, every launch shape),
+    against the oracle and against the same collection compiled without the pass"""
+    import torch
+    funs, vars_ = W.ibp_like_collection(500, 8, seed=2026, den_run=3)
+    funs = funs[:200] + funs[20:30] + funs[200:]
+    p = 4611686018427400249 if generic else ff.primes()[7]     # a 62-bit prime: Barrett kernels
+    par = ff.GpuParser(ctx, funs, vars_)
+    off = ff.GpuParser(ctx, funs, vars_, table=False)
+    par.set_prime(p)
+    off.set_prime(p)
+    assert par.n_table_rows > 40 and off.n_table_rows == 0 and par.cse_fallbacks == 0
+    wp, wo = par.tape_work(), off.tape_work()
+    assert wp["mm"] + 6 * wp["inv"] < 0.8 * (wo["mm"] + 6 * wo["inv"])
+    orc = oracle.parse(funs, vars_, p)
+    for n in (1, 2, 7, 128, 129, 4000, 30001):
+        pts = ff.synthetic_points(8, n, p, seed=n)
+        if n > 2:
+            pts[:, 1] = 0
+            pts[:, 2] = p - 1
+        sel = np.unique(np.concatenate([np.arange(min(n, 8)), np.arange(0, n, max(1, n // 11)), [n - 1]]))
+        got = par.evaluate_pre(pts)
+        assert np.array_equal(got[:, sel], orc.eval(np.ascontiguousarray(pts[:, sel]))), n
+        assert np.array_equal(got, off.evaluate_pre(pts)), n
+    # a batch whose rows exceed the scratch budget is evaluated range by range (caller's device memory, odd size)
+    n = 200001 if not generic else 60001
+    stride = n + 1
+    s = torch.cuda.current_stream().cuda_stream
+    vals = torch.empty((8, stride), dtype=torch.int64, device="cuda")
+    assert ff.lib.ffgpu_fill_points(ctx.h, 0, vals.data_ptr(), 8, n, stride, 0, n, 5, p, s) == 0
+    out = torch.zeros((par.n_out, stride), dtype=torch.int64, device="cuda")
+    out2 = torch.zeros((par.n_out, stride), dtype=torch.int64, device="cuda")
+    par.eval_device(vals.data_ptr(), stride, n, out.data_ptr(), stride, stream=s)
+    off.eval_device(vals.data_ptr(), stride, n, out2.data_ptr(), stride, stream=s)
+    torch.cuda.synchronize()
+    assert torch.equal(out[:, :n], out2[:, :n])
+    sel = np.unique(np.concatenate([np.arange(0, n, n // 37), [n - 2, n - 1]]))
+    host = ff.synthetic_points(8, n, p, seed=5)[:, sel]
+    assert np.array_equal(out[:, :n].cpu().numpy().view(np.uint64)[:, sel], orc.eval(np.ascontiguousarray(host)))
+    if not generic:
+        pts = ff.synthetic_points(8, 3000, p, seed=1)
+        want = orc.eval(np.ascontiguousarray(pts[:, :40]))
+        for k, th in [(1, 128), (2, 256), (4, 512), (8, 128), (8, 256), (8, 1024)]:
+            par.set_launch(k, th)
+            assert np.array_equal(par.evaluate_pre(pts)[:, :40], want), (k, th)
+    par.close()
+    off.close()
