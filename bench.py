@@ -96,11 +96,26 @@ def measured_hbm_peak():
         return 6650.0, "fallback"
 
 
-def measured_link_peak():
-    """pinned host <-> device copy rates of bench/h2d_peak.cu (GB/s), if a run has been kept under profiles/"""
+def measured_link_peak(device_index=None):
+    """pinned host <-> device copy rates (GB/s): build/h2d_peak (bench/h2d_peak.cu) run now on this rank's GPU -- under
+    torchrun all ranks run it at the same time, so the figures are what the host gives N GPUs at once --, else the
+    kept run under profiles/"""
+    exe = os.path.join(ROOT, "build", "h2d_peak")
+    if device_index is not None and os.path.exists(exe):
+        try:
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(device_index))
+            r = subprocess.run([exe, "--gpus", "1", "--mb", "128", "--reps", "5"], capture_output=True, text=True, env=env,
+                               timeout=120, check=True)
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            return {"h2d_gbs": d["h2d_gbs"], "d2h_gbs": d["d2h_gbs"], "both_gbs_sum": d["both_gbs_sum"],
+                    "source": "bench/h2d_peak.cu run inside this bench (128 MB pinned copies)"}
+        except Exception:
+            pass
     try:
         with open(os.path.join(ROOT, "profiles", "r02_h2d_peak.json")) as f:
-            return json.load(f)
+            d = json.load(f)
+        return {"h2d_gbs": d["h2d_gbs"], "d2h_gbs": d["d2h_gbs"], "both_gbs_sum": d["both_gbs_sum"],
+                "source": "profiles/r02_h2d_peak.json (kept run)"}
     except Exception:
         return None
 
@@ -520,6 +535,20 @@ def main():
         if e2e_ctx is not None:
             verified = verified and e2e_ctx["verified_bit_exact_vs_oracle"]
 
+    # ---- what the host link gives this job: every rank copies at the same time ------------------------------------------
+    barrier()
+    physical = os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")
+    dev_index = physical[local] if len(physical) > local and physical[local] else local
+    link_own = measured_link_peak(dev_index)
+    barrier()
+    link = None
+    if link_own:
+        t = torch.tensor([link_own["h2d_gbs"], link_own["d2h_gbs"], link_own["both_gbs_sum"]], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        link = {"h2d_gbs": float(t[0]), "d2h_gbs": float(t[1]), "both_gbs_sum": float(t[2]), "gpus_copying_at_once": world,
+                "source": link_own["source"]}
+
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -549,8 +578,8 @@ def main():
                 "executed_pipe_slot_frac_of_measured": rate * wi["executed_mm_eq"] * SLOTS_PER_MM / peak_int,
                 "hbm_gbs": rate * 8 * (pars[i].n_vars + 1) / 1e9,
             }
-        link = measured_link_peak()
         e2e_bytes_per_s = e2e_value / world * (h2d + d2h) / (len(FUNCS) * ne)
+        e2e_h2d_per_s = e2e_value * h2d / (len(FUNCS) * ne)          # whole job, upload direction only
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -573,8 +602,11 @@ def main():
                     "points_per_function_per_step_per_gpu": ne, "steps": e2e_steps, "gpu_launches": int(e2e_launches),
                     "api": "ffgpu_eval (host pinned buffers, chunked H2D/kernel/D2H pipeline)",
                     "link_gb_per_s_per_gpu": e2e_bytes_per_s / 1e9,
+                    "h2d_gb_per_s": e2e_h2d_per_s / 1e9,
                     "link_peak": link,
-                    "frac_of_link_peak": (e2e_bytes_per_s / 1e9 / link["h2d_gbs"]) if link and link.get("h2d_gbs") else None},
+                    "frac_of_link_peak": (e2e_h2d_per_s / 1e9 / link["h2d_gbs"]) if link and link.get("h2d_gbs") else None,
+                    "frac_note": "upload bytes/s of the whole job / pinned H2D copy rate of all its GPUs copying at once "
+                                 "(87 % of the bytes of a step go up)"},
             "e2e_line": {"value": line_value, "unit": UNIT, "h2d_bytes_per_step": int(lh2d), "d2h_bytes_per_step": int(ld2h),
                          "points_per_function_per_step_per_gpu": ne, "steps": e2e_steps, "gpu_launches": int(line_launches),
                          "api": "ffgpu_eval_line (host pinned t[], x_v = a_v*t + s_v formed on the GPU as "
@@ -767,7 +799,58 @@ def run_cfg_ibp(ff, W, orc, ctx, torch, stream, rank, world, max_over_ranks, all
            "executed_mm_eq_per_probe": x["mm"] + MM_PER_INV * x["inv"],
            "gmm_eq_per_s_per_gpu": n_total / (ms * 1e-3) * (w["mm"] + MM_PER_INV * w["inv"]) / 1e9 / world,
            "compile_and_set_prime_s": compile_s, "verified_bit_exact_vs_oracle": ok,
+           "shared_rows": par.n_table_rows,
            "timing": "CUDA events around evaluate + checksum kernels of every tile, summed, max over ranks"}
+    # A/B: the same collection without shared rows (every power and common factor recomputed where it is used)
+    off = ff.GpuParser(ctx, funs, vars_, table=False)
+    off.set_prime(p)
+    ms_off = 0.0
+    for t in range(2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        off.eval_device(v.data_ptr(), tile, tile, o.data_ptr(), tile, stream=stream)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_off = e0.elapsed_time(e1)
+    xo = off.tape_work()
+    res["without_shared_rows"] = {"ms_per_tile": max_over_ranks(ms_off), "ms_per_tile_with": ms / tiles,
+                                  "executed_mm_eq_per_probe": xo["mm"] + MM_PER_INV * xo["inv"], "slots": off.n_slots}
+    off.close()
+    barrier()
+    if rank == 0:
+        # the plug-in view: ONE call of the black box with a bunch of 128 points in host memory (what a Reconstructor pool
+        # thread does, utils.cpp:305-330) -- GPU through ffgpu_eval, and the reference's evaluate_pre<FFIntVec<128>> on one
+        # host thread beside it (oracle/_ref when it was built, i.e. never on a box without it)
+        pts = ff.synthetic_points(8, 128, p, seed=77)
+        want = orc.parse(funs, vars_, p).eval(pts)
+        got = par.evaluate_pre(pts)
+        for _ in range(5):
+            got = par.evaluate_pre(pts)
+        reps = 30
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            par.evaluate_pre(pts)
+        gpu_us = (time.perf_counter() - t0) / reps * 1e6
+        plug = {"bunch": 128, "gpu_us_per_call": gpu_us, "gpu_function_values_per_s": 128 * F / (gpu_us * 1e-6),
+                "verified_bit_exact_vs_oracle": bool(np.array_equal(got, want))}
+        res["verified_bit_exact_vs_oracle"] = res["verified_bit_exact_vs_oracle"] and plug["verified_bit_exact_vs_oracle"]
+        try:
+            from refs import Ref, have_ref
+            if have_ref():
+                ref = Ref()
+                ref.set_prime(p)
+                rp = ref.parse(funs, vars_)
+                rp.eval(pts, bunch=128, threads=1)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    rp.eval(pts, bunch=128, threads=1)
+                cpu_us = (time.perf_counter() - t0) / 3 * 1e6
+                plug["reference_cpu_us_per_call_1_thread"] = cpu_us
+                plug["speedup_per_call"] = cpu_us / gpu_us
+                rp.close()
+        except Exception as e:
+            plug["reference_cpu_us_per_call_1_thread"] = repr(e)
+        res["plugin_call_bunch_128"] = plug
     par.close()
     return res
 

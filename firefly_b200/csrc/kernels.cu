@@ -567,24 +567,18 @@ __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_
   L.init(prm, smem);
   const FT F = L.F;
 
-#ifdef FFGPU_PREFETCH
-  // experiment: ask for every variable row of the tile before the tape starts
-  if (K == 8) {
-    const u32 nv = prm.n_vars < 32u ? prm.n_vars : 32u;
+  // Ask L2 for this tile's variable rows before the tape starts: the interpreter loads a row where an instruction
+  // uses it, so the first touch of every variable would otherwise pay a full DRAM round trip one after the other
+  // (+2 % on f3 / f4 and the 2000-function collection; with twenty rows as in f1 the requests cost more than they
+  // save: profiles/r02_kbench_prefetch_l2.log against r02_kbench_block_sizes.log, same box).
+  if (K == 8 && prm.n_vars <= 8u) {
 #pragma unroll 1
-    for (u32 v = 0; v < nv; v++) {
+    for (u32 v = 0; v < prm.n_vars; v++) {
       const u64* row = L.vbase + (u64)v * L.in_stride;
 #pragma unroll
-      for (int j = 0; j < Lane<K, THREADS, VEC, FT>::NACC; j++) {
-#if FFGPU_PREFETCH == 2
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(row + L.off[j]));
-#else
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + L.off[j]));
-#endif
-      }
+      for (int j = 0; j < Lane<K, THREADS, VEC, FT>::NACC; j++) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + L.off[j]));
     }
   }
-#endif
   R acc[K];
 #pragma unroll
   for (int k = 0; k < K; k++) acc[k] = opaque(0);
