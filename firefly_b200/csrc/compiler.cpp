@@ -1771,6 +1771,21 @@ void Collection::fuse() {
       i += 3;
       continue;
     }
+    // ---- LOAD.VAR[.P], MUL.CONST  ->  TERM with exponent 1 in load mode (the innermost c * x of a Horner nest)
+    if (a.op == OP_LOAD && a.src == SRC_VAR && (a.flags & ~F_PUSH) == 0 && a.arg < 65536 && i + 1 < n &&
+        plain(tape[i + 1], OP_MUL, SRC_CONST) && patch_of[i + 1] >= 0) {
+      Instr t{};
+      t.op = OP_TERM;
+      t.src = SRC_VAR;
+      t.arg = a.arg | (1u << 16);
+      t.fast = FX_TERM;
+      t.flags = (uint8_t)((a.flags & F_PUSH) | F_CMUL | (TM_LOAD << TM_SHIFT));
+      new_index[i] = new_index[i + 1] = (uint32_t)out.size();
+      patches[patch_of[i + 1]].instr = (uint32_t)out.size();
+      out.push_back(t);
+      i += 2;
+      continue;
+    }
     // ---- ACCUM, ACCUM (two sums fed by the same term)  ->  ACCUM2
     if (a.op == OP_ACCUM && i + 1 < n && tape[i + 1].op == OP_ACCUM && a.arg < 256 && tape[i + 1].arg < 256 &&
         a.arg != tape[i + 1].arg && (a.flags & ~(F_SWAP | F_INIT)) == 0 && (tape[i + 1].flags & ~(F_SWAP | F_INIT)) == 0) {

@@ -745,6 +745,16 @@ __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_
         }
         if (mode != TM_LOAD) L.slot_put(acc, sp);
         else if (ins.flags & F_PUSH) L.slot_put(acc, sp++);
+        if ((ins.arg >> 16) == 1u) {
+          // ACC = c * x: the row goes straight into the accumulator (mode is TM_LOAD here)
+          L.load_var(ins.arg & 0xffffu, acc);
+          if (ins.flags & F_CMUL) {
+            const R c = mkR(ins.imm);
+#pragma unroll
+            for (int k = 0; k < K; k++) acc[k] = fmul(acc[k], c, F);
+          }
+          break;
+        }
         L.load_var(ins.arg & 0xffffu, b);
         pow_from<K>(acc, b, ins.arg >> 16, F);
         if (ins.flags & F_CMUL) {
