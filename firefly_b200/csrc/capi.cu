@@ -216,6 +216,7 @@ int launch_one(ffgpu_tape* t, const ffgpu::Collection& c, const ffgpu::Instr* d_
   prm.n_instr = (uint32_t)(c.tape.size() - 2);
   prm.n_vars = (uint32_t)c.vars.size();
   prm.table = d_table;
+  prm.n_base = d_table ? (uint32_t)c.vars.size() : 0xffffffffu;
   prm.table_stride = table_stride;
   const ffgpu::LaunchShape sh = ffgpu::choose_shape(n_points, c.n_slots, t->ctx->devs[g].sm_count, t->force_k,
                                                     t->force_threads, c.max_chunks, !needs_generic, prm.generic != 0);

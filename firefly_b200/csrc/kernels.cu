@@ -365,7 +365,7 @@ struct Lane {
     out_stride = prm.out_stride;
     tbase = reinterpret_cast<const u64*>(prm.table) + tile;
     t_stride = prm.table_stride;
-    n_base = prm.table ? prm.n_vars : 0xffffffffu;
+    n_base = prm.n_base;
     scratch = smem;
     stk = reinterpret_cast<uint2*>(smem + 64) + threadIdx.x;
     tmp_top = prm.n_slots - 1;

@@ -22,6 +22,7 @@ struct EvalParams {
   uint64_t pinv;              // ... floor((2^126 - 1) / (p << pshift))
   uint32_t n_slots;           // shared-memory slots per probe: spill slots from 0 up, temp slots from n_slots-1 down
   uint32_t n_instr;           // tape length without the terminators
+  uint32_t n_base;            // first variable index that is a shared row (n_vars), 0xffffffff if the collection has none
   uint32_t n_vars;            // rows of `values`; the tape's variables n_vars, n_vars + 1, ... are the shared rows:
   const uint64_t* table;      // device, [n_table_rows][table_stride], written by the collection's pre-pass tape
   uint64_t table_stride;      //   (compiler.cpp, build_table) at the same points; NULL if the collection has none
