@@ -605,8 +605,12 @@ def main():
                     "h2d_gb_per_s": e2e_h2d_per_s / 1e9,
                     "link_peak": link,
                     "frac_of_link_peak": (e2e_h2d_per_s / 1e9 / link["h2d_gbs"]) if link and link.get("h2d_gbs") else None,
-                    "frac_note": "upload bytes/s of the whole job / pinned H2D copy rate of all its GPUs copying at once "
-                                 "(87 % of the bytes of a step go up)"},
+                    "frac_of_both_directions_peak": ((e2e_h2d_per_s + e2e_value * d2h / (len(FUNCS) * ne)) / 1e9 / link["both_gbs_sum"])
+                    if link and link.get("both_gbs_sum") else None,
+                    "frac_note": "frac_of_link_peak = upload bytes/s of the whole job / pinned H2D copy rate of all its GPUs "
+                                 "copying at once (87 % of the bytes of a step go up); frac_of_both_directions_peak = all bytes/s "
+                                 "/ the rate with uploads and downloads running together; the larger of the two is the "
+                                 "ceiling that binds (one GPU: the upload link; eight GPUs of this VM: the host's total)"},
             "e2e_line": {"value": line_value, "unit": UNIT, "h2d_bytes_per_step": int(lh2d), "d2h_bytes_per_step": int(ld2h),
                          "points_per_function_per_step_per_gpu": ne, "steps": e2e_steps, "gpu_launches": int(line_launches),
                          "api": "ffgpu_eval_line (host pinned t[], x_v = a_v*t + s_v formed on the GPU as "
