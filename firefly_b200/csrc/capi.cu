@@ -45,7 +45,7 @@ int cuda_fail(cudaError_t e, const char* what) {
     if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
   } while (0)
 
-constexpr int N_SLOTS = 8;        // concurrent ffgpu_eval callers served without contention
+constexpr int N_SLOTS = 32;       // concurrent ffgpu_eval callers served without contention
 constexpr int N_BUF = 4;          // chunks in flight per slot and device (H2D / kernels / D2H of different chunks overlap)
 
 struct DevBuf {
@@ -148,7 +148,7 @@ struct Coalescer {
 struct ffgpu_tape {
   ffgpu_ctx* ctx = nullptr;
   std::unique_ptr<Coalescer> co{new Coalescer};
-  int coalesce = -1;                   // -1: FFGPU_COALESCE / default on
+  int coalesce = -1;                   // -1: FFGPU_COALESCE / default off
   size_t coalesce_cap = 0;             // points per batch (0: automatic)
   ffgpu::Collection col;
   std::vector<ffgpu::Instr*> d_tape;   // per device
@@ -688,7 +688,11 @@ inline void cpu_relax() {
 int coalesce_default() {
   static const int v = [] {
     const char* e = std::getenv("FFGPU_COALESCE");
-    return e && *e ? std::atoi(e) : 1;
+    // Off unless asked for: on a B200 box the unmodified Reconstructor sees a LOWER black-box time per probe when every
+    // call launches on its own slot's stream (32 slots) than when concurrent calls wait for each other to share a
+    // launch -- f4, 16 threads: 2.6e-5 s against 3.0e-5 s; s_y_4_v, 4 threads: 4.7e-4 against 7.6e-4
+    // (profiles/r02_reconstruct_aggregator_on_off.log).  What the aggregator buys is an eighth to a twelfth of the launches.
+    return e && *e ? std::atoi(e) : 0;
   }();
   return v;
 }

@@ -211,8 +211,10 @@ const char* ffgpu_queue_error(ffgpu_queue*);
 int ffgpu_set_launch(ffgpu_tape*, int probes_per_thread, int threads_per_block);
 /* Aggregator of concurrent small ffgpu_eval calls (a few hundred points at most per call, many caller threads -- the
  * Reconstructor's thread pool, Reconstructor.hpp:3325-3477 with bunches from utils.cpp:305-330): calls that arrive while
- * the batch before them is on the GPU share ONE launch; a lone caller is served at once.  enable: 1 on (default), 0 off
- * (every call its own launch), -1 environment FFGPU_COALESCE / default.  max_points: points per shared launch (0 =
+ * the batch before them is on the GPU share ONE launch; a lone caller is served at once.  enable: 1 on, 0 off (every
+ * call its own launch on its caller slot's stream), -1 environment FFGPU_COALESCE / default OFF: measured under the
+ * unmodified Reconstructor, sharing cuts the launches to an eighth but costs latency (callers wait for each other), and
+ * the reference's own average black-box time is lower without it.  max_points: points per shared launch (0 =
  * automatic, 512..4096 by the collection's width) -- what GpuBlackBox::set_bunch_size steers.  The values are the same
  * either way.  Stats: launches shared so far, calls served by them, points. */
 int ffgpu_set_coalesce(ffgpu_tape*, int enable, size_t max_points);

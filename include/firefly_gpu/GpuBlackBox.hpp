@@ -93,12 +93,17 @@ class GpuBlackBox : public BlackBoxBase<GpuBlackBox> {
   }
 
   // The bunch size is a Reconstructor constructor argument in 2.0.3 (Reconstructor.hpp:73): every pool thread calls
-  // with up to `bunch` points.  The GPU evaluator accepts any batch; concurrent small calls share a launch
-  // (ffgpu_set_coalesce), and the bunch size sets how many points such a shared launch may hold -- room for 32
-  // callers' bunches, at least 512 points.
+  // with up to `bunch` points.  The GPU evaluator accepts any batch.  If the aggregator of concurrent small calls is
+  // switched on (set_coalesce(true) or FFGPU_COALESCE=1; off by default, see ffgpu.h), the bunch size sets how many
+  // points a shared launch may hold -- room for 32 callers' bunches, at least 512 points.
   void set_bunch_size(uint32_t bunch) {
     bunch_hint_ = bunch ? bunch : 1;
-    if (ffgpu_set_coalesce(tape_, -1, std::max<size_t>(512, (size_t)32 * bunch_hint_))) die(ffgpu_last_error());
+    if (ffgpu_set_coalesce(tape_, coalesce_, std::max<size_t>(512, (size_t)32 * bunch_hint_))) die(ffgpu_last_error());
+  }
+  // concurrent small calls share launches (fewer launches, more latency per call)
+  void set_coalesce(bool on) {
+    coalesce_ = on ? 1 : 0;
+    set_bunch_size(bunch_hint_);
   }
   uint32_t bunch_size() const { return bunch_hint_; }
   // launches that the aggregator shared among callers so far, calls they served, points
@@ -134,6 +139,7 @@ class GpuBlackBox : public BlackBoxBase<GpuBlackBox> {
   ffgpu_tape* tape_ = nullptr;
   size_t n_vars_ = 0, n_out_ = 0;
   uint32_t bunch_hint_ = 1;
+  int coalesce_ = -1;          // -1: environment FFGPU_COALESCE / default (off)
 };
 
 }  // namespace firefly

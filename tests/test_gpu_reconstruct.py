@@ -36,8 +36,10 @@ def test_reconstruction_identical(tmp_path, name, bunch, threads):
     g = load_golden(name)
     f = tmp_path / (name + ".m")
     f.write_text(";\n".join(g["functions"]) + ";\n")
+    # the full f4 run also exercises the aggregator of concurrent small calls under the real thread pool (off by default)
+    env = dict(os.environ, FFGPU_COALESCE="1") if name == "f4" else None
     r = subprocess.run([BIN, str(f), str(bunch), str(threads), *g["vars"]], cwd=tmp_path, capture_output=True,
-                       text=True, timeout=1200)
+                       text=True, timeout=1200, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "0 differ" in r.stdout
     # the GPU black box really ran on the GPU
