@@ -43,6 +43,7 @@ NO_CSE = 2
 NO_FUSE = 4
 NO_CROSS = 16
 NO_TABLE = 32
+NO_SPLIT = 64
 ADD_PLAIN, ADD_VALIDATE, ADD_NO_DUPLICATES = 1, 2, 4
 
 
@@ -80,7 +81,10 @@ def _load() -> C.CDLL:
         "ffgpu_n_structural_duplicates": (C.c_size_t, [C.c_void_p]),
         "ffgpu_n_shared_denominators": (C.c_size_t, [C.c_void_p]),
         "ffgpu_n_table_rows": (C.c_size_t, [C.c_void_p]),
-        "ffgpu_get_table_tape": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t]),
+        "ffgpu_get_table_tape": (C.c_size_t, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+        "ffgpu_n_table_levels": (C.c_size_t, [C.c_void_p]),
+        "ffgpu_n_table_rows_level": (C.c_size_t, [C.c_void_p, C.c_size_t]),
+        "ffgpu_n_split_rows": (C.c_size_t, [C.c_void_p]),
         "ffgpu_rpn": (C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
         "ffgpu_get_tape": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t]),
         "ffgpu_work": (None, [C.c_void_p, u64p]),
@@ -139,7 +143,7 @@ lib = _load()
 EXPORTS = [
     "ffgpu_create", "ffgpu_destroy", "ffgpu_n_devices", "ffgpu_last_error", "ffgpu_compile", "ffgpu_compile_text",
     "ffgpu_compile_file", "ffgpu_tape_clone", "ffgpu_tape_destroy", "ffgpu_n_vars", "ffgpu_n_functions", "ffgpu_n_out", "ffgpu_n_instr",
-    "ffgpu_stack_depth", "ffgpu_n_temps", "ffgpu_n_slots", "ffgpu_cse_fallbacks", "ffgpu_n_structural_duplicates", "ffgpu_n_shared_denominators", "ffgpu_n_table_rows", "ffgpu_get_table_tape", "ffgpu_rpn", "ffgpu_get_tape", "ffgpu_work", "ffgpu_tape_work", "ffgpu_set_factors", "ffgpu_set_prime", "ffgpu_get_prime",
+    "ffgpu_stack_depth", "ffgpu_n_temps", "ffgpu_n_slots", "ffgpu_cse_fallbacks", "ffgpu_n_structural_duplicates", "ffgpu_n_shared_denominators", "ffgpu_n_table_rows", "ffgpu_get_table_tape", "ffgpu_n_table_levels", "ffgpu_n_table_rows_level", "ffgpu_n_split_rows", "ffgpu_rpn", "ffgpu_get_tape", "ffgpu_work", "ffgpu_tape_work", "ffgpu_set_factors", "ffgpu_set_prime", "ffgpu_get_prime",
     "ffgpu_add_function", "ffgpu_add_function_rpn", "ffgpu_trim", "ffgpu_is_stale",
     "ffgpu_n_primes", "ffgpu_prime", "ffgpu_eval", "ffgpu_eval_line", "ffgpu_eval_wire", "ffgpu_eval_device", "ffgpu_host_alloc", "ffgpu_host_free",
     "ffgpu_queue_create", "ffgpu_queue_destroy", "ffgpu_queue_push", "ffgpu_queue_push_many", "ffgpu_queue_push_line",
@@ -204,10 +208,10 @@ class GpuParser:
 
     def __init__(self, ctx: Optional[Context], functions=None, vars: Sequence[str] = (), check_is_equal: bool = False,
                  *, file: Optional[str] = None, text: Optional[str] = None, cse: bool = True,
-                 temps: int = 0, fuse: bool = True, cross: bool = True, table: bool = True):
+                 temps: int = 0, fuse: bool = True, cross: bool = True, table: bool = True, split: bool = True):
         self.ctx = ctx
         ch = ctx.h if ctx is not None else None
-        flags = (CHECK_IS_EQUAL if check_is_equal else 0) | (0 if cse else NO_CSE) | (0 if fuse else NO_FUSE) | (0 if cross else NO_CROSS) | (0 if table else NO_TABLE) | ((temps & 15) << 8)
+        flags = (CHECK_IS_EQUAL if check_is_equal else 0) | (0 if cse else NO_CSE) | (0 if fuse else NO_FUSE) | (0 if cross else NO_CROSS) | (0 if table else NO_TABLE) | (0 if split else NO_SPLIT) | ((temps & 15) << 8)
         v = _strs(vars)
         if file is not None:
             self.h = lib.ffgpu_compile_file(ch, file.encode(), v, len(vars), flags)
@@ -241,13 +245,22 @@ class GpuParser:
         lib.ffgpu_get_tape(self.h, arr.ctypes.data, n)
         return arr
 
-    def table_tape(self) -> np.ndarray:
-        """the tape of the shared rows (output r = row r = variable n_vars + r of tape()); empty if there are none"""
-        n = lib.ffgpu_get_table_tape(self.h, None, 0)
+    def table_tape(self, level: int = 0) -> np.ndarray:
+        """the tape of the shared rows of one level (its output r = row offset + r = a variable of tape() and of the
+        levels after it); empty if there is no such level"""
+        n = lib.ffgpu_get_table_tape(self.h, level, None, 0)
         arr = np.zeros(n, dtype=INSTR_DTYPE)
         if n:
-            lib.ffgpu_get_table_tape(self.h, arr.ctypes.data, n)
+            lib.ffgpu_get_table_tape(self.h, level, arr.ctypes.data, n)
         return arr
+
+    def table_levels(self) -> list:
+        """[(tape, rows)] of every level of shared rows, in evaluation order"""
+        return [(self.table_tape(l), lib.ffgpu_n_table_rows_level(self.h, l)) for l in range(lib.ffgpu_n_table_levels(self.h))]
+
+    @property
+    def n_split_rows(self) -> int:
+        return lib.ffgpu_n_split_rows(self.h)
 
     @property
     def n_table_rows(self) -> int:

@@ -153,9 +153,10 @@ struct ffgpu_tape {
   ffgpu::Collection col;
   std::vector<ffgpu::Instr*> d_tape;   // per device
   std::vector<uint32_t*> d_chunks;     // per device: Collection::chunk_table
-  std::vector<ffgpu::Instr*> d_pre;    // per device: the tape of the shared rows (Collection::pre), if the collection has any
-  std::vector<uint32_t*> d_pre_chunks;
-  bool pre_needs_generic = true;
+  // per level of shared rows (Collection::pre: 0 = common sub-expressions, 1 = partial sums) and device: tape, chunk table
+  std::vector<ffgpu::Instr*> d_pre[2];
+  std::vector<uint32_t*> d_pre_chunks[2];
+  bool pre_needs_generic[2] = {true, true};
   int force_k = 0, force_threads = 0;
   size_t chunk = 0;
   bool needs_generic = true;           // the resolved tape has instructions without a fast dispatch code
@@ -181,8 +182,10 @@ ffgpu_tape* finish_compile(ffgpu_ctx* ctx, std::unique_ptr<ffgpu_tape> t, bool o
   if (ctx) {
     t->d_tape.assign(ctx->devs.size(), nullptr);
     t->d_chunks.assign(ctx->devs.size(), nullptr);
-    t->d_pre.assign(ctx->devs.size(), nullptr);
-    t->d_pre_chunks.assign(ctx->devs.size(), nullptr);
+    for (int l = 0; l < 2; ++l) {
+      t->d_pre[l].assign(ctx->devs.size(), nullptr);
+      t->d_pre_chunks[l].assign(ctx->devs.size(), nullptr);
+    }
   }
   return t.release();
 }
@@ -214,9 +217,9 @@ int launch_one(ffgpu_tape* t, const ffgpu::Collection& c, const ffgpu::Instr* d_
   if (prm.generic) ffgpu::barrett_constants(c.prime, &prm.pinv, &prm.pshift);
   prm.n_slots = c.n_slots;
   prm.n_instr = (uint32_t)(c.tape.size() - 2);
-  prm.n_vars = (uint32_t)c.vars.size();
+  prm.n_vars = c.n_input_vars ? c.n_input_vars : (uint32_t)c.vars.size();     // a rows' collection also counts rows as variables
   prm.table = d_table;
-  prm.n_base = d_table ? (uint32_t)c.vars.size() : 0xffffffffu;
+  prm.n_base = d_table ? prm.n_vars : 0xffffffffu;
   prm.table_stride = table_stride;
   const ffgpu::LaunchShape sh = ffgpu::choose_shape(n_points, c.n_slots, t->ctx->devs[g].sm_count, t->force_k,
                                                     t->force_threads, c.max_chunks, !needs_generic, prm.generic != 0);
@@ -241,8 +244,7 @@ int launch(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, siz
   if (c.pre.empty())
     return launch_one(t, c, t->d_tape[g], t->d_chunks[g], t->needs_generic, g, d_values, in_stride, n_points, d_out,
                       out_stride, nullptr, 0, stream);
-  const ffgpu::Collection& pc = c.pre[0];
-  const size_t rows = pc.n_out;
+  const size_t rows = c.n_table_rows;
   constexpr size_t BUDGET = 96u << 20;
   size_t sub = n_points;
   if (rows * n_points * 8 > BUDGET) sub = std::max<size_t>((BUDGET / (rows * 8)) & ~(size_t)2047, 16384);
@@ -252,8 +254,10 @@ int launch(ffgpu_tape* t, int g, const uint64_t* d_values, size_t in_stride, siz
   int rc = 0;
   for (size_t off = 0; off < n_points && !rc; off += sub) {
     const size_t cnt = std::min(sub, n_points - off);
-    rc = launch_one(t, pc, t->d_pre[g], t->d_pre_chunks[g], t->pre_needs_generic, g, d_values + off, in_stride, cnt, tab,
-                    stride, nullptr, 0, stream);
+    // the rows level by level (a level reads the rows of the levels before it), then the functions
+    for (size_t l = 0; l < c.pre.size() && !rc; ++l)
+      rc = launch_one(t, c.pre[l], t->d_pre[l][g], t->d_pre_chunks[l][g], t->pre_needs_generic[l], g, d_values + off, in_stride,
+                      cnt, tab + (size_t)c.pre_row_offset()[l] * stride, stride, l ? tab : nullptr, stride, stream);
     if (!rc)
       rc = launch_one(t, c, t->d_tape[g], t->d_chunks[g], t->needs_generic, g, d_values + off, in_stride, cnt,
                       d_out + off, out_stride, tab, stride, stream);
@@ -279,12 +283,14 @@ void drop_device_copies(ffgpu_tape* t) {
     cudaDeviceSynchronize();
     if (t->d_tape[g]) cudaFree(t->d_tape[g]);
     if (t->d_chunks[g]) cudaFree(t->d_chunks[g]);
-    if (t->d_pre[g]) cudaFree(t->d_pre[g]);
-    if (t->d_pre_chunks[g]) cudaFree(t->d_pre_chunks[g]);
+    for (int l = 0; l < 2; ++l) {
+      if (t->d_pre[l][g]) cudaFree(t->d_pre[l][g]);
+      if (t->d_pre_chunks[l][g]) cudaFree(t->d_pre_chunks[l][g]);
+      t->d_pre[l][g] = nullptr;
+      t->d_pre_chunks[l][g] = nullptr;
+    }
     t->d_tape[g] = nullptr;
     t->d_chunks[g] = nullptr;
-    t->d_pre[g] = nullptr;
-    t->d_pre_chunks[g] = nullptr;
   }
 }
 
@@ -414,6 +420,7 @@ ffgpu_tape* ffgpu_compile(ffgpu_ctx* ctx, const char* const* functions, size_t n
   t->col.enable_fuse = !(flags & FFGPU_NO_FUSE);
   t->col.enable_cross = !(flags & FFGPU_NO_CROSS);
   t->col.enable_table = !(flags & FFGPU_NO_TABLE) && !std::getenv("FFGPU_NO_TABLE");
+  t->col.enable_split = !(flags & FFGPU_NO_SPLIT) && !std::getenv("FFGPU_NO_SPLIT");
   t->col.temp_budget = (int)((flags >> FFGPU_TEMPS_SHIFT) & 15u);
   const bool ok = t->col.compile_strings(to_vec(functions, n_functions), to_vec(vars, n_vars),
                                          (flags & FFGPU_CHECK_IS_EQUAL) != 0, err);
@@ -428,6 +435,7 @@ ffgpu_tape* ffgpu_compile_text(ffgpu_ctx* ctx, const char* text, const char* con
   t->col.enable_fuse = !(flags & FFGPU_NO_FUSE);
   t->col.enable_cross = !(flags & FFGPU_NO_CROSS);
   t->col.enable_table = !(flags & FFGPU_NO_TABLE) && !std::getenv("FFGPU_NO_TABLE");
+  t->col.enable_split = !(flags & FFGPU_NO_SPLIT) && !std::getenv("FFGPU_NO_SPLIT");
   t->col.temp_budget = (int)((flags >> FFGPU_TEMPS_SHIFT) & 15u);
   const bool ok = t->col.compile_text(text ? text : "", to_vec(vars, n_vars), (flags & FFGPU_CHECK_IS_EQUAL) != 0, err);
   return finish_compile(ctx, std::move(t), ok, err);
@@ -461,8 +469,10 @@ ffgpu_tape* ffgpu_tape_clone(const ffgpu_tape* t) {
   if (t->ctx) {
     n->d_tape.assign(t->ctx->devs.size(), nullptr);
     n->d_chunks.assign(t->ctx->devs.size(), nullptr);
-    n->d_pre.assign(t->ctx->devs.size(), nullptr);
-    n->d_pre_chunks.assign(t->ctx->devs.size(), nullptr);
+    for (int l = 0; l < 2; ++l) {
+      n->d_pre[l].assign(t->ctx->devs.size(), nullptr);
+      n->d_pre_chunks[l].assign(t->ctx->devs.size(), nullptr);
+    }
   }
   // the copy gets device buffers of its own, for the prime the original is resolved for
   if (t->col.prime && !t->col.stale && ffgpu_set_prime(n.get(), t->col.prime)) return nullptr;
@@ -478,8 +488,10 @@ void ffgpu_tape_destroy(ffgpu_tape* t) {
     cudaDeviceSynchronize();
     cudaFree(t->d_tape[g]);
     if (t->d_chunks[g]) cudaFree(t->d_chunks[g]);
-    if (t->d_pre[g]) cudaFree(t->d_pre[g]);
-    if (t->d_pre_chunks[g]) cudaFree(t->d_pre_chunks[g]);
+    for (int l = 0; l < 2; ++l) {
+      if (t->d_pre[l][g]) cudaFree(t->d_pre[l][g]);
+      if (t->d_pre_chunks[l][g]) cudaFree(t->d_pre_chunks[l][g]);
+    }
   }
   delete t;
 }
@@ -496,9 +508,12 @@ size_t ffgpu_n_structural_duplicates(const ffgpu_tape* t) { return t->col.n_stru
 size_t ffgpu_n_shared_denominators(const ffgpu_tape* t) { return t->col.n_shared_denominators; }
 
 size_t ffgpu_n_table_rows(const ffgpu_tape* t) { return t->col.n_table_rows; }
-size_t ffgpu_get_table_tape(const ffgpu_tape* t, void* buf, size_t cap) {
-  if (t->col.pre.empty()) return 0;
-  const std::vector<ffgpu::Instr>& tp = t->col.pre[0].tape;
+size_t ffgpu_n_table_levels(const ffgpu_tape* t) { return t->col.pre.size(); }
+size_t ffgpu_n_table_rows_level(const ffgpu_tape* t, size_t level) { return level < t->col.pre.size() ? t->col.pre[level].n_out : 0; }
+size_t ffgpu_n_split_rows(const ffgpu_tape* t) { return t->col.n_split_rows; }
+size_t ffgpu_get_table_tape(const ffgpu_tape* t, size_t level, void* buf, size_t cap) {
+  if (level >= t->col.pre.size()) return 0;
+  const std::vector<ffgpu::Instr>& tp = t->col.pre[level].tape;
   const size_t n = std::min(cap, tp.size());
   if (buf && n) std::memcpy(buf, tp.data(), n * sizeof(ffgpu::Instr));
   return tp.size();
@@ -558,9 +573,10 @@ int ffgpu_set_prime(ffgpu_tape* t, uint64_t p) {
   if (rebuilt) drop_device_copies(t);
   t->needs_generic = false;
   for (const ffgpu::Instr& in : t->col.tape) t->needs_generic |= in.fast == ffgpu::FX_GENERIC && in.op != ffgpu::OP_HALT;
-  t->pre_needs_generic = false;
-  if (!t->col.pre.empty())
-    for (const ffgpu::Instr& in : t->col.pre[0].tape) t->pre_needs_generic |= in.fast == ffgpu::FX_GENERIC && in.op != ffgpu::OP_HALT;
+  for (size_t l = 0; l < t->col.pre.size() && l < 2; ++l) {
+    t->pre_needs_generic[l] = false;
+    for (const ffgpu::Instr& in : t->col.pre[l].tape) t->pre_needs_generic[l] |= in.fast == ffgpu::FX_GENERIC && in.op != ffgpu::OP_HALT;
+  }
   const size_t bytes = t->col.tape.size() * sizeof(ffgpu::Instr);
   for (size_t g = 0; t->ctx && g < t->ctx->devs.size(); ++g) {
     DeviceGuard guard(t->ctx->devs[g].id);
@@ -573,16 +589,16 @@ int ffgpu_set_prime(ffgpu_tape* t, uint64_t p) {
                          cudaMemcpyHostToDevice));
     }
     FF_CUDA(cudaMemcpy(t->d_tape[g], t->col.tape.data(), bytes, cudaMemcpyHostToDevice));
-    if (!t->col.pre.empty()) {
-      const ffgpu::Collection& pc = t->col.pre[0];
+    for (size_t l = 0; l < t->col.pre.size() && l < 2; ++l) {
+      const ffgpu::Collection& pc = t->col.pre[l];
       const size_t pbytes = pc.tape.size() * sizeof(ffgpu::Instr);
-      if (!t->d_pre[g]) FF_CUDA(cudaMalloc(&t->d_pre[g], pbytes));
-      if (!t->d_pre_chunks[g]) {
-        FF_CUDA(cudaMalloc(&t->d_pre_chunks[g], pc.chunk_table.size() * sizeof(uint32_t)));
-        FF_CUDA(cudaMemcpy(t->d_pre_chunks[g], pc.chunk_table.data(), pc.chunk_table.size() * sizeof(uint32_t),
+      if (!t->d_pre[l][g]) FF_CUDA(cudaMalloc(&t->d_pre[l][g], pbytes));
+      if (!t->d_pre_chunks[l][g]) {
+        FF_CUDA(cudaMalloc(&t->d_pre_chunks[l][g], pc.chunk_table.size() * sizeof(uint32_t)));
+        FF_CUDA(cudaMemcpy(t->d_pre_chunks[l][g], pc.chunk_table.data(), pc.chunk_table.size() * sizeof(uint32_t),
                            cudaMemcpyHostToDevice));
       }
-      FF_CUDA(cudaMemcpy(t->d_pre[g], pc.tape.data(), pbytes, cudaMemcpyHostToDevice));
+      FF_CUDA(cudaMemcpy(t->d_pre[l][g], pc.tape.data(), pbytes, cudaMemcpyHostToDevice));
     }
   }
   return 0;

@@ -1238,26 +1238,211 @@ void copy_tree(const Function& f, int32_t root, Function& g, LeafVar leaf_var) {
 }
 }  // namespace
 
+// ---- long sums ---------------------------------------------------------------------------------------------------
+// A function that is one long sum (an amplitude, a reduction coefficient with 10^4 terms) is a serial walk for ONE
+// thread block per tile of points: at the Reconstructor's bunch sizes (<= 128 points) the rest of the chip idles.  Its
+// sums are cut into partial sums of about SPLIT_TARGET tree nodes each; every partial sum becomes a shared row of
+// level 1 (evaluated by the rows' tape, whose chunks run on different SMs), the function adds the rows up.  Addition
+// in Z_p is associative and commutative: the value is unchanged.
+namespace {
+constexpr uint32_t GROUP_BASE = 1u << 24;      // placeholder variable index of partial sum g until the row count is known
+constexpr uint32_t SPLIT_MIN = 768;            // tree nodes below which a sum is left alone
+constexpr uint32_t SPLIT_TARGET = 320;         // tree nodes per partial sum
+constexpr uint32_t SPLIT_MAX_GROUPS = 96;      // partial sums per sum at most
+
+// append the sub-tree of f below `root` to g (children first); returns the index of its root in g
+int32_t append_subtree(const Function& f, int32_t root, Function& g, std::vector<int32_t>& remap) {
+  std::vector<int32_t> reach, st{root};
+  while (!st.empty()) {
+    const int32_t i = st.back();
+    st.pop_back();
+    reach.push_back(i);
+    if (f.nodes[i].l < 0) continue;
+    st.push_back(f.nodes[i].l);
+    st.push_back(f.nodes[i].r);
+  }
+  std::sort(reach.begin(), reach.end());
+  for (int32_t i : reach) {
+    Node n = f.nodes[i];
+    if (n.kind == N_NUM) {
+      n.lit = (uint32_t)g.literals.size();
+      g.literals.push_back(f.literals[f.nodes[i].lit]);
+    } else if (n.l >= 0) {
+      n.l = remap[n.l];
+      n.r = remap[n.r];
+    }
+    remap[i] = (int32_t)g.nodes.size();
+    g.nodes.push_back(n);
+  }
+  return remap[root];
+}
+int32_t push_binary(Function& g, NodeKind kind, int32_t l, int32_t r) {
+  Node n{};
+  n.kind = kind;
+  n.l = l;
+  n.r = r;
+  n.is_const = g.nodes[l].is_const && g.nodes[r].is_const;
+  g.nodes.push_back(n);
+  return (int32_t)g.nodes.size() - 1;
+}
+int32_t push_var(Function& g, uint32_t var) {
+  Node n{};
+  n.kind = N_VAR;
+  n.var = var;
+  n.l = n.r = -1;
+  n.is_const = false;
+  g.nodes.push_back(n);
+  return (int32_t)g.nodes.size() - 1;
+}
+// Cut the long sums of f into partial sums (appended to `groups`); `out` becomes f with each of them replaced by the
+// sum of its placeholder variables.  Returns false (and leaves `out` empty) if f has no long sum.
+bool split_long_sums(const Function& f, std::vector<Function>& groups, Function& out) {
+  const size_t n = f.nodes.size();
+  if (n < SPLIT_MIN) return false;
+  std::vector<uint32_t> size(n, 1);
+  for (size_t i = 0; i < n; ++i)
+    if (f.nodes[i].l >= 0) size[i] = 1 + size[f.nodes[i].l] + size[f.nodes[i].r];
+  auto is_sum = [&](int32_t i) { return !f.nodes[i].is_const && (f.nodes[i].kind == N_ADD || f.nodes[i].kind == N_SUB); };
+  // the long sums: the outermost ones, wherever they sit (numerator, denominator, a factor, the base of a power)
+  std::vector<int32_t> tops;
+  {
+    std::vector<int32_t> st{f.root};
+    while (!st.empty()) {
+      const int32_t i = st.back();
+      st.pop_back();
+      if (size[i] < SPLIT_MIN || f.nodes[i].l < 0 || f.nodes[i].is_const) continue;
+      if (is_sum(i)) { tops.push_back(i); continue; }
+      st.push_back(f.nodes[i].l);
+      st.push_back(f.nodes[i].r);
+    }
+    std::sort(tops.begin(), tops.end());
+  }
+  struct Term { int32_t node; bool minus; };
+  std::unordered_map<int32_t, std::pair<uint32_t, uint32_t>> repl;       // sum node -> (first group, count)
+  std::vector<int32_t> remap(n, -1);
+  for (int32_t top : tops) {
+    std::vector<Term> terms, st{{top, false}};
+    while (!st.empty()) {
+      const Term t = st.back();
+      st.pop_back();
+      if (!is_sum(t.node)) { terms.push_back(t); continue; }
+      const Node& nd = f.nodes[t.node];
+      st.push_back(Term{nd.r, nd.kind == N_SUB ? !t.minus : t.minus});      // right first: the left term comes out first
+      st.push_back(Term{nd.l, t.minus});
+    }
+    uint64_t total = 0;
+    for (const Term& t : terms) total += size[t.node];
+    const uint32_t want = (uint32_t)std::min<uint64_t>(SPLIT_MAX_GROUPS, std::max<uint64_t>(2, total / SPLIT_TARGET));
+    if (terms.size() < 2) continue;
+    const uint64_t per = (total + want - 1) / want;
+    const uint32_t first = (uint32_t)groups.size();
+    size_t k = 0;
+    while (k < terms.size()) {
+      Function g;
+      uint64_t acc_size = 0;
+      int32_t acc = -1;
+      std::vector<Term> mine;
+      while (k < terms.size() && (mine.empty() || acc_size + size[terms[k].node] / 2 < per)) {
+        acc_size += size[terms[k].node];
+        mine.push_back(terms[k++]);
+      }
+      // a term with a plus sign leads; if there is none the sum starts from the literal 0
+      size_t lead = 0;
+      while (lead < mine.size() && mine[lead].minus) ++lead;
+      if (lead == mine.size()) {
+        Node z{};
+        z.kind = N_NUM;
+        z.is_const = true;
+        z.l = z.r = -1;
+        z.lit = (uint32_t)g.literals.size();
+        g.literals.push_back(Literal{"0"});
+        g.nodes.push_back(z);
+        acc = (int32_t)g.nodes.size() - 1;
+      } else {
+        acc = append_subtree(f, mine[lead].node, g, remap);
+      }
+      for (size_t q = 0; q < mine.size(); ++q) {
+        if (q == lead) continue;
+        const int32_t t = append_subtree(f, mine[q].node, g, remap);
+        acc = push_binary(g, mine[q].minus ? N_SUB : N_ADD, acc, t);
+      }
+      g.root = acc;
+      groups.push_back(std::move(g));
+    }
+    repl[top] = {first, (uint32_t)groups.size() - first};
+  }
+  if (repl.empty()) return false;
+  // f with the long sums replaced by sums of placeholder variables
+  std::vector<int32_t> reach, st{f.root};
+  while (!st.empty()) {
+    const int32_t i = st.back();
+    st.pop_back();
+    reach.push_back(i);
+    if (repl.count(i) || f.nodes[i].l < 0) continue;
+    st.push_back(f.nodes[i].l);
+    st.push_back(f.nodes[i].r);
+  }
+  std::sort(reach.begin(), reach.end());
+  out = Function{};
+  for (int32_t i : reach) {
+    auto it = repl.find(i);
+    if (it != repl.end()) {
+      int32_t acc = push_var(out, GROUP_BASE + it->second.first);
+      for (uint32_t q = 1; q < it->second.second; ++q) acc = push_binary(out, N_ADD, acc, push_var(out, GROUP_BASE + it->second.first + q));
+      remap[i] = acc;
+      continue;
+    }
+    Node nd = f.nodes[i];
+    if (nd.kind == N_NUM) {
+      nd.lit = (uint32_t)out.literals.size();
+      out.literals.push_back(f.literals[f.nodes[i].lit]);
+    } else if (nd.l >= 0) {
+      nd.l = remap[nd.l];
+      nd.r = remap[nd.r];
+    }
+    remap[i] = (int32_t)out.nodes.size();
+    out.nodes.push_back(nd);
+  }
+  out.root = remap[f.root];
+  out.rpn = f.rpn;
+  return true;
+}
+}  // namespace
+
 void Collection::build_table(const std::vector<int32_t>& dup_of) {
   lowered_.clear();
   pre.clear();
   n_table_rows = 0;
   const size_t nf = functions.size();
-  if (!enable_cse || !enable_cross || !enable_table || nf < 2 || vars.size() >= 60000) return;
+  if (!enable_cse || !enable_cross || !enable_table || nf == 0 || vars.size() >= 60000) return;
+  const uint32_t n_base = (uint32_t)vars.size();
+  // ---- long sums -> partial sums (level-1 rows)
+  std::vector<Function> groups;
+  std::vector<Function> cut(nf);               // functions whose long sums were replaced (no nodes: unchanged)
+  if (enable_split)
+    for (size_t i = 0; i < nf; ++i)
+      if (dup_of[i] < 0 && groups.size() < 4 * SPLIT_MAX_GROUPS) split_long_sums(functions[i], groups, cut[i]);
+  if (nf < 2 && groups.empty()) return;
+  // the units the sharing pass looks at: every function that is emitted, and the partial sums
+  std::vector<const Function*> unit;
+  std::vector<int64_t> unit_fn;                // function index, or -1 - g for partial sum g
+  for (size_t i = 0; i < nf; ++i)
+    if (dup_of[i] < 0) { unit.push_back(cut[i].nodes.empty() ? &functions[i] : &cut[i]); unit_fn.push_back((int64_t)i); }
+  for (size_t g = 0; g < groups.size(); ++g) { unit.push_back(&groups[g]); unit_fn.push_back(-1 - (int64_t)g); }
+  const size_t nu = unit.size();
   struct Cand {
-    uint32_t fn;
+    uint32_t fn;         // unit of the first occurrence
     int32_t node;
     uint32_t cost;       // multiplications of one evaluation of the whole sub-tree
     uint32_t refs;       // occurrences not covered by a larger selected sub-tree
     bool selected;
     int32_t row;
   };
-  std::vector<std::vector<Fp>> fps(nf);
+  std::vector<std::vector<Fp>> fps(nu);
   std::unordered_map<FpKey, Cand, FpKeyHash> cands;
   std::vector<uint32_t> cost;
-  for (size_t i = 0; i < nf; ++i) {
-    if (dup_of[i] >= 0) continue;
-    const Function& f = functions[i];
+  for (size_t i = 0; i < nu; ++i) {
+    const Function& f = *unit[i];
     fingerprints(f, fps[i]);
     cost.assign(f.nodes.size(), 0);
     for (size_t k = 0; k < f.nodes.size(); ++k) {
@@ -1278,9 +1463,8 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
   auto count_refs = [&]() {
     for (auto& kv : cands) kv.second.refs = 0;
     std::vector<int32_t> st;
-    for (size_t i = 0; i < nf; ++i) {
-      if (dup_of[i] >= 0) continue;
-      const Function& f = functions[i];
+    for (size_t i = 0; i < nu; ++i) {
+      const Function& f = *unit[i];
       st.assign(1, f.root);
       while (!st.empty()) {
         const int32_t k = st.back();
@@ -1306,7 +1490,6 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
   std::vector<Cand*> chosen;
   for (auto& kv : cands)
     if (kv.second.selected) chosen.push_back(&kv.second);
-  if (chosen.empty()) return;
   auto benefit = [](const Cand* c) { return (uint64_t)(c->refs - 1) * c->cost; };
   std::sort(chosen.begin(), chosen.end(), [&](const Cand* x, const Cand* y) {
     if (benefit(x) != benefit(y)) return benefit(x) > benefit(y);
@@ -1323,54 +1506,78 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
       else c->selected = false;
     }
     chosen.swap(kept);
-    if (chosen.empty()) return;
   }
+  if (chosen.empty() && groups.empty()) return;
   // rows in the order of first appearance (deterministic tapes)
   std::sort(chosen.begin(), chosen.end(), [](const Cand* x, const Cand* y) { return x->fn != y->fn ? x->fn < y->fn : x->node < y->node; });
   std::vector<Function> table(chosen.size());
   for (size_t r = 0; r < chosen.size(); ++r) {
     chosen[r]->row = (int32_t)r;
-    copy_tree(functions[chosen[r]->fn], chosen[r]->node, table[r], [](int32_t) { return (int64_t)-1; });
+    copy_tree(*unit[chosen[r]->fn], chosen[r]->node, table[r], [](int32_t) { return (int64_t)-1; });
     compute_needs(table[r]);
   }
   std::vector<std::vector<Fp>> tfps(table.size());
   for (size_t r = 0; r < table.size(); ++r) fingerprints(table[r], tfps[r]);
-  // the functions with every selected occurrence replaced by its row; equal fingerprints are confirmed exactly
-  const uint32_t n_base = (uint32_t)vars.size();
-  lowered_.resize(nf);
-  for (size_t i = 0; i < nf; ++i) {
-    const Function& f = functions[i];
-    if (dup_of[i] >= 0) { lowered_[i] = f; continue; }
-    copy_tree(f, f.root, lowered_[i], [&](int32_t k) -> int64_t {
+  // every unit with its selected occurrences replaced by their rows (equal fingerprints are confirmed exactly) and
+  // the placeholders of the partial sums by theirs: level-0 rows first, the partial sums (level 1) after them
+  const uint32_t R0 = (uint32_t)table.size(), R1 = (uint32_t)groups.size();
+  auto lower = [&](size_t u, Function& dst) {
+    const Function& f = *unit[u];
+    copy_tree(f, f.root, dst, [&](int32_t k) -> int64_t {
       const Node& n = f.nodes[k];
       if (n.l < 0 || n.is_const) return -1;
-      auto it = cands.find(FpKey{fps[i][k].a, fps[i][k].b});
+      auto it = cands.find(FpKey{fps[u][k].a, fps[u][k].b});
       if (it == cands.end() || !it->second.selected) return -1;
       const int32_t r = it->second.row;
-      if (!same_structure(f, fps[i], k, table[r], tfps[r], table[r].root)) return -1;
+      if (!same_structure(f, fps[u], k, table[r], tfps[r], table[r].root)) return -1;
       return (int64_t)n_base + r;
     });
-    lowered_[i].rpn = f.rpn;
-    compute_needs(lowered_[i]);
+    for (Node& n : dst.nodes)
+      if ((n.kind == N_VAR || n.kind == N_NEGVAR) && n.var >= GROUP_BASE) n.var = n_base + R0 + (n.var - GROUP_BASE);
+    compute_needs(dst);
+  };
+  lowered_.resize(nf);
+  std::vector<Function> lowered_groups(R1);
+  for (size_t u = 0; u < nu; ++u) {
+    if (unit_fn[u] >= 0) {
+      lower(u, lowered_[unit_fn[u]]);
+      lowered_[unit_fn[u]].rpn = functions[unit_fn[u]].rpn;
+    } else {
+      lower(u, lowered_groups[(size_t)(-1 - unit_fn[u])]);
+    }
   }
-  pre.emplace_back();
-  Collection& pc = pre[0];
-  pc.vars = vars;
-  pc.var_index = var_index;
-  pc.check_is_equal = false;
-  pc.functions = std::move(table);
-  pc.enable_fuse = enable_fuse;
-  pc.enable_cse = enable_cse;
-  pc.enable_cross = enable_cross;
-  pc.enable_table = false;
-  pc.temp_budget = temp_budget;
-  std::string perr;
-  if (!pc.finish(perr)) {          // never expected; the functions are then compiled as written
+  for (size_t i = 0; i < nf; ++i)
+    if (dup_of[i] >= 0) lowered_[i] = functions[i];
+  // the rows' own collections: level 0 over the variables, level 1 over the variables and the level-0 rows
+  auto add_level = [&](std::vector<Function>&& fns, uint32_t extra_vars) -> bool {
+    pre.emplace_back();
+    Collection& pc = pre.back();
+    pc.vars = vars;
+    pc.var_index = var_index;
+    for (uint32_t r = 0; r < extra_vars; ++r) pc.vars.push_back("$row" + std::to_string(r));
+    pc.n_input_vars = n_base;
+    pc.check_is_equal = false;
+    pc.functions = std::move(fns);
+    pc.enable_fuse = enable_fuse;
+    pc.enable_cse = enable_cse;
+    pc.enable_cross = enable_cross;
+    pc.enable_table = false;
+    pc.temp_budget = temp_budget;
+    std::string perr;
+    return pc.finish(perr);
+  };
+  bool ok = true;
+  pre_row_offset_.clear();
+  if (R0) { pre_row_offset_.push_back(0); ok = add_level(std::move(table), 0); }
+  if (ok && R1) { pre_row_offset_.push_back(R0); ok = add_level(std::move(lowered_groups), R0); }
+  if (!ok) {                       // never expected; the functions are then compiled as written
     pre.clear();
+    pre_row_offset_.clear();
     lowered_.clear();
     return;
   }
-  n_table_rows = (uint32_t)pc.functions.size();
+  n_table_rows = R0 + R1;
+  n_split_rows = R1;
 }
 
 bool Collection::add_function(std::string text, uint64_t index, bool strip_blanks, std::string& err, bool validate,
@@ -1440,8 +1647,10 @@ bool Collection::finish(std::string& err) {
   // sub-expressions shared by several functions become extra variable rows (build_table); from here on the
   // functions are the lowered ones (efn)
   build_table(dup_of);
-  if (!lowered_.empty())
+  if (!lowered_.empty()) {
+    fps.resize(functions.size());
     for (size_t i = 0; i < functions.size(); ++i) fingerprints(efn(i), fps[i]);
+  }
   // Evaluation order: functions over the same denominator are brought together (the group takes the place of its
   // first member), so that a denominator that repeats anywhere in the collection is inverted once.  Outputs are
   // addressed by their slot, the order of evaluation is free.  fn_start is indexed by POSITION in this order.
@@ -1526,14 +1735,15 @@ bool Collection::finish(std::string& err) {
     std::vector<uint64_t> pt(vars.size());
     uint64_t seed = 0x243F6A8885A308D3ULL;
     for (auto& v : pt) v = 1 + splitmix64(seed) % (P0 - 1);
-    if (!pre.empty()) {
-      // the shared rows at that point, from their own expression trees (the pre-pass tape has been checked
-      // against them by its own finish())
-      std::vector<uint64_t> val;
-      for (const Function& tf : pre[0].functions) {
+    // the shared rows at that point, level by level, from their own expression trees (each level's tape has been
+    // checked against them by its own finish()); a level sees the variables and the rows of the levels before it
+    for (const Collection& pc : pre) {
+      std::vector<uint64_t> val, level;
+      for (const Function& tf : pc.functions) {
         eval_nodes(tf, P0, pt.data(), val);
-        pt.push_back(val[tf.root]);
+        level.push_back(val[tf.root]);
       }
+      pt.insert(pt.end(), level.begin(), level.end());
     }
     bool again = false;
     uint64_t chk_temps[16] = {};
@@ -1591,8 +1801,8 @@ bool Collection::finish(std::string& err) {
       if (in.op < OP_TERM && (in.flags & F_NEGR)) ++executed.ma;
     }
   }
-  if (!pre.empty()) {
-    const WorkCount& w = pre[0].executed;
+  for (const Collection& pc : pre) {
+    const WorkCount& w = pc.executed;
     executed.tokens += w.tokens;
     executed.mm += w.mm;
     executed.ma += w.ma;

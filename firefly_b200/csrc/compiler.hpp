@@ -105,8 +105,14 @@ struct Collection {
                                               // factors, numerators): computed once per probe into extra variable rows
   uint32_t table_row_limit = 0;               // most shared rows (0: automatic)
   uint32_t n_table_rows = 0;                  // shared rows in use: the tape addresses them as variables n_vars, n_vars + 1, ...
-  std::vector<Collection> pre;                // empty, or ONE collection over the same variables whose outputs are the shared
-                                              // rows; it is evaluated before this tape, at the same points
+  std::vector<Collection> pre;                // the collections whose outputs are the shared rows, evaluated before this tape at
+                                              // the same points: level 0 (sub-expressions used in several places) over the
+                                              // variables, level 1 (partial sums of long sums) over the variables and level 0
+  bool enable_split = true;                   // cut long sums into partial sums (level-1 rows): intra-function parallelism
+  uint32_t n_split_rows = 0;                  // partial sums among the rows
+  uint32_t n_input_vars = 0;                  // a rows' collection: how many of `vars` are the caller's (0: all of them)
+  // first row each collection of `pre` writes
+  const std::vector<uint32_t>& pre_row_offset() const { return pre_row_offset_; }
   uint32_t cse_fallbacks = 0;                 // functions emitted without sharing after a failed self-check
   uint32_t n_structural_duplicates = 0;       // functions of equal structure: evaluated once, stored to all their outputs
   uint32_t n_shared_denominators = 0;         // functions that reuse the inverted denominator of the function before them
@@ -158,6 +164,7 @@ struct Collection {
   std::vector<Function> base_functions_;      // one per output, before any factor was applied
   // what the tape is generated from: `functions` with every occurrence of a shared row replaced by a variable leaf
   std::vector<Function> lowered_;
+  std::vector<uint32_t> pre_row_offset_;
   const Function& efn(size_t i) const { return lowered_.empty() ? functions[i] : lowered_[i]; }
   void build_table(const std::vector<int32_t>& dup_of);
   void emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots, int den_mode);

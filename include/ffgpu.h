@@ -64,6 +64,7 @@ enum {
   FFGPU_NO_FUSE = 4,          /* do not fuse instruction runs into TERM / MULADD / ACCUM2 / ADDVARS / MULVARS (for A/B tests) */
   FFGPU_NO_CROSS = 16,        /* do not share ACROSS functions: structural duplicates, shared denominators, shared rows (for A/B tests) */
   FFGPU_NO_TABLE = 32,        /* no shared rows (sub-expressions of several functions evaluated once per probe; for A/B tests) */
+  FFGPU_NO_SPLIT = 64,        /* long sums stay in one piece (no partial-sum rows; for A/B tests) */
   FFGPU_TEMPS_SHIFT = 8       /* bits 8..11: temp slots per function for shared sub-expressions (0 = automatic) */
 };
 
@@ -103,13 +104,21 @@ size_t ffgpu_n_structural_duplicates(const ffgpu_tape*);
 /* functions N/D whose denominator has the structure of the denominator of the function before them: 1/D is
  * computed once per run of such functions and kept in a temp slot (no denominator code, no inversion for the rest) */
 size_t ffgpu_n_shared_denominators(const ffgpu_tape*);
-/* shared rows: sub-expressions that occur in several places of the collection (powers of a variable, common
- * factors, numerators of different functions) are evaluated once per probe by a small tape of their own and read by
- * the functions' tape as extra variables n_vars, n_vars + 1, ... (the reference shares nothing between functions,
- * ShuntingYardParser.hpp:365-479 walks every token of every function).  ffgpu_get_table_tape copies that tape
- * (output r = row r); 0 rows: the collection has nothing to share.  FFGPU_NO_TABLE turns the pass off. */
-size_t ffgpu_n_table_rows(const ffgpu_tape*);
-size_t ffgpu_get_table_tape(const ffgpu_tape*, void* buf, size_t cap);
+/* shared rows: values computed once per probe by small tapes of their own and read by the functions' tape as extra
+ * variables n_vars, n_vars + 1, ... (the reference shares nothing between functions and walks every token of every
+ * function on one thread, ShuntingYardParser.hpp:365-479).  Two levels:
+ *   level 0  sub-expressions that occur in several places of the collection (powers of a variable, common factors,
+ *            numerators of different functions), over the variables;
+ *   level 1  partial sums of LONG sums (a function of 10^3..10^5 terms is cut into pieces of about 300 tree nodes):
+ *            the pieces are evaluated by different thread blocks, so a single large function fills the chip even at
+ *            the Reconstructor's bunch sizes; over the variables and the level-0 rows.
+ * ffgpu_get_table_tape copies the tape of a level (its output r is row offset(level) + r); FFGPU_NO_TABLE turns both
+ * levels off, FFGPU_NO_SPLIT the second. */
+size_t ffgpu_n_table_rows(const ffgpu_tape*);                     /* all levels */
+size_t ffgpu_n_table_levels(const ffgpu_tape*);
+size_t ffgpu_n_table_rows_level(const ffgpu_tape*, size_t level);
+size_t ffgpu_n_split_rows(const ffgpu_tape*);                     /* partial sums among them */
+size_t ffgpu_get_table_tape(const ffgpu_tape*, size_t level, void* buf, size_t cap);
 size_t ffgpu_n_slots(const ffgpu_tape*);        /* shared-memory slots per probe the kernel reserves (spill + temps) */
 /* RPN of distinct function i, tokens joined by ' '; returns the length needed (without NUL) */
 size_t ffgpu_rpn(const ffgpu_tape*, size_t i, char* buf, size_t cap);

@@ -102,6 +102,37 @@ def table(rng, vars_, n):
     return out
 
 
+def long_sums(rng, vars_, n):
+    """a few functions that are long sums of monomials (cut into partial-sum rows by the compiler) over a long or short
+    denominator, next to small functions that share monomials with them"""
+    def mono():
+        parts = [f"{v}^{rng.randint(1, 30)}" if rng.random() < 0.7 else v for v in rng.sample(vars_, rng.randint(1, min(3, len(vars_))))]
+        return "*".join([str(rng.randint(1, 10 ** rng.randint(1, 12)))] + parts)
+
+    pool = [mono() for _ in range(rng.randint(200, 900))]
+
+    def poly(k):
+        ts = [rng.choice(pool) if rng.random() < 0.5 else mono() for _ in range(k)]
+        lead = "-" if rng.random() < 0.2 else ""
+        return lead + ts[0] + "".join(rng.choice("+-") + t for t in ts[1:])
+
+    out = []
+    for _ in range(n):
+        r = rng.random()
+        big = rng.randint(150, 700)
+        if r < 0.4:
+            out.append(f"({poly(big)})/({poly(rng.randint(1, 5))})")
+        elif r < 0.6:
+            out.append(f"({poly(big)})/({poly(big)})")
+        elif r < 0.7:
+            out.append(poly(big))
+        elif r < 0.8:
+            out.append(f"({poly(3)})/({poly(big)})")
+        else:
+            out.append(f"({poly(rng.randint(1, 4))})/({rng.choice(vars_)}-{rng.choice(vars_)})")
+    return out
+
+
 def rpn_is_well_formed(rpn):
     depth = 0
     for t in rpn:
@@ -123,7 +154,7 @@ def one_round(seed, rnd):
 
     rng = random.Random((seed << 20) ^ rnd)
     orc = Oracle()
-    kind = rng.choice(["free", "free", "dag", "table", "table", "ibp"])
+    kind = rng.choice(["free", "free", "dag", "table", "table", "ibp", "long"])
     nv = rng.randint(1, 6)
     vars_ = [f"x{i}" for i in range(1, nv + 1)]
     if kind == "free":
@@ -133,11 +164,13 @@ def one_round(seed, rnd):
         funs = _dag_expressions(rng, vars_, rng.randint(1, 30))
     elif kind == "table":
         funs = table(rng, vars_, rng.randint(2, 40))
+    elif kind == "long":
+        funs = long_sums(rng, vars_, rng.randint(1, 5))
     else:
         funs, vars_ = W.ibp_like_collection(rng.randint(2, 25), max(nv, 2), seed=rng.randrange(1 << 30),
                                             den_run=rng.choice([0, 0, 2, 4, 16]))
     nv = len(vars_)
-    opts = dict(cse=rng.random() < 0.85, fuse=rng.random() < 0.85, cross=rng.random() < 0.85, table=rng.random() < 0.8,
+    opts = dict(cse=rng.random() < 0.85, fuse=rng.random() < 0.85, cross=rng.random() < 0.85, table=rng.random() < 0.8, split=rng.random() < 0.85,
                 temps=rng.choice([0, 0, 0, 1, 2, 3, 5, 8]), check_is_equal=rng.random() < 0.2)
     # Equality by value at one random point (check_is_equal, ShuntingYardParser.cpp:125-140) is not a property of two
     # functions once an exponent depends on a variable: (-x)^(x) and (x)^(x) agree exactly when the check point is
@@ -147,7 +180,7 @@ def one_round(seed, rnd):
         opts["check_is_equal"] = False
     table_primes = ff.primes()
     p1, p2 = rng.choice(table_primes), rng.choice(table_primes)
-    npts = 7
+    npts = 7 if kind != "long" else 5
     tag = f"seed={seed} round={rnd} kind={kind} n={len(funs)} opts={opts}"
     try:
         par = ff.GpuParser(None, funs, vars_, **opts)
@@ -205,11 +238,11 @@ def one_round(seed, rnd):
             for row, i in enumerate(factors):
                 want[i] = [int(b) * (pow(int(f), p - 2, p) if int(f) else 0) % p for b, f in zip(want[i], fac[row])]
         tape = par.tape()
-        pre, rows = par.table_tape(), par.n_table_rows
+        levels = par.table_levels()
         for j in range(npts):
             pt = [int(x) for x in pts[:, j]]
-            if rows:
-                pt = pt + run(pre, pt, p, rows)      # the shared rows are variables n_vars, n_vars + 1, ...
+            for pre, rows in levels:
+                pt = pt + run(pre, pt, p, rows)      # the shared rows are variables n_vars, n_vars + 1, ..., level by level
             got = run(tape, pt, p, par.n_out)
             exp = [int(x) for x in want[:, j]]
             if got != exp:

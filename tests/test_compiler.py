@@ -16,11 +16,13 @@ P0 = 9223372036854775783
 
 def interp(par, pts, p):
     tape = par.tape()
-    pre, rows = par.table_tape(), par.n_table_rows
+    levels = par.table_levels()
 
     def one(pt):
-        # the shared rows first (their own tape), then the functions with the rows as extra variables
-        return run(tape, pt + run(pre, pt, p, rows) if rows else pt, p, par.n_out)
+        # the shared rows first, level by level (their own tapes), then the functions with the rows as extra variables
+        for pre, rows in levels:
+            pt = pt + run(pre, pt, p, rows)
+        return run(tape, pt, p, par.n_out)
     cols = [one([int(x) for x in pts[:, j]]) for j in range(pts.shape[1])]
     return np.array(cols, dtype=np.uint64).T.reshape(par.n_out, pts.shape[1])
 
@@ -304,7 +306,7 @@ def test_fused_and_plain_tapes_agree(oracle, cse, fuse):
     par = ff.GpuParser(None, funs, vars_, cse=cse, fuse=fuse)
     par.set_prime(p)
     assert par.cse_fallbacks == 0
-    ops = {ff.OPS[o] for o in par.tape()["op"]} | {ff.OPS[o] for o in par.table_tape()["op"]}
+    ops = {ff.OPS[o] for o in par.tape()["op"]} | {ff.OPS[o] for tp, _ in par.table_levels() for o in tp["op"]}
     assert ({"TERM", "MULADD", "ADDVARS", "MULVARS"} <= ops) == fuse
     assert np.array_equal(interp(par, pts, p), want)
 
@@ -555,6 +557,38 @@ def test_shared_rows_follow_added_and_trimmed_functions(oracle):
     par.set_prime(p)
     assert par.n_table_rows == 0
     assert np.array_equal(interp(par, pts, p), oracle.parse([funs[0], funs[1], funs[3]], vars_, p).eval(pts))
+
+
+def test_long_sums_become_partial_sum_rows(oracle):
+    """a function that is one long sum is cut into partial sums (level-1 rows, evaluated in parallel chunks) over the
+    level-0 rows of what they share; values against the oracle with zeros, signs and a vanishing denominator; a sum
+    whose terms are all subtracted; the pass switched off; small functions are left alone"""
+    rng = random.Random(11)
+    vars_ = ["x", "y", "z"]
+    pool = [f"{rng.randint(1, 10**9)}*x^{rng.randint(1, 30)}*y^{rng.randint(0, 9)}*z^{rng.randint(0, 5)}" for _ in range(1500)]
+    num = "".join(rng.choice("+-") + t for t in pool)[1:]
+    den = "+".join(pool[:400])
+    neg = "-" + "-".join(pool[:300])
+    funs = [f"({num})/({den})", f"({neg})/(x-y)", "x^30*y+z", f"({den})*3"]
+    par = ff.GpuParser(None, funs, vars_)
+    off = ff.GpuParser(None, funs, vars_, split=False)
+    plain = ff.GpuParser(None, funs, vars_, table=False)
+    assert par.n_split_rows >= 8 and off.n_split_rows == 0 and plain.n_table_rows == 0
+    levels = par.table_levels()
+    assert len(levels) == 2 and levels[1][1] == par.n_split_rows and levels[0][1] + levels[1][1] == par.n_table_rows
+    assert par.n_instr < 200 < off.n_instr
+    for p in (ff.primes()[0], ff.primes()[31]):
+        pts = ff.synthetic_points(3, 5, p, seed=6)
+        pts[:, 0] = 0
+        pts[:, 1] = np.array([7, 7, 3], dtype=np.uint64)       # x - y = 0
+        pts[:, 2] = np.array([1, 0, p - 1], dtype=np.uint64)
+        want = oracle.parse(funs, vars_, p).eval(pts)
+        for q in (par, off, plain):
+            q.set_prime(p)
+            assert q.cse_fallbacks == 0
+            assert np.array_equal(interp(q, pts, p), want)
+    small = ff.GpuParser(None, ["(x+y)^3/(z-1)", "x*y"], vars_)
+    assert small.n_split_rows == 0
 
 
 def test_shared_denominator_edge_cases(oracle):

@@ -670,3 +670,43 @@ def test_shared_rows_on_device(ctx, oracle, generic):
             assert np.array_equal(par.evaluate_pre(pts)[:, :40], want), (k, th)
     par.close()
     off.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("generic", [False, True])
+def test_long_sums_on_device(ctx, oracle, generic):
+    """long sums are cut into partial sums that the rows' tapes evaluate in parallel chunks (two levels of shared rows,
+    three kernels per launch): a single large function at the Reconstructor's bunch sizes and at a big batch, against
+    the oracle and against the same collection compiled in one piece"""
+    rng = random.Random(23)
+    vars_ = ["x", "y", "z", "w"]
+    pool = [f"{rng.randint(1, 10**12)}*x^{rng.randint(1, 30)}*y^{rng.randint(0, 9)}*z^{rng.randint(0, 5)}*w^{rng.randint(0, 2)}" for _ in range(2500)]
+    num = "".join(rng.choice("+-") + t for t in pool)[1:]
+    den = "+".join(pool[:600])
+    funs = [f"({num})/({den})", f"(-{'-'.join(pool[:350])})/(x-y)", "x^30*y+z", f"({den})^2*3"]
+    p = 4611686018427400249 if generic else ff.primes()[13]
+    par = ff.GpuParser(ctx, funs, vars_)
+    off = ff.GpuParser(ctx, funs, vars_, split=False)
+    par.set_prime(p)
+    off.set_prime(p)
+    assert par.n_split_rows >= 10 and off.n_split_rows == 0 and par.cse_fallbacks == 0 and len(par.table_levels()) == 2
+    orc = oracle.parse(funs, vars_, p)
+    for n in (1, 2, 7, 128, 129, 3001):
+        pts = ff.synthetic_points(4, n, p, seed=n)
+        if n > 2:
+            pts[:, 1] = 0
+            pts[:2, 2] = 5                    # x - y = 0
+        got = par.evaluate_pre(pts)
+        sel = np.unique(np.concatenate([np.arange(min(n, 8)), np.arange(0, n, max(1, n // 7)), [n - 1]]))
+        assert np.array_equal(got[:, sel], orc.eval(np.ascontiguousarray(pts[:, sel]))), n
+        assert np.array_equal(got, off.evaluate_pre(pts)), n
+    # the example collection of the reference (one function of 1900 instructions among 19)
+    g = load_golden("s_y_4_v")
+    sp = ff.GpuParser(ctx, g["functions"], g["vars"])
+    sp.set_prime(p)
+    assert sp.n_split_rows >= 4
+    pts = ff.synthetic_points(4, 33, p, seed=2)
+    assert np.array_equal(sp.evaluate_pre(pts), oracle.parse(g["functions"], g["vars"], p).eval(pts))
+    sp.close()
+    par.close()
+    off.close()
