@@ -522,6 +522,7 @@ def main():
         barrier()
         if rank == 0:
             configs["cfg1_bunch_sweep"] = run_cfg_sweep(ff, W, orc, ctx)
+            configs["plugin_call_large_function"] = run_cfg_large_function(ff, orc, ctx)
         barrier()
         configs["cfg0_cfg4_reconstructions"] = (
             "tests/test_gpu_reconstruct.py: the unmodified reference Reconstructor over GpuBlackBox against its own CPU black "
@@ -532,6 +533,7 @@ def main():
             verified = verified and configs[c]["verified_bit_exact_vs_oracle"]
         if rank == 0:
             verified = verified and configs["cfg1_bunch_sweep"]["verified_bit_exact_vs_oracle"]
+            verified = verified and configs["plugin_call_large_function"]["verified_bit_exact_vs_oracle"]
         if e2e_ctx is not None:
             verified = verified and e2e_ctx["verified_bit_exact_vs_oracle"]
 
@@ -913,6 +915,65 @@ def run_cfg_sweep(ff, W, orc, ctx):
         par.close()
     return {"config": "bunch sweep 1..4096 through ffgpu_eval, pageable host buffers (BASELINE.json configs[1])",
             "unit": UNIT, "sweep": out, "verified_bit_exact_vs_oracle": ok}
+
+
+def run_cfg_large_function(ff, orc, ctx, n_terms=10000):
+    """The plug-in view for ONE large function (a rational function with 10^4 terms in the numerator, 5 variables): one
+    call of the black box with a bunch of 1 / 128 points in host memory -- what a Reconstructor pool thread does.  The
+    compiler cuts the long sums into partial sums that parallel chunks of the rows' tape evaluate (include/ffgpu.h,
+    shared rows level 1); `unsplit` is the same function walked by one thread block; the reference's
+    evaluate_pre<FFIntVec<128>> on one host thread stands beside it where oracle/_ref was built."""
+    import random
+    rng = random.Random(5)
+    vs = [f"x{i}" for i in range(1, 6)]
+    terms = ["%d*%s" % (rng.randint(1, 10 ** 12), "*".join(f"{v}^{rng.randint(1, 30)}" for v in rng.sample(vs, 3))) for _ in range(n_terms)]
+    fun = "(" + "".join(rng.choice("+-") + t for t in terms)[1:] + ")/(" + "+".join(terms[: n_terms // 4]) + ")"
+    p = ff.primes()[0]
+    res = {"config": f"one rational function, {n_terms} + {n_terms // 4} terms, 5 variables; ffgpu_eval with pageable host buffers",
+           "unit": "us per call"}
+    pts128 = ff.synthetic_points(5, 128, p, seed=9)
+    want = orc.parse([fun], vs, p).eval(pts128)
+    ok = True
+    for split in (True, False):
+        t0 = time.perf_counter()
+        par = ff.GpuParser(ctx, [fun], vs, split=split)
+        par.set_prime(p)
+        tc = time.perf_counter() - t0
+        row = {"compile_and_set_prime_s": tc, "shared_rows": par.n_table_rows, "partial_sums": par.n_split_rows,
+               "main_tape_instructions": par.n_instr}
+        for b in (1, 128):
+            pts = np.ascontiguousarray(pts128[:, :b])
+            for _ in range(3):
+                got = par.evaluate_pre(pts)
+            ok = ok and bool(np.array_equal(got, want[:, :b]))
+            reps = 20 if split else 5
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                par.evaluate_pre(pts)
+            row[f"bunch_{b}_us"] = (time.perf_counter() - t0) / reps * 1e6
+        res["split" if split else "unsplit"] = row
+        par.close()
+    try:
+        from refs import Ref, have_ref
+        if have_ref():
+            ref = Ref()
+            ref.set_prime(p)
+            rp = ref.parse([fun], vs)
+            rp.eval(pts128, bunch=128, threads=1)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                rp.eval(pts128, bunch=128, threads=1)
+            res["reference_cpu_bunch_128_us_1_thread"] = (time.perf_counter() - t0) / 3 * 1e6
+            one = np.ascontiguousarray(pts128[:, :1])
+            t0 = time.perf_counter()
+            for _ in range(5):
+                rp.eval(one)
+            res["reference_cpu_bunch_1_us_1_thread"] = (time.perf_counter() - t0) / 5 * 1e6
+            rp.close()
+    except Exception as e:
+        res["reference_cpu_bunch_128_us_1_thread"] = repr(e)
+    res["verified_bit_exact_vs_oracle"] = ok
+    return res
 
 
 def cpu_baseline(n):

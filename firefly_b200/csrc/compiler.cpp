@@ -1246,9 +1246,13 @@ void copy_tree(const Function& f, int32_t root, Function& g, LeafVar leaf_var) {
 // in Z_p is associative and commutative: the value is unchanged.
 namespace {
 constexpr uint32_t GROUP_BASE = 1u << 24;      // placeholder variable index of partial sum g until the row count is known
-constexpr uint32_t SPLIT_MIN = 768;            // tree nodes below which a sum is left alone
-constexpr uint32_t SPLIT_TARGET = 320;         // tree nodes per partial sum
-constexpr uint32_t SPLIT_MAX_GROUPS = 96;      // partial sums per sum at most
+uint32_t env_u32(const char* name, uint32_t dflt) {
+  const char* e = std::getenv(name);
+  return e && *e ? (uint32_t)std::max(1L, std::atol(e)) : dflt;
+}
+const uint32_t SPLIT_MIN = env_u32("FFGPU_SPLIT_MIN", 768);          // tree nodes below which a sum is left alone
+const uint32_t SPLIT_TARGET = env_u32("FFGPU_SPLIT_TARGET", 320);    // tree nodes per partial sum
+const uint32_t SPLIT_MAX_GROUPS = env_u32("FFGPU_SPLIT_GROUPS", 96); // partial sums per sum at most
 
 // append the sub-tree of f below `root` to g (children first); returns the index of its root in g
 int32_t append_subtree(const Function& f, int32_t root, Function& g, std::vector<int32_t>& remap) {

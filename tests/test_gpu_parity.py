@@ -309,7 +309,7 @@ def test_concurrent_callers(ctx, oracle, coalesce, cap):
     [t.join() for t in ts]
     assert not errs, errs
     st = par.coalesce_stats()
-    kernels = 2 if par.n_table_rows else 1       # a collection with shared rows runs their tape first
+    kernels = 1 + len(par.table_levels())        # a collection with shared rows runs their tapes first
     launches = (ff.launch_count() - l0) // kernels
     if coalesce:
         assert st["calls"] == n_threads * n_iter and st["launches"] == launches
