@@ -885,7 +885,14 @@ __global__ void __launch_bounds__(THREADS, min_blocks<K, THREADS, LEAN>()) eval_
         break;
       }
     }
-    cur = nxt;
+    // The fetched instruction is taken over HERE, at the end of the iteration.  Left to itself ptxas copies it right
+    // behind the load at the top (the fields of the current instruction have been extracted by then) and every
+    // iteration waits out the whole fetch: 40 % of the stall samples of a small launch, where one warp walks the tape
+    // with nothing else to hide it (s_y_4_v at 1..128 points 199 -> 156 us, f4 12.1 -> 10.3 us; +2.4 % on the
+    // 2000-function collection at 65 536 points; profiles/r02_kbench_late_copy_*.log).
+    asm volatile("mov.b32 %0, %4;\n\tmov.b32 %1, %5;\n\tmov.b32 %2, %6;\n\tmov.b32 %3, %7;"
+                 : "=r"(cur.v.x), "=r"(cur.v.y), "=r"(cur.v.z), "=r"(cur.v.w)
+                 : "r"(nxt.v.x), "r"(nxt.v.y), "r"(nxt.v.z), "r"(nxt.v.w));
     ++pc;
   }
 }
