@@ -600,6 +600,11 @@ int ffgpu_set_prime(ffgpu_tape* t, uint64_t p) {
       }
       FF_CUDA(cudaMemcpy(t->d_pre[l][g], pc.tape.data(), pbytes, cudaMemcpyHostToDevice));
     }
+    // cudaMemcpy from pageable memory returns when the data sits in the driver's staging buffer, not when it has
+    // reached the device, and the evaluation streams are non-blocking (no implicit order with the copies' stream):
+    // without this wait a launch right after ffgpu_set_prime could read a tape that is still arriving (one wrong
+    // value or illegal access in about 5000 compile-and-evaluate rounds of scripts/fuzz_gpu.py)
+    FF_CUDA(cudaDeviceSynchronize());
   }
   return 0;
 }

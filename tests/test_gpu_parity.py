@@ -710,3 +710,18 @@ def test_long_sums_on_device(ctx, oracle, generic):
     sp.close()
     par.close()
     off.close()
+
+
+@pytest.mark.gpu
+def test_randomised_collections_through_the_kernels():
+    """twenty seconds of scripts/fuzz_gpu.py: random collections of every kind compiled with random passes, evaluated on
+    the GPU right after ffgpu_set_prime at batch sizes 1..3000 in two primes, every value against the oracle (the long
+    campaigns are in DESIGN.md; this keeps the harness and the compile -> upload -> launch sequence under test)"""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "fuzz_gpu.py"), "--seconds", "20", "--seed", "2026"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " 0 failure(s)" in r.stdout
