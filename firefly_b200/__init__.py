@@ -44,6 +44,7 @@ NO_FUSE = 4
 NO_CROSS = 16
 NO_TABLE = 32
 NO_SPLIT = 64
+NO_HORNER = 128
 ADD_PLAIN, ADD_VALIDATE, ADD_NO_DUPLICATES = 1, 2, 4
 
 
@@ -208,10 +209,10 @@ class GpuParser:
 
     def __init__(self, ctx: Optional[Context], functions=None, vars: Sequence[str] = (), check_is_equal: bool = False,
                  *, file: Optional[str] = None, text: Optional[str] = None, cse: bool = True,
-                 temps: int = 0, fuse: bool = True, cross: bool = True, table: bool = True, split: bool = True):
+                 temps: int = 0, fuse: bool = True, cross: bool = True, table: bool = True, split: bool = True, horner: bool = True):
         self.ctx = ctx
         ch = ctx.h if ctx is not None else None
-        flags = (CHECK_IS_EQUAL if check_is_equal else 0) | (0 if cse else NO_CSE) | (0 if fuse else NO_FUSE) | (0 if cross else NO_CROSS) | (0 if table else NO_TABLE) | (0 if split else NO_SPLIT) | ((temps & 15) << 8)
+        flags = (CHECK_IS_EQUAL if check_is_equal else 0) | (0 if cse else NO_CSE) | (0 if fuse else NO_FUSE) | (0 if cross else NO_CROSS) | (0 if table else NO_TABLE) | (0 if split else NO_SPLIT) | (0 if horner else NO_HORNER) | ((temps & 15) << 8)
         v = _strs(vars)
         if file is not None:
             self.h = lib.ffgpu_compile_file(ch, file.encode(), v, len(vars), flags)

@@ -421,6 +421,7 @@ ffgpu_tape* ffgpu_compile(ffgpu_ctx* ctx, const char* const* functions, size_t n
   t->col.enable_cross = !(flags & FFGPU_NO_CROSS);
   t->col.enable_table = !(flags & FFGPU_NO_TABLE) && !std::getenv("FFGPU_NO_TABLE");
   t->col.enable_split = !(flags & FFGPU_NO_SPLIT) && !std::getenv("FFGPU_NO_SPLIT");
+  t->col.enable_horner = !(flags & FFGPU_NO_HORNER) && !std::getenv("FFGPU_NO_HORNER");
   t->col.temp_budget = (int)((flags >> FFGPU_TEMPS_SHIFT) & 15u);
   const bool ok = t->col.compile_strings(to_vec(functions, n_functions), to_vec(vars, n_vars),
                                          (flags & FFGPU_CHECK_IS_EQUAL) != 0, err);
@@ -436,6 +437,7 @@ ffgpu_tape* ffgpu_compile_text(ffgpu_ctx* ctx, const char* text, const char* con
   t->col.enable_cross = !(flags & FFGPU_NO_CROSS);
   t->col.enable_table = !(flags & FFGPU_NO_TABLE) && !std::getenv("FFGPU_NO_TABLE");
   t->col.enable_split = !(flags & FFGPU_NO_SPLIT) && !std::getenv("FFGPU_NO_SPLIT");
+  t->col.enable_horner = !(flags & FFGPU_NO_HORNER) && !std::getenv("FFGPU_NO_HORNER");
   t->col.temp_budget = (int)((flags >> FFGPU_TEMPS_SHIFT) & 15u);
   const bool ok = t->col.compile_text(text ? text : "", to_vec(vars, n_vars), (flags & FFGPU_CHECK_IS_EQUAL) != 0, err);
   return finish_compile(ctx, std::move(t), ok, err);

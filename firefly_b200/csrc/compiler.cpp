@@ -1254,6 +1254,44 @@ const uint32_t SPLIT_MIN = env_u32("FFGPU_SPLIT_MIN", 768);          // tree nod
 const uint32_t SPLIT_TARGET = env_u32("FFGPU_SPLIT_TARGET", 320);    // tree nodes per partial sum
 const uint32_t SPLIT_MAX_GROUPS = env_u32("FFGPU_SPLIT_GROUPS", 96); // partial sums per sum at most
 
+struct Mono {
+  std::vector<int32_t> consts;                          // constant sub-trees of the source that multiply the term
+  std::vector<std::pair<uint32_t, uint32_t>> pw;        // (variable, exponent), exponent >= 1
+  int32_t opaque = -1;                                  // not a monomial: the term's sub-tree, taken as it is
+  bool minus = false;
+};
+// term -> monomial; false if the term is something else
+bool parse_monomial(const Function& f, int32_t t, Mono& m) {
+  std::vector<int32_t> st{t};
+  while (!st.empty()) {
+    const int32_t i = st.back();
+    st.pop_back();
+    const Node& n = f.nodes[i];
+    if (n.is_const) { m.consts.push_back(i); continue; }
+    if (n.kind == N_VAR) { m.pw.push_back({n.var, 1}); continue; }
+    if (n.kind == N_NEGVAR) { m.pw.push_back({n.var, 1}); m.minus = !m.minus; continue; }
+    if (n.kind == N_MUL) { st.push_back(n.r); st.push_back(n.l); continue; }
+    if ((n.kind == N_POW || n.kind == N_POWNEG) && f.nodes[n.l].kind == N_VAR) {
+      const uint32_t e = literal_exponent(f, f.nodes[n.r]);
+      if (e >= 1 && e < 65536) {
+        m.pw.push_back({f.nodes[n.l].var, e});
+        if (n.kind == N_POWNEG) m.minus = !m.minus;
+        continue;
+      }
+    }
+    return false;
+  }
+  std::sort(m.pw.begin(), m.pw.end());
+  size_t w = 0;
+  for (size_t k = 0; k < m.pw.size(); ++k) {
+    if (w && m.pw[w - 1].first == m.pw[k].first) m.pw[w - 1].second += m.pw[k].second;
+    else m.pw[w++] = m.pw[k];
+  }
+  m.pw.resize(w);
+  for (auto& q : m.pw)
+    if (q.second >= 65536) return false;
+  return true;
+}
 // append the sub-tree of f below `root` to g (children first); returns the index of its root in g
 int32_t append_subtree(const Function& f, int32_t root, Function& g, std::vector<int32_t>& remap) {
   std::vector<int32_t> reach, st{root};
@@ -1334,6 +1372,19 @@ bool split_long_sums(const Function& f, std::vector<Function>& groups, Function&
       st.push_back(Term{nd.r, nd.kind == N_SUB ? !t.minus : t.minus});      // right first: the left term comes out first
       st.push_back(Term{nd.l, t.minus});
     }
+    // monomials that look alike (same variables, neighbouring exponents) go into the same partial sum: that is where
+    // the Horner nests and the shared rows find something to share.  Other terms keep their order, behind them.
+    {
+      std::vector<std::pair<std::vector<std::pair<uint32_t, uint32_t>>, Term>> keyed;
+      keyed.reserve(terms.size());
+      for (const Term& t : terms) {
+        Mono m;
+        if (!parse_monomial(f, t.node, m)) m.pw.assign(1, {~0u, ~0u});
+        keyed.push_back({std::move(m.pw), t});
+      }
+      std::stable_sort(keyed.begin(), keyed.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+      for (size_t q = 0; q < terms.size(); ++q) terms[q] = keyed[q].second;
+    }
     uint64_t total = 0;
     for (const Term& t : terms) total += size[t.node];
     const uint32_t want = (uint32_t)std::min<uint64_t>(SPLIT_MAX_GROUPS, std::max<uint64_t>(2, total / SPLIT_TARGET));
@@ -1413,6 +1464,195 @@ bool split_long_sums(const Function& f, std::vector<Function>& groups, Function&
 }
 }  // namespace
 
+// ---- expanded polynomials -> Horner nests -----------------------------------------------------------------------
+// A sum of monomials c * x^a * y^b * ... (what Expand[] leaves behind) costs one multiplication per variable and per
+// monomial; factored greedily -- the variable that occurs in most terms first, P = v^m * Q + R, then Q and R the same way
+// -- it costs about one per monomial (the FireFly paper measures 5-7x between its Tab. 4 and Tab. 5; the reference has a
+// Horner generator for its own output, PolynomialFF.cpp:46-56, but evaluates input as written).  Ring identities only:
+// every value is unchanged, constants keep their own nodes and are folded per prime as before.
+namespace {
+struct HornerBuilder {
+  const Function& f;
+  Function& g;
+  std::vector<int32_t>& remap;
+  typedef std::pair<int32_t, bool> Val;                 // (node of g, the value is MINUS that node)
+  int32_t literal(const std::string& text) {
+    Node z{};
+    z.kind = N_NUM;
+    z.is_const = true;
+    z.l = z.r = -1;
+    z.lit = (uint32_t)g.literals.size();
+    g.literals.push_back(Literal{text});
+    g.nodes.push_back(z);
+    return (int32_t)g.nodes.size() - 1;
+  }
+  int32_t power(uint32_t var, uint32_t e) {
+    const int32_t v = push_var(g, var);
+    return e == 1 ? v : push_binary(g, N_POW, v, literal(std::to_string(e)));
+  }
+  Val add(Val a, Val b) {
+    if (a.first < 0) return b;
+    if (b.first < 0) return a;
+    if (!a.second) return {push_binary(g, b.second ? N_SUB : N_ADD, a.first, b.first), false};
+    if (!b.second) return {push_binary(g, N_SUB, b.first, a.first), false};
+    return {push_binary(g, N_ADD, a.first, b.first), true};
+  }
+  Val monomial(const Mono& m) {
+    if (m.opaque >= 0) return {append_subtree(f, m.opaque, g, remap), m.minus};
+    int32_t acc = -1;
+    for (int32_t c : m.consts) {
+      const int32_t k = append_subtree(f, c, g, remap);
+      acc = acc < 0 ? k : push_binary(g, N_MUL, acc, k);
+    }
+    for (const auto& q : m.pw) {
+      const int32_t k = power(q.first, q.second);
+      acc = acc < 0 ? k : push_binary(g, N_MUL, acc, k);
+    }
+    if (acc < 0) acc = literal("1");
+    return {acc, m.minus};
+  }
+  // the signed sum of the monomials, factored
+  Val build(std::vector<Mono> terms) {
+    Val total{-1, false};
+    std::unordered_map<uint32_t, uint32_t> count;
+    while (true) {
+      if (terms.size() < 2) break;
+      count.clear();
+      for (const Mono& m : terms)
+        if (m.opaque < 0)
+          for (const auto& q : m.pw) ++count[q.first];
+      uint32_t best = 0, best_n = 1;
+      for (const auto& kv : count)
+        if (kv.second > best_n || (kv.second == best_n && best_n > 1 && kv.first < best)) { best = kv.first; best_n = kv.second; }
+      if (best_n < 2) break;
+      uint32_t low = ~0u;
+      for (const Mono& m : terms)
+        if (m.opaque < 0)
+          for (const auto& q : m.pw)
+            if (q.first == best) low = std::min(low, q.second);
+      std::vector<Mono> inner, rest;
+      for (Mono& m : terms) {
+        bool has = false;
+        if (m.opaque < 0)
+          for (size_t k = 0; k < m.pw.size(); ++k)
+            if (m.pw[k].first == best) {
+              has = true;
+              m.pw[k].second -= low;
+              if (m.pw[k].second == 0) m.pw.erase(m.pw.begin() + (long)k);
+              break;
+            }
+        (has ? inner : rest).push_back(std::move(m));
+      }
+      const Val q = build(std::move(inner));                       // depth: the total degree at most
+      total = add(total, Val{push_binary(g, N_MUL, power(best, low), q.first), q.second});
+      terms = std::move(rest);
+    }
+    for (const Mono& m : terms) total = add(total, monomial(m));
+    return total;
+  }
+};
+// f with every sum of at least three monomials (wherever it sits) replaced by its Horner nest; false: nothing to do
+bool hornerize(const Function& f, Function& out) {
+  const size_t n = f.nodes.size();
+  auto is_sum = [&](int32_t i) { return !f.nodes[i].is_const && (f.nodes[i].kind == N_ADD || f.nodes[i].kind == N_SUB); };
+  std::unordered_map<int32_t, std::vector<Mono>> tops;
+  {
+    std::vector<int32_t> st{f.root};
+    while (!st.empty()) {
+      const int32_t i = st.back();
+      st.pop_back();
+      if (f.nodes[i].l < 0 || f.nodes[i].is_const) continue;
+      if (is_sum(i)) {
+        struct Term { int32_t node; bool minus; };
+        std::vector<Term> ts{{i, false}};
+        std::vector<Mono> monos;
+        size_t n_mono = 0;
+        while (!ts.empty()) {
+          const Term t = ts.back();
+          ts.pop_back();
+          if (is_sum(t.node)) {
+            const Node& nd = f.nodes[t.node];
+            ts.push_back(Term{nd.r, nd.kind == N_SUB ? !t.minus : t.minus});
+            ts.push_back(Term{nd.l, t.minus});
+            continue;
+          }
+          Mono m;
+          if (!parse_monomial(f, t.node, m)) {
+            m = Mono{};
+            m.opaque = t.node;
+          } else {
+            ++n_mono;
+          }
+          if (t.minus) m.minus = !m.minus;
+          monos.push_back(std::move(m));
+        }
+        if (n_mono >= 3) { tops.emplace(i, std::move(monos)); continue; }
+        // too few monomials: look inside the terms instead
+        for (const Mono& m : monos)
+          if (m.opaque >= 0) st.push_back(m.opaque);
+        continue;
+      }
+      st.push_back(f.nodes[i].l);
+      st.push_back(f.nodes[i].r);
+    }
+  }
+  if (tops.empty()) return false;
+  std::vector<int32_t> reach, st{f.root}, remap(n, -1);
+  while (!st.empty()) {
+    const int32_t i = st.back();
+    st.pop_back();
+    reach.push_back(i);
+    if (tops.count(i) || f.nodes[i].l < 0) continue;
+    st.push_back(f.nodes[i].l);
+    st.push_back(f.nodes[i].r);
+  }
+  std::sort(reach.begin(), reach.end());
+  out = Function{};
+  bool changed = false;
+  HornerBuilder hb{f, out, remap};
+  for (int32_t i : reach) {
+    auto it = tops.find(i);
+    if (it != tops.end()) {
+      // keep the nest only if it multiplies less than the sum as written
+      const size_t n0 = out.nodes.size(), l0 = out.literals.size();
+      HornerBuilder::Val v = hb.build(std::move(it->second));
+      if (v.second) v = {push_binary(out, N_SUB, hb.literal("0"), v.first), false};
+      uint64_t after = 0, before = 0;
+      for (size_t k = n0; k < out.nodes.size(); ++k) after += own_cost(out, out.nodes[k]);
+      std::vector<int32_t> walk{i};
+      while (!walk.empty()) {
+        const int32_t k = walk.back();
+        walk.pop_back();
+        before += own_cost(f, f.nodes[k]);
+        if (f.nodes[k].l >= 0 && !f.nodes[k].is_const) { walk.push_back(f.nodes[k].l); walk.push_back(f.nodes[k].r); }
+      }
+      if (after * 10 <= before * 9) {
+        remap[i] = v.first;
+        changed = true;
+      } else {
+        out.nodes.resize(n0);
+        out.literals.resize(l0);
+        remap[i] = append_subtree(f, i, out, remap);
+      }
+      continue;
+    }
+    Node nd = f.nodes[i];
+    if (nd.kind == N_NUM) {
+      nd.lit = (uint32_t)out.literals.size();
+      out.literals.push_back(f.literals[f.nodes[i].lit]);
+    } else if (nd.l >= 0) {
+      nd.l = remap[nd.l];
+      nd.r = remap[nd.r];
+    }
+    remap[i] = (int32_t)out.nodes.size();
+    out.nodes.push_back(nd);
+  }
+  out.root = remap[f.root];
+  out.rpn = f.rpn;
+  return changed;
+}
+}  // namespace
+
 void Collection::build_table(const std::vector<int32_t>& dup_of) {
   lowered_.clear();
   pre.clear();
@@ -1426,7 +1666,22 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
   if (enable_split)
     for (size_t i = 0; i < nf; ++i)
       if (dup_of[i] < 0 && groups.size() < 4 * SPLIT_MAX_GROUPS) split_long_sums(functions[i], groups, cut[i]);
-  if (nf < 2 && groups.empty()) return;
+  // expanded polynomials -> Horner nests: in the partial sums, and in the sums of the functions that were not cut
+  bool any_cut = !groups.empty();
+  if (enable_horner) {
+    Function h;
+    for (Function& g : groups)
+      if (hornerize(g, h)) g = std::move(h);
+    for (size_t i = 0; i < nf; ++i) {
+      if (dup_of[i] >= 0) continue;
+      if (hornerize(cut[i].nodes.empty() ? functions[i] : cut[i], h)) {
+        cut[i] = std::move(h);
+        cut[i].rpn = functions[i].rpn;
+        any_cut = true;
+      }
+    }
+  }
+  if (nf < 2 && !any_cut) return;
   // the units the sharing pass looks at: every function that is emitted, and the partial sums
   std::vector<const Function*> unit;
   std::vector<int64_t> unit_fn;                // function index, or -1 - g for partial sum g
@@ -1459,8 +1714,10 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
       else ++it->second.refs;
     }
   }
-  // first selection: everything that occurs at least twice anywhere
-  for (auto& kv : cands) kv.second.selected = kv.second.refs >= 2;
+  // first selection: everything that occurs at least twice anywhere.  (A single function that was not cut keeps its
+  // shared sub-expressions in temp slots, inside the one kernel: rows would be a second launch and more memory traffic.)
+  const bool want_rows = nf >= 2 || !groups.empty();
+  for (auto& kv : cands) kv.second.selected = want_rows && kv.second.refs >= 2;
   // occurrences, top down: below a selected sub-tree nothing is counted (its inside is evaluated by the row's own
   // function).  Candidates that are left with fewer than two uses, or save less than two multiplications, are
   // dropped, which exposes what they contain -- repeat until nothing changes.
@@ -1511,7 +1768,7 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
     }
     chosen.swap(kept);
   }
-  if (chosen.empty() && groups.empty()) return;
+  if (chosen.empty() && !any_cut) return;
   // rows in the order of first appearance (deterministic tapes)
   std::sort(chosen.begin(), chosen.end(), [](const Cand* x, const Cand* y) { return x->fn != y->fn ? x->fn < y->fn : x->node < y->node; });
   std::vector<Function> table(chosen.size());

@@ -109,6 +109,7 @@ struct Collection {
                                               // the same points: level 0 (sub-expressions used in several places) over the
                                               // variables, level 1 (partial sums of long sums) over the variables and level 0
   bool enable_split = true;                   // cut long sums into partial sums (level-1 rows): intra-function parallelism
+  bool enable_horner = true;                  // sums of monomials (expanded polynomials) are factored into Horner nests
   uint32_t n_split_rows = 0;                  // partial sums among the rows
   uint32_t n_input_vars = 0;                  // a rows' collection: how many of `vars` are the caller's (0: all of them)
   // first row each collection of `pre` writes

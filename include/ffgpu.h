@@ -65,6 +65,7 @@ enum {
   FFGPU_NO_CROSS = 16,        /* do not share ACROSS functions: structural duplicates, shared denominators, shared rows (for A/B tests) */
   FFGPU_NO_TABLE = 32,        /* no shared rows (sub-expressions of several functions evaluated once per probe; for A/B tests) */
   FFGPU_NO_SPLIT = 64,        /* long sums stay in one piece (no partial-sum rows; for A/B tests) */
+  FFGPU_NO_HORNER = 128,      /* sums of monomials are evaluated as written (no Horner nests; for A/B tests) */
   FFGPU_TEMPS_SHIFT = 8       /* bits 8..11: temp slots per function for shared sub-expressions (0 = automatic) */
 };
 

@@ -170,7 +170,7 @@ def one_round(seed, rnd):
         funs, vars_ = W.ibp_like_collection(rng.randint(2, 25), max(nv, 2), seed=rng.randrange(1 << 30),
                                             den_run=rng.choice([0, 0, 2, 4, 16]))
     nv = len(vars_)
-    opts = dict(cse=rng.random() < 0.85, fuse=rng.random() < 0.85, cross=rng.random() < 0.85, table=rng.random() < 0.8, split=rng.random() < 0.85,
+    opts = dict(cse=rng.random() < 0.85, fuse=rng.random() < 0.85, cross=rng.random() < 0.85, table=rng.random() < 0.8, split=rng.random() < 0.85, horner=rng.random() < 0.85,
                 temps=rng.choice([0, 0, 0, 1, 2, 3, 5, 8]), check_is_equal=rng.random() < 0.2)
     # Equality by value at one random point (check_is_equal, ShuntingYardParser.cpp:125-140) is not a property of two
     # functions once an exponent depends on a variable: (-x)^(x) and (x)^(x) agree exactly when the check point is

@@ -62,7 +62,7 @@ def main():
                                                 den_run=rng.choice([0, 0, 2, 4, 16]))
         nv = len(vars_)
         opts = dict(cse=rng.random() < 0.9, fuse=rng.random() < 0.9, cross=rng.random() < 0.9, table=rng.random() < 0.85,
-                    split=rng.random() < 0.9, temps=rng.choice([0, 0, 0, 1, 2, 3, 8]), check_is_equal=rng.random() < 0.15)
+                    split=rng.random() < 0.9, horner=rng.random() < 0.9, temps=rng.choice([0, 0, 0, 1, 2, 3, 8]), check_is_equal=rng.random() < 0.15)
         if opts["check_is_equal"] and any(re.search(r"\^\((?!-?\d+\))", f) for f in funs):
             opts["check_is_equal"] = False
         tag = f"seed={a.seed} round={rounds - 1} kind={kind} n={len(funs)} opts={opts}"

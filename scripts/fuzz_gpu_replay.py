@@ -25,7 +25,7 @@ elif kind == "long": funs = long_sums(rng, vars_, rng.randint(1, 5))
 else: funs, vars_ = W.ibp_like_collection(rng.randint(2, 300), max(nv, 2), seed=rng.randrange(1 << 30), den_run=rng.choice([0, 0, 2, 4, 16]))
 nv = len(vars_)
 opts = dict(cse=rng.random() < 0.9, fuse=rng.random() < 0.9, cross=rng.random() < 0.9, table=rng.random() < 0.85,
-            split=rng.random() < 0.9, temps=rng.choice([0, 0, 0, 1, 2, 3, 8]), check_is_equal=rng.random() < 0.15)
+            split=rng.random() < 0.9, horner=rng.random() < 0.9, temps=rng.choice([0, 0, 0, 1, 2, 3, 8]), check_is_equal=rng.random() < 0.15)
 if opts["check_is_equal"] and any(re.search(r"\^\((?!-?\d+\))", f) for f in funs): opts["check_is_equal"] = False
 primes = [rng.choice(ff.primes()), rng.choice(ff.primes()) if rng.random() < 0.7 else rng.choice(generic)]
 for k, v in over.items():

@@ -591,6 +591,53 @@ def test_long_sums_become_partial_sum_rows(oracle):
     assert small.n_split_rows == 0
 
 
+def test_expanded_polynomials_become_horner_nests(oracle):
+    """sums of monomials are factored greedily (P = v^m * Q + R): fewer multiplications, the same values -- dense
+    polynomials, signs of every kind (-x, -x^3, a term subtracted twice), rational coefficients, terms that are not
+    monomials in between, zeros; sums that would not gain are left as written; the pass switched off"""
+    import itertools
+    rng = random.Random(17)
+    vs = ["x", "y", "z"]
+
+    def dense(deg):
+        ts = []
+        for e in itertools.product(range(deg + 1), repeat=3):
+            if sum(e) > deg:
+                continue
+            mon = "*".join((f"{v}^{k}" if k > 1 else v) for v, k in zip(vs, e) if k > 0)
+            c = f"{rng.randint(1, 10**9)}" + (f"/{rng.randint(2, 999)}" if rng.random() < 0.3 else "")
+            ts.append(c + ("*" + mon if mon else ""))
+        rng.shuffle(ts)
+        return ts[0] + "".join(rng.choice("+-") + t for t in ts[1:])
+
+    funs = [f"({dense(9)})/({dense(4)})",
+            "-x^3*y+5*x^3*z-(-x)*y^2*7-x^3+(x+y)^2*3-(2*x^3*y*z-x^2*(-y))+x^0*4",
+            "x+y+z", "3*x*y+4*x*z", "x^2*y+x^2*z+x^2*7+(1/(x-y))*x^2"]
+    par = ff.GpuParser(None, funs, vs)
+    off = ff.GpuParser(None, funs, vs, horner=False)
+    for p in (ff.primes()[0], ff.primes()[77]):
+        par.set_prime(p)
+        off.set_prime(p)
+        assert par.cse_fallbacks == 0
+        pts = ff.synthetic_points(3, 6, p, seed=3)
+        pts[:, 0] = 0
+        pts[:, 1] = np.array([4, 4, 0], dtype=np.uint64)         # x - y = 0
+        pts[:, 2] = np.array([p - 1, 1, 2], dtype=np.uint64)
+        want = oracle.parse(funs, vs, p).eval(pts)
+        assert np.array_equal(interp(par, pts, p), want) and np.array_equal(interp(off, pts, p), want)
+    assert par.tape_work()["mm"] < 0.7 * off.tape_work()["mm"]
+    # one small function alone: Horner inside the single kernel, no rows
+    small = f"({dense(5)})/(x-y+1)"
+    one = ff.GpuParser(None, [small], vs)
+    assert one.n_table_rows == 0
+    one.set_prime(ff.primes()[0])
+    flat = ff.GpuParser(None, [small], vs, horner=False)
+    flat.set_prime(ff.primes()[0])
+    assert one.tape_work()["mm"] < 0.8 * flat.tape_work()["mm"]
+    pts = ff.synthetic_points(3, 3, ff.primes()[0], seed=5)
+    assert np.array_equal(interp(one, pts, ff.primes()[0]), oracle.parse([small], vs, ff.primes()[0]).eval(pts))
+
+
 def test_shared_denominator_edge_cases(oracle):
     """N and D related in every way a run can meet: D/D, D inside N, a variable as denominator, nested divisions"""
     vars_ = ["x", "y", "z"]
