@@ -114,7 +114,8 @@ size_t ffgpu_n_shared_denominators(const ffgpu_tape*);
  *            the pieces are evaluated by different thread blocks, so a single large function fills the chip even at
  *            the Reconstructor's bunch sizes; over the variables and the level-0 rows.
  * ffgpu_get_table_tape copies the tape of a level (its output r is row offset(level) + r); FFGPU_NO_TABLE turns both
- * levels off, FFGPU_NO_SPLIT the second. */
+ * levels off, FFGPU_NO_SPLIT the second.  Independently of the rows, sums of monomials (expanded polynomials) are
+ * factored into Horner nests where that saves multiplications (FFGPU_NO_HORNER: as written). */
 size_t ffgpu_n_table_rows(const ffgpu_tape*);                     /* all levels */
 size_t ffgpu_n_table_levels(const ffgpu_tape*);
 size_t ffgpu_n_table_rows_level(const ffgpu_tape*, size_t level);
