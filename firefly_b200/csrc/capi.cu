@@ -570,9 +570,9 @@ int ffgpu_set_prime(ffgpu_tape* t, uint64_t p) {
   if (p >= (1ULL << 63) || p < 3 || !(p & 1))
     return fail("unsupported modulus " + std::to_string(p) + ": need an odd prime below 2^63");
   std::string err;
-  const bool rebuilt = t->col.stale;      // functions were added or trimmed: the tape has a new size
+  const uint64_t rebuilds = t->col.rebuilds;      // functions added or trimmed, or a tiny prime: the tape has a new size
   if (!t->col.resolve(p, err)) return fail(err);
-  if (rebuilt) drop_device_copies(t);
+  if (t->col.rebuilds != rebuilds) drop_device_copies(t);
   t->needs_generic = false;
   for (const ffgpu::Instr& in : t->col.tape) t->needs_generic |= in.fast == ffgpu::FX_GENERIC && in.op != ffgpu::OP_HALT;
   for (size_t l = 0; l < t->col.pre.size() && l < 2; ++l) {

@@ -1668,7 +1668,7 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
       if (dup_of[i] < 0 && groups.size() < 4 * SPLIT_MAX_GROUPS) split_long_sums(functions[i], groups, cut[i]);
   // expanded polynomials -> Horner nests: in the partial sums, and in the sums of the functions that were not cut
   bool any_cut = !groups.empty();
-  if (enable_horner) {
+  if (enable_horner && !small_prime_mode_) {
     Function h;
     for (Function& g : groups)
       if (hornerize(g, h)) g = std::move(h);
@@ -1824,6 +1824,7 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
     pc.enable_cross = enable_cross;
     pc.enable_table = false;
     pc.temp_budget = temp_budget;
+    pc.small_prime_mode_ = small_prime_mode_;
     std::string perr;
     return pc.finish(perr);
   };
@@ -1874,6 +1875,7 @@ bool Collection::add_function(std::string text, uint64_t index, bool strip_blank
 
 bool Collection::finish(std::string& err) {
   (void)err;
+  ++rebuilds;
   stale = false;                 // resolve() below must not come back here
   n_out = check_is_equal ? evaluation_positions.size() : functions.size();
   // output slots per distinct function
@@ -1992,7 +1994,7 @@ bool Collection::finish(std::string& err) {
     // Translation check of every function at one pseudo-random point: the tape must reproduce the value of
     // the expression tree.  A function that fails is re-emitted as a plain tree (no sharing) on the second
     // pass; if that fails too the compilation is refused -- never a wrong probe value.
-    if (!resolve(P0, err)) return false;
+    if (!resolve_constants(P0, err)) return false;
     std::vector<uint64_t> pt(vars.size());
     uint64_t seed = 0x243F6A8885A308D3ULL;
     for (auto& v : pt) v = 1 + splitmix64(seed) % (P0 - 1);
@@ -2169,7 +2171,7 @@ void Collection::fuse() {
 
   // value of a literal exponent if it is the same small number for every prime
   auto small_literal = [&](int32_t pi, uint32_t& e) -> bool {
-    if (pi < 0) return false;
+    if (pi < 0 || small_prime_mode_) return false;      // tiny primes: exponents stay per-prime residues (resolve())
     const ConstPatch& cp = patches[pi];
     if (cp.inverse || cp.negate) return false;
     const Function& f = efn(cp.fn);
@@ -2540,11 +2542,25 @@ bool Collection::resolve(uint64_t p, std::string& err) {
     err = "prime must be below 2^63";
     return false;
   }
+  // A literal exponent is a residue like every other number of the input: the reference reduces it mod p and takes
+  // exponents from p/2 up as negative powers (FFInt::pow(const FFInt&), FFInt.cpp:155-179).  For the primes FireFly works
+  // with that never shows (a literal exponent is far below 2^62), and the passes that carry exponents as plain integers
+  // -- TERM's exponent field, the Horner nests, which split x^e into x^m * x^(e-m) -- rely on it.  Below 2^21 they are
+  // switched off: every power then goes through OP_POWU with its per-prime residue.
+  const bool small = p < (1ULL << 21);
+  if (small != small_prime_mode_) {
+    small_prime_mode_ = small;
+    stale = true;
+  }
   if (stale && !finish(err)) {
     stale = true;              // nothing usable was built: evaluation keeps refusing
     prime = 0;
     return false;
   }
+  return resolve_constants(p, err);
+}
+
+bool Collection::resolve_constants(uint64_t p, std::string& err) {
   std::vector<uint64_t> val;
   uint32_t cur = ~0u;
   for (const ConstPatch& cp : patches) {
@@ -2562,7 +2578,7 @@ bool Collection::resolve(uint64_t p, std::string& err) {
     if (in.op == OP_POWU) in.fast = (w < (p >> 1) && in.flags == 0) ? FX_POWU : FX_GENERIC;
   }
   for (Collection& pc : pre)
-    if (!pc.resolve(p, err)) return false;
+    if (!pc.resolve_constants(p, err)) return false;
   prime = p;
   return true;
 }

@@ -138,6 +138,8 @@ struct Collection {
   // recompute every constant for prime p and patch the tape (what prime_changed() ->
   // precompute_tokens() does in the reference, ShuntingYardParser.cpp:550-591)
   bool resolve(uint64_t p, std::string& err);
+  uint64_t rebuilds = 0;                      // how often the tape has been generated (resolve() regenerates it when functions
+                                              // were added or trimmed, and when the prime crosses 2^21: see resolve())
   // divide output `first` by the function `second` (written over factor_vars, matched to vars by position) and
   // rebuild the tape; replaces factors set earlier.  The prime has to be set again afterwards.
   bool apply_factors(const std::vector<std::pair<uint32_t, std::string>>& factors,
@@ -166,6 +168,8 @@ struct Collection {
   // what the tape is generated from: `functions` with every occurrence of a shared row replaced by a variable leaf
   std::vector<Function> lowered_;
   std::vector<uint32_t> pre_row_offset_;
+  bool small_prime_mode_ = false;             // the tape was generated for a prime below 2^21 (no integer-exponent passes)
+  bool resolve_constants(uint64_t p, std::string& err);
   const Function& efn(size_t i) const { return lowered_.empty() ? functions[i] : lowered_[i]; }
   void build_table(const std::vector<int32_t>& dup_of);
   void emit_function(uint32_t fn, const std::vector<uint32_t>& out_slots, int den_mode);

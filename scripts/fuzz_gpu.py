@@ -38,7 +38,7 @@ def main():
     from test_gpu_parity import _dag_expressions
     ctx = ff.Context()
     orc = Oracle()
-    generic = [9223372036854742973, 4611686018427400249, 2305843009213693951, 1099511627689, 4294967311]
+    generic = [9223372036854742973, 4611686018427400249, 2305843009213693951, 1099511627689, 4294967311, 2097143, 65537, 997, 103]
     t0 = time.time()
     values = fails = refused = 0
     rounds = a.first

@@ -10,7 +10,7 @@ from fuzz_compiler import free_grammar, long_sums, table
 from oracle_bind import Oracle
 from test_gpu_parity import _dag_expressions
 orc = Oracle()
-generic = [9223372036854742973, 4611686018427400249, 2305843009213693951, 1099511627689, 4294967311]
+generic = [9223372036854742973, 4611686018427400249, 2305843009213693951, 1099511627689, 4294967311, 2097143, 65537, 997, 103]
 seed, rnd = int(sys.argv[1]), int(sys.argv[2])
 over = dict(kv.split("=") for kv in sys.argv[3:])
 rng = random.Random((seed << 20) ^ rnd)

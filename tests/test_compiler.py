@@ -638,6 +638,21 @@ def test_expanded_polynomials_become_horner_nests(oracle):
     assert np.array_equal(interp(one, pts, ff.primes()[0]), oracle.parse([small], vs, ff.primes()[0]).eval(pts))
 
 
+def test_literal_exponents_are_residues_for_tiny_primes(oracle):
+    """the reference reduces a literal exponent mod p and takes it as a negative power from p/2 up (FFInt.cpp:155-179):
+    invisible for 63-bit primes, but x^103 mod 103 is x^0 there.  Below 2^21 the tape is generated without the passes that
+    carry exponents as plain integers (TERM's exponent field, Horner nests); moving between the two regimes regenerates it"""
+    funs = ["x^200+y", "x^60*y+x^60*3+x^61*y^2", "x^103", "5*x^104*y+7*x^105*y+x^104", "x^20+y^20+(x+y)^200"]
+    par = ff.GpuParser(None, funs, ["x", "y"])
+    sizes = {}
+    for p in (103, ff.primes()[0], 997, 103, 2097143, ff.primes()[3], 3):
+        par.set_prime(p)
+        pts = np.array([[2, 3, 0, 5, 100], [7, 1, 4, 0, 9]], dtype=np.uint64) % np.uint64(p)
+        assert np.array_equal(interp(par, pts, p), oracle.parse(funs, ["x", "y"], p).eval(pts)), p
+        sizes.setdefault(p < (1 << 21), set()).add(par.n_instr)
+    assert len(sizes[True]) == 1 and len(sizes[False]) == 1 and sizes[True] != sizes[False]
+
+
 def test_shared_denominator_edge_cases(oracle):
     """N and D related in every way a run can meet: D/D, D inside N, a variable as denominator, nested divisions"""
     vars_ = ["x", "y", "z"]

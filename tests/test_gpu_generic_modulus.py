@@ -116,3 +116,17 @@ def test_rejected_moduli(ctx):
     for bad in (0, 1, 2, 4, 10, 1 << 63, (1 << 63) + 1):
         with pytest.raises(ff.FFGpuError):
             par.set_prime(bad)
+
+
+def test_literal_exponents_for_tiny_primes_on_device(ctx, oracle):
+    """exponents at and above p/2 and above p (x^103 mod 103 = x^0 in the reference's arithmetic, FFInt.cpp:155-179): the
+    same handle moves between tiny primes and FireFly's, the tape and its device copies are regenerated at the border"""
+    funs = ["x^200+y", "x^60*y+x^60*3+x^61*y^2", "x^103", "5*x^104*y+7*x^105*y+x^104", "x^20+y^20+(x+y)^200", "(x^70-y)/(x^150+3)"]
+    par = ff.GpuParser(ctx, funs, ["x", "y"])
+    for p in (103, ff.primes()[0], 997, 103, 65537, 2097143, ff.primes()[3]):
+        par.set_prime(p)
+        for n in (1, 7, 300):
+            pts = ff.synthetic_points(2, n, p, seed=n)
+            pts[:, 0] = 0
+            assert np.array_equal(par.evaluate_pre(pts), oracle.parse(funs, ["x", "y"], p).eval(pts)), (p, n)
+    par.close()
