@@ -224,12 +224,19 @@ int launch_one(ffgpu_tape* t, const ffgpu::Collection& c, const ffgpu::Instr* d_
   const ffgpu::LaunchShape sh = ffgpu::choose_shape(n_points, c.n_slots, t->ctx->devs[g].sm_count, t->force_k,
                                                     t->force_threads, c.max_chunks, !needs_generic, prm.generic != 0);
   prm.chunk_bounds = nullptr;
-  if (sh.chunks > 1) {
+  ffgpu::LaunchShape shape = sh;
+  static const bool no_exact = std::getenv("FFGPU_NO_EXACT_CHUNKS") != nullptr;       // A/B switch (development)
+  if (!no_exact && c.exact_chunks > shape.chunks && shape.chunks == c.max_chunks && !t->force_k && !t->force_threads &&
+      (uint64_t)shape.blocks * shape.chunks < 4ull * (uint64_t)t->ctx->devs[g].sm_count) {
+    // few points and more functions than the largest power-of-two split: one function per chunk
+    shape.chunks = c.exact_chunks;
+    prm.chunk_bounds = d_chunks + c.chunk_table_off[c.exact_table];
+  } else if (shape.chunks > 1) {
     unsigned idx = 0;
-    while ((1u << idx) < sh.chunks) ++idx;
+    while ((1u << idx) < shape.chunks) ++idx;
     prm.chunk_bounds = d_chunks + c.chunk_table_off[idx];
   }
-  cudaError_t e = ffgpu::launch_eval(prm, sh, stream);
+  cudaError_t e = ffgpu::launch_eval(prm, shape, stream);
   if (e != cudaSuccess) return cuda_fail(e, "launch_eval");
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;

@@ -2091,6 +2091,26 @@ bool Collection::finish(std::string& err) {
     chunk_table.push_back(total);
     max_chunks = C;
   }
+  // One more table with ONE function per chunk (as far as functions may be separated): a collection of a few heavy
+  // functions -- the partial sums of a long sum -- evaluated at a handful of points wants every function on an SM of
+  // its own, and the power-of-two tables above put two of 194 into every second chunk.
+  exact_chunks = 0;
+  exact_table = 0;
+  if (functions.size() > max_chunks && functions.size() <= 1024) {
+    std::vector<uint32_t> starts;
+    for (size_t g = 0; g < functions.size(); ++g) {
+      if (den_mode_[order_[g]] == 2 || dup_of[order_[g]] >= 0) continue;            // stays with the function before it
+      if (!starts.empty() && starts.back() == fn_start[g]) continue;
+      starts.push_back(fn_start[g]);
+    }
+    if (starts.size() > max_chunks && !starts.empty() && starts[0] == 0) {
+      exact_table = (uint32_t)chunk_table_off.size();
+      chunk_table_off.push_back((uint32_t)chunk_table.size());
+      chunk_table.insert(chunk_table.end(), starts.begin(), starts.end());
+      chunk_table.push_back(total);
+      exact_chunks = (uint32_t)starts.size();
+    }
+  }
   Instr halt{};
   halt.op = OP_HALT;
   tape.push_back(halt);

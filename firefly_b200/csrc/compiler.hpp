@@ -124,6 +124,8 @@ struct Collection {
   std::vector<uint32_t> chunk_table;
   std::vector<uint32_t> chunk_table_off;
   unsigned max_chunks = 1;
+  uint32_t exact_chunks = 0;                  // chunks of the one-function-per-chunk table (0: there is none), and its
+  uint32_t exact_table = 0;                   // index into chunk_table_off
   uint64_t prime = 0;                         // prime the imm fields are resolved for (0: none)
   WorkCount work;                             // algorithmic: counted on the reference's token list
   WorkCount executed;                         // what the emitted tape does per probe (tokens = instructions,
