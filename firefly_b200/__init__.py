@@ -85,6 +85,7 @@ def _load() -> C.CDLL:
         "ffgpu_get_table_tape": (C.c_size_t, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
         "ffgpu_n_table_levels": (C.c_size_t, [C.c_void_p]),
         "ffgpu_n_table_rows_level": (C.c_size_t, [C.c_void_p, C.c_size_t]),
+        "ffgpu_table_row_offset": (C.c_size_t, [C.c_void_p, C.c_size_t]),
         "ffgpu_n_split_rows": (C.c_size_t, [C.c_void_p]),
         "ffgpu_rpn": (C.c_size_t, [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]),
         "ffgpu_get_tape": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -144,7 +145,7 @@ lib = _load()
 EXPORTS = [
     "ffgpu_create", "ffgpu_destroy", "ffgpu_n_devices", "ffgpu_last_error", "ffgpu_compile", "ffgpu_compile_text",
     "ffgpu_compile_file", "ffgpu_tape_clone", "ffgpu_tape_destroy", "ffgpu_n_vars", "ffgpu_n_functions", "ffgpu_n_out", "ffgpu_n_instr",
-    "ffgpu_stack_depth", "ffgpu_n_temps", "ffgpu_n_slots", "ffgpu_cse_fallbacks", "ffgpu_n_structural_duplicates", "ffgpu_n_shared_denominators", "ffgpu_n_table_rows", "ffgpu_get_table_tape", "ffgpu_n_table_levels", "ffgpu_n_table_rows_level", "ffgpu_n_split_rows", "ffgpu_rpn", "ffgpu_get_tape", "ffgpu_work", "ffgpu_tape_work", "ffgpu_set_factors", "ffgpu_set_prime", "ffgpu_get_prime",
+    "ffgpu_stack_depth", "ffgpu_n_temps", "ffgpu_n_slots", "ffgpu_cse_fallbacks", "ffgpu_n_structural_duplicates", "ffgpu_n_shared_denominators", "ffgpu_n_table_rows", "ffgpu_get_table_tape", "ffgpu_n_table_levels", "ffgpu_n_table_rows_level", "ffgpu_table_row_offset", "ffgpu_n_split_rows", "ffgpu_rpn", "ffgpu_get_tape", "ffgpu_work", "ffgpu_tape_work", "ffgpu_set_factors", "ffgpu_set_prime", "ffgpu_get_prime",
     "ffgpu_add_function", "ffgpu_add_function_rpn", "ffgpu_trim", "ffgpu_is_stale",
     "ffgpu_n_primes", "ffgpu_prime", "ffgpu_eval", "ffgpu_eval_line", "ffgpu_eval_wire", "ffgpu_eval_device", "ffgpu_host_alloc", "ffgpu_host_free",
     "ffgpu_queue_create", "ffgpu_queue_destroy", "ffgpu_queue_push", "ffgpu_queue_push_many", "ffgpu_queue_push_line",
@@ -256,8 +257,9 @@ class GpuParser:
         return arr
 
     def table_levels(self) -> list:
-        """[(tape, rows)] of every level of shared rows, in evaluation order"""
-        return [(self.table_tape(l), lib.ffgpu_n_table_rows_level(self.h, l)) for l in range(lib.ffgpu_n_table_levels(self.h))]
+        """[(tape, rows, first row)] of every level of shared rows, in evaluation order"""
+        return [(self.table_tape(l), lib.ffgpu_n_table_rows_level(self.h, l), lib.ffgpu_table_row_offset(self.h, l))
+                for l in range(lib.ffgpu_n_table_levels(self.h))]
 
     @property
     def n_split_rows(self) -> int:

@@ -520,6 +520,7 @@ size_t ffgpu_n_table_rows(const ffgpu_tape* t) { return t->col.n_table_rows; }
 size_t ffgpu_n_table_levels(const ffgpu_tape* t) { return t->col.pre.size(); }
 size_t ffgpu_n_table_rows_level(const ffgpu_tape* t, size_t level) { return level < t->col.pre.size() ? t->col.pre[level].n_out : 0; }
 size_t ffgpu_n_split_rows(const ffgpu_tape* t) { return t->col.n_split_rows; }
+size_t ffgpu_table_row_offset(const ffgpu_tape* t, size_t level) { return level < t->col.pre.size() ? t->col.pre_row_offset()[level] : 0; }
 size_t ffgpu_get_table_tape(const ffgpu_tape* t, size_t level, void* buf, size_t cap) {
   if (level >= t->col.pre.size()) return 0;
   const std::vector<ffgpu::Instr>& tp = t->col.pre[level].tape;

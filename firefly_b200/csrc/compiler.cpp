@@ -1780,7 +1780,9 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
   std::vector<std::vector<Fp>> tfps(table.size());
   for (size_t r = 0; r < table.size(); ++r) fingerprints(table[r], tfps[r]);
   // every unit with its selected occurrences replaced by their rows (equal fingerprints are confirmed exactly) and
-  // the placeholders of the partial sums by theirs: level-0 rows first, the partial sums (level 1) after them
+  // the placeholders of the partial sums by theirs.  The partial sums (level 1) get the LOW row numbers, the level-0
+  // rows the ones after them: the function that adds up its partial sums then reaches them with the 8-bit variable
+  // fields of ADDVARS (eight rows per instruction instead of one -- the sum is a serial walk at small batches).
   const uint32_t R0 = (uint32_t)table.size(), R1 = (uint32_t)groups.size();
   auto lower = [&](size_t u, Function& dst) {
     const Function& f = *unit[u];
@@ -1791,10 +1793,10 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
       if (it == cands.end() || !it->second.selected) return -1;
       const int32_t r = it->second.row;
       if (!same_structure(f, fps[u], k, table[r], tfps[r], table[r].root)) return -1;
-      return (int64_t)n_base + r;
+      return (int64_t)n_base + R1 + r;
     });
     for (Node& n : dst.nodes)
-      if ((n.kind == N_VAR || n.kind == N_NEGVAR) && n.var >= GROUP_BASE) n.var = n_base + R0 + (n.var - GROUP_BASE);
+      if ((n.kind == N_VAR || n.kind == N_NEGVAR) && n.var >= GROUP_BASE) n.var = n_base + (n.var - GROUP_BASE);
     compute_needs(dst);
   };
   lowered_.resize(nf);
@@ -1830,8 +1832,8 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
   };
   bool ok = true;
   pre_row_offset_.clear();
-  if (R0) { pre_row_offset_.push_back(0); ok = add_level(std::move(table), 0); }
-  if (ok && R1) { pre_row_offset_.push_back(R0); ok = add_level(std::move(lowered_groups), R0); }
+  if (R0) { pre_row_offset_.push_back(R1); ok = add_level(std::move(table), 0); }
+  if (ok && R1) { pre_row_offset_.push_back(0); ok = add_level(std::move(lowered_groups), R1 + R0); }
   if (!ok) {                       // never expected; the functions are then compiled as written
     pre.clear();
     pre_row_offset_.clear();
@@ -2000,13 +2002,13 @@ bool Collection::finish(std::string& err) {
     for (auto& v : pt) v = 1 + splitmix64(seed) % (P0 - 1);
     // the shared rows at that point, level by level, from their own expression trees (each level's tape has been
     // checked against them by its own finish()); a level sees the variables and the rows of the levels before it
-    for (const Collection& pc : pre) {
-      std::vector<uint64_t> val, level;
-      for (const Function& tf : pc.functions) {
-        eval_nodes(tf, P0, pt.data(), val);
-        level.push_back(val[tf.root]);
+    pt.resize(vars.size() + n_table_rows, 0);
+    for (size_t l = 0; l < pre.size(); ++l) {
+      std::vector<uint64_t> val;
+      for (size_t r = 0; r < pre[l].functions.size(); ++r) {
+        eval_nodes(pre[l].functions[r], P0, pt.data(), val);
+        pt[vars.size() + pre_row_offset_[l] + r] = val[pre[l].functions[r].root];
       }
-      pt.insert(pt.end(), level.begin(), level.end());
     }
     bool again = false;
     uint64_t chk_temps[16] = {};

@@ -119,6 +119,7 @@ size_t ffgpu_n_shared_denominators(const ffgpu_tape*);
 size_t ffgpu_n_table_rows(const ffgpu_tape*);                     /* all levels */
 size_t ffgpu_n_table_levels(const ffgpu_tape*);
 size_t ffgpu_n_table_rows_level(const ffgpu_tape*, size_t level);
+size_t ffgpu_table_row_offset(const ffgpu_tape*, size_t level);   /* first row the level writes */
 size_t ffgpu_n_split_rows(const ffgpu_tape*);                     /* partial sums among them */
 size_t ffgpu_get_table_tape(const ffgpu_tape*, size_t level, void* buf, size_t cap);
 size_t ffgpu_n_slots(const ffgpu_tape*);        /* shared-memory slots per probe the kernel reserves (spill + temps) */

@@ -239,10 +239,13 @@ def one_round(seed, rnd):
                 want[i] = [int(b) * (pow(int(f), p - 2, p) if int(f) else 0) % p for b, f in zip(want[i], fac[row])]
         tape = par.tape()
         levels = par.table_levels()
+        n_rows = par.n_table_rows
         for j in range(npts):
             pt = [int(x) for x in pts[:, j]]
-            for pre, rows in levels:
-                pt = pt + run(pre, pt, p, rows)      # the shared rows are variables n_vars, n_vars + 1, ..., level by level
+            base = len(pt)
+            pt = pt + [0] * n_rows                   # the shared rows are variables n_vars, n_vars + 1, ...
+            for pre, rows, off in levels:            # level by level, each at its offset
+                pt[base + off:base + off + rows] = run(pre, pt, p, rows)
             got = run(tape, pt, p, par.n_out)
             exp = [int(x) for x in want[:, j]]
             if got != exp:

@@ -10,7 +10,7 @@ g = json.load(open("tests/golden/s_y_4_v.json"))
 funs, vars_ = g["functions"], g["vars"]
 par = ff.GpuParser(ctx, funs, vars_)
 par.set_prime(p)
-print(os.environ.get("FFGPU_SPLIT_TARGET"), os.environ.get("FFGPU_SPLIT_MIN"), "rows", par.n_table_rows, "partial sums", par.n_split_rows, "main", par.n_instr, [(len(t), r) for t, r in par.table_levels()])
+print(os.environ.get("FFGPU_SPLIT_TARGET"), os.environ.get("FFGPU_SPLIT_MIN"), "rows", par.n_table_rows, "partial sums", par.n_split_rows, "main", par.n_instr, [(len(t), r, o) for t, r, o in par.table_levels()])
 s = torch.cuda.current_stream().cuda_stream
 for b in (1, 128):
     vals = torch.empty((4, b + (b & 1)), dtype=torch.int64, device="cuda")

@@ -17,12 +17,16 @@ P0 = 9223372036854775783
 def interp(par, pts, p):
     tape = par.tape()
     levels = par.table_levels()
+    n_rows = par.n_table_rows
 
     def one(pt):
-        # the shared rows first, level by level (their own tapes), then the functions with the rows as extra variables
-        for pre, rows in levels:
-            pt = pt + run(pre, pt, p, rows)
-        return run(tape, pt, p, par.n_out)
+        # the shared rows first, level by level (their own tapes; a level writes its rows at its offset), then the
+        # functions with the rows as extra variables
+        full = pt + [0] * n_rows
+        for pre, rows, off in levels:
+            vals = run(pre, full, p, rows)
+            full[len(pt) + off:len(pt) + off + rows] = vals
+        return run(tape, full, p, par.n_out)
     cols = [one([int(x) for x in pts[:, j]]) for j in range(pts.shape[1])]
     return np.array(cols, dtype=np.uint64).T.reshape(par.n_out, pts.shape[1])
 
@@ -306,7 +310,7 @@ def test_fused_and_plain_tapes_agree(oracle, cse, fuse):
     par = ff.GpuParser(None, funs, vars_, cse=cse, fuse=fuse)
     par.set_prime(p)
     assert par.cse_fallbacks == 0
-    ops = {ff.OPS[o] for o in par.tape()["op"]} | {ff.OPS[o] for tp, _ in par.table_levels() for o in tp["op"]}
+    ops = {ff.OPS[o] for o in par.tape()["op"]} | {ff.OPS[o] for tp, _, _ in par.table_levels() for o in tp["op"]}
     assert ({"TERM", "MULADD", "ADDVARS", "MULVARS"} <= ops) == fuse
     assert np.array_equal(interp(par, pts, p), want)
 
@@ -576,6 +580,7 @@ def test_long_sums_become_partial_sum_rows(oracle):
     assert par.n_split_rows >= 8 and off.n_split_rows == 0 and plain.n_table_rows == 0
     levels = par.table_levels()
     assert len(levels) == 2 and levels[1][1] == par.n_split_rows and levels[0][1] + levels[1][1] == par.n_table_rows
+    assert levels[1][2] == 0 and levels[0][2] == par.n_split_rows          # the partial sums have the low row numbers
     assert par.n_instr < 200 < off.n_instr
     for p in (ff.primes()[0], ff.primes()[31]):
         pts = ff.synthetic_points(3, 5, p, seed=6)
