@@ -1756,7 +1756,7 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
     if (benefit(x) != benefit(y)) return benefit(x) > benefit(y);
     return x->fn != y->fn ? x->fn < y->fn : x->node < y->node;       // deterministic
   });
-  const size_t limit = table_row_limit ? table_row_limit : 192;
+  const size_t limit = table_row_limit ? table_row_limit : env_u32("FFGPU_TABLE_ROWS", 192);
   if (chosen.size() > limit) {
     for (size_t k = limit; k < chosen.size(); ++k) chosen[k]->selected = false;
     chosen.resize(limit);
