@@ -28,6 +28,7 @@
 #include <cstdlib>
 #include <functional>
 #include <string>
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -69,8 +70,15 @@ class GpuBlackBox : public BlackBoxBase<GpuBlackBox> {
   // (Reconstructor.hpp:2981-2983); each calling thread is mapped to its own stream slot.
   template <typename FFIntTemp>
   std::vector<FFIntTemp> operator()(const std::vector<FFIntTemp>& values) {
-    const uint32_t slot = (uint32_t)std::hash<std::thread::id>()(std::this_thread::get_id());
-    return (*this)(values, slot);
+    return (*this)(values, caller_slot());
+  }
+
+  // Every calling thread gets a number of its own in order of first appearance: the library maps it to one of its
+  // caller slots (stream + staging), so a pool of up to 32 threads never shares one (a hash of the thread id did).
+  static uint32_t caller_slot() {
+    static std::atomic<uint32_t> next{0};
+    thread_local const uint32_t mine = next.fetch_add(1, std::memory_order_relaxed);
+    return mine;
   }
 
   template <typename FFIntTemp>

@@ -41,6 +41,7 @@
 #include <memory>
 #include <sstream>
 #include <string>
+#include <atomic>
 #include <thread>
 #include <unordered_map>
 #include <unordered_set>
@@ -152,7 +153,8 @@ class GpuShuntingYardParser {
     if (!tape_) return std::vector<FFIntTemp>();
     if (values.size() < ffgpu_n_vars(tape_)) die("parser called with too few variables");
     std::vector<FFIntTemp> result(ffgpu_n_out(tape_));
-    const uint32_t slot = static_cast<uint32_t>(std::hash<std::thread::id>()(std::this_thread::get_id()));
+    static std::atomic<uint32_t> next_slot{0};                 // one caller slot per thread, in order of first appearance
+    thread_local const uint32_t slot = next_slot.fetch_add(1, std::memory_order_relaxed);
     if (ffgpu_eval(tape_, reinterpret_cast<const uint64_t*>(values.data()), lanes,
                    reinterpret_cast<uint64_t*>(result.data()), slot))
       die(ffgpu_last_error());
