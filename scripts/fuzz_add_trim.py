@@ -83,8 +83,13 @@ while time.time()-t0 < float(sys.argv[2]):
     pts = ff.synthetic_points(nv, 4, p, seed=rounds); pts[:,0]=0; pts[:,1]=1
     want = orc.parse(cur, vars_, p).eval(pts)
     tape = par.tape()
+    levels = par.table_levels()
     for j in range(4):
-        got = run(tape, [int(x) for x in pts[:,j]], p, par.n_out)
+        pt = [int(x) for x in pts[:,j]]
+        full = pt + [0] * par.n_table_rows          # shared rows: level by level, each at its offset (include/ffgpu.h)
+        for pre, rows, off in levels:
+            full[len(pt) + off:len(pt) + off + rows] = run(pre, full, p, rows)
+        got = run(tape, full, p, par.n_out)
         if got != [int(x) for x in want[:,j]]:
             bad+=1; print("FAIL", seed0, rounds-1, kind, chk, opts); break
     par.close()
