@@ -38,6 +38,7 @@
 #include "firefly/Logger.hpp"
 
 #include "../ffgpu.h"
+#include "caller_slot.hpp"
 
 namespace firefly {
 
@@ -75,11 +76,7 @@ class GpuBlackBox : public BlackBoxBase<GpuBlackBox> {
 
   // Every calling thread gets a number of its own in order of first appearance: the library maps it to one of its
   // caller slots (stream + staging), so a pool of up to 32 threads never shares one (a hash of the thread id did).
-  static uint32_t caller_slot() {
-    static std::atomic<uint32_t> next{0};
-    thread_local const uint32_t mine = next.fetch_add(1, std::memory_order_relaxed);
-    return mine;
-  }
+  static uint32_t caller_slot() { return gpu_caller_slot(); }
 
   template <typename FFIntTemp>
   std::vector<FFIntTemp> operator()(const std::vector<FFIntTemp>& values, uint32_t thread_id) {

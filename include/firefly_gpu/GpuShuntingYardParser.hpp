@@ -52,6 +52,7 @@
 #include "firefly/Logger.hpp"
 
 #include "../ffgpu.h"
+#include "caller_slot.hpp"
 
 namespace firefly {
 
@@ -153,8 +154,7 @@ class GpuShuntingYardParser {
     if (!tape_) return std::vector<FFIntTemp>();
     if (values.size() < ffgpu_n_vars(tape_)) die("parser called with too few variables");
     std::vector<FFIntTemp> result(ffgpu_n_out(tape_));
-    static std::atomic<uint32_t> next_slot{0};                 // one caller slot per thread, in order of first appearance
-    thread_local const uint32_t slot = next_slot.fetch_add(1, std::memory_order_relaxed);
+    const uint32_t slot = gpu_caller_slot();                   // one caller slot per thread, in order of first appearance
     if (ffgpu_eval(tape_, reinterpret_cast<const uint64_t*>(values.data()), lanes,
                    reinterpret_cast<uint64_t*>(result.data()), slot))
       die(ffgpu_last_error());
