@@ -13,6 +13,9 @@
 //
 //   gpu_reconstruct <file.m> <bunch> <threads> <var> [<var> ...]
 //   exit 0 = identical, 1 = different, 2 = usage
+//   FFGPU_RECONSTRUCT_MODE = shift (default: enable_shift_scan, test/test_normal.cpp:89, test_bunch.cpp:69) |
+//                            safe (set_safe_interpolation, test/test_safe.cpp:80, test_bunch.cpp:84) |
+//                            none (neither, test/test_normal.cpp:81)
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -65,7 +68,14 @@ static std::vector<std::string> reconstruct_all(BB& bb, uint32_t n, uint32_t thr
   FFInt::set_new_prime(primes()[0]);
   bb.prime_changed_internal();
   Reconstructor<BB> rec(n, threads, bunch, bb, Reconstructor<BB>::SILENT);
-  rec.enable_shift_scan();
+  const char* mode_env = std::getenv("FFGPU_RECONSTRUCT_MODE");
+  const std::string mode = mode_env && *mode_env ? mode_env : "shift";
+  if (mode == "shift") rec.enable_shift_scan();
+  else if (mode == "safe") rec.set_safe_interpolation();
+  else if (mode != "none") {
+    std::fprintf(stderr, "FFGPU_RECONSTRUCT_MODE must be shift, safe or none\n");
+    std::exit(2);
+  }
   rec.reconstruct();
   std::vector<std::string> out;
   for (const auto& rf : rec.get_result()) out.push_back(rf.to_string(vars));

@@ -16,28 +16,44 @@ BIN = os.path.join(ROOT, "oracle", "_ref", "gpu_reconstruct")
 
 
 CASES = [
-    ("s_y_4_v", 1, 4),       # configs[0]: s_y_4_v.m, bunch_size = 1
-    ("s_y_4_v", 4, 4),       # the reference's test_bunch.cpp setting
-    ("s_y_1_v", 128, 2),
-    ("f1", 64, 4),
-    ("factors3", 16, 4),
+    ("s_y_4_v", 1, 4, "shift"),       # configs[0]: s_y_4_v.m, bunch_size = 1 (test/test_normal.cpp:87-91)
+    ("s_y_4_v", 4, 4, "shift"),       # the reference's test_bunch.cpp:67-71
+    ("s_y_1_v", 128, 2, "shift"),
+    ("f1", 64, 4, "shift"),
+    ("factors3", 16, 4, "shift"),
+    # the rest of the reference's own test matrix for this path: one variable without scans (test_normal.cpp:79-83)
+    # and in bunches (test_bunch.cpp:74-78), the safe interpolation mode on s_y_safe.m, s_y_1_v.m and s_y_4_v.m
+    # (test_safe.cpp:77-96, test_bunch.cpp:81-85)
+    ("s_y_1_v", 1, 4, "none"),
+    ("s_y_1_v", 4, 4, "shift"),
+    ("s_y_safe", 1, 4, "safe"),
+    ("s_y_safe", 4, 4, "safe"),
+    ("s_y_1_v", 1, 4, "safe"),
+    ("s_y_4_v", 4, 4, "safe"),
 ]
 # configs[4]: the full f4 reconstruction (106 668 probes, about 2.5 minutes for the CPU and the GPU run together --
 # the interpolation is sequential host work).  Runs wherever the box has the cores the reference's thread pool is
 # given here; FFGPU_SKIP_SLOW_TESTS=1 leaves it out.
 if (os.cpu_count() or 1) >= 8 and not os.environ.get("FFGPU_SKIP_SLOW_TESTS"):
-    CASES.append(("f4", 128, 16))
+    CASES.append(("f4", 128, 16, "shift"))
 
 
-@pytest.mark.parametrize("name,bunch,threads", CASES)
-def test_reconstruction_identical(tmp_path, name, bunch, threads):
+def _case_id(c):
+    name, bunch, threads, mode = c
+    return f"{name}-{bunch}-{threads}" + ("" if mode == "shift" else f"-{mode}")
+
+
+@pytest.mark.parametrize("name,bunch,threads,mode", CASES, ids=[_case_id(c) for c in CASES])
+def test_reconstruction_identical(tmp_path, name, bunch, threads, mode):
     if not os.path.exists(BIN):
         pytest.skip("oracle/_ref/gpu_reconstruct not built (needs /root/reference at build time)")
     g = load_golden(name)
     f = tmp_path / (name + ".m")
     f.write_text(";\n".join(g["functions"]) + ";\n")
     # the full f4 run also exercises the aggregator of concurrent small calls under the real thread pool (off by default)
-    env = dict(os.environ, FFGPU_COALESCE="1") if name == "f4" else None
+    env = dict(os.environ, FFGPU_RECONSTRUCT_MODE=mode)
+    if name == "f4":
+        env["FFGPU_COALESCE"] = "1"
     r = subprocess.run([BIN, str(f), str(bunch), str(threads), *g["vars"]], cwd=tmp_path, capture_output=True,
                        text=True, timeout=1200, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
@@ -53,7 +69,7 @@ def test_reconstruction_identical(tmp_path, name, bunch, threads):
     os.makedirs(out_dir, exist_ok=True)
     with open(os.path.join(out_dir, "reconstruct_black_box_times.log"), "a") as log:
         for ln in lines:
-            log.write(f"{name} bunch={bunch} threads={threads} launches={launches} {ln}\n")
+            log.write(f"{name} bunch={bunch} threads={threads} mode={mode} launches={launches} {ln}\n")
     if name == "f4":
         # 16 pool threads with bunches of up to 128 points: concurrent calls share launches (ffgpu_set_coalesce);
         # round 1 needed 28 767 launches for this run
