@@ -138,6 +138,17 @@ class GpuBlackBox : public BlackBoxBase<GpuBlackBox> {
     n_vars_ = ffgpu_n_vars(tape_);
     n_out_ = ffgpu_n_out(tape_);
     prime_changed();      // ShuntingYardParser's constructor precomputes for the current prime (:181)
+    warm_up();
+  }
+  // The first evaluation of a process loads the kernels it launches (the CUDA runtime loads them lazily: 31 ms
+  // measured on a B200, profiles/r02_first_call.log) and sets up the caller slot.  Paid here, once, it stays out of
+  // what the Reconstructor reports as the time of a black-box probe: every pool thread's first call would wait for it.
+  void warm_up() {
+    if (!n_vars_ && !n_out_) return;
+    for (size_t lanes : {(size_t)1, (size_t)128}) {
+      std::vector<uint64_t> ones(std::max<size_t>(n_vars_ * lanes, 1), 1), out(std::max<size_t>(n_out_ * lanes, 1));
+      if (ffgpu_eval(tape_, ones.data(), lanes, out.data(), 0)) die(ffgpu_last_error());
+    }
   }
 
   ffgpu_ctx* ctx_ = nullptr;
