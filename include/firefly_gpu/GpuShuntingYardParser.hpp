@@ -35,6 +35,7 @@
 // Without a GPU the parser can still be built and inspected (RPN, sizes, trim maps: host logic); evaluate_pre then
 // fails loudly.  There is no CPU evaluation path.  Errors: ERROR_MSG + std::exit(EXIT_FAILURE) like the reference.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <functional>
@@ -141,6 +142,17 @@ class GpuShuntingYardParser {
     if (FFInt::p == prime_internal && !force && !ffgpu_is_stale(tape_)) return;
     if (ffgpu_set_prime(tape_, FFInt::p)) die(ffgpu_last_error());
     prime_internal = FFInt::p;
+    warm_up_once();
+  }
+  // The first evaluation of a process loads the kernels it launches (lazy loading: 31 ms on a B200,
+  // profiles/r02_first_call.log).  The first parser that has functions pays it here, so that it does not show up in
+  // what the Reconstructor reports as the time of a black-box probe (see GpuBlackBox::warm_up).
+  void warm_up_once() const {
+    static std::atomic<bool> done{false};
+    const size_t n = ffgpu_n_vars(tape_), m = ffgpu_n_out(tape_);
+    if (m == 0 || done.exchange(true)) return;
+    std::vector<uint64_t> ones(std::max<size_t>(n, 1), 1), out(m);
+    if (ffgpu_eval(tape_, ones.data(), 1, out.data(), 0)) die(ffgpu_last_error());
   }
 
   // --- evaluation ----------------------------------------------------------------------------------------------
