@@ -150,7 +150,7 @@ class GpuShuntingYardParser {
   void warm_up_once() const {
     static std::atomic<bool> done{false};
     const size_t n = ffgpu_n_vars(tape_), m = ffgpu_n_out(tape_);
-    if (m == 0 || done.exchange(true)) return;
+    if (m == 0 || !ctx() || done.exchange(true)) return;      // no GPU: a host-only parser (RPN, sizes) evaluates nothing
     std::vector<uint64_t> ones(std::max<size_t>(n, 1), 1), out(m);
     if (ffgpu_eval(tape_, ones.data(), 1, out.data(), 0)) die(ffgpu_last_error());
   }
