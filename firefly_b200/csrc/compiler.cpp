@@ -1699,19 +1699,28 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
   };
   std::vector<std::vector<Fp>> fps(nu);
   std::unordered_map<FpKey, Cand, FpKeyHash> cands;
+  // the candidate of every node, looked up once (the map's elements never move): the passes below walk the trees
+  // again and again, and on a 10 000-function collection the lookups were half of the whole compilation
+  std::vector<std::vector<Cand*>> cand_of(nu);
+  {
+    size_t total_nodes = 0;
+    for (size_t i = 0; i < nu; ++i) total_nodes += unit[i]->nodes.size();
+    cands.reserve(total_nodes / 2);
+  }
   std::vector<uint32_t> cost;
   for (size_t i = 0; i < nu; ++i) {
     const Function& f = *unit[i];
     fingerprints(f, fps[i]);
     cost.assign(f.nodes.size(), 0);
+    cand_of[i].assign(f.nodes.size(), nullptr);
     for (size_t k = 0; k < f.nodes.size(); ++k) {
       const Node& n = f.nodes[k];
       if (n.l < 0 || n.is_const) continue;
       cost[k] = own_cost(f, n) + cost[n.l] + cost[n.r];
       if (cost[k] == 0) continue;                        // sums of variables: a row would save nothing
-      auto it = cands.find(FpKey{fps[i][k].a, fps[i][k].b});
-      if (it == cands.end()) cands.emplace(FpKey{fps[i][k].a, fps[i][k].b}, Cand{(uint32_t)i, (int32_t)k, cost[k], 1, false, -1});
-      else ++it->second.refs;
+      auto ins = cands.emplace(FpKey{fps[i][k].a, fps[i][k].b}, Cand{(uint32_t)i, (int32_t)k, cost[k], 1, false, -1});
+      if (!ins.second) ++ins.first->second.refs;
+      cand_of[i][k] = &ins.first->second;
     }
   }
   // first selection: everything that occurs at least twice anywhere.  (A single function that was not cut keeps its
@@ -1732,8 +1741,8 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
         st.pop_back();
         const Node& n = f.nodes[k];
         if (n.l < 0 || n.is_const) continue;
-        auto it = cands.find(FpKey{fps[i][k].a, fps[i][k].b});
-        if (it != cands.end() && it->second.selected) { ++it->second.refs; continue; }
+        Cand* c = cand_of[i][k];
+        if (c && c->selected) { ++c->refs; continue; }
         st.push_back(n.l);
         st.push_back(n.r);
       }
@@ -1789,9 +1798,9 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
     copy_tree(f, f.root, dst, [&](int32_t k) -> int64_t {
       const Node& n = f.nodes[k];
       if (n.l < 0 || n.is_const) return -1;
-      auto it = cands.find(FpKey{fps[u][k].a, fps[u][k].b});
-      if (it == cands.end() || !it->second.selected) return -1;
-      const int32_t r = it->second.row;
+      const Cand* c = cand_of[u][k];
+      if (!c || !c->selected) return -1;
+      const int32_t r = c->row;
       if (!same_structure(f, fps[u], k, table[r], tfps[r], table[r].root)) return -1;
       return (int64_t)n_base + R1 + r;
     });
