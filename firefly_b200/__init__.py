@@ -233,6 +233,18 @@ class GpuParser:
             lib.ffgpu_tape_destroy(self.h)
             self.h = None
 
+    def __del__(self):
+        # A host-only handle (no context, no device memory) is released when its last reference goes: loops that
+        # compile thousands of collections for inspection need no close().  A handle with a context is released by
+        # close() only -- its device buffers must go before the context does, and the order in which the collector
+        # visits the two is not ours to choose.
+        try:
+            if getattr(self, "ctx", None) is None and getattr(self, "h", None) and lib is not None:
+                lib.ffgpu_tape_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
     # -- inspection ------------------------------------------------------------------
     def get_rp_function(self, i: int) -> list[str]:
         n = lib.ffgpu_rpn(self.h, i, None, 0)

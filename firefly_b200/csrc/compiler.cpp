@@ -1727,6 +1727,10 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
   // shared sub-expressions in temp slots, inside the one kernel: rows would be a second launch and more memory traffic.)
   const bool want_rows = nf >= 2 || !groups.empty();
   for (auto& kv : cands) kv.second.selected = want_rows && kv.second.refs >= 2;
+  // from here on candidates only ever drop out: a node whose candidate is not selected now needs no second look
+  for (size_t i = 0; i < nu; ++i)
+    for (Cand*& c : cand_of[i])
+      if (c && !c->selected) c = nullptr;
   // occurrences, top down: below a selected sub-tree nothing is counted (its inside is evaluated by the row's own
   // function).  Candidates that are left with fewer than two uses, or save less than two multiplications, are
   // dropped, which exposes what they contain -- repeat until nothing changes.

@@ -100,3 +100,9 @@ class OracleParser:
         if self.h:
             self.o.lib.ffo_free(self.h)
             self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
