@@ -28,6 +28,11 @@
 
 namespace {
 
+// The worker's caller slot (ffgpu_eval's thread_id): the last of the library's 32.  Pool threads are numbered in
+// order of first appearance from 0 (include/firefly_gpu/caller_slot.hpp), so a queue and a pool of up to 31 threads
+// in one process never wait for each other's slot.
+constexpr uint32_t QUEUE_SLOT = 31;
+
 struct Request {
   uint64_t first_index = 0;
   size_t n = 0;
@@ -121,14 +126,14 @@ struct ffgpu_queue {
           const uint64_t* a = r.data.data();
           const uint64_t* s = a + n_vars;
           std::memcpy(h_in, s + n_vars, n * sizeof(uint64_t));
-          ok = ffgpu_eval_line(tape, a, s, h_in, n, h_out, /*thread_id=*/7) == 0;
+          ok = ffgpu_eval_line(tape, a, s, h_in, n, h_out, QUEUE_SLOT) == 0;
         } else {
           // AoS -> SoA, what compute_probe<N> does for its FFIntVec (Reconstructor.hpp:3424-3434)
           size_t j = 0;
           for (const Request& r : batch)
             for (size_t q = 0; q < r.n; ++q, ++j)
               for (size_t v = 0; v < n_vars; ++v) h_in[v * n + j] = r.data[q * n_vars + v];
-          ok = ffgpu_eval(tape, h_in, n, h_out, /*thread_id=*/7) == 0;
+          ok = ffgpu_eval(tape, h_in, n, h_out, QUEUE_SLOT) == 0;
         }
         if (!ok) err = ffgpu_last_error();
       }
