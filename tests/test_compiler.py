@@ -364,6 +364,46 @@ def test_cpp_headers_compile():
                             "-I", gen_inc, "-I", ref_inc, "-I", inc, os.path.join(inc, "firefly_gpu", h)], check=True)
 
 
+def test_caller_slots_are_one_per_thread(tmp_path):
+    """include/firefly_gpu/caller_slot.hpp: every calling thread gets a number of its own, the same from whichever
+    template instantiation it asks first (the Reconstructor's pool threads call the black box with FFInt and with
+    FFIntVec<N>, Reconstructor.hpp:3330-3354) -- compiled and run, no GPU involved."""
+    import subprocess
+    src = tmp_path / "slots.cpp"
+    src.write_text(r"""
+#include <cstdio>
+#include <mutex>
+#include <set>
+#include <thread>
+#include <vector>
+#include "firefly_gpu/caller_slot.hpp"
+template <typename T> unsigned ask() { return firefly::gpu_caller_slot(); }      // one instantiation per bunch type
+int main() {
+  std::mutex m;
+  std::set<unsigned> seen;
+  bool stable = true;
+  std::vector<std::thread> pool;
+  for (int t = 0; t < 32; ++t)
+    pool.emplace_back([&, t] {
+      const unsigned a = (t & 1) ? ask<int>() : ask<double>();
+      const unsigned b = (t & 1) ? ask<double>() : ask<int>();
+      const unsigned c = ask<char>();
+      std::lock_guard<std::mutex> lk(m);
+      stable = stable && a == b && b == c;
+      seen.insert(a);
+    });
+  for (auto& th : pool) th.join();
+  const bool dense = seen.size() == 32 && *seen.rbegin() == 31;
+  std::printf("%zu distinct, stable %d, dense %d\n", seen.size(), (int)stable, (int)dense);
+  return stable && dense ? 0 : 1;
+}
+""")
+    exe = tmp_path / "slots"
+    subprocess.run(["g++", "-std=c++14", "-O1", "-pthread", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 # ---- functions of equal structure are evaluated once (sharing ACROSS functions, SURVEY 8 f4) -----------------------
 def test_structural_duplicates_are_evaluated_once(oracle):
     vars_ = ["x", "y", "z"]
