@@ -1459,7 +1459,6 @@ bool split_long_sums(const Function& f, std::vector<Function>& groups, Function&
     out.nodes.push_back(nd);
   }
   out.root = remap[f.root];
-  out.rpn = f.rpn;
   return true;
 }
 }  // namespace
@@ -1648,7 +1647,6 @@ bool hornerize(const Function& f, Function& out) {
     out.nodes.push_back(nd);
   }
   out.root = remap[f.root];
-  out.rpn = f.rpn;
   return changed;
 }
 }  // namespace
@@ -1676,7 +1674,6 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
       if (dup_of[i] >= 0) continue;
       if (hornerize(cut[i].nodes.empty() ? functions[i] : cut[i], h)) {
         cut[i] = std::move(h);
-        cut[i].rpn = functions[i].rpn;
         any_cut = true;
       }
     }
@@ -1816,8 +1813,7 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
   std::vector<Function> lowered_groups(R1);
   for (size_t u = 0; u < nu; ++u) {
     if (unit_fn[u] >= 0) {
-      lower(u, lowered_[unit_fn[u]]);
-      lowered_[unit_fn[u]].rpn = functions[unit_fn[u]].rpn;
+      lower(u, lowered_[unit_fn[u]]);       // (the RPN strings stay with functions[]: nothing reads them from a lowered copy)
     } else {
       lower(u, lowered_groups[(size_t)(-1 - unit_fn[u])]);
     }
