@@ -1695,15 +1695,39 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
     int32_t row;
   };
   std::vector<std::vector<Fp>> fps(nu);
-  std::unordered_map<FpKey, Cand, FpKeyHash> cands;
-  // the candidate of every node, looked up once (the map's elements never move): the passes below walk the trees
-  // again and again, and on a 10 000-function collection the lookups were half of the whole compilation
-  std::vector<std::vector<Cand*>> cand_of(nu);
+  // Candidates by fingerprint: an open-addressing table of indices into one array (reserved for the most there can
+  // be, so its elements never move).  The candidate of every node is looked up once: the passes below walk the trees
+  // again and again, and on a 10 000-function collection the lookups were half of the whole compilation.
+  std::vector<Cand> cands;
+  std::vector<FpKey> cand_key;
+  std::vector<uint32_t> cand_slot;             // 0 = empty, else index + 1
+  size_t cand_mask = 0;
   {
-    size_t total_nodes = 0;
-    for (size_t i = 0; i < nu; ++i) total_nodes += unit[i]->nodes.size();
-    cands.reserve(total_nodes / 2);
+    size_t inner_nodes = 0;
+    for (size_t i = 0; i < nu; ++i)
+      for (const Node& n : unit[i]->nodes) inner_nodes += n.l >= 0 && !n.is_const;
+    cands.reserve(inner_nodes);
+    cand_key.reserve(inner_nodes);
+    size_t cap = 16;
+    while (cap < 2 * inner_nodes) cap <<= 1;
+    cand_slot.assign(cap, 0);
+    cand_mask = cap - 1;
   }
+  auto cand_emplace = [&](const FpKey& key, const Cand& fresh) -> std::pair<Cand*, bool> {
+    size_t h = FpKeyHash{}(key) & cand_mask;
+    for (;;) {
+      const uint32_t s = cand_slot[h];
+      if (!s) {
+        cands.push_back(fresh);
+        cand_key.push_back(key);
+        cand_slot[h] = (uint32_t)cands.size();
+        return {&cands.back(), true};
+      }
+      if (cand_key[s - 1] == key) return {&cands[s - 1], false};
+      h = (h + 1) & cand_mask;
+    }
+  };
+  std::vector<std::vector<Cand*>> cand_of(nu);
   std::vector<uint32_t> cost;
   for (size_t i = 0; i < nu; ++i) {
     const Function& f = *unit[i];
@@ -1715,15 +1739,15 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
       if (n.l < 0 || n.is_const) continue;
       cost[k] = own_cost(f, n) + cost[n.l] + cost[n.r];
       if (cost[k] == 0) continue;                        // sums of variables: a row would save nothing
-      auto ins = cands.emplace(FpKey{fps[i][k].a, fps[i][k].b}, Cand{(uint32_t)i, (int32_t)k, cost[k], 1, false, -1});
-      if (!ins.second) ++ins.first->second.refs;
-      cand_of[i][k] = &ins.first->second;
+      const std::pair<Cand*, bool> ins = cand_emplace(FpKey{fps[i][k].a, fps[i][k].b}, Cand{(uint32_t)i, (int32_t)k, cost[k], 1, false, -1});
+      if (!ins.second) ++ins.first->refs;
+      cand_of[i][k] = ins.first;
     }
   }
   // first selection: everything that occurs at least twice anywhere.  (A single function that was not cut keeps its
   // shared sub-expressions in temp slots, inside the one kernel: rows would be a second launch and more memory traffic.)
   const bool want_rows = nf >= 2 || !groups.empty();
-  for (auto& kv : cands) kv.second.selected = want_rows && kv.second.refs >= 2;
+  for (Cand& c : cands) c.selected = want_rows && c.refs >= 2;
   // from here on candidates only ever drop out: a node whose candidate is not selected now needs no second look
   for (size_t i = 0; i < nu; ++i)
     for (Cand*& c : cand_of[i])
@@ -1732,7 +1756,7 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
   // function).  Candidates that are left with fewer than two uses, or save less than two multiplications, are
   // dropped, which exposes what they contain -- repeat until nothing changes.
   auto count_refs = [&]() {
-    for (auto& kv : cands) kv.second.refs = 0;
+    for (Cand& c : cands) c.refs = 0;
     std::vector<int32_t> st;
     for (size_t i = 0; i < nu; ++i) {
       const Function& f = *unit[i];
@@ -1752,15 +1776,14 @@ void Collection::build_table(const std::vector<int32_t>& dup_of) {
   for (int round = 0; round < 64; ++round) {
     count_refs();
     bool changed = false;
-    for (auto& kv : cands) {
-      Cand& c = kv.second;
+    for (Cand& c : cands) {
       if (c.selected && (c.refs < 2 || (uint64_t)(c.refs - 1) * c.cost < 2)) { c.selected = false; changed = true; }
     }
     if (!changed) break;
   }
   std::vector<Cand*> chosen;
-  for (auto& kv : cands)
-    if (kv.second.selected) chosen.push_back(&kv.second);
+  for (Cand& c : cands)
+    if (c.selected) chosen.push_back(&c);
   auto benefit = [](const Cand* c) { return (uint64_t)(c->refs - 1) * c->cost; };
   std::sort(chosen.begin(), chosen.end(), [&](const Cand* x, const Cand* y) {
     if (benefit(x) != benefit(y)) return benefit(x) > benefit(y);
