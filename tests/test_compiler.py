@@ -364,6 +364,30 @@ def test_cpp_headers_compile():
                             "-I", gen_inc, "-I", ref_inc, "-I", inc, os.path.join(inc, "firefly_gpu", h)], check=True)
 
 
+def test_host_only_handles_are_released_when_collected(oracle):
+    """Compile-and-drop loops (the campaigns under scripts/) must not grow: a host-only GpuParser and the oracle
+    binding's parsers free their native side when the last reference goes (a 40-minute campaign once grew to
+    13-16 GB per worker)."""
+    def rss_mb():
+        with open("/proc/self/statm") as f:
+            return int(f.read().split()[1]) * os.sysconf("SC_PAGE_SIZE") / 1e6
+    from firefly_b200 import workloads as W
+    funs, vars_ = W.ibp_like_collection(12, 4, seed=5)
+    p = ff.primes()[0]
+    pts = ff.synthetic_points(len(vars_), 2, p, seed=1)
+
+    def cycle(n):
+        for _ in range(n):
+            par = ff.GpuParser(None, funs, vars_)
+            par.set_prime(p)
+            par.tape()
+            oracle.parse(funs, vars_, p).eval(pts)
+    cycle(300)                      # allocator warm-up
+    before = rss_mb()
+    cycle(1500)
+    assert rss_mb() - before < 40, f"{rss_mb() - before:.0f} MB after 1500 compile-and-drop cycles"
+
+
 def test_caller_slots_are_one_per_thread(tmp_path):
     """include/firefly_gpu/caller_slot.hpp: every calling thread gets a number of its own, the same from whichever
     template instantiation it asks first (the Reconstructor's pool threads call the black box with FFInt and with
